@@ -1,0 +1,228 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY:
+importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class OrcMesh(C.Structure):
+    _fields_ = [("verts", C.c_void_p), ("indices", C.c_void_p), ("nverts", C.c_uint32), ("nindices", C.c_uint32)]
+
+
+class OrcTexture(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint32), ("_pad", C.c_uint32), ("data", C.c_void_p)]
+
+
+class OrcInstance(C.Structure):
+    _fields_ = [("transform", C.c_float * 16), ("mesh", C.c_uint32), ("material", C.c_uint32)]
+
+
+class OrcSceneDesc(C.Structure):
+    _fields_ = [("meshes", C.c_void_p), ("nmeshes", C.c_uint32), ("_p0", C.c_uint32),
+                ("materials", C.c_void_p), ("nmaterials", C.c_uint32), ("_p1", C.c_uint32),
+                ("textures", C.c_void_p), ("ntextures", C.c_uint32), ("_p2", C.c_uint32),
+                ("instances", C.c_void_p), ("ninstances", C.c_uint32), ("_p3", C.c_uint32),
+                ("env_rgba", C.c_void_p), ("env_alias", C.c_void_p), ("envW", C.c_uint32), ("envH", C.c_uint32),
+                ("lut_reflect", C.c_void_p), ("lut_refract_out", C.c_void_p), ("lut_refract_in", C.c_void_p)]
+
+
+class OrcConfig(C.Structure):
+    _fields_ = [("ViewInverse", C.c_float * 16), ("ProjectionInverse", C.c_float * 16),
+                ("SampleCount", C.c_uint32), ("MaxDepth", C.c_uint32),
+                ("MaxLuminance", C.c_float), ("FocusDistance", C.c_float), ("DepthOfFieldStrength", C.c_float),
+                ("SkyRotationAzimuth", C.c_float), ("SkyRotationAltitude", C.c_float), ("EnvironmentIntensity", C.c_float),
+                ("EmissiveMeshSamplingPDFBias", C.c_float), ("ScreenSplitCount", C.c_uint32),
+                ("EnableSkyMIS", C.c_uint32), ("EnableMeshMIS", C.c_uint32), ("ShowEnvMapDirectly", C.c_uint32),
+                ("UseOnlyGeometryNormals", C.c_uint32), ("UseEnergyCompensation", C.c_uint32), ("FurnaceTestMode", C.c_uint32)]
+
+
+class OrcCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("paths", "segments", "surface_hits", "misses", "shadow_rays", "medium_events")]
+
+
+class OrcPostConfig(C.Structure):
+    _fields_ = [("Exposure", C.c_float), ("Gamma", C.c_float), ("BloomThreshold", C.c_float), ("BloomStrength", C.c_float),
+                ("FalloffRange", C.c_float), ("MipCount", C.c_uint32)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("pt_oracle.c", "post_oracle.c", "io_oracle.c", "pt_oracle.h", "orc_math.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_pcg_hash.restype = C.c_uint32; L.orc_pcg_hash.argtypes = [C.c_uint32]
+        L.orc_rng_floats.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_dielectric_fresnel.restype = C.c_float; L.orc_dielectric_fresnel.argtypes = [C.c_float, C.c_float]
+        L.orc_aces_fitted.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_build_env_alias.restype = C.c_float; L.orc_build_env_alias.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_camera_from_view.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_default_config.argtypes = [C.POINTER(OrcConfig)]
+        L.orc_load_hdr.restype = C.c_void_p; L.orc_load_hdr.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.orc_free.argtypes = [C.c_void_p]
+        L.orc_scene_create.restype = C.c_void_p; L.orc_scene_create.argtypes = [C.POINTER(OrcSceneDesc)]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_scene_triangle_count.restype = C.c_uint32; L.orc_scene_triangle_count.argtypes = [C.c_void_p]
+        L.orc_scene_emissive_count.restype = C.c_uint32; L.orc_scene_emissive_count.argtypes = [C.c_void_p]
+        L.orc_scene_world_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_trace_closest.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_render.argtypes = [C.c_void_p, C.POINTER(OrcConfig), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                 C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.POINTER(OrcCounters)]
+        L.orc_sample_pixel.argtypes = [C.c_void_p, C.POINTER(OrcConfig), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_void_p, C.POINTER(C.c_uint32)]
+        L.orc_default_post_config.argtypes = [C.POINTER(OrcPostConfig)]
+        L.orc_bloom_mip_sizes.restype = C.c_uint32; L.orc_bloom_mip_sizes.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_post_process.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(OrcPostConfig), C.c_void_p, C.c_void_p, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pcg_hash(x):
+    return int(lib().orc_pcg_hash(C.c_uint32(x & 0xFFFFFFFF)))
+
+
+def rng_floats(seed, n):
+    out = np.empty(n, dtype=np.float32)
+    lib().orc_rng_floats(seed & 0xFFFFFFFF, n, _p(out))
+    return out
+
+
+def load_hdr(path):
+    w, h = C.c_uint32(0), C.c_uint32(0)
+    p = lib().orc_load_hdr(path.encode(), C.byref(w), C.byref(h))
+    if not p:
+        raise IOError("orc_load_hdr failed: " + path)
+    a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(h.value, w.value, 4)).copy()
+    lib().orc_free(p)
+    return a
+
+
+def build_env_alias(rgba):
+    """rgba: (H,W,4) float32, modified copy returned with alpha=pdf; alias: structured (Alias u4, Importance f4)."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32).copy()
+    h, w = rgba.shape[:2]
+    alias = np.zeros(h * w, dtype=np.dtype([("Alias", "<u4"), ("Importance", "<f4")]))
+    s = lib().orc_build_env_alias(_p(rgba), w, h, _p(alias))
+    return rgba, alias, float(s)
+
+
+def camera_from_view(view16, aspect):
+    view16 = np.ascontiguousarray(view16, dtype=np.float32)
+    vi = np.zeros(16, np.float32); pi = np.zeros(16, np.float32)
+    lib().orc_camera_from_view(_p(view16), C.c_float(float(aspect)), _p(vi), _p(pi))
+    return vi, pi
+
+
+def default_config(**kw):
+    c = OrcConfig()
+    lib().orc_default_config(C.byref(c))
+    for k, v in kw.items():
+        if k in ("ViewInverse", "ProjectionInverse"):
+            for i in range(16): getattr(c, k)[i] = float(v[i])
+        else:
+            setattr(c, k, v)
+    return c
+
+
+def default_post_config(**kw):
+    c = OrcPostConfig()
+    lib().orc_default_post_config(C.byref(c))
+    for k, v in kw.items(): setattr(c, k, v)
+    return c
+
+
+class Scene:
+    """Keeps every numpy buffer alive for the lifetime of the C scene."""
+
+    def __init__(self, sc, env_rgba, env_alias, luts):
+        L = lib()
+        self.keep = []
+        meshes = (OrcMesh * len(sc["meshes"]))()
+        for i, (v, idx) in enumerate(sc["meshes"]):
+            v = np.ascontiguousarray(v); idx = np.ascontiguousarray(idx, dtype=np.uint32)
+            self.keep += [v, idx]
+            meshes[i] = OrcMesh(v.ctypes.data, idx.ctypes.data, len(v), len(idx))
+        mats = np.ascontiguousarray(sc["materials"]); self.keep.append(mats)
+        texs = (OrcTexture * len(sc["textures"]))()
+        for i, t in enumerate(sc["textures"]):
+            t = np.ascontiguousarray(t, dtype=np.uint8); self.keep.append(t)
+            texs[i] = OrcTexture(t.shape[1], t.shape[0], t.shape[2], 0, t.ctypes.data)
+        insts = (OrcInstance * len(sc["instances"]))()
+        for i, (xf, m, mat) in enumerate(sc["instances"]):
+            insts[i].mesh = m; insts[i].material = mat
+            for k in range(16): insts[i].transform[k] = float(xf[k])
+        env_rgba = np.ascontiguousarray(env_rgba, dtype=np.float32); env_alias = np.ascontiguousarray(env_alias)
+        luts = [np.ascontiguousarray(l, dtype=np.float32) for l in luts]
+        self.keep += [meshes, texs, insts, env_rgba, env_alias] + luts
+        d = OrcSceneDesc()
+        d.meshes = C.addressof(meshes); d.nmeshes = len(sc["meshes"])
+        d.materials = mats.ctypes.data; d.nmaterials = len(mats)
+        d.textures = C.addressof(texs); d.ntextures = len(sc["textures"])
+        d.instances = C.addressof(insts); d.ninstances = len(sc["instances"])
+        d.env_rgba = env_rgba.ctypes.data; d.env_alias = env_alias.ctypes.data
+        d.envH, d.envW = env_rgba.shape[0], env_rgba.shape[1]
+        d.lut_reflect, d.lut_refract_out, d.lut_refract_in = [l.ctypes.data for l in luts]
+        self.desc = d
+        self.h = L.orc_scene_create(C.byref(d))
+        self.ntris = L.orc_scene_triangle_count(self.h)
+        self.n_emissive = L.orc_scene_emissive_count(self.h)
+
+    def __del__(self):
+        try:
+            if self.h: lib().orc_scene_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+    def world_triangles(self):
+        tri = np.zeros((self.ntris, 9), np.float32); inst = np.zeros(self.ntris, np.uint32); prim = np.zeros(self.ntris, np.uint32)
+        lib().orc_scene_world_triangles(self.h, _p(tri), _p(inst), _p(prim))
+        return tri, inst, prim
+
+    def trace_closest(self, org, dirs, tmin, tmax, use_bvh=True):
+        org = np.ascontiguousarray(org, np.float32); dirs = np.ascontiguousarray(dirs, np.float32)
+        n = len(org)
+        t = np.zeros(n, np.float32); prim = np.zeros(n, np.uint32); inst = np.zeros(n, np.uint32); uv = np.zeros((n, 2), np.float32)
+        lib().orc_trace_closest(self.h, n, _p(org), _p(dirs), C.c_float(tmin), C.c_float(tmax), int(use_bvh), _p(t), _p(prim), _p(inst), _p(uv))
+        return t, prim, inst, uv
+
+    def render(self, cfg, W, H, nframes, base_seed, frame0=0, image=None, rank=0, world=1, band_rows=1, nthreads=0):
+        if image is None: image = np.zeros((H, W, 4), np.float32)
+        cnt = OrcCounters()
+        lib().orc_render(self.h, C.byref(cfg), W, H, frame0, nframes, base_seed & 0xFFFFFFFF, rank, world, band_rows, _p(image), nthreads, C.byref(cnt))
+        return image, {n: getattr(cnt, n) for n, _ in OrcCounters._fields_}
+
+    def sample_pixel(self, cfg, W, H, x, y, seed):
+        out = np.zeros(3, np.float32); seg = C.c_uint32(0)
+        lib().orc_sample_pixel(self.h, C.byref(cfg), W, H, x, y, seed & 0xFFFFFFFF, _p(out), C.byref(seg))
+        return out, seg.value
+
+
+def bloom_mip_sizes(W, H):
+    wh = np.zeros(20, np.uint32)
+    n = lib().orc_bloom_mip_sizes(W, H, _p(wh))
+    return [(int(wh[2 * i]), int(wh[2 * i + 1])) for i in range(n)]
+
+
+def post_process(hdr, pcfg=None, want_bloom=False):
+    hdr = np.ascontiguousarray(hdr, np.float32)
+    H, W = hdr.shape[:2]
+    if pcfg is None: pcfg = default_post_config()
+    ldr = np.zeros((H, W, 4), np.uint8)
+    bloom = np.zeros((H, W, 4), np.float32) if want_bloom else None
+    lib().orc_post_process(_p(hdr), W, H, C.byref(pcfg), _p(ldr), _p(bloom) if want_bloom else None, 0)
+    return (ldr, bloom) if want_bloom else ldr

@@ -1,0 +1,1116 @@
+/*
+ * pt_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see pt_oracle.h for the pin status).
+ * Restates, function by function, the reference's Slang integrator.  Every function cites the
+ * reference file:line it follows (paths relative to /root/reference; SH = PathTracer/Shaders,
+ * PT = PathTracer).  Quirks Q1..Q16 of SURVEY.md Appendix B are kept verbatim.
+ */
+#include "pt_oracle.h"
+#include "orc_math.h"
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------------------------------------
+ * RNG: SH/Sampler.slang:4-9, 21-100
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { uint32_t seed; } Rng;
+
+uint32_t orc_pcg_hash(uint32_t seed) {
+    uint32_t state = seed * 747796405u + 2891336453u;
+    uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+    return (word >> 22u) ^ word;
+}
+static inline uint32_t rng_pcg(Rng *r) { r->seed = orc_pcg_hash(r->seed); return r->seed; }
+/* SH/Sampler.slang:38-43: float(hash) / float(UINT_MAX); float(UINT_MAX) rounds to 2^32 (Q12: result in [0,1]) */
+static inline float rng_f(Rng *r) { return (float)rng_pcg(r) / 4294967296.0f; }
+
+void orc_rng_floats(uint32_t seed, uint32_t n, float *out) {
+    Rng r = { seed };
+    for (uint32_t i = 0; i < n; i++) out[i] = rng_f(&r);
+}
+
+/* SH/Sampler.slang:103-112 */
+static inline void rng_circle(Rng *r, float *ox, float *oy) {
+    float u1 = rng_f(r), u2 = rng_f(r);
+    float theta = 2.0f * ORC_PI * u1;
+    float rad = sqrtf(u2);
+    *ox = rad * cosf(theta); *oy = rad * sinf(theta);
+}
+/* SH/Sampler.slang:115-133 */
+static inline v3 rng_sphere(Rng *r) {
+    float u1 = rng_f(r), u2 = rng_f(r);
+    float theta = 2.0f * ORC_PI * u1;
+    float z = 1.0f - 2.0f * u2;
+    float rad = sqrtf(1.0f - z * z);
+    return V3(rad * cosf(theta), rad * sinf(theta), z);
+}
+/* SH/Sampler.slang:143-166 (Heitz 2018 VNDF) */
+static inline v3 rng_ggx_vndf(Rng *r, v3 Ve, float Ax, float Ay) {
+    float u1 = rng_f(r), u2 = rng_f(r);
+    v3 Vh = v3normalize(V3(Ax * Ve.x, Ay * Ve.y, fabsf(Ve.z)));
+    float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+    v3 T1 = lensq > 0.0f ? v3scale(V3(-Vh.y, Vh.x, 0.0f), 1.0f / sqrtf(lensq)) : V3(1.0f, 0.0f, 0.0f);
+    v3 T2 = v3cross(Vh, T1);
+    float rad = sqrtf(u1);
+    float phi = 2.0f * ORC_PI * u2;
+    float t1 = rad * cosf(phi);
+    float t2 = rad * sinf(phi);
+    float s = 0.5f * (1.0f + Vh.z);
+    t2 = (1.0f - s) * sqrtf(1.0f - t1 * t1) + s * t2;
+    v3 Nh = v3add(v3add(v3scale(T1, t1), v3scale(T2, t2)), v3scale(Vh, sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2))));
+    return v3normalize(V3(Ax * Nh.x, Ay * Nh.y, fmaxf(0.0f, Nh.z)));
+}
+/* SH/Sampler.slang:169-193 */
+static inline v3 rng_henyey_greenstein(Rng *r, v3 incident, float G) {
+    float rx = rng_f(r), ry = rng_f(r);
+    float cosTheta;
+    if (fabsf(G) < 1e-5f) {
+        cosTheta = 2.0f * rx - 1.0f;
+    } else {
+        float sqrTerm = (1.0f - G * G) / (1.0f - G + 2.0f * G * rx);
+        cosTheta = (1.0f + G * G - sqrTerm * sqrTerm) / (2.0f * G);
+    }
+    float phi = 2.0f * ORC_PI * ry;
+    float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+    v3 nd = V3(sinTheta * cosf(phi), sinTheta * sinf(phi), cosTheta);
+    v3 up = fabsf(incident.y) < 0.9999999f ? V3(0, 1, 0) : V3(0, 0, 1);
+    v3 tangent = v3normalize(v3cross(up, incident));
+    v3 bitangent = v3cross(incident, tangent);
+    return v3normalize(v3add(v3add(v3scale(tangent, nd.x), v3scale(bitangent, nd.y)), v3scale(incident, nd.z)));
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Scene
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { uint32_t mesh, material, tri_count, instance; float transform[16]; } EmissiveEntry; /* PT/PathTracer.h:321-328 */
+typedef struct { float o2w[3][4]; float w2o[3][3]; uint32_t tri_base; } InstXf;
+typedef struct { v3 v0, v1, v2; uint32_t inst, prim; } WTri;
+typedef struct { float lo[3], hi[3]; uint32_t left, right, first, count; } BNode; /* count>0 -> leaf */
+
+struct OrcScene {
+    OrcSceneDesc d;
+    InstXf *xf;
+    EmissiveEntry *emissive; uint32_t n_emissive, n_emissive_tris;
+    WTri *tris; uint32_t ntris;
+    uint32_t *order;   /* BVH triangle order */
+    BNode *nodes; uint32_t nnodes;
+};
+
+static v3 xf_point(const float m[3][4], v3 p) {
+    return V3(m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3] * 1.0f,
+              m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3] * 1.0f,
+              m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3] * 1.0f);
+}
+/* mul(float4x4 M, float4(p,1)).xyz with column-major storage */
+static v3 mat4_point(const float t[16], v3 p) {
+    return V3(t[0] * p.x + t[4] * p.y + t[8] * p.z + t[12] * 1.0f,
+              t[1] * p.x + t[5] * p.y + t[9] * p.z + t[13] * 1.0f,
+              t[2] * p.x + t[6] * p.y + t[10] * p.z + t[14] * 1.0f);
+}
+static v3 mat4_dir(const float t[16], v3 p) { /* w = 0 */
+    return V3(t[0] * p.x + t[4] * p.y + t[8] * p.z + t[12] * 0.0f,
+              t[1] * p.x + t[5] * p.y + t[9] * p.z + t[13] * 0.0f,
+              t[2] * p.x + t[6] * p.y + t[10] * p.z + t[14] * 0.0f);
+}
+/* mul(n, WorldToObject()).xyz : row-vector times 3x4 -> (W2O^T n) */
+static v3 xf_normal(const float w[3][3], v3 n) {
+    return V3(n.x * w[0][0] + n.y * w[1][0] + n.z * w[2][0],
+              n.x * w[0][1] + n.y * w[1][1] + n.z * w[2][1],
+              n.x * w[0][2] + n.y * w[1][2] + n.z * w[2][2]);
+}
+
+/* --- BVH (oracle-private: top-down median split, padded boxes) --- */
+static void tri_bounds(const WTri *t, float lo[3], float hi[3]) {
+    const float *a = &t->v0.x, *b = &t->v1.x, *c = &t->v2.x;
+    for (int k = 0; k < 3; k++) { lo[k] = fminf(a[k], fminf(b[k], c[k])); hi[k] = fmaxf(a[k], fmaxf(b[k], c[k])); }
+}
+static uint32_t bvh_build(OrcScene *s, uint32_t first, uint32_t count) {
+    uint32_t id = s->nnodes++;
+    BNode *n = &s->nodes[id];
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    float clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (uint32_t i = first; i < first + count; i++) {
+        float a[3], b[3]; tri_bounds(&s->tris[s->order[i]], a, b);
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fminf(lo[k], a[k]); hi[k] = fmaxf(hi[k], b[k]);
+            float c = 0.5f * (a[k] + b[k]); clo[k] = fminf(clo[k], c); chi[k] = fmaxf(chi[k], c);
+        }
+    }
+    for (int k = 0; k < 3; k++) { /* conservative padding */
+        float pad = 1e-5f * fmaxf(fabsf(lo[k]), fabsf(hi[k])) + 1e-6f;
+        n->lo[k] = lo[k] - pad; n->hi[k] = hi[k] + pad;
+    }
+    n->first = first; n->count = 0; n->left = n->right = 0;
+    int axis = 0; float ext = chi[0] - clo[0];
+    for (int k = 1; k < 3; k++) if (chi[k] - clo[k] > ext) { ext = chi[k] - clo[k]; axis = k; }
+    if (count <= 4 || !(ext > 0.0f)) { n->count = count; return id; }
+    float split = 0.5f * (clo[axis] + chi[axis]);
+    uint32_t i = first, j = first + count;
+    while (i < j) {
+        float a[3], b[3]; tri_bounds(&s->tris[s->order[i]], a, b);
+        if (0.5f * (a[axis] + b[axis]) < split) i++;
+        else { j--; uint32_t tmp = s->order[i]; s->order[i] = s->order[j]; s->order[j] = tmp; }
+    }
+    uint32_t nl = i - first;
+    if (nl == 0 || nl == count) nl = count / 2;
+    uint32_t l = bvh_build(s, first, nl);
+    uint32_t r = bvh_build(s, first + nl, count - nl);
+    s->nodes[id].left = l; s->nodes[id].right = r;
+    return id;
+}
+
+/* Moeller-Trumbore, no culling.  Accept tmin < t < tmax.  Same formula as the product kernel. */
+static inline int tri_hit(const WTri *tr, v3 o, v3 d, float tmin, float tmax, float *t_out, float *u_out, float *v_out) {
+    v3 e1 = v3sub(tr->v1, tr->v0), e2 = v3sub(tr->v2, tr->v0);
+    v3 p = v3cross(d, e2);
+    float det = v3dot(e1, p);
+    if (det == 0.0f) return 0;
+    float inv = 1.0f / det;
+    v3 tv = v3sub(o, tr->v0);
+    float u = v3dot(tv, p) * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return 0;
+    v3 q = v3cross(tv, e1);
+    float v = v3dot(d, q) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return 0;
+    float t = v3dot(e2, q) * inv;
+    if (!(t > tmin && t < tmax)) return 0;
+    *t_out = t; *u_out = u; *v_out = v;
+    return 1;
+}
+
+typedef struct { int hit; float t, u, v; uint32_t tri; } Hit;
+
+static inline void hit_consider(const OrcScene *s, uint32_t ti, v3 o, v3 d, float tmin, float tmax, Hit *h) {
+    float t, u, v;
+    if (tri_hit(&s->tris[ti], o, d, tmin, tmax, &t, &u, &v)) {
+        if (!h->hit || t < h->t || (t == h->t && ti < h->tri)) { h->hit = 1; h->t = t; h->u = u; h->v = v; h->tri = ti; }
+    }
+}
+static Hit trace_brute(const OrcScene *s, v3 o, v3 d, float tmin, float tmax) {
+    Hit h; h.hit = 0; h.t = 0; h.u = h.v = 0; h.tri = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < s->ntris; i++) hit_consider(s, i, o, d, tmin, tmax, &h);
+    return h;
+}
+static Hit trace_bvh(const OrcScene *s, v3 o, v3 d, float tmin, float tmax) {
+    Hit h; h.hit = 0; h.t = 0; h.u = h.v = 0; h.tri = 0xFFFFFFFFu;
+    if (s->ntris == 0) return h;
+    float inv[3] = { 1.0f / d.x, 1.0f / d.y, 1.0f / d.z };
+    const float *oo = &o.x;
+    uint32_t stack[128]; int sp = 0; stack[sp++] = 0;
+    while (sp) {
+        const BNode *n = &s->nodes[stack[--sp]];
+        float t0 = tmin, t1 = h.hit ? h.t : tmax;
+        for (int k = 0; k < 3; k++) {
+            float a = (n->lo[k] - oo[k]) * inv[k], b = (n->hi[k] - oo[k]) * inv[k];
+            t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));   /* fminf/fmaxf ignore NaN */
+        }
+        if (t0 > t1 * 1.0000004f + 1e-30f) continue;
+        if (n->count) { for (uint32_t i = 0; i < n->count; i++) hit_consider(s, s->order[n->first + i], o, d, tmin, tmax, &h); }
+        else { if (sp < 126) { stack[sp++] = n->left; stack[sp++] = n->right; } }
+    }
+    return h;
+}
+
+OrcScene *orc_scene_create(const OrcSceneDesc *desc) {
+    OrcScene *s = (OrcScene *)calloc(1, sizeof(OrcScene));
+    s->d = *desc;
+    uint32_t ni = desc->ninstances;
+    s->xf = (InstXf *)calloc(ni ? ni : 1, sizeof(InstXf));
+    s->emissive = (EmissiveEntry *)calloc(ni ? ni : 1, sizeof(EmissiveEntry));
+    uint32_t ntris = 0;
+    for (uint32_t i = 0; i < ni; i++) {
+        const OrcInstance *in = &desc->instances[i];
+        InstXf *x = &s->xf[i];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) x->o2w[r][c] = in->transform[c * 4 + r];
+        /* inverse of the 3x3 in double, rounded once (driver supplies WorldToObject; SH/Surface.slang:49,60) */
+        double m[3][3]; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) m[r][c] = x->o2w[r][c];
+        double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) + m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+        double id = 1.0 / det;
+        x->w2o[0][0] = (float)((m[1][1] * m[2][2] - m[1][2] * m[2][1]) * id);
+        x->w2o[0][1] = (float)((m[0][2] * m[2][1] - m[0][1] * m[2][2]) * id);
+        x->w2o[0][2] = (float)((m[0][1] * m[1][2] - m[0][2] * m[1][1]) * id);
+        x->w2o[1][0] = (float)((m[1][2] * m[2][0] - m[1][0] * m[2][2]) * id);
+        x->w2o[1][1] = (float)((m[0][0] * m[2][2] - m[0][2] * m[2][0]) * id);
+        x->w2o[1][2] = (float)((m[0][2] * m[1][0] - m[0][0] * m[1][2]) * id);
+        x->w2o[2][0] = (float)((m[1][0] * m[2][1] - m[1][1] * m[2][0]) * id);
+        x->w2o[2][1] = (float)((m[0][1] * m[2][0] - m[0][0] * m[2][1]) * id);
+        x->w2o[2][2] = (float)((m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id);
+        x->tri_base = ntris;
+        uint32_t tc = desc->meshes[in->mesh].nindices / 3;
+        ntris += tc;
+        /* emissive list: PT/PathTracer.cpp:458-469 (constant EmissiveColor != 0 only, Q16) */
+        const OrcMaterial *mat = &desc->materials[in->material];
+        if (mat->EmissiveColor[0] != 0.0f || mat->EmissiveColor[1] != 0.0f || mat->EmissiveColor[2] != 0.0f) {
+            EmissiveEntry *e = &s->emissive[s->n_emissive++];
+            e->mesh = in->mesh; e->material = in->material; e->tri_count = tc; e->instance = i;
+            memcpy(e->transform, in->transform, sizeof(e->transform));
+            s->n_emissive_tris += tc;
+        }
+    }
+    s->ntris = ntris;
+    s->tris = (WTri *)calloc(ntris ? ntris : 1, sizeof(WTri));
+    s->order = (uint32_t *)calloc(ntris ? ntris : 1, sizeof(uint32_t));
+    for (uint32_t i = 0; i < ni; i++) {
+        const OrcInstance *in = &desc->instances[i];
+        const OrcMesh *m = &desc->meshes[in->mesh];
+        uint32_t tc = m->nindices / 3;
+        for (uint32_t p = 0; p < tc; p++) {
+            WTri *t = &s->tris[s->xf[i].tri_base + p];
+            const OrcVertex *a = &m->verts[m->indices[p * 3 + 0]], *b = &m->verts[m->indices[p * 3 + 1]], *c = &m->verts[m->indices[p * 3 + 2]];
+            t->v0 = xf_point(s->xf[i].o2w, V3(a->pos[0], a->pos[1], a->pos[2]));
+            t->v1 = xf_point(s->xf[i].o2w, V3(b->pos[0], b->pos[1], b->pos[2]));
+            t->v2 = xf_point(s->xf[i].o2w, V3(c->pos[0], c->pos[1], c->pos[2]));
+            t->inst = i; t->prim = p;
+        }
+    }
+    for (uint32_t i = 0; i < ntris; i++) s->order[i] = i;
+    s->nodes = (BNode *)calloc(2 * (size_t)(ntris ? ntris : 1) + 2, sizeof(BNode));
+    s->nnodes = 0;
+    if (ntris) bvh_build(s, 0, ntris);
+    return s;
+}
+void orc_scene_destroy(OrcScene *s) {
+    if (!s) return;
+    free(s->xf); free(s->emissive); free(s->tris); free(s->order); free(s->nodes); free(s);
+}
+uint32_t orc_scene_triangle_count(const OrcScene *s) { return s->ntris; }
+uint32_t orc_scene_emissive_count(const OrcScene *s) { return s->n_emissive; }
+void orc_scene_world_triangles(const OrcScene *s, float *out9, uint32_t *inst_out, uint32_t *prim_out) {
+    for (uint32_t i = 0; i < s->ntris; i++) {
+        memcpy(out9 + 9 * (size_t)i, &s->tris[i].v0, 9 * sizeof(float));
+        if (inst_out) inst_out[i] = s->tris[i].inst;
+        if (prim_out) prim_out[i] = s->tris[i].prim;
+    }
+}
+void orc_trace_closest(const OrcScene *s, uint32_t n, const float *org3, const float *dir3, float tmin, float tmax,
+                       int use_bvh, float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out2) {
+    for (uint32_t i = 0; i < n; i++) {
+        v3 o = V3(org3[3 * i], org3[3 * i + 1], org3[3 * i + 2]), d = V3(dir3[3 * i], dir3[3 * i + 1], dir3[3 * i + 2]);
+        Hit h = use_bvh ? trace_bvh(s, o, d, tmin, tmax) : trace_brute(s, o, d, tmin, tmax);
+        t_out[i] = h.hit ? h.t : -1.0f;
+        prim_out[i] = h.hit ? s->tris[h.tri].prim : 0xFFFFFFFFu;
+        inst_out[i] = h.hit ? s->tris[h.tri].inst : 0xFFFFFFFFu;
+        if (uv_out2) { uv_out2[2 * i] = h.hit ? h.u : 0.0f; uv_out2[2 * i + 1] = h.hit ? h.v : 0.0f; }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Texture units in software: bilinear, texel centres at (i+0.5)/N, no mips.
+ * Filtering form: lerp(lerp(t00,t10,a), lerp(t01,t11,a), b) with lerp(p,q,w) = p + w*(q-p).
+ * ---------------------------------------------------------------------------------------------- */
+static inline float tex_mix(float p, float q, float w) { return p + w * (q - p); }
+static inline int wrap_repeat(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+static inline int clamp_i(int i, int lo, int hi) { return i < lo ? lo : (i > hi ? hi : i); }
+
+/* RGBA8/R8 UNORM texture, REPEAT (PT/PathTracer.cpp:84-91).  R8 returns (r,0,0,1). */
+static v4 tex_sample_u8(const OrcTexture *t, float u, float v) {
+    int W = (int)t->width, H = (int)t->height, C = (int)t->channels;
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float ax = x - fx, ay = y - fy;
+    int x0 = wrap_repeat((int)fx, W), x1 = wrap_repeat((int)fx + 1, W);
+    int y0 = wrap_repeat((int)fy, H), y1 = wrap_repeat((int)fy + 1, H);
+    float out[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
+    for (int c = 0; c < C; c++) {
+        float t00 = (float)t->data[((size_t)y0 * W + x0) * C + c] / 255.0f;
+        float t10 = (float)t->data[((size_t)y0 * W + x1) * C + c] / 255.0f;
+        float t01 = (float)t->data[((size_t)y1 * W + x0) * C + c] / 255.0f;
+        float t11 = (float)t->data[((size_t)y1 * W + x1) * C + c] / 255.0f;
+        out[c] = tex_mix(tex_mix(t00, t10, ax), tex_mix(t01, t11, ax), ay);
+    }
+    v4 r = { out[0], out[1], out[2], out[3] };
+    return r;
+}
+/* RGBA32F env map, REPEAT */
+static v4 env_sample(const OrcScene *s, float u, float v) {
+    int W = (int)s->d.envW, H = (int)s->d.envH;
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float ax = x - fx, ay = y - fy;
+    int x0 = wrap_repeat((int)fx, W), x1 = wrap_repeat((int)fx + 1, W);
+    int y0 = wrap_repeat((int)fy, H), y1 = wrap_repeat((int)fy + 1, H);
+    const float *p00 = s->d.env_rgba + ((size_t)y0 * W + x0) * 4, *p10 = s->d.env_rgba + ((size_t)y0 * W + x1) * 4;
+    const float *p01 = s->d.env_rgba + ((size_t)y1 * W + x0) * 4, *p11 = s->d.env_rgba + ((size_t)y1 * W + x1) * 4;
+    float o[4];
+    for (int c = 0; c < 4; c++) o[c] = tex_mix(tex_mix(p00[c], p10[c], ax), tex_mix(p01[c], p11[c], ax), ay);
+    v4 r = { o[0], o[1], o[2], o[3] };
+    return r;
+}
+/* R32F 2D-array LUT, CLAMP_TO_EDGE linear in (x,y), nearest (round-half-even) layer (PT/PathTracer.cpp:93-94,871-937) */
+static float lut_sample(const float *lut, int W, int H, int L, float u, float v, float layer) {
+    int li = clamp_i((int)nearbyintf(layer), 0, L - 1);
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float ax = x - fx, ay = y - fy;
+    int x0 = clamp_i((int)fx, 0, W - 1), x1 = clamp_i((int)fx + 1, 0, W - 1);
+    int y0 = clamp_i((int)fy, 0, H - 1), y1 = clamp_i((int)fy + 1, 0, H - 1);
+    const float *p = lut + (size_t)li * W * H;
+    return tex_mix(tex_mix(p[(size_t)y0 * W + x0], p[(size_t)y0 * W + x1], ax),
+                   tex_mix(p[(size_t)y1 * W + x0], p[(size_t)y1 * W + x1], ax), ay);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Payload: SH/RTCommon.slang:5-35
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    v3 Origin, Direction, BxDF; float PDF; v3 Emitted;
+    uint32_t Depth; Rng Sampler;
+    int InMedium; float MediumDensity, MediumAnisotropy; v3 MediumColor, MediumEmissiveColor;
+} Payload;
+
+static inline float power_heuristic(float a, float b) { return (a * a) / ((a * a) + (b * b)); } /* SH/RTCommon.slang:124-127 */
+
+/* SH/RTCommon.slang:129-136 */
+static inline void direction_to_uv(v3 d, float *u, float *v) {
+    float gamma = asinf(d.y);
+    float theta = atan2f(d.x, -d.z);
+    *u = theta * ORC_1_OVER_PI * 0.5f + 0.5f;
+    *v = gamma * ORC_1_OVER_PI + 0.5f;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Surface: SH/Surface.slang:6-159
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    v3 WorldPos; float u, v;
+    v3 Normal, Tangent, Bitangent, GeometryNormal;
+    v3 P1, P2, P3; /* object-space positions */
+    int HitFromInside;
+} Surface;
+
+static inline v3 surf_tangent_to_world(const Surface *s, v3 a) {
+    return v3normalize(v3add(v3add(v3scale(s->Tangent, a.x), v3scale(s->Bitangent, a.y)), v3scale(s->Normal, a.z)));
+}
+static inline v3 surf_world_to_tangent(const Surface *s, v3 a) {
+    return v3normalize(V3(v3dot(a, s->Tangent), v3dot(a, s->Bitangent), v3dot(a, s->Normal)));
+}
+
+static void surface_init(Surface *sf, const OrcScene *sc, const OrcConfig *cfg, uint32_t inst, uint32_t prim,
+                         float bu, float bv, v3 rayDir, const OrcTexture *normalTex) {
+    const OrcInstance *in = &sc->d.instances[inst];
+    const OrcMesh *m = &sc->d.meshes[in->mesh];
+    const InstXf *x = &sc->xf[inst];
+    float b0 = 1.0f - bu - bv, b1 = bu, b2 = bv;                         /* SH/ClosestHit.slang:45 */
+    const OrcVertex *A = &m->verts[m->indices[prim * 3 + 0]], *B = &m->verts[m->indices[prim * 3 + 1]], *C = &m->verts[m->indices[prim * 3 + 2]];
+    v3 p1 = V3(A->pos[0], A->pos[1], A->pos[2]), p2 = V3(B->pos[0], B->pos[1], B->pos[2]), p3 = V3(C->pos[0], C->pos[1], C->pos[2]);
+    sf->P1 = p1; sf->P2 = p2; sf->P3 = p3;
+    v3 lp = v3add(v3add(v3scale(p1, b0), v3scale(p2, b1)), v3scale(p3, b2));  /* :43 */
+    sf->WorldPos = xf_point(x->o2w, lp);                                       /* :44 */
+    sf->u = A->uv[0] * b0 + B->uv[0] * b1 + C->uv[0] * b2;                    /* :46 */
+    sf->v = A->uv[1] * b0 + B->uv[1] * b1 + C->uv[1] * b2;
+    v3 gn = v3normalize(v3cross(v3sub(p2, p1), v3sub(p3, p1)));               /* :48 */
+    gn = v3normalize(xf_normal(x->w2o, gn));                                   /* :49 */
+    v3 n;
+    if (cfg->UseOnlyGeometryNormals) {
+        n = gn;                                                                /* :53 */
+    } else {
+        v3 n1 = V3(A->nrm[0], A->nrm[1], A->nrm[2]), n2 = V3(B->nrm[0], B->nrm[1], B->nrm[2]), n3 = V3(C->nrm[0], C->nrm[1], C->nrm[2]);
+        n = v3normalize(v3add(v3add(v3scale(n1, b0), v3scale(n2, b1)), v3scale(n3, b2)));   /* :59 */
+        n = v3normalize(xf_normal(x->w2o, n));                                 /* :60 */
+    }
+    v3 view = v3neg(rayDir);                                                   /* :64 */
+    if (v3dot(gn, view) < 0.0f) { n = v3neg(n); gn = v3neg(gn); sf->HitFromInside = 1; } else sf->HitFromInside = 0; /* :66-76 */
+    v3 up = fabsf(n.z) < 0.9999999f ? V3(0, 0, 1) : V3(1, 0, 0);             /* :78 */
+    sf->GeometryNormal = gn;
+    sf->Normal = n;
+    sf->Tangent = v3normalize(v3cross(up, n));                                 /* :82 */
+    sf->Bitangent = v3normalize(v3cross(n, sf->Tangent));                      /* :83 */
+    if (!cfg->UseOnlyGeometryNormals) {                                        /* :85-90 (Q10: default map applied too) */
+        v4 t = tex_sample_u8(normalTex, sf->u, sf->v);
+        v3 nm = V3(t.x * 2.0f - 1.0f, t.y * 2.0f - 1.0f, t.z * 2.0f - 1.0f);
+        sf->Normal = surf_tangent_to_world(sf, nm);
+    }
+    if (v3dot(sf->Normal, view) < 0.0f) {                                      /* :92-100 */
+        float eps = 0.01f;
+        sf->Normal = v3normalize(v3sub(sf->Normal, v3scale(view, v3dot(sf->Normal, view) - eps)));
+    }
+    v3 perfect = v3normalize(v3reflect(v3neg(view), sf->Normal));             /* :102 */
+    if (v3dot(perfect, gn) < 0.0f) {                                           /* :103-112 */
+        float eps = 0.1f;
+        float dp = v3dot(sf->Normal, gn);
+        sf->Normal = v3normalize(v3add(sf->Normal, v3scale(gn, eps + dp)));
+    }
+    sf->Tangent = v3normalize(v3cross(sf->Normal, up));                        /* :115 */
+    sf->Bitangent = v3normalize(v3cross(sf->Normal, sf->Tangent));             /* :116 */
+}
+/* SH/Surface.slang:140-147 */
+static void surface_rotate_tangents(Surface *sf, float deg) {
+    float rot = deg * (ORC_PI / 180.0f);
+    float c = cosf(rot), s = sinf(rot);
+    v3 T = sf->Tangent, N = sf->Normal;
+    v3 r = v3add(v3add(v3scale(T, c), v3scale(v3cross(N, T), s)), v3scale(v3scale(N, v3dot(N, T)), 1.0f - c));
+    sf->Tangent = r;
+    sf->Bitangent = v3cross(r, N);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Material: SH/Material.slang
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    v3 BaseColor, EmissiveColor, SpecularColor, MediumColor, MediumEmissiveColor;
+    float Metallic, Roughness, IOR, Transmission, Anisotropy, AnisotropyRotation, MediumDensity, MediumAnisotropy;
+    float Eta, Ax, Ay;
+} Mat;
+typedef struct { v3 BxDF; float PDF; } Eval;
+typedef struct { v3 L; v3 BxDF; float PDF; } BSample;
+
+/* SH/Material.slang:39-87 */
+static void material_init(Mat *m, const OrcScene *sc, const OrcConfig *cfg, const OrcMaterial *src, const Surface *sf) {
+    m->BaseColor = V3(src->BaseColor[0], src->BaseColor[1], src->BaseColor[2]);
+    m->EmissiveColor = V3(src->EmissiveColor[0], src->EmissiveColor[1], src->EmissiveColor[2]);
+    m->SpecularColor = V3(src->SpecularColor[0], src->SpecularColor[1], src->SpecularColor[2]);
+    m->MediumColor = V3(src->MediumColor[0], src->MediumColor[1], src->MediumColor[2]);
+    m->MediumEmissiveColor = V3(src->MediumEmissiveColor[0], src->MediumEmissiveColor[1], src->MediumEmissiveColor[2]);
+    m->Metallic = src->Metallic; m->Roughness = src->Roughness; m->IOR = src->IOR; m->Transmission = src->Transmission;
+    m->Anisotropy = src->Anisotropy; m->AnisotropyRotation = src->AnisotropyRotation;
+    m->MediumDensity = src->MediumDensity; m->MediumAnisotropy = src->MediumAnisotropy;
+    v4 tb = tex_sample_u8(&sc->d.textures[src->BaseColorTextureIndex], sf->u, sf->v);
+    m->IOR = fmaxf(m->IOR, 1.000001f);
+    m->BaseColor = v3mul(m->BaseColor, V3(powf(tb.x, 2.2f), powf(tb.y, 2.2f), powf(tb.z, 2.2f)));
+    float tr = tex_sample_u8(&sc->d.textures[src->RoughnessTextureIndex], sf->u, sf->v).x;   /* Q8/Q9 */
+    m->Roughness *= tr;
+    m->Metallic *= tex_sample_u8(&sc->d.textures[src->MetallicTextureIndex], sf->u, sf->v).x;
+    v4 te = tex_sample_u8(&sc->d.textures[src->EmissiveTextureIndex], sf->u, sf->v);
+    m->EmissiveColor = v3mul(m->EmissiveColor, V3(te.x, te.y, te.z));
+    float aspect = sqrtf(1.0f - sqrtf(m->Anisotropy) * 0.9f);
+    m->Ax = fmaxf(0.00001f, m->Roughness / aspect);
+    m->Ay = fmaxf(0.00001f, m->Roughness * aspect);
+    m->Eta = sf->HitFromInside ? m->IOR : 1.0f / m->IOR;
+    if (cfg->FurnaceTestMode) {                                                /* :78-86 */
+        m->BaseColor = v3s(1.0f); m->EmissiveColor = v3s(0.0f); m->SpecularColor = v3s(1.0f);
+        m->MediumColor = v3s(1.0f); m->MediumEmissiveColor = v3s(0.0f);
+    }
+}
+/* :427-432 */
+static inline float schlick_fresnel(float VdotH) { float m = orc_clamp(1.0f - VdotH, 0.0f, 1.0f); float m2 = m * m; return m2 * m2 * m; }
+/* :434-449 */
+float orc_dielectric_fresnel(float cosI, float eta) {
+    float sinT2 = eta * eta * (1.0f - cosI * cosI);
+    if (sinT2 > 1.0f) return 1.0f;
+    float cosT = sqrtf(fmaxf(1.0f - sinT2, 0.0f));
+    float rs = (eta * cosT - cosI) / (eta * cosT + cosI);
+    float rp = (eta * cosI - cosT) / (eta * cosI + cosT);
+    return 0.5f * (rs * rs + rp * rp);
+}
+/* :394-404 */
+static inline float ggx_d(const Mat *m, v3 H) {
+    float Hx2 = H.x * H.x, Hy2 = H.y * H.y, Hz2 = H.z * H.z;
+    float ax2 = m->Ax * m->Ax, ay2 = m->Ay * m->Ay;
+    float e = Hx2 / ax2 + Hy2 / ay2 + Hz2;
+    return 1.0f / (ORC_PI * m->Ax * m->Ay * (e * e));
+}
+/* :406-423 */
+static inline float ggx_lambda(const Mat *m, v3 V) {
+    float Vx2 = V.x * V.x, Vy2 = V.y * V.y, Vz2 = fabsf(V.z) * fabsf(V.z);
+    float ax2 = m->Ax * m->Ax, ay2 = m->Ay * m->Ay;
+    float nom = -1.0f + sqrtf(1.0f + (ax2 * Vx2 + ay2 * Vy2) / Vz2);
+    return nom / 2.0f;
+}
+static inline float ggx_g1(const Mat *m, v3 V) { return 1.0f / (1.0f + ggx_lambda(m, V)); }
+/* :331-351 */
+static Eval eval_reflection(const Mat *m, v3 V, v3 L, v3 F) {
+    Eval e = { V3(0, 0, 0), 0.0f };
+    if (L.z <= 1e-5f) return e;
+    v3 H = v3normalize(v3add(V, L));
+    float VdotH = v3dot(V, H);
+    float D = ggx_d(m, H);
+    float GV = ggx_g1(m, V), GL = ggx_g1(m, L);
+    e.PDF = (GV * fmaxf(VdotH, 0.0f) * D / V.z) / (4.0f * VdotH);
+    /* D * F * GV * GL / (4 V.z), left to right */
+    e.BxDF = v3divs(v3scale(v3scale(v3scale(F, D), GV), GL), 4.0f * V.z);
+    return e;
+}
+/* :359-387 */
+static Eval eval_refraction(const Mat *m, v3 V, v3 L, v3 F) {
+    Eval e = { V3(0, 0, 0), 0.0f };
+    if (L.z >= 1e-5f) return e;
+    v3 H = v3normalize(v3add(v3scale(V, m->Eta), L));
+    if (H.z < 0.0f) H = v3neg(H);
+    float VdotH = v3dot(V, H), LdotH = v3dot(L, H);
+    float D = ggx_d(m, H);
+    float GV = ggx_g1(m, V), GL = ggx_g1(m, L);
+    float G = GV * GL;
+    float den = LdotH + m->Eta * VdotH;
+    float den2 = den * den;
+    float eta2 = m->Eta * m->Eta;
+    float jac = (eta2 * fabsf(LdotH)) / den2;
+    e.PDF = (GV * fabsf(VdotH) * D / V.z) * jac;
+    /* (F * D * G * eta2 / den2) * (|VdotH| * |LdotH| / |V.z|) */
+    float k = fabsf(VdotH) * fabsf(LdotH) / fabsf(V.z);
+    e.BxDF = v3scale(v3divs(v3scale(v3scale(v3scale(F, D), G), eta2), den2), k);
+    return e;
+}
+/* :281-289 */
+static Eval eval_diffuse(const Mat *m, v3 V, v3 L) {
+    (void)V;
+    Eval e;
+    e.PDF = L.z * ORC_1_OVER_PI;
+    e.BxDF = v3scale(v3scale(m->BaseColor, ORC_1_OVER_PI), L.z);
+    e.PDF *= (L.z > 0.0f) ? 1.0f : 0.0f;
+    return e;
+}
+/* :291-308 */
+static Eval eval_metallic(const Mat *m, const OrcScene *sc, const OrcConfig *cfg, v3 V, v3 L) {
+    v3 H = v3normalize(v3add(V, L));
+    v3 F = v3lerp(m->BaseColor, m->SpecularColor, schlick_fresnel(v3dot(V, H)));
+    Eval e = eval_reflection(m, V, L, F);
+    if (cfg->UseEnergyCompensation) {
+        float layer = m->Anisotropy * 32.0f;
+        float ec = lut_sample(sc->d.lut_reflect, 64, 64, 32, V.z, m->Roughness, layer);
+        ec = (1.0f - ec) / ec;
+        v3 k = v3add(v3s(1.0f), v3mul(m->BaseColor, v3s(ec)));
+        e.BxDF = v3mul(k, e.BxDF);
+    }
+    return e;
+}
+/* :310-323 */
+static Eval eval_dielectric_reflection(const Mat *m, const OrcScene *sc, const OrcConfig *cfg, v3 V, v3 L) {
+    Eval e = eval_reflection(m, V, L, m->SpecularColor);
+    if (cfg->UseEnergyCompensation) {
+        float layer = m->Anisotropy * 32.0f;
+        float ec = lut_sample(sc->d.lut_reflect, 64, 64, 32, V.z, m->Roughness, layer);
+        e.BxDF = v3divs(e.BxDF, ec);
+    }
+    return e;
+}
+/* :167-279 */
+static Eval eval_bsdf(const Mat *m, const OrcScene *sc, const OrcConfig *cfg, v3 V, v3 L) {
+    float pm = m->Metallic;
+    float pd = (1.0f - m->Metallic) * (1.0f - m->Transmission);
+    float pg = (1.0f - m->Metallic) * m->Transmission;
+    float sum = pm + pd + pg;
+    pm /= sum; pd /= sum; pg /= sum;
+    int refracted = L.z < 0.0f;
+    v3 H; int validRefraction = 0;
+    if (refracted) {
+        H = v3normalize(v3add(v3scale(V, m->Eta), L));
+        if (H.z < 0.0f) H = v3neg(H);
+        float VdotH = v3dot(V, H), LdotH = v3dot(L, H);
+        validRefraction = (VdotH > 0.0f && LdotH < 0.0f) || (VdotH < 0.0f && LdotH > 0.0f);
+    } else {
+        H = v3normalize(v3add(V, L));
+    }
+    float F = orc_dielectric_fresnel(fabsf(v3dot(V, H)), m->Eta);
+    Eval out = { V3(0, 0, 0), 0.0f };
+    float glassEC = 0.0f;
+    if (cfg->UseEnergyCompensation) {
+        int inside = m->Eta > 1.0f;
+        float layer = (orc_clamp(m->IOR, 1.0001f, 2.0f) - 1.0f) * 32.0f;
+        glassEC = lut_sample(inside ? sc->d.lut_refract_in : sc->d.lut_refract_out, 128, 128, 32, sqrtf(V.z), m->Roughness, layer);
+    }
+    if (!refracted) {
+        Eval e = eval_metallic(m, sc, cfg, V, L);
+        out.BxDF = v3add(out.BxDF, v3scale(e.BxDF, pm)); out.PDF += e.PDF * pm;
+    }
+    if (!refracted) {
+        Eval e = eval_diffuse(m, V, L);
+        out.BxDF = v3add(out.BxDF, v3scale(v3scale(e.BxDF, pd), 1.0f - F)); out.PDF += e.PDF * pd * (1.0f - F);
+    }
+    if (!refracted) {
+        Eval e = eval_dielectric_reflection(m, sc, cfg, V, L);
+        out.BxDF = v3add(out.BxDF, v3scale(v3scale(e.BxDF, pd), F)); out.PDF += e.PDF * pd * F;
+    }
+    if (!refracted) {
+        Eval e = eval_reflection(m, V, L, m->SpecularColor);
+        if (cfg->UseEnergyCompensation && glassEC > 0.01f) e.BxDF = v3divs(e.BxDF, glassEC);
+        out.BxDF = v3add(out.BxDF, v3scale(v3scale(e.BxDF, pg), F)); out.PDF += e.PDF * pg * F;
+    }
+    if (refracted && validRefraction) {
+        Eval e = eval_refraction(m, V, L, m->BaseColor);
+        if (cfg->UseEnergyCompensation && glassEC > 0.01f) e.BxDF = v3divs(e.BxDF, glassEC);
+        out.BxDF = v3add(out.BxDF, v3scale(v3scale(e.BxDF, pg), 1.0f - F)); out.PDF += e.PDF * pg * (1.0f - F);
+    }
+    return out;
+}
+/* :94-165 */
+static BSample sample_bsdf(const Mat *m, const OrcScene *sc, const OrcConfig *cfg, Rng *rng, v3 V, v3 H) {
+    float pm = m->Metallic;
+    float pd = (1.0f - m->Metallic) * (1.0f - m->Transmission);
+    float pg = (1.0f - m->Metallic) * m->Transmission;
+    float sum = pm + pd + pg;
+    pm /= sum; pd /= sum; pg /= sum;
+    (void)pg;
+    float F = orc_dielectric_fresnel(v3dot(V, H), m->Eta);
+    float x1 = rng_f(rng);
+    v3 L; int refracted = 0;
+    if (x1 < pm) {
+        L = v3normalize(v3reflect(v3neg(V), H));
+    } else if (x1 < pm + pd) {
+        if (rng_f(rng) < F) L = v3normalize(v3reflect(v3neg(V), H));
+        else L = v3normalize(v3add(rng_sphere(rng), V3(0.0f, 0.0f, 1.0f)));
+    } else {
+        if (rng_f(rng) < F) L = v3normalize(v3reflect(v3neg(V), H));
+        else { L = v3normalize(v3refract(v3neg(V), H, m->Eta)); refracted = 1; }
+    }
+    BSample z = { V3(0, 0, 0), V3(0, 0, 0), 0.0f };
+    if (L.z < 0.0f && !refracted) return z;
+    else if (refracted && L.z >= 0.0f) return z;
+    Eval e = eval_bsdf(m, sc, cfg, V, L);
+    BSample r = { L, e.BxDF, e.PDF };
+    return r;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * NEE samplers
+ * ---------------------------------------------------------------------------------------------- */
+/* SH/Sampler.slang:287-346 */
+static void sample_env(const OrcScene *sc, const OrcConfig *cfg, Rng *rng, v3 *toLight, v4 *outValue) {
+    float xx = rng_f(rng), xy = rng_f(rng), xz = rng_f(rng);
+    uint32_t width = sc->d.envW, height = sc->d.envH;
+    uint32_t size = width * height;
+    uint32_t idx = (uint32_t)(xx * (float)size); if (idx > size - 1) idx = size - 1;
+    OrcAliasEntry e = sc->d.env_alias[idx];
+    uint32_t envIdx;
+    if (xy < e.Importance) { envIdx = idx; xy /= e.Importance; }
+    else { envIdx = e.Alias; xy = (xy - e.Importance) / (1.0f - e.Importance); }
+    uint32_t px = envIdx % width, py = envIdx / width;
+    float u = ((float)px + xy) / (float)width;
+    float phi = u * (2.0f * ORC_PI) - ORC_PI;
+    float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    float stepTheta = ORC_PI / (float)height;
+    float theta0 = (float)py * stepTheta;
+    float cosTheta = cosf(theta0) * (1.0f - xz) + cosf(theta0 + stepTheta) * xz;
+    float theta = acosf(cosTheta);
+    float sinTheta = sinf(theta);
+    float v = theta * ORC_1_OVER_PI;
+    v3 d = V3(sinPhi * sinTheta, -cosTheta, -cosPhi * sinTheta);
+    float az = cfg->SkyRotationAzimuth / 180.0f * ORC_PI;
+    float al = cfg->SkyRotationAltitude / 180.0f * ORC_PI;
+    d = orc_rotate(d, V3(0, 1, 0), az);
+    d = orc_rotate(d, V3(1, 0, 0), al);
+    *toLight = d;
+    v4 val = env_sample(sc, u, v);
+    val.x *= cfg->EnvironmentIntensity; val.y *= cfg->EnvironmentIntensity; val.z *= cfg->EnvironmentIntensity;
+    *outValue = val;
+}
+/* SH/Sampler.slang:349-422 */
+static void sample_emissive(const OrcScene *sc, Rng *rng, v3 pos, v3 *toLight, v4 *colorPDF, uint32_t *tri, uint32_t *inst) {
+    *tri = 0xFFFFFFFFu; *inst = 0xFFFFFFFFu;
+    uint32_t count = sc->n_emissive;
+    if (count == 0) { *toLight = V3(0, 0, 0); v4 z = { 0, 0, 0, 0 }; *colorPDF = z; return; }
+    uint32_t mi = (uint32_t)floorf(rng_f(rng) * (float)count); if (mi > count - 1) mi = count - 1;
+    const EmissiveEntry *em = &sc->emissive[mi];
+    *inst = em->instance;
+    uint32_t ti = (uint32_t)floorf(rng_f(rng) * (float)em->tri_count); if (ti > em->tri_count - 1) ti = em->tri_count - 1;
+    *tri = ti;
+    const OrcMesh *m = &sc->d.meshes[em->mesh];
+    const OrcVertex *A = &m->verts[m->indices[ti * 3 + 0]], *B = &m->verts[m->indices[ti * 3 + 1]], *C = &m->verts[m->indices[ti * 3 + 2]];
+    v3 p0 = mat4_point(em->transform, V3(A->pos[0], A->pos[1], A->pos[2]));
+    v3 p1 = mat4_point(em->transform, V3(B->pos[0], B->pos[1], B->pos[2]));
+    v3 p2 = mat4_point(em->transform, V3(C->pos[0], C->pos[1], C->pos[2]));
+    float x0 = rng_f(rng), x1 = rng_f(rng);
+    float su1 = sqrtf(x0);
+    float b0 = 1.0f - su1, b1 = x1 * su1, b2 = 1.0f - b0 - b1;
+    v3 tp = v3add(v3add(v3scale(p0, b0), v3scale(p1, b1)), v3scale(p2, b2));
+    float uu = b0 * A->uv[0] + b1 * B->uv[0] + b2 * C->uv[0];
+    float vv = b0 * A->uv[1] + b1 * B->uv[1] + b2 * C->uv[1];
+    v3 dlt = v3sub(tp, pos);
+    *toLight = v3normalize(dlt);
+    v3 normal = v3normalize(v3cross(v3sub(p2, p0), v3sub(p1, p0)));
+    float area = v3length(v3cross(v3sub(p1, p0), v3sub(p2, p0))) * 0.5f;
+    float d2 = v3dot(dlt, dlt);
+    float cosTheta = fabsf(v3dot(normal, *toLight));
+    const OrcMaterial *mat = &sc->d.materials[em->material];
+    v4 te = tex_sample_u8(&sc->d.textures[mat->EmissiveTextureIndex], uu, vv);
+    v4 r;
+    r.w = d2 / ((float)count * (float)em->tri_count * area * cosTheta);
+    r.x = mat->EmissiveColor[0] * te.x; r.y = mat->EmissiveColor[1] * te.y; r.z = mat->EmissiveColor[2] * te.z;
+    *colorPDF = r;
+}
+
+/* SH/RTCommon.slang:47-84 (USE_RAY_QUERIES variant, the default PT/PathTracer.h:218) */
+static int does_ray_intersect(const OrcScene *sc, v3 o, v3 d, uint32_t *tri, uint32_t *inst, uint64_t *shadow_rays) {
+    *tri = 0; *inst = 0;
+    (*shadow_rays)++;
+    Hit h = trace_bvh(sc, o, d, 0.0001f, 1000000.0f);
+    if (h.hit) { *tri = sc->tris[h.tri].prim; *inst = sc->tris[h.tri].inst; return 1; }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ClosestHit: SH/ClosestHit.slang:20-378
+ * ---------------------------------------------------------------------------------------------- */
+static void closest_hit(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, v3 rayDir, const Hit *h, OrcCounters *cnt) {
+    pl->Emitted = V3(0, 0, 0);                                                  /* :24 */
+    uint32_t inst = sc->tris[h->tri].inst, prim = sc->tris[h->tri].prim;
+    const OrcInstance *in = &sc->d.instances[inst];
+    const OrcMaterial *cm = &sc->d.materials[in->material];
+    Surface sf;
+    surface_init(&sf, sc, cfg, inst, prim, h->u, h->v, rayDir, &sc->d.textures[cm->NormalTextureIndex]);
+    Mat m;
+    material_init(&m, sc, cfg, cm, &sf);
+    int isLight = m.EmissiveColor.x > 0.0f || m.EmissiveColor.y > 0.0f || m.EmissiveColor.z > 0.0f;  /* :65 */
+    surface_rotate_tangents(&sf, m.AnisotropyRotation);                        /* :67 */
+
+    if (pl->InMedium) {                                                         /* :80-116 (Q6) */
+        float dist = v3length(v3sub(pl->Origin, sf.WorldPos));
+        if (pl->MediumAnisotropy == 1.0f) {
+            v3 a = v3scale(v3scale(v3neg(v3sub(v3s(1.0f), m.MediumColor)), m.MediumDensity), dist);
+            pl->BxDF = V3(expf(a.x), expf(a.y), expf(a.z));
+        } else {
+            float sd = -logf(rng_f(&pl->Sampler)) / pl->MediumDensity;
+            if (sd < dist) {
+                pl->Origin = v3add(pl->Origin, v3scale(pl->Direction, sd));
+                pl->Direction = rng_henyey_greenstein(&pl->Sampler, pl->Direction, pl->MediumAnisotropy);
+                pl->BxDF = pl->MediumColor;
+                cnt->medium_events++;
+                return;
+            }
+        }
+    }
+    cnt->surface_hits++;
+
+    /* sky NEE :125-147 */
+    v3 toSkyW = V3(0, 0, 0), toSkyT = V3(0, 0, 0); v4 sky = { 0, 0, 0, 0 }; int canHitSky = 0;
+    if (cfg->EnableSkyMIS) {
+        sample_env(sc, cfg, &pl->Sampler, &toSkyW, &sky);
+        sky.x *= cfg->EnvironmentIntensity; sky.y *= cfg->EnvironmentIntensity; sky.z *= cfg->EnvironmentIntensity; /* Q7 */
+        toSkyT = surf_world_to_tangent(&sf, toSkyW);
+        uint32_t t0, t1;
+        canHitSky = !does_ray_intersect(sc, v3add(sf.WorldPos, v3scale(sf.Normal, 1e-5f)), toSkyW, &t0, &t1, &cnt->shadow_rays);
+        if (!canHitSky) { v4 z = { 0, 0, 0, 0 }; sky = z; }
+    }
+    /* light NEE :154-184 */
+    v3 toLightW = V3(0, 0, 0), toLightT = V3(0, 0, 0); v4 light = { 0, 0, 0, 0 }; int canHitLight = 0;
+    if (cfg->EnableMeshMIS && !isLight) {
+        uint32_t lt, li;
+        sample_emissive(sc, &pl->Sampler, sf.WorldPos, &toLightW, &light, &lt, &li);
+        if (light.w > 0.0f) {
+            toLightT = surf_world_to_tangent(&sf, toLightW);
+            uint32_t ht, hi;
+            int found = does_ray_intersect(sc, v3add(sf.WorldPos, v3scale(toLightW, 1e-2f)), toLightW, &ht, &hi, &cnt->shadow_rays);
+            canHitLight = found ? (lt == ht && li == hi) : 0;
+            if (!canHitLight) { v4 z = { 0, 0, 0, 0 }; light = z; }
+        }
+    }
+    /* BSDF sampling :191-204 */
+    v3 V = v3normalize(v3neg(rayDir));
+    V = surf_world_to_tangent(&sf, V);
+    v3 H = rng_ggx_vndf(&pl->Sampler, V, m.Ax, m.Ay);
+    BSample ss = sample_bsdf(&m, sc, cfg, &pl->Sampler, V, H);
+    int wasRefracted = ss.L.z < 0.0f;
+    v3 scatterW = surf_tangent_to_world(&sf, ss.L);
+    if (!wasRefracted && v3dot(scatterW, sf.GeometryNormal) < 0.0f) { ss.PDF = 0.0f; ss.BxDF = V3(0, 0, 0); }   /* :220-225 */
+    if (wasRefracted && sf.HitFromInside) {                                     /* :227-238 */
+        pl->InMedium = 0;
+    } else if (wasRefracted && !sf.HitFromInside) {
+        pl->InMedium = 1;
+        pl->MediumColor = m.MediumColor; pl->MediumEmissiveColor = m.MediumEmissiveColor;
+        pl->MediumAnisotropy = m.MediumAnisotropy; pl->MediumDensity = m.MediumDensity;
+    }
+    Eval skyEval = { V3(0, 0, 0), 0.0f };
+    if (cfg->EnableSkyMIS && canHitSky) skyEval = eval_bsdf(&m, sc, cfg, V, toSkyT);          /* :241-247 */
+    Eval lightEval = { V3(0, 0, 0), 0.0f };
+    if (cfg->EnableMeshMIS && canHitLight && !isLight) lightEval = eval_bsdf(&m, sc, cfg, V, toLightT); /* :250-256 */
+
+    /* emission :265-317 */
+    if (cfg->EnableMeshMIS) {
+        if (pl->Depth == 0 && isLight) {
+            pl->Emitted = v3add(pl->Emitted, m.EmissiveColor);
+        } else if (isLight) {
+            v3 w1 = xf_point(sc->xf[inst].o2w, sf.P1), w2 = xf_point(sc->xf[inst].o2w, sf.P2), w3 = xf_point(sc->xf[inst].o2w, sf.P3);
+            float area = v3length(v3cross(v3sub(w2, w1), v3sub(w3, w1))) * 0.5f;
+            v3 dl = v3sub(sf.WorldPos, pl->Origin);
+            float d2 = v3dot(dl, dl);
+            float cosTheta = fabsf(v3dot(sf.Normal, v3normalize(v3sub(pl->Origin, sf.WorldPos))));
+            uint32_t triCount = 0;
+            for (uint32_t i = 0; i < sc->n_emissive; i++) if (sc->emissive[i].instance == inst) { triCount = sc->emissive[i].tri_count; break; }
+            float lp = (1.0f / (float)sc->n_emissive) * (1.0f / (float)triCount) * (1.0f / area) * (d2 / cosTheta);
+            lp = fmaxf(lp, cfg->EmissiveMeshSamplingPDFBias);
+            pl->Emitted = v3add(pl->Emitted, v3scale(m.EmissiveColor, power_heuristic(pl->PDF, lp)));
+        }
+    } else {
+        pl->Emitted = v3add(pl->Emitted, m.EmissiveColor);
+    }
+    /* payload write :319-324 */
+    float off = -1e-3f * (wasRefracted ? 1.0f : 0.0f) + 1e-3f * (wasRefracted ? 0.0f : 1.0f);
+    pl->Origin = v3add(sf.WorldPos, v3scale(sf.Normal, off));
+    pl->Direction = scatterW;
+    pl->BxDF = ss.BxDF;
+    pl->PDF = ss.PDF;
+    /* NEE accumulation :326-372 (volume transmittance == 1 with VolumesCount == 0, SH/Volume.slang:419-446) */
+    if (cfg->EnableSkyMIS && canHitSky) {
+        float pdf = sky.w;
+        if (sky.w > 0.0f && skyEval.PDF > 0.0f) {
+            v3 c = v3divs(v3mul(v3scale(skyEval.BxDF, 1.0f), V3(sky.x, sky.y, sky.z)), pdf);
+            pl->Emitted = v3add(pl->Emitted, v3scale(c, power_heuristic(pdf, skyEval.PDF)));
+        }
+    }
+    if (cfg->EnableMeshMIS && !isLight && canHitLight && light.w > 0.0f && lightEval.PDF > 0.0f) {
+        v3 c = v3divs(v3mul(v3scale(lightEval.BxDF, 1.0f), V3(light.x, light.y, light.z)), light.w);
+        pl->Emitted = v3add(pl->Emitted, v3scale(c, power_heuristic(light.w, lightEval.PDF)));
+    }
+    int invalid = ss.PDF <= 0.0f;                                               /* :375-376 */
+    pl->Depth = ORC_MAX_DEPTH * (invalid ? 1u : 0u) + (pl->Depth + 1u * (invalid ? 0u : 1u));
+}
+
+/* Miss: SH/Miss.slang:8-76 */
+static void miss_shader(const OrcScene *sc, const OrcConfig *cfg, Payload *pl) {
+    v4 c;
+    if (cfg->ShowEnvMapDirectly || pl->Depth > 0) {
+        float az = cfg->SkyRotationAzimuth / 180.0f * ORC_PI, al = cfg->SkyRotationAltitude / 180.0f * ORC_PI;
+        v3 r = orc_rotate(pl->Direction, V3(1, 0, 0), -al);
+        r = orc_rotate(r, V3(0, 1, 0), -az);
+        float u, v; direction_to_uv(r, &u, &v);
+        c = env_sample(sc, u, v);
+    } else { v4 z = { 0, 0, 0, 1 }; c = z; }
+    pl->Emitted = V3(c.x * cfg->EnvironmentIntensity, c.y * cfg->EnvironmentIntensity, c.z * cfg->EnvironmentIntensity);
+    if (cfg->FurnaceTestMode) pl->Emitted = v3s(1.0f);
+    if (cfg->EnableSkyMIS && pl->Depth > 0) pl->Emitted = v3scale(pl->Emitted, power_heuristic(pl->PDF, c.w));
+    pl->Depth = ORC_MAX_DEPTH;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * RayGen: SH/RayGen.slang:9-160  (ScatteredInVolume with VolumesCount==0 returns false, :162-263, Q5)
+ * ---------------------------------------------------------------------------------------------- */
+static v3 trace_one_sample(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, uint32_t W, uint32_t H,
+                           uint32_t px, uint32_t py, OrcCounters *cnt) {
+    const float *VI = cfg->ViewInverse, *PI = cfg->ProjectionInverse;
+    float jx = rng_f(&pl->Sampler) * (0.5f - -0.5f) + -0.5f;                    /* :35 UniformFloat2(-0.5,0.5) */
+    float jy = rng_f(&pl->Sampler) * (0.5f - -0.5f) + -0.5f;
+    float pcx = (float)px + 0.5f + jx, pcy = (float)py + 0.5f + jy;
+    float uvx = pcx / (float)W, uvy = pcy / (float)H;
+    float dx = uvx * 2.0f - 1.0f, dy = uvy * 2.0f - 1.0f;
+    v3 origin = V3(VI[0] * 0.0f + VI[4] * 0.0f + VI[8] * 0.0f + VI[12] * 1.0f,
+                   VI[1] * 0.0f + VI[5] * 0.0f + VI[9] * 0.0f + VI[13] * 1.0f,
+                   VI[2] * 0.0f + VI[6] * 0.0f + VI[10] * 0.0f + VI[14] * 1.0f);
+    v3 target = V3(PI[0] * dx + PI[4] * dy + PI[8] * 1.0f + PI[12] * 1.0f,
+                   PI[1] * dx + PI[5] * dy + PI[9] * 1.0f + PI[13] * 1.0f,
+                   PI[2] * dx + PI[6] * dy + PI[10] * 1.0f + PI[14] * 1.0f);
+    v3 direction = mat4_dir(VI, v3normalize(target));
+    v3 focus = v3add(origin, v3scale(direction, fmaxf(cfg->FocusDistance, 0.001f)));
+    float cx, cy; rng_circle(&pl->Sampler, &cx, &cy);
+    float ox = cx * 0.5f * cfg->DepthOfFieldStrength, oy = cy * 0.5f * cfg->DepthOfFieldStrength;
+    v3 right = V3(VI[0], VI[1], VI[2]);     /* M[0][0],M[1][0],M[2][0] = column 0 */
+    v3 upv = V3(VI[4], VI[5], VI[6]);       /* column 1 */
+    origin = v3add(origin, v3add(v3scale(right, ox), v3scale(upv, oy)));
+    direction = v3normalize(v3sub(focus, origin));
+
+    pl->Depth = 0; pl->Origin = origin; pl->Direction = direction;
+    pl->BxDF = v3s(1.0f); pl->PDF = 1.0f; pl->Emitted = v3s(0.0f); pl->InMedium = 0;
+    v3 throughput = v3s(1.0f), pathLight = v3s(0.0f);
+    cnt->paths++;
+    while (pl->Depth < cfg->MaxDepth) {
+        v3 ro = pl->Origin, rd = v3normalize(pl->Direction);
+        pl->Emitted = v3s(0.0f);
+        cnt->segments++;
+        Hit h = trace_bvh(sc, ro, rd, 0.01f, 100000.0f);
+        if (h.hit) closest_hit(sc, cfg, pl, rd, &h, cnt);
+        else { miss_shader(sc, cfg, pl); cnt->misses++; }
+        v3 contribution = v3mul(pl->Emitted, throughput);
+        if (pl->Depth != 1) {                                                   /* Q3 */
+            float lum = v3dot(contribution, V3(0.212671f, 0.715160f, 0.072169f));
+            float scale = cfg->MaxLuminance / fmaxf(lum, cfg->MaxLuminance);
+            contribution = v3scale(contribution, scale);
+        }
+        pathLight = v3add(pathLight, contribution);
+        throughput = v3mul(throughput, v3divs(pl->BxDF, pl->PDF));
+        float p = fmaxf(throughput.x, fmaxf(throughput.y, throughput.z));
+        p = fminf(p, 1.0f);
+        if (p < rng_f(&pl->Sampler)) break;                                     /* Q4 */
+        throughput = v3divs(throughput, p);
+    }
+    return pathLight;
+}
+
+void orc_sample_pixel(const OrcScene *s, const OrcConfig *cfg, uint32_t W, uint32_t H,
+                      uint32_t x, uint32_t y, uint32_t seed, float out_rgb[3], uint32_t *segments_out) {
+    Payload pl; memset(&pl, 0, sizeof(pl));
+    pl.Sampler.seed = y + W * x + seed;                                         /* :28 (Q13) */
+    OrcCounters c; memset(&c, 0, sizeof(c));
+    v3 l = trace_one_sample(s, cfg, &pl, W, H, x, y, &c);
+    out_rgb[0] = l.x; out_rgb[1] = l.y; out_rgb[2] = l.z;
+    if (segments_out) *segments_out = (uint32_t)c.segments;
+}
+
+typedef struct {
+    const OrcScene *s; const OrcConfig *cfg; uint32_t W, H, frameCount, seed, chunk, rank, world, band;
+    float *image; int tid, nthreads; OrcCounters cnt;
+} RenderJob;
+
+static void *render_thread(void *arg) {
+    RenderJob *j = (RenderJob *)arg;
+    const OrcConfig *cfg = j->cfg;
+    uint32_t S = cfg->ScreenSplitCount ? cfg->ScreenSplitCount : 1;
+    uint32_t LW = (j->W + S - 1) / S, LH = (j->H + S - 1) / S;                  /* PT/PathTracer.cpp:146-150 */
+    for (uint32_t ly = (uint32_t)j->tid; ly < LH; ly += (uint32_t)j->nthreads) {
+        for (uint32_t lx = 0; lx < LW; lx++) {
+            uint32_t x = lx * S + j->chunk % S, y = ly * S + j->chunk / S;      /* SH/RayGen.slang:17-22 */
+            if (x >= j->W || y >= j->H) continue;
+            if (((y / j->band) % j->world) != j->rank) continue;                /* image-tile partition */
+            Payload pl; memset(&pl, 0, sizeof(pl));
+            pl.Sampler.seed = y + j->W * x + j->seed;                           /* :28 */
+            float *px = j->image + ((size_t)y * j->W + x) * 4;
+            v3 prev = V3(px[0], px[1], px[2]);
+            v3 acc = v3s(0.0f);
+            for (uint32_t i = 0; i < cfg->SampleCount; i++) {
+                v3 l = trace_one_sample(j->s, cfg, &pl, j->W, j->H, x, y, &j->cnt);
+                if (!isinf(l.x) && !isinf(l.y) && !isinf(l.z) && !isnan(l.x) && !isnan(l.y) && !isnan(l.z)) acc = v3add(acc, l); /* :116 */
+            }
+            acc = v3divs(acc, (float)cfg->SampleCount);
+            v3 color;
+            if (j->frameCount > 0) { float a = 1.0f / (float)(j->frameCount + 1); color = v3lerp(prev, acc, a); }  /* :132-141 */
+            else color = acc;
+            if (j->frameCount == 0 && j->chunk == 0) {                          /* :144-157 */
+                for (uint32_t a = 0; a < S; a++) for (uint32_t b = 0; b < S; b++) {
+                    uint32_t qx = x + a, qy = y + b;
+                    if (qx < j->W && qy < j->H) { float *q = j->image + ((size_t)qy * j->W + qx) * 4; q[0] = color.x; q[1] = color.y; q[2] = color.z; q[3] = 1.0f; }
+                }
+            }
+            px[0] = color.x; px[1] = color.y; px[2] = color.z; px[3] = 1.0f;
+        }
+    }
+    return NULL;
+}
+
+void orc_render(const OrcScene *s, const OrcConfig *cfg, uint32_t W, uint32_t H,
+                uint32_t frame0, uint32_t nframes, uint32_t base_seed,
+                uint32_t rank, uint32_t world, uint32_t band_rows,
+                float *image, int nthreads, OrcCounters *counters) {
+    if (nthreads <= 0) { long n = sysconf(_SC_NPROCESSORS_ONLN); nthreads = n > 0 ? (int)n : 1; }
+    if (nthreads > 256) nthreads = 256;
+    if (world == 0) world = 1;
+    if (band_rows == 0) band_rows = 1;
+    uint32_t S = cfg->ScreenSplitCount ? cfg->ScreenSplitCount : 1;
+    OrcCounters total; memset(&total, 0, sizeof(total));
+    /* PT/PathTracer.cpp:122-156: dispatch d renders chunk d % S^2 with FrameCount = floor(d / S^2) */
+    for (uint32_t f = frame0; f < frame0 + nframes; f++) {
+        for (uint32_t chunk = 0; chunk < S * S; chunk++) {
+            uint32_t dispatch = f * S * S + chunk;
+            uint32_t seed = orc_pcg_hash(base_seed + dispatch);
+            pthread_t th[256]; RenderJob jobs[256];
+            for (int t = 0; t < nthreads; t++) {
+                RenderJob *j = &jobs[t];
+                j->s = s; j->cfg = cfg; j->W = W; j->H = H; j->frameCount = f; j->seed = seed; j->chunk = chunk;
+                j->rank = rank; j->world = world; j->band = band_rows; j->image = image; j->tid = t; j->nthreads = nthreads;
+                memset(&j->cnt, 0, sizeof(j->cnt));
+                pthread_create(&th[t], NULL, render_thread, j);
+            }
+            for (int t = 0; t < nthreads; t++) {
+                pthread_join(th[t], NULL);
+                total.paths += jobs[t].cnt.paths; total.segments += jobs[t].cnt.segments; total.surface_hits += jobs[t].cnt.surface_hits;
+                total.misses += jobs[t].cnt.misses; total.shadow_rays += jobs[t].cnt.shadow_rays; total.medium_events += jobs[t].cnt.medium_events;
+            }
+        }
+    }
+    if (counters) *counters = total;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Host one-offs
+ * ---------------------------------------------------------------------------------------------- */
+void orc_default_config(OrcConfig *c) {                                         /* PT/PathTracer.h:197-233 */
+    memset(c, 0, sizeof(*c));
+    for (int i = 0; i < 4; i++) c->ViewInverse[i * 5] = c->ProjectionInverse[i * 5] = 1.0f;
+    c->SampleCount = 1; c->MaxDepth = 200; c->MaxLuminance = 500.0f; c->FocusDistance = 1.0f; c->DepthOfFieldStrength = 0.0f;
+    c->SkyRotationAzimuth = 0.0f; c->SkyRotationAltitude = 0.0f; c->EnvironmentIntensity = 1.0f;
+    c->EmissiveMeshSamplingPDFBias = 0.0f; c->ScreenSplitCount = 1;
+    c->EnableSkyMIS = 1; c->EnableMeshMIS = 1; c->ShowEnvMapDirectly = 1; c->UseOnlyGeometryNormals = 0;
+    c->UseEnergyCompensation = 1; c->FurnaceTestMode = 0;
+}
+
+/* PT/PathTracer.cpp:1137-1332 (Q1 kept: lowEnergyCounter++ before the store) */
+float orc_build_env_alias(float *pixels, uint32_t width, uint32_t height, OrcAliasEntry *aliasMap) {
+    const uint32_t size = width * height;
+    float *importance = (float *)malloc(sizeof(float) * (size_t)size);
+    float cosTheta0 = 1.0f;
+    const float stepPhi = (float)2.0f * (float)3.14159265358979323846 / (float)width;
+    const float stepTheta = (float)3.14159265358979323846 / (float)height;
+    for (uint32_t y = 0; y < height; ++y) {
+        const float theta1 = (float)(y + 1) * stepTheta;
+        const float cosTheta1 = cosf(theta1);
+        const float area = (cosTheta0 - cosTheta1) * stepPhi;
+        cosTheta0 = cosTheta1;
+        for (uint32_t x = 0; x < width; ++x) {
+            const uint32_t idx = y * width + x, idx4 = idx * 4;
+            importance[idx] = area * fmaxf(pixels[idx4], fmaxf(pixels[idx4 + 1], pixels[idx4 + 2]));
+        }
+    }
+    float sum = 0.0f;                                      /* std::accumulate(..., 0.0f): sequential fp32 */
+    for (uint32_t i = 0; i < size; i++) sum = sum + importance[i];
+    float average = sum / (float)size;
+    for (uint32_t i = 0; i < size; i++) {
+        aliasMap[i].Importance = (average == 0.0f) ? 0.0f : importance[i] / average;
+        aliasMap[i].Alias = i;
+    }
+    uint32_t *partition = (uint32_t *)calloc((size_t)size + 1, sizeof(uint32_t));  /* +1: the reference writes [size] when every texel is low (UB there) */
+    uint32_t low = 0u, high = size;
+    for (uint32_t i = 0; i < size; ++i) {
+        if (aliasMap[i].Importance < 1.0f) { low++; partition[low] = i; }
+        else { high--; partition[high] = i; }
+    }
+    for (low = 0; low < high && high < size; low++) {
+        const uint32_t li = partition[low], hi = partition[high];
+        aliasMap[li].Alias = hi;
+        const float diff = 1.0f - aliasMap[li].Importance;
+        aliasMap[hi].Importance -= diff;
+        if (aliasMap[hi].Importance < 1.0f) high++;
+    }
+    for (uint32_t i = 0; i < size; ++i) {
+        const uint32_t idx4 = i * 4;
+        pixels[idx4 + 3] = (sum == 0.0f) ? 0.0f : fmaxf(pixels[idx4], fmaxf(pixels[idx4 + 1], pixels[idx4 + 2])) / sum;
+    }
+    free(partition); free(importance);
+    return sum;
+}
+
+/* PT/Editor.cpp:45-48,1042-1051 -> PT/FlyCamera.cpp:110-140 (InitializeFromMatrices), :96-108, :84-94.
+ * view = CameraAsset::ViewMatrix (column-major).  Q2: yfov ignored (45 deg), roll dropped. */
+static void mat4_inverse_rigidish(const float m[16], float out[16]) {
+    /* general 4x4 inverse by cofactors in double */
+    double a[16], inv[16];
+    for (int i = 0; i < 16; i++) a[i] = m[i];
+    inv[0] = a[5] * a[10] * a[15] - a[5] * a[11] * a[14] - a[9] * a[6] * a[15] + a[9] * a[7] * a[14] + a[13] * a[6] * a[11] - a[13] * a[7] * a[10];
+    inv[4] = -a[4] * a[10] * a[15] + a[4] * a[11] * a[14] + a[8] * a[6] * a[15] - a[8] * a[7] * a[14] - a[12] * a[6] * a[11] + a[12] * a[7] * a[10];
+    inv[8] = a[4] * a[9] * a[15] - a[4] * a[11] * a[13] - a[8] * a[5] * a[15] + a[8] * a[7] * a[13] + a[12] * a[5] * a[11] - a[12] * a[7] * a[9];
+    inv[12] = -a[4] * a[9] * a[14] + a[4] * a[10] * a[13] + a[8] * a[5] * a[14] - a[8] * a[6] * a[13] - a[12] * a[5] * a[10] + a[12] * a[6] * a[9];
+    inv[1] = -a[1] * a[10] * a[15] + a[1] * a[11] * a[14] + a[9] * a[2] * a[15] - a[9] * a[3] * a[14] - a[13] * a[2] * a[11] + a[13] * a[3] * a[10];
+    inv[5] = a[0] * a[10] * a[15] - a[0] * a[11] * a[14] - a[8] * a[2] * a[15] + a[8] * a[3] * a[14] + a[12] * a[2] * a[11] - a[12] * a[3] * a[10];
+    inv[9] = -a[0] * a[9] * a[15] + a[0] * a[11] * a[13] + a[8] * a[1] * a[15] - a[8] * a[3] * a[13] - a[12] * a[1] * a[11] + a[12] * a[3] * a[9];
+    inv[13] = a[0] * a[9] * a[14] - a[0] * a[10] * a[13] - a[8] * a[1] * a[14] + a[8] * a[2] * a[13] + a[12] * a[1] * a[10] - a[12] * a[2] * a[9];
+    inv[2] = a[1] * a[6] * a[15] - a[1] * a[7] * a[14] - a[5] * a[2] * a[15] + a[5] * a[3] * a[14] + a[13] * a[2] * a[7] - a[13] * a[3] * a[6];
+    inv[6] = -a[0] * a[6] * a[15] + a[0] * a[7] * a[14] + a[4] * a[2] * a[15] - a[4] * a[3] * a[14] - a[12] * a[2] * a[7] + a[12] * a[3] * a[6];
+    inv[10] = a[0] * a[5] * a[15] - a[0] * a[7] * a[13] - a[4] * a[1] * a[15] + a[4] * a[3] * a[13] + a[12] * a[1] * a[7] - a[12] * a[3] * a[5];
+    inv[14] = -a[0] * a[5] * a[14] + a[0] * a[6] * a[13] + a[4] * a[1] * a[14] - a[4] * a[2] * a[13] - a[12] * a[1] * a[6] + a[12] * a[2] * a[5];
+    inv[3] = -a[1] * a[6] * a[11] + a[1] * a[7] * a[10] + a[5] * a[2] * a[11] - a[5] * a[3] * a[10] - a[9] * a[2] * a[7] + a[9] * a[3] * a[6];
+    inv[7] = a[0] * a[6] * a[11] - a[0] * a[7] * a[10] - a[4] * a[2] * a[11] + a[4] * a[3] * a[10] + a[8] * a[2] * a[7] - a[8] * a[3] * a[6];
+    inv[11] = -a[0] * a[5] * a[11] + a[0] * a[7] * a[9] + a[4] * a[1] * a[11] - a[4] * a[3] * a[9] - a[8] * a[1] * a[7] + a[8] * a[3] * a[5];
+    inv[15] = a[0] * a[5] * a[10] - a[0] * a[6] * a[9] - a[4] * a[1] * a[10] + a[4] * a[2] * a[9] + a[8] * a[1] * a[6] - a[8] * a[2] * a[5];
+    double det = a[0] * inv[0] + a[1] * inv[4] + a[2] * inv[8] + a[3] * inv[12];
+    det = 1.0 / det;
+    for (int i = 0; i < 16; i++) out[i] = (float)(inv[i] * det);
+}
+
+void orc_camera_from_view(const float view[16], float aspect, float viewInv_out[16], float projInv_out[16]) {
+    float invView[16];
+    mat4_inverse_rigidish(view, invView);
+    v3 pos = V3(invView[12], invView[13], invView[14]);
+    /* forward = -(view[0][2], view[1][2], view[2][2]) (glm column-major: view[c][r]) */
+    v3 fwd = v3normalize(v3neg(V3(view[0 * 4 + 2], view[1 * 4 + 2], view[2 * 4 + 2])));
+    const float RAD2DEG = 57.295779513082320876798154814105f, DEG2RAD = 0.01745329251994329576923690768489f;
+    float yaw = atan2f(fwd.z, fwd.x) * RAD2DEG;
+    float pitch = asinf(fwd.y) * RAD2DEG;
+    /* PT/PathTracer.cpp:578: projection perspective(radians(45), aspect, 0.1, 100); FlyCamera re-derives fov/aspect */
+    float tanHalf0 = tanf((45.0f * DEG2RAD) / 2.0f);
+    float P00 = 1.0f / (aspect * tanHalf0), P11 = 1.0f / tanHalf0;
+    float fov = (2.0f * atanf(1.0f / P11)) * RAD2DEG;
+    float asp = P11 / P00;
+    /* UpdateCameraVectors :96-108 */
+    v3 front = v3normalize(V3(cosf(yaw * DEG2RAD) * cosf(pitch * DEG2RAD), sinf(pitch * DEG2RAD), sinf(yaw * DEG2RAD) * cosf(pitch * DEG2RAD)));
+    v3 right = v3normalize(v3cross(front, V3(0, 1, 0)));
+    v3 up = v3normalize(v3cross(right, front));
+    /* glm::lookAt RH (:84-88): f = normalize(center-eye); s = normalize(cross(f, up)); u = cross(s, f) */
+    v3 f = v3normalize(v3sub(v3add(pos, front), pos));
+    v3 s = v3normalize(v3cross(f, up));
+    v3 u = v3cross(s, f);
+    /* inverse(view) for an orthonormal basis: columns s, u, -f, pos */
+    float vi[16] = { s.x, s.y, s.z, 0.0f, u.x, u.y, u.z, 0.0f, -f.x, -f.y, -f.z, 0.0f, pos.x, pos.y, pos.z, 1.0f };
+    memcpy(viewInv_out, vi, sizeof(vi));
+    /* glm::perspective RH_ZO(radians(fov), asp, 0.1, 1000) (:90-94) and its analytic inverse */
+    float tanHalf = tanf((fov * DEG2RAD) / 2.0f);
+    float n = 0.1f, fz = 1000.0f;
+    float A = 1.0f / (asp * tanHalf), B = 1.0f / tanHalf, C = fz / (n - fz), D = -(fz * n) / (fz - n);
+    float pi_[16] = { 1.0f / A, 0, 0, 0, 0, 1.0f / B, 0, 0, 0, 0, 0, 1.0f / D, 0, 0, -1.0f, C / D };
+    memcpy(projInv_out, pi_, sizeof(pi_));
+}
