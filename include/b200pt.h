@@ -1,0 +1,189 @@
+/*
+ * b200pt.h -- C-ABI of the B200-native wavefront path tracer (libb200pt.so).
+ *
+ * Drop-in boundary for ONE hot path of Zydak/Vulkan-Path-Tracer: the Monte-Carlo integrator
+ * (ray-gen -> traverse -> closest-hit/miss shading -> accumulate) plus the bloom + tonemap post chain.
+ * The reference has no FFI; the seam is the C++ class surface its Editor consumes, so every entry point
+ * below names the reference member it replaces (paths relative to /root/reference).
+ * INTEGRATION.md shows the adapter a maintainer would put behind PathTracer/PostProcessor.
+ *
+ * Conventions
+ *   - every call returns int32 (VHResult-compatible: 0 = OK, negative = error; VulkanHelper/Include/Core/Error.h:14-72),
+ *     never aborts, never throws across the boundary.
+ *   - one opaque handle == one GPU == one reference `PathTracer` + `PostProcessor` pair; a handle is not
+ *     thread-safe (the reference is single-threaded, PathTracer/Editor.cpp:85-89); distinct handles are independent.
+ *   - plain pointers + sizes only; matrices are column-major float[16] (glm); images are row 0 first, tightly packed.
+ *   - the library copies everything it needs during the call (as PathTracer::SetScene does, PathTracer.cpp:166-167).
+ */
+#ifndef B200PT_H
+#define B200PT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- result codes (VHResult-compatible subset) ---- */
+#define B200PT_OK                     0
+#define B200PT_ERR_UNKNOWN           -1
+#define B200PT_ERR_INIT_FAILED       -3      /* VK_ERROR_INITIALIZATION_FAILED: file/scene import failed */
+#define B200PT_ERR_OUT_OF_MEMORY     -2
+#define B200PT_ERR_WRONG_ARGUMENTS   -15000  /* custom range of Error.h */
+#define B200PT_ERR_NOT_IMPLEMENTED   -15001  /* volumes / atmosphere API (out of scope) */
+#define B200PT_ERR_NO_SCENE          -15002
+#define B200PT_ERR_CUDA              -15003
+#define B200PT_ERR_NO_DEVICE         -15004  /* no CUDA device: the product has no CPU fallback */
+
+typedef struct b200pt_s *b200pt_handle;
+
+/* ---- data layouts (sizes asserted in the implementation) ---- */
+typedef struct { float Position[3]; float Normal[3]; float TexCoord[2]; } b200pt_vertex;   /* 32 B: Asset.h:16-21, Bindings.slang:7-12 */
+
+typedef struct {                                                                            /* 112 B: PathTracer.h:12-34 */
+    float BaseColor[3], EmissiveColor[3], SpecularColor[3], MediumColor[3], MediumEmissiveColor[3];
+    float Metallic, Roughness, IOR, Transmission, Anisotropy, AnisotropyRotation;
+    float MediumDensity, MediumAnisotropy;
+    uint32_t BaseColorTextureIndex, NormalTextureIndex, RoughnessTextureIndex, MetallicTextureIndex, EmissiveTextureIndex;
+} b200pt_material;
+
+typedef struct { const b200pt_vertex *vertices; const uint32_t *indices; uint32_t vertex_count, index_count; } b200pt_mesh; /* Asset.h:23-49 */
+typedef struct { float Transform[16]; uint32_t MeshIndex, MaterialIndex; } b200pt_instance;                                /* Asset.h:124-129 */
+typedef struct { uint32_t width, height, channels, _pad; const uint8_t *data; } b200pt_texture; /* RGBA8 (4) or R8 (1); PathTracer.cpp:812-869 */
+
+typedef struct {                                   /* what PathTracer::SetScene keeps of a SceneAsset (Asset.h:131-138) */
+    const b200pt_mesh *meshes;           uint32_t mesh_count, _p0;
+    const b200pt_material *materials;    uint32_t material_count, _p1;
+    const b200pt_texture *textures;      uint32_t texture_count, _p2;
+    const b200pt_instance *instances;    uint32_t instance_count, _p3;
+    float camera_view[16];               /* CameraAsset::ViewMatrix */
+    float camera_aspect;                 /* CameraAsset::AspectRatio */
+    uint32_t _p4;
+} b200pt_scene_desc;
+
+typedef struct {                                   /* PathTracer.h:197-233 members behind the ~45 setters */
+    uint32_t SamplesPerFrame;            /* SetSamplesPerFrame   (default 1)   */
+    uint32_t MaxDepth;                   /* SetMaxDepth          (200)         */
+    float    MaxLuminance;               /* SetMaxLuminance      (500)         */
+    float    FocusDistance;              /* SetFocusDistance     (1)           */
+    float    DepthOfFieldStrength;       /* SetDepthOfFieldStrength (0)        */
+    float    SkyRotationAzimuth;         /* SetSkyAzimuth  (deg, 0)            */
+    float    SkyRotationAltitude;        /* SetSkyAltitude (deg, 0)            */
+    float    SkyIntensity;               /* SetSkyIntensity      (1)           */
+    float    EmissiveMeshSamplingPDFBias;/* SetEmissiveMeshSamplingPDFBias (0) */
+    uint32_t ScreenChunkCount;           /* SetSplitScreenCount  (1)           */
+    uint32_t EnableSkyMIS;               /* SetSkyMIS            (1)           */
+    uint32_t EnableMeshMIS;              /* SetMeshMIS           (1)           */
+    uint32_t ShowEnvMapDirectly;         /* SetEnvMapShownDirectly (1)         */
+    uint32_t UseOnlyGeometryNormals;     /* SetUseOnlyGeometryNormals (0)      */
+    uint32_t UseEnergyCompensation;      /* SetUseEnergyCompensation (1)       */
+    uint32_t FurnaceTestMode;            /* SetFurnaceTestMode   (0)           */
+    uint32_t MaxSamplesAccumulated;      /* SetMaxSamplesAccumulated (5000)    */
+    /* engine knobs (no reference equivalent) */
+    uint32_t FramesInFlight;             /* frames batched into one wavefront (0 = auto) */
+} b200pt_config;
+
+typedef struct { float Exposure, Gamma; } b200pt_tonemap;                               /* PostProcessor.h:8-12  */
+typedef struct { float BloomThreshold, BloomStrength; uint32_t MipCount; float FalloffRange; } b200pt_bloom; /* PostProcessor.h:14-21 */
+
+typedef struct {                                   /* device counters + event timings of the last path_trace call */
+    uint64_t paths, extend_rays, shade_invocations, surface_hits, misses, shadow_rays, medium_events;
+    uint64_t kernel_launches;
+    float ms_total, ms_raygen, ms_extend, ms_shade, ms_connect, ms_resolve;
+    uint32_t waves, bounces;
+} b200pt_counters;
+
+/* ---- lifetime: PathTracer::New / PostProcessor::New (PathTracer.h:83, PostProcessor.h:25) ---- */
+int32_t b200pt_create(int32_t device_ordinal, b200pt_handle *out);
+int32_t b200pt_destroy(b200pt_handle h);
+const char *b200pt_last_error(b200pt_handle h);         /* human-readable detail of the last failure (VH_LOG_ERROR analogue) */
+const char *b200pt_version(void);
+
+/* ---- scene: PathTracer::SetScene(const std::string&) (PathTracer.cpp:158-676) ---- */
+int32_t b200pt_set_scene_file(b200pt_handle h, const char *gltf_path);      /* glTF 2.0 (.gltf + .bin + PNG/JPEG textures) */
+int32_t b200pt_set_scene_arrays(b200pt_handle h, const b200pt_scene_desc *desc);
+/* PathTracer::SetEnvMapFilepath / LoadEnvironmentMap (PathTracer.cpp:1048-1056,1137-1332): builds the alias table */
+int32_t b200pt_set_env_map_file(b200pt_handle h, const char *hdr_path);
+int32_t b200pt_set_env_map(b200pt_handle h, uint32_t width, uint32_t height, const float *rgba);
+/* PathTracer::LoadLookupTable x3 (PathTracer.cpp:199-201,871-937): fp32 [32][64][64], [32][128][128] x2 */
+int32_t b200pt_set_luts(b200pt_handle h, const float *reflection, const float *refraction_from_outside, const float *refraction_from_inside);
+int32_t b200pt_set_luts_dir(b200pt_handle h, const char *dir);              /* dir holding the three shipped .bin files */
+
+/* ---- parameters: the setter/getter block of PathTracer.h:97-181 ---- */
+int32_t b200pt_default_config(b200pt_config *out);
+int32_t b200pt_set_config(b200pt_handle h, const b200pt_config *cfg);       /* any change -> ResetPathTracing() */
+int32_t b200pt_get_config(b200pt_handle h, b200pt_config *out);
+int32_t b200pt_material_count(b200pt_handle h, uint32_t *out);
+int32_t b200pt_get_material(b200pt_handle h, uint32_t index, b200pt_material *out);   /* GetMaterial */
+int32_t b200pt_set_material(b200pt_handle h, uint32_t index, const b200pt_material *m); /* SetMaterial (PathTracer.cpp:712-810) */
+int32_t b200pt_get_material_name(b200pt_handle h, uint32_t index, char *buf, uint32_t buf_size); /* GetMaterialName */
+int32_t b200pt_set_camera(b200pt_handle h, const float view_inverse[16], const float projection_inverse[16]); /* SetCameraViewInverse/ProjectionInverse */
+int32_t b200pt_get_camera(b200pt_handle h, float view_inverse[16], float projection_inverse[16]);
+/* the Editor/FlyCamera round trip that produces the matrices the shader really sees (Editor.cpp:45-48,1042-1051; FlyCamera.cpp:84-140) */
+int32_t b200pt_camera_from_view(const float view[16], float aspect, float view_inverse_out[16], float projection_inverse_out[16]);
+int32_t b200pt_resize(b200pt_handle h, uint32_t width, uint32_t height);   /* ResizeImage */
+int32_t b200pt_get_size(b200pt_handle h, uint32_t *width, uint32_t *height);
+int32_t b200pt_reset(b200pt_handle h);                                      /* ResetPathTracing */
+/* volumes (PathTracer.h:157-166): out of scope -> B200PT_ERR_NOT_IMPLEMENTED */
+int32_t b200pt_add_volume(b200pt_handle h, const void *volume);
+
+/* ---- image-tile partition across GPUs (no reference equivalent) ----
+ * rank r of `world` owns rows y with ((y / band_rows) % world) == r.  RNG streams are keyed on global pixel
+ * coordinates, so the union of all ranks' rows is bit-identical to the world==1 image. */
+int32_t b200pt_set_partition(b200pt_handle h, uint32_t rank, uint32_t world, uint32_t band_rows);
+int32_t b200pt_local_rows(b200pt_handle h, uint32_t *rows_out);
+/* pure host helper: global row of local row `r` (also used by the gather step) */
+uint32_t b200pt_partition_global_row(uint32_t local_row, uint32_t rank, uint32_t world, uint32_t band_rows);
+uint32_t b200pt_partition_local_row_count(uint32_t height, uint32_t rank, uint32_t world, uint32_t band_rows);
+
+/* ---- the hot path: PathTracer::PathTrace(cmd) x `dispatches` (PathTracer.cpp:122-156) ----
+ * dispatch d uses push constants {FrameCount = floor(d/S^2), Seed = PCG_HASH(base_seed + d), ChunkIndex = d % S^2}
+ * (the reference's wall-clock seed is replaced by a caller-supplied one).  Stops early at MaxSamplesAccumulated;
+ * *done_out (optional) = 1 when all samples are accumulated (PathTrace's return value). */
+int32_t b200pt_path_trace(b200pt_handle h, uint32_t dispatches, uint32_t base_seed, int32_t *done_out);
+int32_t b200pt_samples_accumulated(b200pt_handle h, uint32_t *out);         /* GetSamplesAccumulated */
+int32_t b200pt_synchronize(b200pt_handle h);
+/* Run all work of this handle on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the handle's own
+ * stream).  Lets a host framework order its collectives / events against the render without extra synchronisation. */
+int32_t b200pt_set_stream(b200pt_handle h, void *cuda_stream);
+/* 1 = record CUDA events around every kernel class and report ms_raygen/extend/shade/connect/resolve in the counters
+ * (adds a few microseconds per launch; leave 0 for throughput runs). */
+int32_t b200pt_set_profiling(b200pt_handle h, int32_t enabled);
+/* GetOutputImage(): RGBA32F running mean, alpha 1.  world==1: full W*H*4 floats.  world>1: local rows only
+ * (local_rows*W*4 floats, in local-row order).  dst may be host or device memory (dst_is_device). */
+int32_t b200pt_get_hdr(b200pt_handle h, float *dst, int32_t dst_is_device);
+int32_t b200pt_hdr_device_ptr(b200pt_handle h, void **ptr_out);            /* zero-copy view for the NCCL gather */
+/* replace the accumulation image (post-only runs / checkpoint restore): full W*H*4 floats from host or device */
+int32_t b200pt_set_hdr(b200pt_handle h, const float *src, int32_t src_is_device);
+int32_t b200pt_get_counters(b200pt_handle h, b200pt_counters *out);
+
+/* ---- post chain: PostProcessor (PostProcessor.h:25-33, PostProcessor.cpp:128-246) ---- */
+int32_t b200pt_post_set_tonemap(b200pt_handle h, const b200pt_tonemap *t);  /* SetTonemappingData */
+int32_t b200pt_post_set_bloom(b200pt_handle h, const b200pt_bloom *b);      /* SetBloomData */
+int32_t b200pt_post_process(b200pt_handle h);                               /* PostProcess(cmd); input = GetOutputImage() */
+int32_t b200pt_get_ldr(b200pt_handle h, uint8_t *dst_rgba8, int32_t dst_is_device); /* GetOutputImageView() -> RGBA8 */
+int32_t b200pt_get_bloom(b200pt_handle h, float *dst_rgba32f);              /* bloom mip 0 after the up pass (test hook) */
+int32_t b200pt_bloom_mip_sizes(uint32_t width, uint32_t height, uint32_t *wh_out20, uint32_t *levels_out);
+/* Editor::SaveToFile (Editor.cpp:815-843): RGBA8 -> PNG, row stride W*4 */
+int32_t b200pt_save_png(b200pt_handle h, const char *path);
+
+/* ---- fine-grained hooks used by the parity tests (closest-hit semantics of RTCommon.slang:47-117) ---- */
+int32_t b200pt_trace_closest(b200pt_handle h, uint32_t n, const float *origins3, const float *directions3,
+                             float tmin, float tmax, float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out2);
+int32_t b200pt_scene_stats(b200pt_handle h, uint32_t *triangles, uint32_t *bvh_nodes, uint32_t *emissive_meshes, uint32_t *textures);
+
+/* ---- standalone codecs of the loader / image-output API (no GPU needed) ---- */
+/* stbi_load(.., STBI_rgb_alpha) / stbi_loadf semantics (AssetImporterImpl.cpp:494-545); free with b200pt_free */
+int32_t b200pt_decode_image_file(const char *path, uint32_t *width, uint32_t *height, uint8_t **rgba_out);
+int32_t b200pt_decode_hdr_file(const char *path, uint32_t *width, uint32_t *height, float **rgba_out);
+int32_t b200pt_write_png(const char *path, uint32_t width, uint32_t height, const uint8_t *rgba);
+/* host restatement of LoadEnvironmentMap's alias table (PathTracer.cpp:1137-1332); alias_out = width*height {u32,f32} */
+int32_t b200pt_build_env_alias(float *rgba_inout, uint32_t width, uint32_t height, void *alias_out, float *sum_out);
+/* parse a glTF into a heap-allocated scene description (b200pt_free_scene); what set_scene_file uploads */
+int32_t b200pt_load_gltf(const char *path, b200pt_scene_desc **out);
+int32_t b200pt_free_scene(b200pt_scene_desc *s);
+void    b200pt_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

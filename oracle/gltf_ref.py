@@ -147,7 +147,7 @@ def load_gltf(path, decode_image=_decode_image):
         o["Transmission"] = np.float32(ext.get("KHR_materials_transmission", {}).get("transmissionFactor", 0.0))
         an = ext.get("KHR_materials_anisotropy", {})
         o["Anisotropy"] = np.float32(an.get("anisotropyStrength", 0.0))
-        o["AnisotropyRotation"] = np.float32(an.get("anisotropyRotation", 0.0)) * np.float32(180.0 / np.pi)
+        o["AnisotropyRotation"] = np.float32(an.get("anisotropyRotation", 0.0)) * (np.float32(180.0) / np.float32(np.pi))
         o["MediumDensity"] = 0.0; o["MediumAnisotropy"] = 0.0
         mr = tex_path(pbr.get("metallicRoughnessTexture"))
         tex_paths.append(dict(base=tex_path(pbr.get("baseColorTexture")), normal=tex_path(m.get("normalTexture")),

@@ -1,0 +1,240 @@
+"""Parity tests proper: the sm_100a kernels (through the C-ABI) against the CPU oracle on the same seeded inputs.
+All tests need a CUDA device (run with -m gpu on the B200 box).
+
+Tolerances (north_star: per-pixel L2 < 1e-3 vs reference at matched seed):
+  * index/ids (primitive, instance) and compaction bookkeeping: bit-exact (ties aside, measured and bounded)
+  * fp32 radiance at matched seed: the GPU uses FMA contraction and CUDA libm (<= 2 ulp) where the oracle uses strict
+    IEEE ops and glibc; a path that lands within an ulp of a branch (lobe pick, RR, triangle edge) takes the other branch.
+    So: >= 99.5 % of the pixels agree to 1e-4 relative at 1 spp, and the relative L2 of the converged image is < 1e-3
+    once the rare divergent samples are averaged down (stated per test).
+"""
+import numpy as np
+import pytest
+
+import util
+from util import orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pt():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import vpt_b200
+    return vpt_b200
+
+
+def _rays(S, n, seed):
+    rng = np.random.default_rng(seed)
+    tri, _, _ = S.world_triangles()
+    lo, hi = tri.reshape(-1, 3).min(0), tri.reshape(-1, 3).max(0)
+    o = (lo - 0.2 * (hi - lo) + 1.4 * (hi - lo) * rng.random((n, 3))).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o, d.astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "cornell_box_glass", "viking_room", "breakfast_room"])
+def test_lbvh_closest_hit_equals_brute_force(pt, name):
+    """GPU LBVH (Morton + radix sort + Karras) + traversal vs the oracle's brute-force closest hit."""
+    S = util.oracle_scene(name)
+    T = util.product_tracer(name, 64, 64)
+    st = T.scene_stats()
+    assert st["triangles"] == S.ntris and st["emissive_meshes"] == S.n_emissive
+    n = 20000 if name != "breakfast_room" else 3000           # brute force is O(n * tris) on the CPU
+    o, d = _rays(S, n, 1)
+    for tmin, tmax in ((0.01, 1e5), (1e-4, 1e6)):
+        t0, p0, i0, uv0 = S.trace_closest(o, d, tmin, tmax, use_bvh=(name == "breakfast_room"))
+        t1, p1, i1, uv1 = T.trace_closest(o, d, tmin, tmax)
+        same = (p0 == p1) & (i0 == i1)
+        assert same.mean() > 0.9995, (name, same.mean())      # only exact-edge / FMA-rounding ties may differ
+        hit = same & (t0 > 0)
+        assert hit.sum() > n // 4
+        assert np.allclose(t0[hit], t1[hit], rtol=2e-5, atol=1e-6)
+        assert np.allclose(uv0[hit], uv1[hit], rtol=0, atol=2e-4)
+        assert np.array_equal(t0[same & (t0 < 0)], t1[same & (t0 < 0)])
+
+
+def _render_both(pt, name, W, H, frames, seed=util.BASE_SEED, **kw):
+    S = util.oracle_scene(name)
+    cfg = util.oracle_config(name, **kw)
+    ref, cnt = S.render(cfg, W, H, frames, seed)
+    T = util.product_tracer(name, W, H, **kw)
+    T.path_trace(frames, seed)
+    got = T.get_hdr()
+    return ref, got, cnt, T
+
+
+@pytest.mark.parametrize("name,depth", [("cornell_box", 8), ("cornell_box_glass", 16), ("viking_room", 8)])
+def test_one_spp_matched_seed(pt, name, depth):
+    W, H = (192, 108) if name == "cornell_box" else (128, 128)
+    ref, got, cnt, T = _render_both(pt, name, W, H, 1, MaxDepth=depth)
+    assert got.shape == ref.shape and np.isfinite(got).all() and np.all(got[..., 3] == 1.0)
+    a, b = ref[..., :3].astype(np.float64), got[..., :3].astype(np.float64)
+    close = np.all(np.abs(a - b) <= 1e-4 * np.maximum(np.abs(a), 1e-2), axis=-1)
+    assert close.mean() > 0.995, (name, close.mean())
+    c = T.counters()
+    assert c["paths"] == W * H
+    # same estimator => same amount of work (a few divergent paths aside)
+    assert abs(c["extend_rays"] - cnt["segments"]) <= 0.002 * cnt["segments"] + 4
+    assert abs(c["misses"] - cnt["misses"]) <= 0.002 * cnt["segments"] + 4
+
+
+def test_converged_image_relative_l2(pt):
+    """config 2 geometry at reduced size: 64 frames, depth 8, matched seeds -> relative L2 of the HDR mean < 1e-3."""
+    ref, got, cnt, T = _render_both(pt, "cornell_box", 160, 90, 64, MaxDepth=8)
+    l2 = util.rel_l2(got[..., :3], ref[..., :3])
+    assert l2 < 1e-3, l2
+    assert T.samples_accumulated() == 64
+
+
+def test_glass_and_rough_conductor_config4(pt):
+    """config 4: CornellBoxGlass + one wall set to Metallic 1 / Roughness 0.3 through set_material, depth 16."""
+    name, W, H = "cornell_box_glass", 96, 96
+    sc = util.scene_dict(name)
+    mats = sc["materials"].copy(); mats["Metallic"][2] = 1.0; mats["Roughness"][2] = 0.3
+    sc2 = dict(sc); sc2["materials"] = mats
+    raw, env_pdf, alias = util.env_small()
+    S = orc.Scene(sc2, env_pdf, alias, util.luts())
+    ref, _ = S.render(util.oracle_config(name, MaxDepth=16), W, H, 32, 5)
+    T = util.product_tracer(name, W, H, MaxDepth=16)
+    m = T.get_material(2); m.Metallic = 1.0; m.Roughness = 0.3; T.set_material(2, m)
+    assert T.samples_accumulated() == 0                       # SetMaterial -> ResetPathTracing
+    T.path_trace(32, 5)
+    got = T.get_hdr()
+    assert util.rel_l2(got[..., :3], ref[..., :3]) < 2e-3
+    assert T.get_material_name(4) == "Sphere" and T.material_count() == 5
+
+
+def test_medium_random_walk(pt):
+    name, W, H = "cornell_box_glass", 64, 64
+    sc = util.scene_dict(name)
+    mats = sc["materials"].copy(); mats["MediumDensity"][4] = 2.0; mats["MediumAnisotropy"][4] = 0.3; mats["MediumColor"][4] = (0.9, 0.5, 0.3)
+    sc2 = dict(sc); sc2["materials"] = mats
+    raw, env_pdf, alias = util.env_small()
+    S = orc.Scene(sc2, env_pdf, alias, util.luts())
+    ref, cnt = S.render(util.oracle_config(name, MaxDepth=12), W, H, 16, 9)
+    T = util.product_tracer(name, W, H, MaxDepth=12)
+    m = T.get_material(4); m.MediumDensity = 2.0; m.MediumAnisotropy = 0.3; m.MediumColor[0], m.MediumColor[1], m.MediumColor[2] = 0.9, 0.5, 0.3
+    T.set_material(4, m)
+    T.path_trace(16, 9)
+    got = T.get_hdr(); c = T.counters()
+    assert cnt["medium_events"] > 0 and abs(c["medium_events"] - cnt["medium_events"]) <= 0.02 * cnt["medium_events"] + 8
+    assert util.rel_l2(got[..., :3], ref[..., :3]) < 5e-3
+
+
+def test_furnace_known_answer(pt):
+    ref, got, _, _ = _render_both(pt, "cornell_box", 64, 36, 32, seed=7, MaxDepth=200, FurnaceTestMode=1, EnableSkyMIS=0, EnableMeshMIS=0)
+    assert np.all(got[:, :12, :3] == 1.0) and np.all(got[:, -12:, :3] == 1.0)      # sky seen directly: exactly 1
+    assert util.rel_l2(got[..., :3], ref[..., :3]) < 2e-3
+
+
+@pytest.mark.parametrize("kw", [dict(EnableSkyMIS=0), dict(EnableMeshMIS=0), dict(ShowEnvMapDirectly=0), dict(UseOnlyGeometryNormals=1),
+                                dict(UseEnergyCompensation=0), dict(SkyRotationAzimuth=70.0, SkyRotationAltitude=20.0, EnvironmentIntensity=2.0),
+                                dict(DepthOfFieldStrength=0.5, FocusDistance=14.0), dict(MaxLuminance=0.5)])
+def test_feature_flags_match_oracle(pt, kw):
+    ref, got, _, _ = _render_both(pt, "cornell_box", 96, 54, 16, seed=21, MaxDepth=6, **kw)
+    assert util.rel_l2(got[..., :3], ref[..., :3]) < 3e-3, kw
+
+
+def test_samples_per_frame_and_running_mean(pt):
+    # SamplesPerFrame = 3: one RNG stream per pixel per frame shared by the 3 samples (SH/RayGen.slang:28,33)
+    ref, got, _, T = _render_both(pt, "cornell_box", 80, 45, 5, seed=3, MaxDepth=6, SampleCount=3)
+    assert T.samples_accumulated() == 15
+    assert util.rel_l2(got[..., :3], ref[..., :3]) < 3e-3
+    # accumulating in two calls == one call (frame counter continues)
+    T2 = util.product_tracer("cornell_box", 80, 45, MaxDepth=6, SampleCount=3)
+    T2.path_trace(2, 3); T2.path_trace(3, 3)
+    assert np.array_equal(T2.get_hdr(), got)
+    # MaxSamplesAccumulated stops the accumulation (PathTracer.cpp:124-125)
+    cfg = T2.get_config(); cfg.MaxSamplesAccumulated = 6; T2.set_config(cfg)
+    assert T2.path_trace(10, 3) is True and T2.samples_accumulated() == 6
+
+
+def test_screen_chunk_split(pt):
+    # ScreenChunkCount S: dispatch d renders chunk d % S^2 (SH/RayGen.slang:17-25,143-157)
+    ref, got, _, T = _render_both(pt, "cornell_box", 50, 31, 8, seed=11, MaxDepth=5, ScreenSplitCount=2)
+    assert T.samples_accumulated() == 8
+    assert util.rel_l2(got[..., :3], ref[..., :3]) < 3e-3
+    # a partial first frame shows the splat of chunk 0
+    S = util.oracle_scene("cornell_box"); cfg = util.oracle_config("cornell_box", MaxDepth=5, ScreenSplitCount=2)
+    T.reset(); T.path_trace(1, 11)
+    # only dispatch 0 of frame 0: the oracle renders one chunk when asked for "1/4 frame" -> emulate with its per-dispatch loop
+    import ctypes
+    img = np.zeros((31, 50, 4), np.float32)
+    # orc_render renders whole frames; compare the splat property instead: 2x2 blocks are constant
+    g = T.get_hdr()
+    assert np.array_equal(g[0:30:2, 0:50:2], g[1:31:2, 0:50:2]) and np.array_equal(g[0:30:2, 0:50:2], g[0:30:2, 1:50:2])
+
+
+def test_tile_partition_is_bit_identical_and_frames_in_flight_invariant(pt):
+    W, H = 96, 70
+    T = util.product_tracer("cornell_box", W, H, MaxDepth=6)
+    T.path_trace(6, 77); full = T.get_hdr()
+    for fif in (1, 4):
+        T2 = util.product_tracer("cornell_box", W, H, MaxDepth=6, FramesInFlight=fif)
+        T2.path_trace(6, 77)
+        assert np.array_equal(T2.get_hdr(), full)             # wavefront batching does not change any pixel
+    world, band = 3, 8
+    out = np.zeros_like(full)
+    for r in range(world):
+        Tr = util.product_tracer("cornell_box", W, H, MaxDepth=6)
+        Tr.set_partition(r, world, band)
+        Tr.path_trace(6, 77)
+        rows = pt.partition_rows(H, r, world, band)
+        loc = Tr.get_hdr()
+        assert loc.shape[0] == len(rows) == Tr.local_rows()
+        out[rows] = loc
+    assert np.array_equal(out, full)                          # RNG keyed on global pixel coordinates
+    T.path_trace(1, 77)                                       # determinism across runs
+    T3 = util.product_tracer("cornell_box", W, H, MaxDepth=6); T3.path_trace(7, 77)
+    assert np.array_equal(T3.get_hdr(), T.get_hdr())
+
+
+def test_post_chain_matches_oracle(pt, tmp_path):
+    rng = np.random.default_rng(7)
+    for (W, H) in ((317, 203), (640, 360)):
+        hdr = np.ones((H, W, 4), np.float32); hdr[..., :3] = (np.exp(rng.normal(0, 1.5, (H, W, 3))) * 0.5).astype(np.float32)
+        for _ in range(6):
+            y, x = rng.integers(0, H - 5), rng.integers(0, W - 5); hdr[y:y + 5, x:x + 5, :3] = 500.0
+        T = util.product_tracer("cornell_box", W, H)
+        T.set_hdr(hdr)
+        for mips, thr, strength, fall, exp, gam in ((10, 2.0, 1.0, 5.0, 1.0, 2.2), (3, 1.0, 0.7, 0.5, 1.7, 1.8), (1, 2.0, 1.0, 5.0, 1.0, 2.2)):
+            T.set_bloom(thr, strength, mips, fall); T.set_tonemap(exp, gam)
+            T.post_process()
+            ldr = T.get_ldr(); bloom = T.get_bloom()
+            pc = orc.default_post_config(Exposure=exp, Gamma=gam, BloomThreshold=thr, BloomStrength=strength, FalloffRange=fall, MipCount=mips)
+            rl, rb = orc.post_process(hdr, pc, want_bloom=True)
+            assert np.allclose(bloom[..., :3], rb[..., :3], rtol=2e-6, atol=1e-6)
+            d = np.abs(ldr.astype(int) - rl.astype(int))
+            assert d.max() <= 1 and (d > 0).mean() < 2e-3      # 8-bit rounding ties only
+    T.save_png(str(tmp_path / "o.png"))
+    assert np.array_equal(pt.decode_image(str(tmp_path / "o.png")), ldr)   # Editor::SaveToFile round trip
+
+
+def test_errors_are_codes_not_aborts(pt):
+    T = pt.PathTracer(0)
+    with pytest.raises(pt.B200ptError) as e:
+        T.path_trace(1, 0)
+    assert e.value.code == pt.ERR_NO_SCENE
+    with pytest.raises(pt.B200ptError) as e:
+        T.set_scene_file("/nonexistent/scene.gltf")
+    assert e.value.code == pt.ERR_INIT_FAILED
+    T = util.product_tracer("cornell_box", 32, 32)
+    with pytest.raises(pt.B200ptError):
+        T.set_material(99, T.get_material(0))
+    cfg = T.get_config(); cfg.ScreenChunkCount = 0
+    with pytest.raises(pt.B200ptError):
+        T.set_config(cfg)
+
+
+@pytest.mark.skipif(not util.HAVE_REF, reason="reference assets not present on this box")
+def test_set_scene_file_equals_set_scene_arrays(pt):
+    import os
+    T = pt.PathTracer(0); T.set_scene_file(os.path.join(util.REF_ASSETS, "CornellBox.gltf"))
+    raw, _, _ = util.env_small(); T.set_env_map(raw); T.set_luts(*util.luts())
+    assert T.size() == (1920, 1080)                           # W = (uint)(1080 * aspect) (PathTracer.cpp:509-511)
+    cfg = T.get_config(); cfg.MaxDepth = 5; T.set_config(cfg); T.resize(64, 36); T.path_trace(2, 1)
+    T2 = util.product_tracer("cornell_box", 64, 36, MaxDepth=5); T2.path_trace(2, 1)
+    assert np.array_equal(T.get_hdr(), T2.get_hdr())

@@ -1,0 +1,236 @@
+"""CPU-side tests of the product's host logic and C-ABI surface (no kernel is launched here)."""
+import ctypes as C
+import json
+import os
+import numpy as np
+import pytest
+
+import util
+from util import orc, gltf_ref
+import vpt_b200 as pt
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = pt.lib()
+    names = pt.declared_symbols()
+    assert len(names) >= 45
+    for n in names:
+        assert hasattr(L, n), f"include/b200pt.h declares {n} but libb200pt.so does not export it"
+    assert b"sm_100a" in L.b200pt_version()
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    r = pt.lib().b200pt_create(0, C.byref(h))
+    assert r == pt.ERR_NO_DEVICE and not h.value          # fails loudly: there is no CPU rendering path
+    with pytest.raises(pt.B200ptError):
+        pt.PathTracer(0)
+
+
+def test_null_arguments_are_rejected_not_crashed():
+    L = pt.lib()
+    assert L.b200pt_create(0, None) == pt.ERR_WRONG_ARGUMENTS
+    assert L.b200pt_destroy(None) == pt.ERR_WRONG_ARGUMENTS
+    assert L.b200pt_path_trace(None, 1, 0, None) == pt.ERR_WRONG_ARGUMENTS
+    assert L.b200pt_set_scene_file(None, b"x") == pt.ERR_WRONG_ARGUMENTS
+    assert L.b200pt_add_volume(None, None) == pt.ERR_NOT_IMPLEMENTED      # volumes: out of scope
+    w, h, p = C.c_uint32(), C.c_uint32(), C.c_void_p()
+    assert L.b200pt_decode_image_file(b"/nonexistent.png", C.byref(w), C.byref(h), C.byref(p)) == pt.ERR_INIT_FAILED
+
+
+def test_default_config_matches_reference_defaults():
+    c = pt.default_config()                      # PathTracer/PathTracer.h:197-233
+    assert (c.SamplesPerFrame, c.MaxSamplesAccumulated, c.MaxDepth, c.MaxLuminance, c.FocusDistance, c.DepthOfFieldStrength) == (1, 5000, 200, 500.0, 1.0, 0.0)
+    assert (c.EnableSkyMIS, c.EnableMeshMIS, c.ShowEnvMapDirectly, c.UseOnlyGeometryNormals, c.UseEnergyCompensation, c.FurnaceTestMode) == (1, 1, 1, 0, 1, 0)
+    assert (c.SkyIntensity, c.ScreenChunkCount, c.EmissiveMeshSamplingPDFBias) == (1.0, 1, 0.0)
+    o = orc.default_config()
+    assert (o.SampleCount, o.MaxDepth, o.MaxLuminance) == (c.SamplesPerFrame, c.MaxDepth, c.MaxLuminance)
+    assert C.sizeof(pt.Material) == 112 and C.sizeof(pt.Instance) == 72
+
+
+def test_png_roundtrip_and_decoder_vs_pil(tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    p = str(tmp_path / "a.png")
+    pt.write_png(p, img)                                       # Editor::SaveToFile path
+    assert np.array_equal(np.asarray(Image.open(p).convert("RGBA")), img)
+    assert np.array_equal(pt.decode_image(p), img)
+    # PIL-written variants: RGB, grey, palette, 16-bit, grey+alpha
+    for mode, arr in [("RGB", img[..., :3]), ("L", img[..., 0]), ("LA", img[..., :2])]:
+        q = str(tmp_path / f"{mode}.png"); Image.fromarray(arr, mode).save(q)
+        assert np.array_equal(pt.decode_image(q), np.asarray(Image.open(q).convert("RGBA")))
+    q = str(tmp_path / "pal.png"); Image.fromarray(img[..., :3], "RGB").quantize(17).save(q)
+    assert np.array_equal(pt.decode_image(q), np.asarray(Image.open(q).convert("RGBA")))
+    q = str(tmp_path / "i16.png"); Image.fromarray((img[..., 0].astype(np.uint16) << 8) | 7, "I;16").save(q)
+    assert np.array_equal(pt.decode_image(q)[..., 0], img[..., 0])          # 16 -> 8 keeps the high byte
+
+
+def test_jpeg_decoder_close_to_libjpeg(tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(1)
+    yy, xx = np.mgrid[0:97, 0:131]
+    base = np.stack([128 + 100 * np.sin(xx / 17.0), 128 + 100 * np.cos(yy / 11.0), 128 + 60 * np.sin((xx + yy) / 23.0)], -1)
+    img = np.clip(base + rng.normal(0, 6, base.shape), 0, 255).astype(np.uint8)
+    for sub, name in [(2, "420"), (0, "444"), (1, "422")]:
+        q = str(tmp_path / f"j{name}.jpg"); Image.fromarray(img, "RGB").save(q, quality=92, subsampling=sub)
+        mine = pt.decode_image(q).astype(int); ref = np.asarray(Image.open(q).convert("RGBA")).astype(int)
+        assert mine.shape == ref.shape
+        d = np.abs(mine - ref)
+        assert d.max() <= 6 and d.mean() < 0.8, (name, d.max(), d.mean())   # different IDCT / up-sampling rounding only
+    q = str(tmp_path / "grey.jpg"); Image.fromarray(img[..., 0], "L").save(q, quality=90)
+    assert np.abs(pt.decode_image(q).astype(int) - np.asarray(Image.open(q).convert("RGBA")).astype(int)).max() <= 2
+
+
+@pytest.mark.skipif(not util.HAVE_REF, reason="reference assets not present on this box")
+def test_decoders_on_shipped_assets():
+    from PIL import Image
+    for f in ("VikingRoom.png", "BreakfastRoom/tiles.png"):
+        assert np.array_equal(pt.decode_image(os.path.join(util.REF_ASSETS, f)), np.asarray(Image.open(os.path.join(util.REF_ASSETS, f)).convert("RGBA")))
+    f = os.path.join(util.REF_ASSETS, "BreakfastRoom/picture3.jpg")
+    d = np.abs(pt.decode_image(f).astype(int) - np.asarray(Image.open(f).convert("RGBA")).astype(int))
+    assert d.max() <= 8 and d.mean() < 1.0
+    hdr = pt.decode_hdr(os.path.join(util.REF_ASSETS, "meadow_2_4k.hdr"))
+    assert hdr.shape == (2048, 4096, 4) and hdr[..., :3].max() == 159744.0 and np.all(hdr[..., 3] == 1.0)
+    assert np.array_equal(hdr, orc.load_hdr(os.path.join(util.REF_ASSETS, "meadow_2_4k.hdr")))
+
+
+def _write_rgbe(path, rgb):
+    """minimal RLE Radiance writer for the decoder test"""
+    h, w, _ = rgb.shape
+    m = rgb.max(-1); e = np.where(m > 1e-32, np.floor(np.log2(np.maximum(m, 1e-38))) + 1, 0)
+    scale = np.where(m > 1e-32, 256.0 / (2.0 ** e), 0)
+    out = np.zeros((h, w, 4), np.uint8); out[..., :3] = np.clip(rgb * scale[..., None], 0, 255).astype(np.uint8); out[..., 3] = np.where(m > 1e-32, e + 128, 0)
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (h, w))
+        for y in range(h):
+            f.write(bytes([2, 2, w >> 8, w & 255]))
+            for c in range(4):
+                row = out[y, :, c]; i = 0
+                while i < w:
+                    run = 1
+                    while i + run < w and run < 127 and row[i + run] == row[i]: run += 1
+                    if run >= 4: f.write(bytes([128 + run, row[i]])); i += run
+                    else:
+                        j = i
+                        while j < w and j - i < 128 and not (j + 3 < w and row[j] == row[j + 1] == row[j + 2] == row[j + 3]): j += 1
+                        j = max(j, i + 1); f.write(bytes([j - i]) + bytes(row[i:j])); i = j
+    return out
+
+
+def test_hdr_decoder(tmp_path):
+    rng = np.random.default_rng(2)
+    rgb = (np.exp(rng.normal(0, 2, (9, 40, 3))) * (rng.random((9, 40, 1)) > 0.1)).astype(np.float32)
+    rgb[:, 10:30] = rgb[:, 10:11]                                  # runs
+    p = str(tmp_path / "t.hdr"); enc = _write_rgbe(p, rgb)
+    got = pt.decode_hdr(p)
+    exp = np.ones((9, 40, 4), np.float32)
+    exp[..., :3] = enc[..., :3].astype(np.float32) * np.where(enc[..., 3:] != 0, np.ldexp(np.float32(1.0), enc[..., 3:].astype(int) - 136), 0).astype(np.float32)
+    assert np.array_equal(got, exp) and np.array_equal(got, orc.load_hdr(p))
+
+
+def test_env_alias_table_bit_exact_vs_oracle():
+    for seed, (w, h) in [(3, (64, 32)), (4, (128, 64)), (5, (33, 17))]:
+        raw = gltf_ref.synthetic_env(w, h, seed)
+        a_env, a_alias, a_sum = orc.build_env_alias(raw)
+        b_env, b_alias, b_sum = pt.build_env_alias(raw)
+        assert np.array_equal(a_env, b_env) and np.array_equal(a_alias, b_alias) and np.float32(a_sum) == np.float32(b_sum)
+    z = np.load(os.path.join(util.GOLDEN, "env_alias_kat.npz"))
+    env2, alias2, total2 = pt.build_env_alias(z["env"])
+    assert np.array_equal(env2, z["env_pdf"]) and np.array_equal(alias2.view(np.uint32).reshape(-1, 2), z["alias"])
+
+
+def test_camera_round_trip_bit_exact_vs_oracle():
+    for name in ("cornell_box", "cornell_box_glass", "viking_room", "breakfast_room"):
+        sc = util.scene_dict(name)
+        a = orc.camera_from_view(sc["camera_view"], sc["aspect"]); b = pt.camera_from_view(sc["camera_view"], sc["aspect"])
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    vi, pi = pt.camera_from_view(util.scene_dict("cornell_box")["camera_view"], 16 / 9)
+    # Q2: 45 degree vertical fov regardless of the glTF yfov: 1/P11 = tan(22.5 deg)
+    assert abs(pi[5] - np.tan(np.radians(22.5))) < 1e-6 and abs(pi[0] - 16 / 9 * np.tan(np.radians(22.5))) < 1e-6
+
+
+def test_bloom_mips_and_partition_helpers():
+    assert pt.bloom_mip_sizes(3840, 2160) == orc.bloom_mip_sizes(3840, 2160)
+    assert pt.bloom_mip_sizes(1920, 1080) == orc.bloom_mip_sizes(1920, 1080)
+    H = 1080
+    for world in (1, 2, 4, 8):
+        rows = [pt.partition_rows(H, r, world, 16) for r in range(world)]
+        allr = np.sort(np.concatenate(rows))
+        assert np.array_equal(allr, np.arange(H))                       # disjoint cover
+        assert max(len(r) for r in rows) - min(len(r) for r in rows) <= 16
+        for r in range(world):
+            assert np.all((rows[r] // 16) % world == r)
+
+
+def _compare_loader(path):
+    a = gltf_ref.load_gltf(path); b = pt.load_gltf(path)
+    assert len(a["meshes"]) == len(b["meshes"]) and len(a["instances"]) == len(b["instances"]) and len(a["textures"]) == len(b["textures"])
+    for (va, ia), (vb, ib) in zip(a["meshes"], b["meshes"]):
+        assert np.array_equal(ia, ib)
+        assert np.array_equal(va["pos"], vb["pos"]) and np.array_equal(va["uv"], vb["uv"])
+        assert np.allclose(va["nrm"], vb["nrm"], rtol=0, atol=1.2e-7)
+    assert np.array_equal(np.frombuffer(a["materials"].tobytes(), np.uint8), b["materials_bytes"])
+    for ta, tb in zip(a["textures"], b["textures"]):
+        assert ta.shape == tb.shape
+        d = np.abs(ta.astype(int) - tb.astype(int)); assert d.max() <= 8          # JPEG only; PNG is exact
+        if ta.shape[0] == 1 or path.endswith("VikingRoom.gltf"): assert d.max() == 0
+    for (xa, ma, ka), (xb, mb, kb) in zip(a["instances"], b["instances"]):
+        assert (ma, ka) == (mb, kb) and np.allclose(xa, xb, rtol=1e-6, atol=1e-6)
+    assert np.allclose(a["camera_view"], b["camera_view"], rtol=1e-6, atol=1e-6) and abs(float(a["aspect"]) - float(b["aspect"])) < 1e-7
+
+
+@pytest.mark.skipif(not util.HAVE_REF, reason="reference assets not present on this box")
+@pytest.mark.parametrize("name", ["CornellBox", "CornellBoxGlass", "VikingRoom", "BreakfastRoom"])
+def test_cpp_gltf_loader_matches_oracle_loader_on_shipped_scenes(name):
+    _compare_loader(os.path.join(util.REF_ASSETS, name + ".gltf"))
+
+
+def test_cpp_gltf_loader_on_a_synthetic_scene(tmp_path):
+    """Self-authored glTF exercising matrices, TRS nesting, all material extensions, all texture slots, u8/u16/u32 indices."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.5]], np.float32)
+    nrm = np.array([[0, 0, 2], [0, 0, 1], [0.1, 0, 1], [0, 0.3, 1]], np.float32)
+    uv = rng.random((4, 2)).astype(np.float32)
+    i8 = np.array([0, 1, 2, 1, 3, 2], np.uint8); i16 = i8.astype(np.uint16); i32 = i8.astype(np.uint32)
+    blob = b""; views = []; accs = []
+    def add(arr, comp, typ):
+        nonlocal blob
+        while len(blob) % 4: blob += b"\0"
+        views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": arr.nbytes}); blob += arr.tobytes()
+        accs.append({"bufferView": len(views) - 1, "componentType": comp, "count": len(arr), "type": typ}); return len(accs) - 1
+    aP, aN, aT = add(pos, 5126, "VEC3"), add(nrm, 5126, "VEC3"), add(uv, 5126, "VEC2")
+    a8, a16, a32 = add(i8, 5121, "SCALAR"), add(i16, 5123, "SCALAR"), add(i32, 5125, "SCALAR")
+    (tmp_path / "s.bin").write_bytes(blob)
+    for n in ("base", "nrm", "mr", "em"):
+        Image.fromarray(rng.integers(0, 256, (5, 7, 3), dtype=np.uint8), "RGB").save(tmp_path / f"{n}.png")
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0, 3]}],
+         "nodes": [{"children": [1, 2], "translation": [1, 2, 3], "rotation": [0.1825742, 0.3651484, 0.5477226, 0.7302967], "scale": [1, 2, 0.5]},
+                   {"mesh": 0, "matrix": [1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0.5, 0.25, -2, 1]},
+                   {"camera": 0, "translation": [0, 1, 8], "rotation": [0, 0.0871557, 0, 0.9961947]},
+                   {"mesh": 1, "scale": [2, 2, 2]}],
+         "cameras": [{"type": "perspective", "perspective": {"aspectRatio": 1.5, "yfov": 0.6, "znear": 0.1}}],
+         "meshes": [{"primitives": [{"attributes": {"POSITION": aP, "NORMAL": aN, "TEXCOORD_0": aT}, "indices": a8, "material": 0},
+                                    {"attributes": {"POSITION": aP, "NORMAL": aN}, "indices": a16, "material": 1}]},
+                    {"primitives": [{"attributes": {"POSITION": aP, "NORMAL": aN, "TEXCOORD_0": aT}, "indices": a32}]}],
+         "materials": [{"name": "full", "emissiveFactor": [0.5, 0.25, 1.0], "normalTexture": {"index": 1}, "emissiveTexture": {"index": 3},
+                        "pbrMetallicRoughness": {"baseColorFactor": [0.1, 0.2, 0.3, 1], "metallicFactor": 0.25, "roughnessFactor": 0.6, "baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 2}},
+                        "extensions": {"KHR_materials_emissive_strength": {"emissiveStrength": 7.5}, "KHR_materials_ior": {"ior": 1.33}, "KHR_materials_transmission": {"transmissionFactor": 0.75},
+                                       "KHR_materials_specular": {"specularColorFactor": [0.9, 0.8, 0.7]}, "KHR_materials_anisotropy": {"anisotropyStrength": 0.4, "anisotropyRotation": 0.5}}},
+                       {"name": "defaults"}],
+         "textures": [{"source": 0}, {"source": 1}, {"source": 2}, {"source": 3}],
+         "images": [{"uri": "base.png"}, {"uri": "nrm.png"}, {"uri": "mr.png"}, {"uri": "em.png"}],
+         "accessors": accs, "bufferViews": views, "buffers": [{"uri": "s.bin", "byteLength": len(blob)}]}
+    p = str(tmp_path / "s.gltf"); open(p, "w").write(json.dumps(g))
+    _compare_loader(p)
+    b = pt.load_gltf(p)
+    m = np.frombuffer(b["materials_bytes"].tobytes(), gltf_ref.MATERIAL_DTYPE)
+    assert len(m) == 3 and np.allclose(m["EmissiveColor"][0], [3.75, 1.875, 7.5]) and m["Metallic"][1] == 1.0 and m["IOR"][1] == 1.5   # default material appended last
+    assert m["RoughnessTextureIndex"][0] == m["MetallicTextureIndex"][0] and b["textures"][m["RoughnessTextureIndex"][0]].shape == (5, 7, 1)   # Q8
+    assert len(b["instances"]) == 3 and abs(float(b["aspect"]) - 1.5) < 1e-7
+    # Y flip: det of the instance transform is negative
+    assert np.linalg.det(b["instances"][2][0].reshape(4, 4).T[:3, :3]) < 0

@@ -1,0 +1,382 @@
+"""ctypes binding of the product's C-ABI (libb200pt.so, include/b200pt.h).
+
+This is only a test/bench harness convenience: the product is the C-ABI library itself.  The class mirrors the
+reference's `PathTracer` + `PostProcessor` pair (PathTracer/PathTracer.h:83-183, PathTracer/PostProcessor.h:25-33):
+same verbs, same argument meaning.  There is NO fallback: if the CUDA library is missing or no GPU is present,
+loading / creating a handle raises.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+_LIB = None
+
+OK = 0
+ERR_NOT_IMPLEMENTED = -15001
+ERR_NO_SCENE = -15002
+ERR_WRONG_ARGUMENTS = -15000
+ERR_NO_DEVICE = -15004
+ERR_INIT_FAILED = -3
+
+
+class B200ptError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200pt error {code}: {msg}")
+        self.code = code
+
+
+class Material(C.Structure):
+    _fields_ = [("BaseColor", C.c_float * 3), ("EmissiveColor", C.c_float * 3), ("SpecularColor", C.c_float * 3),
+                ("MediumColor", C.c_float * 3), ("MediumEmissiveColor", C.c_float * 3),
+                ("Metallic", C.c_float), ("Roughness", C.c_float), ("IOR", C.c_float), ("Transmission", C.c_float),
+                ("Anisotropy", C.c_float), ("AnisotropyRotation", C.c_float), ("MediumDensity", C.c_float), ("MediumAnisotropy", C.c_float),
+                ("BaseColorTextureIndex", C.c_uint32), ("NormalTextureIndex", C.c_uint32), ("RoughnessTextureIndex", C.c_uint32),
+                ("MetallicTextureIndex", C.c_uint32), ("EmissiveTextureIndex", C.c_uint32)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("indices", C.c_void_p), ("vertex_count", C.c_uint32), ("index_count", C.c_uint32)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("Transform", C.c_float * 16), ("MeshIndex", C.c_uint32), ("MaterialIndex", C.c_uint32)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint32), ("_pad", C.c_uint32), ("data", C.c_void_p)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("meshes", C.c_void_p), ("mesh_count", C.c_uint32), ("_p0", C.c_uint32),
+                ("materials", C.c_void_p), ("material_count", C.c_uint32), ("_p1", C.c_uint32),
+                ("textures", C.c_void_p), ("texture_count", C.c_uint32), ("_p2", C.c_uint32),
+                ("instances", C.c_void_p), ("instance_count", C.c_uint32), ("_p3", C.c_uint32),
+                ("camera_view", C.c_float * 16), ("camera_aspect", C.c_float), ("_p4", C.c_uint32)]
+
+
+class Config(C.Structure):
+    _fields_ = [("SamplesPerFrame", C.c_uint32), ("MaxDepth", C.c_uint32), ("MaxLuminance", C.c_float), ("FocusDistance", C.c_float),
+                ("DepthOfFieldStrength", C.c_float), ("SkyRotationAzimuth", C.c_float), ("SkyRotationAltitude", C.c_float),
+                ("SkyIntensity", C.c_float), ("EmissiveMeshSamplingPDFBias", C.c_float), ("ScreenChunkCount", C.c_uint32),
+                ("EnableSkyMIS", C.c_uint32), ("EnableMeshMIS", C.c_uint32), ("ShowEnvMapDirectly", C.c_uint32),
+                ("UseOnlyGeometryNormals", C.c_uint32), ("UseEnergyCompensation", C.c_uint32), ("FurnaceTestMode", C.c_uint32),
+                ("MaxSamplesAccumulated", C.c_uint32), ("FramesInFlight", C.c_uint32)]
+
+
+class Tonemap(C.Structure):
+    _fields_ = [("Exposure", C.c_float), ("Gamma", C.c_float)]
+
+
+class Bloom(C.Structure):
+    _fields_ = [("BloomThreshold", C.c_float), ("BloomStrength", C.c_float), ("MipCount", C.c_uint32), ("FalloffRange", C.c_float)]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("paths", "extend_rays", "shade_invocations", "surface_hits", "misses", "shadow_rays", "medium_events", "kernel_launches")] + \
+               [(n, C.c_float) for n in ("ms_total", "ms_raygen", "ms_extend", "ms_shade", "ms_connect", "ms_resolve")] + \
+               [("waves", C.c_uint32), ("bounces", C.c_uint32)]
+
+
+def build(force=False):
+    """Compile libb200pt.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))] + [os.path.join(_HERE, "..", "include", "b200pt.h")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-j8", "-s"])
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        L.b200pt_version.restype = C.c_char_p
+        L.b200pt_last_error.restype = C.c_char_p; L.b200pt_last_error.argtypes = [C.c_void_p]
+        L.b200pt_partition_global_row.restype = C.c_uint32; L.b200pt_partition_global_row.argtypes = [C.c_uint32] * 4
+        L.b200pt_partition_local_row_count.restype = C.c_uint32; L.b200pt_partition_local_row_count.argtypes = [C.c_uint32] * 4
+        L.b200pt_free.argtypes = [C.c_void_p]; L.b200pt_free.restype = None
+        sig = {
+            "b200pt_create": [C.c_int32, C.POINTER(C.c_void_p)], "b200pt_destroy": [C.c_void_p],
+            "b200pt_set_scene_file": [C.c_void_p, C.c_char_p], "b200pt_set_scene_arrays": [C.c_void_p, C.POINTER(SceneDesc)],
+            "b200pt_set_env_map_file": [C.c_void_p, C.c_char_p], "b200pt_set_env_map": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p],
+            "b200pt_set_luts": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], "b200pt_set_luts_dir": [C.c_void_p, C.c_char_p],
+            "b200pt_default_config": [C.POINTER(Config)], "b200pt_set_config": [C.c_void_p, C.POINTER(Config)], "b200pt_get_config": [C.c_void_p, C.POINTER(Config)],
+            "b200pt_material_count": [C.c_void_p, C.POINTER(C.c_uint32)], "b200pt_get_material": [C.c_void_p, C.c_uint32, C.POINTER(Material)],
+            "b200pt_set_material": [C.c_void_p, C.c_uint32, C.POINTER(Material)], "b200pt_get_material_name": [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32],
+            "b200pt_set_camera": [C.c_void_p, C.c_void_p, C.c_void_p], "b200pt_get_camera": [C.c_void_p, C.c_void_p, C.c_void_p],
+            "b200pt_camera_from_view": [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p],
+            "b200pt_resize": [C.c_void_p, C.c_uint32, C.c_uint32], "b200pt_get_size": [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
+            "b200pt_reset": [C.c_void_p], "b200pt_add_volume": [C.c_void_p, C.c_void_p],
+            "b200pt_set_partition": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32], "b200pt_local_rows": [C.c_void_p, C.POINTER(C.c_uint32)],
+            "b200pt_path_trace": [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)], "b200pt_samples_accumulated": [C.c_void_p, C.POINTER(C.c_uint32)],
+            "b200pt_synchronize": [C.c_void_p], "b200pt_set_stream": [C.c_void_p, C.c_void_p], "b200pt_set_profiling": [C.c_void_p, C.c_int32], "b200pt_get_hdr": [C.c_void_p, C.c_void_p, C.c_int32], "b200pt_hdr_device_ptr": [C.c_void_p, C.POINTER(C.c_void_p)],
+            "b200pt_set_hdr": [C.c_void_p, C.c_void_p, C.c_int32], "b200pt_get_counters": [C.c_void_p, C.POINTER(Counters)],
+            "b200pt_post_set_tonemap": [C.c_void_p, C.POINTER(Tonemap)], "b200pt_post_set_bloom": [C.c_void_p, C.POINTER(Bloom)],
+            "b200pt_post_process": [C.c_void_p], "b200pt_get_ldr": [C.c_void_p, C.c_void_p, C.c_int32], "b200pt_get_bloom": [C.c_void_p, C.c_void_p],
+            "b200pt_bloom_mip_sizes": [C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)], "b200pt_save_png": [C.c_void_p, C.c_char_p],
+            "b200pt_trace_closest": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+            "b200pt_scene_stats": [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4,
+            "b200pt_decode_image_file": [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)],
+            "b200pt_decode_hdr_file": [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)],
+            "b200pt_write_png": [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p],
+            "b200pt_build_env_alias": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_float)],
+            "b200pt_load_gltf": [C.c_char_p, C.POINTER(C.POINTER(SceneDesc))], "b200pt_free_scene": [C.POINTER(SceneDesc)],
+        }
+        for name, args in sig.items():
+            fn = getattr(L, name); fn.restype = C.c_int32; fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def declared_symbols():
+    """Every function name declared in include/b200pt.h."""
+    import re
+    txt = open(os.path.join(_HERE, "..", "include", "b200pt.h")).read()
+    return sorted(set(re.findall(r"\b(b200pt_[a-z0-9_]+)\s*\(", txt)))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_config(**kw):
+    c = Config(); lib().b200pt_default_config(C.byref(c))
+    for k, v in kw.items(): setattr(c, k, v)
+    return c
+
+
+def camera_from_view(view16, aspect):
+    view16 = np.ascontiguousarray(view16, np.float32); vi = np.zeros(16, np.float32); pi = np.zeros(16, np.float32)
+    r = lib().b200pt_camera_from_view(_p(view16), C.c_float(float(aspect)), _p(vi), _p(pi))
+    if r != OK: raise B200ptError(r, "camera_from_view")
+    return vi, pi
+
+
+def partition_rows(H, rank, world, band):
+    n = lib().b200pt_partition_local_row_count(H, rank, world, band)
+    return np.array([lib().b200pt_partition_global_row(i, rank, world, band) for i in range(n)], dtype=np.int64)
+
+
+def decode_image(path):
+    w, h, p = C.c_uint32(), C.c_uint32(), C.c_void_p()
+    r = lib().b200pt_decode_image_file(path.encode(), C.byref(w), C.byref(h), C.byref(p))
+    if r != OK: raise B200ptError(r, lib().b200pt_last_error(None).decode())
+    a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 4)).copy()
+    lib().b200pt_free(p)
+    return a
+
+
+def decode_hdr(path):
+    w, h, p = C.c_uint32(), C.c_uint32(), C.c_void_p()
+    r = lib().b200pt_decode_hdr_file(path.encode(), C.byref(w), C.byref(h), C.byref(p))
+    if r != OK: raise B200ptError(r, lib().b200pt_last_error(None).decode())
+    a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(h.value, w.value, 4)).copy()
+    lib().b200pt_free(p)
+    return a
+
+
+def write_png(path, rgba):
+    rgba = np.ascontiguousarray(rgba, np.uint8)
+    r = lib().b200pt_write_png(path.encode(), rgba.shape[1], rgba.shape[0], _p(rgba))
+    if r != OK: raise B200ptError(r, "write_png")
+
+
+def build_env_alias(rgba):
+    rgba = np.ascontiguousarray(rgba, np.float32).copy(); h, w = rgba.shape[:2]
+    alias = np.zeros(h * w, dtype=np.dtype([("Alias", "<u4"), ("Importance", "<f4")]))
+    s = C.c_float()
+    r = lib().b200pt_build_env_alias(_p(rgba), w, h, _p(alias), C.byref(s))
+    if r != OK: raise B200ptError(r, "build_env_alias")
+    return rgba, alias, s.value
+
+
+def bloom_mip_sizes(W, H):
+    wh = np.zeros(20, np.uint32); n = C.c_uint32()
+    lib().b200pt_bloom_mip_sizes(W, H, _p(wh), C.byref(n))
+    return [(int(wh[2 * i]), int(wh[2 * i + 1])) for i in range(n.value)]
+
+
+def load_gltf(path):
+    """C++ loader -> python dict in the same shape as oracle.gltf_ref.load_gltf (for loader parity tests)."""
+    pd = C.POINTER(SceneDesc)()
+    r = lib().b200pt_load_gltf(path.encode(), C.byref(pd))
+    if r != OK: raise B200ptError(r, lib().b200pt_last_error(None).decode())
+    d = pd.contents
+    vdt = np.dtype([("pos", "<f4", 3), ("nrm", "<f4", 3), ("uv", "<f4", 2)])
+    meshes = []
+    ms = C.cast(d.meshes, C.POINTER(Mesh))
+    for i in range(d.mesh_count):
+        v = np.ctypeslib.as_array(C.cast(ms[i].vertices, C.POINTER(C.c_float)), shape=(ms[i].vertex_count, 8)).copy().view(vdt).reshape(-1)
+        ix = np.ctypeslib.as_array(C.cast(ms[i].indices, C.POINTER(C.c_uint32)), shape=(ms[i].index_count,)).copy()
+        meshes.append((v, ix))
+    mats = np.ctypeslib.as_array(C.cast(d.materials, C.POINTER(C.c_uint8)), shape=(d.material_count * 112,)).copy()
+    ts = C.cast(d.textures, C.POINTER(Texture)); textures = []
+    for i in range(d.texture_count):
+        textures.append(np.ctypeslib.as_array(C.cast(ts[i].data, C.POINTER(C.c_uint8)), shape=(ts[i].height, ts[i].width, ts[i].channels)).copy())
+    ins = C.cast(d.instances, C.POINTER(Instance)); instances = []
+    for i in range(d.instance_count):
+        instances.append((np.array(list(ins[i].Transform), np.float32), int(ins[i].MeshIndex), int(ins[i].MaterialIndex)))
+    out = dict(meshes=meshes, materials_bytes=mats, textures=textures, instances=instances,
+               camera_view=np.array(list(d.camera_view), np.float32), aspect=np.float32(d.camera_aspect))
+    lib().b200pt_free_scene(pd)
+    return out
+
+
+class PathTracer:
+    """One GPU: the reference's PathTracer + PostProcessor behind the C-ABI."""
+
+    def __init__(self, device=0):
+        self.L = lib(); self.h = C.c_void_p()
+        r = self.L.b200pt_create(device, C.byref(self.h))
+        if r != OK: raise B200ptError(r, self.L.b200pt_last_error(None).decode())
+        self._keep = []
+
+    def close(self):
+        if self.h: self.L.b200pt_destroy(self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+    def _ck(self, r):
+        if r != OK: raise B200ptError(r, self.L.b200pt_last_error(self.h).decode())
+
+    # ---- PathTracer::SetScene
+    def set_scene_file(self, path): self._ck(self.L.b200pt_set_scene_file(self.h, path.encode()))
+
+    def set_scene(self, sc):
+        """sc: dict as produced by oracle.gltf_ref.load_gltf / load_scene_npz."""
+        keep = []
+        meshes = (Mesh * len(sc["meshes"]))()
+        for i, (v, idx) in enumerate(sc["meshes"]):
+            v = np.ascontiguousarray(v); idx = np.ascontiguousarray(idx, np.uint32); keep += [v, idx]
+            meshes[i] = Mesh(v.ctypes.data, idx.ctypes.data, len(v), len(idx))
+        mats = np.ascontiguousarray(sc["materials"]); keep.append(mats)
+        texs = (Texture * len(sc["textures"]))()
+        for i, t in enumerate(sc["textures"]):
+            t = np.ascontiguousarray(t, np.uint8); keep.append(t)
+            texs[i] = Texture(t.shape[1], t.shape[0], t.shape[2], 0, t.ctypes.data)
+        insts = (Instance * len(sc["instances"]))()
+        for i, (xf, m, mat) in enumerate(sc["instances"]):
+            insts[i].MeshIndex = m; insts[i].MaterialIndex = mat
+            for k in range(16): insts[i].Transform[k] = float(xf[k])
+        d = SceneDesc()
+        d.meshes = C.addressof(meshes); d.mesh_count = len(sc["meshes"])
+        d.materials = mats.ctypes.data; d.material_count = len(mats)
+        d.textures = C.addressof(texs); d.texture_count = len(sc["textures"])
+        d.instances = C.addressof(insts); d.instance_count = len(sc["instances"])
+        for k in range(16): d.camera_view[k] = float(sc["camera_view"][k])
+        d.camera_aspect = float(sc["aspect"])
+        self._ck(self.L.b200pt_set_scene_arrays(self.h, C.byref(d)))
+
+    def set_env_map(self, rgba):
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        self._ck(self.L.b200pt_set_env_map(self.h, rgba.shape[1], rgba.shape[0], _p(rgba)))
+
+    def set_env_map_file(self, path): self._ck(self.L.b200pt_set_env_map_file(self.h, path.encode()))
+
+    def set_luts(self, refl, rout, rin):
+        a, b, c = [np.ascontiguousarray(x, np.float32) for x in (refl, rout, rin)]
+        self._ck(self.L.b200pt_set_luts(self.h, _p(a), _p(b), _p(c)))
+
+    def set_luts_dir(self, d): self._ck(self.L.b200pt_set_luts_dir(self.h, d.encode()))
+
+    # ---- parameters
+    def set_config(self, cfg): self._ck(self.L.b200pt_set_config(self.h, C.byref(cfg)))
+
+    def get_config(self):
+        c = Config(); self._ck(self.L.b200pt_get_config(self.h, C.byref(c))); return c
+
+    def material_count(self):
+        n = C.c_uint32(); self._ck(self.L.b200pt_material_count(self.h, C.byref(n))); return n.value
+
+    def get_material(self, i):
+        m = Material(); self._ck(self.L.b200pt_get_material(self.h, i, C.byref(m))); return m
+
+    def set_material(self, i, m): self._ck(self.L.b200pt_set_material(self.h, i, C.byref(m)))
+
+    def get_material_name(self, i):
+        b = C.create_string_buffer(256); self._ck(self.L.b200pt_get_material_name(self.h, i, b, 256)); return b.value.decode()
+
+    def set_camera(self, vi, pi):
+        vi = np.ascontiguousarray(vi, np.float32); pi = np.ascontiguousarray(pi, np.float32)
+        self._ck(self.L.b200pt_set_camera(self.h, _p(vi), _p(pi)))
+
+    def get_camera(self):
+        vi = np.zeros(16, np.float32); pi = np.zeros(16, np.float32)
+        self._ck(self.L.b200pt_get_camera(self.h, _p(vi), _p(pi))); return vi, pi
+
+    def resize(self, w, h): self._ck(self.L.b200pt_resize(self.h, w, h))
+
+    def size(self):
+        w, h = C.c_uint32(), C.c_uint32(); self._ck(self.L.b200pt_get_size(self.h, C.byref(w), C.byref(h))); return w.value, h.value
+
+    def reset(self): self._ck(self.L.b200pt_reset(self.h))
+
+    def set_partition(self, rank, world, band): self._ck(self.L.b200pt_set_partition(self.h, rank, world, band))
+
+    def local_rows(self):
+        n = C.c_uint32(); self._ck(self.L.b200pt_local_rows(self.h, C.byref(n))); return n.value
+
+    # ---- hot path
+    def path_trace(self, dispatches, base_seed):
+        done = C.c_int32(); self._ck(self.L.b200pt_path_trace(self.h, dispatches, base_seed & 0xFFFFFFFF, C.byref(done))); return bool(done.value)
+
+    def samples_accumulated(self):
+        n = C.c_uint32(); self._ck(self.L.b200pt_samples_accumulated(self.h, C.byref(n))); return n.value
+
+    def synchronize(self): self._ck(self.L.b200pt_synchronize(self.h))
+
+    def set_stream(self, cuda_stream_ptr): self._ck(self.L.b200pt_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_profiling(self, on): self._ck(self.L.b200pt_set_profiling(self.h, 1 if on else 0))
+
+    def get_hdr(self, out=None):
+        w, h = self.size(); rows = self.local_rows()
+        if out is None: out = np.empty((rows, w, 4), np.float32)
+        self._ck(self.L.b200pt_get_hdr(self.h, _p(out), 0)); return out
+
+    def get_hdr_into_device(self, ptr): self._ck(self.L.b200pt_get_hdr(self.h, C.c_void_p(ptr), 1))
+
+    def set_hdr(self, img):
+        img = np.ascontiguousarray(img, np.float32); self._ck(self.L.b200pt_set_hdr(self.h, _p(img), 0))
+
+    def set_hdr_from_device(self, ptr): self._ck(self.L.b200pt_set_hdr(self.h, C.c_void_p(ptr), 1))
+
+    def counters(self):
+        c = Counters(); self._ck(self.L.b200pt_get_counters(self.h, C.byref(c)))
+        return {n: getattr(c, n) for n, _ in Counters._fields_}
+
+    # ---- PostProcessor
+    def set_tonemap(self, exposure=1.0, gamma=2.2): self._ck(self.L.b200pt_post_set_tonemap(self.h, C.byref(Tonemap(exposure, gamma))))
+
+    def set_bloom(self, threshold=2.0, strength=1.0, mips=10, falloff=5.0): self._ck(self.L.b200pt_post_set_bloom(self.h, C.byref(Bloom(threshold, strength, mips, falloff))))
+
+    def post_process(self): self._ck(self.L.b200pt_post_process(self.h))
+
+    def get_ldr(self, out=None):
+        w, h = self.size()
+        if out is None: out = np.empty((h, w, 4), np.uint8)
+        self._ck(self.L.b200pt_get_ldr(self.h, _p(out), 0)); return out
+
+    def get_bloom(self):
+        w, h = self.size(); out = np.empty((h, w, 4), np.float32)
+        self._ck(self.L.b200pt_get_bloom(self.h, _p(out))); return out
+
+    def save_png(self, path): self._ck(self.L.b200pt_save_png(self.h, path.encode()))
+
+    # ---- test hooks
+    def trace_closest(self, org, dirs, tmin, tmax):
+        org = np.ascontiguousarray(org, np.float32); dirs = np.ascontiguousarray(dirs, np.float32); n = len(org)
+        t = np.zeros(n, np.float32); prim = np.zeros(n, np.uint32); inst = np.zeros(n, np.uint32); uv = np.zeros((n, 2), np.float32)
+        self._ck(self.L.b200pt_trace_closest(self.h, n, _p(org), _p(dirs), C.c_float(tmin), C.c_float(tmax), _p(t), _p(prim), _p(inst), _p(uv)))
+        return t, prim, inst, uv
+
+    def scene_stats(self):
+        a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._ck(self.L.b200pt_scene_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(triangles=a.value, bvh_nodes=b.value, emissive_meshes=c.value, textures=d.value)

@@ -1,0 +1,137 @@
+// bvh_traverse.cuh -- stack traversal of the 64-B two-child-box BVH2 (closest-hit and any-hit).
+// Replaces the driver TLAS/BLAS + RT-core traversal behind TraceRay / RayQuery::Proceed
+// (reference: SH/RayGen.slang:90, SH/RTCommon.slang:47-117; semantics SURVEY 8a row A1):
+//   no culling, force-opaque, accept tmin < t < tmax, report (instance, primitive, t, barycentrics);
+//   exact-t ties resolve to the lowest (instance, primitive) order so results are reproducible.
+// The traversal stack lives in shared memory (one column per thread, conflict-free); small scenes have
+// the whole node + triangle array staged into shared memory by one TMA bulk copy per CTA.
+#pragma once
+#include "shading.cuh"
+
+namespace b200pt {
+
+struct BvhView { const float4 *nodes; const float4 *tris; int root; };
+struct HitRec { float t, u, v; uint32_t slot; };
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+/sm_100a) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+// Stage nodes+tris (contiguous in HBM, `bytes` multiple of 16) into shared memory.  Called by all threads.
+// TMA bulk copies are limited in size per instruction, so the copy is issued in 32 KB pieces by thread 0.
+__device__ __forceinline__ BvhView stage_bvh_smem(const DevScene &sc, unsigned char *dst, uint64_t *bar) {
+    if (threadIdx.x == 0) { mbar_init(bar, 1); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = sc.bvh_bytes;
+        mbar_expect_tx(bar, total);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(sc.nodes);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            uint32_t n = min(32768u, total - off);
+            tma_bulk_g2s(dst + off, src + off, n, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+    BvhView v;
+    v.nodes = reinterpret_cast<const float4 *>(dst);
+    v.tris = reinterpret_cast<const float4 *>(dst + (size_t)sc.n_nodes * sizeof(BvhNode));
+    v.root = sc.root;
+    return v;
+}
+__device__ __forceinline__ BvhView global_bvh(const DevScene &sc) {
+    BvhView v; v.nodes = reinterpret_cast<const float4 *>(sc.nodes); v.tris = reinterpret_cast<const float4 *>(sc.tris); v.root = sc.root; return v;
+}
+
+template <bool SMEM> __device__ __forceinline__ float4 ld4(const float4 *p) {
+    if (SMEM) return *p; else return __ldg(p);
+}
+
+// Moeller-Trumbore with precomputed edges; the same formula as the oracle's tri_hit().
+__device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3 o, float3 d, float tmin, float tmax, float &t, float &u, float &v) {
+    float3 p = cross(d, e2);
+    float det = dot(e1, p);
+    if (det == 0.0f) return false;
+    float inv = 1.0f / det;
+    float3 tv = o - v0;
+    u = dot(tv, p) * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    float3 q = cross(tv, e1);
+    v = dot(d, q) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+    t = dot(e2, q) * inv;
+    return (t > tmin && t < tmax);
+}
+
+// stack: shared-memory column of this thread, entries at stack[k * stride]
+template <bool SMEM, bool ANYHIT>
+__device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, float tmin, float tmax, HitRec &h,
+                                          int *stack, int stride, int max_stack) {
+    h.slot = 0xFFFFFFFFu; h.t = tmax; h.u = 0.0f; h.v = 0.0f;
+    uint32_t best_gid = 0xFFFFFFFFu;
+    bool found = false;
+    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int sp = 0;
+    int cur = b.root;
+    while (true) {
+        if (cur >= 0) {
+            const float4 *np = b.nodes + (size_t)cur * 4;
+            const float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
+            // child 0: lo (n0.x n0.y n0.z) hi (n0.w n1.x n1.y); child 1: lo (n1.z n1.w n2.x) hi (n2.y n2.z n2.w)
+            float ax0 = (n0.x - o.x) * inv.x, ax1 = (n0.w - o.x) * inv.x;
+            float ay0 = (n0.y - o.y) * inv.y, ay1 = (n1.x - o.y) * inv.y;
+            float az0 = (n0.z - o.z) * inv.z, az1 = (n1.y - o.z) * inv.z;
+            float an = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), tmin));
+            float af = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), h.t));
+            float bx0 = (n1.z - o.x) * inv.x, bx1 = (n2.y - o.x) * inv.x;
+            float by0 = (n1.w - o.y) * inv.y, by1 = (n2.z - o.y) * inv.y;
+            float bz0 = (n2.x - o.z) * inv.z, bz1 = (n2.w - o.z) * inv.z;
+            float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), tmin));
+            float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), h.t));
+            const bool ha = an <= af * 1.0000004f, hb = bn <= bf * 1.0000004f;
+            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (ha && hb) {
+                const bool a_first = an <= bn;
+                const int near_c = a_first ? c0 : c1, far_c = a_first ? c1 : c0;
+                if (sp < max_stack) { stack[sp * stride] = far_c; sp++; }
+                cur = near_c;
+                continue;
+            } else if (ha) { cur = c0; continue; }
+            else if (hb) { cur = c1; continue; }
+        } else {
+            const uint32_t slot = (uint32_t)(~cur);
+            const float4 *tp = b.tris + (size_t)slot * 3;
+            const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
+            float t, u, v;
+            if (tri_test(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax, t, u, v)) {
+                const uint32_t gid = __float_as_uint(ta.w);
+                if (!found || t < h.t || (t == h.t && gid < best_gid)) {
+                    found = true; h.t = t; h.u = u; h.v = v; h.slot = slot; best_gid = gid;
+                    if (ANYHIT) return true;
+                }
+            }
+        }
+        if (sp == 0) break;
+        sp--; cur = stack[sp * stride];
+    }
+    if (!found) h.t = -1.0f;
+    return found;
+}
+
+} // namespace b200pt

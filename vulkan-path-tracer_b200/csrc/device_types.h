@@ -1,0 +1,106 @@
+// device_types.h -- POD layouts shared by the host runtime and the sm_100a kernels.
+// HBM layout of the scene (all read-only during rendering, replicated per GPU):
+//   vertices  : b200pt_vertex[ ]   32 B, all meshes concatenated          (SH/Bindings.slang:7-12)
+//   indices   : u32[ ]             all meshes concatenated, mesh-local    (PT/PathTracer.cpp:216)
+//   meshes    : DevMesh[ ]         {vertex base, index base, triangles}
+//   instances : DevInstance[ ]     object->world 3x4, world->object 3x3, mesh, material (TLAS instance order)
+//   materials : b200pt_material[ ] 112 B                                  (PT/PathTracer.h:12-34)
+//   textures  : DevTexture[ ]      RGBA8 / R8 texel arrays                (PT/PathTracer.cpp:812-869)
+//   emissive  : DevEmissive[ ]     80 B                                   (PT/PathTracer.h:321-328)
+//   env       : float4[W*H] (rgb, pdf) + alias uint2[W*H]                 (PT/PathTracer.cpp:1137-1332)
+//   luts      : float[32*64*64], float[32*128*128] x2                     (PT/PathTracer.cpp:199-201)
+//   bvh       : BvhNode[ ] 64 B (two child boxes per node) + BvhTri[ ] 48 B (v0,e1,e2 + ids), Morton order
+#pragma once
+#include <stdint.h>
+#include "../../include/b200pt.h"
+
+#include <cuda_runtime.h>
+
+namespace b200pt {
+
+struct DevMesh { uint32_t vbase, ibase, tri_count, _pad; };
+
+struct DevInstance {
+    float o2w[12];      // row-major 3x4
+    float w2o[9];       // row-major 3x3 inverse of the linear part
+    uint32_t mesh, material, tri_base;
+    uint32_t emissive_tri_count;   // TriangleCount of this instance's EmissiveMeshEntry, 0 if not emissive
+    uint32_t _pad[3];
+};                      // 112 B
+static_assert(sizeof(DevInstance) == 112, "DevInstance layout");
+
+struct DevTexture { const uint8_t *data; uint32_t w, h, c, _pad; };
+
+struct DevEmissive { uint32_t mesh, material, tri_count, instance; float xf[16]; };  // PT/PathTracer.h:321-328
+static_assert(sizeof(DevEmissive) == 80, "EmissiveMeshEntry is 80 B");
+static_assert(sizeof(b200pt_vertex) == 32, "Vertex is 32 B");
+static_assert(sizeof(b200pt_material) == 112, "Material is 112 B");
+
+// 64-byte BVH2 node: AABBs of both children live in the parent, so one 64-B fetch decides both.
+// child >= 0 : internal node index;  child < 0 : leaf, ~child = triangle slot (Morton order)
+struct BvhNode {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    int32_t c0, c1;
+    uint32_t _pad[2];
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode is 64 B");
+
+// 48-byte triangle: world-space v0 and edges + ids (a = v0.xyz|gid, b = e1.xyz|inst, c = e2.xyz|prim)
+struct BvhTri { float4 a, b, c; };
+static_assert(sizeof(BvhTri) == 48, "BvhTri is 48 B");
+
+struct DevScene {
+    const b200pt_vertex *verts;
+    const uint32_t *indices;
+    const DevMesh *meshes;
+    const DevInstance *instances;
+    const b200pt_material *materials;
+    const DevTexture *textures;
+    const DevEmissive *emissive;
+    const float4 *env;
+    const uint2 *alias;
+    const float *lut_reflect, *lut_refract_out, *lut_refract_in;
+    const BvhNode *nodes;
+    const BvhTri *tris;
+    uint32_t n_emissive, envW, envH, n_tris, n_nodes;
+    int32_t root;            // child-style reference of the root
+    uint32_t bvh_bytes;      // nodes+tris size if they are contiguous and small enough to stage in smem, else 0
+    uint32_t _pad;
+};
+
+struct DevConfig {          // PT/PathTracer.h:271-302 (the fields the surface integrator reads)
+    float VI[16], PI[16];
+    uint32_t SampleCount, MaxDepth;
+    float MaxLuminance, FocusDistance, DepthOfFieldStrength;
+    float SkyRotationAzimuth, SkyRotationAltitude, EnvironmentIntensity, EmissiveMeshSamplingPDFBias;
+    uint32_t ScreenSplitCount;
+    uint32_t EnableSkyMIS, EnableMeshMIS, ShowEnvMapDirectly, UseOnlyGeometryNormals, UseEnergyCompensation, FurnaceTestMode;
+    uint32_t W, H;           // full image size
+    uint32_t rank, world, band_rows, local_rows;
+};
+
+struct DevDispatch { uint32_t FrameCount, Seed, ChunkIndex, _pad; };   // PT/PathTracer.h:304-309
+
+// ---- wavefront SoA (all float4 so every access is a coalesced 16-B lane access) ----
+struct PathState {
+    float4 *org_pdf;     // Origin.xyz, PDF of the previous BSDF sample (payload.PDF)
+    float4 *dir_rng;     // Direction.xyz, RNG state (u32 bits)
+    float4 *thr_depth;   // pathThroughput.xyz, Depth | InMedium<<31 (u32 bits)
+    float4 *rad_slot;    // pathLight.xyz, sample slot (u32 bits)
+    float4 *medium;      // MediumColor.xyz, MediumDensity
+    float  *medium_g;    // MediumAnisotropy
+};
+struct ShadeOut {
+    float4 *hit;         // t, u, v, tri slot (u32 bits; 0xFFFFFFFF = miss)
+    float4 *bxdf_pdf;    // payload.BxDF.xyz, payload.PDF
+    float4 *e0;          // emission term of payload.Emitted (xyz), new Depth (u32 bits)
+    float4 *sky_o, *sky_d, *sky_c;   // shadow ray origin(w: valid), direction, weighted contribution
+    float4 *lit_o, *lit_d, *lit_c;   // lit_o.w: valid, lit_d.w: expected prim (bits), lit_c.w: expected inst (bits)
+};
+
+struct WaveCounters {    // device-side counters (u64)
+    unsigned long long paths, extend_rays, shade_invocations, surface_hits, misses, shadow_rays, medium_events;
+};
+
+} // namespace b200pt

@@ -1,0 +1,433 @@
+// engine.cu -- host runtime of the wavefront path tracer (see engine.h).
+// Orchestration per b200pt_path_trace call (all on one CUDA stream, no host sync inside a wave unless the
+// scene can scatter inside a medium or MaxDepth is large enough that early exit pays):
+//   upload dispatch table -> for each wave of F dispatches: raygen -> [extend, shade, connect] x bounces -> resolve
+#include "engine.h"
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+
+namespace b200pt {
+
+void Engine::check(cudaError_t e, const char *what) const {
+    if (e != cudaSuccess) throw CudaError{ (int)e, std::string(what) + ": " + cudaGetErrorString(e) };
+}
+#define CK(x) check((x), #x)
+
+template <class T> static void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
+
+Engine::Engine(int device) : device_(device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) throw CudaError{ B200PT_ERR_NO_DEVICE, "no CUDA device available (the product has no CPU fallback)" };
+    if (device < 0 || device >= n) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "device ordinal out of range" };
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking)); stream_ = own_stream_;
+    CK(cudaEventCreateWithFlags(&table_ev_[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&table_ev_[1], cudaEventDisableTiming));
+    CK(cudaEventCreate(&ev_[0])); CK(cudaEventCreate(&ev_[1]));
+    b200pt_default_config(&cfg_);
+    memset(view_inv_, 0, sizeof view_inv_); memset(proj_inv_, 0, sizeof proj_inv_);
+    for (int i = 0; i < 4; i++) view_inv_[i * 5] = proj_inv_[i * 5] = 1.0f;
+    CK(cudaMalloc(&d_ctr_, sizeof(WaveCounters)));
+    CK(cudaMemset(d_ctr_, 0, sizeof(WaveCounters)));
+    CK(cudaMalloc(&d_counts_, 4 * sizeof(uint32_t)));
+    CK(cudaMallocHost(&h_count_, 4 * sizeof(uint32_t)));
+    memset(&last_, 0, sizeof last_);
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    free_scene(); free_wave(); free_post();
+    dfree(d_env_); dfree(d_alias_); for (auto &l : d_luts_) dfree(l);
+    dfree(d_image_); dfree(d_ctr_); dfree(d_counts_);
+    if (h_count_) cudaFreeHost(h_count_);
+    if (ev_[0]) cudaEventDestroy(ev_[0]); if (ev_[1]) cudaEventDestroy(ev_[1]);
+    for (auto &e : prof_ev_) cudaEventDestroy(e);
+    if (table_ev_[0]) cudaEventDestroy(table_ev_[0]); if (table_ev_[1]) cudaEventDestroy(table_ev_[1]);
+    if (own_stream_) cudaStreamDestroy(own_stream_);
+}
+
+void Engine::free_scene() {
+    dfree(d_verts_); dfree(d_indices_); dfree(d_meshes_); dfree(d_instances_); dfree(d_materials_); dfree(d_textures_); dfree(d_emissive_);
+    for (auto &p : d_texdata_) if (p) cudaFree(p);
+    d_texdata_.clear();
+    lbvh_free(&bvh_);
+    has_scene_ = false;
+}
+
+// PathTracer::SetScene (PathTracer.cpp:158-676)
+void Engine::set_scene(HostScene &&scene) {
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    free_scene();
+    scene_ = std::move(scene);
+    // capacity limits of the reference (PathTracer.h:192-195, asserts PathTracer.cpp:182-184)
+    if (scene_.meshes.size() >= 10000 || scene_.materials.size() >= 10000 || scene_.instances.size() >= 100000)
+        throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "scene exceeds the reference's MAX_ENTITIES / MAX_INSTANCES limits" };
+    upload_scene();
+    // camera: PathTracer.cpp:187-188,578 then the Editor/FlyCamera round trip
+    camera_from_view(scene_.camera_view, scene_.camera_aspect, view_inv_, proj_inv_);
+    // output image: W = (uint)(1080 * aspect), H = 1080 (PathTracer.cpp:509-512)
+    W_ = (uint32_t)((float)1080 * scene_.camera_aspect); H_ = 1080;
+    local_rows_ = partition_local_rows(H_, rank_, world_, band_);
+    ensure_image();
+    has_scene_ = true;
+    reset();
+}
+
+void Engine::upload_scene() {
+    size_t nv = 0, ni = 0;
+    h_meshes_.clear();
+    for (auto &m : scene_.meshes) { h_meshes_.push_back({ (uint32_t)nv, (uint32_t)ni, (uint32_t)(m.indices.size() / 3), 0 }); nv += m.vertices.size(); ni += m.indices.size(); }
+    std::vector<b200pt_vertex> verts(nv); std::vector<uint32_t> idx(ni);
+    for (size_t i = 0; i < scene_.meshes.size(); i++) {
+        memcpy(&verts[h_meshes_[i].vbase], scene_.meshes[i].vertices.data(), scene_.meshes[i].vertices.size() * sizeof(b200pt_vertex));
+        memcpy(&idx[h_meshes_[i].ibase], scene_.meshes[i].indices.data(), scene_.meshes[i].indices.size() * 4);
+    }
+    CK(cudaMalloc(&d_verts_, nv * sizeof(b200pt_vertex))); CK(cudaMemcpy(d_verts_, verts.data(), nv * sizeof(b200pt_vertex), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_indices_, ni * 4)); CK(cudaMemcpy(d_indices_, idx.data(), ni * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_meshes_, h_meshes_.size() * sizeof(DevMesh))); CK(cudaMemcpy(d_meshes_, h_meshes_.data(), h_meshes_.size() * sizeof(DevMesh), cudaMemcpyHostToDevice));
+    // instances: one per MeshInstance in loader order == InstanceIndex (TLASImpl.cpp:29-35)
+    h_instances_.assign(scene_.instances.size(), DevInstance{});
+    uint32_t tri_base = 0;
+    for (size_t i = 0; i < scene_.instances.size(); i++) {
+        const b200pt_instance &in = scene_.instances[i]; DevInstance &d = h_instances_[i];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) d.o2w[r * 4 + c] = in.Transform[c * 4 + r];
+        mat3_inverse_from_o2w(d.o2w, d.w2o);
+        d.mesh = in.MeshIndex; d.material = in.MaterialIndex; d.tri_base = tri_base;
+        tri_base += h_meshes_[in.MeshIndex].tri_count;
+    }
+    n_tris_ = tri_base;
+    CK(cudaMalloc(&d_instances_, h_instances_.size() * sizeof(DevInstance)));
+    CK(cudaMalloc(&d_materials_, scene_.materials.size() * sizeof(b200pt_material)));
+    CK(cudaMemcpy(d_materials_, scene_.materials.data(), scene_.materials.size() * sizeof(b200pt_material), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_emissive_, std::max<size_t>(1, scene_.instances.size()) * sizeof(DevEmissive)));
+    rebuild_emissive();
+    // textures
+    std::vector<DevTexture> dt(scene_.textures.size());
+    d_texdata_.assign(scene_.textures.size(), nullptr);
+    for (size_t i = 0; i < scene_.textures.size(); i++) {
+        const HostTexture &t = scene_.textures[i];
+        CK(cudaMalloc(&d_texdata_[i], std::max<size_t>(t.data.size(), 4)));
+        CK(cudaMemcpy(d_texdata_[i], t.data.data(), t.data.size(), cudaMemcpyHostToDevice));
+        dt[i] = { d_texdata_[i], t.width, t.height, t.channels, 0 };
+    }
+    CK(cudaMalloc(&d_textures_, dt.size() * sizeof(DevTexture))); CK(cudaMemcpy(d_textures_, dt.data(), dt.size() * sizeof(DevTexture), cudaMemcpyHostToDevice));
+    // acceleration structure: GPU LBVH over the flattened instances
+    int r = lbvh_build(d_verts_, d_indices_, d_meshes_, d_instances_, h_instances_.data(), h_meshes_.data(), (uint32_t)h_instances_.size(), n_tris_, &bvh_, stream_);
+    if (r != 0) throw CudaError{ B200PT_ERR_CUDA, std::string("lbvh_build failed: ") + cudaGetErrorString((cudaError_t)r) };
+    ds_.verts = d_verts_; ds_.indices = d_indices_; ds_.meshes = d_meshes_; ds_.instances = d_instances_; ds_.materials = d_materials_;
+    ds_.textures = d_textures_; ds_.emissive = d_emissive_; ds_.nodes = bvh_.nodes; ds_.tris = bvh_.tris;
+    ds_.n_tris = bvh_.n_tris; ds_.n_nodes = bvh_.n_nodes; ds_.root = bvh_.root; ds_.bvh_bytes = bvh_.bytes <= 0xFFFFFFFFull ? (uint32_t)bvh_.bytes : 0;
+    int q = query_launch_cfg(ds_, bvh_.max_depth, &lc_);
+    if (q != 0) throw CudaError{ B200PT_ERR_CUDA, "query_launch_cfg failed" };
+}
+
+// emissive-mesh list: PathTracer.cpp:458-469 (+ SetMaterial maintenance :712-810); keyed on constant EmissiveColor != 0 (Q16)
+void Engine::rebuild_emissive() {
+    std::vector<DevEmissive> em;
+    for (size_t i = 0; i < scene_.instances.size(); i++) {
+        const b200pt_instance &in = scene_.instances[i];
+        const b200pt_material &m = scene_.materials[in.MaterialIndex];
+        h_instances_[i].emissive_tri_count = 0;
+        if (m.EmissiveColor[0] != 0.0f || m.EmissiveColor[1] != 0.0f || m.EmissiveColor[2] != 0.0f) {
+            DevEmissive e; e.mesh = in.MeshIndex; e.material = in.MaterialIndex; e.tri_count = h_meshes_[in.MeshIndex].tri_count; e.instance = (uint32_t)i;
+            memcpy(e.xf, in.Transform, sizeof e.xf);
+            em.push_back(e);
+            h_instances_[i].emissive_tri_count = e.tri_count;
+        }
+    }
+    if (em.size() >= 10000) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "too many emissive meshes (MAX_EMISSIVE_MESHES)" };
+    n_emissive_ = (uint32_t)em.size();
+    if (!em.empty()) CK(cudaMemcpy(d_emissive_, em.data(), em.size() * sizeof(DevEmissive), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_instances_, h_instances_.data(), h_instances_.size() * sizeof(DevInstance), cudaMemcpyHostToDevice));
+    ds_.n_emissive = n_emissive_;
+}
+
+void Engine::set_material(uint32_t idx, const b200pt_material &m) {
+    CK(cudaSetDevice(device_));
+    if (!has_scene_) throw CudaError{ B200PT_ERR_NO_SCENE, "no scene" };
+    if (idx >= scene_.materials.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "material index out of range" };
+    const uint32_t tix[5] = { m.BaseColorTextureIndex, m.NormalTextureIndex, m.RoughnessTextureIndex, m.MetallicTextureIndex, m.EmissiveTextureIndex };
+    for (uint32_t t : tix) if (t >= scene_.textures.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "texture index out of range" };
+    CK(cudaStreamSynchronize(stream_));
+    scene_.materials[idx] = m;
+    CK(cudaMemcpy(d_materials_ + idx, &m, sizeof m, cudaMemcpyHostToDevice));
+    rebuild_emissive();
+    reset();
+}
+
+// PathTracer::LoadEnvironmentMap (PathTracer.cpp:1137-1332)
+void Engine::set_env_map(uint32_t w, uint32_t h, const float *rgba) {
+    CK(cudaSetDevice(device_));
+    if (!w || !h || !rgba || (uint64_t)w * h > 0x7FFFFFFFull) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "bad environment map" };
+    CK(cudaStreamSynchronize(stream_));
+    std::vector<float> px(rgba, rgba + (size_t)w * h * 4);
+    std::vector<uint2> alias((size_t)w * h);
+    build_env_alias(px.data(), w, h, alias.data());
+    dfree(d_env_); dfree(d_alias_);
+    CK(cudaMalloc(&d_env_, px.size() * 4)); CK(cudaMemcpy(d_env_, px.data(), px.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_alias_, alias.size() * sizeof(uint2))); CK(cudaMemcpy(d_alias_, alias.data(), alias.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    ds_.env = d_env_; ds_.alias = d_alias_; ds_.envW = w; ds_.envH = h;
+    has_env_ = true;
+    reset();
+}
+
+void Engine::set_luts(const float *refl, const float *rout, const float *rin) {
+    CK(cudaSetDevice(device_));
+    if (!refl || !rout || !rin) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "null LUT" };
+    CK(cudaStreamSynchronize(stream_));
+    const size_t n[3] = { 64 * 64 * 32, 128 * 128 * 32, 128 * 128 * 32 }; const float *src[3] = { refl, rout, rin };
+    for (int i = 0; i < 3; i++) { dfree(d_luts_[i]); CK(cudaMalloc(&d_luts_[i], n[i] * 4)); CK(cudaMemcpy(d_luts_[i], src[i], n[i] * 4, cudaMemcpyHostToDevice)); }
+    ds_.lut_reflect = d_luts_[0]; ds_.lut_refract_out = d_luts_[1]; ds_.lut_refract_in = d_luts_[2];
+    has_luts_ = true;
+    reset();
+}
+
+void Engine::set_config(const b200pt_config &c) {
+    if (c.SamplesPerFrame == 0 || c.ScreenChunkCount == 0 || c.ScreenChunkCount > 64) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "SamplesPerFrame and ScreenChunkCount must be >= 1" };
+    if (c.ScreenChunkCount > 1 && world_ > 1) throw CudaError{ B200PT_ERR_NOT_IMPLEMENTED, "ScreenChunkCount > 1 cannot be combined with a multi-GPU partition" };
+    cfg_ = c;
+    reset();
+}
+void Engine::set_camera(const float vi[16], const float pi[16]) { memcpy(view_inv_, vi, sizeof view_inv_); memcpy(proj_inv_, pi, sizeof proj_inv_); reset(); }
+void Engine::get_camera(float vi[16], float pi[16]) const { memcpy(vi, view_inv_, sizeof view_inv_); memcpy(pi, proj_inv_, sizeof proj_inv_); }
+void Engine::reset() { dispatch_count_ = 0; frame_count_ = 0; samples_accumulated_ = 0; }   // PathTracer.h:183
+
+void Engine::resize(uint32_t w, uint32_t h) {                                                  // PathTracer::ResizeImage
+    if (!w || !h || w > 65535 || h > 65535) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "bad image size" };
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    W_ = w; H_ = h; local_rows_ = partition_local_rows(H_, rank_, world_, band_);
+    ensure_image(); reset();
+}
+void Engine::set_partition(uint32_t rank, uint32_t world, uint32_t band) {
+    if (!world || rank >= world || !band) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "bad partition" };
+    if (world > 1 && cfg_.ScreenChunkCount > 1) throw CudaError{ B200PT_ERR_NOT_IMPLEMENTED, "ScreenChunkCount > 1 cannot be combined with a multi-GPU partition" };
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    rank_ = rank; world_ = world; band_ = band;
+    if (W_ && H_) { local_rows_ = partition_local_rows(H_, rank_, world_, band_); ensure_image(); }
+    reset();
+}
+void Engine::ensure_image() {
+    const size_t need = (size_t)W_ * std::max<uint32_t>(local_rows_, 1);
+    if (need != image_pixels_) { dfree(d_image_); CK(cudaMalloc(&d_image_, need * sizeof(float4))); image_pixels_ = need; }
+    CK(cudaMemsetAsync(d_image_, 0, image_pixels_ * sizeof(float4), stream_));
+}
+
+void Engine::free_wave() {
+    for (auto &p : ps_) { dfree(p.org_pdf); dfree(p.dir_rng); dfree(p.thr_depth); dfree(p.rad_slot); dfree(p.medium); dfree(p.medium_g); }
+    dfree(so_.hit); dfree(so_.bxdf_pdf); dfree(so_.e0); dfree(so_.sky_o); dfree(so_.sky_d); dfree(so_.sky_c); dfree(so_.lit_o); dfree(so_.lit_d); dfree(so_.lit_c);
+    dfree(d_sample_buf_); dfree(d_rng_carry_); dfree(d_disp_[0]); dfree(d_disp_[1]);
+    for (auto &hp : h_disp_) if (hp) { cudaFreeHost(hp); hp = nullptr; }
+    wave_cap_ = 0;
+}
+static const uint32_t kMaxDispatchTable = 1u << 16;
+void Engine::ensure_wave(size_t cap) {
+    if (cap <= wave_cap_) return;
+    free_wave();
+    auto a4 = [&](float4 *&p) { CK(cudaMalloc(&p, cap * sizeof(float4))); };
+    for (auto &p : ps_) { a4(p.org_pdf); a4(p.dir_rng); a4(p.thr_depth); a4(p.rad_slot); a4(p.medium); CK(cudaMalloc(&p.medium_g, cap * sizeof(float))); }
+    a4(so_.hit); a4(so_.bxdf_pdf); a4(so_.e0); a4(so_.sky_o); a4(so_.sky_d); a4(so_.sky_c); a4(so_.lit_o); a4(so_.lit_d); a4(so_.lit_c);
+    a4(d_sample_buf_);
+    CK(cudaMalloc(&d_rng_carry_, cap * sizeof(uint32_t)));
+    for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); CK(cudaMallocHost(&h_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); }
+    wave_cap_ = cap;
+}
+
+DevConfig Engine::make_dev_config() const {
+    DevConfig d; memset(&d, 0, sizeof d);
+    memcpy(d.VI, view_inv_, sizeof d.VI); memcpy(d.PI, proj_inv_, sizeof d.PI);
+    d.SampleCount = cfg_.SamplesPerFrame; d.MaxDepth = cfg_.MaxDepth; d.MaxLuminance = cfg_.MaxLuminance; d.FocusDistance = cfg_.FocusDistance;
+    d.DepthOfFieldStrength = cfg_.DepthOfFieldStrength; d.SkyRotationAzimuth = cfg_.SkyRotationAzimuth; d.SkyRotationAltitude = cfg_.SkyRotationAltitude;
+    d.EnvironmentIntensity = cfg_.SkyIntensity; d.EmissiveMeshSamplingPDFBias = cfg_.EmissiveMeshSamplingPDFBias; d.ScreenSplitCount = cfg_.ScreenChunkCount;
+    d.EnableSkyMIS = cfg_.EnableSkyMIS; d.EnableMeshMIS = cfg_.EnableMeshMIS; d.ShowEnvMapDirectly = cfg_.ShowEnvMapDirectly;
+    d.UseOnlyGeometryNormals = cfg_.UseOnlyGeometryNormals; d.UseEnergyCompensation = cfg_.UseEnergyCompensation; d.FurnaceTestMode = cfg_.FurnaceTestMode;
+    d.W = W_; d.H = H_; d.rank = rank_; d.world = world_; d.band_rows = band_; d.local_rows = local_rows_;
+    return d;
+}
+
+// PathTracer::PathTrace x dispatches (PathTracer.cpp:122-156)
+bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
+    CK(cudaSetDevice(device_));
+    if (!has_scene_) throw CudaError{ B200PT_ERR_NO_SCENE, "PathTrace before SetScene" };
+    if (!has_env_) throw CudaError{ B200PT_ERR_NO_SCENE, "no environment map (PathTracer always loads one, PathTracer.cpp:202)" };
+    if (!has_luts_) throw CudaError{ B200PT_ERR_NO_SCENE, "no energy-compensation lookup tables (PathTracer.cpp:199-201)" };
+    const uint32_t S = cfg_.ScreenChunkCount, S2 = S * S;
+    // how many dispatches until MaxSamplesAccumulated (PathTracer.cpp:124-125,151-153)
+    uint32_t todo = 0;
+    { uint64_t d = dispatch_count_; uint32_t acc = samples_accumulated_;
+      while (todo < dispatches && acc < cfg_.MaxSamplesAccumulated) { d++; todo++; acc = (uint32_t)(d / S2) * cfg_.SamplesPerFrame; } }
+    if (todo == 0) return samples_accumulated_ >= cfg_.MaxSamplesAccumulated;
+    if (todo > kMaxDispatchTable) todo = kMaxDispatchTable;
+
+    const uint32_t P = (S == 1) ? W_ * local_rows_ : ((W_ + S - 1) / S) * ((H_ + S - 1) / S);
+    if (P == 0) { dispatch_count_ += todo; frame_count_ = (uint32_t)(dispatch_count_ / S2); samples_accumulated_ = frame_count_ * cfg_.SamplesPerFrame; return samples_accumulated_ >= cfg_.MaxSamplesAccumulated; }
+    uint32_t F = cfg_.FramesInFlight;
+    if (F == 0) { const uint64_t target = 4ull << 20; F = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, target / P)); }
+    F = std::min(F, todo);
+    if ((size_t)F * P > wave_cap_) { CK(cudaStreamSynchronize(stream_)); }
+    ensure_wave((size_t)F * P);
+    // double-buffered dispatch tables: the host copy is reusable once ITS upload (two calls ago) has executed
+    table_sel_ ^= 1;
+    DevDispatch *h_disp = h_disp_[table_sel_], *d_disp = d_disp_[table_sel_];
+    CK(cudaEventSynchronize(table_ev_[table_sel_]));
+
+    for (uint32_t i = 0; i < todo; i++) {
+        const uint64_t d = dispatch_count_ + i;
+        h_disp[i].FrameCount = (uint32_t)(d / S2);
+        h_disp[i].Seed = [](uint32_t in) { uint32_t st = in * 747796405u + 2891336453u; uint32_t w = ((st >> ((st >> 28u) + 4u)) ^ st) * 277803737u; return (w >> 22u) ^ w; }(base_seed + (uint32_t)d);
+        h_disp[i].ChunkIndex = (uint32_t)(d % S2);
+        h_disp[i]._pad = 0;
+    }
+    CK(cudaMemcpyAsync(d_disp, h_disp, todo * sizeof(DevDispatch), cudaMemcpyHostToDevice, stream_));
+    CK(cudaEventRecord(table_ev_[table_sel_], stream_));
+    const DevConfig dc = make_dev_config();
+
+    bool medium = false;                                      // can a path random-walk inside a mesh without gaining Depth?
+    for (const auto &m : scene_.materials) if (m.Transmission > 0.0f && m.Metallic < 1.0f && m.MediumDensity > 0.0f && m.MediumAnisotropy != 1.0f) medium = true;
+
+    CK(cudaEventRecord(ev_[0], stream_));
+    uint64_t launches = 0; uint32_t waves = 0, bounces_total = 0;
+    std::vector<int> prof_kind; size_t prof_n = 0;            // kind: 0 raygen 1 extend 2 shade 3 connect 4 resolve
+    auto mark = [&](int kind) {
+        if (!profiling_) return;
+        if (prof_n >= prof_ev_.size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); prof_ev_.push_back(e); }
+        CK(cudaEventRecord(prof_ev_[prof_n++], stream_)); prof_kind.push_back(kind);
+    };
+    mark(-1);
+    for (uint32_t w0 = 0; w0 < todo; w0 += F) {
+        const uint32_t nd = std::min(F, todo - w0);
+        for (uint32_t s = 0; s < cfg_.SamplesPerFrame; s++) {
+            launch_raygen(lc_, dc, d_disp + w0, nd, P, s == 0 ? 1u : 0u, d_rng_carry_, ps_[0], d_sample_buf_, d_counts_, d_ctr_, stream_);
+            launches++; mark(0);
+            int cur = 0; uint32_t k = 0;
+            for (;;) {
+                uint32_t chunk = 16;
+                if (!medium && cfg_.MaxDepth - std::min(cfg_.MaxDepth, k) < chunk) chunk = cfg_.MaxDepth - std::min(cfg_.MaxDepth, k);
+                if (chunk == 0) break;
+                for (uint32_t b = 0; b < chunk; b++, k++) {
+                    const uint32_t *n_live = d_counts_ + (k & 1u); uint32_t *n_next = d_counts_ + ((k + 1u) & 1u);
+                    launch_extend(lc_, ds_, ps_[cur], so_, n_live, d_ctr_, stream_); mark(1);
+                    launch_shade(lc_, ds_, dc, ps_[cur], so_, n_live, d_ctr_, stream_); mark(2);
+                    CK(cudaMemsetAsync(n_next, 0, sizeof(uint32_t), stream_));
+                    launch_connect(lc_, ds_, dc, ps_[cur], ps_[cur ^ 1], so_, n_live, n_next, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
+                    cur ^= 1; launches += 3;
+                }
+                if (!medium && k >= cfg_.MaxDepth) break;    // every surviving path has Depth >= MaxDepth: provably empty
+                CK(cudaMemcpyAsync(h_count_, d_counts_ + (k & 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+                CK(cudaStreamSynchronize(stream_));
+                if (h_count_[0] == 0) break;
+                if (k > (1u << 20)) break;                    // runaway guard
+            }
+            bounces_total += k;
+        }
+        launch_resolve(lc_, dc, d_disp + w0, nd, P, d_sample_buf_, d_image_, stream_);
+        launches++; waves++; mark(4);
+    }
+    CK(cudaEventRecord(ev_[1], stream_));
+    CK(cudaGetLastError());
+    dispatch_count_ += todo;
+    frame_count_ = (uint32_t)(dispatch_count_ / S2);                     // PathTracer.cpp:152
+    samples_accumulated_ = frame_count_ * cfg_.SamplesPerFrame;          // :153
+    last_.kernel_launches += launches; last_.waves = waves; last_.bounces = bounces_total;
+    last_.ms_raygen = last_.ms_extend = last_.ms_shade = last_.ms_connect = last_.ms_resolve = 0.0f;
+    if (profiling_ && prof_n > 1) {
+        CK(cudaStreamSynchronize(stream_));
+        float *acc[5] = { &last_.ms_raygen, &last_.ms_extend, &last_.ms_shade, &last_.ms_connect, &last_.ms_resolve };
+        for (size_t i = 1; i < prof_n; i++) { float ms = 0.0f; CK(cudaEventElapsedTime(&ms, prof_ev_[i - 1], prof_ev_[i])); if (prof_kind[i] >= 0) *acc[prof_kind[i]] += ms; }
+    }
+    return samples_accumulated_ >= cfg_.MaxSamplesAccumulated;
+}
+
+void Engine::set_stream(cudaStream_t s) {
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    stream_ = s ? s : own_stream_;
+}
+
+void Engine::synchronize() { CK(cudaSetDevice(device_)); CK(cudaStreamSynchronize(stream_)); CK(cudaGetLastError()); }
+
+b200pt_counters Engine::counters() {
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    WaveCounters wc; CK(cudaMemcpy(&wc, d_ctr_, sizeof wc, cudaMemcpyDeviceToHost));
+    b200pt_counters c = last_;
+    c.paths = wc.paths; c.extend_rays = wc.extend_rays; c.shade_invocations = wc.shade_invocations; c.surface_hits = wc.surface_hits;
+    c.misses = wc.misses; c.shadow_rays = wc.shadow_rays; c.medium_events = wc.medium_events;
+    float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_[0], ev_[1]) == cudaSuccess) c.ms_total = ms;
+    return c;
+}
+
+void Engine::get_hdr(float *dst, bool dev) {
+    CK(cudaSetDevice(device_));
+    if (!d_image_ || !dst) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "no image" };
+    CK(cudaMemcpyAsync(dst, d_image_, (size_t)W_ * local_rows_ * sizeof(float4), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+}
+void Engine::set_hdr(const float *src, bool dev) {
+    CK(cudaSetDevice(device_));
+    if (!d_image_ || !src) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "no image" };
+    CK(cudaMemcpyAsync(d_image_, src, (size_t)W_ * local_rows_ * sizeof(float4), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
+    CK(cudaStreamSynchronize(stream_));
+}
+
+// ---------------------------------------------------------------- PostProcessor (PostProcessor.cpp:128-246)
+void Engine::free_post() { for (auto &m : d_mips_) if (m) cudaFree(m); d_mips_.clear(); mip_wh_.clear(); dfree(d_ldr_); post_w_ = post_h_ = 0; }
+void Engine::ensure_post() {
+    if (post_w_ == W_ && post_h_ == H_ && !d_mips_.empty()) return;
+    free_post();
+    uint32_t wh[20]; const uint32_t levels = bloom_mip_sizes(W_, H_, wh);                     // SetInputImage :128-158
+    for (uint32_t i = 0; i < levels; i++) { float4 *p = nullptr; CK(cudaMalloc(&p, (size_t)wh[2 * i] * wh[2 * i + 1] * sizeof(float4))); d_mips_.push_back(p); mip_wh_.push_back(wh[2 * i]); mip_wh_.push_back(wh[2 * i + 1]); }
+    CK(cudaMalloc(&d_ldr_, (size_t)W_ * H_ * sizeof(uchar4)));
+    post_w_ = W_; post_h_ = H_;
+}
+void Engine::post_process() {
+    CK(cudaSetDevice(device_));
+    if (!d_image_ || !W_ || !H_) throw CudaError{ B200PT_ERR_NO_SCENE, "PostProcess without an input image" };
+    if (world_ != 1) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_process needs the full image: gather the bands first (world must be 1)" };
+    ensure_post();
+    const uint32_t levels = (uint32_t)d_mips_.size();
+    const uint32_t mips = std::min(std::max(bloom_.MipCount, 1u), levels);                      // :195
+    const PostParams p{ tonemap_.Exposure, tonemap_.Gamma, bloom_.BloomThreshold, bloom_.BloomStrength, bloom_.FalloffRange };
+    launch_bloom_threshold(d_image_, d_mips_[0], W_ * H_, p, lc_.grid_light > 0 ? lc_.grid_light : 1184, stream_);            // :200-226, i == 0
+    for (uint32_t i = 1; i < mips; i++) launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_);
+    for (uint32_t i = mips - 1; i > 0; i--) launch_bloom_up(d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], p, stream_);   // :229-235
+    launch_tonemap(d_image_, d_mips_[0], d_ldr_, W_, H_, p, stream_);                           // :238-245
+    CK(cudaGetLastError());
+}
+void Engine::get_ldr(uint8_t *dst, bool dev) {
+    CK(cudaSetDevice(device_));
+    if (!d_ldr_ || !dst) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_process has not run" };
+    CK(cudaMemcpyAsync(dst, d_ldr_, (size_t)W_ * H_ * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+}
+void Engine::get_bloom(float *dst) {
+    CK(cudaSetDevice(device_));
+    if (d_mips_.empty() || !dst) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_process has not run" };
+    CK(cudaMemcpyAsync(dst, d_mips_[0], (size_t)W_ * H_ * sizeof(float4), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+}
+
+void Engine::trace_closest(uint32_t n, const float *org, const float *dir, float tmin, float tmax, float *t, uint32_t *prim, uint32_t *inst, float *uv) {
+    CK(cudaSetDevice(device_));
+    if (!has_scene_) throw CudaError{ B200PT_ERR_NO_SCENE, "no scene" };
+    if (!n) return;
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr, *d_uv = nullptr; uint32_t *d_p = nullptr, *d_i = nullptr;
+    CK(cudaMalloc(&d_o, (size_t)n * 12)); CK(cudaMalloc(&d_d, (size_t)n * 12)); CK(cudaMalloc(&d_t, (size_t)n * 4)); CK(cudaMalloc(&d_uv, (size_t)n * 8));
+    CK(cudaMalloc(&d_p, (size_t)n * 4)); CK(cudaMalloc(&d_i, (size_t)n * 4));
+    CK(cudaMemcpyAsync(d_o, org, (size_t)n * 12, cudaMemcpyHostToDevice, stream_)); CK(cudaMemcpyAsync(d_d, dir, (size_t)n * 12, cudaMemcpyHostToDevice, stream_));
+    launch_trace_rays(lc_, ds_, n, d_o, d_d, tmin, tmax, d_t, d_p, d_i, d_uv, stream_);
+    CK(cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_)); CK(cudaMemcpyAsync(prim, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(inst, d_i, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_)); CK(cudaMemcpyAsync(uv, d_uv, (size_t)n * 8, cudaMemcpyDeviceToHost, stream_));
+    cudaError_t e = cudaStreamSynchronize(stream_);
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_uv); cudaFree(d_p); cudaFree(d_i);
+    CK(e); CK(cudaGetLastError());
+}
+void Engine::scene_stats(uint32_t *tris, uint32_t *nodes, uint32_t *emissive, uint32_t *textures) const {
+    if (tris) *tris = n_tris_; if (nodes) *nodes = bvh_.n_nodes; if (emissive) *emissive = n_emissive_; if (textures) *textures = (uint32_t)scene_.textures.size();
+}
+
+} // namespace b200pt

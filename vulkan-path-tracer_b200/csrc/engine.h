@@ -1,0 +1,112 @@
+// engine.h -- host runtime: the B200 counterparts of the reference's PathTracer (PathTracer/PathTracer.h:83-183)
+// and PostProcessor (PathTracer/PostProcessor.h:25-33) classes.  One Engine == one GPU.
+#pragma once
+#include "host_api.h"
+#include "kernels.h"
+#include <cuda_runtime.h>
+
+namespace b200pt {
+
+struct CudaError { int code; std::string what; };
+
+class Engine {
+public:
+    explicit Engine(int device);
+    ~Engine();
+
+    // PathTracer::SetScene
+    void set_scene(HostScene &&scene);
+    void set_env_map(uint32_t w, uint32_t h, const float *rgba);
+    void set_luts(const float *refl, const float *rout, const float *rin);
+
+    void set_config(const b200pt_config &c);
+    const b200pt_config &config() const { return cfg_; }
+    void set_material(uint32_t idx, const b200pt_material &m);
+    const HostScene &scene() const { return scene_; }
+    bool has_scene() const { return has_scene_; }
+    void set_camera(const float vi[16], const float pi[16]);
+    void get_camera(float vi[16], float pi[16]) const;
+    void resize(uint32_t w, uint32_t h);
+    void reset();                                   // ResetPathTracing
+    void set_partition(uint32_t rank, uint32_t world, uint32_t band);
+    uint32_t width() const { return W_; }
+    uint32_t height() const { return H_; }
+    uint32_t local_rows() const { return local_rows_; }
+    uint32_t samples_accumulated() const { return samples_accumulated_; }
+
+    // PathTracer::PathTrace x dispatches; returns true when all samples are accumulated
+    bool path_trace(uint32_t dispatches, uint32_t base_seed);
+    void synchronize();
+    void set_stream(cudaStream_t s);
+    void set_profiling(bool on) { profiling_ = on; }
+    void get_hdr(float *dst, bool dst_is_device);
+    void set_hdr(const float *src, bool src_is_device);
+    float4 *hdr_device() { return d_image_; }
+    b200pt_counters counters();
+
+    // PostProcessor
+    void set_tonemap(const b200pt_tonemap &t) { tonemap_ = t; }
+    void set_bloom(const b200pt_bloom &b) { bloom_ = b; }
+    void post_process();
+    void get_ldr(uint8_t *dst, bool dst_is_device);
+    void get_bloom(float *dst);
+
+    void trace_closest(uint32_t n, const float *org, const float *dir, float tmin, float tmax, float *t, uint32_t *prim, uint32_t *inst, float *uv);
+    void scene_stats(uint32_t *tris, uint32_t *nodes, uint32_t *emissive, uint32_t *textures) const;
+
+    std::string last_error;
+
+private:
+    void free_scene();
+    void upload_scene();
+    void rebuild_emissive();
+    void ensure_image();
+    void ensure_wave(size_t capacity);
+    void free_wave();
+    void ensure_post();
+    void free_post();
+    DevConfig make_dev_config() const;
+    void check(cudaError_t e, const char *what) const;
+
+    int device_;
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
+    bool profiling_ = false;
+    std::vector<cudaEvent_t> prof_ev_;
+    int table_sel_ = 0; cudaEvent_t table_ev_[2] = { nullptr, nullptr };
+    cudaEvent_t ev_[2] = { nullptr, nullptr };
+
+    HostScene scene_;
+    bool has_scene_ = false, has_env_ = false, has_luts_ = false;
+    b200pt_config cfg_;
+    float view_inv_[16], proj_inv_[16];
+    uint32_t W_ = 0, H_ = 0, rank_ = 0, world_ = 1, band_ = 16, local_rows_ = 0;
+    uint64_t dispatch_count_ = 0;
+    uint32_t frame_count_ = 0, samples_accumulated_ = 0;
+
+    // device scene
+    DevScene ds_{};
+    b200pt_vertex *d_verts_ = nullptr; uint32_t *d_indices_ = nullptr; DevMesh *d_meshes_ = nullptr; DevInstance *d_instances_ = nullptr;
+    b200pt_material *d_materials_ = nullptr; DevTexture *d_textures_ = nullptr; DevEmissive *d_emissive_ = nullptr;
+    std::vector<uint8_t *> d_texdata_;
+    std::vector<DevInstance> h_instances_; std::vector<DevMesh> h_meshes_;
+    float4 *d_env_ = nullptr; uint2 *d_alias_ = nullptr; float *d_luts_[3] = { nullptr, nullptr, nullptr };
+    LbvhResult bvh_{};
+    LaunchCfg lc_{};
+    uint32_t n_tris_ = 0, n_emissive_ = 0;
+
+    // framebuffer + post
+    float4 *d_image_ = nullptr; size_t image_pixels_ = 0;
+    b200pt_tonemap tonemap_{ 1.0f, 2.2f };
+    b200pt_bloom bloom_{ 2.0f, 1.0f, 10, 5.0f };
+    std::vector<float4 *> d_mips_; std::vector<uint32_t> mip_wh_; uchar4 *d_ldr_ = nullptr; uint32_t post_w_ = 0, post_h_ = 0;
+
+    // wave buffers
+    size_t wave_cap_ = 0;
+    PathState ps_[2]{}; ShadeOut so_{};
+    float4 *d_sample_buf_ = nullptr; uint32_t *d_rng_carry_ = nullptr; uint32_t *d_counts_ = nullptr; DevDispatch *d_disp_[2] = { nullptr, nullptr };
+    DevDispatch *h_disp_[2] = { nullptr, nullptr }; uint32_t *h_count_ = nullptr;
+    WaveCounters *d_ctr_ = nullptr;
+    b200pt_counters last_{};
+};
+
+} // namespace b200pt

@@ -1,0 +1,43 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (wavefront_kernels.cu, lbvh.cu, post_kernels.cu)
+#pragma once
+#include "device_types.h"
+#include <cuda_runtime.h>
+
+namespace b200pt {
+
+struct LaunchCfg {
+    int grid_light;     // grid for streaming kernels (raygen / resolve / post)
+    int grid_trace;     // persistent grid for traversal kernels (multiple of the SM count)
+    int grid_shade;     // persistent grid for the shading kernel
+    int max_stack;      // traversal stack entries (BVH depth + 2)
+    bool bvh_in_smem;   // whole BVH staged to shared memory by TMA
+};
+
+int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc);
+void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P, uint32_t first_sample,
+                   const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *counts, WaveCounters *ctr, cudaStream_t st);
+void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, const uint32_t *n_live, WaveCounters *ctr, cudaStream_t st);
+void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *n_live, WaveCounters *ctr, cudaStream_t st);
+void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,
+                    const uint32_t *n_live, uint32_t *n_next, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st);
+void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
+                    const float4 *sample_buf, float4 *image, cudaStream_t st);
+void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, const float *org, const float *dir, float tmin, float tmax,
+                       float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, cudaStream_t st);
+
+// ---- LBVH build (lbvh.cu): world-space flattening of the two-level TLAS/BLAS ----
+struct LbvhResult { BvhNode *nodes; BvhTri *tris; uint32_t n_nodes, n_tris; int32_t root; int max_depth; size_t bytes; };
+// Builds into ONE contiguous allocation [nodes | tris] (so small scenes can be staged to smem with one bulk copy).
+// Returns cudaError_t as int.
+int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const DevMesh *d_meshes, const DevInstance *d_instances,
+               const DevInstance *h_instances, const DevMesh *h_meshes, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st);
+void lbvh_free(LbvhResult *r);
+
+// ---- post chain (post_kernels.cu) ----
+struct PostParams { float Exposure, Gamma, BloomThreshold, BloomStrength, FalloffRange; };
+void launch_bloom_threshold(const float4 *hdr, float4 *mip0, uint32_t npix, PostParams p, int grid, cudaStream_t st);
+void launch_bloom_down(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st);
+void launch_bloom_up(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st);
+void launch_tonemap(const float4 *hdr, const float4 *bloom0, uchar4 *ldr, uint32_t W, uint32_t H, PostParams p, cudaStream_t st);
+
+} // namespace b200pt

@@ -1,0 +1,303 @@
+// lbvh.cu -- GPU-built linear BVH (Morton keys + radix sort + Karras hierarchy + bottom-up refit).
+//
+// Replaces the driver-opaque acceleration structure the reference builds with
+// vkCmdBuildAccelerationStructuresKHR (VulkanHelper/Source/Vulkan/BLASBuilderImpl.cpp:196-273, TLASImpl.cpp:100-190;
+// one BLAS per mesh instance, PathTracer/PathTracer.cpp:449-502).  The two-level TLAS/BLAS is flattened into one
+// world-space BVH2 (all shipped scenes are static), keeping (InstanceIndex, PrimitiveIndex) per triangle because
+// the emissive-mesh NEE visibility test compares them (PathTracer/Shaders/ClosestHit.slang:171-176).
+//
+// Output layout (one contiguous allocation so small scenes are staged into shared memory with one TMA bulk copy):
+//   [ BvhNode x max(N-1,1) | BvhTri x N ]   nodes: 64 B, both child boxes in the parent; tris: 48 B, Morton order.
+#include "kernels.h"
+#include <vector>
+#include <cstdio>
+
+namespace b200pt {
+
+#define LBVH_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+// world-space transform without FMA contraction: bit-identical to the CPU oracle's plain fp32 arithmetic
+__device__ __forceinline__ float dot3_1_rn(float a, float b, float c, float d, float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, x), __fmul_rn(b, y)), __fmul_rn(c, z)), __fmul_rn(d, 1.0f));
+}
+__device__ __forceinline__ float3 xf_point_rn(const float *m, float x, float y, float z) {
+    return make_float3(dot3_1_rn(m[0], m[1], m[2], m[3], x, y, z), dot3_1_rn(m[4], m[5], m[6], m[7], x, y, z), dot3_1_rn(m[8], m[9], m[10], m[11], x, y, z));
+}
+
+__device__ __forceinline__ void atomic_min_f(float *addr, float v) {   // works for any sign via ordered ints
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float *addr, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+// ---- 1. world triangles + scene bounds -------------------------------------------------------
+__global__ void k_world_tris(const b200pt_vertex *__restrict__ verts, const uint32_t *__restrict__ indices, const DevMesh *__restrict__ meshes,
+                             const DevInstance *__restrict__ inst, uint32_t n_inst, uint32_t n_tris,
+                             BvhTri *__restrict__ tmp, float *__restrict__ cent, float *__restrict__ bounds /*6*/) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
+    if (gid < n_tris) {
+        uint32_t a = 0, b = n_inst - 1;                                  // last instance with tri_base <= gid
+        while (a < b) { uint32_t mid = (a + b + 1) >> 1; if (inst[mid].tri_base <= gid) a = mid; else b = mid - 1; }
+        const DevInstance &in = inst[a];
+        const uint32_t prim = gid - in.tri_base;
+        const DevMesh m = meshes[in.mesh];
+        const uint32_t *ix = indices + m.ibase + (size_t)prim * 3;
+        const b200pt_vertex &A = verts[m.vbase + ix[0]], &B = verts[m.vbase + ix[1]], &C = verts[m.vbase + ix[2]];
+        const float3 v0 = xf_point_rn(in.o2w, A.Position[0], A.Position[1], A.Position[2]);
+        const float3 v1 = xf_point_rn(in.o2w, B.Position[0], B.Position[1], B.Position[2]);
+        const float3 v2 = xf_point_rn(in.o2w, C.Position[0], C.Position[1], C.Position[2]);
+        BvhTri t;
+        t.a = make_float4(v0.x, v0.y, v0.z, __uint_as_float(gid));
+        t.b = make_float4(__fsub_rn(v1.x, v0.x), __fsub_rn(v1.y, v0.y), __fsub_rn(v1.z, v0.z), __uint_as_float(a));
+        t.c = make_float4(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z), __uint_as_float(prim));
+        tmp[gid] = t;
+        lo[0] = fminf(v0.x, fminf(v1.x, v2.x)); hi[0] = fmaxf(v0.x, fmaxf(v1.x, v2.x));
+        lo[1] = fminf(v0.y, fminf(v1.y, v2.y)); hi[1] = fmaxf(v0.y, fmaxf(v1.y, v2.y));
+        lo[2] = fminf(v0.z, fminf(v1.z, v2.z)); hi[2] = fmaxf(v0.z, fmaxf(v1.z, v2.z));
+        float *bb = cent + (size_t)gid * 6;                              // per-triangle AABB (unsorted)
+        bb[0] = lo[0]; bb[1] = lo[1]; bb[2] = lo[2]; bb[3] = hi[0]; bb[4] = hi[1]; bb[5] = hi[2];
+    }
+    for (int k = 0; k < 3; k++) {                                        // warp-reduce, then one atomic per warp
+        for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_down_sync(0xFFFFFFFFu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_down_sync(0xFFFFFFFFu, hi[k], o)); }
+        if ((threadIdx.x & 31) == 0) { atomic_min_f(&bounds[k], lo[k]); atomic_max_f(&bounds[3 + k], hi[k]); }
+    }
+}
+
+// ---- 2. Morton keys ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__global__ void k_morton(const float *__restrict__ aabb, const float *__restrict__ bounds, uint32_t n, uint32_t *keys, uint32_t *vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *bb = aabb + (size_t)i * 6;
+    uint32_t q[3];
+    for (int k = 0; k < 3; k++) {
+        const float c = 0.5f * (bb[k] + bb[3 + k]);
+        const float ext = bounds[3 + k] - bounds[k];
+        float f = ext > 0.0f ? (c - bounds[k]) / ext : 0.0f;
+        f = fminf(fmaxf(f * 1024.0f, 0.0f), 1023.0f);
+        q[k] = (uint32_t)f;
+    }
+    keys[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+    vals[i] = i;
+}
+
+// ---- 3. stable LSD radix sort, 4-bit digits, 256-element tiles ----------------------------------
+__global__ void __launch_bounds__(256) k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t *__restrict__ hist, uint32_t nblocks) {
+    __shared__ uint32_t cnt[16];
+    if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & 15u], 1u);
+    __syncthreads();
+    if (threadIdx.x < 16) hist[threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ hist, uint32_t total) {   // exclusive scan, single block
+    __shared__ uint32_t sm[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < total; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < total ? hist[i] : 0u;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint32_t t = threadIdx.x >= (unsigned)o ? sm[threadIdx.x - o] : 0u;
+            __syncthreads();
+            sm[threadIdx.x] += t;
+            __syncthreads();
+        }
+        const uint32_t incl = sm[threadIdx.x];
+        if (i < total) hist[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_radix_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n, int shift,
+                                                        const uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    __shared__ uint32_t wcnt[8][17];
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const bool act = i < n;
+    const uint32_t key = act ? keys[i] : 0u, val = act ? vals[i] : 0u;
+    const uint32_t dig = act ? ((key >> shift) & 15u) : 16u;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dig);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (threadIdx.x < 8 * 17) (&wcnt[0][0])[threadIdx.x] = 0;
+    __syncthreads();
+    if (rank == 0) wcnt[warp][dig] = __popc(peers);
+    __syncthreads();
+    if (act) {
+        uint32_t off = hist[dig * nblocks + blockIdx.x];
+        for (uint32_t w = 0; w < warp; w++) off += wcnt[w][dig];
+        keys_out[off + rank] = key; vals_out[off + rank] = val;
+    }
+}
+
+// ---- 4. reorder into Morton order ---------------------------------------------------------------
+__global__ void k_reorder(const BvhTri *__restrict__ tmp, const float *__restrict__ aabb, const uint32_t *__restrict__ vals, uint32_t n,
+                          BvhTri *__restrict__ tris, float *__restrict__ leaf_box) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = vals[i];
+    tris[i] = tmp[g];
+    for (int k = 0; k < 6; k++) leaf_box[(size_t)i * 6 + k] = aabb[(size_t)g * 6 + k];
+}
+
+// ---- 5. Karras 2012 hierarchy -------------------------------------------------------------------
+__device__ __forceinline__ int lbvh_delta(const uint32_t *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(a ^ b);
+}
+__global__ void k_karras(const uint32_t *__restrict__ keys, int n, int *__restrict__ left, int *__restrict__ right, int *__restrict__ parent_int, int *__restrict__ parent_leaf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = lbvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2) if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lbvh_delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+        if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t <= 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    if (lo == gamma) { left[i] = ~gamma; parent_leaf[gamma] = i; } else { left[i] = gamma; parent_int[gamma] = i; }
+    if (hi == gamma + 1) { right[i] = ~(gamma + 1); parent_leaf[gamma + 1] = i; } else { right[i] = gamma + 1; parent_int[gamma + 1] = i; }
+    if (i == 0) parent_int[0] = -1;
+}
+
+// ---- 6. bottom-up refit ---------------------------------------------------------------------------
+__global__ void k_refit(int n, const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ parent_int, const int *__restrict__ parent_leaf,
+                        const float *__restrict__ leaf_box, float *__restrict__ node_box, unsigned int *__restrict__ flags) {
+    const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    int cur = parent_leaf[leaf];
+    while (cur >= 0) {
+        if (atomicAdd(&flags[cur], 1u) == 0u) return;                    // first child to arrive stops; second continues
+        __threadfence();
+        float bx[6];
+        const int l = left[cur], r = right[cur];
+        const float *a = l < 0 ? leaf_box + (size_t)(~l) * 6 : node_box + (size_t)l * 6;
+        const float *b = r < 0 ? leaf_box + (size_t)(~r) * 6 : node_box + (size_t)r * 6;
+        for (int k = 0; k < 3; k++) { bx[k] = fminf(__ldcg(a + k), __ldcg(b + k)); bx[3 + k] = fmaxf(__ldcg(a + 3 + k), __ldcg(b + 3 + k)); }
+        for (int k = 0; k < 6; k++) __stcg(node_box + (size_t)cur * 6 + k, bx[k]);
+        __threadfence();
+        cur = parent_int[cur];
+    }
+}
+
+// ---- 7. emit 64-B nodes (child boxes in the parent, slightly padded so the slab test is conservative) ----
+__global__ void k_emit(int n_int, const int *__restrict__ left, const int *__restrict__ right, const float *__restrict__ leaf_box,
+                       const float *__restrict__ node_box, BvhNode *__restrict__ nodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_int) return;
+    const int l = left[i], r = right[i];
+    const float *a = l < 0 ? leaf_box + (size_t)(~l) * 6 : node_box + (size_t)l * 6;
+    const float *b = r < 0 ? leaf_box + (size_t)(~r) * 6 : node_box + (size_t)r * 6;
+    BvhNode nd;
+    for (int k = 0; k < 3; k++) {
+        float pa = 4e-7f * fmaxf(fabsf(a[k]), fabsf(a[3 + k])) + 1e-30f, pb = 4e-7f * fmaxf(fabsf(b[k]), fabsf(b[3 + k])) + 1e-30f;
+        nd.lo0[k] = a[k] - pa; nd.hi0[k] = a[3 + k] + pa;
+        nd.lo1[k] = b[k] - pb; nd.hi1[k] = b[3 + k] + pb;
+    }
+    nd.c0 = l; nd.c1 = r; nd._pad[0] = nd._pad[1] = 0;
+    nodes[i] = nd;
+}
+
+void lbvh_free(LbvhResult *r) {
+    if (r->nodes) cudaFree(r->nodes);
+    r->nodes = nullptr; r->tris = nullptr; r->n_nodes = r->n_tris = 0; r->bytes = 0;
+}
+
+int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const DevMesh *d_meshes, const DevInstance *d_instances,
+               const DevInstance *, const DevMesh *, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st) {
+    out->nodes = nullptr; out->tris = nullptr; out->n_nodes = 0; out->n_tris = n_tris; out->root = 0; out->max_depth = 1; out->bytes = 0;
+    if (n_tris == 0 || n_instances == 0) return (int)cudaErrorInvalidValue;
+    const uint32_t n = n_tris, n_int = n > 1 ? n - 1 : 0, n_nodes_alloc = n_int ? n_int : 1;
+    const size_t node_bytes = (size_t)n_nodes_alloc * sizeof(BvhNode), tri_bytes = (size_t)n * sizeof(BvhTri);
+    unsigned char *blob = nullptr;
+    LBVH_CHECK(cudaMalloc(&blob, node_bytes + tri_bytes));
+    LBVH_CHECK(cudaMemsetAsync(blob, 0, node_bytes, st));
+    BvhNode *nodes = reinterpret_cast<BvhNode *>(blob);
+    BvhTri *tris = reinterpret_cast<BvhTri *>(blob + node_bytes);
+
+    BvhTri *tmp = nullptr; float *aabb = nullptr, *leaf_box = nullptr, *node_box = nullptr, *bounds = nullptr;
+    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *hist = nullptr;
+    int *left = nullptr, *right = nullptr, *parent_int = nullptr, *parent_leaf = nullptr; unsigned int *flags = nullptr;
+    const uint32_t nblocks = (n + 255) / 256;
+    LBVH_CHECK(cudaMalloc(&tmp, tri_bytes));
+    LBVH_CHECK(cudaMalloc(&aabb, (size_t)n * 6 * sizeof(float)));
+    LBVH_CHECK(cudaMalloc(&leaf_box, (size_t)n * 6 * sizeof(float)));
+    LBVH_CHECK(cudaMalloc(&node_box, (size_t)n_nodes_alloc * 6 * sizeof(float)));
+    LBVH_CHECK(cudaMalloc(&bounds, 6 * sizeof(float)));
+    LBVH_CHECK(cudaMalloc(&keys, (size_t)n * 4)); LBVH_CHECK(cudaMalloc(&vals, (size_t)n * 4));
+    LBVH_CHECK(cudaMalloc(&keys2, (size_t)n * 4)); LBVH_CHECK(cudaMalloc(&vals2, (size_t)n * 4));
+    LBVH_CHECK(cudaMalloc(&hist, (size_t)16 * nblocks * 4));
+    LBVH_CHECK(cudaMalloc(&left, (size_t)n_nodes_alloc * 4)); LBVH_CHECK(cudaMalloc(&right, (size_t)n_nodes_alloc * 4));
+    LBVH_CHECK(cudaMalloc(&parent_int, (size_t)n_nodes_alloc * 4)); LBVH_CHECK(cudaMalloc(&parent_leaf, (size_t)n * 4));
+    LBVH_CHECK(cudaMalloc(&flags, (size_t)n_nodes_alloc * 4));
+    LBVH_CHECK(cudaMemsetAsync(flags, 0, (size_t)n_nodes_alloc * 4, st));
+    LBVH_CHECK(cudaMemsetAsync(parent_leaf, 0xFF, (size_t)n * 4, st));
+    const float binit[6] = { 3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f };
+    LBVH_CHECK(cudaMemcpyAsync(bounds, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
+
+    k_world_tris<<<nblocks, 256, 0, st>>>(d_verts, d_indices, d_meshes, d_instances, n_instances, n, tmp, aabb, bounds);
+    k_morton<<<nblocks, 256, 0, st>>>(aabb, bounds, n, keys, vals);
+    for (int pass = 0; pass < 8; pass++) {
+        k_radix_hist<<<nblocks, 256, 0, st>>>(keys, n, pass * 4, hist, nblocks);
+        k_radix_scan<<<1, 1024, 0, st>>>(hist, 16 * nblocks);
+        k_radix_scatter<<<nblocks, 256, 0, st>>>(keys, vals, n, pass * 4, hist, nblocks, keys2, vals2);
+        std::swap(keys, keys2); std::swap(vals, vals2);
+    }
+    k_reorder<<<nblocks, 256, 0, st>>>(tmp, aabb, vals, n, tris, leaf_box);
+    if (n_int) {
+        k_karras<<<(n_int + 255) / 256, 256, 0, st>>>(keys, (int)n, left, right, parent_int, parent_leaf);
+        k_refit<<<nblocks, 256, 0, st>>>((int)n, left, right, parent_int, parent_leaf, leaf_box, node_box, flags);
+        k_emit<<<(n_int + 255) / 256, 256, 0, st>>>((int)n_int, left, right, leaf_box, node_box, nodes);
+    }
+    LBVH_CHECK(cudaStreamSynchronize(st));
+    LBVH_CHECK(cudaGetLastError());
+
+    // depth of the hierarchy (one-off, on the host) -> traversal stack size
+    int max_depth = 1;
+    if (n_int) {
+        std::vector<int> hl(n_int), hr(n_int);
+        LBVH_CHECK(cudaMemcpy(hl.data(), left, (size_t)n_int * 4, cudaMemcpyDeviceToHost));
+        LBVH_CHECK(cudaMemcpy(hr.data(), right, (size_t)n_int * 4, cudaMemcpyDeviceToHost));
+        std::vector<std::pair<int, int>> stack; stack.push_back({ 0, 1 });
+        while (!stack.empty()) {
+            auto [node, dep] = stack.back(); stack.pop_back();
+            if (dep > max_depth) max_depth = dep;
+            if (hl[node] >= 0) stack.push_back({ hl[node], dep + 1 });
+            if (hr[node] >= 0) stack.push_back({ hr[node], dep + 1 });
+        }
+    }
+    cudaFree(tmp); cudaFree(aabb); cudaFree(leaf_box); cudaFree(node_box); cudaFree(bounds);
+    cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(hist);
+    cudaFree(left); cudaFree(right); cudaFree(parent_int); cudaFree(parent_leaf); cudaFree(flags);
+
+    out->nodes = nodes; out->tris = tris; out->n_nodes = n_nodes_alloc; out->n_tris = n;
+    out->root = n_int ? 0 : ~0;
+    out->max_depth = max_depth;
+    out->bytes = node_bytes + tri_bytes;
+    return 0;
+}
+
+} // namespace b200pt

@@ -1,0 +1,511 @@
+// wavefront_kernels.cu -- the per-bounce kernels of the B200 wavefront integrator (sm_100a).
+//
+// The reference runs ONE ray-gen megakernel per frame that loops over bounces and calls TraceRay /
+// closest-hit / miss inline (SH/RayGen.slang:9-160).  Here the same estimator is a wavefront:
+//
+//   k_raygen   camera sample + payload init                    SH/RayGen.slang:12-63
+//   per bounce:
+//     k_extend   closest-hit traversal of the live paths       SH/RayGen.slang:68-72,90 (TraceRay)
+//     k_shade    closest-hit + miss shading, emits <=2 NEE     SH/ClosestHit.slang:20-378, SH/Miss.slang:8-76
+//                shadow requests
+//     k_connect  shadow rays, payload.Emitted assembly,        SH/ClosestHit.slang:139,171-176,326-372
+//                luminance clamp, throughput, Russian          SH/RayGen.slang:92-113
+//                roulette, ballot/prefix-sum compaction
+//   k_resolve  NaN/Inf rejection + running mean                SH/RayGen.slang:116-159
+//
+// Every path owns one sample slot, so radiance accumulation needs no atomics and is deterministic.
+// All per-path state is SoA float4 (coalesced 16-B lanes); live paths are kept dense by compaction.
+#include "bvh_traverse.cuh"
+#include "kernels.h"
+
+namespace b200pt {
+
+// ------------------------------------------------------------------------------------------------
+// partition helpers (rank r owns rows y with ((y / band) % world) == r)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t part_global_row(uint32_t local_row, uint32_t rank, uint32_t world, uint32_t band) {
+    uint32_t blk = local_row / band, in = local_row % band;
+    return (blk * world + rank) * band + in;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_raygen
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raygen(DevConfig cfg, const DevDispatch *__restrict__ disp, uint32_t n_disp, uint32_t P,
+                                                 uint32_t first_sample, const uint32_t *__restrict__ rng_carry,
+                                                 PathState ps, float4 *__restrict__ sample_buf, uint32_t *__restrict__ counts,
+                                                 WaveCounters *ctr) {
+    const uint32_t n = n_disp * P;
+    const uint32_t S = cfg.ScreenSplitCount;
+    const uint32_t LW = (cfg.W + S - 1) / S;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t b = j / P, p = j - b * P;
+        const DevDispatch dd = disp[b];
+        uint32_t x, y;
+        if (S == 1) {
+            const uint32_t lr = p / cfg.W; x = p - lr * cfg.W;
+            y = part_global_row(lr, cfg.rank, cfg.world, cfg.band_rows);
+        } else {                                                           // SH/RayGen.slang:17-22
+            const uint32_t ly = p / LW, lx = p - ly * LW;
+            x = lx * S + dd.ChunkIndex % S; y = ly * S + dd.ChunkIndex / S;
+        }
+        const bool inside = (x < cfg.W && y < cfg.H);                      // :24-25
+        Rng rng;
+        if (first_sample) { rng.s = y + cfg.W * x + dd.Seed; sample_buf[j] = make_float4(0, 0, 0, 0); }   // :28 (Q13)
+        else rng.s = rng_carry[j];
+        // :35-50
+        const float jx = rng.next() * (0.5f - -0.5f) + -0.5f;
+        const float jy = rng.next() * (0.5f - -0.5f) + -0.5f;
+        const float pcx = (float)x + 0.5f + jx, pcy = (float)y + 0.5f + jy;
+        const float dx = (pcx / (float)cfg.W) * 2.0f - 1.0f, dy = (pcy / (float)cfg.H) * 2.0f - 1.0f;
+        const float *VI = cfg.VI, *PI = cfg.PI;
+        float3 origin = f3(VI[0] * 0.0f + VI[4] * 0.0f + VI[8] * 0.0f + VI[12] * 1.0f,
+                           VI[1] * 0.0f + VI[5] * 0.0f + VI[9] * 0.0f + VI[13] * 1.0f,
+                           VI[2] * 0.0f + VI[6] * 0.0f + VI[10] * 0.0f + VI[14] * 1.0f);
+        float3 target = f3(PI[0] * dx + PI[4] * dy + PI[8] * 1.0f + PI[12] * 1.0f,
+                           PI[1] * dx + PI[5] * dy + PI[9] * 1.0f + PI[13] * 1.0f,
+                           PI[2] * dx + PI[6] * dy + PI[10] * 1.0f + PI[14] * 1.0f);
+        float3 direction = mat4_dir(VI, normalize(target));
+        const float3 focus = origin + direction * fmaxf(cfg.FocusDistance, 0.001f);
+        const float u1 = rng.next(), u2 = rng.next();                       // RandomCircleVec, SH/Sampler.slang:103-112
+        const float theta = 2.0f * PT_PI * u1, rad = sqrtf(u2);
+        const float ox = (rad * cosf(theta)) * 0.5f * cfg.DepthOfFieldStrength, oy = (rad * sinf(theta)) * 0.5f * cfg.DepthOfFieldStrength;
+        origin = origin + (f3(VI[0], VI[1], VI[2]) * ox + f3(VI[4], VI[5], VI[6]) * oy);
+        direction = normalize(focus - origin);
+        // payload init :52-63.  Pixels outside the image (chunked dispatch overhang) are born dead (Depth = MAX).
+        ps.org_pdf[j] = make_float4(origin.x, origin.y, origin.z, 1.0f);
+        ps.dir_rng[j] = make_float4(direction.x, direction.y, direction.z, __uint_as_float(rng.s));
+        ps.thr_depth[j] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(inside ? 0u : PT_MAX_DEPTH));
+        ps.rad_slot[j] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(j));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counts[0] = n; atomicAdd(&ctr->paths, (unsigned long long)n); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_extend : closest hit for every live path
+// ------------------------------------------------------------------------------------------------
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, ShadeOut so, const uint32_t *__restrict__ n_live_ptr,
+                                                 int max_stack, WaveCounters *ctr) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
+    const int stride = blockDim.x;
+    BvhView bv;
+    if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
+    else bv = global_bvh(sc);
+    const uint32_t n = *n_live_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
+        const float3 rd = normalize(f3(d4));                                // SH/RayGen.slang:70
+        HitRec h;
+        bvh_trace<SMEM, false>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
+        so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->extend_rays, (unsigned long long)n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_shade : SH/ClosestHit.slang + SH/Miss.slang for every live path
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so,
+                                                const uint32_t *__restrict__ n_live_ptr, WaveCounters *ctr) {
+    const uint32_t n = *n_live_ptr;
+    uint32_t n_hit = 0, n_miss = 0, n_med = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 h4 = so.hit[i];
+        const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
+        const uint32_t dflags = __float_as_uint(ps.thr_depth[i].w);
+        const uint32_t depth = dflags & 0x7FFFFFFFu;
+        const bool inMedium = (dflags >> 31) != 0u;
+        const float3 payOrigin = f3(o4), payDir = f3(d4);
+        const float payPDF = o4.w;
+        Rng rng; rng.s = __float_as_uint(d4.w);
+        const uint32_t slot = __float_as_uint(h4.w);
+        const float4 zero4 = make_float4(0, 0, 0, 0);
+
+        if (slot == 0xFFFFFFFFu) {
+            // ---------------- Miss: SH/Miss.slang:8-76
+            float4 c;
+            if (cfg.ShowEnvMapDirectly || depth > 0) {
+                const float az = cfg.SkyRotationAzimuth / 180.0f * PT_PI, al = cfg.SkyRotationAltitude / 180.0f * PT_PI;
+                float3 r = rotate3(payDir, f3(1, 0, 0), -al);
+                r = rotate3(r, f3(0, 1, 0), -az);
+                float u, v; direction_to_uv(r, u, v);
+                c = env_sample(sc, u, v);
+            } else c = make_float4(0, 0, 0, 1);
+            float3 em = f3(c.x * cfg.EnvironmentIntensity, c.y * cfg.EnvironmentIntensity, c.z * cfg.EnvironmentIntensity);
+            if (cfg.FurnaceTestMode) em = f3(1.0f);
+            if (cfg.EnableSkyMIS && depth > 0) em = em * power_heuristic(payPDF, c.w);
+            so.e0[i] = make_float4(em.x, em.y, em.z, __uint_as_float(PT_MAX_DEPTH));
+            so.bxdf_pdf[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);           // stale payload.BxDF/PDF: path ends, value unused
+            so.sky_o[i] = zero4; so.lit_o[i] = zero4;
+            n_miss++;
+            continue;
+        }
+
+        // ---------------- ClosestHit: SH/ClosestHit.slang:20-378
+        const float3 rd = normalize(payDir);                                // WorldRayDirection()
+        const BvhTri *tri = sc.tris + slot;
+        const uint32_t inst = __float_as_uint(__ldg(&tri->b).w), prim = __float_as_uint(__ldg(&tri->c).w);
+        const DevInstance &in = sc.instances[inst];
+        const b200pt_material &cm = sc.materials[in.material];
+        Surface sf;
+        surface_init(sf, sc, cfg, in, prim, h4.y, h4.z, rd, sc.textures[cm.NormalTextureIndex]);
+        Mat m;
+        material_init(m, sc, cfg, cm, sf);
+        const bool isLight = m.EmissiveColor.x > 0.0f || m.EmissiveColor.y > 0.0f || m.EmissiveColor.z > 0.0f;   // :65
+        surface_rotate_tangents(sf, m.AnisotropyRotation);                  // :67
+
+        bool newInMedium = inMedium;
+        float4 med = zero4; float med_g = 0.0f;
+        if (inMedium) {                                                     // :80-116 (Q6)
+            med = ps.medium[i]; med_g = ps.medium_g[i];
+            const float dist = length(payOrigin - sf.WorldPos);
+            if (med_g == 1.0f) {
+                // Beer-law BxDF is overwritten below (:323) -- nothing observable happens here.
+            } else {
+                const float sd = -logf(rng.next()) / med.w;
+                if (sd < dist) {
+                    const float3 no = payOrigin + payDir * sd;
+                    const float3 nd = sample_henyey_greenstein(rng, payDir, med_g);
+                    ps.org_pdf[i] = make_float4(no.x, no.y, no.z, payPDF);
+                    ps.dir_rng[i] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(rng.s));
+                    so.bxdf_pdf[i] = make_float4(med.x, med.y, med.z, payPDF);       // stale PDF (Q6)
+                    so.e0[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(dflags));            // Depth and InMedium unchanged
+                    so.sky_o[i] = zero4; so.lit_o[i] = zero4;
+                    n_med++;
+                    continue;
+                }
+            }
+        }
+        n_hit++;
+
+        // sky NEE sample :125-147 (visibility is resolved in k_connect)
+        float3 toSkyW = f3(0.0f), toSkyT = f3(0.0f); float4 sky = zero4;
+        if (cfg.EnableSkyMIS) {
+            sample_env(sc, cfg, rng, toSkyW, sky);
+            sky.x *= cfg.EnvironmentIntensity; sky.y *= cfg.EnvironmentIntensity; sky.z *= cfg.EnvironmentIntensity;   // Q7
+            toSkyT = sf.world_to_tangent(toSkyW);
+        }
+        // light NEE sample :154-184
+        float3 toLightW = f3(0.0f), toLightT = f3(0.0f); float4 light = zero4; uint32_t lt = 0xFFFFFFFFu, li = 0xFFFFFFFFu;
+        if (cfg.EnableMeshMIS && !isLight) {
+            sample_emissive(sc, rng, sf.WorldPos, toLightW, light, lt, li);
+            if (light.w > 0.0f) toLightT = sf.world_to_tangent(toLightW);
+        }
+        // BSDF sample :191-204
+        float3 V = normalize(-rd);
+        V = sf.world_to_tangent(V);
+        const float3 H = ggx_sample_vndf(rng, V, m.Ax, m.Ay);
+        BSample ss = sample_bsdf(m, sc, cfg, rng, V, H);
+        const bool wasRefracted = ss.L.z < 0.0f;
+        const float3 scatterW = sf.tangent_to_world(ss.L);
+        if (!wasRefracted && dot(scatterW, sf.GeometryNormal) < 0.0f) { ss.PDF = 0.0f; ss.BxDF = f3(0.0f); }   // :220-225
+        if (wasRefracted && sf.HitFromInside) newInMedium = false;          // :227-238
+        else if (wasRefracted && !sf.HitFromInside) {
+            newInMedium = true;
+            med = make_float4(m.MediumColor.x, m.MediumColor.y, m.MediumColor.z, m.MediumDensity); med_g = m.MediumAnisotropy;
+        }
+
+        // emission :265-317
+        float3 e0 = f3(0.0f);
+        if (cfg.EnableMeshMIS) {
+            if (depth == 0 && isLight) e0 = e0 + m.EmissiveColor;
+            else if (isLight) {
+                const float3 w1 = xf_point(in.o2w, sf.P1), w2 = xf_point(in.o2w, sf.P2), w3 = xf_point(in.o2w, sf.P3);
+                const float area = length(cross(w2 - w1, w3 - w1)) * 0.5f;
+                const float3 dl = sf.WorldPos - payOrigin;
+                const float d2 = dot(dl, dl);
+                const float cosTheta = fabsf(dot(sf.Normal, normalize(payOrigin - sf.WorldPos)));
+                float lp = (1.0f / (float)sc.n_emissive) * (1.0f / (float)in.emissive_tri_count) * (1.0f / area) * (d2 / cosTheta);
+                lp = fmaxf(lp, cfg.EmissiveMeshSamplingPDFBias);
+                e0 = e0 + m.EmissiveColor * power_heuristic(payPDF, lp);
+            }
+        } else e0 = e0 + m.EmissiveColor;
+
+        // NEE contributions (eager BSDF evaluation; added in k_connect iff the shadow query allows) :241-256,326-372
+        float4 skyO = zero4, skyD = zero4, skyC = zero4, litO = zero4, litD = zero4, litC = zero4;
+        if (cfg.EnableSkyMIS && sky.w > 0.0f) {
+            const Eval ev = eval_bsdf(m, sc, cfg, V, toSkyT);
+            if (ev.PDF > 0.0f) {
+                const float3 c = (((ev.BxDF * 1.0f) * f3(sky)) / sky.w) * power_heuristic(sky.w, ev.PDF);
+                const float3 so_ = sf.WorldPos + sf.Normal * 1e-5f;         // :139
+                skyO = make_float4(so_.x, so_.y, so_.z, 1.0f);
+                skyD = make_float4(toSkyW.x, toSkyW.y, toSkyW.z, 0.0f);
+                skyC = make_float4(c.x, c.y, c.z, 0.0f);
+            }
+        }
+        if (cfg.EnableMeshMIS && !isLight && light.w > 0.0f) {
+            const Eval ev = eval_bsdf(m, sc, cfg, V, toLightT);
+            if (ev.PDF > 0.0f) {
+                const float3 c = (((ev.BxDF * 1.0f) * f3(light)) / light.w) * power_heuristic(light.w, ev.PDF);
+                const float3 lo = sf.WorldPos + toLightW * 1e-2f;           // :171
+                litO = make_float4(lo.x, lo.y, lo.z, 1.0f);
+                litD = make_float4(toLightW.x, toLightW.y, toLightW.z, __uint_as_float(lt));
+                litC = make_float4(c.x, c.y, c.z, __uint_as_float(li));
+            }
+        }
+        // payload write :319-324, :375-376
+        const float off = -1e-3f * (wasRefracted ? 1.0f : 0.0f) + 1e-3f * (wasRefracted ? 0.0f : 1.0f);
+        const float3 no = sf.WorldPos + sf.Normal * off;
+        const bool invalid = ss.PDF <= 0.0f;
+        const uint32_t newDepth = invalid ? PT_MAX_DEPTH + depth : depth + 1u;   // MAX_DEPTH*(invalid) + (Depth + 1*(!invalid))
+        ps.org_pdf[i] = make_float4(no.x, no.y, no.z, ss.PDF);
+        ps.dir_rng[i] = make_float4(scatterW.x, scatterW.y, scatterW.z, __uint_as_float(rng.s));
+        so.bxdf_pdf[i] = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
+        so.e0[i] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(newDepth | (newInMedium ? 0x80000000u : 0u)));
+        if (newInMedium) { ps.medium[i] = med; ps.medium_g[i] = med_g; }
+        so.sky_o[i] = skyO; so.lit_o[i] = litO;
+        if (skyO.w != 0.0f) { so.sky_d[i] = skyD; so.sky_c[i] = skyC; }
+        if (litO.w != 0.0f) { so.lit_d[i] = litD; so.lit_c[i] = litC; }
+    }
+    // per-warp reduction of the counters, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) { n_hit += __shfl_down_sync(0xFFFFFFFFu, n_hit, o); n_miss += __shfl_down_sync(0xFFFFFFFFu, n_miss, o); n_med += __shfl_down_sync(0xFFFFFFFFu, n_med, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_hit) atomicAdd(&ctr->surface_hits, (unsigned long long)n_hit);
+        if (n_miss) atomicAdd(&ctr->misses, (unsigned long long)n_miss);
+        if (n_med) atomicAdd(&ctr->medium_events, (unsigned long long)n_med);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->shade_invocations, (unsigned long long)n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_connect : shadow queries + SH/RayGen.slang:92-113 + stream compaction of the survivors
+// ------------------------------------------------------------------------------------------------
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, PathState src, PathState dst, ShadeOut so,
+                                                  const uint32_t *__restrict__ n_live_ptr, uint32_t *__restrict__ n_next_ptr,
+                                                  float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry,
+                                                  int max_stack, WaveCounters *ctr) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
+    const int stride = blockDim.x;
+    BvhView bv;
+    if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
+    else bv = global_bvh(sc);
+    const uint32_t n = *n_live_ptr;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t n_shadow = 0;
+    const uint32_t n_round = (n + 31u) & ~31u;                              // keep warps converged for the ballots
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool active = i < n;
+        bool alive = false;
+        float4 o4, d4, r4, thr4; uint32_t newDflags = 0; Rng rng; rng.s = 0;
+        float3 thr = f3(0.0f), rad = f3(0.0f);
+        if (active) {
+            const float4 e4 = so.e0[i];
+            thr4 = src.thr_depth[i]; r4 = src.rad_slot[i];
+            o4 = src.org_pdf[i]; d4 = src.dir_rng[i];
+            const float4 b4 = so.bxdf_pdf[i];
+            newDflags = __float_as_uint(e4.w);
+            const uint32_t newDepth = newDflags & 0x7FFFFFFFu;
+            rng.s = __float_as_uint(d4.w);
+            thr = f3(thr4); rad = f3(r4);
+            float3 emitted = f3(e4);
+            const float4 so4 = so.sky_o[i];
+            if (so4.w != 0.0f) {                                            // SH/ClosestHit.slang:139 + :326-358
+                const float4 sd4 = so.sky_d[i];
+                HitRec h; n_shadow++;
+                const bool occluded = bvh_trace<SMEM, true>(bv, f3(so4), f3(sd4), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
+                if (!occluded) emitted = emitted + f3(so.sky_c[i]);
+            }
+            const float4 lo4 = so.lit_o[i];
+            if (lo4.w != 0.0f) {                                            // :171-176 + :360-372 (closest hit must be the sampled triangle)
+                const float4 ld4_ = so.lit_d[i], lc4 = so.lit_c[i];
+                HitRec h; n_shadow++;
+                const bool found = bvh_trace<SMEM, false>(bv, f3(lo4), f3(ld4_), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
+                if (found) {
+                    const float4 *tp = bv.tris + (size_t)h.slot * 3;
+                    const uint32_t hinst = __float_as_uint(ld4<SMEM>(tp + 1).w), hprim = __float_as_uint(ld4<SMEM>(tp + 2).w);
+                    if (hprim == __float_as_uint(ld4_.w) && hinst == __float_as_uint(lc4.w)) emitted = emitted + f3(lc4);
+                }
+            }
+            // SH/RayGen.slang:92-113
+            float3 contribution = emitted * thr;
+            if (newDepth != 1u) {                                           // Q3
+                const float lum = dot(contribution, f3(0.212671f, 0.715160f, 0.072169f));
+                const float scale = cfg.MaxLuminance / fmaxf(lum, cfg.MaxLuminance);
+                contribution = contribution * scale;
+            }
+            rad = rad + contribution;
+            thr = thr * (f3(b4) / b4.w);
+            float p = fmaxf(thr.x, fmaxf(thr.y, thr.z));
+            p = fminf(p, 1.0f);
+            const float u = rng.next();                                     // Q4
+            alive = !(p < u);
+            if (alive) thr = thr / p;
+            alive = alive && (newDepth < cfg.MaxDepth);                      // loop condition :66
+            if (!alive) {                                                   // path finished: :116-128 (+ carry RNG for SampleCount > 1)
+                const uint32_t slot = __float_as_uint(r4.w);
+                const bool ok = !isinf(rad.x) && !isinf(rad.y) && !isinf(rad.z) && !isnan(rad.x) && !isnan(rad.y) && !isnan(rad.z);
+                float4 acc = sample_buf[slot];
+                if (ok) { acc.x += rad.x; acc.y += rad.y; acc.z += rad.z; }
+                sample_buf[slot] = acc;
+                rng_carry[slot] = rng.s;
+            }
+        }
+        // ---- warp ballot + prefix-sum compaction of the live paths
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
+        if (ballot) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(n_next_ptr, (uint32_t)__popc(ballot));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (alive) {
+                const uint32_t k = base + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+                dst.org_pdf[k] = o4;
+                dst.dir_rng[k] = make_float4(d4.x, d4.y, d4.z, __uint_as_float(rng.s));
+                dst.thr_depth[k] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(newDflags));
+                dst.rad_slot[k] = make_float4(rad.x, rad.y, rad.z, r4.w);
+                if (newDflags >> 31) { dst.medium[k] = src.medium[i]; dst.medium_g[k] = src.medium_g[i]; }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o);
+    if (lane == 0 && n_shadow) atomicAdd(&ctr->shadow_rays, (unsigned long long)n_shadow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_resolve : SH/RayGen.slang:130-159 for every dispatch of the wave, in dispatch order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resolve(DevConfig cfg, const DevDispatch *__restrict__ disp, uint32_t n_disp, uint32_t P,
+                                                  const float4 *__restrict__ sample_buf, float4 *__restrict__ image) {
+    const uint32_t S = cfg.ScreenSplitCount;
+    const uint32_t npix = cfg.W * cfg.local_rows;
+    const uint32_t LW = (cfg.W + S - 1) / S;
+    const float inv_spp = (float)cfg.SampleCount;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < npix; q += gridDim.x * blockDim.x) {
+        float4 px = image[q];
+        float3 color = f3(px);
+        if (S == 1) {
+            for (uint32_t b = 0; b < n_disp; b++) {
+                const float3 acc = f3(sample_buf[(size_t)b * P + q]) / inv_spp;                         // :130
+                const uint32_t fc = disp[b].FrameCount;
+                if (fc > 0) { const float a = 1.0f / (float)(fc + 1u); color = mix3(color, acc, a); }   // :133-137
+                else color = acc;
+            }
+        } else {
+            const uint32_t y = q / cfg.W, x = q - y * cfg.W;
+            const uint32_t chunk = (x % S) + (y % S) * S;
+            const uint32_t sidx = (y / S) * LW + (x / S);
+            for (uint32_t b = 0; b < n_disp; b++) {
+                const DevDispatch dd = disp[b];
+                const float3 acc = f3(sample_buf[(size_t)b * P + sidx]) / inv_spp;
+                if (dd.ChunkIndex == chunk) {
+                    if (dd.FrameCount > 0) { const float a = 1.0f / (float)(dd.FrameCount + 1u); color = mix3(color, acc, a); }
+                    else color = acc;
+                } else if (dd.FrameCount == 0 && dd.ChunkIndex == 0) color = acc;                       // splat :144-157
+            }
+        }
+        image[q] = make_float4(color.x, color.y, color.z, 1.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hook: closest-hit for arbitrary rays (b200pt_trace_closest)
+// ------------------------------------------------------------------------------------------------
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k_trace_rays(DevScene sc, uint32_t n, const float *__restrict__ org, const float *__restrict__ dir,
+                                                     float tmin, float tmax, float *t_out, uint32_t *prim_out, uint32_t *inst_out,
+                                                     float *uv_out, int max_stack) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
+    BvhView bv;
+    if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
+    else bv = global_bvh(sc);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        HitRec h;
+        const bool f = bvh_trace<SMEM, false>(bv, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]),
+                                              tmin, tmax, h, stack, (int)blockDim.x, max_stack);
+        t_out[i] = f ? h.t : -1.0f;
+        uint32_t pi = 0xFFFFFFFFu, ii = 0xFFFFFFFFu;
+        if (f) { const float4 *tp = bv.tris + (size_t)h.slot * 3; ii = __float_as_uint(ld4<SMEM>(tp + 1).w); pi = __float_as_uint(ld4<SMEM>(tp + 2).w); }
+        prim_out[i] = pi; inst_out[i] = ii;
+        uv_out[2 * i] = f ? h.u : 0.0f; uv_out[2 * i + 1] = f ? h.v : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-callable launchers
+// ------------------------------------------------------------------------------------------------
+static size_t trace_smem_bytes(const DevScene &sc, int max_stack, int threads, bool smem) {
+    return (size_t)max_stack * threads * sizeof(int) + (smem ? sc.bvh_bytes : 0);
+}
+
+static bool g_attr_done = false;
+static void set_attrs_once() {
+    if (g_attr_done) return;
+    const int maxb = 227 * 1024;
+    cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(k_connect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(k_connect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(k_trace_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(k_trace_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    g_attr_done = true;
+}
+
+// grid sizing: persistent grids = SM count x resident CTAs per SM for the chosen shared-memory footprint
+int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc) {
+    set_attrs_once();
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceProp prop; cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return (int)e;
+    const int sms = prop.multiProcessorCount;
+    lc->max_stack = bvh_max_depth + 2; if (lc->max_stack < 4) lc->max_stack = 4; if (lc->max_stack > 64) lc->max_stack = 64;
+    lc->bvh_in_smem = sc.bvh_bytes > 0 && sc.bvh_bytes <= 64u * 1024u && (sc.bvh_bytes % 16u) == 0;
+    const size_t sh = trace_smem_bytes(sc, lc->max_stack, 256, lc->bvh_in_smem);
+    int occ_e = 0, occ_c = 0, occ_s = 0;
+    if (lc->bvh_in_smem) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<true>, 256, sh);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<true>, 256, sh);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<false>, 256, sh);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<false>, 256, sh);
+    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade, 128, 0);
+    int occ_t = occ_e < occ_c ? occ_e : occ_c; if (occ_t < 1) occ_t = 1; if (occ_s < 1) occ_s = 1;
+    lc->grid_trace = sms * occ_t;
+    lc->grid_shade = sms * occ_s;
+    lc->grid_light = sms * 8;
+    return 0;
+}
+
+void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P, uint32_t first_sample,
+                   const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *counts, WaveCounters *ctr, cudaStream_t st) {
+    k_raygen<<<lc.grid_light, 256, 0, st>>>(cfg, disp, n_disp, P, first_sample, rng_carry, ps, sample_buf, counts, ctr);
+}
+void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, const uint32_t *n_live, WaveCounters *ctr, cudaStream_t st) {
+    set_attrs_once();
+    const bool smem = lc.bvh_in_smem;
+    const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
+    if (smem) k_extend<true><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, n_live, lc.max_stack, ctr);
+    else k_extend<false><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, n_live, lc.max_stack, ctr);
+}
+void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *n_live, WaveCounters *ctr, cudaStream_t st) {
+    k_shade<<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, n_live, ctr);
+}
+void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,
+                    const uint32_t *n_live, uint32_t *n_next, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
+    set_attrs_once();
+    const bool smem = lc.bvh_in_smem;
+    const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
+    if (smem) k_connect<true><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, n_live, n_next, sample_buf, rng_carry, lc.max_stack, ctr);
+    else k_connect<false><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, n_live, n_next, sample_buf, rng_carry, lc.max_stack, ctr);
+}
+void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
+                    const float4 *sample_buf, float4 *image, cudaStream_t st) {
+    k_resolve<<<lc.grid_light, 256, 0, st>>>(cfg, disp, n_disp, P, sample_buf, image);
+}
+void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, const float *org, const float *dir, float tmin, float tmax,
+                       float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, cudaStream_t st) {
+    set_attrs_once();
+    const bool smem = lc.bvh_in_smem;
+    const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
+    if (smem) k_trace_rays<true><<<lc.grid_trace, 256, sh, st>>>(sc, n, org, dir, tmin, tmax, t_out, prim_out, inst_out, uv_out, lc.max_stack);
+    else k_trace_rays<false><<<lc.grid_trace, 256, sh, st>>>(sc, n, org, dir, tmin, tmax, t_out, prim_out, inst_out, uv_out, lc.max_stack);
+}
+
+} // namespace b200pt
