@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- Mpaths/sec of the path-tracing hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--frames-per-step F] [--workload NAME]
+  N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A STEP is one pass of the hot path over one batch: F dispatches (frames) of PathTracer::PathTrace at 1 spp/frame over the
+whole image, i.e. W*H*F camera paths.  Workload (BASELINE.json configs[1]): Cornell box 1920x1080, full principled BSDF,
+NEE+MIS (env + emissive mesh), depth 8; K*F = 1024 spp with the default K=8, F=128.  Data: the committed Cornell fixture
+(12 triangles, identical to the shipped glTF) + shipped energy-compensation LUTs + a SYNTHETIC 4096x2048 HDR environment
+map of the same size/dynamic range as the reference's default meadow_2_4k.hdr (25 MB, not committed).
+
+value   : whole-job Mpaths/s, inputs resident in HBM, timed with CUDA events on the launching stream, max over ranks.
+e2e     : same metric through the C-ABI with HOST buffers: per step the parameter block is re-uploaded, and the HDR
+          accumulation image + the post-processed RGBA8 image are read back to pinned host memory.
+N>1     : image-tile partition (16-row bands, rank r owns bands b with b % N == r), scene replicated, ONE NCCL gather of
+          the framebuffer bands to rank 0 per step, no other collective (strong scaling: total work fixed).
+--impl reference : the CPU oracle (port of the reference's estimator; the Vulkan reference cannot run here) on all host
+          cores, each step = 1 frame of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (scene fixture, W, H, MaxDepth)
+    "cornell_1080p_d8": ("cornell_box", 1920, 1080, 8),
+    "glass_1080sq_d16": ("cornell_box_glass", 1080, 1080, 16),
+    "breakfast_1080p_d8": ("breakfast_room", 1920, 1080, 8),
+    "viking_1080sq_d8": ("viking_room", 1080, 1080, 8),
+}
+BASE_SEED = 0x1234ABCD
+BAND_ROWS = 16
+PEAKS_FALLBACK_GBS = 6650.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+        return PEAKS_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows = []; self.proc = None; self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc: return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try: self.proc.wait(timeout=2)
+        except Exception: pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9: continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"): reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_env_4k():
+    from oracle import gltf_ref
+    return gltf_ref.synthetic_env(4096, 2048, seed=3, sun=150000.0)
+
+
+def algorithmic_bytes(c):
+    """SURVEY.md 8(d) streaming model, per kernel, from the device counters of one step."""
+    return {
+        "raygen": 68 * c["paths"],
+        "extend": 44 * c["extend_rays"],
+        "shade": 156 * c["shade_invocations"] + 52 * c["shadow_rays"],
+        "connect": 76 * c["shadow_rays"] + 8 * c["shade_invocations"],
+        "resolve": 48 * c["paths"],
+        "total": 116 * c["paths"] + 224 * c["extend_rays"] + 128 * c["shadow_rays"],
+    }
+
+
+def diff_counters(a, b):
+    return {k: (b[k] - a[k]) for k in ("paths", "extend_rays", "shade_invocations", "surface_hits", "misses", "shadow_rays", "medium_events", "kernel_launches")}
+
+
+def run_reference(args):
+    """CPU arm: the oracle (port of the reference's Slang estimator) on all host cores; step = 1 frame."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import util
+    from oracle import orc
+    scene, W, H, depth = WORKLOADS[args.workload]
+    raw = synthetic_env_4k()
+    env_pdf, alias, _ = orc.build_env_alias(raw)
+    S = orc.Scene(util.scene_dict(scene), env_pdf, alias, util.luts())
+    cfg = util.oracle_config(scene, MaxDepth=depth)
+    cores = os.cpu_count() or 1
+    img = np.zeros((H, W, 4), np.float32)
+    f = 0
+    for _ in range(args.warmup):
+        S.render(cfg, W, H, 1, BASE_SEED, frame0=f, image=img, nthreads=cores); f += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        S.render(cfg, W, H, 1, BASE_SEED, frame0=f, image=img, nthreads=cores); f += 1
+    dt = time.perf_counter() - t0
+    v = W * H * args.steps / dt / 1e6
+    out = {"impl": "reference", "metric": "Mpaths/sec", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, "image": [W, H], "max_depth": depth, "spp_per_frame": 1, "frames_per_step": 1},
+           "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port",
+                            "sample": f"{args.steps} frames x 1 spp of the full {W}x{H} image (oracle/liboracle.so, pthreads over pixel rows)"},
+           "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=128)
+    ap.add_argument("--frames-in-flight", type=int, default=0)
+    ap.add_argument("--workload", default="cornell_1080p_d8", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-baseline-frames", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3: args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import util
+    import vpt_b200 as pt
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1: args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    scene, W, H, depth = WORKLOADS[args.workload]
+    F = args.frames_per_step
+    T = pt.PathTracer(local)
+    T.set_scene(util.scene_dict(scene))
+    raw = synthetic_env_4k()
+    T.set_env_map(raw)
+    T.set_luts(*util.luts())
+    cfg = pt.default_config(MaxDepth=depth, MaxSamplesAccumulated=0x7FFFFFFF, FramesInFlight=args.frames_in_flight)
+    T.set_config(cfg)
+    T.resize(W, H)
+    T.set_partition(rank, world, BAND_ROWS)
+    stream = torch.cuda.Stream()                 # a real (non-NULL) stream shared by the renderer, the events and NCCL
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    T.set_stream(stream.cuda_stream)
+    rows = T.local_rows()
+    max_rows = max(pt.lib().b200pt_partition_local_row_count(H, r, world, BAND_ROWS) for r in range(world))
+    band = torch.zeros((max_rows, W, 4), dtype=torch.float32, device="cuda")
+    gathered = [torch.zeros_like(band) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def gather():
+        if world == 1: return
+        T.get_hdr_into_device(band.data_ptr())
+        dist.gather(band, gathered, dst=0)
+
+    def step():
+        T.path_trace(F, BASE_SEED)
+        gather()
+
+    def barrier():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup): step()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    c0 = T.counters()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps): step()
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = ev0.elapsed_time(ev1)
+    if abs(ms * 1e-3 - wall) > 0.05 * wall + 2e-3:   # device-event time must agree with the wall-clock bracket
+        ms = max(ms, wall * 1e3)
+    clocks = sampler.stop()
+    c1 = T.counters()
+    dc = diff_counters(c0, c1)
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1: dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    paths_total = W * H * F * args.steps
+    value = paths_total / (ms_max * 1e-3) / 1e6
+
+    # ---- e2e through the C-ABI with host buffers (rank-local images; rank 0 assembles for N>1)
+    hdr_host = torch.empty((rows, W, 4), dtype=torch.float32, pin_memory=True).numpy()
+    ldr_host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy() if world == 1 else None
+    def e2e_step():
+        T.set_config(cfg)                       # parameter block re-upload (the reference's setters, PathTracer.cpp:940-986)
+        T.set_partition(rank, world, BAND_ROWS)
+        T.path_trace(F, BASE_SEED)
+        gather()
+        T.get_hdr(hdr_host)                     # D2H of the accumulation image
+        if world == 1:
+            T.post_process(); T.get_ldr(ldr_host)   # bloom + tonemap + RGBA8 read-back (image-output path)
+    e2e_steps = max(2, min(args.steps, 4))
+    e2e_step(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps): e2e_step()
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+    if world > 1: dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = W * H * F * e2e_steps / float(te.item()) / 1e6
+    h2d = F * 16 + 512                           # dispatch table (16 B/dispatch) + kernel parameter blocks
+    d2h = rows * W * 16 + (W * H * 4 if world == 1 else 0)
+
+    # ---- per-kernel split of one profiled step -> roofline of the dominant kernel
+    T.set_config(cfg); T.set_partition(rank, world, BAND_ROWS)
+    T.set_profiling(True)
+    ca = T.counters(); T.path_trace(F, BASE_SEED); cb = T.counters()
+    T.set_profiling(False)
+    dprof = diff_counters(ca, cb)
+    kms = {k: cb["ms_" + k] for k in ("raygen", "extend", "shade", "connect", "resolve")}
+    ab = algorithmic_bytes(dprof)
+    dom = max(kms, key=lambda k: kms[k])
+    n_launch = {"raygen": cb["waves"], "resolve": cb["waves"]}
+    launches_dom = n_launch.get(dom, cb["bounces"])
+    peak, peak_kind = measured_peak()
+    achieved = ab[dom] / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
+    seg_per_path = dprof["extend_rays"] / max(dprof["paths"], 1)
+    pipeline_bytes = ab["total"]
+    step_ms_prof = sum(kms.values())
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "launches_per_step": int(launches_dom), "avg_launch_ms": kms[dom] / max(launches_dom, 1),
+                "algorithmic_bytes_per_launch": ab[dom] / max(launches_dom, 1),
+                "kernel_ms_per_step": kms, "kernel_share": {k: (v / step_ms_prof if step_ms_prof else 0.0) for k, v in kms.items()},
+                "pipeline": {"algorithmic_bytes_per_step": pipeline_bytes, "segments_per_path": seg_per_path,
+                             "shadow_rays_per_path": dprof["shadow_rays"] / max(dprof["paths"], 1),
+                             "roofline_mpaths": peak * 1e9 / (pipeline_bytes / max(dprof["paths"], 1)) / 1e6,
+                             "frac": value / world / (peak * 1e9 / (pipeline_bytes / max(dprof["paths"], 1)) / 1e6)}}
+
+    out = {"metric": "Mpaths/sec", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, "scene": scene, "image": [W, H], "max_depth": depth, "spp_per_frame": 1, "frames_per_step": F,
+                      "spp_total": F * args.steps, "partition": f"{BAND_ROWS}-row bands x {world} ranks", "env_map": "synthetic 4096x2048 RGBA32F (128 MiB) + 64 MiB alias table",
+                      "l2_policy": "working set > L2: env map 128 MiB + alias 64 MiB + wavefront state >= 600 MiB per wave (126 MB L2), no explicit flush",
+                      "timing": "CUDA events on the launching stream, max over ranks", "wall_s": wall},
+           "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+           "gpu_launches": int(dc["kernel_launches"]), "clocks": clocks, "roofline": roofline,
+           "counters_per_step": {k: dc[k] / args.steps for k in dc}}
+
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import orc
+            env_pdf, alias, _ = orc.build_env_alias(raw)
+            S = orc.Scene(util.scene_dict(scene), env_pdf, alias, util.luts())
+            ocfg = util.oracle_config(scene, MaxDepth=depth)
+            cores = os.cpu_count() or 1
+            n = args.cpu_baseline_frames
+            S.render(ocfg, W, H, 1, BASE_SEED, nthreads=cores)
+            t0 = time.perf_counter(); S.render(ocfg, W, H, n, BASE_SEED, frame0=1, nthreads=cores); dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": W * H * n / dt / 1e6, "unit": "Mpaths/s", "cores": cores, "kind": "port",
+                                   "sample": f"{n} frames x 1 spp of the full {W}x{H} image (CPU oracle, all host cores)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,7 @@ struct DevConfig {          // PT/PathTracer.h:271-302 (the fields the surface i
     uint32_t EnableSkyMIS, EnableMeshMIS, ShowEnvMapDirectly, UseOnlyGeometryNormals, UseEnergyCompensation, FurnaceTestMode;
     uint32_t W, H;           // full image size
     uint32_t rank, world, band_rows, local_rows;
+    float cosAz, sinAz, cosAl, sinAl;   // cos/sin(SkyRotation{Azimuth,Altitude} / 180 * PI), evaluated on the host
 };
 
 struct DevDispatch { uint32_t FrameCount, Seed, ChunkIndex, _pad; };   // PT/PathTracer.h:304-309

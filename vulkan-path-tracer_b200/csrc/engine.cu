@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdio>
 #include <algorithm>
+#include <cmath>
 
 namespace b200pt {
 
@@ -220,7 +221,7 @@ void Engine::ensure_image() {
 void Engine::free_wave() {
     for (auto &p : ps_) { dfree(p.org_pdf); dfree(p.dir_rng); dfree(p.thr_depth); dfree(p.rad_slot); dfree(p.medium); dfree(p.medium_g); }
     dfree(so_.hit); dfree(so_.bxdf_pdf); dfree(so_.e0); dfree(so_.sky_o); dfree(so_.sky_d); dfree(so_.sky_c); dfree(so_.lit_o); dfree(so_.lit_d); dfree(so_.lit_c);
-    dfree(d_sample_buf_); dfree(d_rng_carry_); dfree(d_disp_[0]); dfree(d_disp_[1]);
+    dfree(d_sample_buf_); dfree(d_rng_carry_); dfree(d_q_hit_); dfree(d_q_miss_); dfree(d_disp_[0]); dfree(d_disp_[1]);
     for (auto &hp : h_disp_) if (hp) { cudaFreeHost(hp); hp = nullptr; }
     wave_cap_ = 0;
 }
@@ -233,6 +234,7 @@ void Engine::ensure_wave(size_t cap) {
     a4(so_.hit); a4(so_.bxdf_pdf); a4(so_.e0); a4(so_.sky_o); a4(so_.sky_d); a4(so_.sky_c); a4(so_.lit_o); a4(so_.lit_d); a4(so_.lit_c);
     a4(d_sample_buf_);
     CK(cudaMalloc(&d_rng_carry_, cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&d_q_hit_, cap * sizeof(uint32_t))); CK(cudaMalloc(&d_q_miss_, cap * sizeof(uint32_t)));
     for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); CK(cudaMallocHost(&h_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); }
     wave_cap_ = cap;
 }
@@ -245,6 +247,8 @@ DevConfig Engine::make_dev_config() const {
     d.EnvironmentIntensity = cfg_.SkyIntensity; d.EmissiveMeshSamplingPDFBias = cfg_.EmissiveMeshSamplingPDFBias; d.ScreenSplitCount = cfg_.ScreenChunkCount;
     d.EnableSkyMIS = cfg_.EnableSkyMIS; d.EnableMeshMIS = cfg_.EnableMeshMIS; d.ShowEnvMapDirectly = cfg_.ShowEnvMapDirectly;
     d.UseOnlyGeometryNormals = cfg_.UseOnlyGeometryNormals; d.UseEnergyCompensation = cfg_.UseEnergyCompensation; d.FurnaceTestMode = cfg_.FurnaceTestMode;
+    { const float az = cfg_.SkyRotationAzimuth / 180.0f * 3.1415926535897F, al = cfg_.SkyRotationAltitude / 180.0f * 3.1415926535897F;   // SH/Sampler.slang:338-339
+      d.cosAz = cosf(az); d.sinAz = sinf(az); d.cosAl = cosf(al); d.sinAl = sinf(al); }
     d.W = W_; d.H = H_; d.rank = rank_; d.world = world_; d.band_rows = band_; d.local_rows = local_rows_;
     return d;
 }
@@ -309,12 +313,10 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                 if (!medium && cfg_.MaxDepth - std::min(cfg_.MaxDepth, k) < chunk) chunk = cfg_.MaxDepth - std::min(cfg_.MaxDepth, k);
                 if (chunk == 0) break;
                 for (uint32_t b = 0; b < chunk; b++, k++) {
-                    const uint32_t *n_live = d_counts_ + (k & 1u); uint32_t *n_next = d_counts_ + ((k + 1u) & 1u);
-                    launch_extend(lc_, ds_, ps_[cur], so_, n_live, d_ctr_, stream_); mark(1);
-                    launch_shade(lc_, ds_, dc, ps_[cur], so_, n_live, d_ctr_, stream_); mark(2);
-                    CK(cudaMemsetAsync(n_next, 0, sizeof(uint32_t), stream_));
-                    launch_connect(lc_, ds_, dc, ps_[cur], ps_[cur ^ 1], so_, n_live, n_next, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
-                    cur ^= 1; launches += 3;
+                    launch_extend(lc_, ds_, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_ctr_, stream_); mark(1);
+                    launch_shade(lc_, ds_, dc, ps_[cur], so_, d_counts_, d_q_hit_, d_q_miss_, d_ctr_, stream_); mark(2);
+                    launch_connect(lc_, ds_, dc, ps_[cur], ps_[cur ^ 1], so_, d_counts_, k & 1u, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
+                    cur ^= 1; launches += 4;
                 }
                 if (!medium && k >= cfg_.MaxDepth) break;    // every surviving path has Depth >= MaxDepth: provably empty
                 CK(cudaMemcpyAsync(h_count_, d_counts_ + (k & 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));

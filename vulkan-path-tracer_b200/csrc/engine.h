@@ -103,7 +103,7 @@ private:
     // wave buffers
     size_t wave_cap_ = 0;
     PathState ps_[2]{}; ShadeOut so_{};
-    float4 *d_sample_buf_ = nullptr; uint32_t *d_rng_carry_ = nullptr; uint32_t *d_counts_ = nullptr; DevDispatch *d_disp_[2] = { nullptr, nullptr };
+    float4 *d_sample_buf_ = nullptr; uint32_t *d_rng_carry_ = nullptr; uint32_t *d_q_hit_ = nullptr, *d_q_miss_ = nullptr; uint32_t *d_counts_ = nullptr; DevDispatch *d_disp_[2] = { nullptr, nullptr };
     DevDispatch *h_disp_[2] = { nullptr, nullptr }; uint32_t *h_count_ = nullptr;
     WaveCounters *d_ctr_ = nullptr;
     b200pt_counters last_{};

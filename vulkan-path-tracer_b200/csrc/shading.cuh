@@ -39,11 +39,15 @@ __device__ __forceinline__ float3 refract3(float3 i, float3 n, float eta) {
     return i * eta - n * (eta * d + sqrtf(k));
 }
 // SH/RTCommon.slang:37-45
-__device__ __forceinline__ float3 rotate3(float3 v, float3 axis, float theta) {
-    float c = cosf(theta), s = sinf(theta);
+// cos/sin of the sky angles are evaluated once on the host (engine.cu) instead of per call.
+__device__ __forceinline__ float3 rotate3_cs(float3 v, float3 axis, float c, float s) {
     float3 n = normalize(axis);
     return (v * c + cross(n, v) * s) + (n * dot(n, v)) * (1.0f - c);
 }
+// libm calls with large inlined slow paths are funnelled through single out-of-line copies: k_shade's code must stay
+// within the instruction caches (ncu round 1: 189 KB of SASS, stall_no_instruction 20 warps/issue).
+static __device__ __noinline__ void pt_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+static __device__ __noinline__ float pt_pow(float x, float y) { return powf(x, y); }
 
 // ---------------------------------------------------------------- RNG  SH/Sampler.slang:4-9,21-43
 __device__ __forceinline__ uint32_t pcg_hash(uint32_t seed) {
@@ -61,7 +65,7 @@ __device__ __forceinline__ float3 random_sphere(Rng &r) {
     float theta = 2.0f * PT_PI * u1;
     float z = 1.0f - 2.0f * u2;
     float rad = sqrtf(1.0f - z * z);
-    float s, c; sincosf(theta, &s, &c);
+    float s, c; pt_sincos(theta, &s, &c);
     return f3(rad * c, rad * s, z);
 }
 // SH/Sampler.slang:143-166
@@ -73,7 +77,7 @@ __device__ __forceinline__ float3 ggx_sample_vndf(Rng &r, float3 Ve, float Ax, f
     float3 T2 = cross(Vh, T1);
     float rad = sqrtf(u1);
     float phi = 2.0f * PT_PI * u2;
-    float sp, cp; sincosf(phi, &sp, &cp);
+    float sp, cp; pt_sincos(phi, &sp, &cp);
     float t1 = rad * cp, t2 = rad * sp;
     float s = 0.5f * (1.0f + Vh.z);
     t2 = (1.0f - s) * sqrtf(1.0f - t1 * t1) + s * t2;
@@ -88,7 +92,7 @@ __device__ __forceinline__ float3 sample_henyey_greenstein(Rng &r, float3 incide
     else { float sq = (1.0f - G * G) / (1.0f - G + 2.0f * G * rx); cosTheta = (1.0f + G * G - sq * sq) / (2.0f * G); }
     float phi = 2.0f * PT_PI * ry;
     float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
-    float sp, cp; sincosf(phi, &sp, &cp);
+    float sp, cp; pt_sincos(phi, &sp, &cp);
     float3 nd = f3(sinTheta * cp, sinTheta * sp, cosTheta);
     float3 up = fabsf(incident.y) < 0.9999999f ? f3(0, 1, 0) : f3(0, 0, 1);
     float3 tangent = normalize(cross(up, incident));
@@ -102,7 +106,7 @@ __device__ __forceinline__ int wrap_repeat(int i, int n) { int m = i % n; return
 __device__ __forceinline__ int clampi(int i, int lo, int hi) { return i < lo ? lo : (i > hi ? hi : i); }
 
 // RGBA8 / R8 UNORM, bilinear, REPEAT (PT/PathTracer.cpp:84-91). R8 -> (r,0,0,1).
-__device__ __forceinline__ float4 tex_sample_u8(const DevTexture &t, float u, float v) {
+static __device__ __noinline__ float4 tex_sample_u8(const DevTexture t, float u, float v) {
     const int W = (int)t.w, H = (int)t.h;
     if (W == 1 && H == 1) {     // 1x1 defaults (PT/PathTracer.cpp:1557-1621): bilinear of equal texels is the texel
         if (t.c == 4) { uchar4 p = *reinterpret_cast<const uchar4 *>(t.data); return make_float4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, (float)p.w / 255.0f); }
@@ -255,7 +259,8 @@ __device__ __forceinline__ void surface_init(Surface &sf, const DevScene &sc, co
 // SH/Surface.slang:140-147
 __device__ __forceinline__ void surface_rotate_tangents(Surface &sf, float deg) {
     float rot = deg * (PT_PI / 180.0f);
-    float s, c; sincosf(rot, &s, &c);
+    if (deg == 0.0f) { sf.Bitangent = cross(sf.Tangent, sf.Normal); return; }   // cos 0 = 1, sin 0 = 0: T*1 + x*0 + y*0 == T exactly
+    float s, c; pt_sincos(rot, &s, &c);
     float3 T = sf.Tangent, N = sf.Normal;
     float3 r = (T * c + cross(N, T) * s) + (N * dot(N, T)) * (1.0f - c);
     sf.Tangent = r;
@@ -282,7 +287,7 @@ __device__ __forceinline__ void material_init(Mat &m, const DevScene &sc, const 
     m.MediumDensity = src.MediumDensity; m.MediumAnisotropy = src.MediumAnisotropy;
     float4 tb = tex_sample_u8(sc.textures[src.BaseColorTextureIndex], sf.u, sf.v);
     m.IOR = fmaxf(m.IOR, 1.000001f);
-    m.BaseColor = m.BaseColor * f3(powf(tb.x, 2.2f), powf(tb.y, 2.2f), powf(tb.z, 2.2f));
+    m.BaseColor = m.BaseColor * f3(pt_pow(tb.x, 2.2f), pt_pow(tb.y, 2.2f), pt_pow(tb.z, 2.2f));
     m.Roughness *= tex_sample_u8(sc.textures[src.RoughnessTextureIndex], sf.u, sf.v).x;     // Q8, Q9
     m.Metallic *= tex_sample_u8(sc.textures[src.MetallicTextureIndex], sf.u, sf.v).x;
     float4 te = tex_sample_u8(sc.textures[src.EmissiveTextureIndex], sf.u, sf.v);
@@ -401,6 +406,30 @@ __device__ __forceinline__ Eval eval_bsdf(const Mat &m, const DevScene &sc, cons
     return out;
 }
 // :94-165
+// Direction part of SampleBSDF (:94-160).  Returns false for the "invalid reflection/refraction direction" early-outs
+// (:152-160); the BxDF/PDF of a valid direction come from EvaluateBSDF(V, L) (:163), evaluated by the caller.
+__device__ __forceinline__ bool sample_bsdf_direction(const Mat &m, Rng &rng, float3 V, float3 H, float3 &Lout) {
+    float pm = m.Metallic;
+    float pd = (1.0f - m.Metallic) * (1.0f - m.Transmission);
+    float pg = (1.0f - m.Metallic) * m.Transmission;
+    float sum = pm + pd + pg;
+    pm /= sum; pd /= sum; pg /= sum;
+    float F = dielectric_fresnel(dot(V, H), m.Eta);
+    float x1 = rng.next();
+    float3 L; bool refracted = false;
+    if (x1 < pm) L = normalize(reflect3(-V, H));
+    else if (x1 < pm + pd) {
+        if (rng.next() < F) L = normalize(reflect3(-V, H));
+        else L = normalize(random_sphere(rng) + f3(0.0f, 0.0f, 1.0f));
+    } else {
+        if (rng.next() < F) L = normalize(reflect3(-V, H));
+        else { L = normalize(refract3(-V, H, m.Eta)); refracted = true; }
+    }
+    Lout = L;
+    if (L.z < 0.0f && !refracted) return false;
+    else if (refracted && L.z >= 0.0f) return false;
+    return true;
+}
 __device__ __forceinline__ BSample sample_bsdf(const Mat &m, const DevScene &sc, const DevConfig &cfg, Rng &rng, float3 V, float3 H) {
     float pm = m.Metallic;
     float pd = (1.0f - m.Metallic) * (1.0f - m.Transmission);
@@ -441,7 +470,7 @@ __device__ __forceinline__ void sample_env(const DevScene &sc, const DevConfig &
     uint32_t px = envIdx % width, py = envIdx / width;
     float u = ((float)px + xy) / (float)width;
     float phi = u * (2.0f * PT_PI) - PT_PI;
-    float sinPhi, cosPhi; sincosf(phi, &sinPhi, &cosPhi);
+    float sinPhi, cosPhi; pt_sincos(phi, &sinPhi, &cosPhi);
     float stepTheta = PT_PI / (float)height;
     float theta0 = (float)py * stepTheta;
     float cosTheta = cosf(theta0) * (1.0f - xz) + cosf(theta0 + stepTheta) * xz;
@@ -449,9 +478,8 @@ __device__ __forceinline__ void sample_env(const DevScene &sc, const DevConfig &
     float sinTheta = sinf(theta);
     float v = theta * PT_1_OVER_PI;
     float3 d = f3(sinPhi * sinTheta, -cosTheta, -cosPhi * sinTheta);
-    float az = cfg.SkyRotationAzimuth / 180.0f * PT_PI, al = cfg.SkyRotationAltitude / 180.0f * PT_PI;
-    d = rotate3(d, f3(0, 1, 0), az);
-    d = rotate3(d, f3(1, 0, 0), al);
+    d = rotate3_cs(d, f3(0, 1, 0), cfg.cosAz, cfg.sinAz);
+    d = rotate3_cs(d, f3(1, 0, 0), cfg.cosAl, cfg.sinAl);
     toLight = d;
     val = env_sample(sc, u, v);
     val.x *= cfg.EnvironmentIntensity; val.y *= cfg.EnvironmentIntensity; val.z *= cfg.EnvironmentIntensity;

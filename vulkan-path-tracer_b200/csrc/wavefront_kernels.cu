@@ -6,8 +6,10 @@
 //   k_raygen   camera sample + payload init                    SH/RayGen.slang:12-63
 //   per bounce:
 //     k_extend   closest-hit traversal of the live paths       SH/RayGen.slang:68-72,90 (TraceRay)
-//     k_shade    closest-hit + miss shading, emits <=2 NEE     SH/ClosestHit.slang:20-378, SH/Miss.slang:8-76
-//                shadow requests
+//                + hit / miss queue split (ballot compaction)
+//     k_shade_miss  miss shading of the miss queue             SH/Miss.slang:8-76
+//     k_shade_hit   closest-hit shading of the hit queue,      SH/ClosestHit.slang:20-378
+//                   emits <=2 NEE shadow requests
 //     k_connect  shadow rays, payload.Emitted assembly,        SH/ClosestHit.slang:139,171-176,326-372
 //                luminance clamp, throughput, Russian          SH/RayGen.slang:92-113
 //                roulette, ballot/prefix-sum compaction
@@ -29,11 +31,16 @@ __host__ __device__ inline uint32_t part_global_row(uint32_t local_row, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// control block (device memory, u32): [0],[1] live-path counts (ping-pong by bounce parity),
+//                                     [2] hit-queue length, [3] miss-queue length of the current bounce
+// ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
 // k_raygen
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_raygen(DevConfig cfg, const DevDispatch *__restrict__ disp, uint32_t n_disp, uint32_t P,
                                                  uint32_t first_sample, const uint32_t *__restrict__ rng_carry,
-                                                 PathState ps, float4 *__restrict__ sample_buf, uint32_t *__restrict__ counts,
+                                                 PathState ps, float4 *__restrict__ sample_buf, uint32_t *__restrict__ ctrl,
                                                  WaveCounters *ctr) {
     const uint32_t n = n_disp * P;
     const uint32_t S = cfg.ScreenSplitCount;
@@ -78,15 +85,16 @@ __global__ void __launch_bounds__(256) k_raygen(DevConfig cfg, const DevDispatch
         ps.thr_depth[j] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(inside ? 0u : PT_MAX_DEPTH));
         ps.rad_slot[j] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(j));
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { counts[0] = n; atomicAdd(&ctr->paths, (unsigned long long)n); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[0] = n; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; atomicAdd(&ctr->paths, (unsigned long long)n); }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_extend : closest hit for every live path
+// k_extend : closest hit for every live path; splits the live list into a hit queue and a miss queue
+//            (warp ballot + prefix sum, one atomic per warp and queue) so the two shading kernels run converged
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM>
-__global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, ShadeOut so, const uint32_t *__restrict__ n_live_ptr,
-                                                 int max_stack, WaveCounters *ctr) {
+__global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, ShadeOut so, uint32_t *__restrict__ ctrl, uint32_t parity,
+                                                 uint32_t *__restrict__ q_hit, uint32_t *__restrict__ q_miss, int max_stack, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
@@ -94,25 +102,73 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
     BvhView bv;
     if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
     else bv = global_bvh(sc);
-    const uint32_t n = *n_live_ptr;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
-        const float3 rd = normalize(f3(d4));                                // SH/RayGen.slang:70
-        HitRec h;
-        bvh_trace<SMEM, false>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
-        so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+    const uint32_t n = ctrl[parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[parity ^ 1u] = 0;         // next live count: filled by k_connect of this bounce
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool active = i < n;
+        bool hit = false;
+        if (active) {
+            const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
+            const float3 rd = normalize(f3(d4));                            // SH/RayGen.slang:70
+            HitRec h;
+            hit = bvh_trace<SMEM, false>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
+            so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+        }
+        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
+        uint32_t base_h = 0, base_m = 0;
+        if (lane == 0) { if (bh) base_h = atomicAdd(&ctrl[2], (uint32_t)__popc(bh)); if (bm) base_m = atomicAdd(&ctrl[3], (uint32_t)__popc(bm)); }
+        base_h = __shfl_sync(0xFFFFFFFFu, base_h, 0); base_m = __shfl_sync(0xFFFFFFFFu, base_m, 0);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (hit) q_hit[base_h + __popc(bh & lt)] = i;
+        else if (active) q_miss[base_m + __popc(bm & lt)] = i;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->extend_rays, (unsigned long long)n);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_shade : SH/ClosestHit.slang + SH/Miss.slang for every live path
+// k_shade_miss : SH/Miss.slang:8-76 for the miss queue
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so,
-                                                const uint32_t *__restrict__ n_live_ptr, WaveCounters *ctr) {
-    const uint32_t n = *n_live_ptr;
-    uint32_t n_hit = 0, n_miss = 0, n_med = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so,
+                                                     const uint32_t *__restrict__ ctrl, const uint32_t *__restrict__ q_miss, WaveCounters *ctr) {
+    const uint32_t n = ctrl[3];
+    const float4 zero4 = make_float4(0, 0, 0, 0);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = q_miss[j];
+        const float4 d4 = ps.dir_rng[i];
+        const uint32_t depth = __float_as_uint(ps.thr_depth[i].w) & 0x7FFFFFFFu;
+        const float payPDF = ps.org_pdf[i].w;
+        float4 c;
+        if (cfg.ShowEnvMapDirectly || depth > 0) {
+            float3 r = rotate3_cs(f3(d4), f3(1, 0, 0), cfg.cosAl, -cfg.sinAl);   // Rotate(dir, X, -altitude): cos is even, sin odd
+            r = rotate3_cs(r, f3(0, 1, 0), cfg.cosAz, -cfg.sinAz);
+            float u, v; direction_to_uv(r, u, v);
+            c = env_sample(sc, u, v);
+        } else c = make_float4(0, 0, 0, 1);
+        float3 em = f3(c.x * cfg.EnvironmentIntensity, c.y * cfg.EnvironmentIntensity, c.z * cfg.EnvironmentIntensity);
+        if (cfg.FurnaceTestMode) em = f3(1.0f);
+        if (cfg.EnableSkyMIS && depth > 0) em = em * power_heuristic(payPDF, c.w);
+        so.e0[i] = make_float4(em.x, em.y, em.z, __uint_as_float(PT_MAX_DEPTH));
+        so.bxdf_pdf[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);               // stale payload.BxDF/PDF: the path ends, value unused
+        so.sky_o[i] = zero4; so.lit_o[i] = zero4;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr->misses, (unsigned long long)n); atomicAdd(&ctr->shade_invocations, (unsigned long long)n); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_shade_hit : SH/ClosestHit.slang:20-378 for the hit queue
+// ------------------------------------------------------------------------------------------------
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so,
+                                                    const uint32_t *__restrict__ ctrl, const uint32_t *__restrict__ q_hit, WaveCounters *ctr) {
+    const uint32_t n = ctrl[2];
+    uint32_t n_med = 0;
+    const float4 zero4 = make_float4(0, 0, 0, 0);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = q_hit[j];
         const float4 h4 = so.hit[i];
         const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
         const uint32_t dflags = __float_as_uint(ps.thr_depth[i].w);
@@ -122,29 +178,7 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, DevConfig cfg, PathS
         const float payPDF = o4.w;
         Rng rng; rng.s = __float_as_uint(d4.w);
         const uint32_t slot = __float_as_uint(h4.w);
-        const float4 zero4 = make_float4(0, 0, 0, 0);
 
-        if (slot == 0xFFFFFFFFu) {
-            // ---------------- Miss: SH/Miss.slang:8-76
-            float4 c;
-            if (cfg.ShowEnvMapDirectly || depth > 0) {
-                const float az = cfg.SkyRotationAzimuth / 180.0f * PT_PI, al = cfg.SkyRotationAltitude / 180.0f * PT_PI;
-                float3 r = rotate3(payDir, f3(1, 0, 0), -al);
-                r = rotate3(r, f3(0, 1, 0), -az);
-                float u, v; direction_to_uv(r, u, v);
-                c = env_sample(sc, u, v);
-            } else c = make_float4(0, 0, 0, 1);
-            float3 em = f3(c.x * cfg.EnvironmentIntensity, c.y * cfg.EnvironmentIntensity, c.z * cfg.EnvironmentIntensity);
-            if (cfg.FurnaceTestMode) em = f3(1.0f);
-            if (cfg.EnableSkyMIS && depth > 0) em = em * power_heuristic(payPDF, c.w);
-            so.e0[i] = make_float4(em.x, em.y, em.z, __uint_as_float(PT_MAX_DEPTH));
-            so.bxdf_pdf[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);           // stale payload.BxDF/PDF: path ends, value unused
-            so.sky_o[i] = zero4; so.lit_o[i] = zero4;
-            n_miss++;
-            continue;
-        }
-
-        // ---------------- ClosestHit: SH/ClosestHit.slang:20-378
         const float3 rd = normalize(payDir);                                // WorldRayDirection()
         const BvhTri *tri = sc.tris + slot;
         const uint32_t inst = __float_as_uint(__ldg(&tri->b).w), prim = __float_as_uint(__ldg(&tri->c).w);
@@ -172,14 +206,13 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, DevConfig cfg, PathS
                     ps.org_pdf[i] = make_float4(no.x, no.y, no.z, payPDF);
                     ps.dir_rng[i] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(rng.s));
                     so.bxdf_pdf[i] = make_float4(med.x, med.y, med.z, payPDF);       // stale PDF (Q6)
-                    so.e0[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(dflags));            // Depth and InMedium unchanged
+                    so.e0[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(dflags));   // Depth and InMedium unchanged
                     so.sky_o[i] = zero4; so.lit_o[i] = zero4;
                     n_med++;
                     continue;
                 }
             }
         }
-        n_hit++;
 
         // sky NEE sample :125-147 (visibility is resolved in k_connect)
         float3 toSkyW = f3(0.0f), toSkyT = f3(0.0f); float4 sky = zero4;
@@ -198,7 +231,24 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, DevConfig cfg, PathS
         float3 V = normalize(-rd);
         V = sf.world_to_tangent(V);
         const float3 H = ggx_sample_vndf(rng, V, m.Ax, m.Ay);
-        BSample ss = sample_bsdf(m, sc, cfg, rng, V, H);
+        float3 Ls;
+        const bool validDir = sample_bsdf_direction(m, rng, V, H, Ls);
+        // EvaluateBSDF(V, .) for the sampled direction and the two NEE directions: ONE rolled loop keeps a single copy of the
+        // BSDF code in the kernel (SampleBSDF :163; ClosestHit :241-256).  NEE is evaluated eagerly, visibility comes later.
+        const bool needSky = cfg.EnableSkyMIS && sky.w > 0.0f;
+        const bool needLit = cfg.EnableMeshMIS && !isLight && light.w > 0.0f;
+        Eval evS, evSky, evLit;
+        evS.BxDF = evSky.BxDF = evLit.BxDF = f3(0.0f); evS.PDF = evSky.PDF = evLit.PDF = 0.0f;
+        #pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+            const bool need = (k == 0) ? validDir : ((k == 1) ? needSky : needLit);
+            if (!need) continue;
+            const float3 dk = (k == 0) ? Ls : ((k == 1) ? toSkyT : toLightT);
+            const Eval e = eval_bsdf(m, sc, cfg, V, dk);
+            if (k == 0) evS = e; else if (k == 1) evSky = e; else evLit = e;
+        }
+        BSample ss;
+        ss.L = validDir ? Ls : f3(0.0f); ss.BxDF = evS.BxDF; ss.PDF = evS.PDF;
         const bool wasRefracted = ss.L.z < 0.0f;
         const float3 scatterW = sf.tangent_to_world(ss.L);
         if (!wasRefracted && dot(scatterW, sf.GeometryNormal) < 0.0f) { ss.PDF = 0.0f; ss.BxDF = f3(0.0f); }   // :220-225
@@ -224,27 +274,21 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, DevConfig cfg, PathS
             }
         } else e0 = e0 + m.EmissiveColor;
 
-        // NEE contributions (eager BSDF evaluation; added in k_connect iff the shadow query allows) :241-256,326-372
+        // NEE contributions (added in k_connect iff the shadow query allows) :326-372
         float4 skyO = zero4, skyD = zero4, skyC = zero4, litO = zero4, litD = zero4, litC = zero4;
-        if (cfg.EnableSkyMIS && sky.w > 0.0f) {
-            const Eval ev = eval_bsdf(m, sc, cfg, V, toSkyT);
-            if (ev.PDF > 0.0f) {
-                const float3 c = (((ev.BxDF * 1.0f) * f3(sky)) / sky.w) * power_heuristic(sky.w, ev.PDF);
-                const float3 so_ = sf.WorldPos + sf.Normal * 1e-5f;         // :139
-                skyO = make_float4(so_.x, so_.y, so_.z, 1.0f);
-                skyD = make_float4(toSkyW.x, toSkyW.y, toSkyW.z, 0.0f);
-                skyC = make_float4(c.x, c.y, c.z, 0.0f);
-            }
+        if (needSky && evSky.PDF > 0.0f) {
+            const float3 c = (((evSky.BxDF * 1.0f) * f3(sky)) / sky.w) * power_heuristic(sky.w, evSky.PDF);
+            const float3 so_ = sf.WorldPos + sf.Normal * 1e-5f;             // :139
+            skyO = make_float4(so_.x, so_.y, so_.z, 1.0f);
+            skyD = make_float4(toSkyW.x, toSkyW.y, toSkyW.z, 0.0f);
+            skyC = make_float4(c.x, c.y, c.z, 0.0f);
         }
-        if (cfg.EnableMeshMIS && !isLight && light.w > 0.0f) {
-            const Eval ev = eval_bsdf(m, sc, cfg, V, toLightT);
-            if (ev.PDF > 0.0f) {
-                const float3 c = (((ev.BxDF * 1.0f) * f3(light)) / light.w) * power_heuristic(light.w, ev.PDF);
-                const float3 lo = sf.WorldPos + toLightW * 1e-2f;           // :171
-                litO = make_float4(lo.x, lo.y, lo.z, 1.0f);
-                litD = make_float4(toLightW.x, toLightW.y, toLightW.z, __uint_as_float(lt));
-                litC = make_float4(c.x, c.y, c.z, __uint_as_float(li));
-            }
+        if (needLit && evLit.PDF > 0.0f) {
+            const float3 c = (((evLit.BxDF * 1.0f) * f3(light)) / light.w) * power_heuristic(light.w, evLit.PDF);
+            const float3 lo = sf.WorldPos + toLightW * 1e-2f;               // :171
+            litO = make_float4(lo.x, lo.y, lo.z, 1.0f);
+            litD = make_float4(toLightW.x, toLightW.y, toLightW.z, __uint_as_float(lt));
+            litC = make_float4(c.x, c.y, c.z, __uint_as_float(li));
         }
         // payload write :319-324, :375-376
         const float off = -1e-3f * (wasRefracted ? 1.0f : 0.0f) + 1e-3f * (wasRefracted ? 0.0f : 1.0f);
@@ -260,14 +304,9 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, DevConfig cfg, PathS
         if (skyO.w != 0.0f) { so.sky_d[i] = skyD; so.sky_c[i] = skyC; }
         if (litO.w != 0.0f) { so.lit_d[i] = litD; so.lit_c[i] = litC; }
     }
-    // per-warp reduction of the counters, one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) { n_hit += __shfl_down_sync(0xFFFFFFFFu, n_hit, o); n_miss += __shfl_down_sync(0xFFFFFFFFu, n_miss, o); n_med += __shfl_down_sync(0xFFFFFFFFu, n_med, o); }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_hit) atomicAdd(&ctr->surface_hits, (unsigned long long)n_hit);
-        if (n_miss) atomicAdd(&ctr->misses, (unsigned long long)n_miss);
-        if (n_med) atomicAdd(&ctr->medium_events, (unsigned long long)n_med);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->shade_invocations, (unsigned long long)n);
+    for (int o = 16; o > 0; o >>= 1) n_med += __shfl_down_sync(0xFFFFFFFFu, n_med, o);
+    if ((threadIdx.x & 31) == 0 && n_med) atomicAdd(&ctr->medium_events, (unsigned long long)n_med);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr->shade_invocations, (unsigned long long)n); atomicAdd(&ctr->surface_hits, (unsigned long long)n); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -275,7 +314,7 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, DevConfig cfg, PathS
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM>
 __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, PathState src, PathState dst, ShadeOut so,
-                                                  const uint32_t *__restrict__ n_live_ptr, uint32_t *__restrict__ n_next_ptr,
+                                                  uint32_t *__restrict__ ctrl, uint32_t parity,
                                                   float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry,
                                                   int max_stack, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -285,7 +324,9 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
     BvhView bv;
     if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
     else bv = global_bvh(sc);
-    const uint32_t n = *n_live_ptr;
+    const uint32_t n = ctrl[parity];
+    uint32_t *n_next_ptr = ctrl + (parity ^ 1u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[2] = 0; ctrl[3] = 0; }   // queues of this bounce are consumed: reset for the next k_extend
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t n_shadow = 0;
     const uint32_t n_round = (n + 31u) & ~31u;                              // keep warps converged for the ballots
@@ -465,7 +506,7 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<false>, 256, sh);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<false>, 256, sh);
     }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade_hit, 128, 0);
     int occ_t = occ_e < occ_c ? occ_e : occ_c; if (occ_t < 1) occ_t = 1; if (occ_s < 1) occ_s = 1;
     lc->grid_trace = sms * occ_t;
     lc->grid_shade = sms * occ_s;
@@ -474,26 +515,29 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc) {
 }
 
 void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P, uint32_t first_sample,
-                   const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *counts, WaveCounters *ctr, cudaStream_t st) {
-    k_raygen<<<lc.grid_light, 256, 0, st>>>(cfg, disp, n_disp, P, first_sample, rng_carry, ps, sample_buf, counts, ctr);
+                   const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *ctrl, WaveCounters *ctr, cudaStream_t st) {
+    k_raygen<<<lc.grid_light, 256, 0, st>>>(cfg, disp, n_disp, P, first_sample, rng_carry, ps, sample_buf, ctrl, ctr);
 }
-void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, const uint32_t *n_live, WaveCounters *ctr, cudaStream_t st) {
+void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, uint32_t *ctrl, uint32_t parity, uint32_t *q_hit, uint32_t *q_miss,
+                   WaveCounters *ctr, cudaStream_t st) {
     set_attrs_once();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_extend<true><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, n_live, lc.max_stack, ctr);
-    else k_extend<false><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, n_live, lc.max_stack, ctr);
+    if (smem) k_extend<true><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+    else k_extend<false><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
 }
-void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *n_live, WaveCounters *ctr, cudaStream_t st) {
-    k_shade<<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, n_live, ctr);
+void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl,
+                  const uint32_t *q_hit, const uint32_t *q_miss, WaveCounters *ctr, cudaStream_t st) {
+    k_shade_miss<<<lc.grid_light, 256, 0, st>>>(sc, cfg, ps, so, ctrl, q_miss, ctr);
+    k_shade_hit<<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, ctrl, q_hit, ctr);
 }
 void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,
-                    const uint32_t *n_live, uint32_t *n_next, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
+                    uint32_t *ctrl, uint32_t parity, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
     set_attrs_once();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_connect<true><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, n_live, n_next, sample_buf, rng_carry, lc.max_stack, ctr);
-    else k_connect<false><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, n_live, n_next, sample_buf, rng_carry, lc.max_stack, ctr);
+    if (smem) k_connect<true><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, sample_buf, rng_carry, lc.max_stack, ctr);
+    else k_connect<false><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, sample_buf, rng_carry, lc.max_stack, ctr);
 }
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
                     const float4 *sample_buf, float4 *image, cudaStream_t st) {
