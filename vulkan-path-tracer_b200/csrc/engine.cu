@@ -31,7 +31,7 @@ Engine::Engine(int device) : device_(device) {
     for (int i = 0; i < 4; i++) view_inv_[i * 5] = proj_inv_[i * 5] = 1.0f;
     CK(cudaMalloc(&d_ctr_, sizeof(WaveCounters)));
     CK(cudaMemset(d_ctr_, 0, sizeof(WaveCounters)));
-    CK(cudaMalloc(&d_counts_, 4 * sizeof(uint32_t)));
+    CK(cudaMalloc(&d_counts_, 8 * sizeof(uint32_t)));
     CK(cudaMallocHost(&h_count_, 4 * sizeof(uint32_t)));
     memset(&last_, 0, sizeof last_);
 }
@@ -270,7 +270,7 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     const uint32_t P = (S == 1) ? W_ * local_rows_ : ((W_ + S - 1) / S) * ((H_ + S - 1) / S);
     if (P == 0) { dispatch_count_ += todo; frame_count_ = (uint32_t)(dispatch_count_ / S2); samples_accumulated_ = frame_count_ * cfg_.SamplesPerFrame; return samples_accumulated_ >= cfg_.MaxSamplesAccumulated; }
     uint32_t F = cfg_.FramesInFlight;
-    if (F == 0) { const uint64_t target = 4ull << 20; F = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, target / P)); }
+    if (F == 0) { const uint64_t target = 16ull << 20; F = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, target / P)); }
     F = std::min(F, todo);
     if ((size_t)F * P > wave_cap_) { CK(cudaStreamSynchronize(stream_)); }
     ensure_wave((size_t)F * P);
@@ -314,8 +314,8 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                 if (chunk == 0) break;
                 for (uint32_t b = 0; b < chunk; b++, k++) {
                     launch_extend(lc_, ds_, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_ctr_, stream_); mark(1);
-                    launch_shade(lc_, ds_, dc, ps_[cur], so_, d_counts_, d_q_hit_, d_q_miss_, d_ctr_, stream_); mark(2);
-                    launch_connect(lc_, ds_, dc, ps_[cur], ps_[cur ^ 1], so_, d_counts_, k & 1u, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
+                    launch_shade(lc_, ds_, dc, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(2);
+                    launch_connect(lc_, ds_, dc, ps_[cur], ps_[cur ^ 1], so_, d_counts_, k & 1u, d_q_hit_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
                     cur ^= 1; launches += 4;
                 }
                 if (!medium && k >= cfg_.MaxDepth) break;    // every surviving path has Depth >= MaxDepth: provably empty

@@ -308,112 +308,122 @@ __device__ __forceinline__ float dielectric_fresnel(float cosI, float eta) {
     float rp = (eta * cosI - cosT) / (eta * cosI + cosT);
     return 0.5f * (rs * rs + rp * rp);
 }
-__device__ __forceinline__ float ggx_d(const Mat &m, float3 H) {                   // :394-404
-    float ax2 = m.Ax * m.Ax, ay2 = m.Ay * m.Ay;
-    float e = (H.x * H.x) / ax2 + (H.y * H.y) / ay2 + H.z * H.z;
-    return 1.0f / (PT_PI * m.Ax * m.Ay * (e * e));
-}
+// Per-hit quantities of EvaluateBSDF that do not depend on L.  The shader evaluates the BSDF up to three times per hit
+// (sampled direction, sky NEE, light NEE); these values are identical in all three, so they are computed once.  Every
+// expression keeps the operand order of the Slang source, so hoisting does not change a single bit.
+struct BsdfCtx {
+    float pm, pd, pg;          // :169-177 lobe probabilities
+    float ax2, ay2, dnorm;     // Ax^2, Ay^2, PI*Ax*Ay            (:394-404)
+    float GV;                  // GGXSmithAnisotropic(V)          (:420-423)
+    float reflEC, glassEC;     // energy-compensation LUT values  (:203-217, :299-303, :316-320)
+    float3 metalEC;            // 1 + BaseColor * (1-E)/E         (:303-304)
+    float3 diffuse;            // M_1_OVER_PI * BaseColor         (:284)
+    float fourVz;              // 4 * V.z
+};
 __device__ __forceinline__ float ggx_g1(const Mat &m, float3 V) {                  // :406-423
     float Vz2 = fabsf(V.z) * fabsf(V.z);
     float ax2 = m.Ax * m.Ax, ay2 = m.Ay * m.Ay;
     float nom = -1.0f + sqrtf(1.0f + (ax2 * (V.x * V.x) + ay2 * (V.y * V.y)) / Vz2);
     return 1.0f / (1.0f + nom / 2.0f);
 }
-__device__ __forceinline__ Eval eval_reflection(const Mat &m, float3 V, float3 L, float3 F) {     // :331-351
-    Eval e; e.BxDF = f3(0.0f); e.PDF = 0.0f;
-    if (L.z <= 1e-5f) return e;
-    float3 H = normalize(V + L);
-    float VdotH = dot(V, H);
-    float D = ggx_d(m, H);
-    float GV = ggx_g1(m, V), GL = ggx_g1(m, L);
-    e.PDF = (GV * fmaxf(VdotH, 0.0f) * D / V.z) / (4.0f * VdotH);
-    e.BxDF = (((F * D) * GV) * GL) / (4.0f * V.z);
-    return e;
+__device__ __forceinline__ float ggx_d(const BsdfCtx &c, float3 H) {               // :394-404
+    float e = (H.x * H.x) / c.ax2 + (H.y * H.y) / c.ay2 + H.z * H.z;
+    return 1.0f / (c.dnorm * (e * e));
 }
-__device__ __forceinline__ Eval eval_refraction(const Mat &m, float3 V, float3 L, float3 F) {     // :359-387
-    Eval e; e.BxDF = f3(0.0f); e.PDF = 0.0f;
-    if (L.z >= 1e-5f) return e;
-    float3 H = normalize(V * m.Eta + L);
-    if (H.z < 0.0f) H = -H;
-    float VdotH = dot(V, H), LdotH = dot(L, H);
-    float D = ggx_d(m, H);
-    float GV = ggx_g1(m, V), GL = ggx_g1(m, L);
-    float G = GV * GL;
-    float den = LdotH + m.Eta * VdotH;
-    float den2 = den * den;
-    float eta2 = m.Eta * m.Eta;
-    float jac = (eta2 * fabsf(LdotH)) / den2;
-    e.PDF = (GV * fabsf(VdotH) * D / V.z) * jac;
-    float k = fabsf(VdotH) * fabsf(LdotH) / fabsf(V.z);
-    e.BxDF = ((((F * D) * G) * eta2) / den2) * k;
-    return e;
-}
-// :167-279 (+ :281-323).  The reflection-LUT fetch is shared by the metallic and dielectric-specular lobes.
-__device__ __forceinline__ Eval eval_bsdf(const Mat &m, const DevScene &sc, const DevConfig &cfg, float3 V, float3 L) {
-    float pm = m.Metallic;
-    float pd = (1.0f - m.Metallic) * (1.0f - m.Transmission);
-    float pg = (1.0f - m.Metallic) * m.Transmission;
-    float sum = pm + pd + pg;
-    pm /= sum; pd /= sum; pg /= sum;
-    const bool refracted = L.z < 0.0f;
-    float3 H; bool validRefraction = false;
-    if (refracted) {
-        H = normalize(V * m.Eta + L);
-        if (H.z < 0.0f) H = -H;
-        float VdotH = dot(V, H), LdotH = dot(L, H);
-        validRefraction = (VdotH > 0.0f && LdotH < 0.0f) || (VdotH < 0.0f && LdotH > 0.0f);
-    } else H = normalize(V + L);
-    float F = dielectric_fresnel(fabsf(dot(V, H)), m.Eta);
-    Eval out; out.BxDF = f3(0.0f); out.PDF = 0.0f;
-    float glassEC = 0.0f;
+__device__ __forceinline__ void bsdf_ctx_init(BsdfCtx &c, const Mat &m, const DevScene &sc, const DevConfig &cfg, float3 V) {
+    c.pm = m.Metallic;
+    c.pd = (1.0f - m.Metallic) * (1.0f - m.Transmission);
+    c.pg = (1.0f - m.Metallic) * m.Transmission;
+    const float sum = c.pm + c.pd + c.pg;
+    c.pm /= sum; c.pd /= sum; c.pg /= sum;
+    c.ax2 = m.Ax * m.Ax; c.ay2 = m.Ay * m.Ay; c.dnorm = PT_PI * m.Ax * m.Ay;
+    c.GV = ggx_g1(m, V);
+    c.reflEC = 1.0f; c.glassEC = 0.0f; c.metalEC = f3(1.0f);
     if (cfg.UseEnergyCompensation) {
         const bool inside = m.Eta > 1.0f;
-        float layer = (clampf(m.IOR, 1.0001f, 2.0f) - 1.0f) * 32.0f;
-        glassEC = lut_sample(inside ? sc.lut_refract_in : sc.lut_refract_out, 128, 128, 32, sqrtf(V.z), m.Roughness, layer);
+        const float layer = (clampf(m.IOR, 1.0001f, 2.0f) - 1.0f) * 32.0f;
+        c.glassEC = lut_sample(inside ? sc.lut_refract_in : sc.lut_refract_out, 128, 128, 32, sqrtf(V.z), m.Roughness, layer);
+        c.reflEC = lut_sample(sc.lut_reflect, 64, 64, 32, V.z, m.Roughness, m.Anisotropy * 32.0f);
+        const float ec = (1.0f - c.reflEC) / c.reflEC;
+        c.metalEC = f3(1.0f) + m.BaseColor * f3(ec);
     }
+    c.diffuse = m.BaseColor * PT_1_OVER_PI;
+    c.fourVz = 4.0f * V.z;
+}
+// :167-279 (+ :281-387): EvaluateBSDF(V, L)
+__device__ __forceinline__ Eval eval_bsdf(const Mat &m, const BsdfCtx &c, const DevConfig &cfg, float3 V, float3 L) {
+    const bool refracted = L.z < 0.0f;
+    Eval out; out.BxDF = f3(0.0f); out.PDF = 0.0f;
     if (!refracted) {
-        float reflEC = 1.0f;
-        if (cfg.UseEnergyCompensation) reflEC = lut_sample(sc.lut_reflect, 64, 64, 32, V.z, m.Roughness, m.Anisotropy * 32.0f);
+        const float3 H = normalize(V + L);
+        const float VdotH = dot(V, H);
+        const float F = dielectric_fresnel(fabsf(VdotH), m.Eta);                  // :202
+        // EvaluateReflection (:331-351) shared by the metallic, dielectric-specular and glass-reflect lobes
+        float rpdf = 0.0f, DGG = 0.0f; bool refl = false; float D = 0.0f, GL = 0.0f;
+        if (!(L.z <= 1e-5f)) {
+            refl = true;
+            D = ggx_d(c, H); GL = ggx_g1(m, L);
+            rpdf = (c.GV * fmaxf(VdotH, 0.0f) * D / V.z) / (4.0f * VdotH);
+        }
+        (void)DGG;
         {   // metallic :291-308
-            float3 Hm = normalize(V + L);
-            float3 Fm = mix3(m.BaseColor, m.SpecularColor, schlick_fresnel(dot(V, Hm)));
-            Eval e = eval_reflection(m, V, L, Fm);
-            if (cfg.UseEnergyCompensation) { float ec = (1.0f - reflEC) / reflEC; e.BxDF = (f3(1.0f) + m.BaseColor * f3(ec)) * e.BxDF; }
-            out.BxDF = out.BxDF + e.BxDF * pm; out.PDF += e.PDF * pm;
+            float3 b = f3(0.0f);
+            if (refl) {
+                const float3 Fm = mix3(m.BaseColor, m.SpecularColor, schlick_fresnel(VdotH));
+                b = (((Fm * D) * c.GV) * GL) / c.fourVz;
+            }
+            if (cfg.UseEnergyCompensation) b = c.metalEC * b;
+            out.BxDF = out.BxDF + b * c.pm; out.PDF += rpdf * c.pm;
         }
         {   // diffuse :281-289
             float pdf = L.z * PT_1_OVER_PI;
-            float3 brdf = (m.BaseColor * PT_1_OVER_PI) * L.z;
+            const float3 brdf = c.diffuse * L.z;
             pdf *= (L.z > 0.0f) ? 1.0f : 0.0f;
-            out.BxDF = out.BxDF + (brdf * pd) * (1.0f - F); out.PDF += pdf * pd * (1.0f - F);
+            out.BxDF = out.BxDF + (brdf * c.pd) * (1.0f - F); out.PDF += pdf * c.pd * (1.0f - F);
         }
-        Eval spec = eval_reflection(m, V, L, m.SpecularColor);
+        float3 spec = f3(0.0f);
+        if (refl) spec = (((m.SpecularColor * D) * c.GV) * GL) / c.fourVz;
         {   // dielectric specular :310-323
-            Eval e = spec;
-            if (cfg.UseEnergyCompensation) e.BxDF = e.BxDF / reflEC;
-            out.BxDF = out.BxDF + (e.BxDF * pd) * F; out.PDF += e.PDF * pd * F;
+            float3 b = spec;
+            if (cfg.UseEnergyCompensation) b = b / c.reflEC;
+            out.BxDF = out.BxDF + (b * c.pd) * F; out.PDF += rpdf * c.pd * F;
         }
         {   // glass reflect :237-251
-            Eval e = spec;
-            if (cfg.UseEnergyCompensation && glassEC > 0.01f) e.BxDF = e.BxDF / glassEC;
-            out.BxDF = out.BxDF + (e.BxDF * pg) * F; out.PDF += e.PDF * pg * F;
+            float3 b = spec;
+            if (cfg.UseEnergyCompensation && c.glassEC > 0.01f) b = b / c.glassEC;
+            out.BxDF = out.BxDF + (b * c.pg) * F; out.PDF += rpdf * c.pg * F;
         }
-    } else if (validRefraction) {   // glass refract :253-267
-        Eval e = eval_refraction(m, V, L, m.BaseColor);
-        if (cfg.UseEnergyCompensation && glassEC > 0.01f) e.BxDF = e.BxDF / glassEC;
-        out.BxDF = out.BxDF + (e.BxDF * pg) * (1.0f - F); out.PDF += e.PDF * pg * (1.0f - F);
+    } else {
+        float3 H = normalize(V * m.Eta + L);
+        if (H.z < 0.0f) H = -H;
+        const float VdotH = dot(V, H), LdotH = dot(L, H);
+        const bool validRefraction = (VdotH > 0.0f && LdotH < 0.0f) || (VdotH < 0.0f && LdotH > 0.0f);   // :185-186
+        const float F = dielectric_fresnel(fabsf(VdotH), m.Eta);
+        if (validRefraction) {   // glass refract :253-267 + EvaluateRefraction :359-387
+            float3 b = f3(0.0f); float pdf = 0.0f;
+            if (!(L.z >= 1e-5f)) {
+                const float D = ggx_d(c, H);
+                const float GL = ggx_g1(m, L);
+                const float G = c.GV * GL;
+                const float den = LdotH + m.Eta * VdotH;
+                const float den2 = den * den;
+                const float eta2 = m.Eta * m.Eta;
+                const float jac = (eta2 * fabsf(LdotH)) / den2;
+                pdf = (c.GV * fabsf(VdotH) * D / V.z) * jac;
+                const float k = fabsf(VdotH) * fabsf(LdotH) / fabsf(V.z);
+                b = ((((m.BaseColor * D) * G) * eta2) / den2) * k;
+            }
+            if (cfg.UseEnergyCompensation && c.glassEC > 0.01f) b = b / c.glassEC;
+            out.BxDF = out.BxDF + (b * c.pg) * (1.0f - F); out.PDF += pdf * c.pg * (1.0f - F);
+        }
     }
     return out;
 }
 // :94-165
 // Direction part of SampleBSDF (:94-160).  Returns false for the "invalid reflection/refraction direction" early-outs
 // (:152-160); the BxDF/PDF of a valid direction come from EvaluateBSDF(V, L) (:163), evaluated by the caller.
-__device__ __forceinline__ bool sample_bsdf_direction(const Mat &m, Rng &rng, float3 V, float3 H, float3 &Lout) {
-    float pm = m.Metallic;
-    float pd = (1.0f - m.Metallic) * (1.0f - m.Transmission);
-    float pg = (1.0f - m.Metallic) * m.Transmission;
-    float sum = pm + pd + pg;
-    pm /= sum; pd /= sum; pg /= sum;
+__device__ __forceinline__ bool sample_bsdf_direction(const Mat &m, const BsdfCtx &c, Rng &rng, float3 V, float3 H, float3 &Lout) {
+    const float pm = c.pm, pd = c.pd;
     float F = dielectric_fresnel(dot(V, H), m.Eta);
     float x1 = rng.next();
     float3 L; bool refracted = false;
@@ -429,30 +439,6 @@ __device__ __forceinline__ bool sample_bsdf_direction(const Mat &m, Rng &rng, fl
     if (L.z < 0.0f && !refracted) return false;
     else if (refracted && L.z >= 0.0f) return false;
     return true;
-}
-__device__ __forceinline__ BSample sample_bsdf(const Mat &m, const DevScene &sc, const DevConfig &cfg, Rng &rng, float3 V, float3 H) {
-    float pm = m.Metallic;
-    float pd = (1.0f - m.Metallic) * (1.0f - m.Transmission);
-    float pg = (1.0f - m.Metallic) * m.Transmission;
-    float sum = pm + pd + pg;
-    pm /= sum; pd /= sum; pg /= sum;
-    float F = dielectric_fresnel(dot(V, H), m.Eta);
-    float x1 = rng.next();
-    float3 L; bool refracted = false;
-    if (x1 < pm) L = normalize(reflect3(-V, H));
-    else if (x1 < pm + pd) {
-        if (rng.next() < F) L = normalize(reflect3(-V, H));
-        else L = normalize(random_sphere(rng) + f3(0.0f, 0.0f, 1.0f));
-    } else {
-        if (rng.next() < F) L = normalize(reflect3(-V, H));
-        else { L = normalize(refract3(-V, H, m.Eta)); refracted = true; }
-    }
-    BSample z; z.L = f3(0.0f); z.BxDF = f3(0.0f); z.PDF = 0.0f;
-    if (L.z < 0.0f && !refracted) return z;
-    else if (refracted && L.z >= 0.0f) return z;
-    Eval e = eval_bsdf(m, sc, cfg, V, L);
-    BSample r; r.L = L; r.BxDF = e.BxDF; r.PDF = e.PDF;
-    return r;
 }
 
 // ---------------------------------------------------------------- NEE samplers

@@ -31,8 +31,8 @@ __host__ __device__ inline uint32_t part_global_row(uint32_t local_row, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// control block (device memory, u32): [0],[1] live-path counts (ping-pong by bounce parity),
-//                                     [2] hit-queue length, [3] miss-queue length of the current bounce
+// control block (device memory, u32): [0],[1] live-path counts (ping-pong by bounce parity p = bounce & 1),
+//                                     [2+2p] hit-queue length, [3+2p] miss-queue length of a bounce with parity p
 // ------------------------------------------------------------------------------------------------
 
 // ------------------------------------------------------------------------------------------------
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_raygen(DevConfig cfg, const DevDispatch
         ps.thr_depth[j] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(inside ? 0u : PT_MAX_DEPTH));
         ps.rad_slot[j] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(j));
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[0] = n; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; atomicAdd(&ctr->paths, (unsigned long long)n); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[0] = n; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; ctrl[4] = 0; ctrl[5] = 0; atomicAdd(&ctr->paths, (unsigned long long)n); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
     if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
     else bv = global_bvh(sc);
     const uint32_t n = ctrl[parity];
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[parity ^ 1u] = 0;         // next live count: filled by k_connect of this bounce
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                              // counters of the NEXT bounce (last used two bounces ago)
+        ctrl[parity ^ 1u] = 0; ctrl[2u + 2u * (parity ^ 1u)] = 0; ctrl[3u + 2u * (parity ^ 1u)] = 0;
+    }
+    uint32_t *qh_count = ctrl + 2u + 2u * parity, *qm_count = ctrl + 3u + 2u * parity;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_round = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
         }
         const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
         uint32_t base_h = 0, base_m = 0;
-        if (lane == 0) { if (bh) base_h = atomicAdd(&ctrl[2], (uint32_t)__popc(bh)); if (bm) base_m = atomicAdd(&ctrl[3], (uint32_t)__popc(bm)); }
+        if (lane == 0) { if (bh) base_h = atomicAdd(qh_count, (uint32_t)__popc(bh)); if (bm) base_m = atomicAdd(qm_count, (uint32_t)__popc(bm)); }
         base_h = __shfl_sync(0xFFFFFFFFu, base_h, 0); base_m = __shfl_sync(0xFFFFFFFFu, base_m, 0);
         const uint32_t lt = (1u << lane) - 1u;
         if (hit) q_hit[base_h + __popc(bh & lt)] = i;
@@ -128,16 +131,17 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_shade_miss : SH/Miss.slang:8-76 for the miss queue
+// k_shade_miss : SH/Miss.slang:8-76 for the miss queue.  A miss always ends the path (Depth = MAX_DEPTH), so the
+//                ray-gen epilogue (SH/RayGen.slang:92-128) is applied here and the path never reaches k_connect.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so,
-                                                     const uint32_t *__restrict__ ctrl, const uint32_t *__restrict__ q_miss, WaveCounters *ctr) {
-    const uint32_t n = ctrl[3];
-    const float4 zero4 = make_float4(0, 0, 0, 0);
+__global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, PathState ps, const uint32_t *__restrict__ ctrl, uint32_t parity,
+                                                     const uint32_t *__restrict__ q_miss, float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry,
+                                                     WaveCounters *ctr) {
+    const uint32_t n = ctrl[3u + 2u * parity];
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const uint32_t i = q_miss[j];
-        const float4 d4 = ps.dir_rng[i];
-        const uint32_t depth = __float_as_uint(ps.thr_depth[i].w) & 0x7FFFFFFFu;
+        const float4 d4 = ps.dir_rng[i], t4 = ps.thr_depth[i], r4 = ps.rad_slot[i];
+        const uint32_t depth = __float_as_uint(t4.w) & 0x7FFFFFFFu;
         const float payPDF = ps.org_pdf[i].w;
         float4 c;
         if (cfg.ShowEnvMapDirectly || depth > 0) {
@@ -149,9 +153,19 @@ __global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, 
         float3 em = f3(c.x * cfg.EnvironmentIntensity, c.y * cfg.EnvironmentIntensity, c.z * cfg.EnvironmentIntensity);
         if (cfg.FurnaceTestMode) em = f3(1.0f);
         if (cfg.EnableSkyMIS && depth > 0) em = em * power_heuristic(payPDF, c.w);
-        so.e0[i] = make_float4(em.x, em.y, em.z, __uint_as_float(PT_MAX_DEPTH));
-        so.bxdf_pdf[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);               // stale payload.BxDF/PDF: the path ends, value unused
-        so.sky_o[i] = zero4; so.lit_o[i] = zero4;
+        // SH/RayGen.slang:92-102 with payload.Depth == MAX_DEPTH (!= 1): the contribution is always luminance-clamped (Q3)
+        float3 contribution = em * f3(t4);
+        const float lum = dot(contribution, f3(0.212671f, 0.715160f, 0.072169f));
+        contribution = contribution * (cfg.MaxLuminance / fmaxf(lum, cfg.MaxLuminance));
+        const float3 rad = f3(r4) + contribution;
+        Rng rng; rng.s = __float_as_uint(d4.w);
+        (void)rng.next();                                                   // the Russian-roulette draw of this segment (:111) still advances the stream
+        const uint32_t slot = __float_as_uint(r4.w);
+        const bool ok = !isinf(rad.x) && !isinf(rad.y) && !isinf(rad.z) && !isnan(rad.x) && !isnan(rad.y) && !isnan(rad.z);   // :116
+        float4 acc = sample_buf[slot];
+        if (ok) { acc.x += rad.x; acc.y += rad.y; acc.z += rad.z; }
+        sample_buf[slot] = acc;
+        rng_carry[slot] = rng.s;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr->misses, (unsigned long long)n); atomicAdd(&ctr->shade_invocations, (unsigned long long)n); }
 }
@@ -160,11 +174,11 @@ __global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, 
 // k_shade_hit : SH/ClosestHit.slang:20-378 for the hit queue
 // ------------------------------------------------------------------------------------------------
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 3
+#define SHADE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so,
-                                                    const uint32_t *__restrict__ ctrl, const uint32_t *__restrict__ q_hit, WaveCounters *ctr) {
-    const uint32_t n = ctrl[2];
+                                                    const uint32_t *__restrict__ ctrl, uint32_t parity, const uint32_t *__restrict__ q_hit, WaveCounters *ctr) {
+    const uint32_t n = ctrl[2u + 2u * parity];
     uint32_t n_med = 0;
     const float4 zero4 = make_float4(0, 0, 0, 0);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -232,7 +246,9 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         V = sf.world_to_tangent(V);
         const float3 H = ggx_sample_vndf(rng, V, m.Ax, m.Ay);
         float3 Ls;
-        const bool validDir = sample_bsdf_direction(m, rng, V, H, Ls);
+        BsdfCtx bc;
+        bsdf_ctx_init(bc, m, sc, cfg, V);
+        const bool validDir = sample_bsdf_direction(m, bc, rng, V, H, Ls);
         // EvaluateBSDF(V, .) for the sampled direction and the two NEE directions: ONE rolled loop keeps a single copy of the
         // BSDF code in the kernel (SampleBSDF :163; ClosestHit :241-256).  NEE is evaluated eagerly, visibility comes later.
         const bool needSky = cfg.EnableSkyMIS && sky.w > 0.0f;
@@ -244,7 +260,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
             const bool need = (k == 0) ? validDir : ((k == 1) ? needSky : needLit);
             if (!need) continue;
             const float3 dk = (k == 0) ? Ls : ((k == 1) ? toSkyT : toLightT);
-            const Eval e = eval_bsdf(m, sc, cfg, V, dk);
+            const Eval e = eval_bsdf(m, bc, cfg, V, dk);
             if (k == 0) evS = e; else if (k == 1) evSky = e; else evLit = e;
         }
         BSample ss;
@@ -314,7 +330,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM>
 __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, PathState src, PathState dst, ShadeOut so,
-                                                  uint32_t *__restrict__ ctrl, uint32_t parity,
+                                                  uint32_t *__restrict__ ctrl, uint32_t parity, const uint32_t *__restrict__ q_hit,
                                                   float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry,
                                                   int max_stack, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -324,18 +340,19 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
     BvhView bv;
     if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
     else bv = global_bvh(sc);
-    const uint32_t n = ctrl[parity];
+    const uint32_t n = ctrl[2u + 2u * parity];                               // paths that hit a surface this bounce (misses ended in k_shade_miss)
     uint32_t *n_next_ptr = ctrl + (parity ^ 1u);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[2] = 0; ctrl[3] = 0; }   // queues of this bounce are consumed: reset for the next k_extend
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t n_shadow = 0;
     const uint32_t n_round = (n + 31u) & ~31u;                              // keep warps converged for the ballots
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        const bool active = i < n;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+        const bool active = j < n;
         bool alive = false;
         float4 o4, d4, r4, thr4; uint32_t newDflags = 0; Rng rng; rng.s = 0;
         float3 thr = f3(0.0f), rad = f3(0.0f);
+        uint32_t i = 0;
         if (active) {
+            i = q_hit[j];
             const float4 e4 = so.e0[i];
             thr4 = src.thr_depth[i]; r4 = src.rad_slot[i];
             o4 = src.org_pdf[i]; d4 = src.dir_rng[i];
@@ -526,18 +543,18 @@ void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeO
     if (smem) k_extend<true><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
     else k_extend<false><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
 }
-void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl,
-                  const uint32_t *q_hit, const uint32_t *q_miss, WaveCounters *ctr, cudaStream_t st) {
-    k_shade_miss<<<lc.grid_light, 256, 0, st>>>(sc, cfg, ps, so, ctrl, q_miss, ctr);
-    k_shade_hit<<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, ctrl, q_hit, ctr);
+void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity,
+                  const uint32_t *q_hit, const uint32_t *q_miss, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
+    k_shade_miss<<<lc.grid_light, 256, 0, st>>>(sc, cfg, ps, ctrl, parity, q_miss, sample_buf, rng_carry, ctr);
+    k_shade_hit<<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q_hit, ctr);
 }
 void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,
-                    uint32_t *ctrl, uint32_t parity, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
+                    uint32_t *ctrl, uint32_t parity, const uint32_t *q_hit, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
     set_attrs_once();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_connect<true><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, sample_buf, rng_carry, lc.max_stack, ctr);
-    else k_connect<false><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, sample_buf, rng_carry, lc.max_stack, ctr);
+    if (smem) k_connect<true><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
+    else k_connect<false><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
 }
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
                     const float4 *sample_buf, float4 *image, cudaStream_t st) {
