@@ -115,15 +115,19 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
             } else if (ha) { cur = c0; continue; }
             else if (hb) { cur = c1; continue; }
         } else {
-            const uint32_t slot = (uint32_t)(~cur);
-            const float4 *tp = b.tris + (size_t)slot * 3;
-            const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
-            float t, u, v;
-            if (tri_test(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax, t, u, v)) {
-                const uint32_t gid = __float_as_uint(ta.w);
-                if (!found || t < h.t || (t == h.t && gid < best_gid)) {
-                    found = true; h.t = t; h.u = u; h.v = v; h.slot = slot; best_gid = gid;
-                    if (ANYHIT) return true;
+            const uint32_t ref = (uint32_t)(~cur);                            // leaf: up to 4 consecutive Morton slots
+            const uint32_t first = ref >> 2, count = (ref & 3u) + 1u;
+            for (uint32_t q = 0; q < count; q++) {
+                const uint32_t slot = first + q;
+                const float4 *tp = b.tris + (size_t)slot * 3;
+                const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
+                float t, u, v;
+                if (tri_test(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax, t, u, v)) {
+                    const uint32_t gid = __float_as_uint(ta.w);
+                    if (!found || t < h.t || (t == h.t && gid < best_gid)) {
+                        found = true; h.t = t; h.u = u; h.v = v; h.slot = slot; best_gid = gid;
+                        if (ANYHIT) return true;
+                    }
                 }
             }
         }

@@ -31,13 +31,24 @@ static_assert(sizeof(DevInstance) == 112, "DevInstance layout");
 
 struct DevTexture { const uint8_t *data; uint32_t w, h, c, _pad; };
 
-struct DevEmissive { uint32_t mesh, material, tri_count, instance; float xf[16]; };  // PT/PathTracer.h:321-328
+// Reference material (112 B, PT/PathTracer.h:12-34) + the texel values of its 1x1 textures resolved on the host:
+// the default white / (128,128,255) textures (PT/PathTracer.cpp:1557-1621) then cost no dependent texture fetch at all.
+struct DevMaterial {
+    b200pt_material m;
+    uint32_t const_mask;     // bit0 base colour, bit1 normal, bit2 roughness, bit3 metallic, bit4 emissive: that texture is 1x1
+    float crough, cmetal;    // R channel / 255
+    uint32_t _pad;
+    float4 cbase, cnormal, cemis;   // RGBA / 255
+};
+static_assert(sizeof(DevMaterial) == 176, "DevMaterial layout");
+
+struct DevEmissive { uint32_t mesh, material, tri_count, instance; float xf[16]; };  // PT/PathTracer.h:321-328 (80 B)
 static_assert(sizeof(DevEmissive) == 80, "EmissiveMeshEntry is 80 B");
 static_assert(sizeof(b200pt_vertex) == 32, "Vertex is 32 B");
 static_assert(sizeof(b200pt_material) == 112, "Material is 112 B");
 
 // 64-byte BVH2 node: AABBs of both children live in the parent, so one 64-B fetch decides both.
-// child >= 0 : internal node index;  child < 0 : leaf, ~child = triangle slot (Morton order)
+// child >= 0 : internal node index;  child < 0 : leaf, r = ~child, first Morton slot = r >> 2, triangle count = (r & 3) + 1
 struct BvhNode {
     float lo0[3], hi0[3];
     float lo1[3], hi1[3];
@@ -50,12 +61,23 @@ static_assert(sizeof(BvhNode) == 64, "BvhNode is 64 B");
 struct BvhTri { float4 a, b, c; };
 static_assert(sizeof(BvhTri) == 48, "BvhTri is 48 B");
 
+// 112-byte per-triangle shading record, same (Morton) order as BvhTri: one gather replaces the reference's
+// instance -> mesh -> index -> vertex descriptor chain (SH/ClosestHit.slang:46-57, SH/Surface.slang:33-41).
+//   r0 = P1.xyz | instance   r1 = P2.xyz | primitive   r2 = P3.xyz | material
+//   r3 = N1.xyz | uv1.x      r4 = N2.xyz | uv1.y       r5 = N3.xyz | uv2.x      r6 = uv2.y uv3.x uv3.y 0   (object space)
+struct ShadeTri { float4 r[7]; };
+static_assert(sizeof(ShadeTri) == 112, "ShadeTri is 112 B");
+
+// 64-byte emissive triangle: world-space corners (EmissiveMeshEntry::Transform applied, SH/Sampler.slang:389-391) + uvs
+//   r0 = p0.xyz | uv0.x   r1 = p1.xyz | uv0.y   r2 = p2.xyz | uv1.x   r3 = uv1.y uv2.x uv2.y 0
+struct EmTri { float4 r[4]; };
+
 struct DevScene {
     const b200pt_vertex *verts;
     const uint32_t *indices;
     const DevMesh *meshes;
     const DevInstance *instances;
-    const b200pt_material *materials;
+    const DevMaterial *materials;
     const DevTexture *textures;
     const DevEmissive *emissive;
     const float4 *env;
@@ -63,6 +85,9 @@ struct DevScene {
     const float *lut_reflect, *lut_refract_out, *lut_refract_in;
     const BvhNode *nodes;
     const BvhTri *tris;
+    const ShadeTri *shade_tris;
+    const EmTri *em_tris;
+    const uint32_t *em_tri_base;   // per emissive mesh: first EmTri
     uint32_t n_emissive, envW, envH, n_tris, n_nodes;
     int32_t root;            // child-style reference of the root
     uint32_t bvh_bytes;      // nodes+tris size if they are contiguous and small enough to stage in smem, else 0

@@ -50,7 +50,7 @@ Engine::~Engine() {
 }
 
 void Engine::free_scene() {
-    dfree(d_verts_); dfree(d_indices_); dfree(d_meshes_); dfree(d_instances_); dfree(d_materials_); dfree(d_textures_); dfree(d_emissive_);
+    dfree(d_verts_); dfree(d_indices_); dfree(d_meshes_); dfree(d_instances_); dfree(d_materials_); dfree(d_textures_); dfree(d_emissive_); dfree(d_em_tris_); dfree(d_em_tri_base_);
     for (auto &p : d_texdata_) if (p) cudaFree(p);
     d_texdata_.clear();
     lbvh_free(&bvh_);
@@ -101,8 +101,12 @@ void Engine::upload_scene() {
     }
     n_tris_ = tri_base;
     CK(cudaMalloc(&d_instances_, h_instances_.size() * sizeof(DevInstance)));
-    CK(cudaMalloc(&d_materials_, scene_.materials.size() * sizeof(b200pt_material)));
-    CK(cudaMemcpy(d_materials_, scene_.materials.data(), scene_.materials.size() * sizeof(b200pt_material), cudaMemcpyHostToDevice));
+    {
+        std::vector<DevMaterial> dm; dm.reserve(scene_.materials.size());
+        for (const auto &m : scene_.materials) dm.push_back(make_dev_material(m));
+        CK(cudaMalloc(&d_materials_, dm.size() * sizeof(DevMaterial)));
+        CK(cudaMemcpy(d_materials_, dm.data(), dm.size() * sizeof(DevMaterial), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&d_emissive_, std::max<size_t>(1, scene_.instances.size()) * sizeof(DevEmissive)));
     rebuild_emissive();
     // textures
@@ -119,10 +123,31 @@ void Engine::upload_scene() {
     int r = lbvh_build(d_verts_, d_indices_, d_meshes_, d_instances_, h_instances_.data(), h_meshes_.data(), (uint32_t)h_instances_.size(), n_tris_, &bvh_, stream_);
     if (r != 0) throw CudaError{ B200PT_ERR_CUDA, std::string("lbvh_build failed: ") + cudaGetErrorString((cudaError_t)r) };
     ds_.verts = d_verts_; ds_.indices = d_indices_; ds_.meshes = d_meshes_; ds_.instances = d_instances_; ds_.materials = d_materials_;
-    ds_.textures = d_textures_; ds_.emissive = d_emissive_; ds_.nodes = bvh_.nodes; ds_.tris = bvh_.tris;
+    ds_.textures = d_textures_; ds_.emissive = d_emissive_; ds_.nodes = bvh_.nodes; ds_.tris = bvh_.tris; ds_.shade_tris = bvh_.shade;
     ds_.n_tris = bvh_.n_tris; ds_.n_nodes = bvh_.n_nodes; ds_.root = bvh_.root; ds_.bvh_bytes = bvh_.bytes <= 0xFFFFFFFFull ? (uint32_t)bvh_.bytes : 0;
     int q = query_launch_cfg(ds_, bvh_.max_depth, &lc_);
     if (q != 0) throw CudaError{ B200PT_ERR_CUDA, "query_launch_cfg failed" };
+}
+
+// 1x1 textures (the defaults of PathTracer.cpp:1557-1621, or any constant texture) are resolved to their texel value here
+DevMaterial Engine::make_dev_material(const b200pt_material &m) const {
+    DevMaterial d; memset(&d, 0, sizeof d);
+    d.m = m;
+    auto texel = [&](uint32_t idx, float4 &out) -> bool {
+        if (idx >= scene_.textures.size()) return false;
+        const HostTexture &t = scene_.textures[idx];
+        if (t.width != 1 || t.height != 1) return false;
+        if (t.channels == 4) out = make_float4((float)t.data[0] / 255.0f, (float)t.data[1] / 255.0f, (float)t.data[2] / 255.0f, (float)t.data[3] / 255.0f);
+        else out = make_float4((float)t.data[0] / 255.0f, 0.0f, 0.0f, 1.0f);
+        return true;
+    };
+    float4 v;
+    if (texel(m.BaseColorTextureIndex, v)) { d.const_mask |= 1u; d.cbase = v; }
+    if (texel(m.NormalTextureIndex, v)) { d.const_mask |= 2u; d.cnormal = v; }
+    if (texel(m.RoughnessTextureIndex, v)) { d.const_mask |= 4u; d.crough = v.x; }
+    if (texel(m.MetallicTextureIndex, v)) { d.const_mask |= 8u; d.cmetal = v.x; }
+    if (texel(m.EmissiveTextureIndex, v)) { d.const_mask |= 16u; d.cemis = v; }
+    return d;
 }
 
 // emissive-mesh list: PathTracer.cpp:458-469 (+ SetMaterial maintenance :712-810); keyed on constant EmissiveColor != 0 (Q16)
@@ -142,6 +167,29 @@ void Engine::rebuild_emissive() {
     if (em.size() >= 10000) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "too many emissive meshes (MAX_EMISSIVE_MESHES)" };
     n_emissive_ = (uint32_t)em.size();
     if (!em.empty()) CK(cudaMemcpy(d_emissive_, em.data(), em.size() * sizeof(DevEmissive), cudaMemcpyHostToDevice));
+    // world-space emissive triangles (SH/Sampler.slang:376-391: vertices fetched and transformed per sample in the reference)
+    std::vector<EmTri> et; std::vector<uint32_t> base;
+    for (const DevEmissive &e : em) {
+        base.push_back((uint32_t)et.size());
+        const HostMesh &hm = scene_.meshes[e.mesh];
+        auto xf = [&](const b200pt_vertex &v) {
+            const float *t = e.xf; const float x = v.Position[0], y = v.Position[1], z = v.Position[2];
+            return make_float3(t[0] * x + t[4] * y + t[8] * z + t[12] * 1.0f, t[1] * x + t[5] * y + t[9] * z + t[13] * 1.0f, t[2] * x + t[6] * y + t[10] * z + t[14] * 1.0f);
+        };
+        for (uint32_t t = 0; t < e.tri_count; t++) {
+            const b200pt_vertex &A = hm.vertices[hm.indices[t * 3]], &B = hm.vertices[hm.indices[t * 3 + 1]], &C = hm.vertices[hm.indices[t * 3 + 2]];
+            const float3 p0 = xf(A), p1 = xf(B), p2 = xf(C);
+            EmTri r;
+            r.r[0] = make_float4(p0.x, p0.y, p0.z, A.TexCoord[0]); r.r[1] = make_float4(p1.x, p1.y, p1.z, A.TexCoord[1]);
+            r.r[2] = make_float4(p2.x, p2.y, p2.z, B.TexCoord[0]); r.r[3] = make_float4(B.TexCoord[1], C.TexCoord[0], C.TexCoord[1], 0.0f);
+            et.push_back(r);
+        }
+    }
+    dfree(d_em_tris_); dfree(d_em_tri_base_);
+    CK(cudaMalloc(&d_em_tris_, std::max<size_t>(1, et.size()) * sizeof(EmTri))); CK(cudaMalloc(&d_em_tri_base_, std::max<size_t>(1, base.size()) * sizeof(uint32_t)));
+    if (!et.empty()) CK(cudaMemcpy(d_em_tris_, et.data(), et.size() * sizeof(EmTri), cudaMemcpyHostToDevice));
+    if (!base.empty()) CK(cudaMemcpy(d_em_tri_base_, base.data(), base.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ds_.em_tris = d_em_tris_; ds_.em_tri_base = d_em_tri_base_;
     CK(cudaMemcpy(d_instances_, h_instances_.data(), h_instances_.size() * sizeof(DevInstance), cudaMemcpyHostToDevice));
     ds_.n_emissive = n_emissive_;
 }
@@ -154,7 +202,7 @@ void Engine::set_material(uint32_t idx, const b200pt_material &m) {
     for (uint32_t t : tix) if (t >= scene_.textures.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "texture index out of range" };
     CK(cudaStreamSynchronize(stream_));
     scene_.materials[idx] = m;
-    CK(cudaMemcpy(d_materials_ + idx, &m, sizeof m, cudaMemcpyHostToDevice));
+    { const DevMaterial dm = make_dev_material(m); CK(cudaMemcpy(d_materials_ + idx, &dm, sizeof dm, cudaMemcpyHostToDevice)); }
     rebuild_emissive();
     reset();
 }

@@ -60,6 +60,7 @@ private:
     void free_scene();
     void upload_scene();
     void rebuild_emissive();
+    DevMaterial make_dev_material(const b200pt_material &m) const;
     void ensure_image();
     void ensure_wave(size_t capacity);
     void free_wave();
@@ -86,7 +87,7 @@ private:
     // device scene
     DevScene ds_{};
     b200pt_vertex *d_verts_ = nullptr; uint32_t *d_indices_ = nullptr; DevMesh *d_meshes_ = nullptr; DevInstance *d_instances_ = nullptr;
-    b200pt_material *d_materials_ = nullptr; DevTexture *d_textures_ = nullptr; DevEmissive *d_emissive_ = nullptr;
+    DevMaterial *d_materials_ = nullptr; DevTexture *d_textures_ = nullptr; DevEmissive *d_emissive_ = nullptr; EmTri *d_em_tris_ = nullptr; uint32_t *d_em_tri_base_ = nullptr;
     std::vector<uint8_t *> d_texdata_;
     std::vector<DevInstance> h_instances_; std::vector<DevMesh> h_meshes_;
     float4 *d_env_ = nullptr; uint2 *d_alias_ = nullptr; float *d_luts_[3] = { nullptr, nullptr, nullptr };

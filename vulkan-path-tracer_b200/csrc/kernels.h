@@ -7,7 +7,8 @@ namespace b200pt {
 
 struct LaunchCfg {
     int grid_light;     // grid for streaming kernels (raygen / resolve / post)
-    int grid_trace;     // persistent grid for traversal kernels (multiple of the SM count)
+    int grid_trace;     // persistent grid for the ray-query test hook
+    int grid_extend, grid_connect;   // persistent grids of the traversal kernels (SM count x resident CTAs of each kernel)
     int grid_shade;     // persistent grid for the shading kernel
     int max_stack;      // traversal stack entries (BVH depth + 2)
     bool bvh_in_smem;   // whole BVH staged to shared memory by TMA
@@ -28,7 +29,7 @@ void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, cons
                        float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, cudaStream_t st);
 
 // ---- LBVH build (lbvh.cu): world-space flattening of the two-level TLAS/BLAS ----
-struct LbvhResult { BvhNode *nodes; BvhTri *tris; uint32_t n_nodes, n_tris; int32_t root; int max_depth; size_t bytes; };
+struct LbvhResult { ShadeTri *shade; BvhNode *nodes; BvhTri *tris; uint32_t n_nodes, n_tris; int32_t root; int max_depth; size_t bytes; };
 // Builds into ONE contiguous allocation [nodes | tris] (so small scenes can be staged to smem with one bulk copy).
 // Returns cudaError_t as int.
 int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const DevMesh *d_meshes, const DevInstance *d_instances,

@@ -14,6 +14,7 @@
 
 namespace b200pt {
 
+#define LBVH_LEAF_MAX 4
 #define LBVH_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
 // world-space transform without FMA contraction: bit-identical to the CPU oracle's plain fp32 arithmetic
@@ -36,7 +37,7 @@ __device__ __forceinline__ void atomic_max_f(float *addr, float v) {
 // ---- 1. world triangles + scene bounds -------------------------------------------------------
 __global__ void k_world_tris(const b200pt_vertex *__restrict__ verts, const uint32_t *__restrict__ indices, const DevMesh *__restrict__ meshes,
                              const DevInstance *__restrict__ inst, uint32_t n_inst, uint32_t n_tris,
-                             BvhTri *__restrict__ tmp, float *__restrict__ cent, float *__restrict__ bounds /*6*/) {
+                             BvhTri *__restrict__ tmp, ShadeTri *__restrict__ tmp_shade, float *__restrict__ cent, float *__restrict__ bounds /*6*/) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
     if (gid < n_tris) {
@@ -55,6 +56,15 @@ __global__ void k_world_tris(const b200pt_vertex *__restrict__ verts, const uint
         t.b = make_float4(__fsub_rn(v1.x, v0.x), __fsub_rn(v1.y, v0.y), __fsub_rn(v1.z, v0.z), __uint_as_float(a));
         t.c = make_float4(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z), __uint_as_float(prim));
         tmp[gid] = t;
+        ShadeTri sh;
+        sh.r[0] = make_float4(A.Position[0], A.Position[1], A.Position[2], __uint_as_float(a));
+        sh.r[1] = make_float4(B.Position[0], B.Position[1], B.Position[2], __uint_as_float(prim));
+        sh.r[2] = make_float4(C.Position[0], C.Position[1], C.Position[2], __uint_as_float(in.material));
+        sh.r[3] = make_float4(A.Normal[0], A.Normal[1], A.Normal[2], A.TexCoord[0]);
+        sh.r[4] = make_float4(B.Normal[0], B.Normal[1], B.Normal[2], A.TexCoord[1]);
+        sh.r[5] = make_float4(C.Normal[0], C.Normal[1], C.Normal[2], B.TexCoord[0]);
+        sh.r[6] = make_float4(B.TexCoord[1], C.TexCoord[0], C.TexCoord[1], 0.0f);
+        tmp_shade[gid] = sh;
         lo[0] = fminf(v0.x, fminf(v1.x, v2.x)); hi[0] = fmaxf(v0.x, fmaxf(v1.x, v2.x));
         lo[1] = fminf(v0.y, fminf(v1.y, v2.y)); hi[1] = fmaxf(v0.y, fmaxf(v1.y, v2.y));
         lo[2] = fminf(v0.z, fminf(v1.z, v2.z)); hi[2] = fmaxf(v0.z, fmaxf(v1.z, v2.z));
@@ -144,12 +154,13 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const uint32_t *__restric
 }
 
 // ---- 4. reorder into Morton order ---------------------------------------------------------------
-__global__ void k_reorder(const BvhTri *__restrict__ tmp, const float *__restrict__ aabb, const uint32_t *__restrict__ vals, uint32_t n,
-                          BvhTri *__restrict__ tris, float *__restrict__ leaf_box) {
+__global__ void k_reorder(const BvhTri *__restrict__ tmp, const ShadeTri *__restrict__ tmp_shade, const float *__restrict__ aabb, const uint32_t *__restrict__ vals, uint32_t n,
+                          BvhTri *__restrict__ tris, ShadeTri *__restrict__ shade, float *__restrict__ leaf_box) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t g = vals[i];
     tris[i] = tmp[g];
+    shade[i] = tmp_shade[g];
     for (int k = 0; k < 6; k++) leaf_box[(size_t)i * 6 + k] = aabb[(size_t)g * 6 + k];
 }
 
@@ -160,7 +171,8 @@ __device__ __forceinline__ int lbvh_delta(const uint32_t *keys, int n, int i, in
     if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
     return __clz(a ^ b);
 }
-__global__ void k_karras(const uint32_t *__restrict__ keys, int n, int *__restrict__ left, int *__restrict__ right, int *__restrict__ parent_int, int *__restrict__ parent_leaf) {
+__global__ void k_karras(const uint32_t *__restrict__ keys, int n, int *__restrict__ left, int *__restrict__ right, int *__restrict__ parent_int, int *__restrict__ parent_leaf,
+                         int2 *__restrict__ range) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     const int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -178,6 +190,7 @@ __global__ void k_karras(const uint32_t *__restrict__ keys, int n, int *__restri
     }
     const int gamma = i + s * d + min(d, 0);
     const int lo = min(i, j), hi = max(i, j);
+    range[i] = make_int2(lo, hi);                                        // triangles (Morton slots) covered by this node
     if (lo == gamma) { left[i] = ~gamma; parent_leaf[gamma] = i; } else { left[i] = gamma; parent_int[gamma] = i; }
     if (hi == gamma + 1) { right[i] = ~(gamma + 1); parent_leaf[gamma + 1] = i; } else { right[i] = gamma + 1; parent_int[gamma + 1] = i; }
     if (i == 0) parent_int[0] = -1;
@@ -204,7 +217,16 @@ __global__ void k_refit(int n, const int *__restrict__ left, const int *__restri
 }
 
 // ---- 7. emit 64-B nodes (child boxes in the parent, slightly padded so the slab test is conservative) ----
-__global__ void k_emit(int n_int, const int *__restrict__ left, const int *__restrict__ right, const float *__restrict__ leaf_box,
+// A subtree covering <= LBVH_LEAF_MAX consecutive Morton slots is referenced as ONE leaf (first slot + count), which removes
+// the two deepest levels of the binary hierarchy: fewer node fetches and stack operations per ray.
+// leaf reference: child < 0, r = ~child, first = r >> 2, count = (r & 3) + 1
+__device__ __forceinline__ int lbvh_child_ref(int c, const int2 *range) {
+    if (c < 0) return ~(((~c) << 2) | 0);                                // single triangle
+    const int2 r = range[c];
+    if (r.y - r.x + 1 <= LBVH_LEAF_MAX) return ~((r.x << 2) | (r.y - r.x));
+    return c;
+}
+__global__ void k_emit(int n_int, const int *__restrict__ left, const int *__restrict__ right, const int2 *__restrict__ range, const float *__restrict__ leaf_box,
                        const float *__restrict__ node_box, BvhNode *__restrict__ nodes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_int) return;
@@ -217,17 +239,20 @@ __global__ void k_emit(int n_int, const int *__restrict__ left, const int *__res
         nd.lo0[k] = a[k] - pa; nd.hi0[k] = a[3 + k] + pa;
         nd.lo1[k] = b[k] - pb; nd.hi1[k] = b[3 + k] + pb;
     }
-    nd.c0 = l; nd.c1 = r; nd._pad[0] = nd._pad[1] = 0;
+    nd.c0 = lbvh_child_ref(l, range); nd.c1 = lbvh_child_ref(r, range); nd._pad[0] = nd._pad[1] = 0;
     nodes[i] = nd;
 }
 
 void lbvh_free(LbvhResult *r) {
     if (r->nodes) cudaFree(r->nodes);
+    if (r->shade) cudaFree(r->shade);
+    r->shade = nullptr;
     r->nodes = nullptr; r->tris = nullptr; r->n_nodes = r->n_tris = 0; r->bytes = 0;
 }
 
 int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const DevMesh *d_meshes, const DevInstance *d_instances,
                const DevInstance *, const DevMesh *, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st) {
+    out->shade = nullptr;
     out->nodes = nullptr; out->tris = nullptr; out->n_nodes = 0; out->n_tris = n_tris; out->root = 0; out->max_depth = 1; out->bytes = 0;
     if (n_tris == 0 || n_instances == 0) return (int)cudaErrorInvalidValue;
     const uint32_t n = n_tris, n_int = n > 1 ? n - 1 : 0, n_nodes_alloc = n_int ? n_int : 1;
@@ -238,9 +263,12 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
     BvhNode *nodes = reinterpret_cast<BvhNode *>(blob);
     BvhTri *tris = reinterpret_cast<BvhTri *>(blob + node_bytes);
 
+    ShadeTri *tmp_shade = nullptr, *shade = nullptr;
+    LBVH_CHECK(cudaMalloc(&tmp_shade, (size_t)n * sizeof(ShadeTri))); LBVH_CHECK(cudaMalloc(&shade, (size_t)n * sizeof(ShadeTri)));
     BvhTri *tmp = nullptr; float *aabb = nullptr, *leaf_box = nullptr, *node_box = nullptr, *bounds = nullptr;
     uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *hist = nullptr;
-    int *left = nullptr, *right = nullptr, *parent_int = nullptr, *parent_leaf = nullptr; unsigned int *flags = nullptr;
+    int *left = nullptr, *right = nullptr, *parent_int = nullptr, *parent_leaf = nullptr; unsigned int *flags = nullptr; int2 *range = nullptr;
+    LBVH_CHECK(cudaMalloc(&range, (size_t)(n > 1 ? n - 1 : 1) * sizeof(int2)));
     const uint32_t nblocks = (n + 255) / 256;
     LBVH_CHECK(cudaMalloc(&tmp, tri_bytes));
     LBVH_CHECK(cudaMalloc(&aabb, (size_t)n * 6 * sizeof(float)));
@@ -258,7 +286,7 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
     const float binit[6] = { 3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f };
     LBVH_CHECK(cudaMemcpyAsync(bounds, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
 
-    k_world_tris<<<nblocks, 256, 0, st>>>(d_verts, d_indices, d_meshes, d_instances, n_instances, n, tmp, aabb, bounds);
+    k_world_tris<<<nblocks, 256, 0, st>>>(d_verts, d_indices, d_meshes, d_instances, n_instances, n, tmp, tmp_shade, aabb, bounds);
     k_morton<<<nblocks, 256, 0, st>>>(aabb, bounds, n, keys, vals);
     for (int pass = 0; pass < 8; pass++) {
         k_radix_hist<<<nblocks, 256, 0, st>>>(keys, n, pass * 4, hist, nblocks);
@@ -266,35 +294,42 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
         k_radix_scatter<<<nblocks, 256, 0, st>>>(keys, vals, n, pass * 4, hist, nblocks, keys2, vals2);
         std::swap(keys, keys2); std::swap(vals, vals2);
     }
-    k_reorder<<<nblocks, 256, 0, st>>>(tmp, aabb, vals, n, tris, leaf_box);
+    k_reorder<<<nblocks, 256, 0, st>>>(tmp, tmp_shade, aabb, vals, n, tris, shade, leaf_box);
     if (n_int) {
-        k_karras<<<(n_int + 255) / 256, 256, 0, st>>>(keys, (int)n, left, right, parent_int, parent_leaf);
+        k_karras<<<(n_int + 255) / 256, 256, 0, st>>>(keys, (int)n, left, right, parent_int, parent_leaf, range);
         k_refit<<<nblocks, 256, 0, st>>>((int)n, left, right, parent_int, parent_leaf, leaf_box, node_box, flags);
-        k_emit<<<(n_int + 255) / 256, 256, 0, st>>>((int)n_int, left, right, leaf_box, node_box, nodes);
+        k_emit<<<(n_int + 255) / 256, 256, 0, st>>>((int)n_int, left, right, range, leaf_box, node_box, nodes);
     }
     LBVH_CHECK(cudaStreamSynchronize(st));
     LBVH_CHECK(cudaGetLastError());
 
-    // depth of the hierarchy (one-off, on the host) -> traversal stack size
-    int max_depth = 1;
+    // depth of the hierarchy actually traversed (one-off, on the host) -> traversal stack size
+    int max_depth = 1; int root_ref = n_int ? 0 : ~0;
     if (n_int) {
-        std::vector<int> hl(n_int), hr(n_int);
+        std::vector<int> hl(n_int), hr(n_int); std::vector<int2> hrange(n_int);
         LBVH_CHECK(cudaMemcpy(hl.data(), left, (size_t)n_int * 4, cudaMemcpyDeviceToHost));
         LBVH_CHECK(cudaMemcpy(hr.data(), right, (size_t)n_int * 4, cudaMemcpyDeviceToHost));
-        std::vector<std::pair<int, int>> stack; stack.push_back({ 0, 1 });
-        while (!stack.empty()) {
-            auto [node, dep] = stack.back(); stack.pop_back();
-            if (dep > max_depth) max_depth = dep;
-            if (hl[node] >= 0) stack.push_back({ hl[node], dep + 1 });
-            if (hr[node] >= 0) stack.push_back({ hr[node], dep + 1 });
+        LBVH_CHECK(cudaMemcpy(hrange.data(), range, (size_t)n_int * sizeof(int2), cudaMemcpyDeviceToHost));
+        auto is_leaf = [&](int c) { return c < 0 || hrange[c].y - hrange[c].x + 1 <= LBVH_LEAF_MAX; };
+        if (is_leaf(0)) root_ref = ~((0 << 2) | (int)(n - 1));              // whole scene fits one leaf
+        else {
+            std::vector<std::pair<int, int>> stack; stack.push_back({ 0, 1 });
+            while (!stack.empty()) {
+                auto [node, dep] = stack.back(); stack.pop_back();
+                if (dep > max_depth) max_depth = dep;
+                if (!is_leaf(hl[node])) stack.push_back({ hl[node], dep + 1 });
+                if (!is_leaf(hr[node])) stack.push_back({ hr[node], dep + 1 });
+            }
         }
     }
+    cudaFree(tmp_shade);
     cudaFree(tmp); cudaFree(aabb); cudaFree(leaf_box); cudaFree(node_box); cudaFree(bounds);
     cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(hist);
-    cudaFree(left); cudaFree(right); cudaFree(parent_int); cudaFree(parent_leaf); cudaFree(flags);
+    cudaFree(left); cudaFree(right); cudaFree(parent_int); cudaFree(parent_leaf); cudaFree(flags); cudaFree(range);
 
+    out->shade = shade;
     out->nodes = nodes; out->tris = tris; out->n_nodes = n_nodes_alloc; out->n_tris = n;
-    out->root = n_int ? 0 : ~0;
+    out->root = root_ref;
     out->max_depth = max_depth;
     out->bytes = node_bytes + tri_bytes;
     return 0;

@@ -22,12 +22,20 @@ __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x 
 __device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
 __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+#ifdef B200PT_PRECISE
 __device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+#else   // one reciprocal instead of three divisions (2-ulp class, see Makefile PRECISE)
+__device__ __forceinline__ float3 operator/(float3 a, float s) { const float r = 1.0f / s; return f3(a.x * r, a.y * r, a.z * r); }
+#endif
 __device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 __device__ __forceinline__ float length(float3 a) { return sqrtf(dot(a, a)); }
+#ifdef B200PT_PRECISE
 __device__ __forceinline__ float3 normalize(float3 a) { float inv = 1.0f / sqrtf(dot(a, a)); return a * inv; }
+#else
+__device__ __forceinline__ float3 normalize(float3 a) { float inv = rsqrtf(dot(a, a)); return a * inv; }
+#endif
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float mixf(float x, float y, float a) { return x * (1.0f - a) + y * a; }            // FMix
 __device__ __forceinline__ float3 mix3(float3 x, float3 y, float a) { return f3(mixf(x.x, y.x, a), mixf(x.y, y.y, a), mixf(x.z, y.z, a)); }
@@ -212,13 +220,15 @@ __device__ __forceinline__ b200pt_vertex load_vertex(const b200pt_vertex *p) {
     return v;
 }
 
-__device__ __forceinline__ void surface_init(Surface &sf, const DevScene &sc, const DevConfig &cfg, const DevInstance &in,
-                                             uint32_t prim, float bu, float bv, float3 rayDir, const DevTexture &normalTex) {
-    const DevMesh m = sc.meshes[in.mesh];
-    const uint32_t *ix = sc.indices + m.ibase + (size_t)prim * 3;
-    const b200pt_vertex A = load_vertex(sc.verts + m.vbase + __ldg(ix + 0));
-    const b200pt_vertex B = load_vertex(sc.verts + m.vbase + __ldg(ix + 1));
-    const b200pt_vertex C = load_vertex(sc.verts + m.vbase + __ldg(ix + 2));
+__device__ __forceinline__ void surface_init(Surface &sf, const DevScene &sc, const DevConfig &cfg, const DevInstance &in, const float4 (&g)[7],
+                                             float bu, float bv, float3 rayDir, const DevMaterial &dm) {
+    // g = ShadeTri of the hit triangle (object-space vertices, SH/Surface.slang:33-41)
+    b200pt_vertex A, B, C;
+    A.Position[0] = g[0].x; A.Position[1] = g[0].y; A.Position[2] = g[0].z; B.Position[0] = g[1].x; B.Position[1] = g[1].y; B.Position[2] = g[1].z;
+    C.Position[0] = g[2].x; C.Position[1] = g[2].y; C.Position[2] = g[2].z;
+    A.Normal[0] = g[3].x; A.Normal[1] = g[3].y; A.Normal[2] = g[3].z; B.Normal[0] = g[4].x; B.Normal[1] = g[4].y; B.Normal[2] = g[4].z;
+    C.Normal[0] = g[5].x; C.Normal[1] = g[5].y; C.Normal[2] = g[5].z;
+    A.TexCoord[0] = g[3].w; A.TexCoord[1] = g[4].w; B.TexCoord[0] = g[5].w; B.TexCoord[1] = g[6].x; C.TexCoord[0] = g[6].y; C.TexCoord[1] = g[6].z;
     float b0 = 1.0f - bu - bv, b1 = bu, b2 = bv;                                  // SH/ClosestHit.slang:45
     float3 p1 = f3(A.Position[0], A.Position[1], A.Position[2]), p2 = f3(B.Position[0], B.Position[1], B.Position[2]), p3 = f3(C.Position[0], C.Position[1], C.Position[2]);
     sf.P1 = p1; sf.P2 = p2; sf.P3 = p3;
@@ -242,7 +252,7 @@ __device__ __forceinline__ void surface_init(Surface &sf, const DevScene &sc, co
     sf.Tangent = normalize(cross(up, n));                                         // :82
     sf.Bitangent = normalize(cross(n, sf.Tangent));                               // :83
     if (!cfg.UseOnlyGeometryNormals) {                                            // :85-90 (Q10)
-        float4 t = tex_sample_u8(normalTex, sf.u, sf.v);
+        const float4 t = (dm.const_mask & 2u) ? dm.cnormal : tex_sample_u8(sc.textures[dm.m.NormalTextureIndex], sf.u, sf.v);
         sf.Normal = sf.tangent_to_world(f3(t.x * 2.0f - 1.0f, t.y * 2.0f - 1.0f, t.z * 2.0f - 1.0f));
     }
     if (dot(sf.Normal, view) < 0.0f) {                                            // :92-100
@@ -277,7 +287,8 @@ struct Eval { float3 BxDF; float PDF; };
 struct BSample { float3 L; float3 BxDF; float PDF; };
 
 // :39-87
-__device__ __forceinline__ void material_init(Mat &m, const DevScene &sc, const DevConfig &cfg, const b200pt_material &src, const Surface &sf) {
+__device__ __forceinline__ void material_init(Mat &m, const DevScene &sc, const DevConfig &cfg, const DevMaterial &dm, const Surface &sf) {
+    const b200pt_material &src = dm.m;
     m.BaseColor = f3(src.BaseColor[0], src.BaseColor[1], src.BaseColor[2]);
     m.EmissiveColor = f3(src.EmissiveColor[0], src.EmissiveColor[1], src.EmissiveColor[2]);
     m.SpecularColor = f3(src.SpecularColor[0], src.SpecularColor[1], src.SpecularColor[2]);
@@ -285,12 +296,12 @@ __device__ __forceinline__ void material_init(Mat &m, const DevScene &sc, const 
     m.Metallic = src.Metallic; m.Roughness = src.Roughness; m.IOR = src.IOR; m.Transmission = src.Transmission;
     m.Anisotropy = src.Anisotropy; m.AnisotropyRotation = src.AnisotropyRotation;
     m.MediumDensity = src.MediumDensity; m.MediumAnisotropy = src.MediumAnisotropy;
-    float4 tb = tex_sample_u8(sc.textures[src.BaseColorTextureIndex], sf.u, sf.v);
+    const float4 tb = (dm.const_mask & 1u) ? dm.cbase : tex_sample_u8(sc.textures[src.BaseColorTextureIndex], sf.u, sf.v);
     m.IOR = fmaxf(m.IOR, 1.000001f);
     m.BaseColor = m.BaseColor * f3(pt_pow(tb.x, 2.2f), pt_pow(tb.y, 2.2f), pt_pow(tb.z, 2.2f));
-    m.Roughness *= tex_sample_u8(sc.textures[src.RoughnessTextureIndex], sf.u, sf.v).x;     // Q8, Q9
-    m.Metallic *= tex_sample_u8(sc.textures[src.MetallicTextureIndex], sf.u, sf.v).x;
-    float4 te = tex_sample_u8(sc.textures[src.EmissiveTextureIndex], sf.u, sf.v);
+    m.Roughness *= (dm.const_mask & 4u) ? dm.crough : tex_sample_u8(sc.textures[src.RoughnessTextureIndex], sf.u, sf.v).x;     // Q8, Q9
+    m.Metallic *= (dm.const_mask & 8u) ? dm.cmetal : tex_sample_u8(sc.textures[src.MetallicTextureIndex], sf.u, sf.v).x;
+    const float4 te = (dm.const_mask & 16u) ? dm.cemis : tex_sample_u8(sc.textures[src.EmissiveTextureIndex], sf.u, sf.v);
     m.EmissiveColor = m.EmissiveColor * f3(te.x, te.y, te.z);
     float aspect = sqrtf(1.0f - sqrtf(m.Anisotropy) * 0.9f);
     m.Ax = fmaxf(0.00001f, m.Roughness / aspect);
@@ -442,17 +453,22 @@ __device__ __forceinline__ bool sample_bsdf_direction(const Mat &m, const BsdfCt
 }
 
 // ---------------------------------------------------------------- NEE samplers
-// SH/Sampler.slang:287-346
-__device__ __forceinline__ void sample_env(const DevScene &sc, const DevConfig &cfg, Rng &rng, float3 &toLight, float4 &val) {
-    float xx = rng.next(), xy = rng.next(), xz = rng.next();
-    uint32_t width = sc.envW, height = sc.envH;
-    uint32_t size = width * height;
-    uint32_t idx = min((uint32_t)(xx * (float)size), size - 1u);
-    uint2 e = __ldg(sc.alias + idx);
-    float imp = __uint_as_float(e.y);
+// SH/Sampler.slang:287-346, split in two so the dependent DRAM access (random 8-B alias entry out of a 64 MiB table)
+// can be issued at the top of the shading kernel and overlap the surface / material set-up.
+struct EnvPick { float xy, xz; uint32_t idx; uint2 entry; };
+__device__ __forceinline__ void sample_env_begin(const DevScene &sc, Rng &rng, EnvPick &p) {
+    const float xx = rng.next(); p.xy = rng.next(); p.xz = rng.next();     // UniformFloat3 (:290)
+    const uint32_t size = sc.envW * sc.envH;
+    p.idx = min((uint32_t)(xx * (float)size), size - 1u);                   // :297
+    p.entry = __ldg(sc.alias + p.idx);                                      // :300
+}
+__device__ __forceinline__ void sample_env_finish(const DevScene &sc, const DevConfig &cfg, const EnvPick &p, float3 &toLight, float4 &val) {
+    float xy = p.xy; const float xz = p.xz;
+    const uint32_t width = sc.envW, height = sc.envH;
+    const float imp = __uint_as_float(p.entry.y);
     uint32_t envIdx;
-    if (xy < imp) { envIdx = idx; xy /= imp; }
-    else { envIdx = e.x; xy = (xy - imp) / (1.0f - imp); }
+    if (xy < imp) { envIdx = p.idx; xy /= imp; }
+    else { envIdx = p.entry.x; xy = (xy - imp) / (1.0f - imp); }
     uint32_t px = envIdx % width, py = envIdx / width;
     float u = ((float)px + xy) / (float)width;
     float phi = u * (2.0f * PT_PI) - PT_PI;
@@ -481,14 +497,11 @@ __device__ __forceinline__ void sample_emissive(const DevScene &sc, Rng &rng, fl
     const uint32_t tc = em.tri_count;
     uint32_t ti = min((uint32_t)floorf(rng.next() * (float)tc), tc - 1u);
     tri = ti;
-    const DevMesh m = sc.meshes[em.mesh];
-    const uint32_t *ix = sc.indices + m.ibase + (size_t)ti * 3;
-    const b200pt_vertex A = load_vertex(sc.verts + m.vbase + __ldg(ix + 0));
-    const b200pt_vertex B = load_vertex(sc.verts + m.vbase + __ldg(ix + 1));
-    const b200pt_vertex C = load_vertex(sc.verts + m.vbase + __ldg(ix + 2));
-    float3 p0 = mat4_point(em.xf, f3(A.Position[0], A.Position[1], A.Position[2]));
-    float3 p1 = mat4_point(em.xf, f3(B.Position[0], B.Position[1], B.Position[2]));
-    float3 p2 = mat4_point(em.xf, f3(C.Position[0], C.Position[1], C.Position[2]));
+    const float4 *et = reinterpret_cast<const float4 *>(sc.em_tris + (__ldg(sc.em_tri_base + mi) + ti));
+    const float4 e0 = __ldg(et), e1 = __ldg(et + 1), e2 = __ldg(et + 2), e3 = __ldg(et + 3);
+    const float3 p0 = f3(e0), p1 = f3(e1), p2 = f3(e2);                   // world-space corners (:389-391, transformed once on the host)
+    b200pt_vertex A, B, C;
+    A.TexCoord[0] = e0.w; A.TexCoord[1] = e1.w; B.TexCoord[0] = e2.w; B.TexCoord[1] = e3.x; C.TexCoord[0] = e3.y; C.TexCoord[1] = e3.z;
     float x0 = rng.next(), x1 = rng.next();
     float su1 = sqrtf(x0);
     float b0 = 1.0f - su1, b1 = x1 * su1, b2 = 1.0f - b0 - b1;
@@ -501,8 +514,9 @@ __device__ __forceinline__ void sample_emissive(const DevScene &sc, Rng &rng, fl
     float area = length(cross(p1 - p0, p2 - p0)) * 0.5f;
     float d2 = dot(dl, dl);
     float cosTheta = fabsf(dot(normal, toLight));
-    const b200pt_material &mat = sc.materials[em.material];
-    float4 te = tex_sample_u8(sc.textures[mat.EmissiveTextureIndex], uu, vv);
+    const DevMaterial &dmat = sc.materials[em.material];
+    const b200pt_material &mat = dmat.m;
+    const float4 te = (dmat.const_mask & 16u) ? dmat.cemis : tex_sample_u8(sc.textures[mat.EmissiveTextureIndex], uu, vv);
     colorPDF.w = d2 / ((float)count * (float)tc * area * cosTheta);
     colorPDF.x = mat.EmissiveColor[0] * te.x; colorPDF.y = mat.EmissiveColor[1] * te.y; colorPDF.z = mat.EmissiveColor[2] * te.z;
 }

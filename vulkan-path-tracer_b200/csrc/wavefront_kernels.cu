@@ -107,25 +107,43 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
         ctrl[parity ^ 1u] = 0; ctrl[2u + 2u * (parity ^ 1u)] = 0; ctrl[3u + 2u * (parity ^ 1u)] = 0;
     }
     uint32_t *qh_count = ctrl + 2u + 2u * parity, *qm_count = ctrl + 3u + 2u * parity;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_round = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    __shared__ uint32_t s_cnt[2][8], s_base[2];
+    const uint32_t n_round = (n + 255u) & ~255u;                            // whole blocks iterate together (block-level scan below)
+    // software pipelining: the ray of the NEXT grid-stride iteration is loaded before the current one is traversed
+    const uint32_t step = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
+    if (i < n) { o4 = ps.org_pdf[i]; d4 = ps.dir_rng[i]; }
+    for (; i < n_round; i += step) {
         const bool active = i < n;
         bool hit = false;
+        const uint32_t inext = i + step;
+        float4 o4n = make_float4(0, 0, 0, 0), d4n = o4n;
+        if (inext < n) { o4n = ps.org_pdf[inext]; d4n = ps.dir_rng[inext]; }
         if (active) {
-            const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
             const float3 rd = normalize(f3(d4));                            // SH/RayGen.slang:70
             HitRec h;
             hit = bvh_trace<SMEM, false>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
             so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
         }
+        o4 = o4n; d4 = d4n;
+        // queue append: warp ballots -> block scan in shared memory -> ONE atomic per block and queue (ncu round 1: the per-warp
+        // atomics on two addresses serialised in L2 and were 51 % of this kernel's stall samples)
         const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
-        uint32_t base_h = 0, base_m = 0;
-        if (lane == 0) { if (bh) base_h = atomicAdd(qh_count, (uint32_t)__popc(bh)); if (bm) base_m = atomicAdd(qm_count, (uint32_t)__popc(bm)); }
-        base_h = __shfl_sync(0xFFFFFFFFu, base_h, 0); base_m = __shfl_sync(0xFFFFFFFFu, base_m, 0);
+        if (lane == 0) { s_cnt[0][warp] = (uint32_t)__popc(bh); s_cnt[1][warp] = (uint32_t)__popc(bm); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            uint32_t tot = 0;
+            #pragma unroll
+            for (int w = 0; w < 8; w++) { const uint32_t c = s_cnt[threadIdx.x][w]; s_cnt[threadIdx.x][w] = tot; tot += c; }
+            s_base[threadIdx.x] = tot ? atomicAdd(threadIdx.x == 0 ? qh_count : qm_count, tot) : 0u;
+        }
+        __syncthreads();
         const uint32_t lt = (1u << lane) - 1u;
-        if (hit) q_hit[base_h + __popc(bh & lt)] = i;
-        else if (active) q_miss[base_m + __popc(bm & lt)] = i;
+        if (hit) q_hit[s_base[0] + s_cnt[0][warp] + __popc(bh & lt)] = i;
+        else if (active) q_miss[s_base[1] + s_cnt[1][warp] + __popc(bm & lt)] = i;
+        __syncthreads();
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->extend_rays, (unsigned long long)n);
 }
@@ -193,13 +211,23 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         Rng rng; rng.s = __float_as_uint(d4.w);
         const uint32_t slot = __float_as_uint(h4.w);
 
+        // The sky-NEE draws are the first draws of a hit outside a medium: take them now and put the alias-table load in flight.
+        EnvPick ep;
+        const bool envEarly = cfg.EnableSkyMIS && !inMedium;
+        if (envEarly) sample_env_begin(sc, rng, ep);
+
         const float3 rd = normalize(payDir);                                // WorldRayDirection()
-        const BvhTri *tri = sc.tris + slot;
-        const uint32_t inst = __float_as_uint(__ldg(&tri->b).w), prim = __float_as_uint(__ldg(&tri->c).w);
+        float4 g[7];                                                        // one 112-B gather: vertices + ids of the hit triangle
+        {
+            const float4 *gp = reinterpret_cast<const float4 *>(sc.shade_tris + slot);
+            #pragma unroll
+            for (int q = 0; q < 7; q++) g[q] = __ldg(gp + q);
+        }
+        const uint32_t inst = __float_as_uint(g[0].w);
         const DevInstance &in = sc.instances[inst];
-        const b200pt_material &cm = sc.materials[in.material];
+        const DevMaterial &cm = sc.materials[__float_as_uint(g[2].w)];
         Surface sf;
-        surface_init(sf, sc, cfg, in, prim, h4.y, h4.z, rd, sc.textures[cm.NormalTextureIndex]);
+        surface_init(sf, sc, cfg, in, g, h4.y, h4.z, rd, cm);
         Mat m;
         material_init(m, sc, cfg, cm, sf);
         const bool isLight = m.EmissiveColor.x > 0.0f || m.EmissiveColor.y > 0.0f || m.EmissiveColor.z > 0.0f;   // :65
@@ -231,7 +259,8 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         // sky NEE sample :125-147 (visibility is resolved in k_connect)
         float3 toSkyW = f3(0.0f), toSkyT = f3(0.0f); float4 sky = zero4;
         if (cfg.EnableSkyMIS) {
-            sample_env(sc, cfg, rng, toSkyW, sky);
+            if (!envEarly) sample_env_begin(sc, rng, ep);
+            sample_env_finish(sc, cfg, ep, toSkyW, sky);
             sky.x *= cfg.EnvironmentIntensity; sky.y *= cfg.EnvironmentIntensity; sky.z *= cfg.EnvironmentIntensity;   // Q7
             toSkyT = sf.world_to_tangent(toSkyW);
         }
@@ -362,16 +391,16 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
             rng.s = __float_as_uint(d4.w);
             thr = f3(thr4); rad = f3(r4);
             float3 emitted = f3(e4);
-            const float4 so4 = so.sky_o[i];
+            // all six request words are fetched up front (independent 16-B loads in flight together); the d/c words of an
+            // invalid request are stale and never used
+            const float4 so4 = so.sky_o[i], sd4 = so.sky_d[i], sc4 = so.sky_c[i];
+            const float4 lo4 = so.lit_o[i], ld4_ = so.lit_d[i], lc4 = so.lit_c[i];
             if (so4.w != 0.0f) {                                            // SH/ClosestHit.slang:139 + :326-358
-                const float4 sd4 = so.sky_d[i];
                 HitRec h; n_shadow++;
                 const bool occluded = bvh_trace<SMEM, true>(bv, f3(so4), f3(sd4), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
-                if (!occluded) emitted = emitted + f3(so.sky_c[i]);
+                if (!occluded) emitted = emitted + f3(sc4);
             }
-            const float4 lo4 = so.lit_o[i];
             if (lo4.w != 0.0f) {                                            // :171-176 + :360-372 (closest hit must be the sampled triangle)
-                const float4 ld4_ = so.lit_d[i], lc4 = so.lit_c[i];
                 HitRec h; n_shadow++;
                 const bool found = bvh_trace<SMEM, false>(bv, f3(lo4), f3(ld4_), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
                 if (found) {
@@ -524,8 +553,9 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<false>, 256, sh);
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade_hit, 128, 0);
-    int occ_t = occ_e < occ_c ? occ_e : occ_c; if (occ_t < 1) occ_t = 1; if (occ_s < 1) occ_s = 1;
-    lc->grid_trace = sms * occ_t;
+    if (occ_e < 1) occ_e = 1; if (occ_c < 1) occ_c = 1; if (occ_s < 1) occ_s = 1;
+    lc->grid_extend = sms * occ_e; lc->grid_connect = sms * occ_c;
+    lc->grid_trace = sms * occ_e;
     lc->grid_shade = sms * occ_s;
     lc->grid_light = sms * 8;
     return 0;
@@ -540,8 +570,8 @@ void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeO
     set_attrs_once();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_extend<true><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
-    else k_extend<false><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+    if (smem) k_extend<true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+    else k_extend<false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
 }
 void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity,
                   const uint32_t *q_hit, const uint32_t *q_miss, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
@@ -553,8 +583,8 @@ void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cf
     set_attrs_once();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_connect<true><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
-    else k_connect<false><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
+    if (smem) k_connect<true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
+    else k_connect<false><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
 }
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
                     const float4 *sample_buf, float4 *image, cudaStream_t st) {
