@@ -169,6 +169,8 @@ int32_t b200pt_save_png(b200pt_handle h, const char *path);
 /* ---- fine-grained hooks used by the parity tests (closest-hit semantics of RTCommon.slang:47-117) ---- */
 int32_t b200pt_trace_closest(b200pt_handle h, uint32_t n, const float *origins3, const float *directions3,
                              float tmin, float tmax, float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out2);
+/* traversal cost of the same query: nodes_tris_out[2*i] = BVH nodes visited, [2*i+1] = triangles tested (measurement hook) */
+int32_t b200pt_trace_stats(b200pt_handle h, uint32_t n, const float *origins3, const float *directions3, float tmin, float tmax, uint32_t *nodes_tris_out);
 int32_t b200pt_scene_stats(b200pt_handle h, uint32_t *triangles, uint32_t *bvh_nodes, uint32_t *emissive_meshes, uint32_t *textures);
 
 /* ---- standalone codecs of the loader / image-output API (no GPU needed) ---- */

@@ -120,6 +120,7 @@ def lib():
             "b200pt_bloom_mip_sizes": [C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)], "b200pt_save_png": [C.c_void_p, C.c_char_p],
             "b200pt_trace_closest": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
             "b200pt_scene_stats": [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4,
+            "b200pt_trace_stats": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p],
             "b200pt_decode_image_file": [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)],
             "b200pt_decode_hdr_file": [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)],
             "b200pt_write_png": [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p],
@@ -375,6 +376,12 @@ class PathTracer:
         t = np.zeros(n, np.float32); prim = np.zeros(n, np.uint32); inst = np.zeros(n, np.uint32); uv = np.zeros((n, 2), np.float32)
         self._ck(self.L.b200pt_trace_closest(self.h, n, _p(org), _p(dirs), C.c_float(tmin), C.c_float(tmax), _p(t), _p(prim), _p(inst), _p(uv)))
         return t, prim, inst, uv
+
+    def trace_stats(self, org, dirs, tmin, tmax):
+        org = np.ascontiguousarray(org, np.float32); dirs = np.ascontiguousarray(dirs, np.float32); n = len(org)
+        st = np.zeros((n, 2), np.uint32)
+        self._ck(self.L.b200pt_trace_stats(self.h, n, _p(org), _p(dirs), C.c_float(tmin), C.c_float(tmax), _p(st)))
+        return st
 
     def scene_stats(self):
         a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()

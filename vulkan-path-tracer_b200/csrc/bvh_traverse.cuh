@@ -80,9 +80,9 @@ __device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3
 }
 
 // stack: shared-memory column of this thread, entries at stack[k * stride]
-template <bool SMEM, bool ANYHIT>
+template <bool SMEM, bool ANYHIT, bool COUNT = false>
 __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, float tmin, float tmax, HitRec &h,
-                                          int *stack, int stride, int max_stack) {
+                                          int *stack, int stride, int max_stack, uint32_t *n_nodes = nullptr, uint32_t *n_tris = nullptr) {
     h.slot = 0xFFFFFFFFu; h.t = tmax; h.u = 0.0f; h.v = 0.0f;
     uint32_t best_gid = 0xFFFFFFFFu;
     bool found = false;
@@ -91,6 +91,7 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
     int cur = b.root;
     while (true) {
         if (cur >= 0) {
+            if (COUNT) (*n_nodes)++;
             const float4 *np = b.nodes + (size_t)cur * 4;
             const float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
             // child 0: lo (n0.x n0.y n0.z) hi (n0.w n1.x n1.y); child 1: lo (n1.z n1.w n2.x) hi (n2.y n2.z n2.w)
@@ -119,6 +120,7 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
             const uint32_t first = ref >> 2, count = (ref & 3u) + 1u;
             for (uint32_t q = 0; q < count; q++) {
                 const uint32_t slot = first + q;
+                if (COUNT) (*n_tris)++;
                 const float4 *tp = b.tris + (size_t)slot * 3;
                 const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
                 float t, u, v;

@@ -151,6 +151,10 @@ int32_t b200pt_trace_closest(b200pt_handle h, uint32_t n, const float *o, const 
     if (n && (!o || !d || !t || !prim || !inst || !uv)) return B200PT_ERR_WRONG_ARGUMENTS;
     return guard(h, [&](Engine &e) { e.trace_closest(n, o, d, tmin, tmax, t, prim, inst, uv); });
 }
+int32_t b200pt_trace_stats(b200pt_handle h, uint32_t n, const float *o, const float *d, float tmin, float tmax, uint32_t *nodes_tris) {
+    if (n && (!o || !d || !nodes_tris)) return B200PT_ERR_WRONG_ARGUMENTS;
+    return guard(h, [&](Engine &e) { std::vector<float> t(n), uv(2 * (size_t)n); std::vector<uint32_t> p(n), i(n); e.trace_closest(n, o, d, tmin, tmax, t.data(), p.data(), i.data(), uv.data(), nodes_tris); });
+}
 int32_t b200pt_scene_stats(b200pt_handle h, uint32_t *a, uint32_t *b, uint32_t *c, uint32_t *d) { return guard(h, [&](Engine &e) { e.scene_stats(a, b, c, d); }); }
 
 // ---- standalone codecs ----

@@ -461,7 +461,7 @@ void Engine::get_bloom(float *dst) {
     CK(cudaStreamSynchronize(stream_));
 }
 
-void Engine::trace_closest(uint32_t n, const float *org, const float *dir, float tmin, float tmax, float *t, uint32_t *prim, uint32_t *inst, float *uv) {
+void Engine::trace_closest(uint32_t n, const float *org, const float *dir, float tmin, float tmax, float *t, uint32_t *prim, uint32_t *inst, float *uv, uint32_t *stats) {
     CK(cudaSetDevice(device_));
     if (!has_scene_) throw CudaError{ B200PT_ERR_NO_SCENE, "no scene" };
     if (!n) return;
@@ -469,11 +469,13 @@ void Engine::trace_closest(uint32_t n, const float *org, const float *dir, float
     CK(cudaMalloc(&d_o, (size_t)n * 12)); CK(cudaMalloc(&d_d, (size_t)n * 12)); CK(cudaMalloc(&d_t, (size_t)n * 4)); CK(cudaMalloc(&d_uv, (size_t)n * 8));
     CK(cudaMalloc(&d_p, (size_t)n * 4)); CK(cudaMalloc(&d_i, (size_t)n * 4));
     CK(cudaMemcpyAsync(d_o, org, (size_t)n * 12, cudaMemcpyHostToDevice, stream_)); CK(cudaMemcpyAsync(d_d, dir, (size_t)n * 12, cudaMemcpyHostToDevice, stream_));
-    launch_trace_rays(lc_, ds_, n, d_o, d_d, tmin, tmax, d_t, d_p, d_i, d_uv, stream_);
+    uint32_t *d_st = nullptr; if (stats) CK(cudaMalloc(&d_st, (size_t)n * 8));
+    launch_trace_rays(lc_, ds_, n, d_o, d_d, tmin, tmax, d_t, d_p, d_i, d_uv, d_st, stream_);
+    if (stats) CK(cudaMemcpyAsync(stats, d_st, (size_t)n * 8, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_)); CK(cudaMemcpyAsync(prim, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(inst, d_i, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_)); CK(cudaMemcpyAsync(uv, d_uv, (size_t)n * 8, cudaMemcpyDeviceToHost, stream_));
     cudaError_t e = cudaStreamSynchronize(stream_);
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_uv); cudaFree(d_p); cudaFree(d_i);
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_uv); cudaFree(d_p); cudaFree(d_i); if (d_st) cudaFree(d_st);
     CK(e); CK(cudaGetLastError());
 }
 void Engine::scene_stats(uint32_t *tris, uint32_t *nodes, uint32_t *emissive, uint32_t *textures) const {

@@ -51,7 +51,7 @@ public:
     void get_ldr(uint8_t *dst, bool dst_is_device);
     void get_bloom(float *dst);
 
-    void trace_closest(uint32_t n, const float *org, const float *dir, float tmin, float tmax, float *t, uint32_t *prim, uint32_t *inst, float *uv);
+    void trace_closest(uint32_t n, const float *org, const float *dir, float tmin, float tmax, float *t, uint32_t *prim, uint32_t *inst, float *uv, uint32_t *stats = nullptr);
     void scene_stats(uint32_t *tris, uint32_t *nodes, uint32_t *emissive, uint32_t *textures) const;
 
     std::string last_error;

@@ -26,7 +26,7 @@ void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cf
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
                     const float4 *sample_buf, float4 *image, cudaStream_t st);
 void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, const float *org, const float *dir, float tmin, float tmax,
-                       float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, cudaStream_t st);
+                       float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, uint32_t *stats, cudaStream_t st);
 
 // ---- LBVH build (lbvh.cu): world-space flattening of the two-level TLAS/BLAS ----
 struct LbvhResult { ShadeTri *shade; BvhNode *nodes; BvhTri *tris; uint32_t n_nodes, n_tris; int32_t root; int max_depth; size_t bytes; };

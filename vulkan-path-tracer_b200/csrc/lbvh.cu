@@ -78,34 +78,47 @@ __global__ void k_world_tris(const b200pt_vertex *__restrict__ verts, const uint
 }
 
 // ---- 2. Morton keys ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
-    v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;
-    v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
-    return v;
+// 60-bit Morton keys (20 bits per axis) + 2 size-class bits: with 10 bits per axis every finely tessellated object collapses into a handful of
+// 1.2-cm cells of equal key and Karras falls back to index order there (measured on BreakfastRoom: up to 647 triangle
+// tests for one camera ray, profiles/r01_bvh_stats.txt)
+__device__ __forceinline__ unsigned long long expand_bits21(unsigned long long x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
 }
-__global__ void k_morton(const float *__restrict__ aabb, const float *__restrict__ bounds, uint32_t n, uint32_t *keys, uint32_t *vals) {
+__global__ void k_morton(const float *__restrict__ aabb, const float *__restrict__ bounds, uint32_t n, unsigned long long *keys, uint32_t *vals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float *bb = aabb + (size_t)i * 6;
-    uint32_t q[3];
+    unsigned long long q[3];
+    float rel = 0.0f;                                                     // largest extent of the triangle relative to the scene
     for (int k = 0; k < 3; k++) {
         const float c = 0.5f * (bb[k] + bb[3 + k]);
         const float ext = bounds[3 + k] - bounds[k];
         float f = ext > 0.0f ? (c - bounds[k]) / ext : 0.0f;
-        f = fminf(fmaxf(f * 1024.0f, 0.0f), 1023.0f);
-        q[k] = (uint32_t)f;
+        if (ext > 0.0f) rel = fmaxf(rel, (bb[3 + k] - bb[k]) / ext);
+        f = fminf(fmaxf(f * 1048576.0f, 0.0f), 1048575.0f);
+        q[k] = (unsigned long long)f;
     }
-    keys[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+    // Size class in the top key bits: a wall-sized triangle sorted by its centroid alone inflates every ancestor box on its
+    // root-to-leaf path (BreakfastRoom: p99 143 / max 324 node visits per camera ray).  Sorting by (size class, Morton code)
+    // makes Karras split by size first, so large triangles live in their own small subtrees next to the root.
+    const unsigned long long cls = rel > 0.25f ? 3ull : (rel > 0.0625f ? 2ull : (rel > 0.015625f ? 1ull : 0ull));
+    keys[i] = (cls << 60) | (expand_bits21(q[0]) << 2) | (expand_bits21(q[1]) << 1) | expand_bits21(q[2]);
     vals[i] = i;
 }
 
 // ---- 3. stable LSD radix sort, 4-bit digits, 256-element tiles ----------------------------------
-__global__ void __launch_bounds__(256) k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t *__restrict__ hist, uint32_t nblocks) {
+__global__ void __launch_bounds__(256) k_radix_hist(const unsigned long long *__restrict__ keys, uint32_t n, int shift, uint32_t *__restrict__ hist, uint32_t nblocks) {
     __shared__ uint32_t cnt[16];
     if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & 15u], 1u);
+    if (i < n) atomicAdd(&cnt[(uint32_t)(keys[i] >> shift) & 15u], 1u);
     __syncthreads();
     if (threadIdx.x < 16) hist[threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
 }
@@ -132,14 +145,14 @@ __global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ hist
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(256) k_radix_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n, int shift,
-                                                        const uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+__global__ void __launch_bounds__(256) k_radix_scatter(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n, int shift,
+                                                        const uint32_t *__restrict__ hist, uint32_t nblocks, unsigned long long *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
     __shared__ uint32_t wcnt[8][17];
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const bool act = i < n;
-    const uint32_t key = act ? keys[i] : 0u, val = act ? vals[i] : 0u;
-    const uint32_t dig = act ? ((key >> shift) & 15u) : 16u;
+    const unsigned long long key = act ? keys[i] : 0ull; const uint32_t val = act ? vals[i] : 0u;
+    const uint32_t dig = act ? ((uint32_t)(key >> shift) & 15u) : 16u;
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dig);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     if (threadIdx.x < 8 * 17) (&wcnt[0][0])[threadIdx.x] = 0;
@@ -165,13 +178,13 @@ __global__ void k_reorder(const BvhTri *__restrict__ tmp, const ShadeTri *__rest
 }
 
 // ---- 5. Karras 2012 hierarchy -------------------------------------------------------------------
-__device__ __forceinline__ int lbvh_delta(const uint32_t *keys, int n, int i, int j) {
+__device__ __forceinline__ int lbvh_delta(const unsigned long long *keys, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
-    const uint32_t a = keys[i], b = keys[j];
-    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
-    return __clz(a ^ b);
+    const unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
 }
-__global__ void k_karras(const uint32_t *__restrict__ keys, int n, int *__restrict__ left, int *__restrict__ right, int *__restrict__ parent_int, int *__restrict__ parent_leaf,
+__global__ void k_karras(const unsigned long long *__restrict__ keys, int n, int *__restrict__ left, int *__restrict__ right, int *__restrict__ parent_int, int *__restrict__ parent_leaf,
                          int2 *__restrict__ range) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -266,7 +279,7 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
     ShadeTri *tmp_shade = nullptr, *shade = nullptr;
     LBVH_CHECK(cudaMalloc(&tmp_shade, (size_t)n * sizeof(ShadeTri))); LBVH_CHECK(cudaMalloc(&shade, (size_t)n * sizeof(ShadeTri)));
     BvhTri *tmp = nullptr; float *aabb = nullptr, *leaf_box = nullptr, *node_box = nullptr, *bounds = nullptr;
-    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *hist = nullptr;
+    unsigned long long *keys = nullptr, *keys2 = nullptr; uint32_t *vals = nullptr, *vals2 = nullptr, *hist = nullptr;
     int *left = nullptr, *right = nullptr, *parent_int = nullptr, *parent_leaf = nullptr; unsigned int *flags = nullptr; int2 *range = nullptr;
     LBVH_CHECK(cudaMalloc(&range, (size_t)(n > 1 ? n - 1 : 1) * sizeof(int2)));
     const uint32_t nblocks = (n + 255) / 256;
@@ -275,8 +288,8 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
     LBVH_CHECK(cudaMalloc(&leaf_box, (size_t)n * 6 * sizeof(float)));
     LBVH_CHECK(cudaMalloc(&node_box, (size_t)n_nodes_alloc * 6 * sizeof(float)));
     LBVH_CHECK(cudaMalloc(&bounds, 6 * sizeof(float)));
-    LBVH_CHECK(cudaMalloc(&keys, (size_t)n * 4)); LBVH_CHECK(cudaMalloc(&vals, (size_t)n * 4));
-    LBVH_CHECK(cudaMalloc(&keys2, (size_t)n * 4)); LBVH_CHECK(cudaMalloc(&vals2, (size_t)n * 4));
+    LBVH_CHECK(cudaMalloc(&keys, (size_t)n * 8)); LBVH_CHECK(cudaMalloc(&vals, (size_t)n * 4));
+    LBVH_CHECK(cudaMalloc(&keys2, (size_t)n * 8)); LBVH_CHECK(cudaMalloc(&vals2, (size_t)n * 4));
     LBVH_CHECK(cudaMalloc(&hist, (size_t)16 * nblocks * 4));
     LBVH_CHECK(cudaMalloc(&left, (size_t)n_nodes_alloc * 4)); LBVH_CHECK(cudaMalloc(&right, (size_t)n_nodes_alloc * 4));
     LBVH_CHECK(cudaMalloc(&parent_int, (size_t)n_nodes_alloc * 4)); LBVH_CHECK(cudaMalloc(&parent_leaf, (size_t)n * 4));
@@ -288,7 +301,7 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
 
     k_world_tris<<<nblocks, 256, 0, st>>>(d_verts, d_indices, d_meshes, d_instances, n_instances, n, tmp, tmp_shade, aabb, bounds);
     k_morton<<<nblocks, 256, 0, st>>>(aabb, bounds, n, keys, vals);
-    for (int pass = 0; pass < 8; pass++) {
+    for (int pass = 0; pass < 16; pass++) {                              // 63-bit keys, 4-bit digits
         k_radix_hist<<<nblocks, 256, 0, st>>>(keys, n, pass * 4, hist, nblocks);
         k_radix_scan<<<1, 1024, 0, st>>>(hist, 16 * nblocks);
         k_radix_scatter<<<nblocks, 256, 0, st>>>(keys, vals, n, pass * 4, hist, nblocks, keys2, vals2);

@@ -106,11 +106,16 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
     if (blockIdx.x == 0 && threadIdx.x == 0) {                              // counters of the NEXT bounce (last used two bounces ago)
         ctrl[parity ^ 1u] = 0; ctrl[2u + 2u * (parity ^ 1u)] = 0; ctrl[3u + 2u * (parity ^ 1u)] = 0;
     }
-    uint32_t *qh_count = ctrl + 2u + 2u * parity, *qm_count = ctrl + 3u + 2u * parity;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    __shared__ uint32_t s_cnt[2][8], s_base[2];
-    const uint32_t n_round = (n + 255u) & ~255u;                            // whole blocks iterate together (block-level scan below)
-    // software pipelining: the ray of the NEXT grid-stride iteration is loaded before the current one is traversed
+    uint32_t *qh_count = ctrl + 2u + 2u * parity;                            // [hit count, miss count] adjacent: 8-byte aligned
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    unsigned long long *q_count = reinterpret_cast<unsigned long long *>(qh_count);   // {hit count (low), miss count (high)}: one 64-bit atomic
+    // Queue append without exposing the atomic's round trip (ncu round 1: returning per-warp atomics on hot addresses were
+    // 51 % of this kernel's stalls; a block-level scan fixed that but its barriers cost 9.5 stalled warps per issue on the
+    // 270 k-triangle scene): the reservation is ISSUED right after a ray is traced and only CONSUMED one grid-stride
+    // iteration later, after the next ray's traversal.
+    uint32_t p_i = 0, p_bh = 0, p_bm = 0; bool p_hit = false, p_act = false; unsigned long long p_base = 0ull;
     const uint32_t step = gridDim.x * blockDim.x;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
         bool hit = false;
         const uint32_t inext = i + step;
         float4 o4n = make_float4(0, 0, 0, 0), d4n = o4n;
-        if (inext < n) { o4n = ps.org_pdf[inext]; d4n = ps.dir_rng[inext]; }
+        if (inext < n) { o4n = ps.org_pdf[inext]; d4n = ps.dir_rng[inext]; }   // software pipelining of the state loads
         if (active) {
             const float3 rd = normalize(f3(d4));                            // SH/RayGen.slang:70
             HitRec h;
@@ -128,22 +133,21 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
             so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
         }
         o4 = o4n; d4 = d4n;
-        // queue append: warp ballots -> block scan in shared memory -> ONE atomic per block and queue (ncu round 1: the per-warp
-        // atomics on two addresses serialised in L2 and were 51 % of this kernel's stall samples)
-        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
-        if (lane == 0) { s_cnt[0][warp] = (uint32_t)__popc(bh); s_cnt[1][warp] = (uint32_t)__popc(bm); }
-        __syncthreads();
-        if (threadIdx.x < 2) {
-            uint32_t tot = 0;
-            #pragma unroll
-            for (int w = 0; w < 8; w++) { const uint32_t c = s_cnt[threadIdx.x][w]; s_cnt[threadIdx.x][w] = tot; tot += c; }
-            s_base[threadIdx.x] = tot ? atomicAdd(threadIdx.x == 0 ? qh_count : qm_count, tot) : 0u;
+        // flush the previous iteration's queue entries (its reservation has arrived by now)
+        {
+            const unsigned long long base = __shfl_sync(0xFFFFFFFFu, p_base, 0);
+            if (p_hit) q_hit[(uint32_t)base + __popc(p_bh & lt)] = p_i;
+            else if (p_act) q_miss[(uint32_t)(base >> 32) + __popc(p_bm & lt)] = p_i;
         }
-        __syncthreads();
-        const uint32_t lt = (1u << lane) - 1u;
-        if (hit) q_hit[s_base[0] + s_cnt[0][warp] + __popc(bh & lt)] = i;
-        else if (active) q_miss[s_base[1] + s_cnt[1][warp] + __popc(bm & lt)] = i;
-        __syncthreads();
+        // reserve space for this iteration's entries
+        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
+        if (lane == 0 && (bh | bm)) p_base = atomicAdd(q_count, ((unsigned long long)__popc(bm) << 32) | (unsigned long long)__popc(bh));
+        p_i = i; p_bh = bh; p_bm = bm; p_hit = hit; p_act = active;
+    }
+    {
+        const unsigned long long base = __shfl_sync(0xFFFFFFFFu, p_base, 0);
+        if (p_hit) q_hit[(uint32_t)base + __popc(p_bh & lt)] = p_i;
+        else if (p_act) q_miss[(uint32_t)(base >> 32) + __popc(p_bm & lt)] = p_i;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->extend_rays, (unsigned long long)n);
 }
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(256) k_resolve(DevConfig cfg, const DevDispatc
 template <bool SMEM>
 __global__ void __launch_bounds__(256) k_trace_rays(DevScene sc, uint32_t n, const float *__restrict__ org, const float *__restrict__ dir,
                                                      float tmin, float tmax, float *t_out, uint32_t *prim_out, uint32_t *inst_out,
-                                                     float *uv_out, int max_stack) {
+                                                     float *uv_out, int max_stack, uint32_t *stats) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
@@ -504,8 +508,12 @@ __global__ void __launch_bounds__(256) k_trace_rays(DevScene sc, uint32_t n, con
     else bv = global_bvh(sc);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         HitRec h;
-        const bool f = bvh_trace<SMEM, false>(bv, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]),
-                                              tmin, tmax, h, stack, (int)blockDim.x, max_stack);
+        uint32_t nn = 0, nt = 0;
+        const bool f = stats ? bvh_trace<SMEM, false, true>(bv, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]),
+                                                            tmin, tmax, h, stack, (int)blockDim.x, max_stack, &nn, &nt)
+                             : bvh_trace<SMEM, false>(bv, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]),
+                                                      tmin, tmax, h, stack, (int)blockDim.x, max_stack);
+        if (stats) { stats[2 * i] = nn; stats[2 * i + 1] = nt; }
         t_out[i] = f ? h.t : -1.0f;
         uint32_t pi = 0xFFFFFFFFu, ii = 0xFFFFFFFFu;
         if (f) { const float4 *tp = bv.tris + (size_t)h.slot * 3; ii = __float_as_uint(ld4<SMEM>(tp + 1).w); pi = __float_as_uint(ld4<SMEM>(tp + 2).w); }
@@ -591,12 +599,12 @@ void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch
     k_resolve<<<lc.grid_light, 256, 0, st>>>(cfg, disp, n_disp, P, sample_buf, image);
 }
 void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, const float *org, const float *dir, float tmin, float tmax,
-                       float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, cudaStream_t st) {
+                       float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, uint32_t *stats, cudaStream_t st) {
     set_attrs_once();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_trace_rays<true><<<lc.grid_trace, 256, sh, st>>>(sc, n, org, dir, tmin, tmax, t_out, prim_out, inst_out, uv_out, lc.max_stack);
-    else k_trace_rays<false><<<lc.grid_trace, 256, sh, st>>>(sc, n, org, dir, tmin, tmax, t_out, prim_out, inst_out, uv_out, lc.max_stack);
+    if (smem) k_trace_rays<true><<<lc.grid_trace, 256, sh, st>>>(sc, n, org, dir, tmin, tmax, t_out, prim_out, inst_out, uv_out, lc.max_stack, stats);
+    else k_trace_rays<false><<<lc.grid_trace, 256, sh, st>>>(sc, n, org, dir, tmin, tmax, t_out, prim_out, inst_out, uv_out, lc.max_stack, stats);
 }
 
 } // namespace b200pt
