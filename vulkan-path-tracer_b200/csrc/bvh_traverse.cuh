@@ -11,7 +11,7 @@
 namespace b200pt {
 
 struct BvhView { const float4 *nodes; const float4 *tris; int root; };
-struct HitRec { float t, u, v; uint32_t slot; };
+struct HitRec { float t, u, v; uint32_t slot; uint32_t gid; };   // slot: BvhTri (reference) slot; gid: triangle id in (instance, primitive) order
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+/sm_100a) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,7 +83,7 @@ __device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3
 template <bool SMEM, bool ANYHIT, bool COUNT = false>
 __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, float tmin, float tmax, HitRec &h,
                                           int *stack, int stride, int max_stack, uint32_t *n_nodes = nullptr, uint32_t *n_tris = nullptr) {
-    h.slot = 0xFFFFFFFFu; h.t = tmax; h.u = 0.0f; h.v = 0.0f;
+    h.slot = 0xFFFFFFFFu; h.gid = 0xFFFFFFFFu; h.t = tmax; h.u = 0.0f; h.v = 0.0f;
     uint32_t best_gid = 0xFFFFFFFFu;
     bool found = false;
     const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -127,7 +127,7 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
                 if (tri_test(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax, t, u, v)) {
                     const uint32_t gid = __float_as_uint(ta.w);
                     if (!found || t < h.t || (t == h.t && gid < best_gid)) {
-                        found = true; h.t = t; h.u = u; h.v = v; h.slot = slot; best_gid = gid;
+                        found = true; h.t = t; h.u = u; h.v = v; h.slot = slot; h.gid = gid; best_gid = gid;
                         if (ANYHIT) return true;
                     }
                 }

@@ -61,7 +61,7 @@ static_assert(sizeof(BvhNode) == 64, "BvhNode is 64 B");
 struct BvhTri { float4 a, b, c; };
 static_assert(sizeof(BvhTri) == 48, "BvhTri is 48 B");
 
-// 112-byte per-triangle shading record, same (Morton) order as BvhTri: one gather replaces the reference's
+// 112-byte per-triangle shading record, indexed by the global triangle id ((instance, primitive) order): one gather replaces the reference's
 // instance -> mesh -> index -> vertex descriptor chain (SH/ClosestHit.slang:46-57, SH/Surface.slang:33-41).
 //   r0 = P1.xyz | instance   r1 = P2.xyz | primitive   r2 = P3.xyz | material
 //   r3 = N1.xyz | uv1.x      r4 = N2.xyz | uv1.y       r5 = N3.xyz | uv2.x      r6 = uv2.y uv3.x uv3.y 0   (object space)

@@ -14,7 +14,15 @@
 
 namespace b200pt {
 
+#ifndef LBVH_LEAF_MAX
 #define LBVH_LEAF_MAX 4
+#endif
+#ifndef LBVH_SIZE_CLASS
+#define LBVH_SIZE_CLASS 0
+#endif
+#ifndef LBVH_SPLIT_MAX
+#define LBVH_SPLIT_MAX 16
+#endif
 #define LBVH_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
 // world-space transform without FMA contraction: bit-identical to the CPU oracle's plain fp32 arithmetic
@@ -37,7 +45,7 @@ __device__ __forceinline__ void atomic_max_f(float *addr, float v) {
 // ---- 1. world triangles + scene bounds -------------------------------------------------------
 __global__ void k_world_tris(const b200pt_vertex *__restrict__ verts, const uint32_t *__restrict__ indices, const DevMesh *__restrict__ meshes,
                              const DevInstance *__restrict__ inst, uint32_t n_inst, uint32_t n_tris,
-                             BvhTri *__restrict__ tmp, ShadeTri *__restrict__ tmp_shade, float *__restrict__ cent, float *__restrict__ bounds /*6*/) {
+                             BvhTri *__restrict__ tmp, ShadeTri *__restrict__ shade, float *__restrict__ cent, float *__restrict__ bounds /*6*/) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
     if (gid < n_tris) {
@@ -64,7 +72,7 @@ __global__ void k_world_tris(const b200pt_vertex *__restrict__ verts, const uint
         sh.r[4] = make_float4(B.Normal[0], B.Normal[1], B.Normal[2], A.TexCoord[1]);
         sh.r[5] = make_float4(C.Normal[0], C.Normal[1], C.Normal[2], B.TexCoord[0]);
         sh.r[6] = make_float4(B.TexCoord[1], C.TexCoord[0], C.TexCoord[1], 0.0f);
-        tmp_shade[gid] = sh;
+        shade[gid] = sh;
         lo[0] = fminf(v0.x, fminf(v1.x, v2.x)); hi[0] = fmaxf(v0.x, fmaxf(v1.x, v2.x));
         lo[1] = fminf(v0.y, fminf(v1.y, v2.y)); hi[1] = fmaxf(v0.y, fmaxf(v1.y, v2.y));
         lo[2] = fminf(v0.z, fminf(v1.z, v2.z)); hi[2] = fmaxf(v0.z, fmaxf(v1.z, v2.z));
@@ -74,6 +82,76 @@ __global__ void k_world_tris(const b200pt_vertex *__restrict__ verts, const uint
     for (int k = 0; k < 3; k++) {                                        // warp-reduce, then one atomic per warp
         for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_down_sync(0xFFFFFFFFu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_down_sync(0xFFFFFFFFu, hi[k], o)); }
         if ((threadIdx.x & 31) == 0) { atomic_min_f(&bounds[k], lo[k]); atomic_max_f(&bounds[3 + k], hi[k]); }
+    }
+}
+
+// ---- 1b. early split clipping: fat boxes of thin diagonal triangles are cut into up to 8 references ------------------
+// BreakfastRoom's chair legs are 86,880 slivers (aspect ratio 240 at p90) lying diagonally: every sliver's AABB is as big as
+// the whole tube, so a ray near a leg tested ~170 triangles (profiles/r01_bvh_stats.txt).  Each reference is the AABB of the
+// triangle clipped to one slab of its longest axis; all references of a triangle point to the same BvhTri.
+__global__ void k_split_count(const BvhTri *__restrict__ tmp, const float *__restrict__ aabb, const float *__restrict__ bounds, uint32_t n, uint32_t *__restrict__ ksplit) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *bb = aabb + (size_t)i * 6;
+    float e[3] = { bb[3] - bb[0], bb[4] - bb[1], bb[5] - bb[2] };
+    if (e[0] < e[1]) { float t = e[0]; e[0] = e[1]; e[1] = t; }
+    if (e[1] < e[2]) { float t = e[1]; e[1] = e[2]; e[2] = t; }
+    if (e[0] < e[1]) { float t = e[0]; e[0] = e[1]; e[1] = t; }
+    const float4 b = tmp[i].b, c = tmp[i].c;
+    const float cx = b.y * c.z - b.z * c.y, cy = b.z * c.x - b.x * c.z, cz = b.x * c.y - b.y * c.x;
+    const float area2 = sqrtf(cx * cx + cy * cy + cz * cz);
+    const float scene = fmaxf(bounds[3] - bounds[0], fmaxf(bounds[4] - bounds[1], bounds[5] - bounds[2]));
+    uint32_t k = 1;
+    const float ratio = (e[0] * e[1]) / fmaxf(area2, 1e-30f);
+    if (ratio > 8.0f && e[0] > scene * (1.0f / 1024.0f)) k = (uint32_t)fminf(fmaxf(ceilf(sqrtf(ratio)), 2.0f), (float)LBVH_SPLIT_MAX);
+    ksplit[i] = k;
+}
+__device__ __forceinline__ int clip_poly(const float3 *in, int n, int axis, float plane, bool keep_greater, float3 *out) {
+    int m = 0;
+    for (int a = 0; a < n; a++) {
+        const float3 P = in[a], Q = in[(a + 1) % n];
+        const float pa = axis == 0 ? P.x : (axis == 1 ? P.y : P.z), qa = axis == 0 ? Q.x : (axis == 1 ? Q.y : Q.z);
+        const bool pin = keep_greater ? pa >= plane : pa <= plane, qin = keep_greater ? qa >= plane : qa <= plane;
+        if (pin) out[m++] = P;
+        if (pin != qin) { const float t = (plane - pa) / (qa - pa); out[m++] = make_float3(P.x + t * (Q.x - P.x), P.y + t * (Q.y - P.y), P.z + t * (Q.z - P.z)); }
+    }
+    return m;
+}
+__global__ void k_make_refs(const BvhTri *__restrict__ tmp, const float *__restrict__ aabb, const uint32_t *__restrict__ ksplit, const uint32_t *__restrict__ ref_off,
+                            uint32_t n, float *__restrict__ ref_box, uint32_t *__restrict__ ref_tri) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *bb = aabb + (size_t)i * 6;
+    const uint32_t k = ksplit[i], r0 = ref_off[i];
+    if (k == 1) { for (int q = 0; q < 6; q++) ref_box[(size_t)r0 * 6 + q] = bb[q]; ref_tri[r0] = i; return; }
+    const float ex = bb[3] - bb[0], ey = bb[4] - bb[1], ez = bb[5] - bb[2];
+    const int axis = (ex >= ey && ex >= ez) ? 0 : (ey >= ez ? 1 : 2);
+    const float lo = bb[axis], w = (bb[3 + axis] - bb[axis]) / (float)k;
+    const BvhTri t = tmp[i];
+    const float3 v0 = make_float3(t.a.x, t.a.y, t.a.z), v1 = make_float3(t.a.x + t.b.x, t.a.y + t.b.y, t.a.z + t.b.z), v2 = make_float3(t.a.x + t.c.x, t.a.y + t.c.y, t.a.z + t.c.z);
+    for (uint32_t j = 0; j < k; j++) {
+        const float s0 = lo + w * (float)j, s1 = (j + 1 == k) ? bb[3 + axis] : lo + w * (float)(j + 1);
+        float3 p0[8], p1[8];                                             // a triangle clipped by two planes has <= 5 vertices
+        p0[0] = v0; p0[1] = v1; p0[2] = v2;
+        int m = clip_poly(p0, 3, axis, s0, true, p1);
+        m = clip_poly(p1, m, axis, s1, false, p0);
+        float blo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, bhi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
+        for (int a = 0; a < m; a++) {
+            blo[0] = fminf(blo[0], p0[a].x); blo[1] = fminf(blo[1], p0[a].y); blo[2] = fminf(blo[2], p0[a].z);
+            bhi[0] = fmaxf(bhi[0], p0[a].x); bhi[1] = fmaxf(bhi[1], p0[a].y); bhi[2] = fmaxf(bhi[2], p0[a].z);
+        }
+        float *o = ref_box + (size_t)(r0 + j) * 6;
+        for (int q = 0; q < 3; q++) {
+            float l = bb[q], h = bb[3 + q];
+            if (q == axis) { l = s0; h = s1; }
+            if (m >= 1) {                                                // clipped polygon bounds, padded, never beyond the triangle's own box
+                const float pad = 1e-5f * fmaxf(fabsf(blo[q]), fabsf(bhi[q])) + 1e-6f * (bb[3 + q] - bb[q]) + 1e-30f;
+                l = fmaxf(l, blo[q] - pad); h = fminf(h, bhi[q] + pad);
+                if (l > h) { l = bb[q]; h = bb[3 + q]; if (q == axis) { l = s0; h = s1; } }
+            }
+            o[q] = l; o[3 + q] = h;
+        }
+        ref_tri[r0 + j] = i;
     }
 }
 
@@ -107,7 +185,7 @@ __global__ void k_morton(const float *__restrict__ aabb, const float *__restrict
     // Size class in the top key bits: a wall-sized triangle sorted by its centroid alone inflates every ancestor box on its
     // root-to-leaf path (BreakfastRoom: p99 143 / max 324 node visits per camera ray).  Sorting by (size class, Morton code)
     // makes Karras split by size first, so large triangles live in their own small subtrees next to the root.
-    const unsigned long long cls = rel > 0.25f ? 3ull : (rel > 0.0625f ? 2ull : (rel > 0.015625f ? 1ull : 0ull));
+    const unsigned long long cls = !LBVH_SIZE_CLASS ? 0ull : (rel > 0.25f ? 3ull : (rel > 0.0625f ? 2ull : (rel > 0.015625f ? 1ull : 0ull)));
     keys[i] = (cls << 60) | (expand_bits21(q[0]) << 2) | (expand_bits21(q[1]) << 1) | expand_bits21(q[2]);
     vals[i] = i;
 }
@@ -167,13 +245,12 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const unsigned long long 
 }
 
 // ---- 4. reorder into Morton order ---------------------------------------------------------------
-__global__ void k_reorder(const BvhTri *__restrict__ tmp, const ShadeTri *__restrict__ tmp_shade, const float *__restrict__ aabb, const uint32_t *__restrict__ vals, uint32_t n,
-                          BvhTri *__restrict__ tris, ShadeTri *__restrict__ shade, float *__restrict__ leaf_box) {
+__global__ void k_reorder(const BvhTri *__restrict__ tmp, const uint32_t *__restrict__ ref_tri, const float *__restrict__ aabb, const uint32_t *__restrict__ vals, uint32_t n,
+                          BvhTri *__restrict__ tris, float *__restrict__ leaf_box) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t g = vals[i];
-    tris[i] = tmp[g];
-    shade[i] = tmp_shade[g];
+    tris[i] = tmp[ref_tri[g]];
     for (int k = 0; k < 6; k++) leaf_box[(size_t)i * 6 + k] = aabb[(size_t)g * 6 + k];
 }
 
@@ -268,46 +345,60 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
     out->shade = nullptr;
     out->nodes = nullptr; out->tris = nullptr; out->n_nodes = 0; out->n_tris = n_tris; out->root = 0; out->max_depth = 1; out->bytes = 0;
     if (n_tris == 0 || n_instances == 0) return (int)cudaErrorInvalidValue;
-    const uint32_t n = n_tris, n_int = n > 1 ? n - 1 : 0, n_nodes_alloc = n_int ? n_int : 1;
+    const uint32_t nt = n_tris, ntblocks = (nt + 255) / 256;
+
+    // ---- per-triangle stage: world-space triangles, shading records (final, gid order), boxes, scene bounds, split counts
+    ShadeTri *shade = nullptr; BvhTri *tmp = nullptr; float *aabb = nullptr, *bounds = nullptr; uint32_t *ksplit = nullptr, *ref_off = nullptr;
+    LBVH_CHECK(cudaMalloc(&shade, (size_t)nt * sizeof(ShadeTri)));
+    LBVH_CHECK(cudaMalloc(&tmp, (size_t)nt * sizeof(BvhTri)));
+    LBVH_CHECK(cudaMalloc(&aabb, (size_t)nt * 6 * sizeof(float)));
+    LBVH_CHECK(cudaMalloc(&bounds, 6 * sizeof(float)));
+    LBVH_CHECK(cudaMalloc(&ksplit, (size_t)nt * 4)); LBVH_CHECK(cudaMalloc(&ref_off, (size_t)nt * 4));
+    const float binit[6] = { 3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f };
+    LBVH_CHECK(cudaMemcpyAsync(bounds, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
+    k_world_tris<<<ntblocks, 256, 0, st>>>(d_verts, d_indices, d_meshes, d_instances, n_instances, nt, tmp, shade, aabb, bounds);
+    k_split_count<<<ntblocks, 256, 0, st>>>(tmp, aabb, bounds, nt, ksplit);
+    std::vector<uint32_t> hk(nt), hoff(nt);
+    LBVH_CHECK(cudaMemcpyAsync(hk.data(), ksplit, (size_t)nt * 4, cudaMemcpyDeviceToHost, st));
+    LBVH_CHECK(cudaStreamSynchronize(st));
+    uint64_t total = 0; for (uint32_t i = 0; i < nt; i++) { hoff[i] = (uint32_t)total; total += hk[i]; }
+    if (total >= (1ull << 28)) return (int)cudaErrorMemoryAllocation;       // leaf references keep the slot in 28 bits
+    LBVH_CHECK(cudaMemcpyAsync(ref_off, hoff.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, st));
+
+    // ---- per-reference stage
+    const uint32_t n = (uint32_t)total, n_int = n > 1 ? n - 1 : 0, n_nodes_alloc = n_int ? n_int : 1;
     const size_t node_bytes = (size_t)n_nodes_alloc * sizeof(BvhNode), tri_bytes = (size_t)n * sizeof(BvhTri);
     unsigned char *blob = nullptr;
     LBVH_CHECK(cudaMalloc(&blob, node_bytes + tri_bytes));
     LBVH_CHECK(cudaMemsetAsync(blob, 0, node_bytes, st));
     BvhNode *nodes = reinterpret_cast<BvhNode *>(blob);
     BvhTri *tris = reinterpret_cast<BvhTri *>(blob + node_bytes);
-
-    ShadeTri *tmp_shade = nullptr, *shade = nullptr;
-    LBVH_CHECK(cudaMalloc(&tmp_shade, (size_t)n * sizeof(ShadeTri))); LBVH_CHECK(cudaMalloc(&shade, (size_t)n * sizeof(ShadeTri)));
-    BvhTri *tmp = nullptr; float *aabb = nullptr, *leaf_box = nullptr, *node_box = nullptr, *bounds = nullptr;
+    float *ref_box = nullptr, *leaf_box = nullptr, *node_box = nullptr; uint32_t *ref_tri = nullptr;
     unsigned long long *keys = nullptr, *keys2 = nullptr; uint32_t *vals = nullptr, *vals2 = nullptr, *hist = nullptr;
     int *left = nullptr, *right = nullptr, *parent_int = nullptr, *parent_leaf = nullptr; unsigned int *flags = nullptr; int2 *range = nullptr;
-    LBVH_CHECK(cudaMalloc(&range, (size_t)(n > 1 ? n - 1 : 1) * sizeof(int2)));
     const uint32_t nblocks = (n + 255) / 256;
-    LBVH_CHECK(cudaMalloc(&tmp, tri_bytes));
-    LBVH_CHECK(cudaMalloc(&aabb, (size_t)n * 6 * sizeof(float)));
+    LBVH_CHECK(cudaMalloc(&ref_box, (size_t)n * 6 * sizeof(float))); LBVH_CHECK(cudaMalloc(&ref_tri, (size_t)n * 4));
     LBVH_CHECK(cudaMalloc(&leaf_box, (size_t)n * 6 * sizeof(float)));
     LBVH_CHECK(cudaMalloc(&node_box, (size_t)n_nodes_alloc * 6 * sizeof(float)));
-    LBVH_CHECK(cudaMalloc(&bounds, 6 * sizeof(float)));
     LBVH_CHECK(cudaMalloc(&keys, (size_t)n * 8)); LBVH_CHECK(cudaMalloc(&vals, (size_t)n * 4));
     LBVH_CHECK(cudaMalloc(&keys2, (size_t)n * 8)); LBVH_CHECK(cudaMalloc(&vals2, (size_t)n * 4));
     LBVH_CHECK(cudaMalloc(&hist, (size_t)16 * nblocks * 4));
+    LBVH_CHECK(cudaMalloc(&range, (size_t)n_nodes_alloc * sizeof(int2)));
     LBVH_CHECK(cudaMalloc(&left, (size_t)n_nodes_alloc * 4)); LBVH_CHECK(cudaMalloc(&right, (size_t)n_nodes_alloc * 4));
     LBVH_CHECK(cudaMalloc(&parent_int, (size_t)n_nodes_alloc * 4)); LBVH_CHECK(cudaMalloc(&parent_leaf, (size_t)n * 4));
     LBVH_CHECK(cudaMalloc(&flags, (size_t)n_nodes_alloc * 4));
     LBVH_CHECK(cudaMemsetAsync(flags, 0, (size_t)n_nodes_alloc * 4, st));
     LBVH_CHECK(cudaMemsetAsync(parent_leaf, 0xFF, (size_t)n * 4, st));
-    const float binit[6] = { 3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f };
-    LBVH_CHECK(cudaMemcpyAsync(bounds, binit, sizeof(binit), cudaMemcpyHostToDevice, st));
 
-    k_world_tris<<<nblocks, 256, 0, st>>>(d_verts, d_indices, d_meshes, d_instances, n_instances, n, tmp, tmp_shade, aabb, bounds);
-    k_morton<<<nblocks, 256, 0, st>>>(aabb, bounds, n, keys, vals);
-    for (int pass = 0; pass < 16; pass++) {                              // 63-bit keys, 4-bit digits
+    k_make_refs<<<ntblocks, 256, 0, st>>>(tmp, aabb, ksplit, ref_off, nt, ref_box, ref_tri);
+    k_morton<<<nblocks, 256, 0, st>>>(ref_box, bounds, n, keys, vals);
+    for (int pass = 0; pass < 16; pass++) {                              // 62-bit keys, 4-bit digits
         k_radix_hist<<<nblocks, 256, 0, st>>>(keys, n, pass * 4, hist, nblocks);
         k_radix_scan<<<1, 1024, 0, st>>>(hist, 16 * nblocks);
         k_radix_scatter<<<nblocks, 256, 0, st>>>(keys, vals, n, pass * 4, hist, nblocks, keys2, vals2);
         std::swap(keys, keys2); std::swap(vals, vals2);
     }
-    k_reorder<<<nblocks, 256, 0, st>>>(tmp, tmp_shade, aabb, vals, n, tris, shade, leaf_box);
+    k_reorder<<<nblocks, 256, 0, st>>>(tmp, ref_tri, ref_box, vals, n, tris, leaf_box);
     if (n_int) {
         k_karras<<<(n_int + 255) / 256, 256, 0, st>>>(keys, (int)n, left, right, parent_int, parent_leaf, range);
         k_refit<<<nblocks, 256, 0, st>>>((int)n, left, right, parent_int, parent_leaf, leaf_box, node_box, flags);
@@ -335,13 +426,13 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
             }
         }
     }
-    cudaFree(tmp_shade);
-    cudaFree(tmp); cudaFree(aabb); cudaFree(leaf_box); cudaFree(node_box); cudaFree(bounds);
+    cudaFree(tmp); cudaFree(aabb); cudaFree(bounds); cudaFree(ksplit); cudaFree(ref_off);
+    cudaFree(ref_box); cudaFree(ref_tri); cudaFree(leaf_box); cudaFree(node_box);
     cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(hist);
     cudaFree(left); cudaFree(right); cudaFree(parent_int); cudaFree(parent_leaf); cudaFree(flags); cudaFree(range);
 
     out->shade = shade;
-    out->nodes = nodes; out->tris = tris; out->n_nodes = n_nodes_alloc; out->n_tris = n;
+    out->nodes = nodes; out->tris = tris; out->n_nodes = n_nodes_alloc; out->n_tris = n;   // n_tris = BvhTri slots (references)
     out->root = root_ref;
     out->max_depth = max_depth;
     out->bytes = node_bytes + tri_bytes;

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
             const float3 rd = normalize(f3(d4));                            // SH/RayGen.slang:70
             HitRec h;
             hit = bvh_trace<SMEM, false>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
-            so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+            so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
         }
         o4 = o4n; d4 = d4n;
         // flush the previous iteration's queue entries (its reservation has arrived by now)
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         const float3 payOrigin = f3(o4), payDir = f3(d4);
         const float payPDF = o4.w;
         Rng rng; rng.s = __float_as_uint(d4.w);
-        const uint32_t slot = __float_as_uint(h4.w);
+        const uint32_t gid = __float_as_uint(h4.w);                            // global triangle id of the hit
 
         // The sky-NEE draws are the first draws of a hit outside a medium: take them now and put the alias-table load in flight.
         EnvPick ep;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         const float3 rd = normalize(payDir);                                // WorldRayDirection()
         float4 g[7];                                                        // one 112-B gather: vertices + ids of the hit triangle
         {
-            const float4 *gp = reinterpret_cast<const float4 *>(sc.shade_tris + slot);
+            const float4 *gp = reinterpret_cast<const float4 *>(sc.shade_tris + gid);
             #pragma unroll
             for (int q = 0; q < 7; q++) g[q] = __ldg(gp + q);
         }
