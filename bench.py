@@ -138,6 +138,41 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def run_post(args):
+    """configs[4]: 3840x2160 HDR accumulate + bloom (10 mips) + tonemap, post only; GB/s against the unfused 174.7 B/pixel model."""
+    import torch
+    import util
+    import vpt_b200 as pt
+    W, H = 3840, 2160
+    rng = np.random.default_rng(7)
+    hdr = np.ones((H, W, 4), np.float32); hdr[..., :3] = (np.exp(rng.normal(0, 1.5, (H, W, 3))) * 0.5).astype(np.float32)
+    for _ in range(64):
+        y, x = rng.integers(0, H - 5), rng.integers(0, W - 5); hdr[y:y + 5, x:x + 5, :3] = 500.0
+    T = pt.PathTracer(0)
+    T.set_scene(util.scene_dict("cornell_box")); T.resize(W, H)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); T.set_stream(stream.cuda_stream)
+    T.set_hdr(hdr)
+    iters = 100
+    for _ in range(max(args.warmup, 3)): T.post_process()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(iters): T.post_process()
+    ev1.record(stream); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / iters
+    mips = pt.bloom_mip_sizes(W, H)
+    px = [w * h for w, h in mips]
+    # unfused pass structure (SURVEY 8d): threshold R16+W16 per px0; down i: one compulsory read of mip i-1 + write of mip i;
+    # up i: read mip i + RMW mip i-1; tonemap: read hdr + bloom, write rgba8
+    bytes_model = 32 * px[0] + sum(16 * px[i - 1] + 16 * px[i] for i in range(1, len(px))) + sum(16 * px[i] + 32 * px[i - 1] for i in range(1, len(px))) + (16 + 16 + 4) * px[0]
+    peak, kind = measured_peak()
+    gbs = bytes_model / (ms * 1e-3) / 1e9
+    print(json.dumps({"metric": "post chain GB/s (3840x2160 bloom 10 mips + tonemap)", "value": gbs, "unit": "GB/s", "n_gpus": 1, "steps": iters, "warmup": max(args.warmup, 3),
+                      "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "post_4k", "image": [W, H], "mips": mips, "bytes_per_pixel_model": bytes_model / px[0]},
+                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "peak_kind": kind, "unit": "GB/s", "frac": gbs / peak, "traffic": None}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -146,11 +181,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=128)
     ap.add_argument("--frames-in-flight", type=int, default=0)
-    ap.add_argument("--workload", default="cornell_1080p_d8", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cornell_1080p_d8", choices=sorted(WORKLOADS) + ["post_4k"])
     ap.add_argument("--cpu-baseline-frames", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3: args.warmup = 3
+    if args.workload == "post_4k":
+        return run_post(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -264,8 +301,16 @@ def main():
     seg_per_path = dprof["extend_rays"] / max(dprof["paths"], 1)
     pipeline_bytes = ab["total"]
     step_ms_prof = sum(kms.values())
-    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "launches_per_step": int(launches_dom), "avg_launch_ms": kms[dom] / max(launches_dom, 1),
+    kname = {"shade": "k_shade_hit (+k_shade_miss)", "extend": "k_extend", "connect": "k_connect", "raygen": "k_raygen", "resolve": "k_resolve"}[dom]
+    traffic = None                                # DRAM bytes per launch of that kernel from the committed ncu --set full capture, if any
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(args.workload, {}).get(dom)
+        if ent: traffic = {"dram_bytes_per_launch": ent["dram_bytes_per_launch"], "algorithmic_bytes_of_that_launch": ent.get("algorithmic_bytes"), "source": ent["source"]}
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "launches_per_step": int(launches_dom), "avg_launch_ms": kms[dom] / max(launches_dom, 1),
                 "algorithmic_bytes_per_launch": ab[dom] / max(launches_dom, 1),
                 "kernel_ms_per_step": kms, "kernel_share": {k: (v / step_ms_prof if step_ms_prof else 0.0) for k, v in kms.items()},
                 "pipeline": {"algorithmic_bytes_per_step": pipeline_bytes, "segments_per_path": seg_per_path,
@@ -277,7 +322,7 @@ def main():
            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "scene": scene, "image": [W, H], "max_depth": depth, "spp_per_frame": 1, "frames_per_step": F,
                       "spp_total": F * args.steps, "partition": f"{BAND_ROWS}-row bands x {world} ranks", "env_map": "synthetic 4096x2048 RGBA32F (128 MiB) + 64 MiB alias table",
-                      "l2_policy": "working set > L2: env map 128 MiB + alias 64 MiB + wavefront state >= 600 MiB per wave (126 MB L2), no explicit flush",
+                      "l2_policy": "working set > L2: env map 128 MiB + alias 64 MiB + wavefront state of a 16.6 M-path wave ~5 GB (126 MB L2), no explicit flush",
                       "timing": "CUDA events on the launching stream, max over ranks", "wall_s": wall},
            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
            "gpu_launches": int(dc["kernel_launches"]), "clocks": clocks, "roofline": roofline,

@@ -65,6 +65,8 @@ def lib():
         L.orc_rng_floats.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_dielectric_fresnel.restype = C.c_float; L.orc_dielectric_fresnel.argtypes = [C.c_float, C.c_float]
         L.orc_aces_fitted.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_bake_reflect_texel.restype = C.c_float; L.orc_bake_reflect_texel.argtypes = [C.c_uint32] * 5
+        L.orc_bake_refract_texel.restype = C.c_float; L.orc_bake_refract_texel.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32]
         L.orc_build_env_alias.restype = C.c_float; L.orc_build_env_alias.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_camera_from_view.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.orc_default_config.argtypes = [C.POINTER(OrcConfig)]

@@ -652,6 +652,66 @@ static BSample sample_bsdf(const Mat *m, const OrcScene *sc, const OrcConfig *cf
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Energy-compensation LUT baker: SH/LookupReflect.slang:25-84, SH/LookupRefract.slang:23-102 (one texel).
+ * Not on the render path: it exists so the restated GGX sampler / EvaluateReflection / EvaluateRefraction / DielectricFresnel
+ * can be checked against the tables the REFERENCE's own shaders produced (Assets/LookupTables/[*].bin, 10^7 samples/texel).
+ * ---------------------------------------------------------------------------------------------- */
+float orc_bake_reflect_texel(uint32_t tx, uint32_t ty, uint32_t tz, uint32_t samples, uint32_t seed) {
+    const float SX = 64.0f, SY = 64.0f, SZ = 32.0f;                          /* PT/Application.cpp:41 */
+    Rng rng = { ty + tx * tx + seed };                                       /* LookupReflect.slang:34 */
+    float viewCosine = orc_clamp((float)tx / SX, 0.05f, 0.999f);
+    float roughness = orc_clamp((float)ty / SY, 0.0001f, 1.0f);
+    float anisotropy = (float)tz / SZ;
+    float aspect = sqrtf(1.0f - sqrtf(anisotropy) * 0.9f);
+    Mat m; memset(&m, 0, sizeof m);
+    m.Anisotropy = anisotropy; m.Roughness = roughness; m.BaseColor = v3s(1.0f);
+    m.Ax = fmaxf(0.0001f, roughness / aspect); m.Ay = fmaxf(0.0001f, roughness * aspect);
+    double total = 0.0;
+    for (uint32_t i = 0; i < samples; i++) {
+        float xy = sqrtf(1.0f - viewCosine * viewCosine);
+        float phi = rng_f(&rng) * ORC_2PI;
+        v3 V = v3normalize(V3(xy * cosf(phi), xy * sinf(phi), viewCosine));
+        v3 H = rng_ggx_vndf(&rng, V, m.Ax, m.Ay);
+        v3 L = v3normalize(v3reflect(v3neg(V), H));
+        if (L.z <= 0.0f) continue;
+        Eval e = eval_reflection(&m, V, L, v3s(1.0f));
+        if (e.PDF <= 0.0f) continue;
+        if (isnan(e.BxDF.x) || isinf(e.BxDF.x)) continue;
+        total += e.BxDF.x / e.PDF;
+    }
+    return (float)(total / samples);
+}
+float orc_bake_refract_texel(uint32_t tx, uint32_t ty, uint32_t tz, int above_surface, uint32_t samples, uint32_t seed) {
+    const float SX = 128.0f, SY = 128.0f, SZ = 32.0f;                        /* PT/Application.cpp:54,67 */
+    Rng rng = { ty + tx * tx + seed };
+    float vc = (float)tx / (SX - 1.0f);
+    float viewCosine = orc_clamp(vc * vc, 0.01f, 0.9999f);                   /* LookupRefract.slang:34: pow(.,2) */
+    float roughness = orc_clamp((float)ty / (SY - 1.0f), 0.01f, 1.0f);
+    float ior = 1.0f + orc_clamp((float)tz / (SZ - 1.0f), 0.0001f, 1.0f);
+    Mat m; memset(&m, 0, sizeof m);
+    m.Roughness = roughness; m.BaseColor = v3s(1.0f); m.IOR = ior; m.Ax = roughness; m.Ay = roughness;
+    m.Eta = above_surface ? (1.0f / ior) : ior;
+    double total = 0.0;
+    for (uint32_t i = 0; i < samples; i++) {
+        float xy = sqrtf(1.0f - viewCosine * viewCosine);
+        float phi = rng_f(&rng) * ORC_2PI;
+        v3 V = v3normalize(V3(xy * cosf(phi), xy * sinf(phi), viewCosine));
+        v3 H = rng_ggx_vndf(&rng, V, m.Ax, m.Ay);
+        float F = orc_dielectric_fresnel(fabsf(v3dot(V, H)), m.Eta);
+        float val = 0.0f;
+        if (rng_f(&rng) < F) {
+            v3 L = v3normalize(v3reflect(v3neg(V), H));
+            if (L.z > 0.0f) { Eval e = eval_reflection(&m, V, L, v3s(1.0f)); if (e.PDF > 0.0f && !isnan(e.BxDF.x) && !isinf(e.BxDF.x)) val += e.BxDF.x / e.PDF; }
+        } else {
+            v3 L = v3normalize(v3refract(v3neg(V), H, m.Eta));
+            if (L.z < 0.0f) { Eval e = eval_refraction(&m, V, L, v3s(1.0f)); if (e.PDF > 0.0f && !isnan(e.BxDF.x) && !isinf(e.BxDF.x)) val += e.BxDF.x / e.PDF; }
+        }
+        if (!isnan(val) && !isinf(val)) total += val;
+    }
+    return (float)(total / samples);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * NEE samplers
  * ---------------------------------------------------------------------------------------------- */
 /* SH/Sampler.slang:287-346 */

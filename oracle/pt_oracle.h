@@ -11,11 +11,15 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product (vulkan-path-tracer_b200/) never links or calls it.
  *
- * PARITY PIN STATUS: "parity unpinned" against a Vulkan run.  The reference ships no tests,
- * golden vectors or fixtures for this path and cannot be built here;
- * the oracle is pinned only by (a) analytic known-answer tests derived from the reference
- * source (furnace image == 1, PCG sequences, Fresnel/ACES fixed points, bloom mip sizes,
- * alias-table invariants) and (b) the shipped LUT/asset files.
+ * PARITY PIN STATUS: "parity unpinned" against a Vulkan RENDER.  The reference ships no tests,
+ * golden images or fixtures for this path and cannot be built here.
+ * What pins the oracle instead:
+ *   (a) reference-produced data: the shipped energy-compensation tables Assets/LookupTables/[*].bin were
+ *       baked by the reference's own shaders from the hot-path functions GGXSampleAnisotopic /
+ *       EvaluateReflection / EvaluateRefraction / DielectricFresnel / UniformFloat; the oracle's restated
+ *       baker (orc_bake_*_texel) reproduces them within Monte-Carlo noise (tests/test_oracle_kat.py);
+ *   (b) analytic known-answer tests derived from the reference source (furnace mode, PCG sequences,
+ *       Fresnel/ACES fixed points, bloom mip sizes, alias-table invariants, LUT ranges, fixture facts).
  */
 #ifndef PT_ORACLE_H
 #define PT_ORACLE_H
@@ -74,6 +78,10 @@ uint32_t orc_pcg_hash(uint32_t seed);                                  /* SH/Sam
 void     orc_rng_floats(uint32_t seed, uint32_t n, float *out);        /* SH/Sampler.slang:38-43 */
 float    orc_dielectric_fresnel(float cosI, float eta);                /* SH/Material.slang:434-449 */
 void     orc_aces_fitted(const float in[3], float out[3]);             /* SH/PostProcess/Tonemap.slang:20-55 */
+
+/* one texel of the reference's energy-compensation LUT baker (SH/LookupReflect.slang, SH/LookupRefract.slang) */
+float    orc_bake_reflect_texel(uint32_t tx, uint32_t ty, uint32_t tz, uint32_t samples, uint32_t seed);
+float    orc_bake_refract_texel(uint32_t tx, uint32_t ty, uint32_t tz, int above_surface, uint32_t samples, uint32_t seed);
 
 /* ---- host-side one-offs ---- */
 /* PT/PathTracer.cpp:1137-1332. rgba is modified in place (alpha <- pdf). Returns importance sum. */

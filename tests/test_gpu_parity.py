@@ -89,6 +89,26 @@ def test_converged_image_relative_l2(pt):
     assert T.samples_accumulated() == 64
 
 
+def test_full_size_config2_frame(pt):
+    """BASELINE.json configs[1] at its FULL size (1920x1080, depth 8), one frame at the matched seed: per-pixel agreement and the
+    size-independent invariants (alpha == 1, finite, equal work counters, equal image mean)."""
+    W, H = 1920, 1080
+    ref, got, cnt, T = _render_both(pt, "cornell_box", W, H, 1, MaxDepth=8)
+    assert np.isfinite(got).all() and np.all(got[..., 3] == 1.0)
+    a, b = ref[..., :3].astype(np.float64), got[..., :3].astype(np.float64)
+    close = np.all(np.abs(a - b) <= 1e-4 * np.maximum(np.abs(a), 1e-2), axis=-1)
+    assert close.mean() > 0.999, close.mean()
+    c = T.counters()
+    assert c["paths"] == W * H and abs(c["extend_rays"] - cnt["segments"]) <= 1e-3 * cnt["segments"]
+    assert abs(b.mean() - a.mean()) <= 2e-3 * a.mean()
+    # the same frame rendered as two half-height tiles is bit-identical (RNG keyed on global pixel coordinates)
+    halves = np.zeros_like(got)
+    for r in range(2):
+        Tr = util.product_tracer("cornell_box", W, H, MaxDepth=8); Tr.set_partition(r, 2, 16); Tr.path_trace(1, util.BASE_SEED)
+        halves[pt.partition_rows(H, r, 2, 16)] = Tr.get_hdr()
+    assert np.array_equal(halves, got)
+
+
 def test_glass_and_rough_conductor_config4(pt):
     """config 4: CornellBoxGlass + one wall set to Metallic 1 / Roughness 0.3 through set_material, depth 16."""
     name, W, H = "cornell_box_glass", 96, 96

@@ -82,6 +82,7 @@ struct DevScene {
     const DevEmissive *emissive;
     const float4 *env;
     const uint2 *alias;
+    const float2 *env_row_cos;     // per env-map row py: { cos(py*stepTheta), cos(py*stepTheta + stepTheta) } (SH/Sampler.slang:329-331), host-evaluated
     const float *lut_reflect, *lut_refract_out, *lut_refract_in;
     const BvhNode *nodes;
     const BvhTri *tris;

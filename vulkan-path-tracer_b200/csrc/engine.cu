@@ -40,7 +40,7 @@ Engine::~Engine() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
     free_scene(); free_wave(); free_post();
-    dfree(d_env_); dfree(d_alias_); for (auto &l : d_luts_) dfree(l);
+    dfree(d_env_); dfree(d_alias_); dfree(d_env_row_cos_); for (auto &l : d_luts_) dfree(l);
     dfree(d_image_); dfree(d_ctr_); dfree(d_counts_);
     if (h_count_) cudaFreeHost(h_count_);
     if (ev_[0]) cudaEventDestroy(ev_[0]); if (ev_[1]) cudaEventDestroy(ev_[1]);
@@ -215,7 +215,13 @@ void Engine::set_env_map(uint32_t w, uint32_t h, const float *rgba) {
     std::vector<float> px(rgba, rgba + (size_t)w * h * 4);
     std::vector<uint2> alias((size_t)w * h);
     build_env_alias(px.data(), w, h, alias.data());
-    dfree(d_env_); dfree(d_alias_);
+    dfree(d_env_); dfree(d_alias_); dfree(d_env_row_cos_);
+    {   // SH/Sampler.slang:329-331: stepTheta = M_PI / height; theta0 = py * stepTheta; cos(theta0), cos(theta0 + stepTheta)
+        std::vector<float2> rc(h); const float stepTheta = 3.1415926535897F / (float)h;
+        for (uint32_t y = 0; y < h; y++) { const float t0 = (float)y * stepTheta; rc[y] = make_float2(cosf(t0), cosf(t0 + stepTheta)); }
+        CK(cudaMalloc(&d_env_row_cos_, rc.size() * sizeof(float2))); CK(cudaMemcpy(d_env_row_cos_, rc.data(), rc.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        ds_.env_row_cos = d_env_row_cos_;
+    }
     CK(cudaMalloc(&d_env_, px.size() * 4)); CK(cudaMemcpy(d_env_, px.data(), px.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_alias_, alias.size() * sizeof(uint2))); CK(cudaMemcpy(d_alias_, alias.data(), alias.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     ds_.env = d_env_; ds_.alias = d_alias_; ds_.envW = w; ds_.envH = h;

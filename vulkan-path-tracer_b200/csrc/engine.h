@@ -90,7 +90,7 @@ private:
     DevMaterial *d_materials_ = nullptr; DevTexture *d_textures_ = nullptr; DevEmissive *d_emissive_ = nullptr; EmTri *d_em_tris_ = nullptr; uint32_t *d_em_tri_base_ = nullptr;
     std::vector<uint8_t *> d_texdata_;
     std::vector<DevInstance> h_instances_; std::vector<DevMesh> h_meshes_;
-    float4 *d_env_ = nullptr; uint2 *d_alias_ = nullptr; float *d_luts_[3] = { nullptr, nullptr, nullptr };
+    float4 *d_env_ = nullptr; uint2 *d_alias_ = nullptr; float2 *d_env_row_cos_ = nullptr; float *d_luts_[3] = { nullptr, nullptr, nullptr };
     LbvhResult bvh_{};
     LaunchCfg lc_{};
     uint32_t n_tris_ = 0, n_emissive_ = 0;

@@ -473,9 +473,8 @@ __device__ __forceinline__ void sample_env_finish(const DevScene &sc, const DevC
     float u = ((float)px + xy) / (float)width;
     float phi = u * (2.0f * PT_PI) - PT_PI;
     float sinPhi, cosPhi; pt_sincos(phi, &sinPhi, &cosPhi);
-    float stepTheta = PT_PI / (float)height;
-    float theta0 = (float)py * stepTheta;
-    float cosTheta = cosf(theta0) * (1.0f - xz) + cosf(theta0 + stepTheta) * xz;
+    const float2 rc = __ldg(sc.env_row_cos + py);                          // cos(theta0), cos(theta0 + stepTheta): 2 table reads instead of 2 cosf
+    float cosTheta = rc.x * (1.0f - xz) + rc.y * xz;
     float theta = acosf(cosTheta);
     float sinTheta = sinf(theta);
     float v = theta * PT_1_OVER_PI;

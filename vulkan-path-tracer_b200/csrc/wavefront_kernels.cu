@@ -107,14 +107,13 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
         ctrl[parity ^ 1u] = 0; ctrl[2u + 2u * (parity ^ 1u)] = 0; ctrl[3u + 2u * (parity ^ 1u)] = 0;
     }
     uint32_t *qh_count = ctrl + 2u + 2u * parity;                            // [hit count, miss count] adjacent: 8-byte aligned
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t n_round = (n + 31u) & ~31u;
+    __shared__ uint32_t s_cnt[2][8], s_base[2];
+    const uint32_t n_round = SMEM ? ((n + 255u) & ~255u) : ((n + 31u) & ~31u);   // SMEM variant: whole blocks iterate together
     unsigned long long *q_count = reinterpret_cast<unsigned long long *>(qh_count);   // {hit count (low), miss count (high)}: one 64-bit atomic
-    // Queue append without exposing the atomic's round trip (ncu round 1: returning per-warp atomics on hot addresses were
-    // 51 % of this kernel's stalls; a block-level scan fixed that but its barriers cost 9.5 stalled warps per issue on the
-    // 270 k-triangle scene): the reservation is ISSUED right after a ray is traced and only CONSUMED one grid-stride
-    // iteration later, after the next ray's traversal.
+    // Queue append (ncu round 1: returning per-warp atomics on two hot addresses were 51 % of this kernel's stalls): two strategies,
+    // see below.
     uint32_t p_i = 0, p_bh = 0, p_bm = 0; bool p_hit = false, p_act = false; unsigned long long p_base = 0ull;
     const uint32_t step = gridDim.x * blockDim.x;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,18 +132,37 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
             so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
         }
         o4 = o4n; d4 = d4n;
-        // flush the previous iteration's queue entries (its reservation has arrived by now)
-        {
-            const unsigned long long base = __shfl_sync(0xFFFFFFFFu, p_base, 0);
-            if (p_hit) q_hit[(uint32_t)base + __popc(p_bh & lt)] = p_i;
-            else if (p_act) q_miss[(uint32_t)(base >> 32) + __popc(p_bm & lt)] = p_i;
-        }
-        // reserve space for this iteration's entries
         const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
-        if (lane == 0 && (bh | bm)) p_base = atomicAdd(q_count, ((unsigned long long)__popc(bm) << 32) | (unsigned long long)__popc(bh));
-        p_i = i; p_bh = bh; p_bm = bm; p_hit = hit; p_act = active;
+        if (SMEM) {
+            // tiny scene (BVH in shared memory): every warp of the block takes about the same time, so a block-level scan with
+            // ONE atomic per block is cheapest (Cornell: 4.0 ms/step vs 4.6 ms with the deferred per-warp atomic)
+            if (lane == 0) { s_cnt[0][warp] = (uint32_t)__popc(bh); s_cnt[1][warp] = (uint32_t)__popc(bm); }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t th = 0, tm = 0;
+                #pragma unroll
+                for (int w = 0; w < 8; w++) { const uint32_t ch = s_cnt[0][w], cm = s_cnt[1][w]; s_cnt[0][w] = th; s_cnt[1][w] = tm; th += ch; tm += cm; }
+                const unsigned long long base = (th | tm) ? atomicAdd(q_count, ((unsigned long long)tm << 32) | (unsigned long long)th) : 0ull;
+                s_base[0] = (uint32_t)base; s_base[1] = (uint32_t)(base >> 32);
+            }
+            __syncthreads();
+            if (hit) q_hit[s_base[0] + s_cnt[0][warp] + __popc(bh & lt)] = i;
+            else if (active) q_miss[s_base[1] + s_cnt[1][warp] + __popc(bm & lt)] = i;
+            __syncthreads();
+        } else {
+            // big scene: traversal time varies a lot between warps, barriers would stall them on the slowest one (ncu: 9.5 warps
+            // stalled on the barrier per issue).  Per-warp reservation, ISSUED now and CONSUMED one iteration later, after the next
+            // ray's traversal, so the atomic's round trip is never exposed.
+            {
+                const unsigned long long base = __shfl_sync(0xFFFFFFFFu, p_base, 0);
+                if (p_hit) q_hit[(uint32_t)base + __popc(p_bh & lt)] = p_i;
+                else if (p_act) q_miss[(uint32_t)(base >> 32) + __popc(p_bm & lt)] = p_i;
+            }
+            if (lane == 0 && (bh | bm)) p_base = atomicAdd(q_count, ((unsigned long long)__popc(bm) << 32) | (unsigned long long)__popc(bh));
+            p_i = i; p_bh = bh; p_bm = bm; p_hit = hit; p_act = active;
+        }
     }
-    {
+    if (!SMEM) {
         const unsigned long long base = __shfl_sync(0xFFFFFFFFu, p_base, 0);
         if (p_hit) q_hit[(uint32_t)base + __popc(p_bh & lt)] = p_i;
         else if (p_act) q_miss[(uint32_t)(base >> 32) + __popc(p_bm & lt)] = p_i;
