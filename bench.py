@@ -173,6 +173,31 @@ def run_post(args):
                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "peak_kind": kind, "unit": "GB/s", "frac": gbs / peak, "traffic": None}}))
 
 
+def run_lut_bake(args):
+    """SURVEY 8f row 2: the energy-compensation LUT bake (LookupTableCalculator::CalculateTable, Application.cpp:35-72).  Pure ALU/MUFU
+    work (4 B written per texel): reported as BSDF samples/s; the oracle restatement is timed beside it on a few texels."""
+    import util
+    import vpt_b200 as pt
+    from oracle import orc
+    T = pt.PathTracer(0)
+    n_samp = 20000
+    out = {}
+    tot_s, tot_ms = 0, 0.0
+    for kind, name in ((0, "reflect_64x64x32"), (1, "refract_outside_128x128x32"), (2, "refract_inside_128x128x32")):
+        T.bake_lut(kind, 400, seed=1)                                   # warm-up
+        tab, ms = T.bake_lut(kind, n_samp, seed=7)
+        out[name] = {"ms": ms, "Gsamples_per_s": tab.size * n_samp / (ms * 1e-3) / 1e9}
+        tot_s += tab.size * n_samp; tot_ms += ms
+    L = orc.lib(); t0 = time.time(); cpu_s = 0
+    for i in range(16):
+        L.orc_bake_lut_texel(1, 128, 128, 32, 8 * i + 3, 5 * i + 20, 2 * i, 200000, 1); cpu_s += 200000
+    cpu = cpu_s / (time.time() - t0) / 1e9
+    print(json.dumps({"metric": "LUT bake Gsamples/s", "value": tot_s / (tot_ms * 1e-3) / 1e9, "unit": "Gsamples/s", "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": tot_ms,
+                      "higher_is_better": True, "dtype": "f32", "data": "synthetic", "config": {"workload": "lut_bake", "samples_per_texel": n_samp, "tables": out,
+                      "full_bake_estimate_s": 1e7 / n_samp * tot_ms * 1e-3},
+                      "cpu_baseline": {"value": cpu, "unit": "Gsamples/s", "cores": 1, "kind": "port", "sample": "16 texels x 200,000 samples of the refraction table, one core"}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,11 +206,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=128)
     ap.add_argument("--frames-in-flight", type=int, default=0)
-    ap.add_argument("--workload", default="cornell_1080p_d8", choices=sorted(WORKLOADS) + ["post_4k"])
+    ap.add_argument("--workload", default="cornell_1080p_d8", choices=sorted(WORKLOADS) + ["post_4k", "lut_bake"])
     ap.add_argument("--cpu-baseline-frames", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3: args.warmup = 3
+    if args.workload == "lut_bake":
+        return run_lut_bake(args)
     if args.workload == "post_4k":
         return run_post(args)
     if args.impl == "reference":

@@ -171,6 +171,20 @@ int32_t b200pt_trace_closest(b200pt_handle h, uint32_t n, const float *origins3,
                              float tmin, float tmax, float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out2);
 /* traversal cost of the same query: nodes_tris_out[2*i] = BVH nodes visited, [2*i+1] = triangles tested (measurement hook) */
 int32_t b200pt_trace_stats(b200pt_handle h, uint32_t n, const float *origins3, const float *directions3, float tmin, float tmax, uint32_t *nodes_tris_out);
+
+/* Energy-compensation lookup-table baker.
+ * Replaces LookupTableCalculator::CalculateTable(tableSize, sampleCount) (PathTracer/LookupTableCalculator.h:8,
+ * LookupTableCalculator.cpp:44-157) with its shaders LookupReflect.slang / LookupRefract.slang (ABOVE_SURFACE / BELOW_SURFACE).
+ * kind: 0 = reflection {64,64,32}, 1 = refraction hit-from-outside {128,128,32}, 2 = refraction hit-from-inside {128,128,32}
+ * (sizes as Application.cpp:41,54,67 passes them; any size is accepted).  out = sx*sy*sz floats, layout [z][y][x] as the .bin files.
+ * sample_count is rounded down to a multiple of 20 like the reference (20 samples per dispatch).  `seed` replaces the wall-clock
+ * term of the reference's per-dispatch seed, making a bake reproducible.  slices: 0 = auto; 1 = the reference's fp32 summation order.
+ * elapsed_ms (optional): device time of the bake kernels (CUDA events). */
+int32_t b200pt_bake_lut(b200pt_handle h, int32_t kind, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t sample_count, uint32_t seed,
+                        uint32_t slices, float *out, float *elapsed_ms);
+/* Application.cpp:35-72: write ReflectionLookup.bin / RefractionLookupHitFromOutside.bin / RefractionLookupHitFromInside.bin into dir
+ * (only the missing ones unless overwrite != 0); the reference uses sample_count = 10,000,000. */
+int32_t b200pt_bake_luts_to_dir(b200pt_handle h, const char *dir, uint32_t sample_count, uint32_t seed, int32_t overwrite);
 int32_t b200pt_scene_stats(b200pt_handle h, uint32_t *triangles, uint32_t *bvh_nodes, uint32_t *emissive_meshes, uint32_t *textures);
 
 /* ---- standalone codecs of the loader / image-output API (no GPU needed) ---- */

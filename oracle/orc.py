@@ -67,6 +67,7 @@ def lib():
         L.orc_aces_fitted.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_bake_reflect_texel.restype = C.c_float; L.orc_bake_reflect_texel.argtypes = [C.c_uint32] * 5
         L.orc_bake_refract_texel.restype = C.c_float; L.orc_bake_refract_texel.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32]
+        L.orc_bake_lut_texel.restype = C.c_float; L.orc_bake_lut_texel.argtypes = [C.c_int] + [C.c_uint32] * 8
         L.orc_build_env_alias.restype = C.c_float; L.orc_build_env_alias.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_camera_from_view.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.orc_default_config.argtypes = [C.POINTER(OrcConfig)]

@@ -711,6 +711,66 @@ float orc_bake_refract_texel(uint32_t tx, uint32_t ty, uint32_t tz, int above_su
     return (float)(total / samples);
 }
 
+/* The whole bake of one texel with the reference's DISPATCH STRUCTURE (PT/LookupTableCalculator.cpp:44-157):
+ * loopCount = sampleCount / 20 dispatches of 20 samples; dispatch i re-seeds the per-texel sampler with
+ * ty + tx*tx + Seed_i (LookupReflect.slang:30, LookupRefract.slang:32) and does uTable[index] += finalValue / 20 in fp32;
+ * the host divides by loopCount at the end (:151-154).  The reference derives Seed_i from the wall clock
+ * (PCGHash(i*2 + sampleCount + PCGHash(timeMillis)), :104-105) -- not reproducible -- so `seed` stands in for timeMillis.
+ * kind: 0 = LookupReflect, 1 = LookupRefract ABOVE_SURFACE, 2 = LookupRefract BELOW_SURFACE.  Used to check the CUDA baker bit-for-bit. */
+float orc_bake_lut_texel(int kind, uint32_t SXu, uint32_t SYu, uint32_t SZu, uint32_t tx, uint32_t ty, uint32_t tz, uint32_t sample_count, uint32_t seed) {
+    const float SX = (float)SXu, SY = (float)SYu, SZ = (float)SZu;
+    const uint32_t per = 20, loops = sample_count / per;
+    Mat m; memset(&m, 0, sizeof m); m.BaseColor = v3s(1.0f);
+    float viewCosine;
+    if (kind == 0) {
+        viewCosine = orc_clamp((float)tx / SX, 0.05f, 0.999f);
+        float roughness = orc_clamp((float)ty / SY, 0.0001f, 1.0f), anisotropy = (float)tz / SZ;
+        float aspect = sqrtf(1.0f - sqrtf(anisotropy) * 0.9f);
+        m.Anisotropy = anisotropy; m.Roughness = roughness;
+        m.Ax = fmaxf(0.0001f, roughness / aspect); m.Ay = fmaxf(0.0001f, roughness * aspect);
+    } else {
+        float vc = (float)tx / (SX - 1.0f);
+        viewCosine = orc_clamp(vc * vc, 0.01f, 0.9999f);
+        float roughness = orc_clamp((float)ty / (SY - 1.0f), 0.01f, 1.0f);
+        float ior = 1.0f + orc_clamp((float)tz / (SZ - 1.0f), 0.0001f, 1.0f);
+        m.Roughness = roughness; m.IOR = ior; m.Ax = roughness; m.Ay = roughness;
+        m.Eta = kind == 1 ? (1.0f / ior) : ior;
+    }
+    const uint32_t hseed = orc_pcg_hash(seed);
+    float table = 0.0f;
+    for (uint32_t i = 0; i < loops; i++) {
+        Rng rng = { ty + tx * tx + orc_pcg_hash(i * 2u + sample_count + hseed) };
+        float finalValue = 0.0f;
+        for (uint32_t k = 0; k < per; k++) {
+            float xy = sqrtf(1.0f - viewCosine * viewCosine);
+            float phi = rng_f(&rng) * ORC_2PI;
+            v3 V = v3normalize(V3(xy * cosf(phi), xy * sinf(phi), viewCosine));
+            v3 H = rng_ggx_vndf(&rng, V, m.Ax, m.Ay);
+            if (kind == 0) {
+                v3 L = v3normalize(v3reflect(v3neg(V), H));
+                if (L.z <= 0.0f) continue;
+                Eval e = eval_reflection(&m, V, L, v3s(1.0f));
+                if (e.PDF <= 0.0f) continue;
+                if (isnan(e.BxDF.x) || isinf(e.BxDF.x)) continue;
+                finalValue += e.BxDF.x / e.PDF;
+            } else {
+                float F = orc_dielectric_fresnel(fabsf(v3dot(V, H)), m.Eta);
+                float val = 0.0f;
+                if (rng_f(&rng) < F) {
+                    v3 L = v3normalize(v3reflect(v3neg(V), H));
+                    if (L.z > 0.0f) { Eval e = eval_reflection(&m, V, L, v3s(1.0f)); if (e.PDF > 0.0f && !isnan(e.BxDF.x) && !isinf(e.BxDF.x)) val += e.BxDF.x / e.PDF; }
+                } else {
+                    v3 L = v3normalize(v3refract(v3neg(V), H, m.Eta));
+                    if (L.z < 0.0f) { Eval e = eval_refraction(&m, V, L, v3s(1.0f)); if (e.PDF > 0.0f && !isnan(e.BxDF.x) && !isinf(e.BxDF.x)) val += e.BxDF.x / e.PDF; }
+                }
+                if (!isnan(val) && !isinf(val)) finalValue += val;
+            }
+        }
+        table += finalValue / (float)per;
+    }
+    return loops ? table / (float)loops : 0.0f;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * NEE samplers
  * ---------------------------------------------------------------------------------------------- */

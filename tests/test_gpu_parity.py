@@ -257,3 +257,59 @@ def test_set_scene_file_equals_set_scene_arrays(pt):
     cfg = T.get_config(); cfg.MaxDepth = 5; T.set_config(cfg); T.resize(64, 36); T.path_trace(2, 1)
     T2 = util.product_tracer("cornell_box", 64, 36, MaxDepth=5); T2.path_trace(2, 1)
     assert np.array_equal(T.get_hdr(), T2.get_hdr())
+
+
+# ---- the LUT baker (LookupTableCalculator + LookupReflect/LookupRefract) --------------------------------------
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_lut_baker_matches_oracle_per_texel(pt, kind):
+    """Same per-dispatch seeds, same 20-sample dispatches, same fp32 summation order (slices=1): the CUDA bake must reproduce the
+    oracle's restated bake texel by texel.  A sample within 2 ulp of the Fresnel coin flip or of a rejection test may take the
+    other branch (2-ulp division / CUDA libm vs glibc), shifting that texel by <= 1/samples; so: most texels to 1e-5, all to 3e-3."""
+    T = pt.PathTracer(0)
+    sx, sy, sz = (16, 16, 8) if kind == 0 else (24, 24, 8)
+    n_samp = 1000
+    tab, ms = T.bake_lut(kind, n_samp, seed=11, size=(sx, sy, sz), slices=1)
+    assert tab.shape == (sz, sy, sx) and np.isfinite(tab).all() and ms > 0
+    L = orc.lib(); rng = np.random.default_rng(kind)
+    d = []
+    for _ in range(96):
+        x, y, z = int(rng.integers(0, sx)), int(rng.integers(0, sy)), int(rng.integers(0, sz))
+        d.append(abs(L.orc_bake_lut_texel(kind, sx, sy, sz, x, y, z, n_samp, 11) - tab[z, y, x]))
+    d = np.array(d)
+    assert (d < 1e-5).mean() > 0.8 and d.max() < 3e-3, (np.sort(d)[-5:], (d < 1e-5).mean())
+    # slicing the dispatch range only re-associates the fp32 sum
+    tab4, _ = T.bake_lut(kind, n_samp, seed=11, size=(sx, sy, sz), slices=5)
+    assert np.abs(tab4 - tab).max() < 1e-5
+    # a different seed gives a different (but statistically equal) table
+    tab2, _ = T.bake_lut(kind, n_samp, seed=12, size=(sx, sy, sz), slices=1)
+    assert not np.array_equal(tab2, tab) and abs(float(tab2.mean() - tab.mean())) < 5e-3
+
+
+def test_lut_baker_regenerates_the_shipped_reference_tables(pt):
+    """The CUDA BSDF sampling/evaluation primitives against REFERENCE-PRODUCED data: re-bake the three shipped tables at full size
+    (20,000 samples per texel instead of 10^7) and compare with Assets/LookupTables/*.bin (tests/golden/luts.npz).  Per-texel noise
+    is ~2e-3; the mean difference over the bulk of each table must vanish.  The near-mirror grazing corner where the shipped tables
+    deviate from any IEEE re-bake (see tests/test_oracle_kat.py) is reported but only loosely bounded."""
+    T = pt.PathTracer(0)
+    refl, rout, rin = util.luts()
+    for kind, ship, ylo in ((0, refl, 6), (1, rout, 12), (2, rin, 12)):
+        tab, ms = T.bake_lut(kind, 20000, seed=3)
+        assert tab.shape == ship.shape
+        diff = tab - ship
+        bulk = diff[:, ylo:, :]
+        assert abs(float(bulk.mean())) < 4e-4, (kind, bulk.mean())
+        assert float(np.sqrt((bulk ** 2).mean())) < 6e-3, (kind, np.sqrt((bulk ** 2).mean()))
+        assert float(np.abs(bulk).max()) < 6e-2, (kind, np.abs(bulk).max())
+        assert float(np.abs(diff).max()) < 0.12, (kind, np.abs(diff).max())
+
+
+def test_bake_luts_to_dir_writes_reference_file_layout(pt, tmp_path):
+    T = pt.PathTracer(0)
+    T.bake_luts_to_dir(tmp_path, sample_count=200, seed=1)
+    sizes = {"ReflectionLookup.bin": 524288, "RefractionLookupHitFromOutside.bin": 2097152, "RefractionLookupHitFromInside.bin": 2097152}
+    for name, nbytes in sizes.items():
+        assert (tmp_path / name).stat().st_size == nbytes                      # SURVEY 8c: verified sizes of the shipped files
+    before = (tmp_path / "ReflectionLookup.bin").read_bytes()
+    T.bake_luts_to_dir(tmp_path, sample_count=400, seed=2)                       # existing files are kept (Application.cpp:35)
+    assert (tmp_path / "ReflectionLookup.bin").read_bytes() == before
+    T2 = pt.PathTracer(0); T2.set_luts_dir(str(tmp_path))                        # and load back through the normal path

@@ -121,6 +121,8 @@ def lib():
             "b200pt_trace_closest": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
             "b200pt_scene_stats": [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4,
             "b200pt_trace_stats": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p],
+            "b200pt_bake_lut": [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p],
+            "b200pt_bake_luts_to_dir": [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int32],
             "b200pt_decode_image_file": [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)],
             "b200pt_decode_hdr_file": [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)],
             "b200pt_write_png": [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p],
@@ -376,6 +378,18 @@ class PathTracer:
         t = np.zeros(n, np.float32); prim = np.zeros(n, np.uint32); inst = np.zeros(n, np.uint32); uv = np.zeros((n, 2), np.float32)
         self._ck(self.L.b200pt_trace_closest(self.h, n, _p(org), _p(dirs), C.c_float(tmin), C.c_float(tmax), _p(t), _p(prim), _p(inst), _p(uv)))
         return t, prim, inst, uv
+
+    LUT_SIZES = {0: (64, 64, 32), 1: (128, 128, 32), 2: (128, 128, 32)}   # Application.cpp:41,54,67
+
+    def bake_lut(self, kind, sample_count, seed=0, size=None, slices=0):
+        """LookupTableCalculator::CalculateTable on the GPU -> (table[z][y][x] float32, device milliseconds)."""
+        sx, sy, sz = size or self.LUT_SIZES[kind]
+        out = np.zeros((sz, sy, sx), np.float32); ms = C.c_float(0)
+        self._ck(self.L.b200pt_bake_lut(self.h, kind, sx, sy, sz, sample_count, seed, slices, _p(out), C.byref(ms)))
+        return out, ms.value
+
+    def bake_luts_to_dir(self, path, sample_count=10_000_000, seed=0, overwrite=False):
+        self._ck(self.L.b200pt_bake_luts_to_dir(self.h, str(path).encode(), sample_count, seed, int(overwrite)))
 
     def trace_stats(self, org, dirs, tmin, tmax):
         org = np.ascontiguousarray(org, np.float32); dirs = np.ascontiguousarray(dirs, np.float32); n = len(org)

@@ -155,6 +155,28 @@ int32_t b200pt_trace_stats(b200pt_handle h, uint32_t n, const float *o, const fl
     if (n && (!o || !d || !nodes_tris)) return B200PT_ERR_WRONG_ARGUMENTS;
     return guard(h, [&](Engine &e) { std::vector<float> t(n), uv(2 * (size_t)n); std::vector<uint32_t> p(n), i(n); e.trace_closest(n, o, d, tmin, tmax, t.data(), p.data(), i.data(), uv.data(), nodes_tris); });
 }
+int32_t b200pt_bake_lut(b200pt_handle h, int32_t kind, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t sample_count, uint32_t seed, uint32_t slices, float *out, float *elapsed_ms) {
+    if (!out || kind < 0 || kind > 2 || !sx || !sy || !sz) return B200PT_ERR_WRONG_ARGUMENTS;
+    return guard(h, [&](Engine &e) { e.bake_lut(kind, sx, sy, sz, sample_count, seed, slices, out, elapsed_ms); });
+}
+// Application.cpp:35-72: bake the three tables with the reference's sizes and write the .bin files that are missing in `dir`.
+int32_t b200pt_bake_luts_to_dir(b200pt_handle h, const char *dir, uint32_t sample_count, uint32_t seed, int32_t overwrite) {
+    if (!dir) return B200PT_ERR_WRONG_ARGUMENTS;
+    static const struct { const char *name; int kind; uint32_t sx, sy, sz; } tabs[3] = {
+        { "ReflectionLookup.bin", 0, 64, 64, 32 }, { "RefractionLookupHitFromOutside.bin", 1, 128, 128, 32 }, { "RefractionLookupHitFromInside.bin", 2, 128, 128, 32 } };
+    for (const auto &t : tabs) {
+        const std::string path = std::string(dir) + "/" + t.name;
+        if (!overwrite) { FILE *f = fopen(path.c_str(), "rb"); if (f) { fclose(f); continue; } }
+        std::vector<float> data((size_t)t.sx * t.sy * t.sz);
+        int32_t r = guard(h, [&](Engine &e) { e.bake_lut(t.kind, t.sx, t.sy, t.sz, sample_count, seed, 0, data.data(), nullptr); });
+        if (r != B200PT_OK) return r;
+        FILE *f = fopen(path.c_str(), "wb");
+        if (!f) { g_err = "cannot write " + path; return B200PT_ERR_INIT_FAILED; }
+        const size_t w = fwrite(data.data(), sizeof(float), data.size(), f); fclose(f);
+        if (w != data.size()) { g_err = "short write " + path; return B200PT_ERR_UNKNOWN; }
+    }
+    return B200PT_OK;
+}
 int32_t b200pt_scene_stats(b200pt_handle h, uint32_t *a, uint32_t *b, uint32_t *c, uint32_t *d) { return guard(h, [&](Engine &e) { e.scene_stats(a, b, c, d); }); }
 
 // ---- standalone codecs ----

@@ -484,6 +484,33 @@ void Engine::trace_closest(uint32_t n, const float *org, const float *dir, float
     cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_uv); cudaFree(d_p); cudaFree(d_i); if (d_st) cudaFree(d_st);
     CK(e); CK(cudaGetLastError());
 }
+// LookupTableCalculator::CalculateTable (PT/LookupTableCalculator.cpp:44-157) on this engine's device and stream.
+// slices == 0 picks enough dispatch slices to give every SM ~2048 resident threads.
+void Engine::bake_lut(int kind, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t sample_count, uint32_t seed, uint32_t slices, float *out_host, float *elapsed_ms) {
+    CK(cudaSetDevice(device_));
+    if (kind < 0 || kind > 2 || !sx || !sy || !sz || !out_host || (uint64_t)sx * sy * sz > (1ull << 28)) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "bake_lut: bad arguments" };
+    const size_t n = (size_t)sx * sy * sz;
+    if (!slices) {
+        cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device_));
+        const size_t want = (size_t)prop.multiProcessorCount * 2048;
+        slices = (uint32_t)std::max<size_t>(1, (want + n - 1) / n);
+    }
+    slices = std::min<uint32_t>(slices, 4096u);
+    float *d_part = nullptr, *d_tab = nullptr;
+    CK(cudaMalloc(&d_part, n * slices * sizeof(float)));
+    if (cudaMalloc(&d_tab, n * sizeof(float)) != cudaSuccess) { cudaFree(d_part); throw CudaError{ B200PT_ERR_OUT_OF_MEMORY, "bake_lut: out of device memory" }; }
+    cudaEvent_t e0 = nullptr, e1 = nullptr; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, stream_);
+    launch_bake_lut(kind, d_part, d_tab, sx, sy, sz, sample_count, seed, slices, stream_);
+    cudaEventRecord(e1, stream_);
+    cudaError_t e = cudaMemcpyAsync(out_host, d_tab, n * sizeof(float), cudaMemcpyDeviceToHost, stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0.0f; if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    if (elapsed_ms) *elapsed_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_part); cudaFree(d_tab);
+    CK(e);
+}
 void Engine::scene_stats(uint32_t *tris, uint32_t *nodes, uint32_t *emissive, uint32_t *textures) const {
     if (tris) *tris = n_tris_; if (nodes) *nodes = bvh_.n_nodes; if (emissive) *emissive = n_emissive_; if (textures) *textures = (uint32_t)scene_.textures.size();
 }
