@@ -80,9 +80,13 @@ __device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3
 }
 
 // stack: shared-memory column of this thread, entries at stack[k * stride]
-template <bool SMEM, bool ANYHIT, bool COUNT = false>
+// TARGET (with ANYHIT): "is anything in front of triangle target_gid, which the ray hits at tmax?"  A triangle occludes when
+// t < tmax, or t == tmax and its id is lower than the target's (the tie rule of the closest-hit query); the target itself never does.
+template <bool SMEM, bool ANYHIT, bool COUNT = false, bool TARGET = false>
 __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, float tmin, float tmax, HitRec &h,
-                                          int *stack, int stride, int max_stack, uint32_t *n_nodes = nullptr, uint32_t *n_tris = nullptr) {
+                                          int *stack, int stride, int max_stack, uint32_t *n_nodes = nullptr, uint32_t *n_tris = nullptr,
+                                          uint32_t target_gid = 0xFFFFFFFFu) {
+    const float tmax_test = TARGET ? __uint_as_float(__float_as_uint(tmax) + 1u) : tmax;   // TARGET: admit t == tmax (tmax > 0)
     h.slot = 0xFFFFFFFFu; h.gid = 0xFFFFFFFFu; h.t = tmax; h.u = 0.0f; h.v = 0.0f;
     uint32_t best_gid = 0xFFFFFFFFu;
     bool found = false;
@@ -124,8 +128,9 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
                 const float4 *tp = b.tris + (size_t)slot * 3;
                 const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
                 float t, u, v;
-                if (tri_test(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax, t, u, v)) {
+                if (tri_test(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax_test, t, u, v)) {
                     const uint32_t gid = __float_as_uint(ta.w);
+                    if (TARGET && !(t < tmax || gid < target_gid)) continue;
                     if (!found || t < h.t || (t == h.t && gid < best_gid)) {
                         found = true; h.t = t; h.u = u; h.v = v; h.slot = slot; h.gid = gid; best_gid = gid;
                         if (ANYHIT) return true;

@@ -69,7 +69,7 @@ struct ShadeTri { float4 r[7]; };
 static_assert(sizeof(ShadeTri) == 112, "ShadeTri is 112 B");
 
 // 64-byte emissive triangle: world-space corners (EmissiveMeshEntry::Transform applied, SH/Sampler.slang:389-391) + uvs
-//   r0 = p0.xyz | uv0.x   r1 = p1.xyz | uv0.y   r2 = p2.xyz | uv1.x   r3 = uv1.y uv2.x uv2.y 0
+//   r0 = p0.xyz | uv0.x   r1 = p1.xyz | uv0.y   r2 = p2.xyz | uv1.x   r3 = uv1.y uv2.x uv2.y | global triangle id (bits)
 struct EmTri { float4 r[4]; };
 
 struct DevScene {
@@ -84,6 +84,7 @@ struct DevScene {
     const uint2 *alias;
     const float2 *env_row_cos;     // per env-map row py: { cos(py*stepTheta), cos(py*stepTheta + stepTheta) } (SH/Sampler.slang:329-331), host-evaluated
     const float *lut_reflect, *lut_refract_out, *lut_refract_in;
+    const uint32_t *tri_slot;      // global triangle id -> one of its BvhTri slots (light-ray visibility test in k_connect)
     const BvhNode *nodes;
     const BvhTri *tris;
     const ShadeTri *shade_tris;

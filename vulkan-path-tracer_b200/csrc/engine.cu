@@ -123,7 +123,7 @@ void Engine::upload_scene() {
     int r = lbvh_build(d_verts_, d_indices_, d_meshes_, d_instances_, h_instances_.data(), h_meshes_.data(), (uint32_t)h_instances_.size(), n_tris_, &bvh_, stream_);
     if (r != 0) throw CudaError{ B200PT_ERR_CUDA, std::string("lbvh_build failed: ") + cudaGetErrorString((cudaError_t)r) };
     ds_.verts = d_verts_; ds_.indices = d_indices_; ds_.meshes = d_meshes_; ds_.instances = d_instances_; ds_.materials = d_materials_;
-    ds_.textures = d_textures_; ds_.emissive = d_emissive_; ds_.nodes = bvh_.nodes; ds_.tris = bvh_.tris; ds_.shade_tris = bvh_.shade;
+    ds_.textures = d_textures_; ds_.emissive = d_emissive_; ds_.nodes = bvh_.nodes; ds_.tris = bvh_.tris; ds_.shade_tris = bvh_.shade; ds_.tri_slot = bvh_.tri_slot;
     ds_.n_tris = bvh_.n_tris; ds_.n_nodes = bvh_.n_nodes; ds_.root = bvh_.root; ds_.bvh_bytes = bvh_.bytes <= 0xFFFFFFFFull ? (uint32_t)bvh_.bytes : 0;
     int q = query_launch_cfg(ds_, bvh_.max_depth, &lc_);
     if (q != 0) throw CudaError{ B200PT_ERR_CUDA, "query_launch_cfg failed" };
@@ -181,7 +181,9 @@ void Engine::rebuild_emissive() {
             const float3 p0 = xf(A), p1 = xf(B), p2 = xf(C);
             EmTri r;
             r.r[0] = make_float4(p0.x, p0.y, p0.z, A.TexCoord[0]); r.r[1] = make_float4(p1.x, p1.y, p1.z, A.TexCoord[1]);
-            r.r[2] = make_float4(p2.x, p2.y, p2.z, B.TexCoord[0]); r.r[3] = make_float4(B.TexCoord[1], C.TexCoord[0], C.TexCoord[1], 0.0f);
+            r.r[2] = make_float4(p2.x, p2.y, p2.z, B.TexCoord[0]);
+            const uint32_t gid = h_instances_[e.instance].tri_base + t; float gidf; memcpy(&gidf, &gid, 4);
+            r.r[3] = make_float4(B.TexCoord[1], C.TexCoord[0], C.TexCoord[1], gidf);
             et.push_back(r);
         }
     }

@@ -246,11 +246,13 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const unsigned long long 
 
 // ---- 4. reorder into Morton order ---------------------------------------------------------------
 __global__ void k_reorder(const BvhTri *__restrict__ tmp, const uint32_t *__restrict__ ref_tri, const float *__restrict__ aabb, const uint32_t *__restrict__ vals, uint32_t n,
-                          BvhTri *__restrict__ tris, float *__restrict__ leaf_box) {
+                          BvhTri *__restrict__ tris, float *__restrict__ leaf_box, uint32_t *__restrict__ tri_slot) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t g = vals[i];
-    tris[i] = tmp[ref_tri[g]];
+    const BvhTri t = tmp[ref_tri[g]];
+    tris[i] = t;
+    tri_slot[__float_as_uint(t.a.w)] = i;       // any one of the triangle's reference slots (all hold the same 48 B); benign race
     for (int k = 0; k < 6; k++) leaf_box[(size_t)i * 6 + k] = aabb[(size_t)g * 6 + k];
 }
 
@@ -336,13 +338,14 @@ __global__ void k_emit(int n_int, const int *__restrict__ left, const int *__res
 void lbvh_free(LbvhResult *r) {
     if (r->nodes) cudaFree(r->nodes);
     if (r->shade) cudaFree(r->shade);
-    r->shade = nullptr;
+    if (r->tri_slot) cudaFree(r->tri_slot);
+    r->shade = nullptr; r->tri_slot = nullptr;
     r->nodes = nullptr; r->tris = nullptr; r->n_nodes = r->n_tris = 0; r->bytes = 0;
 }
 
 int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const DevMesh *d_meshes, const DevInstance *d_instances,
                const DevInstance *, const DevMesh *, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st) {
-    out->shade = nullptr;
+    out->shade = nullptr; out->tri_slot = nullptr;
     out->nodes = nullptr; out->tris = nullptr; out->n_nodes = 0; out->n_tris = n_tris; out->root = 0; out->max_depth = 1; out->bytes = 0;
     if (n_tris == 0 || n_instances == 0) return (int)cudaErrorInvalidValue;
     const uint32_t nt = n_tris, ntblocks = (nt + 255) / 256;
@@ -350,6 +353,8 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
     // ---- per-triangle stage: world-space triangles, shading records (final, gid order), boxes, scene bounds, split counts
     ShadeTri *shade = nullptr; BvhTri *tmp = nullptr; float *aabb = nullptr, *bounds = nullptr; uint32_t *ksplit = nullptr, *ref_off = nullptr;
     LBVH_CHECK(cudaMalloc(&shade, (size_t)nt * sizeof(ShadeTri)));
+    uint32_t *tri_slot = nullptr;
+    LBVH_CHECK(cudaMalloc(&tri_slot, (size_t)nt * sizeof(uint32_t)));
     LBVH_CHECK(cudaMalloc(&tmp, (size_t)nt * sizeof(BvhTri)));
     LBVH_CHECK(cudaMalloc(&aabb, (size_t)nt * 6 * sizeof(float)));
     LBVH_CHECK(cudaMalloc(&bounds, 6 * sizeof(float)));
@@ -398,7 +403,7 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
         k_radix_scatter<<<nblocks, 256, 0, st>>>(keys, vals, n, pass * 4, hist, nblocks, keys2, vals2);
         std::swap(keys, keys2); std::swap(vals, vals2);
     }
-    k_reorder<<<nblocks, 256, 0, st>>>(tmp, ref_tri, ref_box, vals, n, tris, leaf_box);
+    k_reorder<<<nblocks, 256, 0, st>>>(tmp, ref_tri, ref_box, vals, n, tris, leaf_box, tri_slot);
     if (n_int) {
         k_karras<<<(n_int + 255) / 256, 256, 0, st>>>(keys, (int)n, left, right, parent_int, parent_leaf, range);
         k_refit<<<nblocks, 256, 0, st>>>((int)n, left, right, parent_int, parent_leaf, leaf_box, node_box, flags);
@@ -431,7 +436,7 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
     cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(hist);
     cudaFree(left); cudaFree(right); cudaFree(parent_int); cudaFree(parent_leaf); cudaFree(flags); cudaFree(range);
 
-    out->shade = shade;
+    out->shade = shade; out->tri_slot = tri_slot;
     out->nodes = nodes; out->tris = tris; out->n_nodes = n_nodes_alloc; out->n_tris = n;   // n_tris = BvhTri slots (references)
     out->root = root_ref;
     out->max_depth = max_depth;

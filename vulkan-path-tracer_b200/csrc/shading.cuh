@@ -54,7 +54,8 @@ __device__ __forceinline__ float3 rotate3_cs(float3 v, float3 axis, float c, flo
 }
 // libm calls with large inlined slow paths are funnelled through single out-of-line copies: k_shade's code must stay
 // within the instruction caches (ncu round 1: 189 KB of SASS, stall_no_instruction 20 warps/issue).
-static __device__ __noinline__ void pt_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+static __device__ __noinline__ float2 pt_sincos2(float x) { float s, c; sincosf(x, &s, &c); return make_float2(s, c); }   // by value: no stack round trip
+__device__ __forceinline__ void pt_sincos(float x, float *s, float *c) { const float2 r = pt_sincos2(x); *s = r.x; *c = r.y; }
 static __device__ __noinline__ float pt_pow(float x, float y) { return powf(x, y); }
 
 // ---------------------------------------------------------------- RNG  SH/Sampler.slang:4-9,21-43
@@ -110,7 +111,10 @@ __device__ __forceinline__ float3 sample_henyey_greenstein(Rng &r, float3 incide
 
 // ---------------------------------------------------------------- software texture units
 __device__ __forceinline__ float tex_mix(float p, float q, float w) { return p + w * (q - p); }
-__device__ __forceinline__ int wrap_repeat(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+__device__ __forceinline__ int wrap_repeat(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;        // interior texel: skip the integer division (same result)
+    int m = i % n; return m < 0 ? m + n : m;
+}
 __device__ __forceinline__ int clampi(int i, int lo, int hi) { return i < lo ? lo : (i > hi ? hi : i); }
 
 // RGBA8 / R8 UNORM, bilinear, REPEAT (PT/PathTracer.cpp:84-91). R8 -> (r,0,0,1).
@@ -486,18 +490,18 @@ __device__ __forceinline__ void sample_env_finish(const DevScene &sc, const DevC
     val.x *= cfg.EnvironmentIntensity; val.y *= cfg.EnvironmentIntensity; val.z *= cfg.EnvironmentIntensity;
 }
 // SH/Sampler.slang:349-422
-__device__ __forceinline__ void sample_emissive(const DevScene &sc, Rng &rng, float3 pos, float3 &toLight, float4 &colorPDF, uint32_t &tri, uint32_t &inst) {
-    tri = 0xFFFFFFFFu; inst = 0xFFFFFFFFu;
+// gid: global id of the sampled triangle -- the light ray contributes iff that triangle is the closest hit (SH/ClosestHit.slang:171-176)
+__device__ __forceinline__ void sample_emissive(const DevScene &sc, Rng &rng, float3 pos, float3 &toLight, float4 &colorPDF, uint32_t &gid) {
+    gid = 0xFFFFFFFFu;
     const uint32_t count = sc.n_emissive;
     if (count == 0) { toLight = f3(0.0f); colorPDF = make_float4(0, 0, 0, 0); return; }
     uint32_t mi = min((uint32_t)floorf(rng.next() * (float)count), count - 1u);
     const DevEmissive &em = sc.emissive[mi];
-    inst = em.instance;
     const uint32_t tc = em.tri_count;
     uint32_t ti = min((uint32_t)floorf(rng.next() * (float)tc), tc - 1u);
-    tri = ti;
     const float4 *et = reinterpret_cast<const float4 *>(sc.em_tris + (__ldg(sc.em_tri_base + mi) + ti));
     const float4 e0 = __ldg(et), e1 = __ldg(et + 1), e2 = __ldg(et + 2), e3 = __ldg(et + 3);
+    gid = __float_as_uint(e3.w);
     const float3 p0 = f3(e0), p1 = f3(e1), p2 = f3(e2);                   // world-space corners (:389-391, transformed once on the host)
     b200pt_vertex A, B, C;
     A.TexCoord[0] = e0.w; A.TexCoord[1] = e1.w; B.TexCoord[0] = e2.w; B.TexCoord[1] = e3.x; C.TexCoord[0] = e3.y; C.TexCoord[1] = e3.z;

@@ -106,66 +106,51 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
     if (blockIdx.x == 0 && threadIdx.x == 0) {                              // counters of the NEXT bounce (last used two bounces ago)
         ctrl[parity ^ 1u] = 0; ctrl[2u + 2u * (parity ^ 1u)] = 0; ctrl[3u + 2u * (parity ^ 1u)] = 0;
     }
-    uint32_t *qh_count = ctrl + 2u + 2u * parity;                            // [hit count, miss count] adjacent: 8-byte aligned
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long *q_count = reinterpret_cast<unsigned long long *>(ctrl + 2u + 2u * parity);   // {hit count (low), miss count (high)}, 8-byte aligned
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt = (1u << lane) - 1u;
-    __shared__ uint32_t s_cnt[2][8], s_base[2];
-    const uint32_t n_round = SMEM ? ((n + 255u) & ~255u) : ((n + 31u) & ~31u);   // SMEM variant: whole blocks iterate together
-    unsigned long long *q_count = reinterpret_cast<unsigned long long *>(qh_count);   // {hit count (low), miss count (high)}: one 64-bit atomic
-    // Queue append (ncu round 1: returning per-warp atomics on two hot addresses were 51 % of this kernel's stalls): two strategies,
-    // see below.
-    uint32_t p_i = 0, p_bh = 0, p_bm = 0; bool p_hit = false, p_act = false; unsigned long long p_base = 0ull;
-    const uint32_t step = gridDim.x * blockDim.x;
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
-    if (i < n) { o4 = ps.org_pdf[i]; d4 = ps.dir_rng[i]; }
-    for (; i < n_round; i += step) {
-        const bool active = i < n;
-        bool hit = false;
-        const uint32_t inext = i + step;
-        float4 o4n = make_float4(0, 0, 0, 0), d4n = o4n;
-        if (inext < n) { o4n = ps.org_pdf[inext]; d4n = ps.dir_rng[inext]; }   // software pipelining of the state loads
-        if (active) {
-            const float3 rd = normalize(f3(d4));                            // SH/RayGen.slang:70
-            HitRec h;
-            hit = bvh_trace<SMEM, false>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
-            so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
-        }
-        o4 = o4n; d4 = d4n;
-        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
-        if (SMEM) {
-            // tiny scene (BVH in shared memory): every warp of the block takes about the same time, so a block-level scan with
-            // ONE atomic per block is cheapest (Cornell: 4.0 ms/step vs 4.6 ms with the deferred per-warp atomic)
-            if (lane == 0) { s_cnt[0][warp] = (uint32_t)__popc(bh); s_cnt[1][warp] = (uint32_t)__popc(bm); }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t th = 0, tm = 0;
-                #pragma unroll
-                for (int w = 0; w < 8; w++) { const uint32_t ch = s_cnt[0][w], cm = s_cnt[1][w]; s_cnt[0][w] = th; s_cnt[1][w] = tm; th += ch; tm += cm; }
-                const unsigned long long base = (th | tm) ? atomicAdd(q_count, ((unsigned long long)tm << 32) | (unsigned long long)th) : 0ull;
-                s_base[0] = (uint32_t)base; s_base[1] = (uint32_t)(base >> 32);
+    // Queue append without block barriers and with few atomics (ncu round 1: returning per-warp atomics on two hot addresses were
+    // 51 % of this kernel's stalls; the block-level scan that replaced them left 2.9 warps/issue parked on __syncthreads).
+    // A block owns SEGMENTS of K*256 consecutive paths (grid-stride over segments); in iteration `it` its 8 warps cover 256
+    // consecutive paths (neighbouring pixels -> shared BVH nodes in L1), each warp traces its K rays without ever waiting for the
+    // others, lane `it` keeps the hit/miss ballots of iteration `it` in registers, then ONE 64-bit atomic per warp reserves room in
+    // both queues for all K iterations.  K adapts to the live count so small waves still fill the GPU.
+    const uint32_t K = min(8u, max(1u, n / (gridDim.x * blockDim.x * 2u)));
+    const uint32_t seg_paths = K * blockDim.x, n_seg = (n + seg_paths - 1u) / seg_paths;
+    for (uint32_t seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+        const uint32_t base_i = seg * seg_paths + (threadIdx.x & ~31u);     // first path of this warp in iteration 0
+        uint32_t my_bh = 0, my_bm = 0, ch = 0, cm = 0;
+        uint32_t i = base_i + lane;
+        float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
+        if (i < n) { o4 = ps.org_pdf[i]; d4 = ps.dir_rng[i]; }
+        for (uint32_t it = 0; it < K; it++, i += blockDim.x) {
+            if (base_i + it * blockDim.x >= n) break;                               // warp-uniform
+            const bool active = i < n;
+            bool hit = false;
+            float4 o4n = make_float4(0, 0, 0, 0), d4n = o4n;
+            if (it + 1u < K && i + blockDim.x < n) { o4n = ps.org_pdf[i + blockDim.x]; d4n = ps.dir_rng[i + blockDim.x]; }   // software pipelining of the state loads
+            if (active) {
+                const float3 rd = normalize(f3(d4));                        // SH/RayGen.slang:70
+                HitRec h;
+                hit = bvh_trace<SMEM, false>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
+                so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
             }
-            __syncthreads();
-            if (hit) q_hit[s_base[0] + s_cnt[0][warp] + __popc(bh & lt)] = i;
-            else if (active) q_miss[s_base[1] + s_cnt[1][warp] + __popc(bm & lt)] = i;
-            __syncthreads();
-        } else {
-            // big scene: traversal time varies a lot between warps, barriers would stall them on the slowest one (ncu: 9.5 warps
-            // stalled on the barrier per issue).  Per-warp reservation, ISSUED now and CONSUMED one iteration later, after the next
-            // ray's traversal, so the atomic's round trip is never exposed.
-            {
-                const unsigned long long base = __shfl_sync(0xFFFFFFFFu, p_base, 0);
-                if (p_hit) q_hit[(uint32_t)base + __popc(p_bh & lt)] = p_i;
-                else if (p_act) q_miss[(uint32_t)(base >> 32) + __popc(p_bm & lt)] = p_i;
-            }
-            if (lane == 0 && (bh | bm)) p_base = atomicAdd(q_count, ((unsigned long long)__popc(bm) << 32) | (unsigned long long)__popc(bh));
-            p_i = i; p_bh = bh; p_bm = bm; p_hit = hit; p_act = active;
+            o4 = o4n; d4 = d4n;
+            const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
+            if (lane == it) { my_bh = bh; my_bm = bm; }
+            ch += (uint32_t)__popc(bh); cm += (uint32_t)__popc(bm);
         }
-    }
-    if (!SMEM) {
-        const unsigned long long base = __shfl_sync(0xFFFFFFFFu, p_base, 0);
-        if (p_hit) q_hit[(uint32_t)base + __popc(p_bh & lt)] = p_i;
-        else if (p_act) q_miss[(uint32_t)(base >> 32) + __popc(p_bm & lt)] = p_i;
+        unsigned long long base = 0ull;
+        if (lane == 0 && (ch | cm)) base = atomicAdd(q_count, ((unsigned long long)cm << 32) | (unsigned long long)ch);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        uint32_t oh = (uint32_t)base, om = (uint32_t)(base >> 32);
+        i = base_i + lane;
+        for (uint32_t it = 0; it < K; it++, i += blockDim.x) {
+            const uint32_t bh = __shfl_sync(0xFFFFFFFFu, my_bh, (int)it), bm = __shfl_sync(0xFFFFFFFFu, my_bm, (int)it);
+            if ((bh >> lane) & 1u) q_hit[oh + __popc(bh & lt)] = i;
+            else if ((bm >> lane) & 1u) q_miss[om + __popc(bm & lt)] = i;
+            oh += (uint32_t)__popc(bh); om += (uint32_t)__popc(bm);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->extend_rays, (unsigned long long)n);
 }
@@ -214,18 +199,30 @@ __global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, 
 // k_shade_hit : SH/ClosestHit.slang:20-378 for the hit queue
 // ------------------------------------------------------------------------------------------------
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 4
+#define SHADE_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so,
                                                     const uint32_t *__restrict__ ctrl, uint32_t parity, const uint32_t *__restrict__ q_hit, WaveCounters *ctr) {
     const uint32_t n = ctrl[2u + 2u * parity];
     uint32_t n_med = 0;
     const float4 zero4 = make_float4(0, 0, 0, 0);
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const uint32_t i = q_hit[j];
-        const float4 h4 = so.hit[i];
+    // The queue entry and the hit record of the NEXT path of this thread are fetched one iteration ahead (two dependent DRAM
+    // round trips off the critical path for 5 registers); its path-state lines are pulled towards L2 meanwhile.
+    const uint32_t jstep = gridDim.x * blockDim.x;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i_nx = 0; float4 h4_nx = zero4;
+    if (j < n) { i_nx = q_hit[j]; h4_nx = so.hit[i_nx]; }
+    for (; j < n; j += jstep) {
+        const uint32_t i = i_nx;
+        const float4 h4 = h4_nx;
         const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
         const uint32_t dflags = __float_as_uint(ps.thr_depth[i].w);
+        if (j + jstep < n) {
+            i_nx = q_hit[j + jstep]; h4_nx = so.hit[i_nx];
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.org_pdf + i_nx));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.dir_rng + i_nx));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.thr_depth + i_nx));
+        }
         const uint32_t depth = dflags & 0x7FFFFFFFu;
         const bool inMedium = (dflags >> 31) != 0u;
         const float3 payOrigin = f3(o4), payDir = f3(d4);
@@ -256,9 +253,8 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         surface_rotate_tangents(sf, m.AnisotropyRotation);                  // :67
 
         bool newInMedium = inMedium;
-        float4 med = zero4; float med_g = 0.0f;
         if (inMedium) {                                                     // :80-116 (Q6)
-            med = ps.medium[i]; med_g = ps.medium_g[i];
+            const float4 med = ps.medium[i]; const float med_g = ps.medium_g[i];
             const float dist = length(payOrigin - sf.WorldPos);
             if (med_g == 1.0f) {
                 // Beer-law BxDF is overwritten below (:323) -- nothing observable happens here.
@@ -278,54 +274,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
             }
         }
 
-        // sky NEE sample :125-147 (visibility is resolved in k_connect)
-        float3 toSkyW = f3(0.0f), toSkyT = f3(0.0f); float4 sky = zero4;
-        if (cfg.EnableSkyMIS) {
-            if (!envEarly) sample_env_begin(sc, rng, ep);
-            sample_env_finish(sc, cfg, ep, toSkyW, sky);
-            sky.x *= cfg.EnvironmentIntensity; sky.y *= cfg.EnvironmentIntensity; sky.z *= cfg.EnvironmentIntensity;   // Q7
-            toSkyT = sf.world_to_tangent(toSkyW);
-        }
-        // light NEE sample :154-184
-        float3 toLightW = f3(0.0f), toLightT = f3(0.0f); float4 light = zero4; uint32_t lt = 0xFFFFFFFFu, li = 0xFFFFFFFFu;
-        if (cfg.EnableMeshMIS && !isLight) {
-            sample_emissive(sc, rng, sf.WorldPos, toLightW, light, lt, li);
-            if (light.w > 0.0f) toLightT = sf.world_to_tangent(toLightW);
-        }
-        // BSDF sample :191-204
-        float3 V = normalize(-rd);
-        V = sf.world_to_tangent(V);
-        const float3 H = ggx_sample_vndf(rng, V, m.Ax, m.Ay);
-        float3 Ls;
-        BsdfCtx bc;
-        bsdf_ctx_init(bc, m, sc, cfg, V);
-        const bool validDir = sample_bsdf_direction(m, bc, rng, V, H, Ls);
-        // EvaluateBSDF(V, .) for the sampled direction and the two NEE directions: ONE rolled loop keeps a single copy of the
-        // BSDF code in the kernel (SampleBSDF :163; ClosestHit :241-256).  NEE is evaluated eagerly, visibility comes later.
-        const bool needSky = cfg.EnableSkyMIS && sky.w > 0.0f;
-        const bool needLit = cfg.EnableMeshMIS && !isLight && light.w > 0.0f;
-        Eval evS, evSky, evLit;
-        evS.BxDF = evSky.BxDF = evLit.BxDF = f3(0.0f); evS.PDF = evSky.PDF = evLit.PDF = 0.0f;
-        #pragma unroll 1
-        for (int k = 0; k < 3; k++) {
-            const bool need = (k == 0) ? validDir : ((k == 1) ? needSky : needLit);
-            if (!need) continue;
-            const float3 dk = (k == 0) ? Ls : ((k == 1) ? toSkyT : toLightT);
-            const Eval e = eval_bsdf(m, bc, cfg, V, dk);
-            if (k == 0) evS = e; else if (k == 1) evSky = e; else evLit = e;
-        }
-        BSample ss;
-        ss.L = validDir ? Ls : f3(0.0f); ss.BxDF = evS.BxDF; ss.PDF = evS.PDF;
-        const bool wasRefracted = ss.L.z < 0.0f;
-        const float3 scatterW = sf.tangent_to_world(ss.L);
-        if (!wasRefracted && dot(scatterW, sf.GeometryNormal) < 0.0f) { ss.PDF = 0.0f; ss.BxDF = f3(0.0f); }   // :220-225
-        if (wasRefracted && sf.HitFromInside) newInMedium = false;          // :227-238
-        else if (wasRefracted && !sf.HitFromInside) {
-            newInMedium = true;
-            med = make_float4(m.MediumColor.x, m.MediumColor.y, m.MediumColor.z, m.MediumDensity); med_g = m.MediumAnisotropy;
-        }
-
-        // emission :265-317
+        // emission :265-317 (no RNG draws: evaluated before the NEE/BSDF loop so the corner positions and the ray origin die here)
         float3 e0 = f3(0.0f);
         if (cfg.EnableMeshMIS) {
             if (depth == 0 && isLight) e0 = e0 + m.EmissiveColor;
@@ -341,22 +290,66 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
             }
         } else e0 = e0 + m.EmissiveColor;
 
-        // NEE contributions (added in k_connect iff the shadow query allows) :326-372
-        float4 skyO = zero4, skyD = zero4, skyC = zero4, litO = zero4, litD = zero4, litC = zero4;
-        if (needSky && evSky.PDF > 0.0f) {
-            const float3 c = (((evSky.BxDF * 1.0f) * f3(sky)) / sky.w) * power_heuristic(sky.w, evSky.PDF);
-            const float3 so_ = sf.WorldPos + sf.Normal * 1e-5f;             // :139
-            skyO = make_float4(so_.x, so_.y, so_.z, 1.0f);
-            skyD = make_float4(toSkyW.x, toSkyW.y, toSkyW.z, 0.0f);
-            skyC = make_float4(c.x, c.y, c.z, 0.0f);
+        float3 V = normalize(-rd);
+        V = sf.world_to_tangent(V);
+        BsdfCtx bc;
+        bsdf_ctx_init(bc, m, sc, cfg, V);
+        // Three uses of EvaluateBSDF(V, .) per hit -- sky NEE (:125-147, :326-358), light NEE (:154-184, :360-372) and the sampled
+        // direction (SampleBSDF :94-165) -- run as ONE rolled loop in the reference's RNG order (sky draws, light draws, BSDF draws):
+        // a single copy of the BSDF code stays in the kernel, and each NEE request is built and stored inside its own iteration so
+        // its direction / radiance / pdf registers die there.  NEE is evaluated eagerly; visibility is resolved in k_connect.
+        Eval evS; evS.BxDF = f3(0.0f); evS.PDF = 0.0f;
+        float3 Ls = f3(0.0f); bool validDir = false;
+        #pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+            float3 toW = f3(0.0f), dk = f3(0.0f); float4 lv = zero4; uint32_t lgid = 0xFFFFFFFFu;
+            bool need = false;
+            if (k == 0) {
+                if (cfg.EnableSkyMIS) {
+                    if (!envEarly) sample_env_begin(sc, rng, ep);
+                    sample_env_finish(sc, cfg, ep, toW, lv);
+                    lv.x *= cfg.EnvironmentIntensity; lv.y *= cfg.EnvironmentIntensity; lv.z *= cfg.EnvironmentIntensity;   // Q7
+                    dk = sf.world_to_tangent(toW);
+                    need = lv.w > 0.0f;
+                }
+            } else if (k == 1) {
+                if (cfg.EnableMeshMIS && !isLight) {
+                    sample_emissive(sc, rng, sf.WorldPos, toW, lv, lgid);
+                    if (lv.w > 0.0f) { dk = sf.world_to_tangent(toW); need = true; }
+                }
+            } else {
+                const float3 H = ggx_sample_vndf(rng, V, m.Ax, m.Ay);           // :191-204
+                validDir = sample_bsdf_direction(m, bc, rng, V, H, Ls);
+                dk = Ls; need = validDir;
+            }
+            Eval e; e.BxDF = f3(0.0f); e.PDF = 0.0f;
+            if (need) e = eval_bsdf(m, bc, cfg, V, dk);
+            if (k == 2) { evS = e; break; }
+            // NEE request (added in k_connect iff the shadow query allows) :326-372
+            float4 rO = zero4;
+            if (need && e.PDF > 0.0f) {
+                const float3 c = (((e.BxDF * 1.0f) * f3(lv)) / lv.w) * power_heuristic(lv.w, e.PDF);
+                const float3 ro = (k == 0) ? sf.WorldPos + sf.Normal * 1e-5f : sf.WorldPos + toW * 1e-2f;   // :139, :171
+                rO = make_float4(ro.x, ro.y, ro.z, 1.0f);
+                float4 *const pd = (k == 0) ? so.sky_d : so.lit_d, *const pc = (k == 0) ? so.sky_c : so.lit_c;
+                pd[i] = make_float4(toW.x, toW.y, toW.z, __uint_as_float(lgid));        // .w of the light request: id of the sampled triangle
+                pc[i] = make_float4(c.x, c.y, c.z, 0.0f);
+            }
+            ((k == 0) ? so.sky_o : so.lit_o)[i] = rO;
         }
-        if (needLit && evLit.PDF > 0.0f) {
-            const float3 c = (((evLit.BxDF * 1.0f) * f3(light)) / light.w) * power_heuristic(light.w, evLit.PDF);
-            const float3 lo = sf.WorldPos + toLightW * 1e-2f;               // :171
-            litO = make_float4(lo.x, lo.y, lo.z, 1.0f);
-            litD = make_float4(toLightW.x, toLightW.y, toLightW.z, __uint_as_float(lt));
-            litC = make_float4(c.x, c.y, c.z, __uint_as_float(li));
+        BSample ss;
+        ss.L = validDir ? Ls : f3(0.0f); ss.BxDF = evS.BxDF; ss.PDF = evS.PDF;
+        const bool wasRefracted = ss.L.z < 0.0f;
+        const float3 scatterW = sf.tangent_to_world(ss.L);
+        if (!wasRefracted && dot(scatterW, sf.GeometryNormal) < 0.0f) { ss.PDF = 0.0f; ss.BxDF = f3(0.0f); }   // :220-225
+        if (wasRefracted && sf.HitFromInside) newInMedium = false;          // :227-238
+        else if (wasRefracted && !sf.HitFromInside) {                       // entering: the medium parameters are re-read from the material
+            newInMedium = true;                                             // record here instead of being carried through the loop above
+            const b200pt_material &mm = cm.m;
+            const float3 mc = cfg.FurnaceTestMode ? f3(1.0f) : f3(mm.MediumColor[0], mm.MediumColor[1], mm.MediumColor[2]);   // SH/Material.slang:78-86
+            ps.medium[i] = make_float4(mc.x, mc.y, mc.z, mm.MediumDensity); ps.medium_g[i] = mm.MediumAnisotropy;
         }
+
         // payload write :319-324, :375-376
         const float off = -1e-3f * (wasRefracted ? 1.0f : 0.0f) + 1e-3f * (wasRefracted ? 0.0f : 1.0f);
         const float3 no = sf.WorldPos + sf.Normal * off;
@@ -366,10 +359,6 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         ps.dir_rng[i] = make_float4(scatterW.x, scatterW.y, scatterW.z, __uint_as_float(rng.s));
         so.bxdf_pdf[i] = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
         so.e0[i] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(newDepth | (newInMedium ? 0x80000000u : 0u)));
-        if (newInMedium) { ps.medium[i] = med; ps.medium_g[i] = med_g; }
-        so.sky_o[i] = skyO; so.lit_o[i] = litO;
-        if (skyO.w != 0.0f) { so.sky_d[i] = skyD; so.sky_c[i] = skyC; }
-        if (litO.w != 0.0f) { so.lit_d[i] = litD; so.lit_c[i] = litC; }
     }
     for (int o = 16; o > 0; o >>= 1) n_med += __shfl_down_sync(0xFFFFFFFFu, n_med, o);
     if ((threadIdx.x & 31) == 0 && n_med) atomicAdd(&ctr->medium_events, (unsigned long long)n_med);
@@ -422,13 +411,18 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
                 const bool occluded = bvh_trace<SMEM, true>(bv, f3(so4), f3(sd4), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
                 if (!occluded) emitted = emitted + f3(sc4);
             }
-            if (lo4.w != 0.0f) {                                            // :171-176 + :360-372 (closest hit must be the sampled triangle)
-                HitRec h; n_shadow++;
-                const bool found = bvh_trace<SMEM, false>(bv, f3(lo4), f3(ld4_), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
-                if (found) {
-                    const float4 *tp = bv.tris + (size_t)h.slot * 3;
-                    const uint32_t hinst = __float_as_uint(ld4<SMEM>(tp + 1).w), hprim = __float_as_uint(ld4<SMEM>(tp + 2).w);
-                    if (hprim == __float_as_uint(ld4_.w) && hinst == __float_as_uint(lc4.w)) emitted = emitted + f3(lc4);
+            if (lo4.w != 0.0f) {                                            // :171-176 + :360-372: the closest hit must be the sampled triangle.
+                // Equivalent any-hit form: the ray hits the sampled triangle at tL and nothing lies in front of it (ties at tL
+                // resolve to the lower triangle id, exactly like the closest-hit query) -- bounded by tL and free to stop at the first occluder.
+                n_shadow++;
+                const uint32_t lgid = __float_as_uint(ld4_.w);
+                const float4 *tp = bv.tris + (size_t)__ldg(sc.tri_slot + lgid) * 3;
+                const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
+                float tL, uL, vL;
+                if (tri_test(f3(ta), f3(tb), f3(tc), f3(lo4), f3(ld4_), 0.0001f, 1000000.0f, tL, uL, vL)) {
+                    HitRec h;
+                    const bool occluded = bvh_trace<SMEM, true, false, true>(bv, f3(lo4), f3(ld4_), 0.0001f, tL, h, stack, stride, max_stack, nullptr, nullptr, lgid);
+                    if (!occluded) emitted = emitted + f3(lc4);
                 }
             }
             // SH/RayGen.slang:92-113
