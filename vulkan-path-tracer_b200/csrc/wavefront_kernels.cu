@@ -266,8 +266,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
                     ps.org_pdf[i] = make_float4(no.x, no.y, no.z, payPDF);
                     ps.dir_rng[i] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(rng.s));
                     so.bxdf_pdf[i] = make_float4(med.x, med.y, med.z, payPDF);       // stale PDF (Q6)
-                    so.e0[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(dflags));   // Depth and InMedium unchanged
-                    so.sky_o[i] = zero4; so.lit_o[i] = zero4;
+                    so.e0[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(dflags));   // Depth and InMedium unchanged, no shadow request
                     n_med++;
                     continue;
                 }
@@ -300,6 +299,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         // its direction / radiance / pdf registers die there.  NEE is evaluated eagerly; visibility is resolved in k_connect.
         Eval evS; evS.BxDF = f3(0.0f); evS.PDF = 0.0f;
         float3 Ls = f3(0.0f); bool validDir = false;
+        uint32_t reqMask = 0u;                                              // bit 0: sky request stored, bit 1: light request stored
         #pragma unroll 1
         for (int k = 0; k < 3; k++) {
             float3 toW = f3(0.0f), dk = f3(0.0f); float4 lv = zero4; uint32_t lgid = 0xFFFFFFFFu;
@@ -326,16 +326,15 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
             if (need) e = eval_bsdf(m, bc, cfg, V, dk);
             if (k == 2) { evS = e; break; }
             // NEE request (added in k_connect iff the shadow query allows) :326-372
-            float4 rO = zero4;
             if (need && e.PDF > 0.0f) {
                 const float3 c = (((e.BxDF * 1.0f) * f3(lv)) / lv.w) * power_heuristic(lv.w, e.PDF);
                 const float3 ro = (k == 0) ? sf.WorldPos + sf.Normal * 1e-5f : sf.WorldPos + toW * 1e-2f;   // :139, :171
-                rO = make_float4(ro.x, ro.y, ro.z, 1.0f);
-                float4 *const pd = (k == 0) ? so.sky_d : so.lit_d, *const pc = (k == 0) ? so.sky_c : so.lit_c;
+                float4 *const po = (k == 0) ? so.sky_o : so.lit_o, *const pd = (k == 0) ? so.sky_d : so.lit_d, *const pc = (k == 0) ? so.sky_c : so.lit_c;
+                po[i] = make_float4(ro.x, ro.y, ro.z, 1.0f);
                 pd[i] = make_float4(toW.x, toW.y, toW.z, __uint_as_float(lgid));        // .w of the light request: id of the sampled triangle
                 pc[i] = make_float4(c.x, c.y, c.z, 0.0f);
+                reqMask |= 1u << k;
             }
-            ((k == 0) ? so.sky_o : so.lit_o)[i] = rO;
         }
         BSample ss;
         ss.L = validDir ? Ls : f3(0.0f); ss.BxDF = evS.BxDF; ss.PDF = evS.PDF;
@@ -358,7 +357,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         ps.org_pdf[i] = make_float4(no.x, no.y, no.z, ss.PDF);
         ps.dir_rng[i] = make_float4(scatterW.x, scatterW.y, scatterW.z, __uint_as_float(rng.s));
         so.bxdf_pdf[i] = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
-        so.e0[i] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(newDepth | (newInMedium ? 0x80000000u : 0u)));
+        so.e0[i] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(newDepth | (reqMask << 29) | (newInMedium ? 0x80000000u : 0u)));   // bits 29/30: stored shadow requests
     }
     for (int o = 16; o > 0; o >>= 1) n_med += __shfl_down_sync(0xFFFFFFFFu, n_med, o);
     if ((threadIdx.x & 31) == 0 && n_med) atomicAdd(&ctr->medium_events, (unsigned long long)n_med);
@@ -394,27 +393,27 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
         if (active) {
             i = q_hit[j];
             const float4 e4 = so.e0[i];
-            thr4 = src.thr_depth[i]; r4 = src.rad_slot[i];
-            o4 = src.org_pdf[i]; d4 = src.dir_rng[i];
-            const float4 b4 = so.bxdf_pdf[i];
-            newDflags = __float_as_uint(e4.w);
+            uint32_t pending = (__float_as_uint(e4.w) >> 29) & 3u;         // bit 0: sky request, bit 1: light request (k_shade_hit)
+            newDflags = __float_as_uint(e4.w) & 0x9FFFFFFFu;
             const uint32_t newDepth = newDflags & 0x7FFFFFFFu;
-            rng.s = __float_as_uint(d4.w);
-            thr = f3(thr4); rad = f3(r4);
             float3 emitted = f3(e4);
-            // all six request words are fetched up front (independent 16-B loads in flight together); the d/c words of an
-            // invalid request are stale and never used
-            const float4 so4 = so.sky_o[i], sd4 = so.sky_d[i], sc4 = so.sky_c[i];
-            const float4 lo4 = so.lit_o[i], ld4_ = so.lit_d[i], lc4 = so.lit_c[i];
-            if (so4.w != 0.0f) {                                            // SH/ClosestHit.slang:139 + :326-358
-                HitRec h; n_shadow++;
+            // Request words are read when needed: the light request after the sky query, a contribution only if its ray came out
+            // unoccluded, the path state after both queries -- little is live across the traversal loops.
+            // (One resumable loop serving both rays of a lane, if-if style, was measured 1.6x SLOWER than two tight while-while loops.)
+            //   sky   (SH/ClosestHit.slang:139 + :326-358): any hit in (1e-4, 1e6) occludes;
+            //   light (:171-176 + :360-372): the closest hit must be the sampled triangle.  Equivalent occlusion form: the ray hits
+            //         that triangle at tL and nothing lies in front of it (ties at tL resolve to the lower triangle id, exactly like
+            //         the closest-hit query) -- bounded by tL and free to stop at the first occluder.
+            n_shadow += (pending & 1u) + (pending >> 1);
+            float4 so4 = make_float4(0, 0, 0, 0), sd4 = so4;
+            if (pending & 1u) { so4 = so.sky_o[i]; sd4 = so.sky_d[i]; }
+            if (pending & 1u) {
+                HitRec h;
                 const bool occluded = bvh_trace<SMEM, true>(bv, f3(so4), f3(sd4), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
-                if (!occluded) emitted = emitted + f3(sc4);
+                if (!occluded) emitted = emitted + f3(so.sky_c[i]);
             }
-            if (lo4.w != 0.0f) {                                            // :171-176 + :360-372: the closest hit must be the sampled triangle.
-                // Equivalent any-hit form: the ray hits the sampled triangle at tL and nothing lies in front of it (ties at tL
-                // resolve to the lower triangle id, exactly like the closest-hit query) -- bounded by tL and free to stop at the first occluder.
-                n_shadow++;
+            if (pending & 2u) {
+                const float4 lo4 = so.lit_o[i], ld4_ = so.lit_d[i];
                 const uint32_t lgid = __float_as_uint(ld4_.w);
                 const float4 *tp = bv.tris + (size_t)__ldg(sc.tri_slot + lgid) * 3;
                 const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
@@ -422,9 +421,15 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
                 if (tri_test(f3(ta), f3(tb), f3(tc), f3(lo4), f3(ld4_), 0.0001f, 1000000.0f, tL, uL, vL)) {
                     HitRec h;
                     const bool occluded = bvh_trace<SMEM, true, false, true>(bv, f3(lo4), f3(ld4_), 0.0001f, tL, h, stack, stride, max_stack, nullptr, nullptr, lgid);
-                    if (!occluded) emitted = emitted + f3(lc4);
+                    if (!occluded) emitted = emitted + f3(so.lit_c[i]);
                 }
             }
+            // the path state is fetched only now: nothing but the emission and the request bits is live across the traversal loop
+            thr4 = src.thr_depth[i]; r4 = src.rad_slot[i];
+            o4 = src.org_pdf[i]; d4 = src.dir_rng[i];
+            const float4 b4 = so.bxdf_pdf[i];
+            rng.s = __float_as_uint(d4.w);
+            thr = f3(thr4); rad = f3(r4);
             // SH/RayGen.slang:92-113
             float3 contribution = emitted * thr;
             if (newDepth != 1u) {                                           // Q3
