@@ -79,10 +79,15 @@ __device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3
     return (t > tmin && t < tmax);
 }
 
-// stack: shared-memory column of this thread, entries at stack[k * stride]
+// stack: shared-memory column of this thread, entries at stack[k * stride] (addressed through the shared window: STS/LDS with
+// an incrementally maintained address instead of a generic-pointer computation per push).
+// Slab test: with FMA_SLABS the plane distances are one FFMA each, t = n*inv - (o*inv) (12 FFMA per node instead of 12 FADD + 12 FMUL).
+// That form perturbs a plane by <= 6e-8*|o| (the rounding of o*inv); the node boxes carry an absolute pad of 2e-6 * scene extent
+// (lbvh.cu: k_emit), so it is conservative for every origin within ~16 scene extents -- i.e. for all secondary rays, whose origins lie
+// on scene surfaces.  Camera rays (origin anywhere) and the test hook use the subtract-then-multiply form (FMA_SLABS = false).
 // TARGET (with ANYHIT): "is anything in front of triangle target_gid, which the ray hits at tmax?"  A triangle occludes when
 // t < tmax, or t == tmax and its id is lower than the target's (the tie rule of the closest-hit query); the target itself never does.
-template <bool SMEM, bool ANYHIT, bool COUNT = false, bool TARGET = false>
+template <bool SMEM, bool ANYHIT, bool COUNT = false, bool TARGET = false, bool FMA_SLABS = false>
 __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, float tmin, float tmax, HitRec &h,
                                           int *stack, int stride, int max_stack, uint32_t *n_nodes = nullptr, uint32_t *n_tris = nullptr,
                                           uint32_t target_gid = 0xFFFFFFFFu) {
@@ -91,7 +96,9 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
     uint32_t best_gid = 0xFFFFFFFFu;
     bool found = false;
     const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int sp = 0;
+    const float3 oi = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+    const uint32_t s_base = smem_u32(stack), s_step = (uint32_t)stride * 4u, s_limit = s_base + (uint32_t)max_stack * s_step;
+    uint32_t s_top = s_base;                                               // address of the next free stack entry
     int cur = b.root;
     while (true) {
         if (cur >= 0) {
@@ -99,22 +106,32 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
             const float4 *np = b.nodes + (size_t)cur * 4;
             const float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
             // child 0: lo (n0.x n0.y n0.z) hi (n0.w n1.x n1.y); child 1: lo (n1.z n1.w n2.x) hi (n2.y n2.z n2.w)
-            float ax0 = (n0.x - o.x) * inv.x, ax1 = (n0.w - o.x) * inv.x;
-            float ay0 = (n0.y - o.y) * inv.y, ay1 = (n1.x - o.y) * inv.y;
-            float az0 = (n0.z - o.z) * inv.z, az1 = (n1.y - o.z) * inv.z;
-            float an = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), tmin));
-            float af = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), h.t));
-            float bx0 = (n1.z - o.x) * inv.x, bx1 = (n2.y - o.x) * inv.x;
-            float by0 = (n1.w - o.y) * inv.y, by1 = (n2.z - o.y) * inv.y;
-            float bz0 = (n2.x - o.z) * inv.z, bz1 = (n2.w - o.z) * inv.z;
-            float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), tmin));
-            float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), h.t));
-            const bool ha = an <= af * 1.0000004f, hb = bn <= bf * 1.0000004f;
+            float ax0, ax1, ay0, ay1, az0, az1, bx0, bx1, by0, by1, bz0, bz1;
+            if (FMA_SLABS) {
+                ax0 = __fmaf_rn(n0.x, inv.x, -oi.x); ax1 = __fmaf_rn(n0.w, inv.x, -oi.x);
+                ay0 = __fmaf_rn(n0.y, inv.y, -oi.y); ay1 = __fmaf_rn(n1.x, inv.y, -oi.y);
+                az0 = __fmaf_rn(n0.z, inv.z, -oi.z); az1 = __fmaf_rn(n1.y, inv.z, -oi.z);
+                bx0 = __fmaf_rn(n1.z, inv.x, -oi.x); bx1 = __fmaf_rn(n2.y, inv.x, -oi.x);
+                by0 = __fmaf_rn(n1.w, inv.y, -oi.y); by1 = __fmaf_rn(n2.z, inv.y, -oi.y);
+                bz0 = __fmaf_rn(n2.x, inv.z, -oi.z); bz1 = __fmaf_rn(n2.w, inv.z, -oi.z);
+            } else {
+                ax0 = (n0.x - o.x) * inv.x; ax1 = (n0.w - o.x) * inv.x;
+                ay0 = (n0.y - o.y) * inv.y; ay1 = (n1.x - o.y) * inv.y;
+                az0 = (n0.z - o.z) * inv.z; az1 = (n1.y - o.z) * inv.z;
+                bx0 = (n1.z - o.x) * inv.x; bx1 = (n2.y - o.x) * inv.x;
+                by0 = (n1.w - o.y) * inv.y; by1 = (n2.z - o.y) * inv.y;
+                bz0 = (n2.x - o.z) * inv.z; bz1 = (n2.w - o.z) * inv.z;
+            }
+            const float an = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), tmin));
+            const float af = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), h.t));
+            const float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), tmin));
+            const float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), h.t));
+            const bool ha = an <= af, hb = bn <= bf;                        // the boxes are padded (k_emit), no slack needed here
             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (ha && hb) {
                 const bool a_first = an <= bn;
                 const int near_c = a_first ? c0 : c1, far_c = a_first ? c1 : c0;
-                if (sp < max_stack) { stack[sp * stride] = far_c; sp++; }
+                if (s_top < s_limit) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_top), "r"(far_c) : "memory"); s_top += s_step; }
                 cur = near_c;
                 continue;
             } else if (ha) { cur = c0; continue; }
@@ -138,8 +155,9 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
                 }
             }
         }
-        if (sp == 0) break;
-        sp--; cur = stack[sp * stride];
+        if (s_top == s_base) break;
+        s_top -= s_step;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(cur) : "r"(s_top) : "memory");
     }
     if (!found) h.t = -1.0f;
     return found;

@@ -369,7 +369,7 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                 if (!medium && cfg_.MaxDepth - std::min(cfg_.MaxDepth, k) < chunk) chunk = cfg_.MaxDepth - std::min(cfg_.MaxDepth, k);
                 if (chunk == 0) break;
                 for (uint32_t b = 0; b < chunk; b++, k++) {
-                    launch_extend(lc_, ds_, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_ctr_, stream_); mark(1);
+                    launch_extend(lc_, ds_, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_ctr_, k == 0, stream_); mark(1);
                     launch_shade(lc_, ds_, dc, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(2);
                     launch_connect(lc_, ds_, dc, ps_[cur], ps_[cur ^ 1], so_, d_counts_, k & 1u, d_q_hit_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
                     cur ^= 1; launches += 4;

@@ -18,7 +18,7 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc);
 void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P, uint32_t first_sample,
                    const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *ctrl, WaveCounters *ctr, cudaStream_t st);
 void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, uint32_t *ctrl, uint32_t parity, uint32_t *q_hit, uint32_t *q_miss,
-                   WaveCounters *ctr, cudaStream_t st);
+                   WaveCounters *ctr, bool primary, cudaStream_t st);
 void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity,
                   const uint32_t *q_hit, const uint32_t *q_miss, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st);      // k_shade_miss + k_shade_hit
 void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,

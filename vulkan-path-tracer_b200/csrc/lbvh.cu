@@ -319,15 +319,21 @@ __device__ __forceinline__ int lbvh_child_ref(int c, const int2 *range) {
     return c;
 }
 __global__ void k_emit(int n_int, const int *__restrict__ left, const int *__restrict__ right, const int2 *__restrict__ range, const float *__restrict__ leaf_box,
-                       const float *__restrict__ node_box, BvhNode *__restrict__ nodes) {
+                       const float *__restrict__ node_box, const float *__restrict__ bounds, BvhNode *__restrict__ nodes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_int) return;
+    // absolute pad: the FMA slab test of bvh_trace perturbs a plane by <= 6e-8*|ray origin|; 2e-6 * (largest |coordinate| of the scene)
+    // keeps it conservative for origins within ~16 scene extents (every secondary ray), and also covers the rounding of the
+    // subtract-multiply form, so the traversal needs no slack factor on its interval comparison
+    float ext = 0.0f;
+    for (int k = 0; k < 6; k++) ext = fmaxf(ext, fabsf(bounds[k]));
+    const float pabs = 2e-6f * ext + 1e-30f;
     const int l = left[i], r = right[i];
     const float *a = l < 0 ? leaf_box + (size_t)(~l) * 6 : node_box + (size_t)l * 6;
     const float *b = r < 0 ? leaf_box + (size_t)(~r) * 6 : node_box + (size_t)r * 6;
     BvhNode nd;
     for (int k = 0; k < 3; k++) {
-        float pa = 4e-7f * fmaxf(fabsf(a[k]), fabsf(a[3 + k])) + 1e-30f, pb = 4e-7f * fmaxf(fabsf(b[k]), fabsf(b[3 + k])) + 1e-30f;
+        const float pa = 4e-7f * fmaxf(fabsf(a[k]), fabsf(a[3 + k])) + pabs, pb = 4e-7f * fmaxf(fabsf(b[k]), fabsf(b[3 + k])) + pabs;
         nd.lo0[k] = a[k] - pa; nd.hi0[k] = a[3 + k] + pa;
         nd.lo1[k] = b[k] - pb; nd.hi1[k] = b[3 + k] + pb;
     }
@@ -407,7 +413,7 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
     if (n_int) {
         k_karras<<<(n_int + 255) / 256, 256, 0, st>>>(keys, (int)n, left, right, parent_int, parent_leaf, range);
         k_refit<<<nblocks, 256, 0, st>>>((int)n, left, right, parent_int, parent_leaf, leaf_box, node_box, flags);
-        k_emit<<<(n_int + 255) / 256, 256, 0, st>>>((int)n_int, left, right, range, leaf_box, node_box, nodes);
+        k_emit<<<(n_int + 255) / 256, 256, 0, st>>>((int)n_int, left, right, range, leaf_box, node_box, bounds, nodes);
     }
     LBVH_CHECK(cudaStreamSynchronize(st));
     LBVH_CHECK(cudaGetLastError());

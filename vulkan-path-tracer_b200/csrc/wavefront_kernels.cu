@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) k_raygen(DevConfig cfg, const DevDispatch
 // k_extend : closest hit for every live path; splits the live list into a hit queue and a miss queue
 //            (warp ballot + prefix sum, one atomic per warp and queue) so the two shading kernels run converged
 // ------------------------------------------------------------------------------------------------
-template <bool SMEM>
+template <bool SMEM, bool PRIMARY>   // PRIMARY: camera rays (origin anywhere) -> exact slab arithmetic; later bounces start on scene surfaces -> FMA slabs
 __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, ShadeOut so, uint32_t *__restrict__ ctrl, uint32_t parity,
                                                  uint32_t *__restrict__ q_hit, uint32_t *__restrict__ q_miss, int max_stack, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
             if (active) {
                 const float3 rd = normalize(f3(d4));                        // SH/RayGen.slang:70
                 HitRec h;
-                hit = bvh_trace<SMEM, false>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
+                hit = bvh_trace<SMEM, false, false, false, !PRIMARY>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
                 so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
             }
             o4 = o4n; d4 = d4n;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
             if (pending & 1u) { so4 = so.sky_o[i]; sd4 = so.sky_d[i]; }
             if (pending & 1u) {
                 HitRec h;
-                const bool occluded = bvh_trace<SMEM, true>(bv, f3(so4), f3(sd4), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
+                const bool occluded = bvh_trace<SMEM, true, false, false, true>(bv, f3(so4), f3(sd4), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
                 if (!occluded) emitted = emitted + f3(so.sky_c[i]);
             }
             if (pending & 2u) {
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
                 float tL, uL, vL;
                 if (tri_test(f3(ta), f3(tb), f3(tc), f3(lo4), f3(ld4_), 0.0001f, 1000000.0f, tL, uL, vL)) {
                     HitRec h;
-                    const bool occluded = bvh_trace<SMEM, true, false, true>(bv, f3(lo4), f3(ld4_), 0.0001f, tL, h, stack, stride, max_stack, nullptr, nullptr, lgid);
+                    const bool occluded = bvh_trace<SMEM, true, false, true, true>(bv, f3(lo4), f3(ld4_), 0.0001f, tL, h, stack, stride, max_stack, nullptr, nullptr, lgid);
                     if (!occluded) emitted = emitted + f3(so.lit_c[i]);
                 }
             }
@@ -550,8 +550,10 @@ static bool g_attr_done = false;
 static void set_attrs_once() {
     if (g_attr_done) return;
     const int maxb = 227 * 1024;
-    cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(k_extend<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(k_extend<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(k_extend<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    cudaFuncSetAttribute(k_extend<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
     cudaFuncSetAttribute(k_connect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
     cudaFuncSetAttribute(k_connect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
     cudaFuncSetAttribute(k_trace_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
@@ -571,10 +573,10 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc) {
     const size_t sh = trace_smem_bytes(sc, lc->max_stack, 256, lc->bvh_in_smem);
     int occ_e = 0, occ_c = 0, occ_s = 0;
     if (lc->bvh_in_smem) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<true>, 256, sh);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<true, false>, 256, sh);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<true>, 256, sh);
     } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<false>, 256, sh);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<false, false>, 256, sh);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<false>, 256, sh);
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade_hit, 128, 0);
@@ -591,12 +593,17 @@ void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch 
     k_raygen<<<lc.grid_light, 256, 0, st>>>(cfg, disp, n_disp, P, first_sample, rng_carry, ps, sample_buf, ctrl, ctr);
 }
 void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, uint32_t *ctrl, uint32_t parity, uint32_t *q_hit, uint32_t *q_miss,
-                   WaveCounters *ctr, cudaStream_t st) {
+                   WaveCounters *ctr, bool primary, cudaStream_t st) {
     set_attrs_once();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_extend<true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
-    else k_extend<false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+    if (smem) {
+        if (primary) k_extend<true, true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+        else k_extend<true, false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+    } else {
+        if (primary) k_extend<false, true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+        else k_extend<false, false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+    }
 }
 void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity,
                   const uint32_t *q_hit, const uint32_t *q_miss, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
