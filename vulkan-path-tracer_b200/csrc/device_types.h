@@ -36,11 +36,18 @@ struct DevTexture { const uint8_t *data; uint32_t w, h, c, _pad; };
 struct DevMaterial {
     b200pt_material m;
     uint32_t const_mask;     // bit0 base colour, bit1 normal, bit2 roughness, bit3 metallic, bit4 emissive: that texture is 1x1
+                             // bit5: pre0..pre3 below are valid (bits 0,2,3,4 all set: nothing of the material depends on the hit's uv)
     float crough, cmetal;    // R channel / 255
     uint32_t _pad;
     float4 cbase, cnormal, cemis;   // RGBA / 255
+    // uv-independent part of Material construction (SH/Material.slang:39-77) and of the lobe probabilities (:169-177), evaluated
+    // ONCE per material by k_prepare_materials (wavefront_kernels.cu) with the very device functions the per-hit path uses
+    float4 pre0;             // BaseColor * texel^2.2 (rgb) | Roughness * texel
+    float4 pre1;             // EmissiveColor * texel (rgb) | Metallic * texel
+    float4 pre2;             // Ax | Ay | max(IOR, 1.000001) | 0
+    float4 pre3;             // pm | pd | pg | 0
 };
-static_assert(sizeof(DevMaterial) == 176, "DevMaterial layout");
+static_assert(sizeof(DevMaterial) == 240, "DevMaterial layout");
 
 struct DevEmissive { uint32_t mesh, material, tri_count, instance; float xf[16]; };  // PT/PathTracer.h:321-328 (80 B)
 static_assert(sizeof(DevEmissive) == 80, "EmissiveMeshEntry is 80 B");

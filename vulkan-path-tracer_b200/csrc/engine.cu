@@ -106,6 +106,8 @@ void Engine::upload_scene() {
         for (const auto &m : scene_.materials) dm.push_back(make_dev_material(m));
         CK(cudaMalloc(&d_materials_, dm.size() * sizeof(DevMaterial)));
         CK(cudaMemcpy(d_materials_, dm.data(), dm.size() * sizeof(DevMaterial), cudaMemcpyHostToDevice));
+        launch_prepare_materials(d_materials_, 0, (uint32_t)dm.size(), stream_);
+        CK(cudaStreamSynchronize(stream_));
     }
     CK(cudaMalloc(&d_emissive_, std::max<size_t>(1, scene_.instances.size()) * sizeof(DevEmissive)));
     rebuild_emissive();
@@ -204,7 +206,7 @@ void Engine::set_material(uint32_t idx, const b200pt_material &m) {
     for (uint32_t t : tix) if (t >= scene_.textures.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "texture index out of range" };
     CK(cudaStreamSynchronize(stream_));
     scene_.materials[idx] = m;
-    { const DevMaterial dm = make_dev_material(m); CK(cudaMemcpy(d_materials_ + idx, &dm, sizeof dm, cudaMemcpyHostToDevice)); }
+    { const DevMaterial dm = make_dev_material(m); CK(cudaMemcpy(d_materials_ + idx, &dm, sizeof dm, cudaMemcpyHostToDevice)); launch_prepare_materials(d_materials_, idx, 1, stream_); CK(cudaStreamSynchronize(stream_)); }
     rebuild_emissive();
     reset();
 }

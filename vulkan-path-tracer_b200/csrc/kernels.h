@@ -42,6 +42,7 @@ void launch_bloom_threshold(const float4 *hdr, float4 *mip0, uint32_t npix, Post
 void launch_bloom_down(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st);
 void launch_bloom_up(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st);
 void launch_tonemap(const float4 *hdr, const float4 *bloom0, uchar4 *ldr, uint32_t W, uint32_t H, PostParams p, cudaStream_t st);
+void launch_prepare_materials(DevMaterial *mats, uint32_t first, uint32_t count, cudaStream_t st);   // fills DevMaterial::pre0..pre3
 // lut_baker.cu : kind 0 = reflect, 1 = refract hit-from-outside, 2 = refract hit-from-inside; partial holds slices * SX*SY*SZ floats
 void launch_bake_lut(int kind, float *partial, float *table, uint32_t SX, uint32_t SY, uint32_t SZ, uint32_t sample_count, uint32_t seed,
                      uint32_t slices, cudaStream_t st);

@@ -283,35 +283,57 @@ __device__ __forceinline__ void surface_rotate_tangents(Surface &sf, float deg) 
 
 // ---------------------------------------------------------------- Material  SH/Material.slang
 struct Mat {
-    float3 BaseColor, EmissiveColor, SpecularColor, MediumColor;
-    float Metallic, Roughness, IOR, Transmission, Anisotropy, AnisotropyRotation, MediumDensity, MediumAnisotropy;
+    float3 BaseColor, EmissiveColor, SpecularColor;
+    float Metallic, Roughness, IOR, Transmission, Anisotropy, AnisotropyRotation;
     float Eta, Ax, Ay;
+    float pm, pd, pg;        // lobe probabilities (SH/Material.slang:169-177); uv-independent for constant textures, so they live here
 };
 struct Eval { float3 BxDF; float PDF; };
 struct BSample { float3 L; float3 BxDF; float PDF; };
 
-// :39-87
-__device__ __forceinline__ void material_init(Mat &m, const DevScene &sc, const DevConfig &cfg, const DevMaterial &dm, const Surface &sf) {
-    const b200pt_material &src = dm.m;
-    m.BaseColor = f3(src.BaseColor[0], src.BaseColor[1], src.BaseColor[2]);
-    m.EmissiveColor = f3(src.EmissiveColor[0], src.EmissiveColor[1], src.EmissiveColor[2]);
-    m.SpecularColor = f3(src.SpecularColor[0], src.SpecularColor[1], src.SpecularColor[2]);
-    m.MediumColor = f3(src.MediumColor[0], src.MediumColor[1], src.MediumColor[2]);
-    m.Metallic = src.Metallic; m.Roughness = src.Roughness; m.IOR = src.IOR; m.Transmission = src.Transmission;
-    m.Anisotropy = src.Anisotropy; m.AnisotropyRotation = src.AnisotropyRotation;
-    m.MediumDensity = src.MediumDensity; m.MediumAnisotropy = src.MediumAnisotropy;
-    const float4 tb = (dm.const_mask & 1u) ? dm.cbase : tex_sample_u8(sc.textures[src.BaseColorTextureIndex], sf.u, sf.v);
+// The part of Material construction that needs texels (SH/Material.slang:39-77) + the lobe probabilities (:169-177).  One function,
+// used per hit for textured materials and once per material (k_prepare_materials) for constant ones: identical arithmetic either way.
+__device__ __forceinline__ void material_apply_texels(Mat &m, float4 tb, float rough_t, float metal_t, float4 te) {
     m.IOR = fmaxf(m.IOR, 1.000001f);
     m.BaseColor = m.BaseColor * f3(pt_pow(tb.x, 2.2f), pt_pow(tb.y, 2.2f), pt_pow(tb.z, 2.2f));
-    m.Roughness *= (dm.const_mask & 4u) ? dm.crough : tex_sample_u8(sc.textures[src.RoughnessTextureIndex], sf.u, sf.v).x;     // Q8, Q9
-    m.Metallic *= (dm.const_mask & 8u) ? dm.cmetal : tex_sample_u8(sc.textures[src.MetallicTextureIndex], sf.u, sf.v).x;
-    const float4 te = (dm.const_mask & 16u) ? dm.cemis : tex_sample_u8(sc.textures[src.EmissiveTextureIndex], sf.u, sf.v);
+    m.Roughness *= rough_t;                                                       // Q8, Q9
+    m.Metallic *= metal_t;
     m.EmissiveColor = m.EmissiveColor * f3(te.x, te.y, te.z);
     float aspect = sqrtf(1.0f - sqrtf(m.Anisotropy) * 0.9f);
     m.Ax = fmaxf(0.00001f, m.Roughness / aspect);
     m.Ay = fmaxf(0.00001f, m.Roughness * aspect);
+    m.pm = m.Metallic;
+    m.pd = (1.0f - m.Metallic) * (1.0f - m.Transmission);
+    m.pg = (1.0f - m.Metallic) * m.Transmission;
+    const float sum = m.pm + m.pd + m.pg;
+    m.pm /= sum; m.pd /= sum; m.pg /= sum;
+}
+__device__ __forceinline__ void material_load_constants(Mat &m, const b200pt_material &src) {
+    m.BaseColor = f3(src.BaseColor[0], src.BaseColor[1], src.BaseColor[2]);
+    m.EmissiveColor = f3(src.EmissiveColor[0], src.EmissiveColor[1], src.EmissiveColor[2]);
+    m.Metallic = src.Metallic; m.Roughness = src.Roughness; m.IOR = src.IOR; m.Transmission = src.Transmission;
+    m.Anisotropy = src.Anisotropy;
+}
+// :39-87
+__device__ __forceinline__ void material_init(Mat &m, const DevScene &sc, const DevConfig &cfg, const DevMaterial &dm, const Surface &sf) {
+    const b200pt_material &src = dm.m;
+    m.SpecularColor = f3(src.SpecularColor[0], src.SpecularColor[1], src.SpecularColor[2]);
+    m.AnisotropyRotation = src.AnisotropyRotation;
+    if (dm.const_mask & 32u) {                                                   // every texture of the material is 1x1: use the per-material results
+        const float4 p0 = dm.pre0, p1 = dm.pre1, p2 = dm.pre2, p3 = dm.pre3;
+        m.BaseColor = f3(p0); m.Roughness = p0.w; m.EmissiveColor = f3(p1); m.Metallic = p1.w;
+        m.Ax = p2.x; m.Ay = p2.y; m.IOR = p2.z; m.pm = p3.x; m.pd = p3.y; m.pg = p3.z;
+        m.Transmission = src.Transmission; m.Anisotropy = src.Anisotropy;
+    } else {
+        material_load_constants(m, src);
+        const float4 tb = (dm.const_mask & 1u) ? dm.cbase : tex_sample_u8(sc.textures[src.BaseColorTextureIndex], sf.u, sf.v);
+        const float tr = (dm.const_mask & 4u) ? dm.crough : tex_sample_u8(sc.textures[src.RoughnessTextureIndex], sf.u, sf.v).x;
+        const float tm = (dm.const_mask & 8u) ? dm.cmetal : tex_sample_u8(sc.textures[src.MetallicTextureIndex], sf.u, sf.v).x;
+        const float4 te = (dm.const_mask & 16u) ? dm.cemis : tex_sample_u8(sc.textures[src.EmissiveTextureIndex], sf.u, sf.v);
+        material_apply_texels(m, tb, tr, tm, te);
+    }
     m.Eta = sf.HitFromInside ? m.IOR : 1.0f / m.IOR;
-    if (cfg.FurnaceTestMode) { m.BaseColor = f3(1.0f); m.EmissiveColor = f3(0.0f); m.SpecularColor = f3(1.0f); m.MediumColor = f3(1.0f); }   // :78-86
+    if (cfg.FurnaceTestMode) { m.BaseColor = f3(1.0f); m.EmissiveColor = f3(0.0f); m.SpecularColor = f3(1.0f); }   // :78-86 (MediumColor: k_shade_hit)
 }
 __device__ __forceinline__ float schlick_fresnel(float VdotH) { float m = clampf(1.0f - VdotH, 0.0f, 1.0f); float m2 = m * m; return m2 * m2 * m; }   // :427-432
 // :434-449
@@ -346,11 +368,7 @@ __device__ __forceinline__ float ggx_d(const BsdfCtx &c, float3 H) {            
     return 1.0f / (c.dnorm * (e * e));
 }
 __device__ __forceinline__ void bsdf_ctx_init(BsdfCtx &c, const Mat &m, const DevScene &sc, const DevConfig &cfg, float3 V) {
-    c.pm = m.Metallic;
-    c.pd = (1.0f - m.Metallic) * (1.0f - m.Transmission);
-    c.pg = (1.0f - m.Metallic) * m.Transmission;
-    const float sum = c.pm + c.pd + c.pg;
-    c.pm /= sum; c.pd /= sum; c.pg /= sum;
+    c.pm = m.pm; c.pd = m.pd; c.pg = m.pg;                                   // :169-177 (material_apply_texels)
     c.ax2 = m.Ax * m.Ax; c.ay2 = m.Ay * m.Ay; c.dnorm = PT_PI * m.Ax * m.Ay;
     c.GV = ggx_g1(m, V);
     c.reflEC = 1.0f; c.glassEC = 0.0f; c.metalEC = f3(1.0f);

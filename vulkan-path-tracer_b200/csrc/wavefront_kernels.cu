@@ -475,6 +475,27 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_prepare_materials : per-material constants of materials whose textures are all 1x1 (DevMaterial::pre0..pre3)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_prepare_materials(DevMaterial *mats, uint32_t first, uint32_t count) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    DevMaterial &dm = mats[first + j];
+    if ((dm.const_mask & 29u) != 29u) { dm.const_mask &= ~32u; return; }     // base, roughness, metallic, emissive textures must all be constant
+    Mat m;
+    material_load_constants(m, dm.m);
+    material_apply_texels(m, dm.cbase, dm.crough, dm.cmetal, dm.cemis);
+    dm.pre0 = make_float4(m.BaseColor.x, m.BaseColor.y, m.BaseColor.z, m.Roughness);
+    dm.pre1 = make_float4(m.EmissiveColor.x, m.EmissiveColor.y, m.EmissiveColor.z, m.Metallic);
+    dm.pre2 = make_float4(m.Ax, m.Ay, m.IOR, 0.0f);
+    dm.pre3 = make_float4(m.pm, m.pd, m.pg, 0.0f);
+    dm.const_mask |= 32u;
+}
+void launch_prepare_materials(DevMaterial *mats, uint32_t first, uint32_t count, cudaStream_t st) {
+    if (count) k_prepare_materials<<<(count + 127) / 128, 128, 0, st>>>(mats, first, count);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_resolve : SH/RayGen.slang:130-159 for every dispatch of the wave, in dispatch order
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_resolve(DevConfig cfg, const DevDispatch *__restrict__ disp, uint32_t n_disp, uint32_t P,
