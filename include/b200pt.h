@@ -187,6 +187,13 @@ int32_t b200pt_bake_lut(b200pt_handle h, int32_t kind, uint32_t sx, uint32_t sy,
 int32_t b200pt_bake_luts_to_dir(b200pt_handle h, const char *dir, uint32_t sample_count, uint32_t seed, int32_t overwrite);
 int32_t b200pt_scene_stats(b200pt_handle h, uint32_t *triangles, uint32_t *bvh_nodes, uint32_t *emissive_meshes, uint32_t *textures);
 
+/* Host half of the acceleration-structure build (replaces the driver's BLAS/TLAS build behind VH/Source/Vulkan/BLASBuilderImpl.cpp,
+ * TLASImpl.cpp for scenes that traverse out of L2): collapse of the GPU-built BVH2 into 128-byte BVH4 nodes.  Pure CPU code, exposed so
+ * the structure can be checked without a GPU.  nodes2: n_nodes2 x 64-B {lo0[3],hi0[3],lo1[3],hi1[3],c0,c1,pad[2]} with child >= 0 an
+ * inner node and child < 0 a leaf reference; nodes4_out: room for n_nodes2 x 128-B {lox[4],loy[4],loz[4],hix[4],hiy[4],hiz[4],child[4],pad[4]}.
+ * Returns the node count in *n_nodes4_out (0 when root2 is a leaf) and the BVH4 depth in *depth_out. */
+int32_t b200pt_bvh4_collapse(const void *nodes2, uint32_t n_nodes2, int32_t root2, void *nodes4_out, uint32_t *n_nodes4_out, int32_t *depth_out);
+
 /* ---- standalone codecs of the loader / image-output API (no GPU needed) ---- */
 /* stbi_load(.., STBI_rgb_alpha) / stbi_loadf semantics (AssetImporterImpl.cpp:494-545); free with b200pt_free */
 int32_t b200pt_decode_image_file(const char *path, uint32_t *width, uint32_t *height, uint8_t **rgba_out);

@@ -313,3 +313,31 @@ def test_bake_luts_to_dir_writes_reference_file_layout(pt, tmp_path):
     T.bake_luts_to_dir(tmp_path, sample_count=400, seed=2)                       # existing files are kept (Application.cpp:35)
     assert (tmp_path / "ReflectionLookup.bin").read_bytes() == before
     T2 = pt.PathTracer(0); T2.set_luts_dir(str(tmp_path))                        # and load back through the normal path
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,depth", [("cornell_box_glass", 16), ("viking_room", 8), ("breakfast_room", 8)])
+def test_traversal_shapes_are_bit_identical(pt, name, depth, monkeypatch):
+    """One-ray-per-thread BVH2 traversal (bvh_traverse.cuh) and the dynamic-fetch kernels (bvh_dynfetch.cuh: k_extend_dyn, k_shadow_dyn +
+    join-only k_connect; BVH2 or the host-collapsed BVH4) answer the same queries (SH/RayGen.slang:90,
+    SH/ClosestHit.slang:139,171-176): images and work counters must be identical bit for bit in every configuration."""
+    W, H, frames = 160, 120, 3
+    out = {}
+    modes = [dict(B200PT_TRAV="classic"),
+             dict(B200PT_TRAV="dyn", B200PT_WIDE="0", B200PT_DYN_THRESH="20"),
+             dict(B200PT_TRAV="dyn", B200PT_WIDE="0", B200PT_DYN_THRESH="32"),
+             dict(B200PT_TRAV="dyn", B200PT_WIDE="1", B200PT_DYN_THRESH="20"),
+             dict(B200PT_TRAV="dyn", B200PT_WIDE="1", B200PT_DYN_THRESH="1"),
+             dict(B200PT_TRAV="dyn", B200PT_WIDE="1", B200PT_WIDE_STACK="4")]      # tiny shared column: the local-memory overflow stack carries the traversal
+    for m in modes:
+        for k in ("B200PT_TRAV", "B200PT_WIDE", "B200PT_DYN_THRESH", "B200PT_WIDE_STACK"): monkeypatch.delenv(k, raising=False)
+        for k, v in m.items(): monkeypatch.setenv(k, v)
+        T = util.product_tracer(name, W, H, MaxDepth=depth)
+        T.path_trace(frames, util.BASE_SEED)
+        c = T.counters()
+        out[tuple(sorted(m.items()))] = (T.get_hdr().copy(), {k: c[k] for k in ("paths", "extend_rays", "surface_hits", "misses", "shadow_rays")})
+    ref_img, ref_c = out[tuple(sorted(modes[0].items()))]
+    assert np.isfinite(ref_img).all() and ref_c["shadow_rays"] > 0
+    for k, (img, c) in out.items():
+        assert c == ref_c, (k, c, ref_c)
+        assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32)), (k, float(np.abs(img - ref_img).max()))

@@ -234,3 +234,80 @@ def test_cpp_gltf_loader_on_a_synthetic_scene(tmp_path):
     assert len(b["instances"]) == 3 and abs(float(b["aspect"]) - 1.5) < 1e-7
     # Y flip: det of the instance transform is negative
     assert np.linalg.det(b["instances"][2][0].reshape(4, 4).T[:3, :3]) < 0
+
+
+def _random_bvh2(n_leaves, rng, chain=False):
+    """A random binary hierarchy in the product's 64-B node layout: leaves are references ~((first << 2) | (count - 1))."""
+    from vpt_b200 import binding as B
+    boxes = rng.random((n_leaves, 2, 3)).astype(np.float32); boxes[:, 1] = boxes[:, 0] + 0.05 * rng.random((n_leaves, 3)).astype(np.float32)
+    refs = [~((4 * i << 2) | int(rng.integers(0, 4))) for i in range(n_leaves)]
+    nodes = np.zeros(n_leaves - 1, B.BVH2_DTYPE)
+    box_of = {}
+    counter = [0]
+
+    def build(lo, hi):                                   # leaves [lo, hi) -> (child ref, box)
+        if hi - lo == 1:
+            return refs[lo], boxes[lo]
+        idx = counter[0]; counter[0] += 1
+        mid = lo + 1 if chain else int(rng.integers(lo + 1, hi))
+        ca, ba = build(lo, mid); cb, bb = build(mid, hi)
+        nodes[idx]["lo0"], nodes[idx]["hi0"], nodes[idx]["lo1"], nodes[idx]["hi1"] = ba[0], ba[1], bb[0], bb[1]
+        nodes[idx]["c0"], nodes[idx]["c1"] = ca, cb
+        bx = np.stack([np.minimum(ba[0], bb[0]), np.maximum(ba[1], bb[1])])
+        box_of[idx] = bx
+        return idx, bx
+
+    import sys
+    sys.setrecursionlimit(10000)
+    build(0, n_leaves)
+    return nodes, refs
+
+
+@pytest.mark.parametrize("n_leaves,chain", [(2, False), (3, False), (9, False), (1000, False), (40, True)])
+def test_bvh4_collapse_preserves_leaves_and_boxes(n_leaves, chain):
+    """Host half of the acceleration-structure build (lbvh.cu: bvh4_collapse_host): every BVH2 leaf reference appears exactly once in
+    the BVH4, every child box is the box its BVH2 parent stored for it, the layout is breadth-first and the reported depth is exact."""
+    from vpt_b200 import binding as B
+    rng = np.random.default_rng(n_leaves)
+    nodes2, refs = _random_bvh2(n_leaves, rng, chain)
+    box2 = {}                                            # child ref -> box as stored in its BVH2 parent
+    for n in nodes2:
+        box2[int(n["c0"])] = (n["lo0"].copy(), n["hi0"].copy()); box2[int(n["c1"])] = (n["lo1"].copy(), n["hi1"].copy())
+    nodes4, depth = B.bvh4_collapse(nodes2, 0)
+    assert 1 <= len(nodes4) <= len(nodes2)
+    seen_leaves, depth_of, max_d = [], {0: 1}, 1
+    inner2_of = {0: 0}                                   # BVH4 node -> BVH2 node it was made from (reconstructed through the boxes)
+    for i, n in enumerate(nodes4):
+        kids = [int(c) for c in n["child"]]
+        used = [k for k in range(4) if kids[k] != B.BVH4_EMPTY]
+        assert len(used) >= 2 and used == list(range(len(used)))          # slots are filled from the front
+        for k in range(4):
+            lo = np.array([n["lox"][k], n["loy"][k], n["loz"][k]]); hi = np.array([n["hix"][k], n["hiy"][k], n["hiz"][k]])
+            if k not in used:
+                assert np.all(lo == np.float32(3.0e38)) and np.all(hi == np.float32(3.0e38))
+                continue
+            c = kids[k]
+            if c < 0:
+                seen_leaves.append(c)
+                blo, bhi = box2[c]
+                assert np.array_equal(lo, blo) and np.array_equal(hi, bhi)
+            else:
+                assert i < c < len(nodes4)                                   # breadth-first: children come later
+                depth_of[c] = depth_of[i] + 1; max_d = max(max_d, depth_of[c])
+                # an inner child's box must be one of the BVH2 inner-node boxes
+                assert any(np.array_equal(lo, b[0]) and np.array_equal(hi, b[1]) for r, b in box2.items() if r >= 0)
+        if len(used) < 4:
+            assert all(kids[k] < 0 for k in used)                            # a node stops short of 4 slots only when all are leaves
+    assert sorted(seen_leaves) == sorted(refs)
+    assert depth == max_d
+    if chain: assert depth <= (n_leaves + 1) // 2 + 1                        # each level absorbs at least two BVH2 levels of a chain... or one + leaf
+
+
+def test_bvh4_collapse_rejects_bad_arguments_and_leaf_root():
+    from vpt_b200 import binding as B
+    rng = np.random.default_rng(1)
+    nodes2, _ = _random_bvh2(4, rng)
+    n4, d = B.bvh4_collapse(nodes2, -5)                   # leaf root: nothing to collapse
+    assert len(n4) == 0 and d == 0
+    with pytest.raises(B.B200ptError):
+        B.bvh4_collapse(nodes2, 99)

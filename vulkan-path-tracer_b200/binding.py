@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+LIB_PATH = os.environ.get("B200PT_LIB") or os.path.join(_HERE, "libb200pt.so")   # B200PT_LIB: A/B a differently built library (profiles/)
 _LIB = None
 
 OK = 0
@@ -127,6 +127,7 @@ def lib():
             "b200pt_decode_hdr_file": [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)],
             "b200pt_write_png": [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p],
             "b200pt_build_env_alias": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_float)],
+            "b200pt_bvh4_collapse": [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)],
             "b200pt_load_gltf": [C.c_char_p, C.POINTER(C.POINTER(SceneDesc))], "b200pt_free_scene": [C.POINTER(SceneDesc)],
         }
         for name, args in sig.items():
@@ -186,6 +187,21 @@ def write_png(path, rgba):
     rgba = np.ascontiguousarray(rgba, np.uint8)
     r = lib().b200pt_write_png(path.encode(), rgba.shape[1], rgba.shape[0], _p(rgba))
     if r != OK: raise B200ptError(r, "write_png")
+
+
+BVH2_DTYPE = np.dtype([("lo0", "<f4", 3), ("hi0", "<f4", 3), ("lo1", "<f4", 3), ("hi1", "<f4", 3), ("c0", "<i4"), ("c1", "<i4"), ("pad", "<u4", 2)])
+BVH4_DTYPE = np.dtype([("lox", "<f4", 4), ("loy", "<f4", 4), ("loz", "<f4", 4), ("hix", "<f4", 4), ("hiy", "<f4", 4), ("hiz", "<f4", 4), ("child", "<i4", 4), ("pad", "<u4", 4)])
+BVH4_EMPTY = -(1 << 31)
+
+
+def bvh4_collapse(nodes2, root2=0):
+    """Host BVH2 -> BVH4 collapse (csrc/lbvh.cu: bvh4_collapse_host).  nodes2: BVH2_DTYPE array; returns (BVH4_DTYPE array, depth)."""
+    nodes2 = np.ascontiguousarray(nodes2, BVH2_DTYPE)
+    out = np.zeros(len(nodes2), BVH4_DTYPE)
+    n4, d = C.c_uint32(), C.c_int32()
+    r = lib().b200pt_bvh4_collapse(_p(nodes2), len(nodes2), int(root2), _p(out), C.byref(n4), C.byref(d))
+    if r != OK: raise B200ptError(r, "bvh4_collapse")
+    return out[:n4.value].copy(), d.value
 
 
 def build_env_alias(rgba):

@@ -64,18 +64,33 @@ template <bool SMEM> __device__ __forceinline__ float4 ld4(const float4 *p) {
 }
 
 // Moeller-Trumbore with precomputed edges; the same formula as the oracle's tri_hit().
+// The products are written with explicit FMA / multiply intrinsics so that every kernel this is inlined into (k_extend, k_connect,
+// k_extend_dyn, k_shadow_dyn, k_trace_rays) rounds identically: the traversal shapes are interchangeable bit for bit (tested).
+__device__ __forceinline__ float3 cross_fma(float3 a, float3 b) {          // a x b, each component fma(a1, b2, -(a2 * b1))
+    return f3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)), __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float dot_fma(float3 a, float3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, __fmul_rn(a.x, b.x))); }
+// normalize() of the extension-ray direction (SH/RayGen.slang:70) with pinned rounding, shared by k_extend and k_extend_dyn
+__device__ __forceinline__ float3 normalize_ray(float3 a) {
+#ifdef B200PT_PRECISE
+    const float inv = 1.0f / sqrtf(dot_fma(a, a));
+#else
+    const float inv = rsqrtf(dot_fma(a, a));
+#endif
+    return f3(__fmul_rn(a.x, inv), __fmul_rn(a.y, inv), __fmul_rn(a.z, inv));
+}
 __device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3 o, float3 d, float tmin, float tmax, float &t, float &u, float &v) {
-    float3 p = cross(d, e2);
-    float det = dot(e1, p);
+    const float3 p = cross_fma(d, e2);
+    const float det = dot_fma(e1, p);
     if (det == 0.0f) return false;
-    float inv = 1.0f / det;
-    float3 tv = o - v0;
-    u = dot(tv, p) * inv;
+    const float inv = 1.0f / det;
+    const float3 tv = f3(__fsub_rn(o.x, v0.x), __fsub_rn(o.y, v0.y), __fsub_rn(o.z, v0.z));
+    u = __fmul_rn(dot_fma(tv, p), inv);
     if (!(u >= 0.0f && u <= 1.0f)) return false;
-    float3 q = cross(tv, e1);
-    v = dot(d, q) * inv;
-    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
-    t = dot(e2, q) * inv;
+    const float3 q = cross_fma(tv, e1);
+    v = __fmul_rn(dot_fma(d, q), inv);
+    if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
+    t = __fmul_rn(dot_fma(e2, q), inv);
     return (t > tmin && t < tmax);
 }
 

@@ -198,6 +198,14 @@ int32_t b200pt_write_png(const char *path, uint32_t w, uint32_t hh, const uint8_
     if (!path || !w || !hh || !rgba) return B200PT_ERR_WRONG_ARGUMENTS;
     return write_png_rgba8(path, w, hh, rgba) ? B200PT_OK : B200PT_ERR_UNKNOWN;
 }
+int32_t b200pt_bvh4_collapse(const void *nodes2, uint32_t n_nodes2, int32_t root2, void *nodes4_out, uint32_t *n_nodes4_out, int32_t *depth_out) {
+    if (!nodes2 || !nodes4_out || !n_nodes4_out || !n_nodes2) return B200PT_ERR_WRONG_ARGUMENTS;
+    if (root2 >= 0 && (uint32_t)root2 >= n_nodes2) return B200PT_ERR_WRONG_ARGUMENTS;
+    int d = 0;
+    *n_nodes4_out = b200pt::bvh4_collapse_host(static_cast<const b200pt::BvhNode *>(nodes2), n_nodes2, root2, static_cast<b200pt::Bvh4Node *>(nodes4_out), &d);
+    if (depth_out) *depth_out = d;
+    return B200PT_OK;
+}
 int32_t b200pt_build_env_alias(float *rgba, uint32_t w, uint32_t hh, void *alias, float *sum) {
     if (!rgba || !w || !hh || !alias) return B200PT_ERR_WRONG_ARGUMENTS;
     float s = build_env_alias(rgba, w, hh, (uint2 *)alias); if (sum) *sum = s; return B200PT_OK;

@@ -64,6 +64,18 @@ struct BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode is 64 B");
 
+// 128-byte BVH4 node (wide traversal of scenes that live in L2/HBM): the four child boxes in SoA order, so a node is eight 16-B loads and
+// one memory round trip decides four children.  Built on the host by collapsing the GPU-built BVH2 (lbvh.cu: bvh4_collapse_host).
+// child >= 0 : BVH4 node index;  child < 0 : leaf reference, same encoding as BvhNode;  unused slot: child = BVH4_EMPTY and a point box
+// at +3e38 that no ray interval reaches (no special case in the traversal).
+struct Bvh4Node {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int32_t child[4];
+    uint32_t _pad[4];
+};
+static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node is 128 B");
+constexpr int32_t BVH4_EMPTY = (int32_t)0x80000000;
+
 // 48-byte triangle: world-space v0 and edges + ids (a = v0.xyz|gid, b = e1.xyz|inst, c = e2.xyz|prim)
 struct BvhTri { float4 a, b, c; };
 static_assert(sizeof(BvhTri) == 48, "BvhTri is 48 B");
@@ -93,6 +105,7 @@ struct DevScene {
     const float *lut_reflect, *lut_refract_out, *lut_refract_in;
     const uint32_t *tri_slot;      // global triangle id -> one of its BvhTri slots (light-ray visibility test in k_connect)
     const BvhNode *nodes;
+    const Bvh4Node *nodes4;        // BVH4 collapse of `nodes` (nullptr when the scene is traversed as BVH2), root = node 0
     const BvhTri *tris;
     const ShadeTri *shade_tris;
     const EmTri *em_tris;

@@ -31,7 +31,7 @@ Engine::Engine(int device) : device_(device) {
     for (int i = 0; i < 4; i++) view_inv_[i * 5] = proj_inv_[i * 5] = 1.0f;
     CK(cudaMalloc(&d_ctr_, sizeof(WaveCounters)));
     CK(cudaMemset(d_ctr_, 0, sizeof(WaveCounters)));
-    CK(cudaMalloc(&d_counts_, 8 * sizeof(uint32_t)));
+    CK(cudaMalloc(&d_counts_, 16 * sizeof(uint32_t)));
     CK(cudaMallocHost(&h_count_, 4 * sizeof(uint32_t)));
     memset(&last_, 0, sizeof last_);
 }
@@ -127,7 +127,13 @@ void Engine::upload_scene() {
     ds_.verts = d_verts_; ds_.indices = d_indices_; ds_.meshes = d_meshes_; ds_.instances = d_instances_; ds_.materials = d_materials_;
     ds_.textures = d_textures_; ds_.emissive = d_emissive_; ds_.nodes = bvh_.nodes; ds_.tris = bvh_.tris; ds_.shade_tris = bvh_.shade; ds_.tri_slot = bvh_.tri_slot;
     ds_.n_tris = bvh_.n_tris; ds_.n_nodes = bvh_.n_nodes; ds_.root = bvh_.root; ds_.bvh_bytes = bvh_.bytes <= 0xFFFFFFFFull ? (uint32_t)bvh_.bytes : 0;
-    int q = query_launch_cfg(ds_, bvh_.max_depth, &lc_);
+    ds_.nodes4 = nullptr;
+    if (bvh_.bytes > 64u * 1024u) {                                         // scenes that traverse out of L2/HBM get the BVH4 (host collapse of the GPU-built BVH2)
+        r = lbvh_build_wide(&bvh_, stream_);
+        if (r != 0) throw CudaError{ B200PT_ERR_CUDA, std::string("lbvh_build_wide failed: ") + cudaGetErrorString((cudaError_t)r) };
+        ds_.nodes4 = bvh_.nodes4;
+    }
+    int q = query_launch_cfg(ds_, bvh_.max_depth, bvh_.depth4, &lc_);
     if (q != 0) throw CudaError{ B200PT_ERR_CUDA, "query_launch_cfg failed" };
 }
 
@@ -374,7 +380,7 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                     launch_extend(lc_, ds_, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_ctr_, k == 0, stream_); mark(1);
                     launch_shade(lc_, ds_, dc, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(2);
                     launch_connect(lc_, ds_, dc, ps_[cur], ps_[cur ^ 1], so_, d_counts_, k & 1u, d_q_hit_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
-                    cur ^= 1; launches += 4;
+                    cur ^= 1; launches += lc_.trav_dyn ? 5 : 4;
                 }
                 if (!medium && k >= cfg_.MaxDepth) break;    // every surviving path has Depth >= MaxDepth: provably empty
                 CK(cudaMemcpyAsync(h_count_, d_counts_ + (k & 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));

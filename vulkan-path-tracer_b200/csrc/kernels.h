@@ -12,9 +12,14 @@ struct LaunchCfg {
     int grid_shade;     // persistent grid for the shading kernel
     int max_stack;      // traversal stack entries (BVH depth + 2)
     bool bvh_in_smem;   // whole BVH staged to shared memory by TMA
+    bool trav_dyn;      // dynamic-fetch while-while traversal kernels (k_extend_dyn / k_shadow_dyn) instead of one ray per thread
+    int dyn_thresh;     // a warp refills its idle lanes when fewer than this many lanes are still traversing
+    int grid_shadow;    // persistent grid of k_shadow_dyn
+    bool wide;          // the dynamic-fetch kernels walk the BVH4 (DevScene::nodes4)
+    int dyn_stack;      // shared-memory stack entries per thread of the dynamic-fetch kernels (BVH4: overflow goes to local memory)
 };
 
-int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc);
+int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, LaunchCfg *lc);
 void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P, uint32_t first_sample,
                    const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *ctrl, WaveCounters *ctr, cudaStream_t st);
 void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, uint32_t *ctrl, uint32_t parity, uint32_t *q_hit, uint32_t *q_miss,
@@ -29,12 +34,18 @@ void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, cons
                        float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, uint32_t *stats, cudaStream_t st);
 
 // ---- LBVH build (lbvh.cu): world-space flattening of the two-level TLAS/BLAS ----
-struct LbvhResult { ShadeTri *shade; uint32_t *tri_slot; BvhNode *nodes; BvhTri *tris; uint32_t n_nodes, n_tris; int32_t root; int max_depth; size_t bytes; };
+struct LbvhResult { ShadeTri *shade; uint32_t *tri_slot; BvhNode *nodes; BvhTri *tris; uint32_t n_nodes, n_tris; int32_t root; int max_depth; size_t bytes;
+                    Bvh4Node *nodes4; uint32_t n_nodes4; int depth4; };
 // Builds into ONE contiguous allocation [nodes | tris] (so small scenes can be staged to smem with one bulk copy).
 // Returns cudaError_t as int.
 int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const DevMesh *d_meshes, const DevInstance *d_instances,
                const DevInstance *h_instances, const DevMesh *h_meshes, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st);
 void lbvh_free(LbvhResult *r);
+// BVH2 -> BVH4 on the host (pure CPU code, unit-tested without a GPU through b200pt_bvh4_collapse).  `out` must hold n_nodes2 entries.
+// Returns the number of BVH4 nodes written (0 if the root is a leaf), *depth4 = depth of the BVH4 (root = 1).
+uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, Bvh4Node *out, int *depth4);
+// Downloads r->nodes, collapses, uploads r->nodes4 (own allocation).  Returns cudaError_t as int; leaves nodes4 = nullptr if the root is a leaf.
+int lbvh_build_wide(LbvhResult *r, cudaStream_t st);
 
 // ---- post chain (post_kernels.cu) ----
 struct PostParams { float Exposure, Gamma, BloomThreshold, BloomStrength, FalloffRange; };

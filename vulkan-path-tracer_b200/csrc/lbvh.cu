@@ -341,7 +341,76 @@ __global__ void k_emit(int n_int, const int *__restrict__ left, const int *__res
     nodes[i] = nd;
 }
 
+// ------------------------------------------------------------------------------------------------
+// BVH2 -> BVH4 collapse (host).  Every BVH4 node takes a BVH2 node, starts from its two children and keeps replacing the internal
+// child of largest surface area by that child's two children until four slots are filled (or only leaves remain).  Child boxes are
+// copied verbatim from the BVH2 nodes, so the BVH4 is exactly as conservative as the BVH2 (same padded boxes, same leaves): both
+// structures return identical hits.  Nodes are emitted in breadth-first order (the hot top levels are contiguous).
+// ------------------------------------------------------------------------------------------------
+uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, Bvh4Node *out, int *depth4) {
+    if (depth4) *depth4 = 0;
+    if (root2 < 0 || n_nodes2 == 0) return 0;
+    struct Slot { int32_t child; float lo[3], hi[3]; };
+    auto area = [](const Slot &s) { const float dx = s.hi[0] - s.lo[0], dy = s.hi[1] - s.lo[1], dz = s.hi[2] - s.lo[2]; return dx * dy + dy * dz + dz * dx; };
+    auto slots_of = [&](int32_t n, Slot &a, Slot &b) {
+        const BvhNode &N = nodes2[n];
+        a.child = N.c0; b.child = N.c1;
+        for (int k = 0; k < 3; k++) { a.lo[k] = N.lo0[k]; a.hi[k] = N.hi0[k]; b.lo[k] = N.lo1[k]; b.hi[k] = N.hi1[k]; }
+    };
+    std::vector<std::pair<int32_t, int>> queue;                          // (BVH2 node, depth) of BVH4 node i, in emission order
+    queue.reserve(n_nodes2 / 2 + 1);
+    queue.push_back({ root2, 1 });
+    int max_d = 1;
+    for (size_t i = 0; i < queue.size(); i++) {
+        const int32_t n2 = queue[i].first; const int dep = queue[i].second;
+        if (dep > max_d) max_d = dep;
+        Slot sl[4]; int ns = 2;
+        slots_of(n2, sl[0], sl[1]);
+        while (ns < 4) {
+            int best = -1; float best_a = -1.0f;
+            for (int k = 0; k < ns; k++) if (sl[k].child >= 0) { const float a = area(sl[k]); if (a > best_a) { best_a = a; best = k; } }
+            if (best < 0) break;
+            Slot a, b; slots_of(sl[best].child, a, b);
+            sl[best] = a; sl[ns++] = b;
+        }
+        Bvh4Node &o = out[i];
+        for (int k = 0; k < 4; k++) {
+            if (k < ns) {
+                o.lox[k] = sl[k].lo[0]; o.loy[k] = sl[k].lo[1]; o.loz[k] = sl[k].lo[2];
+                o.hix[k] = sl[k].hi[0]; o.hiy[k] = sl[k].hi[1]; o.hiz[k] = sl[k].hi[2];
+                if (sl[k].child >= 0) { o.child[k] = (int32_t)queue.size(); queue.push_back({ sl[k].child, dep + 1 }); }
+                else o.child[k] = sl[k].child;
+            } else {
+                o.lox[k] = o.loy[k] = o.loz[k] = o.hix[k] = o.hiy[k] = o.hiz[k] = 3.0e38f;
+                o.child[k] = BVH4_EMPTY;
+            }
+            o._pad[k] = 0;
+        }
+    }
+    if (depth4) *depth4 = max_d;
+    return (uint32_t)queue.size();
+}
+
+int lbvh_build_wide(LbvhResult *r, cudaStream_t st) {
+    r->nodes4 = nullptr; r->n_nodes4 = 0; r->depth4 = 0;
+    if (!r->nodes || r->root < 0 || r->n_nodes == 0) return 0;
+    std::vector<BvhNode> h2(r->n_nodes);
+    LBVH_CHECK(cudaMemcpyAsync(h2.data(), r->nodes, (size_t)r->n_nodes * sizeof(BvhNode), cudaMemcpyDeviceToHost, st));
+    LBVH_CHECK(cudaStreamSynchronize(st));
+    std::vector<Bvh4Node> h4(r->n_nodes);
+    int d4 = 0;
+    const uint32_t n4 = bvh4_collapse_host(h2.data(), r->n_nodes, r->root, h4.data(), &d4);
+    if (n4 == 0) return 0;
+    LBVH_CHECK(cudaMalloc(&r->nodes4, (size_t)n4 * sizeof(Bvh4Node)));
+    LBVH_CHECK(cudaMemcpyAsync(r->nodes4, h4.data(), (size_t)n4 * sizeof(Bvh4Node), cudaMemcpyHostToDevice, st));
+    LBVH_CHECK(cudaStreamSynchronize(st));
+    r->n_nodes4 = n4; r->depth4 = d4;
+    return 0;
+}
+
 void lbvh_free(LbvhResult *r) {
+    if (r->nodes4) cudaFree(r->nodes4);
+    r->nodes4 = nullptr; r->n_nodes4 = 0; r->depth4 = 0;
     if (r->nodes) cudaFree(r->nodes);
     if (r->shade) cudaFree(r->shade);
     if (r->tri_slot) cudaFree(r->tri_slot);
@@ -353,6 +422,7 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
                const DevInstance *, const DevMesh *, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st) {
     out->shade = nullptr; out->tri_slot = nullptr;
     out->nodes = nullptr; out->tris = nullptr; out->n_nodes = 0; out->n_tris = n_tris; out->root = 0; out->max_depth = 1; out->bytes = 0;
+    out->nodes4 = nullptr; out->n_nodes4 = 0; out->depth4 = 0;
     if (n_tris == 0 || n_instances == 0) return (int)cudaErrorInvalidValue;
     const uint32_t nt = n_tris, ntblocks = (nt + 255) / 256;
 

@@ -18,7 +18,11 @@
 // Every path owns one sample slot, so radiance accumulation needs no atomics and is deterministic.
 // All per-path state is SoA float4 (coalesced 16-B lanes); live paths are kept dense by compaction.
 #include "bvh_traverse.cuh"
+#include "bvh_dynfetch.cuh"
 #include "kernels.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace b200pt {
 
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(256) k_raygen(DevConfig cfg, const DevDispatch
         ps.thr_depth[j] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(inside ? 0u : PT_MAX_DEPTH));
         ps.rad_slot[j] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(j));
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[0] = n; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; ctrl[4] = 0; ctrl[5] = 0; atomicAdd(&ctr->paths, (unsigned long long)n); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[0] = n; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; ctrl[4] = 0; ctrl[5] = 0; ctrl[8] = 0; ctrl[9] = 0; ctrl[10] = 0; ctrl[11] = 0; atomicAdd(&ctr->paths, (unsigned long long)n); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
     else bv = global_bvh(sc);
     const uint32_t n = ctrl[parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) {                              // counters of the NEXT bounce (last used two bounces ago)
-        ctrl[parity ^ 1u] = 0; ctrl[2u + 2u * (parity ^ 1u)] = 0; ctrl[3u + 2u * (parity ^ 1u)] = 0;
+        ctrl[parity ^ 1u] = 0; ctrl[2u + 2u * (parity ^ 1u)] = 0; ctrl[3u + 2u * (parity ^ 1u)] = 0; ctrl[8u + (parity ^ 1u)] = 0; ctrl[10u + (parity ^ 1u)] = 0;
     }
     unsigned long long *q_count = reinterpret_cast<unsigned long long *>(ctrl + 2u + 2u * parity);   // {hit count (low), miss count (high)}, 8-byte aligned
     const uint32_t lane = threadIdx.x & 31u;
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
             float4 o4n = make_float4(0, 0, 0, 0), d4n = o4n;
             if (it + 1u < K && i + blockDim.x < n) { o4n = ps.org_pdf[i + blockDim.x]; d4n = ps.dir_rng[i + blockDim.x]; }   // software pipelining of the state loads
             if (active) {
-                const float3 rd = normalize(f3(d4));                        // SH/RayGen.slang:70
+                const float3 rd = normalize_ray(f3(d4));                    // SH/RayGen.slang:70
                 HitRec h;
                 hit = bvh_trace<SMEM, false, false, false, !PRIMARY>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
                 so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
 // ------------------------------------------------------------------------------------------------
 // k_connect : shadow queries + SH/RayGen.slang:92-113 + stream compaction of the survivors
 // ------------------------------------------------------------------------------------------------
-template <bool SMEM>
+template <bool SMEM, bool TRACE>   // TRACE = false: k_shadow_dyn already cleared the request bits of occluded rays; only the join / roulette / compaction runs here
 __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, PathState src, PathState dst, ShadeOut so,
                                                   uint32_t *__restrict__ ctrl, uint32_t parity, const uint32_t *__restrict__ q_hit,
                                                   float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry,
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
     const int stride = blockDim.x;
     BvhView bv;
-    if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
+    if (SMEM && TRACE) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
     else bv = global_bvh(sc);
     const uint32_t n = ctrl[2u + 2u * parity];                               // paths that hit a surface this bounce (misses ended in k_shade_miss)
     uint32_t *n_next_ptr = ctrl + (parity ^ 1u);
@@ -404,7 +408,12 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
             //   light (:171-176 + :360-372): the closest hit must be the sampled triangle.  Equivalent occlusion form: the ray hits
             //         that triangle at tL and nothing lies in front of it (ties at tL resolve to the lower triangle id, exactly like
             //         the closest-hit query) -- bounded by tL and free to stop at the first occluder.
-            n_shadow += (pending & 1u) + (pending >> 1);
+            if (TRACE) n_shadow += (pending & 1u) + (pending >> 1);
+            if (!TRACE) {                                                   // surviving bits = unoccluded requests, joined in the reference's order
+                if (pending & 1u) emitted = emitted + f3(so.sky_c[i]);
+                if (pending & 2u) emitted = emitted + f3(so.lit_c[i]);
+                pending = 0u;
+            }
             float4 so4 = make_float4(0, 0, 0, 0), sd4 = so4;
             if (pending & 1u) { so4 = so.sky_o[i]; sd4 = so.sky_d[i]; }
             if (pending & 1u) {
@@ -469,6 +478,169 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
                 if (newDflags >> 31) { dst.medium[k] = src.medium[i]; dst.medium_g[k] = src.medium_g[i]; }
             }
         }
+    }
+    for (int o = 16; o > 0; o >>= 1) n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o);
+    if (lane == 0 && n_shadow) atomicAdd(&ctr->shadow_rays, (unsigned long long)n_shadow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_extend_dyn / k_shadow_dyn : the traversal kernels for scenes whose BVH does not fit in shared memory (bvh_dynfetch.cuh).
+//   control block additions: ctrl[8+p] = fetch counter of k_extend_dyn, ctrl[10+p] = fetch counter of k_shadow_dyn (p = bounce parity)
+// ------------------------------------------------------------------------------------------------
+template <bool SMEM, bool PRIMARY, bool WIDE>   // WIDE: BVH4 nodes (sc.nodes4) instead of the BVH2
+__global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, ShadeOut so, uint32_t *__restrict__ ctrl, uint32_t parity,
+                                                     uint32_t *__restrict__ q_hit, uint32_t *__restrict__ q_miss, int max_stack, int thresh,
+                                                     WaveCounters *ctr) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
+    stack[0] = DYN_DONE;
+    BvhView bv;
+    if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)(max_stack + 1) * blockDim.x * sizeof(int), &bar);
+    else bv = global_bvh(sc);
+    const uint32_t n = ctrl[parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                              // counters of the NEXT bounce (last used two bounces ago)
+        const uint32_t q = parity ^ 1u;
+        ctrl[q] = 0; ctrl[2u + 2u * q] = 0; ctrl[3u + 2u * q] = 0; ctrl[8u + q] = 0; ctrl[10u + q] = 0;
+        atomicAdd(&ctr->extend_rays, (unsigned long long)n);
+    }
+    unsigned long long *q_count = reinterpret_cast<unsigned long long *>(ctrl + 2u + 2u * parity);
+    uint32_t *fetch = ctrl + 8u + parity;
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint32_t s_base = smem_u32(stack), s_step = blockDim.x * 4u, s_limit = s_base + (uint32_t)(max_stack + 1) * s_step;
+    DynPool pool; pool.init(n, gridDim.x * (blockDim.x >> 5));
+    DynRay r; r.cur = DYN_DONE; r.gid = DYN_NONE; r.t = 0.0f; r.u = 0.0f; r.v = 0.0f; r.s_top = s_base; r.n_spill = 0;
+    int spill[WIDE ? DYN_SPILL : 1];
+    const float4 *nodes4 = reinterpret_cast<const float4 *>(sc.nodes4);
+    if (WIDE) bv.root = 0;                                                  // the BVH4 root is node 0 (bvh4_collapse_host)
+    uint32_t i = DYN_NONE;
+    while (true) {
+        // ---- commit finished rays: hit record + hit / miss queue entry (one 64-bit atomic per refill event)
+        const bool fin = (r.cur == DYN_DONE);
+        const bool have = fin && i != DYN_NONE;
+        const bool hit = have && r.gid != DYN_NONE;
+        if (have) so.hit[i] = make_float4(hit ? r.t : -1.0f, r.u, r.v, __uint_as_float(r.gid));
+        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, have && !hit);
+        if (bh | bm) {
+            unsigned long long base = 0ull;
+            if (lane == 0) base = atomicAdd(q_count, ((unsigned long long)__popc(bm) << 32) | (unsigned long long)__popc(bh));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (hit) q_hit[(uint32_t)base + (uint32_t)__popc(bh & lt)] = i;
+            else if (have) q_miss[(uint32_t)(base >> 32) + (uint32_t)__popc(bm & lt)] = i;
+        }
+        // ---- refill
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, fin);
+        if (need) {
+            const uint32_t idx = pool.take(need, lane, fetch);
+            if (fin) {
+                i = idx;
+                if (i != DYN_NONE) {
+                    const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
+                    const float3 rd = normalize_ray(f3(d4));                // SH/RayGen.slang:70
+                    dyn_init(r, f3(o4), rd, 0.01f, 100000.0f, 100000.0f, DYN_NONE, bv.root, s_base, s_step);   // :71-72
+                }
+            }
+        }
+        uint32_t act = __ballot_sync(0xFFFFFFFFu, r.cur != DYN_DONE);
+        if (act == 0u) break;                                               // nobody got a ray: the bounce is drained
+        const int thr_now = pool.empty() ? 1 : thresh;
+        do {
+            if (WIDE) { while (r.cur >= 0) dyn_node4_step<!PRIMARY>(nodes4, r, s_step, s_limit, spill); }
+            else { while (r.cur >= 0) dyn_node_step<SMEM, !PRIMARY>(bv, r, s_step, s_limit); }
+            __syncwarp();
+            while (r.cur < 0 && r.cur != DYN_DONE) dyn_leaf_step<SMEM, false, WIDE>(bv, r, s_step, spill);
+            act = __ballot_sync(0xFFFFFFFFu, r.cur != DYN_DONE);
+        } while (__popc(act) >= thr_now);
+    }
+}
+
+// Shadow requests of the hit queue, compacted per warp: ring entry = (path index << 1) | kind (0 sky, 1 light).
+// An occluded ray clears its request bit in e0.w (bit 29 sky, bit 30 light); k_connect<.., false> joins the surviving requests.
+constexpr size_t DYN_RING_BYTES = 8 * 128 * sizeof(uint32_t);              // per-CTA request rings of k_shadow_dyn (dynamic shared memory, after the stacks)
+template <bool SMEM, bool WIDE>
+__global__ void __launch_bounds__(256, 4) k_shadow_dyn(DevScene sc, ShadeOut so, uint32_t *__restrict__ ctrl, uint32_t parity,
+                                                     const uint32_t *__restrict__ q_hit, int max_stack, int thresh, WaveCounters *ctr) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
+    stack[0] = DYN_DONE;
+    const size_t stack_bytes = (size_t)(max_stack + 1) * blockDim.x * sizeof(int);
+    uint32_t *ring_all = reinterpret_cast<uint32_t *>(smem + stack_bytes);  // 128 entries per warp
+    BvhView bv;
+    if (SMEM) bv = stage_bvh_smem(sc, smem + stack_bytes + DYN_RING_BYTES, &bar);
+    else bv = global_bvh(sc);
+    const uint32_t n = ctrl[2u + 2u * parity];                               // hit-queue length of this bounce
+    uint32_t *fetch = ctrl + 10u + parity;
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    uint32_t *ring = ring_all + (threadIdx.x >> 5) * 128u;
+    const uint32_t s_base = smem_u32(stack), s_step = blockDim.x * 4u, s_limit = s_base + (uint32_t)(max_stack + 1) * s_step;
+    DynPool pool; pool.init(n, gridDim.x * (blockDim.x >> 5));
+    DynRay r; r.cur = DYN_DONE; r.s_top = s_base; r.gid = DYN_NONE; r.t = 0.0f; r.n_spill = 0;
+    int spill[WIDE ? DYN_SPILL : 1];
+    const float4 *nodes4 = reinterpret_cast<const float4 *>(sc.nodes4);
+    if (WIDE) bv.root = 0;
+    uint32_t head = 0, tail = 0;                                            // warp-uniform ring cursors
+    uint32_t n_shadow = 0;
+    while (true) {
+        const bool fin = (r.cur == DYN_DONE);
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, fin);
+        const uint32_t cnt = (uint32_t)__popc(need);
+        // ---- top the ring up with the requests of the next 32 hit-queue entries until it covers the idle lanes
+        while (tail - head < cnt && !pool.empty()) {
+            const uint32_t j = pool.take(0xFFFFFFFFu, lane, fetch);
+            uint32_t pend = 0, i = 0;
+            if (j != DYN_NONE) { i = q_hit[j]; pend = (__float_as_uint(so.e0[i].w) >> 29) & 3u; }
+            const uint32_t c = (pend & 1u) + (pend >> 1);
+            uint32_t incl = c;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += y; }
+            uint32_t w = tail + incl - c;
+            if (pend & 1u) { ring[w & 127u] = i << 1; w++; }
+            if (pend & 2u) ring[w & 127u] = (i << 1) | 1u;
+            tail += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            n_shadow += c;
+            __syncwarp();
+        }
+        // ---- hand requests to the idle lanes
+        if (fin) {
+            const uint32_t rank = (uint32_t)__popc(need & lt);
+            if (rank < tail - head) {
+                const uint32_t e = ring[(head + rank) & 127u];
+                const uint32_t i = e >> 1;
+                if (e & 1u) {                                               // light: SH/ClosestHit.slang:171-176 in its bounded any-hit form (k_connect)
+                    const float4 lo4 = so.lit_o[i], ld4_ = so.lit_d[i];
+                    const uint32_t lgid = __float_as_uint(ld4_.w);
+                    const float4 *tp = bv.tris + (size_t)__ldg(sc.tri_slot + lgid) * 3;
+                    const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
+                    float tL, uL, vL;
+                    if (tri_test(f3(ta), f3(tb), f3(tc), f3(lo4), f3(ld4_), 0.0001f, 1000000.0f, tL, uL, vL)) {
+                        dyn_init(r, f3(lo4), f3(ld4_), 0.0001f, tL, __uint_as_float(__float_as_uint(tL) + 1u), lgid, bv.root, s_base, s_step);
+                        r.gid = e;
+                    } else {
+                        atomicAnd(reinterpret_cast<unsigned int *>(&so.e0[i].w), ~(1u << 30));
+                    }
+                } else {                                                    // sky: SH/ClosestHit.slang:139 -- any hit in (1e-4, 1e6) occludes
+                    const float4 so4 = so.sky_o[i], sd4 = so.sky_d[i];
+                    dyn_init(r, f3(so4), f3(sd4), 0.0001f, 1000000.0f, 1000000.0f, DYN_NONE, bv.root, s_base, s_step);
+                    r.gid = e;
+                }
+            }
+        }
+        { const uint32_t avail = tail - head; head += cnt < avail ? cnt : avail; }
+        __syncwarp();
+        uint32_t act = __ballot_sync(0xFFFFFFFFu, r.cur != DYN_DONE);
+        if (act == 0u) { if (tail == head && pool.empty()) break; else continue; }
+        const int thr_now = (tail == head && pool.empty()) ? 1 : thresh;
+        do {
+            if (WIDE) { while (r.cur >= 0) dyn_node4_step<true>(nodes4, r, s_step, s_limit, spill); }
+            else { while (r.cur >= 0) dyn_node_step<SMEM, true>(bv, r, s_step, s_limit); }
+            __syncwarp();
+            while (r.cur < 0 && r.cur != DYN_DONE) {
+                if (dyn_leaf_step<SMEM, true, WIDE>(bv, r, s_step, spill))  // occluded: drop the request
+                    atomicAnd(reinterpret_cast<unsigned int *>(&so.e0[r.gid >> 1].w), ~(1u << (29u + (r.gid & 1u))));
+            }
+            act = __ballot_sync(0xFFFFFFFFu, r.cur != DYN_DONE);
+        } while (__popc(act) >= thr_now);
     }
     for (int o = 16; o > 0; o >>= 1) n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o);
     if (lane == 0 && n_shadow) atomicAdd(&ctr->shadow_rays, (unsigned long long)n_shadow);
@@ -563,6 +735,7 @@ __global__ void __launch_bounds__(256) k_trace_rays(DevScene sc, uint32_t n, con
 // ------------------------------------------------------------------------------------------------
 // host-callable launchers
 // ------------------------------------------------------------------------------------------------
+static constexpr size_t DYN_RING_BYTES_HOST = 8 * 128 * sizeof(uint32_t);
 static size_t trace_smem_bytes(const DevScene &sc, int max_stack, int threads, bool smem) {
     return (size_t)max_stack * threads * sizeof(int) + (smem ? sc.bvh_bytes : 0);
 }
@@ -570,20 +743,26 @@ static size_t trace_smem_bytes(const DevScene &sc, int max_stack, int threads, b
 static bool g_attr_done = false;
 static void set_attrs_once() {
     if (g_attr_done) return;
-    const int maxb = 227 * 1024;
-    cudaFuncSetAttribute(k_extend<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    cudaFuncSetAttribute(k_extend<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    cudaFuncSetAttribute(k_extend<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    cudaFuncSetAttribute(k_extend<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    cudaFuncSetAttribute(k_connect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    cudaFuncSetAttribute(k_connect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    cudaFuncSetAttribute(k_trace_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
-    cudaFuncSetAttribute(k_trace_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb);
+    // opt-in dynamic shared memory: the 227 KB per-CTA limit covers static + dynamic, so each kernel gets 227 KB minus its static part
+    auto optin = [](const void *f) {
+        cudaFuncAttributes a{};
+        if (cudaFuncGetAttributes(&a, f) != cudaSuccess) return;
+        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)a.sharedSizeBytes);
+    };
+    optin((const void *)k_extend<true, true>); optin((const void *)k_extend<true, false>);
+    optin((const void *)k_extend<false, true>); optin((const void *)k_extend<false, false>);
+    optin((const void *)k_connect<true, true>); optin((const void *)k_connect<false, true>); optin((const void *)k_connect<false, false>);
+    optin((const void *)k_extend_dyn<true, true, false>); optin((const void *)k_extend_dyn<true, false, false>);
+    optin((const void *)k_extend_dyn<false, true, false>); optin((const void *)k_extend_dyn<false, false, false>);
+    optin((const void *)k_extend_dyn<false, true, true>); optin((const void *)k_extend_dyn<false, false, true>);
+    optin((const void *)k_shadow_dyn<true, false>); optin((const void *)k_shadow_dyn<false, false>); optin((const void *)k_shadow_dyn<false, true>);
+    optin((const void *)k_trace_rays<true>); optin((const void *)k_trace_rays<false>);
+    cudaGetLastError();
     g_attr_done = true;
 }
 
 // grid sizing: persistent grids = SM count x resident CTAs per SM for the chosen shared-memory footprint
-int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc) {
+int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, LaunchCfg *lc) {
     set_attrs_once();
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceProp prop; cudaError_t e = cudaGetDeviceProperties(&prop, dev);
@@ -592,20 +771,56 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, LaunchCfg *lc) {
     lc->max_stack = bvh_max_depth + 2; if (lc->max_stack < 4) lc->max_stack = 4; if (lc->max_stack > 64) lc->max_stack = 64;
     lc->bvh_in_smem = sc.bvh_bytes > 0 && sc.bvh_bytes <= 64u * 1024u && (sc.bvh_bytes % 16u) == 0;
     const size_t sh = trace_smem_bytes(sc, lc->max_stack, 256, lc->bvh_in_smem);
-    int occ_e = 0, occ_c = 0, occ_s = 0;
-    if (lc->bvh_in_smem) {
+    // traversal shape: dynamic-fetch while-while kernels (bvh_dynfetch.cuh) over the BVH4 when the BVH lives in L2/HBM, one ray per thread
+    // over the BVH2 when the whole BVH sits in shared memory (tiny scenes: no divergence or latency to recover).
+    // Overrides: B200PT_TRAV=classic|dyn, B200PT_WIDE=0|1, B200PT_DYN_THRESH=1..32, B200PT_WIDE_STACK=<shared-memory stack entries>.
+    lc->trav_dyn = !lc->bvh_in_smem;
+    if (const char *e = getenv("B200PT_TRAV")) { if (!strcmp(e, "dyn")) lc->trav_dyn = true; else if (!strcmp(e, "classic")) lc->trav_dyn = false; }
+    lc->dyn_thresh = 20;
+    if (const char *e = getenv("B200PT_DYN_THRESH")) { int v = atoi(e); if (v >= 1 && v <= 32) lc->dyn_thresh = v; }
+    lc->wide = lc->trav_dyn && !lc->bvh_in_smem && sc.nodes4 != nullptr && sc.bvh_bytes >= (8u << 20);   // small BVHs stay L1/L2-hot: BVH2 is cheaper there (profiles/r01_variants.txt)
+    if (const char *e = getenv("B200PT_WIDE")) { if (atoi(e) == 1 && lc->trav_dyn && !lc->bvh_in_smem && sc.nodes4 != nullptr) lc->wide = true; }
+    if (const char *e = getenv("B200PT_WIDE")) { if (atoi(e) == 0) lc->wide = false; }
+    lc->dyn_stack = lc->max_stack;                                          // BVH2: depth + 2 entries always suffice
+    if (lc->wide) {
+        const int need = 3 * bvh4_depth + 2;                                // worst case: three pushes per level
+        int cap = 24;
+        if (const char *e = getenv("B200PT_WIDE_STACK")) { int v = atoi(e); if (v >= 4 && v <= 96) cap = v; }
+        lc->dyn_stack = need < cap ? need : cap;
+        if (need - lc->dyn_stack > DYN_SPILL) lc->wide = false, lc->dyn_stack = lc->max_stack;   // deeper than shared column + overflow array: BVH2
+    }
+    const size_t sh_dyn = trace_smem_bytes(sc, lc->dyn_stack + 1, 256, lc->bvh_in_smem);
+    int occ_e = 0, occ_c = 0, occ_s = 0, occ_sh = 0;
+    if (lc->trav_dyn) {
+        if (lc->wide) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend_dyn<false, false, true>, 256, sh_dyn);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sh, k_shadow_dyn<false, true>, 256, sh_dyn + DYN_RING_BYTES_HOST);
+        } else if (lc->bvh_in_smem) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend_dyn<true, false, false>, 256, sh_dyn);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sh, k_shadow_dyn<true, false>, 256, sh_dyn + DYN_RING_BYTES_HOST);
+        } else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend_dyn<false, false, false>, 256, sh_dyn);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sh, k_shadow_dyn<false, false>, 256, sh_dyn + DYN_RING_BYTES_HOST);
+        }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<false, false>, 256, 0);
+    } else if (lc->bvh_in_smem) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<true, false>, 256, sh);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<true>, 256, sh);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<true, true>, 256, sh);
     } else {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<false, false>, 256, sh);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<false>, 256, sh);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<false, true>, 256, sh);
     }
+    if (occ_sh < 1) occ_sh = 1;
+    lc->grid_shadow = sms * occ_sh;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade_hit, 128, 0);
     if (occ_e < 1) occ_e = 1; if (occ_c < 1) occ_c = 1; if (occ_s < 1) occ_s = 1;
     lc->grid_extend = sms * occ_e; lc->grid_connect = sms * occ_c;
     lc->grid_trace = sms * occ_e;
     lc->grid_shade = sms * occ_s;
     lc->grid_light = sms * 8;
+    if (getenv("B200PT_DEBUG"))
+        fprintf(stderr, "[b200pt] launch cfg: bvh depth %d (bvh4 %d) max_stack %d dyn_stack %d bvh_bytes %u smem %d dyn %d wide %d thresh %d | CTAs/SM extend %d connect %d shadow %d shade %d\n",
+                bvh_max_depth, bvh4_depth, lc->max_stack, lc->dyn_stack, sc.bvh_bytes, (int)lc->bvh_in_smem, (int)lc->trav_dyn, (int)lc->wide, lc->dyn_thresh, occ_e, occ_c, occ_sh, occ_s);
     return 0;
 }
 
@@ -617,6 +832,15 @@ void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeO
                    WaveCounters *ctr, bool primary, cudaStream_t st) {
     set_attrs_once();
     const bool smem = lc.bvh_in_smem;
+    if (lc.trav_dyn) {
+        const size_t sh = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem);
+#define B200PT_EXT_DYN(S, P, W) k_extend_dyn<S, P, W><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.dyn_stack, lc.dyn_thresh, ctr)
+        if (lc.wide) { if (primary) B200PT_EXT_DYN(false, true, true); else B200PT_EXT_DYN(false, false, true); }
+        else if (smem) { if (primary) B200PT_EXT_DYN(true, true, false); else B200PT_EXT_DYN(true, false, false); }
+        else { if (primary) B200PT_EXT_DYN(false, true, false); else B200PT_EXT_DYN(false, false, false); }
+#undef B200PT_EXT_DYN
+        return;
+    }
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
     if (smem) {
         if (primary) k_extend<true, true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
@@ -635,9 +859,17 @@ void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cf
                     uint32_t *ctrl, uint32_t parity, const uint32_t *q_hit, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
     set_attrs_once();
     const bool smem = lc.bvh_in_smem;
+    if (lc.trav_dyn) {                                                      // shadow rays in their own dynamic-fetch kernel, then the join without tracing
+        const size_t shd = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem) + DYN_RING_BYTES_HOST;
+#define B200PT_SH_DYN(S, W) k_shadow_dyn<S, W><<<lc.grid_shadow, 256, shd, st>>>(sc, so, ctrl, parity, q_hit, lc.dyn_stack, lc.dyn_thresh, ctr)
+        if (lc.wide) B200PT_SH_DYN(false, true); else if (smem) B200PT_SH_DYN(true, false); else B200PT_SH_DYN(false, false);
+#undef B200PT_SH_DYN
+        k_connect<false, false><<<lc.grid_connect, 256, 0, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
+        return;
+    }
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_connect<true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
-    else k_connect<false><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
+    if (smem) k_connect<true, true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
+    else k_connect<false, true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
 }
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
                     const float4 *sample_buf, float4 *image, cudaStream_t st) {
