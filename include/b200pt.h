@@ -29,7 +29,7 @@ extern "C" {
 #define B200PT_ERR_INIT_FAILED       -3      /* VK_ERROR_INITIALIZATION_FAILED: file/scene import failed */
 #define B200PT_ERR_OUT_OF_MEMORY     -2
 #define B200PT_ERR_WRONG_ARGUMENTS   -15000  /* custom range of Error.h */
-#define B200PT_ERR_NOT_IMPLEMENTED   -15001  /* volumes / atmosphere API (out of scope) */
+#define B200PT_ERR_NOT_IMPLEMENTED   -15001  /* NanoVDB volume data / atmosphere API */
 #define B200PT_ERR_NO_SCENE          -15002
 #define B200PT_ERR_CUDA              -15003
 #define B200PT_ERR_NO_DEVICE         -15004  /* no CUDA device: the product has no CPU fallback */
@@ -123,8 +123,35 @@ int32_t b200pt_camera_from_view(const float view[16], float aspect, float view_i
 int32_t b200pt_resize(b200pt_handle h, uint32_t width, uint32_t height);   /* ResizeImage */
 int32_t b200pt_get_size(b200pt_handle h, uint32_t *width, uint32_t *height);
 int32_t b200pt_reset(b200pt_handle h);                                      /* ResetPathTracing */
-/* volumes (PathTracer.h:157-166): out of scope -> B200PT_ERR_NOT_IMPLEMENTED */
-int32_t b200pt_add_volume(b200pt_handle h, const void *volume);
+/* ---- volumes: PathTracer::AddVolume / RemoveVolume / SetVolume / GetVolumes / SetPhaseFunction (PathTracer.h:36-81,157-166,
+ * PathTracer.cpp:1334-1345,1518-1555).  Homogeneous AABB volumes are implemented (SH/Volume.slang with m_DensityDataIndex == -1,
+ * SH/RayGen.slang:162-380): free-flight sampling against the geometry distance, phase-function scattering with sky / light NEE, and
+ * analytic transmittance on the NEE terms of surface hits.  Heterogeneous (NanoVDB) density / temperature data is not:
+ * DensityDataIndex must be -1 and b200pt_add_density_data_to_volume returns B200PT_ERR_NOT_IMPLEMENTED.  At most B200PT_MAX_VOLUMES. */
+#define B200PT_MAX_VOLUMES 16
+typedef struct {                         /* PathTracer::Volume, PT/PathTracer.h:36-70 (defaults in comments) */
+    float CornerMin[3], CornerMax[3];    /* AABB in world space (-1 / +1)      */
+    float Color[3];                      /* scattering albedo (0.8)            */
+    float EmissiveColor[3];              /* (0)                                */
+    float Density;                       /* extinction coefficient (1)         */
+    float Anisotropy;                    /* g of Henyey-Greenstein / Draine (0)*/
+    float Alpha;                         /* Draine alpha (1)                   */
+    float DropletSize;                   /* HG + Draine fit, micrometres (20)  */
+    int32_t DensityDataIndex;            /* -1 = homogeneous (only value accepted) */
+    uint32_t ApproximatedScatteringForClouds; /* anisotropy decays with the volume depth (0) */
+    float ApproximatedScatteringFalloff; /* (0.8) unused by homogeneous volumes */
+    uint32_t _reserved;
+} b200pt_volume;
+int32_t b200pt_default_volume(b200pt_volume *out);
+int32_t b200pt_add_volume(b200pt_handle h, const b200pt_volume *volume);                 /* AddVolume  -> ResetPathTracing() */
+int32_t b200pt_set_volume(b200pt_handle h, uint32_t index, const b200pt_volume *volume); /* SetVolume  -> ResetPathTracing() */
+int32_t b200pt_remove_volume(b200pt_handle h, uint32_t index);                           /* RemoveVolume (later volumes move down one index) */
+int32_t b200pt_volume_count(b200pt_handle h, uint32_t *out);
+int32_t b200pt_get_volume(b200pt_handle h, uint32_t index, b200pt_volume *out);          /* GetVolumes()[index] */
+int32_t b200pt_add_density_data_to_volume(b200pt_handle h, uint32_t index, const char *vdb_path);   /* AddDensityDataToVolume: NOT_IMPLEMENTED */
+/* PathTracer::SetPhaseFunction (PathTracer.h:76-81,168-169): 0 Henyey-Greenstein, 1 Draine, 2 Henyey-Greenstein + Draine */
+int32_t b200pt_set_phase_function(b200pt_handle h, uint32_t phase_function);
+int32_t b200pt_get_phase_function(b200pt_handle h, uint32_t *out);
 
 /* ---- image-tile partition across GPUs (no reference equivalent) ----
  * rank r of `world` owns rows y with ((y / band_rows) % world) == r.  RNG streams are keyed on global pixel

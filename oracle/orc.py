@@ -30,6 +30,12 @@ class OrcSceneDesc(C.Structure):
                 ("lut_reflect", C.c_void_p), ("lut_refract_out", C.c_void_p), ("lut_refract_in", C.c_void_p)]
 
 
+class OrcVolume(C.Structure):
+    _fields_ = [("CornerMin", C.c_float * 3), ("CornerMax", C.c_float * 3), ("Color", C.c_float * 3), ("EmissiveColor", C.c_float * 3),
+                ("Density", C.c_float), ("Anisotropy", C.c_float), ("Alpha", C.c_float), ("DropletSize", C.c_float),
+                ("ApproximatedScattering", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 class OrcConfig(C.Structure):
     _fields_ = [("ViewInverse", C.c_float * 16), ("ProjectionInverse", C.c_float * 16),
                 ("SampleCount", C.c_uint32), ("MaxDepth", C.c_uint32),
@@ -37,7 +43,8 @@ class OrcConfig(C.Structure):
                 ("SkyRotationAzimuth", C.c_float), ("SkyRotationAltitude", C.c_float), ("EnvironmentIntensity", C.c_float),
                 ("EmissiveMeshSamplingPDFBias", C.c_float), ("ScreenSplitCount", C.c_uint32),
                 ("EnableSkyMIS", C.c_uint32), ("EnableMeshMIS", C.c_uint32), ("ShowEnvMapDirectly", C.c_uint32),
-                ("UseOnlyGeometryNormals", C.c_uint32), ("UseEnergyCompensation", C.c_uint32), ("FurnaceTestMode", C.c_uint32)]
+                ("UseOnlyGeometryNormals", C.c_uint32), ("UseEnergyCompensation", C.c_uint32), ("FurnaceTestMode", C.c_uint32),
+                ("PhaseFunction", C.c_uint32), ("VolumesCount", C.c_uint32), ("Volumes", C.c_void_p)]
 
 
 class OrcCounters(C.Structure):
@@ -131,12 +138,33 @@ def camera_from_view(view16, aspect):
     return vi, pi
 
 
+VOLUME_DEFAULTS = dict(CornerMin=(-1.0, -1.0, -1.0), CornerMax=(1.0, 1.0, 1.0), Color=(0.8, 0.8, 0.8), EmissiveColor=(0.0, 0.0, 0.0),
+                       Density=1.0, Anisotropy=0.0, Alpha=1.0, DropletSize=20.0, ApproximatedScattering=0)   # PT/PathTracer.h:36-70
+
+
+def set_volumes(cfg, volumes):
+    """Attach homogeneous AABB volumes (list of dicts with the VOLUME_DEFAULTS keys) to an OrcConfig; the array is kept alive on cfg."""
+    arr = (OrcVolume * max(1, len(volumes)))()
+    for i, v in enumerate(volumes):
+        d = dict(VOLUME_DEFAULTS); d.update(v)
+        for k in ("CornerMin", "CornerMax", "Color", "EmissiveColor"):
+            for j in range(3): getattr(arr[i], k)[j] = float(d[k][j])
+        for k in ("Density", "Anisotropy", "Alpha", "DropletSize"): setattr(arr[i], k, float(d[k]))
+        arr[i].ApproximatedScattering = int(d["ApproximatedScattering"])
+    cfg._volumes_keepalive = arr
+    cfg.Volumes = C.cast(arr, C.c_void_p).value if volumes else None
+    cfg.VolumesCount = len(volumes)
+    return cfg
+
+
 def default_config(**kw):
     c = OrcConfig()
     lib().orc_default_config(C.byref(c))
     for k, v in kw.items():
         if k in ("ViewInverse", "ProjectionInverse"):
             for i in range(16): getattr(c, k)[i] = float(v[i])
+        elif k == "Volumes":
+            set_volumes(c, v)
         else:
             setattr(c, k, v)
     return c

@@ -357,6 +357,7 @@ typedef struct {
     v3 Origin, Direction, BxDF; float PDF; v3 Emitted;
     uint32_t Depth; Rng Sampler;
     int InMedium; float MediumDensity, MediumAnisotropy; v3 MediumColor, MediumEmissiveColor;
+    int VolumeDepth;                                                            /* SH/RTCommon.slang Payload::VolumeDepth, reset per sample (SH/RayGen.slang:61) */
 } Payload;
 
 static inline float power_heuristic(float a, float b) { return (a * a) / ((a * a) + (b * b)); } /* SH/RTCommon.slang:124-127 */
@@ -849,6 +850,201 @@ static int does_ray_intersect(const OrcScene *sc, v3 o, v3 d, uint32_t *tri, uin
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Homogeneous AABB volumes: SH/Volume.slang (the m_DensityDataIndex == -1 paths), SH/RayGen.slang:162-380,
+ * phase functions SH/RTCommon.slang:214-227 and their samplers SH/Sampler.slang:169-284.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { float Near, Far; } VolIsect;
+/* SH/Volume.slang:188-211 (the y/z mix-up of the max/min chains is the reference's) */
+static VolIsect vol_intersect(v3 o, v3 d, const float mn[3], const float mx[3]) {
+    v3 inv = V3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    v3 t0 = v3mul(v3sub(V3(mn[0], mn[1], mn[2]), o), inv), t1 = v3mul(v3sub(V3(mx[0], mx[1], mx[2]), o), inv);
+    v3 ts = V3(fminf(t0.x, t1.x), fminf(t0.y, t1.y), fminf(t0.z, t1.z)), tb = V3(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y), fmaxf(t0.z, t1.z));
+    float tmin = fmaxf(fmaxf(ts.x, ts.y), fmaxf(ts.x, ts.z));
+    float tmax = fminf(fminf(tb.x, tb.y), fminf(tb.x, tb.z));
+    VolIsect r = { tmin, tmax };
+    if (tmax < 0.0f || tmin > tmax) { r.Near = -1.0f; r.Far = -1.0f; }
+    return r;
+}
+/* SH/Volume.slang:150-156 */
+static float vol_effective_anisotropy(const OrcVolume *v, float rayDepth) {
+    if (v->ApproximatedScattering != 0) {
+        float sg = v->Anisotropy > 0.0f ? 1.0f : (v->Anisotropy < 0.0f ? -1.0f : 0.0f);
+        return powf(fabsf(v->Anisotropy), 1.0f + rayDepth) * sg;
+    }
+    return v->Anisotropy;
+}
+/* SH/RTCommon.slang:214-221 */
+static float phase_hg(v3 V, v3 L, float g) {
+    if (g == 0.0f) return 1.0f / (4.0f * ORC_PI);
+    float c = v3dot(V, L);
+    return (1.0f / (4.0f * ORC_PI)) * ((1.0f - g * g) / powf(1.0f + g * g - 2.0f * g * c, 1.5f));
+}
+/* SH/RTCommon.slang:223-228 */
+static float phase_draine(v3 V, v3 L, float g, float a) {
+    float c = v3dot(V, L);
+    return ((1.0f - g * g) * (1.0f + a * c * c)) / (4.0f * (1.0f + (a * (1.0f + 2.0f * g * g)) / 3.0f) * ORC_PI * powf(1.0f + g * g - 2.0f * g * c, 1.5f));
+}
+/* rotation of a tangent-space direction around the incident direction, shared tail of SH/Sampler.slang:183-192 / :265-274 */
+static v3 phase_frame(v3 incident, float cosTheta, float phi) {
+    float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+    v3 nd = V3(sinTheta * cosf(phi), sinTheta * sinf(phi), cosTheta);
+    v3 up = fabsf(incident.y) < 0.9999999f ? V3(0, 1, 0) : V3(0, 0, 1);
+    v3 tangent = v3normalize(v3cross(up, incident));
+    v3 bitangent = v3cross(incident, tangent);
+    return v3normalize(v3add(v3add(v3scale(tangent, nd.x), v3scale(bitangent, nd.y)), v3scale(incident, nd.z)));
+}
+/* SH/Sampler.slang:219-276 */
+static v3 rng_draine(Rng *r, v3 incident, float g, float a) {
+    float rx = rng_f(r), ry = rng_f(r);
+    float cosTheta;
+    if (fabsf(g) < 1e-5f) {
+        cosTheta = 2.0f * rx - 1.0f;
+    } else if (fabsf(a) < 1e-5f) {
+        float sqrTerm = (1.0f - g * g) / (1.0f - g + 2.0f * g * rx);
+        cosTheta = (1.0f + g * g - sqrTerm * sqrTerm) / (2.0f * g);
+    } else {
+        const float g2 = g * g, g3 = g * g2, g4 = g2 * g2, g6 = g2 * g4;
+        const float pgp1_2 = (1.0f + g2) * (1.0f + g2);
+        const float T1a = -a + a * g4;
+        const float T1a3 = T1a * T1a * T1a;
+        const float T2 = -1296.0f * (-1.0f + g2) * (a - a * g2) * (T1a) * (4.0f * g2 + a * pgp1_2);
+        const float T3 = 3.0f * g2 * (1.0f + g * (-1.0f + 2.0f * rx)) + a * (2.0f + g2 + g3 * (1.0f + 2.0f * g2) * (-1.0f + 2.0f * rx));
+        const float T4a = 432.0f * T1a3 + T2 + 432.0f * (a - a * g2) * T3 * T3;
+        const float T4b = -144.0f * a * g2 + 288.0f * a * g4 - 144.0f * a * g6;
+        const float T4b3 = T4b * T4b * T4b;
+        const float T4 = T4a + sqrtf(-4.0f * T4b3 + T4a * T4a);
+        const float T4p3 = powf(T4, 1.0f / 3.0f);
+        const float cbrt2 = powf(2.0f, 1.0f / 3.0f);
+        const float T6 = (2.0f * T1a + (48.0f * cbrt2 * (-(a * g2) + 2.0f * a * g4 - a * g6)) / T4p3 + T4p3 / (3.0f * cbrt2)) / (a - a * g2);
+        const float T5 = 6.0f * (1.0f + g2) + T6;
+        const float q = -0.5f * sqrtf(T5) + sqrtf(6.0f * (1.0f + g2) - (8.0f * T3) / (a * (-1.0f + g2) * sqrtf(T5)) - T6) / 2.0f;
+        cosTheta = (1.0f + g2 - q * q) / (2.0f * g);
+    }
+    return phase_frame(incident, cosTheta, 2.0f * ORC_PI * ry);
+}
+/* droplet-size fit of SH/Volume.slang:389-400 / SH/Sampler.slang:278-295 */
+static void hg_draine_fit(float d, float *GHG, float *GD, float *ALPHA_D, float *W_D) {
+    *GHG = expf(-(0.0990567f / (d - 1.67154f)));
+    *GD = expf(-(2.20679f / (d + 3.91029f)) - 0.428934f);
+    *ALPHA_D = expf(3.62489f - (8.29288f / (d + 5.52825f)));
+    *W_D = expf(-(0.599085f / (d - 0.641583f)) - 0.665888f);
+}
+/* Volume::GetScatteringDirection, SH/Volume.slang:354-371 */
+static v3 vol_scatter_direction(const OrcConfig *cfg, const OrcVolume *v, Rng *rng, v3 incident, int rayDepth) {
+    if (cfg->PhaseFunction == 0) return rng_henyey_greenstein(rng, incident, vol_effective_anisotropy(v, (float)rayDepth));
+    if (cfg->PhaseFunction == 1) return rng_draine(rng, incident, vol_effective_anisotropy(v, (float)rayDepth), v->Alpha);
+    float GHG, GD, AD, WD; hg_draine_fit(v->DropletSize, &GHG, &GD, &AD, &WD);          /* SH/Sampler.slang:278-295 */
+    GHG = powf(fmaxf(GHG, 0.0f), 1.0f + (float)rayDepth);
+    GD = powf(fmaxf(GD, 0.0f), 1.0f + (float)rayDepth);
+    float u = rng_f(rng);
+    if (u < WD) return rng_henyey_greenstein(rng, incident, GHG);
+    return rng_draine(rng, incident, GD, AD);
+}
+/* Volume::EvaluatePhaseFunction, SH/Volume.slang:373-401 (the HG+Draine evaluation ignores the depth, unlike its sampler) */
+static float vol_phase(const OrcConfig *cfg, const OrcVolume *v, v3 V, v3 L, int rayDepth) {
+    if (cfg->PhaseFunction == 0) return phase_hg(V, L, vol_effective_anisotropy(v, (float)rayDepth));
+    if (cfg->PhaseFunction == 1) return phase_draine(V, L, vol_effective_anisotropy(v, (float)rayDepth), v->Alpha);
+    float GHG, GD, AD, WD; hg_draine_fit(v->DropletSize, &GHG, &GD, &AD, &WD);
+    return orc_lerp(phase_hg(V, L, GHG), phase_draine(V, L, GD, AD), WD);
+}
+/* Volume::CalculateVolumesTransmittance, SH/Volume.slang:419-446: analytic for homogeneous volumes (no random numbers) */
+static float volumes_transmittance(const OrcConfig *cfg, v3 o, v3 d) {
+    float T = 1.0f;
+    for (uint32_t i = 0; i < cfg->VolumesCount; i++) {
+        const OrcVolume *v = &cfg->Volumes[i];
+        VolIsect is = vol_intersect(o, d, v->CornerMin, v->CornerMax);
+        is.Near = fmaxf(is.Near, 0.0f);
+        float len = is.Far - is.Near;
+        if (len > 0.0f) T *= expf(-v->Density * len);
+    }
+    return orc_clamp(T, 0.0f, 1.0f);
+}
+/* Volume::DoesRayScatterInVolume, SH/Volume.slang:254-289 (homogeneous branch: one random number when the ray crosses the box) */
+static float vol_scatter_distance(const OrcVolume *v, v3 o, v3 d, Rng *rng, float ignoreIfFartherThan) {
+    VolIsect is = vol_intersect(o, d, v->CornerMin, v->CornerMax);
+    if (is.Far < 0.0f) return -1.0f;
+    if (ignoreIfFartherThan >= 0.0f && is.Near > ignoreIfFartherThan) return -1.0f;
+    float inside = is.Far - fmaxf(is.Near, 0.0f);
+    if (inside <= 0.0f) return -1.0f;
+    float sampled = -logf(rng_f(rng)) / v->Density;                             /* SH/Sampler.slang:425-428 */
+    if (sampled < inside) return fmaxf(is.Near, 0.0f) + sampled;
+    return -1.0f;
+}
+static int does_ray_intersect(const OrcScene *sc, v3 o, v3 d, uint32_t *tri, uint32_t *inst, uint64_t *shadow_rays);
+static void sample_env(const OrcScene *sc, const OrcConfig *cfg, Rng *rng, v3 *toLight, v4 *outValue);
+static void sample_emissive(const OrcScene *sc, Rng *rng, v3 pos, v3 *toLight, v4 *colorPDF, uint32_t *tri, uint32_t *inst);
+/* EvaluateVolumeScatteringEvent, SH/RayGen.slang:265-380 */
+static void volume_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, float scatterDistance, int vi, OrcCounters *cnt) {
+    const OrcVolume *v = &cfg->Volumes[vi];
+    const v3 color = V3(v->Color[0], v->Color[1], v->Color[2]);
+    pl->Origin = v3add(pl->Origin, v3scale(pl->Direction, scatterDistance));
+    pl->Emitted = V3(v->EmissiveColor[0], v->EmissiveColor[1], v->EmissiveColor[2]);   /* + temperature emission: 0 without grid data */
+    v3 toSky = V3(0, 0, 0); v4 sky = { 0, 0, 0, 0 };
+    if (cfg->EnableSkyMIS) {
+        sample_env(sc, cfg, &pl->Sampler, &toSky, &sky);
+        sky.x *= cfg->EnvironmentIntensity; sky.y *= cfg->EnvironmentIntensity; sky.z *= cfg->EnvironmentIntensity;   /* :277 (Q7 again) */
+        uint32_t t0, t1;
+        if (does_ray_intersect(sc, pl->Origin, toSky, &t0, &t1, &cnt->shadow_rays)) { v4 z = { 0, 0, 0, 0 }; sky = z; }
+    }
+    v3 toLight = V3(0, 0, 0); v4 light = { 0, 0, 0, 0 };
+    if (cfg->EnableMeshMIS) {
+        uint32_t lt, li, ht, hi;
+        sample_emissive(sc, &pl->Sampler, pl->Origin, &toLight, &light, &lt, &li);
+        does_ray_intersect(sc, pl->Origin, toLight, &ht, &hi, &cnt->shadow_rays);       /* a miss leaves (0, 0): compared all the same, :301-302 */
+        if (ht != lt || hi != li) { v4 z = { 0, 0, 0, 0 }; light = z; }
+    }
+    const v3 newDir = vol_scatter_direction(cfg, v, &pl->Sampler, pl->Direction, pl->VolumeDepth);
+    const float phaseS = vol_phase(cfg, v, pl->Direction, newDir, pl->VolumeDepth);
+    if (cfg->EnableSkyMIS && sky.w > 0.0f) {
+        float ph = vol_phase(cfg, v, pl->Direction, toSky, pl->VolumeDepth);
+        float T = volumes_transmittance(cfg, pl->Origin, toSky);
+        v3 bx = v3scale(color, ph);
+        if (ph > 0.0f)
+            pl->Emitted = v3add(pl->Emitted, v3scale(v3mul(v3mul(v3s(T), bx), v3divs(V3(sky.x, sky.y, sky.z), sky.w)), power_heuristic(sky.w, ph)));
+    }
+    if (cfg->EnableMeshMIS && light.w > 0.0f) {
+        float ph = vol_phase(cfg, v, pl->Direction, toLight, pl->VolumeDepth);
+        float T = volumes_transmittance(cfg, pl->Origin, toLight);
+        v3 bx = v3scale(color, ph);
+        if (ph > 0.0f)
+            pl->Emitted = v3add(pl->Emitted, v3scale(v3mul(v3mul(v3s(T), bx), v3divs(V3(light.x, light.y, light.z), light.w)), power_heuristic(light.w, ph)));
+    }
+    pl->Direction = newDir;
+    pl->BxDF = v3scale(color, phaseS);
+    pl->PDF = phaseS;
+    pl->Depth++;
+    pl->VolumeDepth++;
+    cnt->medium_events++;
+}
+static Hit trace_bvh(const OrcScene *s, v3 o, v3 d, float tmin, float tmax);
+/* ScatteredInVolume, SH/RayGen.slang:162-263 (atmosphere off) */
+#define ORC_MAX_VOLUMES 100
+static int scattered_in_volume(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, OrcCounters *cnt) {
+    float distances[ORC_MAX_VOLUMES]; int indices[ORC_MAX_VOLUMES];
+    const int n = (int)(cfg->VolumesCount < ORC_MAX_VOLUMES ? cfg->VolumesCount : ORC_MAX_VOLUMES);
+    for (int i = 0; i < n; i++) {
+        VolIsect is = vol_intersect(pl->Origin, pl->Direction, cfg->Volumes[i].CornerMin, cfg->Volumes[i].CornerMax);
+        distances[i] = fmaxf(0.0f, is.Near); indices[i] = i;
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++)
+            if (distances[j] < distances[i]) { float td = distances[i]; int ti = indices[i]; distances[i] = distances[j]; indices[i] = indices[j]; distances[j] = td; indices[j] = ti; }
+    /* GetDistanceToGeometry, SH/RTCommon.slang:86-100: un-normalised direction, tmin 1e-5, tmax 1e6 */
+    Hit gh = trace_bvh(sc, pl->Origin, pl->Direction, 0.00001f, 1000000.0f);
+    const float distanceToGeometry = gh.hit ? gh.t : -1.0f;
+    float scatterDistance = -1.0f; int scattered = -1;
+    for (int i = 0; i < n; i++) {
+        float t = vol_scatter_distance(&cfg->Volumes[indices[i]], pl->Origin, pl->Direction, &pl->Sampler, scatterDistance);
+        if (t >= 0.0f && (t < scatterDistance || scatterDistance < 0.0f)) { scatterDistance = t; scattered = indices[i]; }
+    }
+    if (scatterDistance >= 0.0f && (distanceToGeometry < 0.0f || scatterDistance < distanceToGeometry)) {
+        volume_scatter_event(sc, cfg, pl, scatterDistance, scattered, cnt);
+        return 1;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * ClosestHit: SH/ClosestHit.slang:20-378
  * ---------------------------------------------------------------------------------------------- */
 static void closest_hit(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, v3 rayDir, const Hit *h, OrcCounters *cnt) {
@@ -952,13 +1148,15 @@ static void closest_hit(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, v
     /* NEE accumulation :326-372 (volume transmittance == 1 with VolumesCount == 0, SH/Volume.slang:419-446) */
     if (cfg->EnableSkyMIS && canHitSky) {
         float pdf = sky.w;
+        const float T = cfg->VolumesCount ? volumes_transmittance(cfg, pl->Origin, toSkyW) : 1.0f;      /* :332-333 */
         if (sky.w > 0.0f && skyEval.PDF > 0.0f) {
-            v3 c = v3divs(v3mul(v3scale(skyEval.BxDF, 1.0f), V3(sky.x, sky.y, sky.z)), pdf);
+            v3 c = v3divs(v3mul(v3scale(skyEval.BxDF, T), V3(sky.x, sky.y, sky.z)), pdf);
             pl->Emitted = v3add(pl->Emitted, v3scale(c, power_heuristic(pdf, skyEval.PDF)));
         }
     }
     if (cfg->EnableMeshMIS && !isLight && canHitLight && light.w > 0.0f && lightEval.PDF > 0.0f) {
-        v3 c = v3divs(v3mul(v3scale(lightEval.BxDF, 1.0f), V3(light.x, light.y, light.z)), light.w);
+        const float T = cfg->VolumesCount ? volumes_transmittance(cfg, pl->Origin, toLightW) : 1.0f;    /* :364 */
+        v3 c = v3divs(v3mul(v3scale(lightEval.BxDF, T), V3(light.x, light.y, light.z)), light.w);
         pl->Emitted = v3add(pl->Emitted, v3scale(c, power_heuristic(light.w, lightEval.PDF)));
     }
     int invalid = ss.PDF <= 0.0f;                                               /* :375-376 */
@@ -1008,16 +1206,18 @@ static v3 trace_one_sample(const OrcScene *sc, const OrcConfig *cfg, Payload *pl
     direction = v3normalize(v3sub(focus, origin));
 
     pl->Depth = 0; pl->Origin = origin; pl->Direction = direction;
-    pl->BxDF = v3s(1.0f); pl->PDF = 1.0f; pl->Emitted = v3s(0.0f); pl->InMedium = 0;
+    pl->BxDF = v3s(1.0f); pl->PDF = 1.0f; pl->Emitted = v3s(0.0f); pl->InMedium = 0; pl->VolumeDepth = 0;
     v3 throughput = v3s(1.0f), pathLight = v3s(0.0f);
     cnt->paths++;
     while (pl->Depth < cfg->MaxDepth) {
         v3 ro = pl->Origin, rd = v3normalize(pl->Direction);
         pl->Emitted = v3s(0.0f);
         cnt->segments++;
-        Hit h = trace_bvh(sc, ro, rd, 0.01f, 100000.0f);
-        if (h.hit) closest_hit(sc, cfg, pl, rd, &h, cnt);
-        else { miss_shader(sc, cfg, pl); cnt->misses++; }
+        if (!(cfg->VolumesCount && scattered_in_volume(sc, cfg, pl, cnt))) {         /* :86-90 */
+            Hit h = trace_bvh(sc, ro, rd, 0.01f, 100000.0f);
+            if (h.hit) closest_hit(sc, cfg, pl, rd, &h, cnt);
+            else { miss_shader(sc, cfg, pl); cnt->misses++; }
+        }
         v3 contribution = v3mul(pl->Emitted, throughput);
         if (pl->Depth != 1) {                                                   /* Q3 */
             float lum = v3dot(contribution, V3(0.212671f, 0.715160f, 0.072169f));

@@ -56,6 +56,16 @@ typedef struct {
     const float *lut_refract_in;   /* 128x128x32               :201 */
 } OrcSceneDesc;
 
+/* Homogeneous AABB volume: the fields of VolumeGPU (PT/PathTracer.h:341-395, SH/Volume.slang:20-52) that a volume without NanoVDB
+ * density data (m_DensityDataIndex == -1) reads. */
+typedef struct {
+    float CornerMin[3], CornerMax[3];
+    float Color[3], EmissiveColor[3];
+    float Density, Anisotropy, Alpha, DropletSize;
+    uint32_t ApproximatedScattering;     /* m_ApproximatedScattering: anisotropy decays with the volume depth (SH/Volume.slang:150-156) */
+    uint32_t _pad;
+} OrcVolume;
+
 typedef struct {                                                             /* PT/PathTracer.h:271-309 subset */
     float ViewInverse[16];        /* column-major */
     float ProjectionInverse[16];
@@ -67,9 +77,13 @@ typedef struct {                                                             /* 
     uint32_t ScreenSplitCount;
     /* shader #defines, PT/PathTracer.cpp:621-654 */
     uint32_t EnableSkyMIS, EnableMeshMIS, ShowEnvMapDirectly, UseOnlyGeometryNormals, UseEnergyCompensation, FurnaceTestMode;
+    /* volumes: SH/RayGen.slang:162-380, SH/Volume.slang (homogeneous part); PHASE_FUNCTION_* define, PT/PathTracer.cpp:639-650 */
+    uint32_t PhaseFunction;       /* 0 Henyey-Greenstein, 1 Draine, 2 Henyey-Greenstein + Draine (PT/PathTracer.h:76-81) */
+    uint32_t VolumesCount;
+    const OrcVolume *Volumes;
 } OrcConfig;
 
-typedef struct { uint64_t paths, segments, surface_hits, misses, shadow_rays, medium_events; } OrcCounters;
+typedef struct { uint64_t paths, segments, surface_hits, misses, shadow_rays, medium_events; } OrcCounters;   /* medium_events: scattering events inside a mesh medium or an AABB volume */
 
 typedef struct OrcScene OrcScene;
 

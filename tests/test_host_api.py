@@ -36,7 +36,8 @@ def test_null_arguments_are_rejected_not_crashed():
     assert L.b200pt_destroy(None) == pt.ERR_WRONG_ARGUMENTS
     assert L.b200pt_path_trace(None, 1, 0, None) == pt.ERR_WRONG_ARGUMENTS
     assert L.b200pt_set_scene_file(None, b"x") == pt.ERR_WRONG_ARGUMENTS
-    assert L.b200pt_add_volume(None, None) == pt.ERR_NOT_IMPLEMENTED      # volumes: out of scope
+    assert L.b200pt_add_volume(None, None) == pt.ERR_WRONG_ARGUMENTS      # homogeneous volumes are implemented: a null volume is a bad argument
+    assert L.b200pt_add_density_data_to_volume(None, 0, None) == pt.ERR_NOT_IMPLEMENTED   # NanoVDB grids are not
     w, h, p = C.c_uint32(), C.c_uint32(), C.c_void_p()
     assert L.b200pt_decode_image_file(b"/nonexistent.png", C.byref(w), C.byref(h), C.byref(p)) == pt.ERR_INIT_FAILED
 
@@ -311,3 +312,16 @@ def test_bvh4_collapse_rejects_bad_arguments_and_leaf_root():
     assert len(n4) == 0 and d == 0
     with pytest.raises(B.B200ptError):
         B.bvh4_collapse(nodes2, 99)
+
+
+def test_volume_struct_and_defaults_without_gpu():
+    """b200pt_volume mirrors PathTracer::Volume (PT/PathTracer.h:36-70): layout and defaults are checked on the CPU."""
+    import ctypes as C
+    from vpt_b200 import binding as B
+    assert C.sizeof(B.Volume) == 80
+    v = B.PathTracer.make_volume()
+    assert list(v.CornerMin) == [-1.0] * 3 and list(v.CornerMax) == [1.0] * 3
+    assert all(abs(c - 0.8) < 1e-7 for c in v.Color) and list(v.EmissiveColor) == [0.0] * 3
+    assert (v.Density, v.Anisotropy, v.Alpha, v.DropletSize, v.DensityDataIndex) == (1.0, 0.0, 1.0, 20.0, -1)
+    assert v.ApproximatedScatteringForClouds == 0 and abs(v.ApproximatedScatteringFalloff - 0.8) < 1e-7
+    assert B.lib().b200pt_default_volume(None) == B.ERR_WRONG_ARGUMENTS

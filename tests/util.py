@@ -61,7 +61,12 @@ def product_tracer(name, W, H, env=None, device=0, **cfg_kw):
     t.set_luts(*luts())
     cfg = pt.default_config()
     for k, v in cfg_kw.items():
-        setattr(cfg, _ORC2PT.get(k, k), v)
+        if k == "Volumes":                       # homogeneous AABB volumes: list of dicts (oracle.orc.VOLUME_DEFAULTS keys)
+            for vol in v: t.add_volume(**vol)
+        elif k == "PhaseFunction":
+            t.set_phase_function(v)
+        else:
+            setattr(cfg, _ORC2PT.get(k, k), v)
     t.set_config(cfg)
     t.resize(W, H)
     return t

@@ -66,6 +66,16 @@ class Config(C.Structure):
                 ("MaxSamplesAccumulated", C.c_uint32), ("FramesInFlight", C.c_uint32)]
 
 
+class Volume(C.Structure):     # b200pt_volume (PathTracer::Volume, PT/PathTracer.h:36-70)
+    _fields_ = [("CornerMin", C.c_float * 3), ("CornerMax", C.c_float * 3), ("Color", C.c_float * 3), ("EmissiveColor", C.c_float * 3),
+                ("Density", C.c_float), ("Anisotropy", C.c_float), ("Alpha", C.c_float), ("DropletSize", C.c_float),
+                ("DensityDataIndex", C.c_int32), ("ApproximatedScatteringForClouds", C.c_uint32), ("ApproximatedScatteringFalloff", C.c_float),
+                ("_reserved", C.c_uint32)]
+
+
+MAX_VOLUMES = 16
+
+
 class Tonemap(C.Structure):
     _fields_ = [("Exposure", C.c_float), ("Gamma", C.c_float)]
 
@@ -111,6 +121,10 @@ def lib():
             "b200pt_camera_from_view": [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p],
             "b200pt_resize": [C.c_void_p, C.c_uint32, C.c_uint32], "b200pt_get_size": [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
             "b200pt_reset": [C.c_void_p], "b200pt_add_volume": [C.c_void_p, C.c_void_p],
+            "b200pt_default_volume": [C.c_void_p], "b200pt_set_volume": [C.c_void_p, C.c_uint32, C.c_void_p], "b200pt_remove_volume": [C.c_void_p, C.c_uint32],
+            "b200pt_volume_count": [C.c_void_p, C.POINTER(C.c_uint32)], "b200pt_get_volume": [C.c_void_p, C.c_uint32, C.c_void_p],
+            "b200pt_add_density_data_to_volume": [C.c_void_p, C.c_uint32, C.c_char_p],
+            "b200pt_set_phase_function": [C.c_void_p, C.c_uint32], "b200pt_get_phase_function": [C.c_void_p, C.POINTER(C.c_uint32)],
             "b200pt_set_partition": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32], "b200pt_local_rows": [C.c_void_p, C.POINTER(C.c_uint32)],
             "b200pt_path_trace": [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)], "b200pt_samples_accumulated": [C.c_void_p, C.POINTER(C.c_uint32)],
             "b200pt_synchronize": [C.c_void_p], "b200pt_set_stream": [C.c_void_p, C.c_void_p], "b200pt_set_profiling": [C.c_void_p, C.c_int32], "b200pt_get_hdr": [C.c_void_p, C.c_void_p, C.c_int32], "b200pt_hdr_device_ptr": [C.c_void_p, C.POINTER(C.c_void_p)],
@@ -263,6 +277,37 @@ class PathTracer:
 
     def _ck(self, r):
         if r != OK: raise B200ptError(r, self.L.b200pt_last_error(self.h).decode())
+
+    # ---- volumes: PathTracer::AddVolume / SetVolume / RemoveVolume / SetPhaseFunction (homogeneous AABB volumes)
+    @staticmethod
+    def make_volume(**kw):
+        v = Volume(); r = lib().b200pt_default_volume(C.byref(v))
+        if r != OK: raise B200ptError(r, "default_volume")
+        for k, val in kw.items():
+            if k == "ApproximatedScattering": k = "ApproximatedScatteringForClouds"
+            if k in ("CornerMin", "CornerMax", "Color", "EmissiveColor"):
+                for j in range(3): getattr(v, k)[j] = float(val[j])
+            else: setattr(v, k, val)
+        return v
+
+    def add_volume(self, vol=None, **kw):
+        v = vol if vol is not None else self.make_volume(**kw)
+        self._ck(self.L.b200pt_add_volume(self.h, C.byref(v)))
+
+    def set_volume(self, idx, vol): self._ck(self.L.b200pt_set_volume(self.h, idx, C.byref(vol)))
+
+    def remove_volume(self, idx): self._ck(self.L.b200pt_remove_volume(self.h, idx))
+
+    def volume_count(self):
+        n = C.c_uint32(); self._ck(self.L.b200pt_volume_count(self.h, C.byref(n))); return n.value
+
+    def get_volume(self, idx):
+        v = Volume(); self._ck(self.L.b200pt_get_volume(self.h, idx, C.byref(v))); return v
+
+    def set_phase_function(self, pf): self._ck(self.L.b200pt_set_phase_function(self.h, pf))
+
+    def get_phase_function(self):
+        n = C.c_uint32(); self._ck(self.L.b200pt_get_phase_function(self.h, C.byref(n))); return n.value
 
     # ---- PathTracer::SetScene
     def set_scene_file(self, path): self._ck(self.L.b200pt_set_scene_file(self.h, path.encode()))

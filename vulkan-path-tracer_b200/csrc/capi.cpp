@@ -113,7 +113,25 @@ int32_t b200pt_camera_from_view(const float view[16], float aspect, float vi[16]
 int32_t b200pt_resize(b200pt_handle h, uint32_t w, uint32_t hh) { return guard(h, [&](Engine &e) { e.resize(w, hh); }); }
 int32_t b200pt_get_size(b200pt_handle h, uint32_t *w, uint32_t *hh) { if (!w || !hh) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { *w = e.width(); *hh = e.height(); }); }
 int32_t b200pt_reset(b200pt_handle h) { return guard(h, [&](Engine &e) { e.reset(); }); }
-int32_t b200pt_add_volume(b200pt_handle h, const void *) { if (h) h->err = "volumes are out of scope for this hot path (SURVEY 8f)"; return B200PT_ERR_NOT_IMPLEMENTED; }
+int32_t b200pt_default_volume(b200pt_volume *v) {                                      /* PT/PathTracer.h:36-70 */
+    if (!v) return B200PT_ERR_WRONG_ARGUMENTS;
+    memset(v, 0, sizeof *v);
+    for (int k = 0; k < 3; k++) { v->CornerMin[k] = -1.0f; v->CornerMax[k] = 1.0f; v->Color[k] = 0.8f; v->EmissiveColor[k] = 0.0f; }
+    v->Density = 1.0f; v->Anisotropy = 0.0f; v->Alpha = 1.0f; v->DropletSize = 20.0f; v->DensityDataIndex = -1;
+    v->ApproximatedScatteringForClouds = 0; v->ApproximatedScatteringFalloff = 0.8f;
+    return B200PT_OK;
+}
+int32_t b200pt_add_volume(b200pt_handle h, const b200pt_volume *v) { if (!v) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.add_volume(*v); }); }
+int32_t b200pt_set_volume(b200pt_handle h, uint32_t i, const b200pt_volume *v) { if (!v) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.set_volume(i, *v); }); }
+int32_t b200pt_remove_volume(b200pt_handle h, uint32_t i) { return guard(h, [&](Engine &e) { e.remove_volume(i); }); }
+int32_t b200pt_volume_count(b200pt_handle h, uint32_t *out) { if (!out) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { *out = (uint32_t)e.volumes().size(); }); }
+int32_t b200pt_get_volume(b200pt_handle h, uint32_t i, b200pt_volume *out) {
+    if (!out) return B200PT_ERR_WRONG_ARGUMENTS;
+    return guard(h, [&](Engine &e) { if (i >= e.volumes().size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume index out of range" }; *out = e.volumes()[i]; });
+}
+int32_t b200pt_add_density_data_to_volume(b200pt_handle h, uint32_t, const char *) { if (h) h->err = "NanoVDB density data is not implemented (SURVEY 8f row 1: needs a NanoVDB reader)"; return B200PT_ERR_NOT_IMPLEMENTED; }
+int32_t b200pt_set_phase_function(b200pt_handle h, uint32_t pf) { return guard(h, [&](Engine &e) { e.set_phase_function(pf); }); }
+int32_t b200pt_get_phase_function(b200pt_handle h, uint32_t *out) { if (!out) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { *out = e.phase_function(); }); }
 
 int32_t b200pt_set_partition(b200pt_handle h, uint32_t r, uint32_t w, uint32_t b) { return guard(h, [&](Engine &e) { e.set_partition(r, w, b); }); }
 int32_t b200pt_local_rows(b200pt_handle h, uint32_t *out) { if (!out) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { *out = e.local_rows(); }); }

@@ -91,6 +91,11 @@ static_assert(sizeof(ShadeTri) == 112, "ShadeTri is 112 B");
 //   r0 = p0.xyz | uv0.x   r1 = p1.xyz | uv0.y   r2 = p2.xyz | uv1.x   r3 = uv1.y uv2.x uv2.y | global triangle id (bits)
 struct EmTri { float4 r[4]; };
 
+// 80-byte homogeneous volume (VolumeGPU of PT/PathTracer.h:341-395 without the grid fields): mn_density = CornerMin | Density,
+// mx_g = CornerMax | Anisotropy, color_alpha = Color | Alpha, emis_droplet = EmissiveColor | DropletSize, flags.x = ApproximatedScattering
+struct DevVolume { float4 mn_density, mx_g, color_alpha, emis_droplet; uint4 flags; };
+static_assert(sizeof(DevVolume) == 80, "DevVolume is 80 B");
+
 struct DevScene {
     const b200pt_vertex *verts;
     const uint32_t *indices;
@@ -110,6 +115,8 @@ struct DevScene {
     const ShadeTri *shade_tris;
     const EmTri *em_tris;
     const uint32_t *em_tri_base;   // per emissive mesh: first EmTri
+    const DevVolume *volumes;      // homogeneous AABB volumes (volumes.cuh), n_volumes entries
+    uint32_t n_volumes, phase_function;   // phase_function: 0 HG, 1 Draine, 2 HG + Draine (PT/PathTracer.h:76-81)
     uint32_t n_emissive, envW, envH, n_tris, n_nodes;
     int32_t root;            // child-style reference of the root
     uint32_t bvh_bytes;      // nodes+tris size if they are contiguous and small enough to stage in smem, else 0
@@ -138,6 +145,7 @@ struct PathState {
     float4 *rad_slot;    // pathLight.xyz, sample slot (u32 bits)
     float4 *medium;      // MediumColor.xyz, MediumDensity
     float  *medium_g;    // MediumAnisotropy
+    uint32_t *vol_depth; // payload.VolumeDepth (nullptr while the scene has no volumes)
 };
 struct ShadeOut {
     float4 *hit;         // t, u, v, tri slot (u32 bits; 0xFFFFFFFF = miss)

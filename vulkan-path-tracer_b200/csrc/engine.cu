@@ -41,7 +41,7 @@ Engine::~Engine() {
     if (stream_) cudaStreamSynchronize(stream_);
     free_scene(); free_wave(); free_post();
     dfree(d_env_); dfree(d_alias_); dfree(d_env_row_cos_); for (auto &l : d_luts_) dfree(l);
-    dfree(d_image_); dfree(d_ctr_); dfree(d_counts_);
+    dfree(d_image_); dfree(d_ctr_); dfree(d_counts_); dfree(d_volumes_);
     if (h_count_) cudaFreeHost(h_count_);
     if (ev_[0]) cudaEventDestroy(ev_[0]); if (ev_[1]) cudaEventDestroy(ev_[1]);
     for (auto &e : prof_ev_) cudaEventDestroy(e);
@@ -217,6 +217,49 @@ void Engine::set_material(uint32_t idx, const b200pt_material &m) {
     reset();
 }
 
+// PathTracer::AddVolume / SetVolume / RemoveVolume (PathTracer.cpp:1334-1345,1518-1555): homogeneous AABB volumes only
+static void check_volume(const b200pt_volume &v) {
+    if (v.DensityDataIndex != -1) throw CudaError{ B200PT_ERR_NOT_IMPLEMENTED, "heterogeneous (NanoVDB) volumes are not implemented: DensityDataIndex must be -1" };
+    for (int k = 0; k < 3; k++) if (!(v.CornerMin[k] <= v.CornerMax[k])) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume AABB: CornerMin > CornerMax" };
+    if (!(v.Density >= 0.0f)) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume density must be >= 0" };
+}
+void Engine::upload_volumes() {
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    if (!d_volumes_) CK(cudaMalloc(&d_volumes_, B200PT_MAX_VOLUMES * sizeof(DevVolume)));
+    std::vector<DevVolume> dv(volumes_.size());
+    for (size_t i = 0; i < volumes_.size(); i++) {
+        const b200pt_volume &v = volumes_[i];
+        dv[i].mn_density = make_float4(v.CornerMin[0], v.CornerMin[1], v.CornerMin[2], v.Density);
+        dv[i].mx_g = make_float4(v.CornerMax[0], v.CornerMax[1], v.CornerMax[2], v.Anisotropy);
+        dv[i].color_alpha = make_float4(v.Color[0], v.Color[1], v.Color[2], v.Alpha);
+        dv[i].emis_droplet = make_float4(v.EmissiveColor[0], v.EmissiveColor[1], v.EmissiveColor[2], v.DropletSize);
+        dv[i].flags = make_uint4(v.ApproximatedScatteringForClouds, 0u, 0u, 0u);
+    }
+    if (!dv.empty()) CK(cudaMemcpy(d_volumes_, dv.data(), dv.size() * sizeof(DevVolume), cudaMemcpyHostToDevice));
+    ds_.volumes = d_volumes_; ds_.n_volumes = (uint32_t)dv.size(); ds_.phase_function = phase_function_;
+    reset();
+}
+uint32_t Engine::add_volume(const b200pt_volume &v) {
+    check_volume(v);
+    if (volumes_.size() >= B200PT_MAX_VOLUMES) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "too many volumes (B200PT_MAX_VOLUMES)" };
+    volumes_.push_back(v); upload_volumes();
+    return (uint32_t)volumes_.size() - 1u;
+}
+void Engine::set_volume(uint32_t idx, const b200pt_volume &v) {
+    check_volume(v);
+    if (idx >= volumes_.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume index out of range" };
+    volumes_[idx] = v; upload_volumes();
+}
+void Engine::remove_volume(uint32_t idx) {
+    if (idx >= volumes_.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume index out of range" };
+    volumes_.erase(volumes_.begin() + idx); upload_volumes();
+}
+void Engine::set_phase_function(uint32_t pf) {
+    if (pf > 2u) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "phase function: 0 HG, 1 Draine, 2 HG + Draine" };
+    phase_function_ = pf; ds_.phase_function = pf; reset();
+}
+
 // PathTracer::LoadEnvironmentMap (PathTracer.cpp:1137-1332)
 void Engine::set_env_map(uint32_t w, uint32_t h, const float *rgba) {
     CK(cudaSetDevice(device_));
@@ -283,7 +326,7 @@ void Engine::ensure_image() {
 }
 
 void Engine::free_wave() {
-    for (auto &p : ps_) { dfree(p.org_pdf); dfree(p.dir_rng); dfree(p.thr_depth); dfree(p.rad_slot); dfree(p.medium); dfree(p.medium_g); }
+    for (auto &p : ps_) { dfree(p.org_pdf); dfree(p.dir_rng); dfree(p.thr_depth); dfree(p.rad_slot); dfree(p.medium); dfree(p.medium_g); dfree(p.vol_depth); }
     dfree(so_.hit); dfree(so_.bxdf_pdf); dfree(so_.e0); dfree(so_.sky_o); dfree(so_.sky_d); dfree(so_.sky_c); dfree(so_.lit_o); dfree(so_.lit_d); dfree(so_.lit_c);
     dfree(d_sample_buf_); dfree(d_rng_carry_); dfree(d_q_hit_); dfree(d_q_miss_); dfree(d_disp_[0]); dfree(d_disp_[1]);
     for (auto &hp : h_disp_) if (hp) { cudaFreeHost(hp); hp = nullptr; }
@@ -294,7 +337,7 @@ void Engine::ensure_wave(size_t cap) {
     if (cap <= wave_cap_) return;
     free_wave();
     auto a4 = [&](float4 *&p) { CK(cudaMalloc(&p, cap * sizeof(float4))); };
-    for (auto &p : ps_) { a4(p.org_pdf); a4(p.dir_rng); a4(p.thr_depth); a4(p.rad_slot); a4(p.medium); CK(cudaMalloc(&p.medium_g, cap * sizeof(float))); }
+    for (auto &p : ps_) { a4(p.org_pdf); a4(p.dir_rng); a4(p.thr_depth); a4(p.rad_slot); a4(p.medium); CK(cudaMalloc(&p.medium_g, cap * sizeof(float))); CK(cudaMalloc(&p.vol_depth, cap * sizeof(uint32_t))); }
     a4(so_.hit); a4(so_.bxdf_pdf); a4(so_.e0); a4(so_.sky_o); a4(so_.sky_d); a4(so_.sky_c); a4(so_.lit_o); a4(so_.lit_d); a4(so_.lit_c);
     a4(d_sample_buf_);
     CK(cudaMalloc(&d_rng_carry_, cap * sizeof(uint32_t)));
@@ -354,6 +397,9 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     CK(cudaEventRecord(table_ev_[table_sel_], stream_));
     const DevConfig dc = make_dev_config();
 
+    const uint32_t n_vol = ds_.n_volumes;
+    PathState pst[2] = { ps_[0], ps_[1] };                    // payload.VolumeDepth travels only while the scene has volumes
+    if (!n_vol) { pst[0].vol_depth = nullptr; pst[1].vol_depth = nullptr; }
     bool medium = false;                                      // can a path random-walk inside a mesh without gaining Depth?
     for (const auto &m : scene_.materials) if (m.Transmission > 0.0f && m.Metallic < 1.0f && m.MediumDensity > 0.0f && m.MediumAnisotropy != 1.0f) medium = true;
 
@@ -369,7 +415,7 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     for (uint32_t w0 = 0; w0 < todo; w0 += F) {
         const uint32_t nd = std::min(F, todo - w0);
         for (uint32_t s = 0; s < cfg_.SamplesPerFrame; s++) {
-            launch_raygen(lc_, dc, d_disp + w0, nd, P, s == 0 ? 1u : 0u, d_rng_carry_, ps_[0], d_sample_buf_, d_counts_, d_ctr_, stream_);
+            launch_raygen(lc_, dc, d_disp + w0, nd, P, s == 0 ? 1u : 0u, d_rng_carry_, pst[0], d_sample_buf_, d_counts_, d_ctr_, stream_);
             launches++; mark(0);
             int cur = 0; uint32_t k = 0;
             for (;;) {
@@ -377,9 +423,10 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                 if (!medium && cfg_.MaxDepth - std::min(cfg_.MaxDepth, k) < chunk) chunk = cfg_.MaxDepth - std::min(cfg_.MaxDepth, k);
                 if (chunk == 0) break;
                 for (uint32_t b = 0; b < chunk; b++, k++) {
-                    launch_extend(lc_, ds_, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_ctr_, k == 0, stream_); mark(1);
-                    launch_shade(lc_, ds_, dc, ps_[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(2);
-                    launch_connect(lc_, ds_, dc, ps_[cur], ps_[cur ^ 1], so_, d_counts_, k & 1u, d_q_hit_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
+                    if (n_vol) { launch_volume_decide(lc_, ds_, pst[cur], so_, d_counts_, k & 1u, stream_); launches += 2; }   // + k_shade_volume
+                    launch_extend(lc_, ds_, pst[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_ctr_, k == 0, stream_); mark(1);
+                    launch_shade(lc_, ds_, dc, pst[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(2);
+                    launch_connect(lc_, ds_, dc, pst[cur], pst[cur ^ 1], so_, d_counts_, k & 1u, d_q_hit_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
                     cur ^= 1; launches += lc_.trav_dyn ? 5 : 4;
                 }
                 if (!medium && k >= cfg_.MaxDepth) break;    // every surviving path has Depth >= MaxDepth: provably empty

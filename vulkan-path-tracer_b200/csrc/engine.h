@@ -22,6 +22,13 @@ public:
     void set_config(const b200pt_config &c);
     const b200pt_config &config() const { return cfg_; }
     void set_material(uint32_t idx, const b200pt_material &m);
+    // PathTracer::AddVolume / SetVolume / RemoveVolume / SetPhaseFunction (homogeneous volumes, volumes.cuh)
+    uint32_t add_volume(const b200pt_volume &v);
+    void set_volume(uint32_t idx, const b200pt_volume &v);
+    void remove_volume(uint32_t idx);
+    const std::vector<b200pt_volume> &volumes() const { return volumes_; }
+    void set_phase_function(uint32_t pf);
+    uint32_t phase_function() const { return phase_function_; }
     const HostScene &scene() const { return scene_; }
     bool has_scene() const { return has_scene_; }
     void set_camera(const float vi[16], const float pi[16]);
@@ -61,6 +68,7 @@ private:
     void free_scene();
     void upload_scene();
     void rebuild_emissive();
+    void upload_volumes();
     DevMaterial make_dev_material(const b200pt_material &m) const;
     void ensure_image();
     void ensure_wave(size_t capacity);
@@ -92,6 +100,7 @@ private:
     std::vector<uint8_t *> d_texdata_;
     std::vector<DevInstance> h_instances_; std::vector<DevMesh> h_meshes_;
     float4 *d_env_ = nullptr; uint2 *d_alias_ = nullptr; float2 *d_env_row_cos_ = nullptr; float *d_luts_[3] = { nullptr, nullptr, nullptr };
+    std::vector<b200pt_volume> volumes_; uint32_t phase_function_ = 0; DevVolume *d_volumes_ = nullptr;
     LbvhResult bvh_{};
     LaunchCfg lc_{};
     uint32_t n_tris_ = 0, n_emissive_ = 0;

@@ -26,6 +26,7 @@ void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeO
                    WaveCounters *ctr, bool primary, cudaStream_t st);
 void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity,
                   const uint32_t *q_hit, const uint32_t *q_miss, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st);      // k_shade_miss + k_shade_hit
+void launch_volume_decide(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity, cudaStream_t st);   // before launch_extend when the scene has volumes
 void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,
                     uint32_t *ctrl, uint32_t parity, const uint32_t *q_hit, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st);
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,

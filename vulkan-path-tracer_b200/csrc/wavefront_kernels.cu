@@ -19,6 +19,7 @@
 // All per-path state is SoA float4 (coalesced 16-B lanes); live paths are kept dense by compaction.
 #include "bvh_traverse.cuh"
 #include "bvh_dynfetch.cuh"
+#include "volumes.cuh"
 #include "kernels.h"
 #include <cstdio>
 #include <cstdlib>
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(256) k_raygen(DevConfig cfg, const DevDispatch
         ps.dir_rng[j] = make_float4(direction.x, direction.y, direction.z, __uint_as_float(rng.s));
         ps.thr_depth[j] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(inside ? 0u : PT_MAX_DEPTH));
         ps.rad_slot[j] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(j));
+        if (ps.vol_depth) ps.vol_depth[j] = 0u;                             // payload.VolumeDepth = 0 (SH/RayGen.slang:61)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[0] = n; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; ctrl[4] = 0; ctrl[5] = 0; ctrl[8] = 0; ctrl[9] = 0; ctrl[10] = 0; ctrl[11] = 0; atomicAdd(&ctr->paths, (unsigned long long)n); }
 }
@@ -133,7 +135,9 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
             bool hit = false;
             float4 o4n = make_float4(0, 0, 0, 0), d4n = o4n;
             if (it + 1u < K && i + blockDim.x < n) { o4n = ps.org_pdf[i + blockDim.x]; d4n = ps.dir_rng[i + blockDim.x]; }   // software pipelining of the state loads
-            if (active) {
+            if (active && sc.n_volumes && __float_as_uint(so.hit[i].w) == VOLUME_EVENT) {
+                hit = true;                                                 // scattered inside a volume (k_volume_decide): no TraceRay, SH/RayGen.slang:86-90
+            } else if (active) {
                 const float3 rd = normalize_ray(f3(d4));                    // SH/RayGen.slang:70
                 HitRec h;
                 hit = bvh_trace<SMEM, false, false, false, !PRIMARY>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, 
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 5
 #endif
+template <bool VOL>   // VOL: the scene has AABB volumes (volumes.cuh) -- volume events in the hit queue are skipped, NEE terms get the transmittance
 __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so,
                                                     const uint32_t *__restrict__ ctrl, uint32_t parity, const uint32_t *__restrict__ q_hit, WaveCounters *ctr) {
     const uint32_t n = ctrl[2u + 2u * parity];
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         const float payPDF = o4.w;
         Rng rng; rng.s = __float_as_uint(d4.w);
         const uint32_t gid = __float_as_uint(h4.w);                            // global triangle id of the hit
+        if (VOL && gid == VOLUME_EVENT) continue;                           // a volume scattering event: k_shade_volume
 
         // The sky-NEE draws are the first draws of a hit outside a medium: take them now and put the alias-table load in flight.
         EnvPick ep;
@@ -358,6 +364,10 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc
         const float3 no = sf.WorldPos + sf.Normal * off;
         const bool invalid = ss.PDF <= 0.0f;
         const uint32_t newDepth = invalid ? PT_MAX_DEPTH + depth : depth + 1u;   // MAX_DEPTH*(invalid) + (Depth + 1*(!invalid))
+        if (VOL && reqMask) {                                               // volumes cast shadows on the NEE terms: transmittance from the NEW origin (:332-333, :364)
+            if (reqMask & 1u) { const float T = volumes_transmittance(sc, no, f3(so.sky_d[i])); const float4 c = so.sky_c[i]; so.sky_c[i] = make_float4(c.x * T, c.y * T, c.z * T, 0.0f); }
+            if (reqMask & 2u) { const float T = volumes_transmittance(sc, no, f3(so.lit_d[i])); const float4 c = so.lit_c[i]; so.lit_c[i] = make_float4(c.x * T, c.y * T, c.z * T, 0.0f); }
+        }
         ps.org_pdf[i] = make_float4(no.x, no.y, no.z, ss.PDF);
         ps.dir_rng[i] = make_float4(scatterW.x, scatterW.y, scatterW.z, __uint_as_float(rng.s));
         so.bxdf_pdf[i] = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
@@ -476,6 +486,7 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
                 dst.thr_depth[k] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(newDflags));
                 dst.rad_slot[k] = make_float4(rad.x, rad.y, rad.z, r4.w);
                 if (newDflags >> 31) { dst.medium[k] = src.medium[i]; dst.medium_g[k] = src.medium_g[i]; }
+                if (src.vol_depth) dst.vol_depth[k] = src.vol_depth[i];
             }
         }
     }
@@ -519,7 +530,7 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, S
         const bool fin = (r.cur == DYN_DONE);
         const bool have = fin && i != DYN_NONE;
         const bool hit = have && r.gid != DYN_NONE;
-        if (have) so.hit[i] = make_float4(hit ? r.t : -1.0f, r.u, r.v, __uint_as_float(r.gid));
+        if (have && r.gid != VOLUME_EVENT) so.hit[i] = make_float4(hit ? r.t : -1.0f, r.u, r.v, __uint_as_float(r.gid));
         const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, have && !hit);
         if (bh | bm) {
             unsigned long long base = 0ull;
@@ -534,7 +545,9 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, S
             const uint32_t idx = pool.take(need, lane, fetch);
             if (fin) {
                 i = idx;
-                if (i != DYN_NONE) {
+                if (i != DYN_NONE && sc.n_volumes && __float_as_uint(so.hit[i].w) == VOLUME_EVENT) {
+                    r.gid = VOLUME_EVENT;                                   // scattered inside a volume (k_volume_decide): queued as a hit at the next commit, record kept
+                } else if (i != DYN_NONE) {
                     const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
                     const float3 rd = normalize_ray(f3(d4));                // SH/RayGen.slang:70
                     dyn_init(r, f3(o4), rd, 0.01f, 100000.0f, 100000.0f, DYN_NONE, bv.root, s_base, s_step);   // :71-72
@@ -542,7 +555,10 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, S
             }
         }
         uint32_t act = __ballot_sync(0xFFFFFFFFu, r.cur != DYN_DONE);
-        if (act == 0u) break;                                               // nobody got a ray: the bounce is drained
+        if (act == 0u) {                                                    // nobody traverses: drained, unless lanes hold volume events to commit
+            if (__ballot_sync(0xFFFFFFFFu, i != DYN_NONE) == 0u) break;
+            continue;
+        }
         const int thr_now = pool.empty() ? 1 : thresh;
         do {
             if (WIDE) { while (r.cur >= 0) dyn_node4_step<!PRIMARY>(nodes4, r, s_step, s_limit, spill); }
@@ -644,6 +660,95 @@ __global__ void __launch_bounds__(256, 4) k_shadow_dyn(DevScene sc, ShadeOut so,
     }
     for (int o = 16; o > 0; o >>= 1) n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o);
     if (lane == 0 && n_shadow) atomicAdd(&ctr->shadow_rays, (unsigned long long)n_shadow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_volume_decide / k_shade_volume : homogeneous AABB volumes (volumes.cuh; SH/RayGen.slang:162-380)
+// ------------------------------------------------------------------------------------------------
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k_volume_decide(DevScene sc, PathState ps, ShadeOut so, const uint32_t *__restrict__ ctrl, uint32_t parity, int max_stack) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
+    BvhView bv;
+    if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
+    else bv = global_bvh(sc);
+    const uint32_t n = ctrl[parity];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
+        const float3 o = f3(o4), d = f3(d4);
+        Rng rng; rng.s = __float_as_uint(d4.w);
+        HitRec h;                                                           // GetDistanceToGeometry (SH/RTCommon.slang:86-100): payload.Direction as is, tmin 1e-5, tmax 1e6
+        const bool found = bvh_trace<SMEM, false>(bv, o, d, 0.00001f, 1000000.0f, h, stack, (int)blockDim.x, max_stack);
+        const float distanceToGeometry = found ? h.t : -1.0f;
+        int vi = -1;
+        const float sd = volumes_free_flight(sc, o, d, rng, vi);            // :164-209
+        ps.dir_rng[i] = make_float4(d4.x, d4.y, d4.z, __uint_as_float(rng.s));
+        const bool ev = sd >= 0.0f && (distanceToGeometry < 0.0f || sd < distanceToGeometry);   // :236
+        so.hit[i] = ev ? make_float4(sd, __int_as_float(vi), 0.0f, __uint_as_float(VOLUME_EVENT)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+// EvaluateVolumeScatteringEvent (SH/RayGen.slang:265-380) for the flagged entries of the hit queue
+__global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so, const uint32_t *__restrict__ ctrl, uint32_t parity,
+                                                      const uint32_t *__restrict__ q_hit, WaveCounters *ctr) {
+    const uint32_t n = ctrl[2u + 2u * parity];
+    uint32_t n_ev = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = q_hit[j];
+        const float4 h4 = so.hit[i];
+        if (__float_as_uint(h4.w) != VOLUME_EVENT) continue;
+        n_ev++;
+        const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
+        const uint32_t dflags = __float_as_uint(ps.thr_depth[i].w);
+        Rng rng; rng.s = __float_as_uint(d4.w);
+        const DevVolume v = sc.volumes[__float_as_int(h4.y)];
+        const float3 dir = f3(d4), color = f3(v.color_alpha);
+        const float3 origin = f3(o4) + dir * h4.x;                          // :267
+        const int vdepth = (int)ps.vol_depth[i];
+        const float3 emitted = f3(v.emis_droplet);                          // :268 (no temperature grid)
+        float3 toSky = f3(0.0f), toLight = f3(0.0f); float4 sky = make_float4(0, 0, 0, 0), light = sky; uint32_t lgid = 0xFFFFFFFFu;
+        if (cfg.EnableSkyMIS) {                                             // :273-287
+            EnvPick ep; sample_env_begin(sc, rng, ep); sample_env_finish(sc, cfg, ep, toSky, sky);
+            sky.x *= cfg.EnvironmentIntensity; sky.y *= cfg.EnvironmentIntensity; sky.z *= cfg.EnvironmentIntensity;   // Q7 again (:277)
+        }
+        if (cfg.EnableMeshMIS) sample_emissive(sc, rng, origin, toLight, light, lgid);   // :294-308
+        const float3 newDir = vol_scatter_direction(sc.phase_function, v, rng, dir, vdepth);   // :311
+        const float phaseS = vol_phase(sc.phase_function, v, dir, newDir, vdepth);             // :314
+        uint32_t reqMask = 0u;
+        // the two visibility queries of :280-306 become shadow requests; the phase-weighted, transmittance-attenuated MIS terms of
+        // :319-369 are added by k_connect iff the query comes out clear (sky: any hit occludes; light: the sampled triangle must be the closest hit)
+        if (cfg.EnableSkyMIS && sky.w > 0.0f) {
+            const float ph = vol_phase(sc.phase_function, v, dir, toSky, vdepth);
+            if (ph > 0.0f) {
+                const float T = volumes_transmittance(sc, origin, toSky);
+                const float3 c = ((f3(T) * (color * ph)) * (f3(sky) / sky.w)) * power_heuristic(sky.w, ph);
+                so.sky_o[i] = make_float4(origin.x, origin.y, origin.z, 1.0f);
+                so.sky_d[i] = make_float4(toSky.x, toSky.y, toSky.z, __uint_as_float(0xFFFFFFFFu));
+                so.sky_c[i] = make_float4(c.x, c.y, c.z, 0.0f);
+                reqMask |= 1u;
+            }
+        }
+        if (cfg.EnableMeshMIS && light.w > 0.0f) {
+            const float ph = vol_phase(sc.phase_function, v, dir, toLight, vdepth);
+            if (ph > 0.0f) {
+                const float T = volumes_transmittance(sc, origin, toLight);
+                const float3 c = ((f3(T) * (color * ph)) * (f3(light) / light.w)) * power_heuristic(light.w, ph);
+                so.lit_o[i] = make_float4(origin.x, origin.y, origin.z, 1.0f);
+                so.lit_d[i] = make_float4(toLight.x, toLight.y, toLight.z, __uint_as_float(lgid));
+                so.lit_c[i] = make_float4(c.x, c.y, c.z, 0.0f);
+                reqMask |= 2u;
+            }
+        }
+        const uint32_t newDepth = (dflags & 0x7FFFFFFFu) + 1u;              // :377
+        ps.org_pdf[i] = make_float4(origin.x, origin.y, origin.z, phaseS);  // payload.PDF = phase (:374)
+        ps.dir_rng[i] = make_float4(newDir.x, newDir.y, newDir.z, __uint_as_float(rng.s));
+        so.bxdf_pdf[i] = make_float4(color.x * phaseS, color.y * phaseS, color.z * phaseS, phaseS);
+        so.e0[i] = make_float4(emitted.x, emitted.y, emitted.z, __uint_as_float(newDepth | (dflags & 0x80000000u) | (reqMask << 29)));
+        ps.vol_depth[i] = (uint32_t)(vdepth + 1);                           // :378
+    }
+    for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xFFFFFFFFu, n_ev, o);
+    if ((threadIdx.x & 31) == 0 && n_ev) atomicAdd(&ctr->medium_events, (unsigned long long)n_ev);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -757,6 +862,7 @@ static void set_attrs_once() {
     optin((const void *)k_extend_dyn<false, true, true>); optin((const void *)k_extend_dyn<false, false, true>);
     optin((const void *)k_shadow_dyn<true, false>); optin((const void *)k_shadow_dyn<false, false>); optin((const void *)k_shadow_dyn<false, true>);
     optin((const void *)k_trace_rays<true>); optin((const void *)k_trace_rays<false>);
+    optin((const void *)k_volume_decide<true>); optin((const void *)k_volume_decide<false>);
     cudaGetLastError();
     g_attr_done = true;
 }
@@ -812,7 +918,7 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
     }
     if (occ_sh < 1) occ_sh = 1;
     lc->grid_shadow = sms * occ_sh;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade_hit, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade_hit<false>, 128, 0);
     if (occ_e < 1) occ_e = 1; if (occ_c < 1) occ_c = 1; if (occ_s < 1) occ_s = 1;
     lc->grid_extend = sms * occ_e; lc->grid_connect = sms * occ_c;
     lc->grid_trace = sms * occ_e;
@@ -853,7 +959,16 @@ void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeO
 void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity,
                   const uint32_t *q_hit, const uint32_t *q_miss, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
     k_shade_miss<<<lc.grid_light, 256, 0, st>>>(sc, cfg, ps, ctrl, parity, q_miss, sample_buf, rng_carry, ctr);
-    k_shade_hit<<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q_hit, ctr);
+    if (sc.n_volumes) k_shade_hit<true><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q_hit, ctr);
+    else k_shade_hit<false><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q_hit, ctr);
+    if (sc.n_volumes) k_shade_volume<<<lc.grid_light, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q_hit, ctr);
+}
+void launch_volume_decide(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity, cudaStream_t st) {
+    set_attrs_once();
+    const bool smem = lc.bvh_in_smem;
+    const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
+    if (smem) k_volume_decide<true><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, lc.max_stack);
+    else k_volume_decide<false><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, lc.max_stack);
 }
 void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,
                     uint32_t *ctrl, uint32_t parity, const uint32_t *q_hit, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
