@@ -231,6 +231,25 @@ def test_post_chain_matches_oracle(pt, tmp_path):
     assert np.array_equal(pt.decode_image(str(tmp_path / "o.png")), ldr)   # Editor::SaveToFile round trip
 
 
+def test_fused_post_chain_equals_pass_per_pass(pt, monkeypatch):
+    """The default post chain never materialises bloom mip 0 (threshold folded into the first down pass, last up pass + tonemap in one
+    kernel: PostProcessor.cpp:193-246 in 2 + 2(n-2) launches less traffic); B200PT_POST_FUSED=0 runs the reference's pass structure.
+    Both must give the same RGBA8 image and the same mip 0, bit for bit, including odd sizes and image borders."""
+    rng = np.random.default_rng(3)
+    for (W, H) in ((317, 203), (64, 33), (1280, 720)):
+        hdr = np.ones((H, W, 4), np.float32); hdr[..., :3] = (np.exp(rng.normal(0, 1.5, (H, W, 3))) * 0.5).astype(np.float32)
+        hdr[H // 3:H // 3 + 4, W // 2:W // 2 + 4, :3] = 500.0; hdr[0, 0, :3] = 300.0; hdr[H - 1, W - 1, :3] = 300.0
+        out = {}
+        for fused in ("1", "0"):
+            monkeypatch.setenv("B200PT_POST_FUSED", fused)
+            T = util.product_tracer("cornell_box", W, H)
+            T.set_hdr(hdr); T.set_bloom(1.5, 0.9, 10, 2.0); T.set_tonemap(1.3, 2.2)
+            T.post_process()
+            out[fused] = (T.get_ldr().copy(), T.get_bloom().copy())
+        assert np.array_equal(out["1"][0], out["0"][0]), (W, H)
+        assert np.array_equal(out["1"][1].view(np.uint32), out["0"][1].view(np.uint32)), (W, H)
+
+
 def test_errors_are_codes_not_aborts(pt):
     T = pt.PathTracer(0)
     with pytest.raises(pt.B200ptError) as e:

@@ -505,10 +505,24 @@ void Engine::post_process() {
     const uint32_t levels = (uint32_t)d_mips_.size();
     const uint32_t mips = std::min(std::max(bloom_.MipCount, 1u), levels);                      // :195
     const PostParams p{ tonemap_.Exposure, tonemap_.Gamma, bloom_.BloomThreshold, bloom_.BloomStrength, bloom_.FalloffRange };
-    launch_bloom_threshold(d_image_, d_mips_[0], W_ * H_, p, lc_.grid_light > 0 ? lc_.grid_light : 1184, stream_);            // :200-226, i == 0
-    for (uint32_t i = 1; i < mips; i++) launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_);
-    for (uint32_t i = mips - 1; i > 0; i--) launch_bloom_up(d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], p, stream_);   // :229-235
-    launch_tonemap(d_image_, d_mips_[0], d_ldr_, W_, H_, p, stream_);                           // :238-245
+    // Fused chain (default): mip 0 is never materialised -- the threshold is evaluated inside the first down pass and inside the final
+    // [up + tonemap] kernel.  B200PT_POST_FUSED=0 (or a 1-level chain) runs the reference's pass-per-pass structure; both produce the
+    // same RGBA8 image bit for bit (tested).
+    bool fused = mips >= 2;
+    if (const char *e = getenv("B200PT_POST_FUSED")) { if (atoi(e) == 0) fused = false; }
+    if (fused) {
+        launch_bloom_down_first(d_image_, W_, H_, d_mips_[1], mip_wh_[2], mip_wh_[3], p, stream_);                               // :200-226, i == 0 and i == 1
+        for (uint32_t i = 2; i < mips; i++) launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_);
+        for (uint32_t i = mips - 1; i > 1; i--) launch_bloom_up(d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], p, stream_);   // :229-235
+        launch_bloom_final(d_image_, d_mips_[1], mip_wh_[2], mip_wh_[3], d_ldr_, keep_bloom_ ? d_mips_[0] : nullptr, W_, H_, p, stream_);   // last up pass + :238-245
+        bloom_valid_ = keep_bloom_;
+    } else {
+        launch_bloom_threshold(d_image_, d_mips_[0], W_ * H_, p, lc_.grid_light > 0 ? lc_.grid_light : 1184, stream_);            // :200-226, i == 0
+        for (uint32_t i = 1; i < mips; i++) launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_);
+        for (uint32_t i = mips - 1; i > 0; i--) launch_bloom_up(d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], p, stream_);   // :229-235
+        launch_tonemap(d_image_, d_mips_[0], d_ldr_, W_, H_, p, stream_);                           // :238-245
+        bloom_valid_ = true;
+    }
     CK(cudaGetLastError());
 }
 void Engine::get_ldr(uint8_t *dst, bool dev) {
@@ -520,6 +534,7 @@ void Engine::get_ldr(uint8_t *dst, bool dev) {
 void Engine::get_bloom(float *dst) {
     CK(cudaSetDevice(device_));
     if (d_mips_.empty() || !dst) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_process has not run" };
+    if (!bloom_valid_) { keep_bloom_ = true; post_process(); }              // the fused chain skips mip 0 until somebody asks for it
     CK(cudaMemcpyAsync(dst, d_mips_[0], (size_t)W_ * H_ * sizeof(float4), cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
 }

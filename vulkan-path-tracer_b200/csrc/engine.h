@@ -110,6 +110,7 @@ private:
     b200pt_tonemap tonemap_{ 1.0f, 2.2f };
     b200pt_bloom bloom_{ 2.0f, 1.0f, 10, 5.0f };
     std::vector<float4 *> d_mips_; std::vector<uint32_t> mip_wh_; uchar4 *d_ldr_ = nullptr; uint32_t post_w_ = 0, post_h_ = 0;
+    bool keep_bloom_ = false, bloom_valid_ = false;   // fused post chain: mip 0 is written only once get_bloom() has been used
 
     // wave buffers
     size_t wave_cap_ = 0;

@@ -7,43 +7,53 @@
 
 namespace b200pt {
 
+// Every arithmetic step that more than one kernel evaluates is written with explicit-rounding intrinsics (no FMA contraction, IEEE
+// division), in the operation order of the oracle (oracle/post_oracle.c): the fused chain below and the pass-per-pass chain produce
+// bit-identical images (tests/test_gpu_parity.py::test_fused_post_chain_equals_pass_per_pass).
 __device__ __forceinline__ float smoothstepf(float e0, float e1, float x) {
-    float t = clampf((x - e0) / (e1 - e0), 0.0f, 1.0f);
-    return t * t * (3.0f - 2.0f * t);
+    const float t = clampf(__fdiv_rn(__fsub_rn(x, e0), __fsub_rn(e1, e0)), 0.0f, 1.0f);
+    return __fmul_rn(__fmul_rn(t, t), __fsub_rn(3.0f, __fmul_rn(2.0f, t)));
 }
+// BloomDownSample.slang:32-45 (FirstDispatch): one thresholded texel
+__device__ __forceinline__ float3 bloom_threshold_px(float4 s, float start, float end) {
+    const float br = __fadd_rn(__fadd_rn(__fmul_rn(s.x, 0.2126f), __fmul_rn(s.y, 0.7152f)), __fmul_rn(s.z, 0.0722f));
+    const float f = smoothstepf(start, end, br);
+    return f3(__fmul_rn(s.x, f), __fmul_rn(s.y, f), __fmul_rn(s.z, f));
+}
+__device__ __forceinline__ float bloom_scale(float acc, float strength) { return __fmul_rn(__fdiv_rn(acc, 25.0f), strength); }   // /25 (Q14), *strength
+__device__ __forceinline__ float mix_rn(float p, float q, float w) { return __fadd_rn(p, __fmul_rn(w, __fsub_rn(q, p))); }
 
-// BloomDownSample.slang:32-45 (FirstDispatch)
 __global__ void __launch_bounds__(256) k_bloom_threshold(const float4 *__restrict__ hdr, float4 *__restrict__ mip0, uint32_t npix, PostParams p) {
     const float start = p.BloomThreshold - p.FalloffRange, end = p.BloomThreshold + p.FalloffRange;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
-        const float4 s = hdr[i];
-        const float br = s.x * 0.2126f + s.y * 0.7152f + s.z * 0.0722f;
-        const float f = smoothstepf(start, end, br);
-        mip0[i] = make_float4(s.x * f, s.y * f, s.z * f, 1.0f);
+        const float3 t = bloom_threshold_px(hdr[i], start, end);
+        mip0[i] = make_float4(t.x, t.y, t.z, 1.0f);
     }
 }
 
-// BloomDownSample.slang:46-64 : taps 2*xy + (a,b), a,b in [-2,1], clamp, /25, *strength (Q14)
+// BloomDownSample.slang:46-64 : taps 2*xy + (a,b), a,b in [-2,1], clamp, /25, *strength (Q14).
+// FIRST: the source is the HDR image and every tap is thresholded on the fly -- mip 0 is never materialised (fused chain).
+template <bool FIRST>
 __global__ void __launch_bounds__(256) k_bloom_down(const float4 *__restrict__ src, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= dw || y >= dh) return;
+    const float start = p.BloomThreshold - p.FalloffRange, end = p.BloomThreshold + p.FalloffRange;
     float3 acc = f3(0.0f);
     #pragma unroll
     for (int a = -2; a < 2; a++) {
         #pragma unroll
         for (int b = -2; b < 2; b++) {
             const int sx = clampi(x * 2 + a, 0, sw - 1), sy = clampi(y * 2 + b, 0, sh - 1);
-            const float4 s = __ldg(src + (size_t)sy * sw + sx);
-            acc.x += s.x; acc.y += s.y; acc.z += s.z;
+            const float4 s4 = __ldg(src + (size_t)sy * sw + sx);
+            const float3 s = FIRST ? bloom_threshold_px(s4, start, end) : f3(s4);
+            acc.x = __fadd_rn(acc.x, s.x); acc.y = __fadd_rn(acc.y, s.y); acc.z = __fadd_rn(acc.z, s.z);
         }
     }
-    dst[(size_t)y * dw + x] = make_float4((acc.x / 25.0f) * p.BloomStrength, (acc.y / 25.0f) * p.BloomStrength, (acc.z / 25.0f) * p.BloomStrength, 1.0f);
+    dst[(size_t)y * dw + x] = make_float4(bloom_scale(acc.x, p.BloomStrength), bloom_scale(acc.y, p.BloomStrength), bloom_scale(acc.z, p.BloomStrength), 1.0f);
 }
 
-// BloomUpSample.slang:21-48 : taps xy/2 + (a,b) + 1, clamp, /25, *strength, added to the finer mip in place
-__global__ void __launch_bounds__(256) k_bloom_up(const float4 *__restrict__ src, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= dw || y >= dh) return;
+// BloomUpSample.slang:21-48 : taps xy/2 + (a,b) + 1, clamp, /25, *strength
+__device__ __forceinline__ float3 bloom_up_taps(const float4 *__restrict__ src, int sw, int sh, int x, int y, float strength) {
     float3 acc = f3(0.0f);
     #pragma unroll
     for (int a = -2; a < 2; a++) {
@@ -51,11 +61,18 @@ __global__ void __launch_bounds__(256) k_bloom_up(const float4 *__restrict__ src
         for (int b = -2; b < 2; b++) {
             const int sx = clampi(x / 2 + a + 1, 0, sw - 1), sy = clampi(y / 2 + b + 1, 0, sh - 1);
             const float4 s = __ldg(src + (size_t)sy * sw + sx);
-            acc.x += s.x; acc.y += s.y; acc.z += s.z;
+            acc.x = __fadd_rn(acc.x, s.x); acc.y = __fadd_rn(acc.y, s.y); acc.z = __fadd_rn(acc.z, s.z);
         }
     }
+    return f3(bloom_scale(acc.x, strength), bloom_scale(acc.y, strength), bloom_scale(acc.z, strength));
+}
+// ... added to the finer mip in place
+__global__ void __launch_bounds__(256) k_bloom_up(const float4 *__restrict__ src, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    const float3 u = bloom_up_taps(src, sw, sh, x, y, p.BloomStrength);
     const float4 cur = dst[(size_t)y * dw + x];
-    dst[(size_t)y * dw + x] = make_float4((acc.x / 25.0f) * p.BloomStrength + cur.x, (acc.y / 25.0f) * p.BloomStrength + cur.y, (acc.z / 25.0f) * p.BloomStrength + cur.z, 1.0f);
+    dst[(size_t)y * dw + x] = make_float4(__fadd_rn(u.x, cur.x), __fadd_rn(u.y, cur.y), __fadd_rn(u.z, cur.z), 1.0f);
 }
 
 // Tonemap.slang:20-55
@@ -75,27 +92,70 @@ __device__ __forceinline__ unsigned char unorm8(float q) {
     if (q > 1.0f) q = 1.0f;
     return (unsigned char)__float2int_rn(q * 255.0f);
 }
-// Tonemap.slang:159-175 : HDR + bilinear(bloom, uv = xy/size, CLAMP_TO_EDGE) -> *exposure -> pow(1/gamma) -> ACES -> RGBA8 (Q15)
+// Tonemap.slang:159-175 after the bloom fetch: (HDR + bloom) * exposure -> pow(1/gamma) -> ACES -> RGBA8 (Q15).  One compiled copy
+// (noinline) serves k_tonemap and k_bloom_final, so both round identically.
+static __device__ __noinline__ uchar4 tonemap_px(float3 h, float3 bl, float exposure, float gamma) {
+    float3 c = f3(__fmul_rn(__fadd_rn(h.x, bl.x), exposure), __fmul_rn(__fadd_rn(h.y, bl.y), exposure), __fmul_rn(__fadd_rn(h.z, bl.z), exposure));
+    const float ig = __fdiv_rn(1.0f, gamma);
+    c = f3(powf(c.x, ig), powf(c.y, ig), powf(c.z, ig));
+    const float3 o = aces_fitted(c);
+    return make_uchar4(unorm8(o.x), unorm8(o.y), unorm8(o.z), 255);
+}
+// bilinear footprint of the bloom fetch: uv = xy / size, CLAMP_TO_EDGE, texel centres at +0.5
+struct BloomTap { int x0, x1, y0, y1; float ax, ay; };
+__device__ __forceinline__ BloomTap bloom_tap(int x, int y, int W, int H) {
+    const float u = __fdiv_rn((float)x, (float)W), v = __fdiv_rn((float)y, (float)H);
+    const float fxp = __fsub_rn(__fmul_rn(u, (float)W), 0.5f), fyp = __fsub_rn(__fmul_rn(v, (float)H), 0.5f);
+    const float fx = floorf(fxp), fy = floorf(fyp);
+    BloomTap t;
+    t.ax = __fsub_rn(fxp, fx); t.ay = __fsub_rn(fyp, fy);
+    t.x0 = clampi((int)fx, 0, W - 1); t.x1 = clampi((int)fx + 1, 0, W - 1);
+    t.y0 = clampi((int)fy, 0, H - 1); t.y1 = clampi((int)fy + 1, 0, H - 1);
+    return t;
+}
+__device__ __forceinline__ float3 bloom_blend(float4 t00, float4 t10, float4 t01, float4 t11, float ax, float ay) {
+    return f3(mix_rn(mix_rn(t00.x, t10.x, ax), mix_rn(t01.x, t11.x, ax), ay),
+              mix_rn(mix_rn(t00.y, t10.y, ax), mix_rn(t01.y, t11.y, ax), ay),
+              mix_rn(mix_rn(t00.z, t10.z, ax), mix_rn(t01.z, t11.z, ax), ay));
+}
 __global__ void __launch_bounds__(256) k_tonemap(const float4 *__restrict__ hdr, const float4 *__restrict__ bloom0, uchar4 *__restrict__ ldr, int W, int H, PostParams p) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
-    const float u = (float)x / (float)W, v = (float)y / (float)H;
-    const float fxp = u * (float)W - 0.5f, fyp = v * (float)H - 0.5f;
-    const float fx = floorf(fxp), fy = floorf(fyp);
-    const float ax = fxp - fx, ay = fyp - fy;
-    const int x0 = clampi((int)fx, 0, W - 1), x1 = clampi((int)fx + 1, 0, W - 1);
-    const int y0 = clampi((int)fy, 0, H - 1), y1 = clampi((int)fy + 1, 0, H - 1);
-    const float4 t00 = __ldg(bloom0 + (size_t)y0 * W + x0), t10 = __ldg(bloom0 + (size_t)y0 * W + x1);
-    const float4 t01 = __ldg(bloom0 + (size_t)y1 * W + x0), t11 = __ldg(bloom0 + (size_t)y1 * W + x1);
+    const BloomTap t = bloom_tap(x, y, W, H);
+    const float4 t00 = __ldg(bloom0 + (size_t)t.y0 * W + t.x0), t10 = __ldg(bloom0 + (size_t)t.y0 * W + t.x1);
+    const float4 t01 = __ldg(bloom0 + (size_t)t.y1 * W + t.x0), t11 = __ldg(bloom0 + (size_t)t.y1 * W + t.x1);
     const float4 h4 = hdr[(size_t)y * W + x];
-    float3 bl = f3(tex_mix(tex_mix(t00.x, t10.x, ax), tex_mix(t01.x, t11.x, ax), ay),
-                   tex_mix(tex_mix(t00.y, t10.y, ax), tex_mix(t01.y, t11.y, ax), ay),
-                   tex_mix(tex_mix(t00.z, t10.z, ax), tex_mix(t01.z, t11.z, ax), ay));
-    float3 c = (f3(h4) + bl) * p.Exposure;
-    const float ig = 1.0f / p.Gamma;
-    c = f3(powf(c.x, ig), powf(c.y, ig), powf(c.z, ig));
-    const float3 o = aces_fitted(c);
-    ldr[(size_t)y * W + x] = make_uchar4(unorm8(o.x), unorm8(o.y), unorm8(o.z), 255);
+    ldr[(size_t)y * W + x] = tonemap_px(f3(h4), bloom_blend(t00, t10, t01, t11, t.ax, t.ay), p.Exposure, p.Gamma);
+}
+
+// Fused last stage of the chain: [up-sample mip 1 into mip 0] + [threshold of the HDR image = the mip-0 term it is added to] + [tonemap].
+// The reference materialises mip 0 three times (threshold write, up-sample read-modify-write, tonemap read: 5 x 16 B per pixel); here
+// a 33 x 9 tile of mip 0 (the 32 x 8 output pixels + the one-texel halo the bilinear bloom fetch reaches to the left / top) is built in
+// shared memory from the HDR image and mip 1 and consumed on the spot: HBM sees the HDR read, the small mip-1 read and the RGBA8 write.
+// mip0_out (optional) receives the tile interior so GetBloom-style consumers can still see mip 0.
+__global__ void __launch_bounds__(256) k_bloom_final(const float4 *__restrict__ hdr, const float4 *__restrict__ mip1, int mw, int mh,
+                                                     uchar4 *__restrict__ ldr, float4 *__restrict__ mip0_out, int W, int H, PostParams p) {
+    __shared__ float4 tile[9][34];      // bloom mip 0 (rgb), halo at row / column 0
+    __shared__ float4 tile_h[9][34];    // HDR texel of the same pixel
+    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 8;
+    const float start = p.BloomThreshold - p.FalloffRange, end = p.BloomThreshold + p.FalloffRange;
+    for (int k = threadIdx.x; k < 33 * 9; k += 256) {
+        const int lx = k % 33, ly = k / 33;
+        const int gx = clampi(tx0 - 1 + lx, 0, W - 1), gy = clampi(ty0 - 1 + ly, 0, H - 1);
+        const float4 h4 = __ldg(hdr + (size_t)gy * W + gx);
+        const float3 cur = bloom_threshold_px(h4, start, end);             // mip 0 before the up pass
+        const float3 u = bloom_up_taps(mip1, mw, mh, gx, gy, p.BloomStrength);
+        tile[ly][lx] = make_float4(__fadd_rn(u.x, cur.x), __fadd_rn(u.y, cur.y), __fadd_rn(u.z, cur.z), 1.0f);
+        tile_h[ly][lx] = h4;
+    }
+    __syncthreads();
+    const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const BloomTap t = bloom_tap(x, y, W, H);                               // x0 in {x-1, x}, x1 = x0 + 1 (clamped): inside the tile + halo
+    const int lx0 = t.x0 - (tx0 - 1), lx1 = t.x1 - (tx0 - 1), ly0 = t.y0 - (ty0 - 1), ly1 = t.y1 - (ty0 - 1);
+    const int cx = (threadIdx.x & 31) + 1, cy = (threadIdx.x >> 5) + 1;
+    ldr[(size_t)y * W + x] = tonemap_px(f3(tile_h[cy][cx]), bloom_blend(tile[ly0][lx0], tile[ly0][lx1], tile[ly1][lx0], tile[ly1][lx1], t.ax, t.ay), p.Exposure, p.Gamma);
+    if (mip0_out) mip0_out[(size_t)y * W + x] = tile[cy][cx];
 }
 
 void launch_bloom_threshold(const float4 *hdr, float4 *mip0, uint32_t npix, PostParams p, int grid, cudaStream_t st) {
@@ -103,7 +163,15 @@ void launch_bloom_threshold(const float4 *hdr, float4 *mip0, uint32_t npix, Post
 }
 void launch_bloom_down(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st) {
     dim3 g((dw + 31) / 32, (dh + 7) / 8);
-    k_bloom_down<<<g, 256, 0, st>>>(src, (int)sw, (int)sh, dst, (int)dw, (int)dh, p);
+    k_bloom_down<false><<<g, 256, 0, st>>>(src, (int)sw, (int)sh, dst, (int)dw, (int)dh, p);
+}
+void launch_bloom_down_first(const float4 *hdr, uint32_t W, uint32_t H, float4 *mip1, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st) {
+    dim3 g((dw + 31) / 32, (dh + 7) / 8);
+    k_bloom_down<true><<<g, 256, 0, st>>>(hdr, (int)W, (int)H, mip1, (int)dw, (int)dh, p);
+}
+void launch_bloom_final(const float4 *hdr, const float4 *mip1, uint32_t mw, uint32_t mh, uchar4 *ldr, float4 *mip0_out, uint32_t W, uint32_t H, PostParams p, cudaStream_t st) {
+    dim3 g((W + 31) / 32, (H + 7) / 8);
+    k_bloom_final<<<g, 256, 0, st>>>(hdr, mip1, (int)mw, (int)mh, ldr, mip0_out, (int)W, (int)H, p);
 }
 void launch_bloom_up(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st) {
     dim3 g((dw + 31) / 32, (dh + 7) / 8);
