@@ -181,6 +181,12 @@ int32_t b200pt_get_hdr(b200pt_handle h, float *dst, int32_t dst_is_device);
 int32_t b200pt_hdr_device_ptr(b200pt_handle h, void **ptr_out);            /* zero-copy view for the NCCL gather */
 /* replace the accumulation image (post-only runs / checkpoint restore): full W*H*4 floats from host or device */
 int32_t b200pt_set_hdr(b200pt_handle h, const float *src, int32_t src_is_device);
+/* Checkpoint / resume of the progressive accumulation (the reference keeps it only in the GPU image and loses it on exit, PathTracer.h:183,
+ * 199-201).  The file holds the RGBA32F accumulation of THIS handle's rows + the dispatch counters; after
+ * b200pt_load_checkpoint into a handle with the same scene / config / size / partition, path_trace(frames, same base_seed) continues the
+ * identical sample sequence: the final image equals an uninterrupted run bit for bit. */
+int32_t b200pt_save_checkpoint(b200pt_handle h, const char *path);
+int32_t b200pt_load_checkpoint(b200pt_handle h, const char *path);
 int32_t b200pt_get_counters(b200pt_handle h, b200pt_counters *out);
 
 /* ---- post chain: PostProcessor (PostProcessor.h:25-33, PostProcessor.cpp:128-246) ---- */

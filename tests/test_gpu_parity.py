@@ -250,6 +250,26 @@ def test_fused_post_chain_equals_pass_per_pass(pt, monkeypatch):
         assert np.array_equal(out["1"][1].view(np.uint32), out["0"][1].view(np.uint32)), (W, H)
 
 
+def test_checkpoint_resume_is_bit_identical(pt, tmp_path):
+    """k frames + save_checkpoint + (new handle) load_checkpoint + (N - k) frames == N frames in one go, bit for bit: the dispatch counter
+    travels with the image, so frame f keeps its seed PCG(base_seed + f) and its 1/(f+1) running-mean weight (SH/RayGen.slang:130-141)."""
+    name, W, H, seed = "cornell_box_glass", 96, 64, 77
+    A = util.product_tracer(name, W, H, MaxDepth=8); A.path_trace(8, seed); full = A.get_hdr().copy()
+    B = util.product_tracer(name, W, H, MaxDepth=8); B.path_trace(3, seed)
+    ck = tmp_path / "acc.b2pt"; B.save_checkpoint(ck)
+    Cc = util.product_tracer(name, W, H, MaxDepth=8); Cc.load_checkpoint(ck)
+    assert Cc.samples_accumulated() == 3
+    Cc.path_trace(5, seed)
+    assert Cc.samples_accumulated() == 8
+    assert np.array_equal(Cc.get_hdr().view(np.uint32), full.view(np.uint32))
+    # a checkpoint of another size / a non-checkpoint file are rejected with an error code
+    D = util.product_tracer(name, W + 2, H, MaxDepth=8)
+    with pytest.raises(pt.B200ptError): D.load_checkpoint(ck)
+    bad = tmp_path / "bad.b2pt"; bad.write_bytes(b"not a checkpoint" * 8)
+    with pytest.raises(pt.B200ptError): Cc.load_checkpoint(bad)
+    with pytest.raises(pt.B200ptError): Cc.load_checkpoint(tmp_path / "missing.b2pt")
+
+
 def test_errors_are_codes_not_aborts(pt):
     T = pt.PathTracer(0)
     with pytest.raises(pt.B200ptError) as e:

@@ -121,6 +121,7 @@ def lib():
             "b200pt_camera_from_view": [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p],
             "b200pt_resize": [C.c_void_p, C.c_uint32, C.c_uint32], "b200pt_get_size": [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
             "b200pt_reset": [C.c_void_p], "b200pt_add_volume": [C.c_void_p, C.c_void_p],
+            "b200pt_save_checkpoint": [C.c_void_p, C.c_char_p], "b200pt_load_checkpoint": [C.c_void_p, C.c_char_p],
             "b200pt_default_volume": [C.c_void_p], "b200pt_set_volume": [C.c_void_p, C.c_uint32, C.c_void_p], "b200pt_remove_volume": [C.c_void_p, C.c_uint32],
             "b200pt_volume_count": [C.c_void_p, C.POINTER(C.c_uint32)], "b200pt_get_volume": [C.c_void_p, C.c_uint32, C.c_void_p],
             "b200pt_add_density_data_to_volume": [C.c_void_p, C.c_uint32, C.c_char_p],
@@ -350,6 +351,10 @@ class PathTracer:
     def set_luts_dir(self, d): self._ck(self.L.b200pt_set_luts_dir(self.h, d.encode()))
 
     # ---- parameters
+    def save_checkpoint(self, path): self._ck(self.L.b200pt_save_checkpoint(self.h, str(path).encode()))
+
+    def load_checkpoint(self, path): self._ck(self.L.b200pt_load_checkpoint(self.h, str(path).encode()))
+
     def set_config(self, cfg): self._ck(self.L.b200pt_set_config(self.h, C.byref(cfg)))
 
     def get_config(self):

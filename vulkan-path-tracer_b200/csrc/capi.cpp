@@ -148,6 +148,8 @@ int32_t b200pt_set_profiling(b200pt_handle h, int32_t on) { return guard(h, [&](
 int32_t b200pt_get_hdr(b200pt_handle h, float *dst, int32_t dev) { if (!dst) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.get_hdr(dst, dev != 0); }); }
 int32_t b200pt_hdr_device_ptr(b200pt_handle h, void **out) { if (!out) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.synchronize(); *out = e.hdr_device(); }); }
 int32_t b200pt_set_hdr(b200pt_handle h, const float *src, int32_t dev) { if (!src) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.set_hdr(src, dev != 0); }); }
+int32_t b200pt_save_checkpoint(b200pt_handle h, const char *path) { if (!path) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.save_checkpoint(path); }); }
+int32_t b200pt_load_checkpoint(b200pt_handle h, const char *path) { if (!path) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.load_checkpoint(path); }); }
 int32_t b200pt_get_counters(b200pt_handle h, b200pt_counters *out) { if (!out) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { *out = e.counters(); }); }
 
 int32_t b200pt_post_set_tonemap(b200pt_handle h, const b200pt_tonemap *t) { if (!t) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.set_tonemap(*t); }); }

@@ -487,6 +487,45 @@ void Engine::set_hdr(const float *src, bool dev) {
     CK(cudaStreamSynchronize(stream_));
 }
 
+// ---------------------------------------------------------------- checkpoint / resume
+// The whole progressive state of the reference is the RGBA32F image + three counters (PT/PathTracer.h:199-201); frame f always uses
+// Seed_f = PCG(base_seed + dispatch index), so a render resumed from a checkpoint continues the SAME sample sequence: N frames in one go
+// and k frames + checkpoint + (N - k) frames give bit-identical images (tested).  File: 64-byte header + local rows of float4.
+namespace {
+struct CkptHeader { char magic[8]; uint32_t version, W, H, rank, world, band, local_rows, frame_count, samples_accumulated, samples_per_frame, chunk_count, _pad; uint64_t dispatch_count; };
+static_assert(sizeof(CkptHeader) == 64, "checkpoint header is 64 B");
+}
+void Engine::save_checkpoint(const char *path) {
+    CK(cudaSetDevice(device_));
+    if (!d_image_ || !path) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "no image to checkpoint" };
+    std::vector<float> img((size_t)W_ * local_rows_ * 4);
+    get_hdr(img.data(), false);
+    CkptHeader h{}; memcpy(h.magic, "B2PTCKPT", 8); h.version = 1; h.W = W_; h.H = H_; h.rank = rank_; h.world = world_; h.band = band_; h.local_rows = local_rows_;
+    h.frame_count = frame_count_; h.samples_accumulated = samples_accumulated_; h.samples_per_frame = cfg_.SamplesPerFrame; h.chunk_count = cfg_.ScreenChunkCount;
+    h.dispatch_count = dispatch_count_;
+    FILE *f = fopen(path, "wb");
+    if (!f) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, std::string("cannot open checkpoint for writing: ") + path };
+    const bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(img.data(), sizeof(float), img.size(), f) == img.size();
+    if (fclose(f) != 0 || !ok) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "short write of the checkpoint" };
+}
+void Engine::load_checkpoint(const char *path) {
+    CK(cudaSetDevice(device_));
+    if (!d_image_ || !path) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "resize the image before loading a checkpoint" };
+    FILE *f = fopen(path, "rb");
+    if (!f) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, std::string("cannot open checkpoint: ") + path };
+    CkptHeader h{};
+    std::vector<float> img;
+    bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "B2PTCKPT", 8) == 0 && h.version == 1;
+    const bool fits = ok && h.W == W_ && h.H == H_ && h.rank == rank_ && h.world == world_ && h.band == band_ && h.local_rows == local_rows_ &&
+                      h.samples_per_frame == cfg_.SamplesPerFrame && h.chunk_count == cfg_.ScreenChunkCount;
+    if (fits) { img.resize((size_t)W_ * local_rows_ * 4); ok = fread(img.data(), sizeof(float), img.size(), f) == img.size(); }
+    fclose(f);
+    if (!ok) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "not a b200pt checkpoint (bad magic / version / truncated)" };
+    if (!fits) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "checkpoint was taken with another image size, partition, SamplesPerFrame or ScreenChunkCount" };
+    set_hdr(img.data(), false);
+    dispatch_count_ = h.dispatch_count; frame_count_ = h.frame_count; samples_accumulated_ = h.samples_accumulated;
+}
+
 // ---------------------------------------------------------------- PostProcessor (PostProcessor.cpp:128-246)
 void Engine::free_post() { for (auto &m : d_mips_) if (m) cudaFree(m); d_mips_.clear(); mip_wh_.clear(); dfree(d_ldr_); post_w_ = post_h_ = 0; }
 void Engine::ensure_post() {

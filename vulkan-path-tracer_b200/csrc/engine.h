@@ -49,6 +49,9 @@ public:
     void get_hdr(float *dst, bool dst_is_device);
     void set_hdr(const float *src, bool src_is_device);
     float4 *hdr_device() { return d_image_; }
+    // checkpoint / resume of the accumulation (SURVEY 5 "checkpoint / resume", 8f row 4): image + dispatch bookkeeping
+    void save_checkpoint(const char *path);
+    void load_checkpoint(const char *path);
     b200pt_counters counters();
 
     // PostProcessor
