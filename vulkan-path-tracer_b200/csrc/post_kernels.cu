@@ -32,21 +32,46 @@ __global__ void __launch_bounds__(256) k_bloom_threshold(const float4 *__restric
 }
 
 // BloomDownSample.slang:46-64 : taps 2*xy + (a,b), a,b in [-2,1], clamp, /25, *strength (Q14).
-// FIRST: the source is the HDR image and every tap is thresholded on the fly -- mip 0 is never materialised (fused chain).
-template <bool FIRST>
 __global__ void __launch_bounds__(256) k_bloom_down(const float4 *__restrict__ src, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= dw || y >= dh) return;
-    const float start = p.BloomThreshold - p.FalloffRange, end = p.BloomThreshold + p.FalloffRange;
     float3 acc = f3(0.0f);
     #pragma unroll
     for (int a = -2; a < 2; a++) {
         #pragma unroll
         for (int b = -2; b < 2; b++) {
             const int sx = clampi(x * 2 + a, 0, sw - 1), sy = clampi(y * 2 + b, 0, sh - 1);
-            const float4 s4 = __ldg(src + (size_t)sy * sw + sx);
-            const float3 s = FIRST ? bloom_threshold_px(s4, start, end) : f3(s4);
+            const float4 s = __ldg(src + (size_t)sy * sw + sx);
             acc.x = __fadd_rn(acc.x, s.x); acc.y = __fadd_rn(acc.y, s.y); acc.z = __fadd_rn(acc.z, s.z);
+        }
+    }
+    dst[(size_t)y * dw + x] = make_float4(bloom_scale(acc.x, p.BloomStrength), bloom_scale(acc.y, p.BloomStrength), bloom_scale(acc.z, p.BloomStrength), 1.0f);
+}
+// Fused first two dispatches of the chain (threshold + down-sample into mip 1): mip 0 is never written.  A 32 x 8 block of mip-1 texels
+// needs the 66 x 18 HDR texels around it; each is thresholded ONCE into shared memory (it feeds up to 4 outputs) and the 16 taps of an
+// output are read from there in the reference's order.  Clamping happens on the load, so tile slot (lx, ly) always holds the texel the
+// clamped tap coordinate 2*x0 - 2 + lx would fetch.
+__global__ void __launch_bounds__(256) k_bloom_down_first(const float4 *__restrict__ hdr, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p) {
+    __shared__ float tr[18][66], tg[18][66], tb[18][66];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const float start = p.BloomThreshold - p.FalloffRange, end = p.BloomThreshold + p.FalloffRange;
+    for (int k = threadIdx.x; k < 66 * 18; k += 256) {
+        const int lx = k % 66, ly = k / 66;
+        const int gx = clampi(2 * x0 - 2 + lx, 0, sw - 1), gy = clampi(2 * y0 - 2 + ly, 0, sh - 1);
+        const float3 t = bloom_threshold_px(__ldg(hdr + (size_t)gy * sw + gx), start, end);
+        tr[ly][lx] = t.x; tg[ly][lx] = t.y; tb[ly][lx] = t.z;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= dw || y >= dh) return;
+    float3 acc = f3(0.0f);
+    #pragma unroll
+    for (int a = -2; a < 2; a++) {
+        #pragma unroll
+        for (int b = -2; b < 2; b++) {
+            const int lx = 2 * tx + a + 2, ly = 2 * ty + b + 2;
+            acc.x = __fadd_rn(acc.x, tr[ly][lx]); acc.y = __fadd_rn(acc.y, tg[ly][lx]); acc.z = __fadd_rn(acc.z, tb[ly][lx]);
         }
     }
     dst[(size_t)y * dw + x] = make_float4(bloom_scale(acc.x, p.BloomStrength), bloom_scale(acc.y, p.BloomStrength), bloom_scale(acc.z, p.BloomStrength), 1.0f);
@@ -137,16 +162,27 @@ __global__ void __launch_bounds__(256) k_bloom_final(const float4 *__restrict__ 
                                                      uchar4 *__restrict__ ldr, float4 *__restrict__ mip0_out, int W, int H, PostParams p) {
     __shared__ float4 tile[9][34];      // bloom mip 0 (rgb), halo at row / column 0
     __shared__ float4 tile_h[9][34];    // HDR texel of the same pixel
+    __shared__ float4 up[5][18];        // the up-sampled term: it depends on (x/2, y/2) only, so the 33 x 9 pixels share <= 17 x 5 values
     const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 8;
+    const int mx0 = clampi(tx0 - 1, 0, W - 1) / 2, my0 = clampi(ty0 - 1, 0, H - 1) / 2;
     const float start = p.BloomThreshold - p.FalloffRange, end = p.BloomThreshold + p.FalloffRange;
+    for (int k = threadIdx.x; k < 17 * 5; k += 256) {
+        const int ux = k % 17, uy = k / 17;
+        const float3 u = bloom_up_taps(mip1, mw, mh, 2 * (mx0 + ux), 2 * (my0 + uy), p.BloomStrength);   // taps of every pixel with x/2 == mx0+ux, y/2 == my0+uy
+        up[uy][ux] = make_float4(u.x, u.y, u.z, 0.0f);
+    }
     for (int k = threadIdx.x; k < 33 * 9; k += 256) {
         const int lx = k % 33, ly = k / 33;
         const int gx = clampi(tx0 - 1 + lx, 0, W - 1), gy = clampi(ty0 - 1 + ly, 0, H - 1);
-        const float4 h4 = __ldg(hdr + (size_t)gy * W + gx);
-        const float3 cur = bloom_threshold_px(h4, start, end);             // mip 0 before the up pass
-        const float3 u = bloom_up_taps(mip1, mw, mh, gx, gy, p.BloomStrength);
+        tile_h[ly][lx] = __ldg(hdr + (size_t)gy * W + gx);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 33 * 9; k += 256) {
+        const int lx = k % 33, ly = k / 33;
+        const int gx = clampi(tx0 - 1 + lx, 0, W - 1), gy = clampi(ty0 - 1 + ly, 0, H - 1);
+        const float3 cur = bloom_threshold_px(tile_h[ly][lx], start, end);  // mip 0 before the up pass
+        const float4 u = up[gy / 2 - my0][gx / 2 - mx0];
         tile[ly][lx] = make_float4(__fadd_rn(u.x, cur.x), __fadd_rn(u.y, cur.y), __fadd_rn(u.z, cur.z), 1.0f);
-        tile_h[ly][lx] = h4;
     }
     __syncthreads();
     const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
@@ -163,11 +199,11 @@ void launch_bloom_threshold(const float4 *hdr, float4 *mip0, uint32_t npix, Post
 }
 void launch_bloom_down(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st) {
     dim3 g((dw + 31) / 32, (dh + 7) / 8);
-    k_bloom_down<false><<<g, 256, 0, st>>>(src, (int)sw, (int)sh, dst, (int)dw, (int)dh, p);
+    k_bloom_down<<<g, 256, 0, st>>>(src, (int)sw, (int)sh, dst, (int)dw, (int)dh, p);
 }
 void launch_bloom_down_first(const float4 *hdr, uint32_t W, uint32_t H, float4 *mip1, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st) {
     dim3 g((dw + 31) / 32, (dh + 7) / 8);
-    k_bloom_down<true><<<g, 256, 0, st>>>(hdr, (int)W, (int)H, mip1, (int)dw, (int)dh, p);
+    k_bloom_down_first<<<g, 256, 0, st>>>(hdr, (int)W, (int)H, mip1, (int)dw, (int)dh, p);
 }
 void launch_bloom_final(const float4 *hdr, const float4 *mip1, uint32_t mw, uint32_t mh, uchar4 *ldr, float4 *mip0_out, uint32_t W, uint32_t H, PostParams p, cudaStream_t st) {
     dim3 g((W + 31) / 32, (H + 7) / 8);
