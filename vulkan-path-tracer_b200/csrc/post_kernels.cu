@@ -7,11 +7,20 @@
 
 namespace b200pt {
 
-// Every arithmetic step that more than one kernel evaluates is written with explicit-rounding intrinsics (no FMA contraction, IEEE
-// division), in the operation order of the oracle (oracle/post_oracle.c): the fused chain below and the pass-per-pass chain produce
-// bit-identical images (tests/test_gpu_parity.py::test_fused_post_chain_equals_pass_per_pass).
+// Every arithmetic step that more than one kernel evaluates is written with explicit-rounding intrinsics (no FMA contraction) in the
+// operation order of the oracle (oracle/post_oracle.c): the fused chain below and the pass-per-pass chain produce bit-identical
+// images (tests/test_gpu_parity.py::test_fused_post_chain_equals_pass_per_pass).  Divisions and pow follow the build's precision class
+// (2-ulp division and exp2(y * log2 x) by default -- the forms SPIR-V grants the reference's shaders; IEEE / libm with PRECISE=1):
+// ncu showed the chain's last kernel compute-bound (208 us for 185 MB of traffic) on libm powf and IEEE division sequences.
+__device__ __forceinline__ float post_pow(float x, float y) {
+#ifdef B200PT_PRECISE
+    return powf(x, y);
+#else
+    return x > 0.0f ? exp2f(__fmul_rn(y, __log2f(x))) : (x == 0.0f ? 0.0f : __int_as_float(0x7FC00000));   // pow(0, y>0) = 0, pow(x<0, non-integer) = NaN
+#endif
+}
 __device__ __forceinline__ float smoothstepf(float e0, float e1, float x) {
-    const float t = clampf(__fdiv_rn(__fsub_rn(x, e0), __fsub_rn(e1, e0)), 0.0f, 1.0f);
+    const float t = clampf(__fsub_rn(x, e0) / __fsub_rn(e1, e0), 0.0f, 1.0f);
     return __fmul_rn(__fmul_rn(t, t), __fsub_rn(3.0f, __fmul_rn(2.0f, t)));
 }
 // BloomDownSample.slang:32-45 (FirstDispatch): one thresholded texel
@@ -20,7 +29,7 @@ __device__ __forceinline__ float3 bloom_threshold_px(float4 s, float start, floa
     const float f = smoothstepf(start, end, br);
     return f3(__fmul_rn(s.x, f), __fmul_rn(s.y, f), __fmul_rn(s.z, f));
 }
-__device__ __forceinline__ float bloom_scale(float acc, float strength) { return __fmul_rn(__fdiv_rn(acc, 25.0f), strength); }   // /25 (Q14), *strength
+__device__ __forceinline__ float bloom_scale(float acc, float strength) { return __fmul_rn(acc / 25.0f, strength); }   // /25 (Q14), *strength
 __device__ __forceinline__ float mix_rn(float p, float q, float w) { return __fadd_rn(p, __fmul_rn(w, __fsub_rn(q, p))); }
 
 __global__ void __launch_bounds__(256) k_bloom_threshold(const float4 *__restrict__ hdr, float4 *__restrict__ mip0, uint32_t npix, PostParams p) {
@@ -121,15 +130,15 @@ __device__ __forceinline__ unsigned char unorm8(float q) {
 // (noinline) serves k_tonemap and k_bloom_final, so both round identically.
 static __device__ __noinline__ uchar4 tonemap_px(float3 h, float3 bl, float exposure, float gamma) {
     float3 c = f3(__fmul_rn(__fadd_rn(h.x, bl.x), exposure), __fmul_rn(__fadd_rn(h.y, bl.y), exposure), __fmul_rn(__fadd_rn(h.z, bl.z), exposure));
-    const float ig = __fdiv_rn(1.0f, gamma);
-    c = f3(powf(c.x, ig), powf(c.y, ig), powf(c.z, ig));
+    const float ig = 1.0f / gamma;
+    c = f3(post_pow(c.x, ig), post_pow(c.y, ig), post_pow(c.z, ig));
     const float3 o = aces_fitted(c);
     return make_uchar4(unorm8(o.x), unorm8(o.y), unorm8(o.z), 255);
 }
 // bilinear footprint of the bloom fetch: uv = xy / size, CLAMP_TO_EDGE, texel centres at +0.5
 struct BloomTap { int x0, x1, y0, y1; float ax, ay; };
 __device__ __forceinline__ BloomTap bloom_tap(int x, int y, int W, int H) {
-    const float u = __fdiv_rn((float)x, (float)W), v = __fdiv_rn((float)y, (float)H);
+    const float u = (float)x / (float)W, v = (float)y / (float)H;
     const float fxp = __fsub_rn(__fmul_rn(u, (float)W), 0.5f), fyp = __fsub_rn(__fmul_rn(v, (float)H), 0.5f);
     const float fx = floorf(fxp), fy = floorf(fyp);
     BloomTap t;
