@@ -270,6 +270,47 @@ def test_checkpoint_resume_is_bit_identical(pt, tmp_path):
     with pytest.raises(pt.B200ptError): Cc.load_checkpoint(tmp_path / "missing.b2pt")
 
 
+def test_cli_renderer_equals_the_api_and_resumes(pt, tmp_path):
+    """b200pt_render (csrc/cli_main.cpp) drives the C-ABI the way the reference's Editor drives PathTracer / PostProcessor: SetScene(file),
+    env map + lookup tables from files, PathTrace until MaxSamplesAccumulated, PostProcess, SaveToFile.  Its PNG must equal the image the
+    same calls produce through the Python harness, and a render split by --checkpoint / --resume must equal the uninterrupted one.
+    This is also the only place the file-based scene / env / LUT entry points run on the GPU box (no reference assets there)."""
+    import os, subprocess, json
+    exe = os.path.join(os.path.dirname(pt.LIB_PATH), "b200pt_render")
+    gltf = util.write_synthetic_gltf(tmp_path)
+    raw = util.gltf_ref.synthetic_env(64, 32, 5)
+    hdr = str(tmp_path / "env.hdr"); util.write_rgbe(hdr, raw[..., :3])
+    lut_dir = util.write_luts_dir(tmp_path / "luts")
+    common = ["--scene", gltf, "--env", hdr, "--luts", lut_dir, "--size", "96", "64", "--depth", "6", "--seed", "5", "--batch", "4", "--quiet",
+              "--volume", "-1", "-1", "-1", "3", "3", "3", "0.3", "0.8", "0.7", "0.6", "--volume-g", "-0.2", "--phase", "1"]
+    r = subprocess.run([exe, *common, "--spp", "6", "--out", str(tmp_path / "a.png")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["spp"] == 6 and info["size"] == [96, 64] and info["paths"] == 6 * 96 * 64
+    a = pt.decode_image(str(tmp_path / "a.png"))
+    # the same sequence through the harness
+    T = pt.PathTracer(0)
+    T.set_luts_dir(lut_dir); T.set_env_map_file(hdr); T.set_scene_file(gltf)
+    assert T.size() == (1620, 1080)                               # aspect 1.5 of the glTF camera (PathTracer.cpp:509-511)
+    T.resize(96, 64)
+    cfg = T.get_config(); cfg.MaxDepth = 6; cfg.MaxSamplesAccumulated = 6; T.set_config(cfg)
+    T.add_volume(CornerMin=(-1, -1, -1), CornerMax=(3, 3, 3), Density=0.3, Color=(0.8, 0.7, 0.6), Anisotropy=-0.2); T.set_phase_function(1)
+    T.path_trace(4, 5); T.path_trace(4, 5)                        # the second call stops at MaxSamplesAccumulated
+    assert T.samples_accumulated() == 6
+    T.post_process()
+    assert np.array_equal(T.get_ldr(), a)
+    assert a[..., :3].std() > 5                                  # not a blank image
+    # split render: 3 spp + checkpoint, then resume to 6
+    ck = str(tmp_path / "acc.b2pt")
+    r1 = subprocess.run([exe, *common, "--spp", "3", "--batch", "3", "--checkpoint", ck, "--out", str(tmp_path / "b3.png")], capture_output=True, text=True)
+    r2 = subprocess.run([exe, *common, "--spp", "6", "--resume", ck, "--out", str(tmp_path / "b6.png")], capture_output=True, text=True)
+    assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr, r2.stderr)
+    assert np.array_equal(pt.decode_image(str(tmp_path / "b6.png")), a)
+    # errors surface as non-zero exit codes with the library's message
+    r3 = subprocess.run([exe, "--scene", str(tmp_path / "missing.gltf"), "--env", hdr, "--luts", lut_dir, "--out", str(tmp_path / "c.png")], capture_output=True, text=True)
+    assert r3.returncode != 0 and "failed" in r3.stderr
+
+
 def test_errors_are_codes_not_aborts(pt):
     T = pt.PathTracer(0)
     with pytest.raises(pt.B200ptError) as e:

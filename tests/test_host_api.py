@@ -99,34 +99,11 @@ def test_decoders_on_shipped_assets():
     assert np.array_equal(hdr, orc.load_hdr(os.path.join(util.REF_ASSETS, "meadow_2_4k.hdr")))
 
 
-def _write_rgbe(path, rgb):
-    """minimal RLE Radiance writer for the decoder test"""
-    h, w, _ = rgb.shape
-    m = rgb.max(-1); e = np.where(m > 1e-32, np.floor(np.log2(np.maximum(m, 1e-38))) + 1, 0)
-    scale = np.where(m > 1e-32, 256.0 / (2.0 ** e), 0)
-    out = np.zeros((h, w, 4), np.uint8); out[..., :3] = np.clip(rgb * scale[..., None], 0, 255).astype(np.uint8); out[..., 3] = np.where(m > 1e-32, e + 128, 0)
-    with open(path, "wb") as f:
-        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (h, w))
-        for y in range(h):
-            f.write(bytes([2, 2, w >> 8, w & 255]))
-            for c in range(4):
-                row = out[y, :, c]; i = 0
-                while i < w:
-                    run = 1
-                    while i + run < w and run < 127 and row[i + run] == row[i]: run += 1
-                    if run >= 4: f.write(bytes([128 + run, row[i]])); i += run
-                    else:
-                        j = i
-                        while j < w and j - i < 128 and not (j + 3 < w and row[j] == row[j + 1] == row[j + 2] == row[j + 3]): j += 1
-                        j = max(j, i + 1); f.write(bytes([j - i]) + bytes(row[i:j])); i = j
-    return out
-
-
 def test_hdr_decoder(tmp_path):
     rng = np.random.default_rng(2)
     rgb = (np.exp(rng.normal(0, 2, (9, 40, 3))) * (rng.random((9, 40, 1)) > 0.1)).astype(np.float32)
     rgb[:, 10:30] = rgb[:, 10:11]                                  # runs
-    p = str(tmp_path / "t.hdr"); enc = _write_rgbe(p, rgb)
+    p = str(tmp_path / "t.hdr"); enc = util.write_rgbe(p, rgb)
     got = pt.decode_hdr(p)
     exp = np.ones((9, 40, 4), np.float32)
     exp[..., :3] = enc[..., :3].astype(np.float32) * np.where(enc[..., 3:] != 0, np.ldexp(np.float32(1.0), enc[..., 3:].astype(int) - 136), 0).astype(np.float32)
@@ -192,41 +169,7 @@ def test_cpp_gltf_loader_matches_oracle_loader_on_shipped_scenes(name):
 
 def test_cpp_gltf_loader_on_a_synthetic_scene(tmp_path):
     """Self-authored glTF exercising matrices, TRS nesting, all material extensions, all texture slots, u8/u16/u32 indices."""
-    from PIL import Image
-    rng = np.random.default_rng(3)
-    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.5]], np.float32)
-    nrm = np.array([[0, 0, 2], [0, 0, 1], [0.1, 0, 1], [0, 0.3, 1]], np.float32)
-    uv = rng.random((4, 2)).astype(np.float32)
-    i8 = np.array([0, 1, 2, 1, 3, 2], np.uint8); i16 = i8.astype(np.uint16); i32 = i8.astype(np.uint32)
-    blob = b""; views = []; accs = []
-    def add(arr, comp, typ):
-        nonlocal blob
-        while len(blob) % 4: blob += b"\0"
-        views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": arr.nbytes}); blob += arr.tobytes()
-        accs.append({"bufferView": len(views) - 1, "componentType": comp, "count": len(arr), "type": typ}); return len(accs) - 1
-    aP, aN, aT = add(pos, 5126, "VEC3"), add(nrm, 5126, "VEC3"), add(uv, 5126, "VEC2")
-    a8, a16, a32 = add(i8, 5121, "SCALAR"), add(i16, 5123, "SCALAR"), add(i32, 5125, "SCALAR")
-    (tmp_path / "s.bin").write_bytes(blob)
-    for n in ("base", "nrm", "mr", "em"):
-        Image.fromarray(rng.integers(0, 256, (5, 7, 3), dtype=np.uint8), "RGB").save(tmp_path / f"{n}.png")
-    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0, 3]}],
-         "nodes": [{"children": [1, 2], "translation": [1, 2, 3], "rotation": [0.1825742, 0.3651484, 0.5477226, 0.7302967], "scale": [1, 2, 0.5]},
-                   {"mesh": 0, "matrix": [1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0.5, 0.25, -2, 1]},
-                   {"camera": 0, "translation": [0, 1, 8], "rotation": [0, 0.0871557, 0, 0.9961947]},
-                   {"mesh": 1, "scale": [2, 2, 2]}],
-         "cameras": [{"type": "perspective", "perspective": {"aspectRatio": 1.5, "yfov": 0.6, "znear": 0.1}}],
-         "meshes": [{"primitives": [{"attributes": {"POSITION": aP, "NORMAL": aN, "TEXCOORD_0": aT}, "indices": a8, "material": 0},
-                                    {"attributes": {"POSITION": aP, "NORMAL": aN}, "indices": a16, "material": 1}]},
-                    {"primitives": [{"attributes": {"POSITION": aP, "NORMAL": aN, "TEXCOORD_0": aT}, "indices": a32}]}],
-         "materials": [{"name": "full", "emissiveFactor": [0.5, 0.25, 1.0], "normalTexture": {"index": 1}, "emissiveTexture": {"index": 3},
-                        "pbrMetallicRoughness": {"baseColorFactor": [0.1, 0.2, 0.3, 1], "metallicFactor": 0.25, "roughnessFactor": 0.6, "baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 2}},
-                        "extensions": {"KHR_materials_emissive_strength": {"emissiveStrength": 7.5}, "KHR_materials_ior": {"ior": 1.33}, "KHR_materials_transmission": {"transmissionFactor": 0.75},
-                                       "KHR_materials_specular": {"specularColorFactor": [0.9, 0.8, 0.7]}, "KHR_materials_anisotropy": {"anisotropyStrength": 0.4, "anisotropyRotation": 0.5}}},
-                       {"name": "defaults"}],
-         "textures": [{"source": 0}, {"source": 1}, {"source": 2}, {"source": 3}],
-         "images": [{"uri": "base.png"}, {"uri": "nrm.png"}, {"uri": "mr.png"}, {"uri": "em.png"}],
-         "accessors": accs, "bufferViews": views, "buffers": [{"uri": "s.bin", "byteLength": len(blob)}]}
-    p = str(tmp_path / "s.gltf"); open(p, "w").write(json.dumps(g))
+    p = util.write_synthetic_gltf(tmp_path)
     _compare_loader(p)
     b = pt.load_gltf(p)
     m = np.frombuffer(b["materials_bytes"].tobytes(), gltf_ref.MATERIAL_DTYPE)
@@ -325,3 +268,16 @@ def test_volume_struct_and_defaults_without_gpu():
     assert (v.Density, v.Anisotropy, v.Alpha, v.DropletSize, v.DensityDataIndex) == (1.0, 0.0, 1.0, 20.0, -1)
     assert v.ApproximatedScatteringForClouds == 0 and abs(v.ApproximatedScatteringFalloff - 0.8) < 1e-7
     assert B.lib().b200pt_default_volume(None) == B.ERR_WRONG_ARGUMENTS
+
+
+def test_cli_renderer_builds_and_fails_loudly_without_a_gpu():
+    """b200pt_render (csrc/cli_main.cpp), the headless stand-in for the reference's Editor: built next to the library, prints its usage,
+    and -- like every product path -- refuses to run without a CUDA device instead of falling back to anything."""
+    import subprocess, torch
+    exe = os.path.join(os.path.dirname(pt.LIB_PATH), "b200pt_render")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: b200pt_render" in r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "--scene", "s.gltf", "--env", "e.hdr", "--luts", "d", "--out", "o.png"], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CUDA device" in r.stderr
