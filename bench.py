@@ -53,37 +53,58 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler runs from the first warm-up
+    step to the end of the timed steps; mark_begin() / mark_end() bracket the timed region.  Samples inside the bracket are reported; if
+    the region is shorter than the sampling period (multi-GPU runs finish a step in ~10 ms) the samples of the whole loaded window
+    (warm-up + timed steps, same kernels, same clocks) are used instead and "window" says so."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
-        self.rows = []; self.proc = None; self.gpu = gpu_index
+        self.rows = []; self.proc = None; self.gpu = gpu_index; self.i0 = None; self.i1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True); self.th.start()
         except Exception:
             self.proc = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        try:
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def mark_begin(self): self.i0 = len(self.rows)
+
+    def mark_end(self): self.i1 = len(self.rows)
 
     def stop(self):
-        if not self.proc: return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try: self.proc.wait(timeout=2)
-        except Exception: pass
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        if not self.proc: return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        rows = list(self.rows)
+        i0 = self.i0 if self.i0 is not None else 0
+        i1 = self.i1 if self.i1 is not None else len(rows)
+        timed = [r for r in rows[i0:i1] if len(r) >= 9]
+        window = "timed region"
+        if not timed:
+            timed = [r for r in rows if len(r) >= 9]; window = "warm-up + timed steps (timed region shorter than the 100 ms sampling period)"
+        def num(x):
+            try: return float(x)
+            except Exception: return None
+        sm = [v for v in (num(r[1]) for r in timed) if v is not None]
+        mx = [v for v in (num(r[2]) for r in timed) if v is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) < 9: continue
+        for r in timed:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"): reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def synthetic_env_4k():
@@ -274,18 +295,20 @@ def main():
         if world > 1: dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(args.warmup): step()
     barrier()
-    sampler = ClockSampler(local); sampler.start()
     c0 = T.counters()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps): step()
     ev1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     if abs(ms * 1e-3 - wall) > 0.05 * wall + 2e-3:   # device-event time must agree with the wall-clock bracket
         ms = max(ms, wall * 1e3)
