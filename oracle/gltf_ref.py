@@ -82,9 +82,29 @@ def load_gltf(path, decode_image=_decode_image):
     """Returns a dict: meshes [(verts(VERTEX_DTYPE), indices u32)], materials (MATERIAL_DTYPE),
     material_names, textures [HxWxC u8], instances [(transform col-major f32[16], mesh, material)],
     camera_view (f32[16] col-major) , aspect."""
-    g = json.load(open(path))
+    raw = open(path, "rb").read()
+    glb_bin = None
+    if raw[:4] == b"glTF":                                  # binary glTF container: JSON chunk + optional BIN chunk (= buffer 0)
+        import struct
+        total = min(struct.unpack_from("<I", raw, 8)[0], len(raw)); o = 12; jtxt = None
+        while o + 8 <= total:
+            ln, ty = struct.unpack_from("<II", raw, o); o += 8
+            if ty == 0x4E4F534A and jtxt is None: jtxt = raw[o:o + ln]
+            elif ty == 0x004E4942 and glb_bin is None: glb_bin = raw[o:o + ln]
+            o += (ln + 3) & ~3
+        g = json.loads(jtxt.decode("utf-8"))
+    else:
+        g = json.loads(raw.decode("utf-8"))
     base = os.path.dirname(os.path.abspath(path))
-    buffers = [open(os.path.join(base, b["uri"]), "rb").read() for b in g["buffers"]]
+
+    def _buffer(i, b):
+        uri = b.get("uri")
+        if uri is None: return glb_bin
+        if uri.startswith("data:"):
+            import base64
+            return base64.b64decode(uri.split(";base64,", 1)[1])
+        return open(os.path.join(base, uri), "rb").read()
+    buffers = [_buffer(i, b) for i, b in enumerate(g["buffers"])]
 
     # ---- meshes: one per primitive
     meshes, prim_of_mesh, mesh_material = [], [], []

@@ -281,3 +281,36 @@ def test_cli_renderer_builds_and_fails_loudly_without_a_gpu():
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "--scene", "s.gltf", "--env", "e.hdr", "--luts", "d", "--out", "o.png"], capture_output=True, text=True)
         assert r.returncode != 0 and "no CUDA device" in r.stderr
+
+
+def test_cpp_gltf_loader_reads_glb_and_base64_buffers(tmp_path):
+    """assimp's glTF2 importer (the reference's loader, AssetImporterImpl.cpp:82-97) also reads binary .glb containers and base64 data: URIs
+    for geometry buffers.  The same synthetic scene stored three ways must load to identical arrays; embedded TEXTURES are rejected with an
+    error (the reference only loads texture files next to the model, :287-328)."""
+    import base64, struct
+    p = util.write_synthetic_gltf(tmp_path)
+    g = json.load(open(p)); blob = (tmp_path / "s.bin").read_bytes()
+    ref = pt.load_gltf(p)
+    # (a) base64 data URI
+    g64 = json.loads(json.dumps(g)); g64["buffers"][0] = {"uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode(), "byteLength": len(blob)}
+    pa = str(tmp_path / "s64.gltf"); open(pa, "w").write(json.dumps(g64))
+    # (b) .glb: JSON chunk + BIN chunk, textures stay external
+    gb = json.loads(json.dumps(g)); gb["buffers"][0] = {"byteLength": len(blob)}
+    jtxt = json.dumps(gb).encode(); jtxt += b" " * (-len(jtxt) % 4); bchunk = blob + b"\\0" * (-len(blob) % 4)
+    glb = b"glTF" + struct.pack("<II", 2, 12 + 8 + len(jtxt) + 8 + len(bchunk)) + struct.pack("<II", len(jtxt), 0x4E4F534A) + jtxt + struct.pack("<II", len(bchunk), 0x004E4942) + bchunk
+    pb = str(tmp_path / "s.glb"); open(pb, "wb").write(glb)
+    for q in (pa, pb):
+        _compare_loader(q)                                         # C++ loader == oracle-side python loader
+        b = pt.load_gltf(q)
+        assert len(b["meshes"]) == len(ref["meshes"]) and len(b["instances"]) == len(ref["instances"])
+        for (v0, i0), (v1, i1) in zip(ref["meshes"], b["meshes"]):
+            assert np.array_equal(v0, v1) and np.array_equal(i0, i1)
+        assert np.array_equal(ref["materials_bytes"], b["materials_bytes"])
+        for t0, t1 in zip(ref["textures"], b["textures"]): assert np.array_equal(t0, t1)
+    # embedded image -> error code, no crash
+    ge = json.loads(json.dumps(g)); ge["images"][0] = {"uri": "data:image/png;base64,AAAA"}
+    pe = str(tmp_path / "emb.gltf"); open(pe, "w").write(json.dumps(ge))
+    with pytest.raises(pt.B200ptError): pt.load_gltf(pe)
+    # truncated .glb -> error code
+    open(str(tmp_path / "bad.glb"), "wb").write(glb[:40])
+    with pytest.raises(pt.B200ptError): pt.load_gltf(str(tmp_path / "bad.glb"))

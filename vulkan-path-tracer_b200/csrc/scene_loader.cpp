@@ -137,9 +137,44 @@ static bool read_all(const std::string &path, std::vector<uint8_t> &out) {
     return got == out.size();
 }
 
+// base64 payload of a "data:<mime>;base64,<payload>" URI (glTF 2.0 spec 3.6.1.1); assimp's glTF2 importer decodes these transparently
+static bool decode_data_uri(const std::string &uri, std::vector<uint8_t> &out) {
+    const size_t k = uri.find(";base64,");
+    if (k == std::string::npos) return false;
+    out.clear();
+    uint32_t acc = 0; int bits = 0;
+    for (size_t i = k + 8; i < uri.size(); i++) {
+        const char c = uri[i];
+        int v;
+        if (c >= 'A' && c <= 'Z') v = c - 'A'; else if (c >= 'a' && c <= 'z') v = c - 'a' + 26; else if (c >= '0' && c <= '9') v = c - '0' + 52;
+        else if (c == '+' || c == '-') v = 62; else if (c == '/' || c == '_') v = 63; else if (c == '=') break; else continue;
+        acc = (acc << 6) | (uint32_t)v; bits += 6;
+        if (bits >= 8) { bits -= 8; out.push_back((uint8_t)((acc >> bits) & 0xFFu)); }
+    }
+    return true;
+}
+
 bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
     std::vector<uint8_t> text;
     if (!read_all(path, text)) { err = "cannot read " + path; return false; }
+    // binary glTF (.glb, spec chapter 4): 12-byte header "glTF" | version | length, then a JSON chunk and an optional BIN chunk (= buffer 0)
+    std::vector<uint8_t> glb_bin; bool is_glb = false;
+    if (text.size() >= 20 && memcmp(text.data(), "glTF", 4) == 0) {
+        is_glb = true;
+        auto u32 = [&](size_t o) { uint32_t v; memcpy(&v, text.data() + o, 4); return v; };
+        if (u32(4) != 2u) { err = "unsupported .glb container version"; return false; }
+        const size_t total = std::min<size_t>(u32(8), text.size());
+        size_t o = 12; std::vector<uint8_t> json;
+        while (o + 8 <= total) {
+            const size_t len = u32(o); const uint32_t type = u32(o + 4); o += 8;
+            if (o + len > total) { err = "truncated .glb chunk"; return false; }
+            if (type == 0x4E4F534Au && json.empty()) json.assign(text.begin() + (long)o, text.begin() + (long)(o + len));
+            else if (type == 0x004E4942u && glb_bin.empty()) glb_bin.assign(text.begin() + (long)o, text.begin() + (long)(o + len));
+            o += (len + 3u) & ~(size_t)3u;
+        }
+        if (json.empty()) { err = ".glb without a JSON chunk"; return false; }
+        text.swap(json);
+    }
     JVal g; JParser jp{ (const char *)text.data(), (const char *)text.data() + text.size(), "" };
     if (!jp.val(g) || g.t != JVal::Obj) { err = "glTF JSON parse error: " + jp.err; return false; }
     std::string base = path; { size_t k = base.find_last_of("/\\"); base = (k == std::string::npos) ? "." : base.substr(0, k); }   // AssetImporterImpl.cpp:283-284
@@ -147,9 +182,13 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
     std::vector<std::vector<uint8_t>> buffers;
     if (const JVal *bs = g.get("buffers")) for (size_t i = 0; i < bs->size(); i++) {
         const JVal *uri = (*bs)[i].get("uri");
-        if (!uri || uri->t != JVal::Str || uri->s.rfind("data:", 0) == 0) { err = "only external .bin buffers are supported"; return false; }
         buffers.emplace_back();
-        if (!read_all(base + "/" + uri->s, buffers.back())) { err = "cannot read buffer " + uri->s; return false; }
+        if (!uri || uri->t != JVal::Str) {                                 // the BIN chunk of a .glb
+            if (!is_glb || i != 0 || glb_bin.empty()) { err = "buffer without uri outside a .glb BIN chunk"; return false; }
+            buffers.back() = glb_bin;
+        } else if (uri->s.rfind("data:", 0) == 0) {
+            if (!decode_data_uri(uri->s, buffers.back())) { err = "unsupported data: URI encoding (base64 expected)"; return false; }
+        } else if (!read_all(base + "/" + uri->s, buffers.back())) { err = "cannot read buffer " + uri->s; return false; }
     }
     const JVal *accs = g.get("accessors"), *views = g.get("bufferViews");
     auto accessor = [&](int idx, int want_comps, std::vector<float> *fout, std::vector<uint32_t> *uout, size_t &count) -> bool {
@@ -230,11 +269,13 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
     bool need_default = false; for (int m : mesh_material) if (m < 0) need_default = true;
     struct TexPaths { std::string base, normal, rough, metal, emissive; };
     std::vector<TexPaths> tps;
+    bool embedded_image = false;
     auto tex_path = [&](const JVal *ti) -> std::string {
         if (!ti || !texs) return "";
         int idx = (int)ti->num("index", -1); if (idx < 0 || (size_t)idx >= texs->size()) return "";
         int src = (int)(*texs)[idx].num("source", -1); if (src < 0 || !imgs || (size_t)src >= imgs->size()) return "";
-        const JVal *uri = (*imgs)[src].get("uri"); if (!uri) return "";
+        const JVal *uri = (*imgs)[src].get("uri");
+        if (!uri || uri->s.rfind("data:", 0) == 0) { embedded_image = true; return ""; }         // bufferView / data: images: the reference only loads texture FILES (:287-328)
         return base + "/" + uri->s;                                                            // :287-328
     };
     for (size_t i = 0; i < nmat + (need_default ? 1 : 0); i++) {
@@ -259,6 +300,7 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
         tp.rough = tp.metal = tex_path(pbr->get("metallicRoughnessTexture")); tp.emissive = tex_path(m.get("emissiveTexture"));
         tps.push_back(tp);
     }
+    if (embedded_image) { err = "embedded (bufferView / data: URI) textures are not supported: the reference loads textures from files next to the model only"; return false; }
     // ---- texture table in PathTracer::SetScene order (PathTracer.cpp:228-408)
     std::map<std::string, uint32_t> index_of;
     auto get_tex = [&](const std::string &p, const char *def_key, std::vector<uint8_t> def_px, bool single, uint32_t &out_idx) -> bool {
