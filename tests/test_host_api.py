@@ -296,7 +296,7 @@ def test_cpp_gltf_loader_reads_glb_and_base64_buffers(tmp_path):
     pa = str(tmp_path / "s64.gltf"); open(pa, "w").write(json.dumps(g64))
     # (b) .glb: JSON chunk + BIN chunk, textures stay external
     gb = json.loads(json.dumps(g)); gb["buffers"][0] = {"byteLength": len(blob)}
-    jtxt = json.dumps(gb).encode(); jtxt += b" " * (-len(jtxt) % 4); bchunk = blob + b"\\0" * (-len(blob) % 4)
+    jtxt = json.dumps(gb).encode(); jtxt += b" " * (-len(jtxt) % 4); bchunk = blob + b"\0" * (-len(blob) % 4)
     glb = b"glTF" + struct.pack("<II", 2, 12 + 8 + len(jtxt) + 8 + len(bchunk)) + struct.pack("<II", len(jtxt), 0x4E4F534A) + jtxt + struct.pack("<II", len(bchunk), 0x004E4942) + bchunk
     pb = str(tmp_path / "s.glb"); open(pb, "wb").write(glb)
     for q in (pa, pb):
@@ -314,3 +314,52 @@ def test_cpp_gltf_loader_reads_glb_and_base64_buffers(tmp_path):
     # truncated .glb -> error code
     open(str(tmp_path / "bad.glb"), "wb").write(glb[:40])
     with pytest.raises(pt.B200ptError): pt.load_gltf(str(tmp_path / "bad.glb"))
+
+
+def _write_png_adam7(path, arr, ctype, depth=8, palette=None, sub_filter=False):
+    """Tiny PNG writer with Adam7 interlacing (PIL cannot write interlaced files).  arr: HxWxC uint8 samples (C = channels of ctype; for
+    depth < 8, values < 2**depth)."""
+    import struct, zlib
+    H, W = arr.shape[:2]; C = arr.shape[2]
+    def chunk(t, d): return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    xs, ys, dx, dy = (0, 4, 0, 2, 0, 1, 0), (0, 0, 4, 0, 2, 0, 1), (8, 8, 4, 4, 2, 2, 1), (8, 8, 8, 4, 4, 2, 2)
+    raw = b""
+    for p in range(7):
+        sub = arr[ys[p]::dy[p], xs[p]::dx[p]]
+        if sub.shape[0] == 0 or sub.shape[1] == 0: continue
+        for row in sub:
+            samples = row.reshape(-1)
+            if depth == 8: b = bytes(samples)
+            elif depth == 16: b = b"".join(bytes([int(v), 0x5A]) for v in samples)
+            else:
+                bits = "".join(format(int(v), f"0{depth}b") for v in samples); bits += "0" * (-len(bits) % 8)
+                b = bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8))
+            if sub_filter:
+                bpp = max(1, C * depth // 8); f = bytearray(b)
+                for i in range(len(b) - 1, bpp - 1, -1): f[i] = (b[i] - b[i - bpp]) & 255
+                raw += b"\x01" + bytes(f)
+            else:
+                raw += b"\x00" + b
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, ctype, 0, 0, 1))
+    if palette is not None: out += chunk(b"PLTE", bytes(palette.reshape(-1)))
+    out += chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    open(path, "wb").write(out)
+
+
+def test_png_decoder_reads_adam7_interlaced_files(tmp_path):
+    """stb_image (the reference's texture decoder, AssetImporterImpl.cpp:494-545) reads interlaced PNGs; so does ours, for every colour type,
+    1..16-bit samples, odd sizes smaller than the 8x8 interlace cell, and filtered scanlines inside the passes."""
+    rng = np.random.default_rng(11)
+    for (W, H) in ((1, 1), (3, 2), (9, 5), (33, 17)):
+        rgba = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+        p = str(tmp_path / "a.png"); _write_png_adam7(p, rgba, 6); assert np.array_equal(pt.decode_image(p), rgba)
+        _write_png_adam7(p, rgba, 6, sub_filter=True); assert np.array_equal(pt.decode_image(p), rgba)
+        rgb = rgba[..., :3]; _write_png_adam7(p, rgb, 2); got = pt.decode_image(p); assert np.array_equal(got[..., :3], rgb) and np.all(got[..., 3] == 255)
+        _write_png_adam7(p, rgba, 6, depth=16); assert np.array_equal(pt.decode_image(p), rgba)      # high byte kept
+        ga = rgba[..., :2]; _write_png_adam7(p, ga, 4); got = pt.decode_image(p)
+        assert np.array_equal(got[..., 0], ga[..., 0]) and np.array_equal(got[..., 1], ga[..., 0]) and np.array_equal(got[..., 3], ga[..., 1])
+        for depth in (1, 2, 4):
+            g = rng.integers(0, 2 ** depth, (H, W, 1), dtype=np.uint8); _write_png_adam7(p, g, 0, depth=depth)
+            assert np.array_equal(pt.decode_image(p)[..., 0], g[..., 0] * (255 // (2 ** depth - 1)))
+            pal = rng.integers(0, 256, (2 ** depth, 3), dtype=np.uint8); _write_png_adam7(p, g, 3, depth=depth, palette=pal)
+            assert np.array_equal(pt.decode_image(p)[..., :3], pal[g[..., 0]])

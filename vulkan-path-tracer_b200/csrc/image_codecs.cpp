@@ -54,31 +54,25 @@ static bool decode_png(const std::vector<uint8_t> &d, uint32_t &W, uint32_t &H, 
         pos += 12 + (size_t)len;
     }
     if (!have_ihdr || W == 0 || H == 0) { err = "missing IHDR"; return false; }
-    if (interlace != 0) { err = "interlaced PNG not supported"; return false; }
+    if (interlace > 1) { err = "unknown PNG interlace method"; return false; }
     int chans = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!chans || !(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) { err = "unsupported PNG format"; return false; }
-    const size_t bpp_bits = (size_t)chans * depth, stride = (W * bpp_bits + 7) / 8, bpp = (bpp_bits + 7) / 8;
-    std::vector<uint8_t> raw((stride + 1) * (size_t)H);
+    const size_t bpp_bits = (size_t)chans * depth, bpp = (bpp_bits + 7) / 8;
+    auto stride_of = [&](uint32_t w) { return ((size_t)w * bpp_bits + 7) / 8; };
+    // Adam7 (PNG spec 8.2): seven reduced images, each filtered on its own; interlace == 0 is the single full-size "pass"
+    static const int xs[7] = { 0, 4, 0, 2, 0, 1, 0 }, ys[7] = { 0, 0, 4, 0, 2, 0, 1 }, dxs[7] = { 8, 8, 4, 4, 2, 2, 1 }, dys[7] = { 8, 8, 8, 4, 4, 2, 2 };
+    struct Pass { uint32_t w, h; int x0, y0, dx, dy; };
+    std::vector<Pass> passes;
+    if (!interlace) passes.push_back({ W, H, 0, 0, 1, 1 });
+    else for (int p = 0; p < 7; p++) {
+        const uint32_t pw = (W > (uint32_t)xs[p]) ? (W - xs[p] + dxs[p] - 1) / dxs[p] : 0, ph = (H > (uint32_t)ys[p]) ? (H - ys[p] + dys[p] - 1) / dys[p] : 0;
+        if (pw && ph) passes.push_back({ pw, ph, xs[p], ys[p], dxs[p], dys[p] });
+    }
+    size_t raw_size = 0; for (const Pass &ps : passes) raw_size += (stride_of(ps.w) + 1) * (size_t)ps.h;
+    std::vector<uint8_t> raw(raw_size);
     uLongf rawlen = (uLongf)raw.size();
     int zr = uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size());
     if (zr != Z_OK || rawlen != raw.size()) { err = "PNG inflate failed"; return false; }
-    std::vector<uint8_t> img(stride * (size_t)H);
-    for (uint32_t y = 0; y < H; y++) {
-        const uint8_t *src = &raw[(stride + 1) * (size_t)y]; uint8_t ft = src[0]; src++;
-        uint8_t *cur = &img[stride * (size_t)y]; const uint8_t *prev = y ? &img[stride * (size_t)(y - 1)] : nullptr;
-        for (size_t i = 0; i < stride; i++) {
-            int a = i >= bpp ? cur[i - bpp] : 0, b = prev ? prev[i] : 0, c = (prev && i >= bpp) ? prev[i - bpp] : 0, x = src[i];
-            switch (ft) {
-            case 0: break;
-            case 1: x += a; break;
-            case 2: x += b; break;
-            case 3: x += (a + b) >> 1; break;
-            case 4: x += paeth(a, b, c); break;
-            default: err = "bad PNG filter"; return false;
-            }
-            cur[i] = (uint8_t)x;
-        }
-    }
     rgba.resize((size_t)W * H * 4);
     auto sample = [&](const uint8_t *row, size_t idx) -> int {   // idx = sample index within the row
         if (depth == 8) return row[idx];
@@ -87,19 +81,42 @@ static bool decode_png(const std::vector<uint8_t> &d, uint32_t &W, uint32_t &H, 
         return v;
     };
     const int scale = depth < 8 ? (depth == 1 ? 255 : depth == 2 ? 85 : 17) : 1;
-    for (uint32_t y = 0; y < H; y++) {
-        const uint8_t *row = &img[stride * (size_t)y];
-        for (uint32_t x = 0; x < W; x++) {
-            uint8_t *o = &rgba[((size_t)y * W + x) * 4];
-            switch (ctype) {
-            case 0: { int g = sample(row, x); int g8 = depth < 8 ? g * scale : g; o[0] = o[1] = o[2] = (uint8_t)g8; o[3] = 255;
-                      if (trns.size() >= 2) { int t = depth == 16 ? trns[0] : ((trns[0] << 8) | trns[1]); if (depth == 16 ? (row[x * 2] == trns[0] && row[x * 2 + 1] == trns[1]) : g == t) o[3] = 0; } } break;
-            case 2: { o[0] = (uint8_t)sample(row, x * 3); o[1] = (uint8_t)sample(row, x * 3 + 1); o[2] = (uint8_t)sample(row, x * 3 + 2); o[3] = 255;
-                      if (trns.size() >= 6 && depth == 8 && o[0] == trns[1] && o[1] == trns[3] && o[2] == trns[5]) o[3] = 0; } break;
-            case 3: { int i = sample(row, x); if ((size_t)i * 3 + 2 >= plte.size()) { err = "PNG palette index out of range"; return false; }
-                      o[0] = plte[i * 3]; o[1] = plte[i * 3 + 1]; o[2] = plte[i * 3 + 2]; o[3] = (size_t)i < trns.size() ? trns[i] : 255; } break;
-            case 4: { int g = sample(row, x * 2); o[0] = o[1] = o[2] = (uint8_t)g; o[3] = (uint8_t)sample(row, x * 2 + 1); } break;
-            case 6: { o[0] = (uint8_t)sample(row, x * 4); o[1] = (uint8_t)sample(row, x * 4 + 1); o[2] = (uint8_t)sample(row, x * 4 + 2); o[3] = (uint8_t)sample(row, x * 4 + 3); } break;
+    size_t raw_off = 0;
+    std::vector<uint8_t> img;
+    for (const Pass &ps : passes) {
+        const size_t stride = stride_of(ps.w);
+        img.assign(stride * (size_t)ps.h, 0);
+        for (uint32_t y = 0; y < ps.h; y++) {
+            const uint8_t *src = &raw[raw_off + (stride + 1) * (size_t)y]; uint8_t ft = src[0]; src++;
+            uint8_t *cur = &img[stride * (size_t)y]; const uint8_t *prev = y ? &img[stride * (size_t)(y - 1)] : nullptr;
+            for (size_t i = 0; i < stride; i++) {
+                int a = i >= bpp ? cur[i - bpp] : 0, b = prev ? prev[i] : 0, c = (prev && i >= bpp) ? prev[i - bpp] : 0, x = src[i];
+                switch (ft) {
+                case 0: break;
+                case 1: x += a; break;
+                case 2: x += b; break;
+                case 3: x += (a + b) >> 1; break;
+                case 4: x += paeth(a, b, c); break;
+                default: err = "bad PNG filter"; return false;
+                }
+                cur[i] = (uint8_t)x;
+            }
+        }
+        raw_off += (stride + 1) * (size_t)ps.h;
+        for (uint32_t y = 0; y < ps.h; y++) {
+            const uint8_t *row = &img[stride * (size_t)y];
+            for (uint32_t x = 0; x < ps.w; x++) {
+                uint8_t *o = &rgba[((size_t)(ps.y0 + (int)y * ps.dy) * W + (size_t)(ps.x0 + (int)x * ps.dx)) * 4];
+                switch (ctype) {
+                case 0: { int g = sample(row, x); int g8 = depth < 8 ? g * scale : g; o[0] = o[1] = o[2] = (uint8_t)g8; o[3] = 255;
+                          if (trns.size() >= 2) { int t = depth == 16 ? trns[0] : ((trns[0] << 8) | trns[1]); if (depth == 16 ? (row[x * 2] == trns[0] && row[x * 2 + 1] == trns[1]) : g == t) o[3] = 0; } } break;
+                case 2: { o[0] = (uint8_t)sample(row, x * 3); o[1] = (uint8_t)sample(row, x * 3 + 1); o[2] = (uint8_t)sample(row, x * 3 + 2); o[3] = 255;
+                          if (trns.size() >= 6 && depth == 8 && o[0] == trns[1] && o[1] == trns[3] && o[2] == trns[5]) o[3] = 0; } break;
+                case 3: { int i = sample(row, x); if ((size_t)i * 3 + 2 >= plte.size()) { err = "PNG palette index out of range"; return false; }
+                          o[0] = plte[i * 3]; o[1] = plte[i * 3 + 1]; o[2] = plte[i * 3 + 2]; o[3] = (size_t)i < trns.size() ? trns[i] : 255; } break;
+                case 4: { int g = sample(row, x * 2); o[0] = o[1] = o[2] = (uint8_t)g; o[3] = (uint8_t)sample(row, x * 2 + 1); } break;
+                case 6: { o[0] = (uint8_t)sample(row, x * 4); o[1] = (uint8_t)sample(row, x * 4 + 1); o[2] = (uint8_t)sample(row, x * 4 + 2); o[3] = (uint8_t)sample(row, x * 4 + 3); } break;
+                }
             }
         }
     }
