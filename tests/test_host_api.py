@@ -363,3 +363,33 @@ def test_png_decoder_reads_adam7_interlaced_files(tmp_path):
             assert np.array_equal(pt.decode_image(p)[..., 0], g[..., 0] * (255 // (2 ** depth - 1)))
             pal = rng.integers(0, 256, (2 ** depth, 3), dtype=np.uint8); _write_png_adam7(p, g, 3, depth=depth, palette=pal)
             assert np.array_equal(pt.decode_image(p)[..., :3], pal[g[..., 0]])
+
+
+def test_progressive_jpeg_decodes_like_the_baseline_file(tmp_path):
+    """stb_image (AssetImporterImpl.cpp:494-545) reads progressive JPEGs (SOF2: spectral selection + successive approximation, ITU T.81
+    annex G).  The coefficients of a progressive file equal those of the baseline file made from the same image and quality, so OUR decode of
+    both must be bit-identical; against libjpeg only IDCT / up-sampling rounding differs (same bound as the baseline test)."""
+    from PIL import Image
+    rng = np.random.default_rng(4)
+    yy, xx = np.mgrid[0:75, 0:118]
+    base = np.stack([128 + 100 * np.sin(xx / 13.0), 128 + 100 * np.cos(yy / 9.0), 128 + 60 * np.sin((xx + yy) / 19.0)], -1)
+    img = np.clip(base + rng.normal(0, 8, base.shape), 0, 255).astype(np.uint8)
+    for sub, name in [(2, "420"), (0, "444"), (1, "422")]:
+        qb = str(tmp_path / f"b{name}.jpg"); qp = str(tmp_path / f"p{name}.jpg")
+        Image.fromarray(img, "RGB").save(qb, quality=88, subsampling=sub)
+        Image.fromarray(img, "RGB").save(qp, quality=88, subsampling=sub, progressive=True)
+        assert b"\xff\xc2" in open(qp, "rb").read() and b"\xff\xc2" not in open(qb, "rb").read()
+        mine = pt.decode_image(qp)
+        assert np.array_equal(mine, pt.decode_image(qb)), name
+        d = np.abs(mine.astype(int) - np.asarray(Image.open(qp).convert("RGBA")).astype(int))
+        assert d.max() <= 6 and d.mean() < 0.8, (name, d.max(), d.mean())
+    qg = str(tmp_path / "pg.jpg"); Image.fromarray(img[..., 1], "L").save(qg, quality=85, progressive=True)
+    assert np.abs(pt.decode_image(qg).astype(int) - np.asarray(Image.open(qg).convert("RGBA")).astype(int)).max() <= 2
+    # restart intervals inside progressive scans
+    qr = str(tmp_path / "pr.jpg"); Image.fromarray(img, "RGB").save(qr, quality=80, progressive=True, restart_marker_blocks=3)
+    d = np.abs(pt.decode_image(qr).astype(int) - np.asarray(Image.open(qr).convert("RGBA")).astype(int))
+    assert d.max() <= 6 and d.mean() < 0.8
+    # truncated file: error code, no crash
+    raw = open(qp, "rb").read(); open(str(tmp_path / "cut.jpg"), "wb").write(raw[:len(raw) // 3])
+    try: pt.decode_image(str(tmp_path / "cut.jpg"))
+    except pt.B200ptError: pass

@@ -150,14 +150,16 @@ bool write_png_rgba8(const std::string &path, uint32_t W, uint32_t H, const uint
     return ok;
 }
 
-// =================================================================================== baseline JPEG decode
+// =================================================================================== JPEG decode (baseline + progressive, 8-bit Huffman)
 namespace {
 struct Huff { uint8_t size[257]; uint16_t code[256]; uint8_t values[256]; int maxcode[18]; int delta[17]; uint8_t fast[512]; };
-struct Comp { int id, h, v, tq, td, ta, dc_pred; int w2, h2; std::vector<uint8_t> data; };
+struct Comp { int id, h, v, tq, td, ta, dc_pred; int w2, h2; std::vector<uint8_t> data; int x = 0, y = 0, coeff_w = 0; std::vector<short> coeff; };   // x, y: size in samples; coeff: progressive scans
 struct Jpeg {
     const uint8_t *p, *end; uint32_t W = 0, H = 0; Huff dc[4], ac[4]; uint16_t dq[4][64]; Comp c[3]; int ncomp = 0;
     int hmax = 1, vmax = 1, mcux = 0, mcuy = 0, restart = 0;
     uint32_t bits = 0; int nbits = 0; bool marker_hit = false; int todo = 0; std::string err;
+    bool progressive = false; int spec_start = 0, spec_end = 63, succ_high = 0, succ_low = 0, eob_run = 0;   // SOS parameters of a progressive scan
+    int scan_n = 0, order[3] = { 0, 1, 2 };
 };
 const uint8_t kZig[64 + 15] = { 0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50,
                                 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63 };
@@ -228,6 +230,81 @@ bool decode_block(Jpeg &j, short data[64], const Huff &hdc, const Huff &hac, int
     } while (k < 64);
     return true;
 }
+// ---- progressive scans (ITU T.81 annex G): DC first / refinement, AC first / refinement with end-of-band runs
+int get_bits(Jpeg &j, int n) {
+    if (n == 0) return 0;
+    if (j.nbits < n) grow_bits(j);
+    uint32_t k = (j.bits << n) | (j.bits >> (32 - n));
+    j.bits = k & ~((1u << n) - 1u);
+    k &= (1u << n) - 1u;
+    j.nbits -= n;
+    return (int)k;
+}
+inline int get_bit(Jpeg &j) { if (j.nbits < 1) grow_bits(j); const uint32_t k = j.bits; j.bits <<= 1; --j.nbits; return (int)(k >> 31); }
+bool decode_block_prog_dc(Jpeg &j, short data[64], const Huff &hdc, int b) {
+    if (j.spec_end != 0) { j.err = "can't merge dc and ac"; return false; }
+    if (j.nbits < 16) grow_bits(j);
+    if (j.succ_high == 0) {                                                 // first scan of the DC coefficient
+        memset(data, 0, 64 * sizeof(short));
+        const int t = huff_decode(j, hdc);
+        if (t < 0 || t > 15) { j.err = "bad huffman code"; return false; }
+        const int diff = t ? extend_receive(j, t) : 0;
+        const int dc = j.c[b].dc_pred + diff; j.c[b].dc_pred = dc;
+        data[0] = (short)(dc * (1 << j.succ_low));
+    } else if (get_bit(j)) data[0] = (short)(data[0] + (short)(1 << j.succ_low));   // refinement: one more bit
+    return true;
+}
+bool decode_block_prog_ac(Jpeg &j, short data[64], const Huff &hac) {
+    if (j.spec_start == 0) { j.err = "can't merge dc and ac"; return false; }
+    if (j.succ_high == 0) {                                                 // first scan of this band
+        const int shift = j.succ_low;
+        if (j.eob_run) { --j.eob_run; return true; }
+        int k = j.spec_start;
+        do {
+            if (j.nbits < 16) grow_bits(j);
+            const int rs = huff_decode(j, hac);
+            if (rs < 0) { j.err = "bad huffman code"; return false; }
+            const int s = rs & 15; int r = rs >> 4;
+            if (s == 0) {
+                if (r < 15) { j.eob_run = (1 << r); if (r) j.eob_run += get_bits(j, r); --j.eob_run; break; }
+                k += 16;
+            } else {
+                k += r;
+                const int zig = kZig[k++];
+                data[zig] = (short)(extend_receive(j, s) * (1 << shift));
+            }
+        } while (k <= j.spec_end);
+    } else {                                                                // refinement of a band
+        const short bit = (short)(1 << j.succ_low);
+        if (j.eob_run) {
+            --j.eob_run;
+            for (int k = j.spec_start; k <= j.spec_end; ++k) {
+                short *p = &data[kZig[k]];
+                if (*p != 0 && get_bit(j) && (*p & bit) == 0) *p = (short)(*p > 0 ? *p + bit : *p - bit);
+            }
+        } else {
+            int k = j.spec_start;
+            do {
+                if (j.nbits < 16) grow_bits(j);
+                const int rs = huff_decode(j, hac);
+                if (rs < 0) { j.err = "bad huffman code"; return false; }
+                int s = rs & 15, r = rs >> 4;
+                if (s == 0) {
+                    if (r < 15) { j.eob_run = (1 << r) - 1; if (r) j.eob_run += get_bits(j, r); r = 64; }   // end of band: only refinements remain in this block
+                } else {
+                    if (s != 1) { j.err = "bad huffman code"; return false; }
+                    s = get_bit(j) ? bit : -bit;
+                }
+                while (k <= j.spec_end) {
+                    short *p = &data[kZig[k++]];
+                    if (*p != 0) { if (get_bit(j) && (*p & bit) == 0) *p = (short)(*p > 0 ? *p + bit : *p - bit); }
+                    else { if (r == 0) { *p = (short)s; break; } --r; }
+                }
+            } while (k <= j.spec_end);
+        }
+    }
+    return true;
+}
 inline uint8_t clamp8(int x) { if ((unsigned)x > 255) { if (x < 0) return 0; if (x > 255) return 255; } return (uint8_t)x; }
 #define F2F(x) ((int)(((x) * 4096 + 0.5)))
 #define FSH(x) ((x) * 4096)
@@ -293,40 +370,108 @@ bool jpeg_decode(Jpeg &j, std::vector<uint8_t> &rgba) {
         if (de > j.end) { j.err = "truncated JPEG"; return false; }
         if (m == 0xDB) { while (d < de) { int q = *d++; int p16 = q >> 4, t = q & 15; if (t > 3) { j.err = "bad DQT"; return false; } for (int i = 0; i < 64; i++) { j.dq[t][kZig[i]] = (uint16_t)(p16 ? u16(d) : *d); d += p16 ? 2 : 1; } } }
         else if (m == 0xC4) { while (d < de) { int q = *d++; int tc = q >> 4, th = q & 15; if (tc > 1 || th > 3) { j.err = "bad DHT"; return false; } const uint8_t *counts = d; int n = 0; for (int i = 0; i < 16; i++) n += counts[i]; d += 16; Huff &h = tc ? j.ac[th] : j.dc[th]; if (!build_huff(h, counts)) { j.err = "bad huffman table"; return false; } memcpy(h.values, d, (size_t)n); d += n; } }
-        else if (m == 0xC0 || m == 0xC1) {
+        else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
             if (d[0] != 8) { j.err = "only 8-bit JPEG"; return false; }
+            j.progressive = (m == 0xC2);
             j.H = (uint32_t)u16(d + 1); j.W = (uint32_t)u16(d + 3); j.ncomp = d[5];
             if (j.ncomp != 1 && j.ncomp != 3) { j.err = "unsupported JPEG component count"; return false; }
             for (int i = 0; i < j.ncomp; i++) { Comp &c = j.c[i]; c.id = d[6 + i * 3]; c.h = d[7 + i * 3] >> 4; c.v = d[7 + i * 3] & 15; c.tq = d[8 + i * 3]; if (!c.h || !c.v || c.h > 4 || c.v > 4 || c.tq > 3) { j.err = "bad SOF"; return false; } j.hmax = std::max(j.hmax, c.h); j.vmax = std::max(j.vmax, c.v); }
+            if (!j.W || !j.H) { j.err = "JPEG without size"; return false; }
+            const int mcuw = j.hmax * 8, mcuh = j.vmax * 8;
+            j.mcux = ((int)j.W + mcuw - 1) / mcuw; j.mcuy = ((int)j.H + mcuh - 1) / mcuh;
+            for (int i = 0; i < j.ncomp; i++) {
+                Comp &c = j.c[i]; c.w2 = j.mcux * c.h * 8; c.h2 = j.mcuy * c.v * 8; c.data.assign((size_t)c.w2 * c.h2, 0); c.dc_pred = 0;
+                c.x = ((int)j.W * c.h + j.hmax - 1) / j.hmax; c.y = ((int)j.H * c.v + j.vmax - 1) / j.vmax;
+                if (j.progressive) { c.coeff_w = c.w2 / 8; c.coeff.assign((size_t)c.w2 * c.h2, 0); }
+            }
             sof = true;
-        } else if (m == 0xC2) { j.err = "progressive JPEG not supported"; return false; }
+        }
         else if (m == 0xDD) j.restart = u16(d);
         else if (m == 0xDA) {
-            int ns = d[0]; if (!sof || ns != j.ncomp) { j.err = "unsupported SOS"; return false; }
-            for (int i = 0; i < ns; i++) { int id = d[1 + i * 2], q = d[2 + i * 2]; int which = -1; for (int k = 0; k < j.ncomp; k++) if (j.c[k].id == id) which = k; if (which != i) { j.err = "bad SOS order"; return false; } j.c[i].td = q >> 4; j.c[i].ta = q & 15; }
+            const int ns = d[0];
+            if (!sof || ns < 1 || ns > j.ncomp || (!j.progressive && ns != j.ncomp)) { j.err = "unsupported SOS"; return false; }
+            for (int i = 0; i < ns; i++) {
+                const int id = d[1 + i * 2], q = d[2 + i * 2]; int which = -1;
+                for (int k = 0; k < j.ncomp; k++) if (j.c[k].id == id) which = k;
+                if (which < 0 || (!j.progressive && which != i)) { j.err = "bad SOS order"; return false; }
+                j.c[which].td = q >> 4; j.c[which].ta = q & 15; j.order[i] = which;
+                if (j.c[which].td > 3 || j.c[which].ta > 3) { j.err = "bad SOS tables"; return false; }
+            }
+            j.scan_n = ns;
+            j.spec_start = d[1 + ns * 2]; j.spec_end = d[2 + ns * 2]; j.succ_high = d[3 + ns * 2] >> 4; j.succ_low = d[3 + ns * 2] & 15;
+            if (j.progressive) {
+                if (j.spec_start > 63 || j.spec_end > 63 || j.spec_start > j.spec_end || j.succ_high > 13 || j.succ_low > 13) { j.err = "bad SOS"; return false; }
+                // ---- one progressive scan: entropy-coded data starts right after the header
+                j.p = de; j.bits = 0; j.nbits = 0; j.marker_hit = false; j.eob_run = 0;
+                for (int n = 0; n < j.ncomp; n++) j.c[n].dc_pred = 0;
+                j.todo = j.restart ? j.restart : 0x7fffffff;
+                auto restart_check = [&]() {
+                    if (--j.todo <= 0) {
+                        if (j.nbits < 24) grow_bits(j);
+                        if (j.marker_hit && j.p + 1 < j.end && j.p[0] == 0xFF && j.p[1] >= 0xD0 && j.p[1] <= 0xD7) j.p += 2;
+                        j.bits = 0; j.nbits = 0; j.marker_hit = false; j.eob_run = 0; for (int n = 0; n < j.ncomp; n++) j.c[n].dc_pred = 0;
+                        j.todo = j.restart ? j.restart : 0x7fffffff;
+                    }
+                };
+                if (ns == 1) {                                              // non-interleaved: the component's own block grid
+                    const int n = j.order[0]; Comp &c = j.c[n];
+                    const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
+                    for (int by = 0; by < bh; by++) for (int bx = 0; bx < bw; bx++) {
+                        short *data = &c.coeff[64 * ((size_t)bx + (size_t)by * c.coeff_w)];
+                        if (j.spec_start == 0) { if (!decode_block_prog_dc(j, data, j.dc[c.td], n)) return false; }
+                        else if (!decode_block_prog_ac(j, data, j.ac[c.ta])) return false;
+                        restart_check();
+                    }
+                } else {                                                    // interleaved: DC scans only
+                    for (int my = 0; my < j.mcuy; my++) for (int mx = 0; mx < j.mcux; mx++) {
+                        for (int k = 0; k < ns; k++) { const int n = j.order[k]; Comp &c = j.c[n];
+                            for (int y = 0; y < c.v; y++) for (int x = 0; x < c.h; x++) {
+                                short *data = &c.coeff[64 * ((size_t)(mx * c.h + x) + (size_t)(my * c.v + y) * c.coeff_w)];
+                                if (!decode_block_prog_dc(j, data, j.dc[c.td], n)) return false;
+                            } }
+                        restart_check();
+                    }
+                }
+                // move to the next marker (the bit reader stops in front of it; otherwise scan forward for 0xFF xx)
+                if (!j.marker_hit) { while (j.p + 1 < j.end && !(j.p[0] == 0xFF && j.p[1] != 0x00 && !(j.p[1] >= 0xD0 && j.p[1] <= 0xD7))) j.p++; }
+                j.bits = 0; j.nbits = 0; j.marker_hit = false;
+                sos = false;                                                // keep reading markers: more scans / tables follow
+                if (j.p + 1 < j.end && j.p[0] == 0xFF && j.p[1] == 0xD9) break;
+                continue;
+            }
             sos = true;
         }
+        else if (m == 0xD9) break;
         j.p = de;
     }
-    if (!sos || !j.W || !j.H) { j.err = "JPEG without scan"; return false; }
-    const int mcuw = j.hmax * 8, mcuh = j.vmax * 8;
-    j.mcux = ((int)j.W + mcuw - 1) / mcuw; j.mcuy = ((int)j.H + mcuh - 1) / mcuh;
-    for (int i = 0; i < j.ncomp; i++) { Comp &c = j.c[i]; c.w2 = j.mcux * c.h * 8; c.h2 = j.mcuy * c.v * 8; c.data.assign((size_t)c.w2 * c.h2, 0); c.dc_pred = 0; }
-    j.todo = j.restart ? j.restart : 0x7fffffff;
-    short block[64];
-    for (int my = 0; my < j.mcuy; my++) for (int mx = 0; mx < j.mcux; mx++) {
+    if (!sof || !j.W || !j.H) { j.err = "JPEG without frame"; return false; }
+    if (j.progressive) {
+        // finish: dequantise and inverse-transform every block of every component
         for (int n = 0; n < j.ncomp; n++) { Comp &c = j.c[n];
-            for (int y = 0; y < c.v; y++) for (int x = 0; x < c.h; x++) {
-                int x2 = (mx * c.h + x) * 8, y2 = (my * c.v + y) * 8;
-                if (!decode_block(j, block, j.dc[c.td], j.ac[c.ta], n, j.dq[c.tq])) return false;
-                idct_block(&c.data[(size_t)c.w2 * y2 + x2], c.w2, block);
+            const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
+            for (int by = 0; by < bh; by++) for (int bx = 0; bx < bw; bx++) {
+                short *data = &c.coeff[64 * ((size_t)bx + (size_t)by * c.coeff_w)];
+                for (int k = 0; k < 64; k++) data[k] = (short)(data[k] * j.dq[c.tq][k]);
+                idct_block(&c.data[(size_t)c.w2 * by * 8 + (size_t)bx * 8], c.w2, data);
             } }
-        if (--j.todo <= 0) {
-            if (j.nbits < 24) grow_bits(j);
-            // restart marker
-            if (j.marker_hit && j.p + 1 < j.end && j.p[0] == 0xFF && j.p[1] >= 0xD0 && j.p[1] <= 0xD7) j.p += 2;
-            j.bits = 0; j.nbits = 0; j.marker_hit = false; for (int n = 0; n < j.ncomp; n++) j.c[n].dc_pred = 0;
-            j.todo = j.restart ? j.restart : 0x7fffffff;
+    } else {
+        if (!sos) { j.err = "JPEG without scan"; return false; }
+        j.todo = j.restart ? j.restart : 0x7fffffff;
+        short block[64];
+        for (int my = 0; my < j.mcuy; my++) for (int mx = 0; mx < j.mcux; mx++) {
+            for (int n = 0; n < j.ncomp; n++) { Comp &c = j.c[n];
+                for (int y = 0; y < c.v; y++) for (int x = 0; x < c.h; x++) {
+                    int x2 = (mx * c.h + x) * 8, y2 = (my * c.v + y) * 8;
+                    if (!decode_block(j, block, j.dc[c.td], j.ac[c.ta], n, j.dq[c.tq])) return false;
+                    idct_block(&c.data[(size_t)c.w2 * y2 + x2], c.w2, block);
+                } }
+            if (--j.todo <= 0) {
+                if (j.nbits < 24) grow_bits(j);
+                // restart marker
+                if (j.marker_hit && j.p + 1 < j.end && j.p[0] == 0xFF && j.p[1] >= 0xD0 && j.p[1] <= 0xD7) j.p += 2;
+                j.bits = 0; j.nbits = 0; j.marker_hit = false; for (int n = 0; n < j.ncomp; n++) j.c[n].dc_pred = 0;
+                j.todo = j.restart ? j.restart : 0x7fffffff;
+            }
         }
     }
     // resample + colour convert
