@@ -116,18 +116,29 @@ def load_gltf(path, decode_image=_decode_image):
             n = len(pos)
             v = np.zeros(n, dtype=VERTEX_DTYPE)
             v["pos"] = pos
-            if "NORMAL" in at:
-                nr = _accessor(g, buffers, at["NORMAL"]).astype(np.float32)
-                inv = (np.float32(1.0) / np.sqrt((nr[:, 0] * nr[:, 0] + nr[:, 1] * nr[:, 1] + nr[:, 2] * nr[:, 2]).astype(np.float32))).astype(np.float32)
-                v["nrm"] = nr * inv[:, None]                      # glm::normalize (AssetImporterImpl.cpp:165)
-            else:
-                raise NotImplementedError("aiProcess_GenNormals path (primitive without NORMAL) is not restated")
-            if "TEXCOORD_0" in at:
-                v["uv"] = _accessor(g, buffers, at["TEXCOORD_0"]).astype(np.float32)   # importer flip + FlipUVs = identity
             if "indices" in p:
                 idx = _accessor(g, buffers, p["indices"]).astype(np.uint32).reshape(-1)
             else:
                 idx = np.arange(n, dtype=np.uint32)
+            idx = idx[:len(idx) // 3 * 3]
+            if "NORMAL" in at:
+                nr = _accessor(g, buffers, at["NORMAL"]).astype(np.float32)
+            else:
+                # aiProcess_GenNormals = assimp 6.0.2 GenFaceNormalsProcess (upstream knowledge): face normal written to the
+                # face's three vertices in face order -- a shared vertex keeps the LAST face's normal; unreferenced vertices stay 0
+                nr = np.zeros((n, 3), np.float32)
+                for f in range(0, len(idx), 3):
+                    a, b, c = pos[idx[f]], pos[idx[f + 1]], pos[idx[f + 2]]
+                    e1 = (b - a).astype(np.float32); e2 = (c - a).astype(np.float32)
+                    nx = np.float32(e1[1] * e2[2]) - np.float32(e1[2] * e2[1]); ny = np.float32(e1[2] * e2[0]) - np.float32(e1[0] * e2[2]); nz = np.float32(e1[0] * e2[1]) - np.float32(e1[1] * e2[0])
+                    ln = np.sqrt(np.float32(np.float32(nx * nx) + np.float32(ny * ny)) + np.float32(nz * nz), dtype=np.float32)
+                    if ln > 0: nx, ny, nz = np.float32(nx / ln), np.float32(ny / ln), np.float32(nz / ln)
+                    nr[idx[f]] = nr[idx[f + 1]] = nr[idx[f + 2]] = (nx, ny, nz)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inv = (np.float32(1.0) / np.sqrt((nr[:, 0] * nr[:, 0] + nr[:, 1] * nr[:, 1] + nr[:, 2] * nr[:, 2]).astype(np.float32))).astype(np.float32)
+                v["nrm"] = nr * inv[:, None]                      # glm::normalize (AssetImporterImpl.cpp:165)
+            if "TEXCOORD_0" in at:
+                v["uv"] = _accessor(g, buffers, at["TEXCOORD_0"]).astype(np.float32)   # importer flip + FlipUVs = identity
             if p.get("mode", 4) != 4:
                 raise NotImplementedError("only TRIANGLES primitives")
             ids.append(len(meshes))

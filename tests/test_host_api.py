@@ -150,7 +150,7 @@ def _compare_loader(path):
     for (va, ia), (vb, ib) in zip(a["meshes"], b["meshes"]):
         assert np.array_equal(ia, ib)
         assert np.array_equal(va["pos"], vb["pos"]) and np.array_equal(va["uv"], vb["uv"])
-        assert np.allclose(va["nrm"], vb["nrm"], rtol=0, atol=1.2e-7)
+        assert np.allclose(va["nrm"], vb["nrm"], rtol=0, atol=1.2e-7, equal_nan=True)
     assert np.array_equal(np.frombuffer(a["materials"].tobytes(), np.uint8), b["materials_bytes"])
     for ta, tb in zip(a["textures"], b["textures"]):
         assert ta.shape == tb.shape
@@ -393,3 +393,24 @@ def test_progressive_jpeg_decodes_like_the_baseline_file(tmp_path):
     raw = open(qp, "rb").read(); open(str(tmp_path / "cut.jpg"), "wb").write(raw[:len(raw) // 3])
     try: pt.decode_image(str(tmp_path / "cut.jpg"))
     except pt.B200ptError: pass
+
+
+def test_gltf_without_normals_gets_assimp_style_face_normals(tmp_path):
+    """aiProcess_GenNormals (AssetImporterImpl.cpp:82-97): a primitive without NORMAL gets flat face normals the way assimp 6.0.2 writes them
+    (a shared vertex keeps the normal of the last face that uses it).  C++ loader == oracle-side loader, and the values are the expected ones."""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [5, 5, 5]], np.float32)        # vertex 4 is referenced by no face
+    idx = np.array([0, 1, 2, 0, 3, 1], np.uint16)                                                # faces normal to +z then +y... (0,3,1): (3-0)x(1-0) = z x x = +y
+    blob = pos.tobytes() + idx.tobytes()
+    (tmp_path / "n.bin").write_bytes(blob)
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+         "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+         "accessors": [{"bufferView": 0, "componentType": 5126, "count": 5, "type": "VEC3"}, {"bufferView": 1, "componentType": 5123, "count": 6, "type": "SCALAR"}],
+         "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 60}, {"buffer": 0, "byteOffset": 60, "byteLength": 12}],
+         "buffers": [{"uri": "n.bin", "byteLength": len(blob)}]}
+    p = str(tmp_path / "n.gltf"); open(p, "w").write(json.dumps(g))
+    _compare_loader(p)
+    v, i = pt.load_gltf(p)["meshes"][0]
+    nrm = np.asarray(v["nrm"], np.float32)
+    assert np.allclose(nrm[2], [0, 0, 1]) and np.allclose(nrm[3], [0, 1, 0])                 # only in one face each
+    assert np.allclose(nrm[0], [0, 1, 0]) and np.allclose(nrm[1], [0, 1, 0])                 # shared: the LAST face (0,3,1) wins
+    assert np.isnan(nrm[4]).all()                                                            # glm::normalize of the zero vector, like the reference

@@ -238,12 +238,30 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
             const JVal *at = p.get("attributes"); if (!at || !at->has("POSITION")) { err = "primitive without POSITION"; return false; }
             std::vector<float> pos, nrm, uv; size_t n = 0, nn = 0, nu = 0;
             if (!accessor((int)at->num("POSITION", -1), 3, &pos, nullptr, n)) return false;
-            if (!at->has("NORMAL")) { err = "primitive without NORMAL (aiProcess_GenNormals path not restated)"; return false; }
-            if (!accessor((int)at->num("NORMAL", -1), 3, &nrm, nullptr, nn) || nn != n) { if (err.empty()) err = "NORMAL count mismatch"; return false; }
+            const bool has_nrm = at->has("NORMAL");
+            if (has_nrm && (!accessor((int)at->num("NORMAL", -1), 3, &nrm, nullptr, nn) || nn != n)) { if (err.empty()) err = "NORMAL count mismatch"; return false; }
             const bool has_uv = at->has("TEXCOORD_0");
             if (has_uv && (!accessor((int)at->num("TEXCOORD_0", -1), 2, &uv, nullptr, nu) || nu != n)) { if (err.empty()) err = "TEXCOORD_0 count mismatch"; return false; }
             HostMesh hm; hm.vertices.resize(n);
             if (const JVal *nm = (*ms)[mi].get("name")) hm.name = nm->s;
+            if (p.has("indices")) { size_t ni = 0; if (!accessor((int)p.num("indices", -1), 1, nullptr, &hm.indices, ni)) return false; }
+            else { hm.indices.resize(n); for (size_t i = 0; i < n; i++) hm.indices[i] = (uint32_t)i; }
+            hm.indices.resize(hm.indices.size() / 3 * 3);
+            for (uint32_t ix : hm.indices) if (ix >= n) { err = "index out of range"; return false; }
+            if (!has_nrm) {
+                // aiProcess_GenNormals (AssetImporterImpl.cpp:82-97) = assimp 6.0.2 GenFaceNormalsProcess (from upstream knowledge):
+                // every face writes NormalizeSafe(cross(v1 - v0, v2 - v0)) to its three vertices, so a shared vertex keeps the normal of the
+                // LAST face that uses it (assimp does not split vertices here); a vertex no face references stays (0, 0, 0).
+                nrm.assign(n * 3, 0.0f);
+                for (size_t f = 0; f + 2 < hm.indices.size(); f += 3) {
+                    const float *a = &pos[hm.indices[f] * 3], *b = &pos[hm.indices[f + 1] * 3], *c = &pos[hm.indices[f + 2] * 3];
+                    const float e1[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] }, e2[3] = { c[0] - a[0], c[1] - a[1], c[2] - a[2] };
+                    float nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+                    const float len = sqrtf(nx * nx + ny * ny + nz * nz);
+                    if (len > 0.0f) { nx /= len; ny /= len; nz /= len; }
+                    for (int k = 0; k < 3; k++) { float *o = &nrm[hm.indices[f + k] * 3]; o[0] = nx; o[1] = ny; o[2] = nz; }
+                }
+            }
             for (size_t i = 0; i < n; i++) {
                 b200pt_vertex &v = hm.vertices[i];
                 v.Position[0] = pos[i * 3]; v.Position[1] = pos[i * 3 + 1]; v.Position[2] = pos[i * 3 + 2];
@@ -252,10 +270,6 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
                 v.Normal[0] = nx * inv; v.Normal[1] = ny * inv; v.Normal[2] = nz * inv;
                 v.TexCoord[0] = has_uv ? uv[i * 2] : 0.0f; v.TexCoord[1] = has_uv ? uv[i * 2 + 1] : 0.0f;   // importer flip + FlipUVs = identity
             }
-            if (p.has("indices")) { size_t ni = 0; if (!accessor((int)p.num("indices", -1), 1, nullptr, &hm.indices, ni)) return false; }
-            else { hm.indices.resize(n); for (size_t i = 0; i < n; i++) hm.indices[i] = (uint32_t)i; }
-            hm.indices.resize(hm.indices.size() / 3 * 3);
-            for (uint32_t ix : hm.indices) if (ix >= n) { err = "index out of range"; return false; }
             prims_of_mesh.back().push_back((uint32_t)sc.meshes.size());
             mesh_material.push_back(p.has("material") ? (int)p.num("material", 0) : -1);
             sc.meshes.push_back(std::move(hm));
