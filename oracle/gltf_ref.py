@@ -120,6 +120,11 @@ def load_gltf(path, decode_image=_decode_image):
                 idx = _accessor(g, buffers, p["indices"]).astype(np.uint32).reshape(-1)
             else:
                 idx = np.arange(n, dtype=np.uint32)
+            mode = p.get("mode", 4)
+            if mode == 5:                                    # TRIANGLE_STRIP -> faces, odd faces swapped to keep the orientation (assimp glTF2 importer)
+                idx = np.array([(idx[f + 1], idx[f], idx[f + 2]) if (f + 1) % 2 == 0 else (idx[f], idx[f + 1], idx[f + 2]) for f in range(max(len(idx) - 2, 0))], np.uint32).reshape(-1)
+            elif mode == 6:                                  # TRIANGLE_FAN
+                idx = np.array([(idx[0], idx[f + 1], idx[f + 2]) for f in range(max(len(idx) - 2, 0))], np.uint32).reshape(-1)
             idx = idx[:len(idx) // 3 * 3]
             if "NORMAL" in at:
                 nr = _accessor(g, buffers, at["NORMAL"]).astype(np.float32)
@@ -139,8 +144,8 @@ def load_gltf(path, decode_image=_decode_image):
                 v["nrm"] = nr * inv[:, None]                      # glm::normalize (AssetImporterImpl.cpp:165)
             if "TEXCOORD_0" in at:
                 v["uv"] = _accessor(g, buffers, at["TEXCOORD_0"]).astype(np.float32)   # importer flip + FlipUVs = identity
-            if p.get("mode", 4) != 4:
-                raise NotImplementedError("only TRIANGLES primitives")
+            if p.get("mode", 4) not in (4, 5, 6):
+                raise NotImplementedError("only TRIANGLES / TRIANGLE_STRIP / TRIANGLE_FAN primitives")
             ids.append(len(meshes))
             meshes.append((v, idx))
             mesh_material.append(p.get("material", None))

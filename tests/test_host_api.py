@@ -414,3 +414,23 @@ def test_gltf_without_normals_gets_assimp_style_face_normals(tmp_path):
     assert np.allclose(nrm[2], [0, 0, 1]) and np.allclose(nrm[3], [0, 1, 0])                 # only in one face each
     assert np.allclose(nrm[0], [0, 1, 0]) and np.allclose(nrm[1], [0, 1, 0])                 # shared: the LAST face (0,3,1) wins
     assert np.isnan(nrm[4]).all()                                                            # glm::normalize of the zero vector, like the reference
+
+
+def test_gltf_strips_and_fans_become_triangles(tmp_path):
+    """glTF primitive modes 5 / 6: the reference's importer (assimp glTF2) expands strips and fans into faces; same face list in both loaders."""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [2, 1, 0]], np.float32)
+    idx = np.array([0, 1, 2, 3, 4], np.uint16)
+    blob = pos.tobytes() + idx.tobytes() + b"\0\0"
+    (tmp_path / "s.bin").write_bytes(blob)
+    for mode, want in ((5, [0, 1, 2, 2, 1, 3, 2, 3, 4]), (6, [0, 1, 2, 0, 2, 3, 0, 3, 4])):
+        g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+             "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1, "mode": mode}]}],
+             "accessors": [{"bufferView": 0, "componentType": 5126, "count": 5, "type": "VEC3"}, {"bufferView": 1, "componentType": 5123, "count": 5, "type": "SCALAR"}],
+             "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 60}, {"buffer": 0, "byteOffset": 60, "byteLength": 10}],
+             "buffers": [{"uri": "s.bin", "byteLength": len(blob)}]}
+        p = str(tmp_path / f"m{mode}.gltf"); open(p, "w").write(json.dumps(g))
+        _compare_loader(p)
+        assert list(pt.load_gltf(p)["meshes"][0][1]) == want
+    g["meshes"][0]["primitives"][0]["mode"] = 1
+    p = str(tmp_path / "lines.gltf"); open(p, "w").write(json.dumps(g))
+    with pytest.raises(pt.B200ptError): pt.load_gltf(p)

@@ -234,7 +234,8 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
         const JVal *prs = (*ms)[mi].get("primitives"); if (!prs) continue;
         for (size_t pi = 0; pi < prs->size(); pi++) {
             const JVal &p = (*prs)[pi];
-            if ((int)p.num("mode", 4) != 4) { err = "only TRIANGLES primitives are supported"; return false; }
+            const int mode = (int)p.num("mode", 4);
+            if (mode < 4 || mode > 6) { err = "only TRIANGLES / TRIANGLE_STRIP / TRIANGLE_FAN primitives are supported"; return false; }
             const JVal *at = p.get("attributes"); if (!at || !at->has("POSITION")) { err = "primitive without POSITION"; return false; }
             std::vector<float> pos, nrm, uv; size_t n = 0, nn = 0, nu = 0;
             if (!accessor((int)at->num("POSITION", -1), 3, &pos, nullptr, n)) return false;
@@ -246,6 +247,14 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
             if (const JVal *nm = (*ms)[mi].get("name")) hm.name = nm->s;
             if (p.has("indices")) { size_t ni = 0; if (!accessor((int)p.num("indices", -1), 1, nullptr, &hm.indices, ni)) return false; }
             else { hm.indices.resize(n); for (size_t i = 0; i < n; i++) hm.indices[i] = (uint32_t)i; }
+            if (mode != 4) {                                              // assimp's glTF2 importer expands strips and fans into triangle faces
+                std::vector<uint32_t> src; src.swap(hm.indices);
+                const size_t nf = src.size() >= 3 ? src.size() - 2 : 0;
+                for (size_t f = 0; f < nf; f++) {
+                    if (mode == 5) { if ((f + 1) % 2 == 0) { hm.indices.push_back(src[f + 1]); hm.indices.push_back(src[f]); } else { hm.indices.push_back(src[f]); hm.indices.push_back(src[f + 1]); } hm.indices.push_back(src[f + 2]); }   // same orientation for every triangle
+                    else { hm.indices.push_back(src[0]); hm.indices.push_back(src[f + 1]); hm.indices.push_back(src[f + 2]); }
+                }
+            }
             hm.indices.resize(hm.indices.size() / 3 * 3);
             for (uint32_t ix : hm.indices) if (ix >= n) { err = "index out of range"; return false; }
             if (!has_nrm) {
