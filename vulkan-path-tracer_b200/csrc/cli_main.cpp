@@ -33,13 +33,14 @@ static void usage() {
         "  --volume x0 y0 z0 x1 y1 z1 density r g b   add a homogeneous AABB volume (repeatable); --volume-g G sets the anisotropy of the last one\n"
         "  --phase 0|1|2     phase function: Henyey-Greenstein, Draine, HG + Draine\n"
         "  --checkpoint FILE save the accumulation when done         --resume FILE  continue from a checkpoint\n"
+        "  --preview-every K rewrite the output PNG after every K PathTrace calls (the editor's progressive view, Editor.cpp:83-121)\n"
         "  --bake-luts N     bake missing lookup tables into DIR with N samples per texel first (Application.cpp:35-72)\n"
         "  --device K        CUDA device ordinal (default 0)         --quiet\n");
 }
 
 int main(int argc, char **argv) {
     std::string scene, env, luts, out, ckpt_out, ckpt_in;
-    uint32_t W = 0, H = 0, spp = 64, depth = 200, seed = 0x1234ABCDu, chunks = 1, batch = 8, bake = 0, phase = 0;
+    uint32_t W = 0, H = 0, spp = 64, depth = 200, seed = 0x1234ABCDu, chunks = 1, batch = 8, bake = 0, phase = 0, preview = 0;
     int device = 0; bool quiet = false;
     b200pt_tonemap tm{ 1.0f, 2.2f }; b200pt_bloom bl{ 2.0f, 1.0f, 10, 5.0f };
     std::vector<b200pt_volume> vols;
@@ -64,6 +65,7 @@ int main(int argc, char **argv) {
         }
         else if (a == "--volume-g") { need(1); if (vols.empty()) { usage(); return 2; } vols.back().Anisotropy = (float)atof(argv[++i]); }
         else if (a == "--phase") { need(1); phase = (uint32_t)atoi(argv[++i]); }
+        else if (a == "--preview-every") { need(1); preview = (uint32_t)atoi(argv[++i]); }
         else if (a == "--checkpoint") { need(1); ckpt_out = argv[++i]; } else if (a == "--resume") { need(1); ckpt_in = argv[++i]; }
         else if (a == "--bake-luts") { need(1); bake = (uint32_t)atoi(argv[++i]); } else if (a == "--device") { need(1); device = atoi(argv[++i]); }
         else if (a == "--quiet") quiet = true;
@@ -90,6 +92,7 @@ int main(int argc, char **argv) {
     uint32_t acc = 0; CALL(b200pt_samples_accumulated(h, &acc));
     const uint32_t start_acc = acc;
     const auto t0 = std::chrono::steady_clock::now();
+    uint32_t calls = 0;
     while (acc < spp) {                                                     // Editor::Draw: PathTrace() until all samples are accumulated (Editor.cpp:116-121)
         int32_t done = 0;
         CALL(b200pt_path_trace(h, batch, seed, &done));
@@ -99,6 +102,9 @@ int main(int argc, char **argv) {
             const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             const double rate = (double)(acc - start_acc) * W * H / (s > 0 ? s : 1e-9) / 1e6;
             fprintf(stderr, "\rsamples %u / %u   %.2f s   %.1f Mpaths/s   ETA %.1f s   ", acc, spp, s, rate, acc > start_acc ? s * (spp - acc) / (acc - start_acc) : 0.0);
+        }
+        if (preview && (++calls % preview) == 0 && acc < spp) {             // what the viewport would show right now: post chain on the running mean
+            CALL(b200pt_post_process(h)); CALL(b200pt_save_png(h, out.c_str()));
         }
         if (done) break;
     }
