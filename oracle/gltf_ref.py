@@ -252,6 +252,167 @@ def load_gltf(path, decode_image=_decode_image):
 
 
 # ------------------------------------------------------------------------------------------------
+# Wavefront OBJ / MTL: oracle-side mirror of csrc/scene_loader.cpp:load_obj_scene (assimp ObjFileParser / ObjFileMtlImporter semantics from
+# upstream knowledge -- PARITY UNPINNED, see the C++ header comment for the mapping)
+# ------------------------------------------------------------------------------------------------
+def _obj_lines(path):
+    raw = open(path, "rb").read().decode("latin-1")
+    out, cur = [], ""
+    for ln in raw.split("\n"):
+        if ln.endswith("\r"): ln = ln[:-1]
+        if ln.endswith("\\"): cur += ln[:-1] + " "; continue
+        cur += ln
+        h = cur.find("#")
+        if h >= 0: cur = cur[:h]
+        out.append(cur); cur = ""
+    if cur: out.append(cur)
+    return out
+
+
+def _obj_default_material():
+    m = np.zeros(1, dtype=MATERIAL_DTYPE)[0]
+    m["BaseColor"] = 0.6; m["SpecularColor"] = 0.0; m["MediumColor"] = 1.0; m["Roughness"] = 1.0; m["IOR"] = 1.0
+    return m
+
+
+def load_obj(path, decode_image=_decode_image):
+    base = os.path.dirname(os.path.abspath(path))
+    atof = lambda t: np.float32(_c_atof(t))
+    P, N, T = [], [], []
+    mats = [dict(name="DefaultMaterial", m=_obj_default_material(), tp=dict(base="", normal="", rough="", metal="", emissive=""))]
+
+    def load_mtl(fp):
+        cur = None
+        for ln in _obj_lines(fp):
+            t = ln.split()
+            if not t: continue
+            if t[0] == "newmtl":
+                cur = dict(name=t[1] if len(t) > 1 else "", m=_obj_default_material(), tp=dict(base="", normal="", rough="", metal="", emissive="")); mats.append(cur); continue
+            if cur is None or len(t) < 2: continue
+            k = t[0]; f3 = lambda: np.array([atof(t[min(1 + c, len(t) - 1)]) for c in range(3)], np.float32); fp2 = base + "/" + t[-1]
+            if k == "Kd": cur["m"]["BaseColor"] = f3()
+            elif k == "Ke": cur["m"]["EmissiveColor"] = f3()
+            elif k == "Ks": cur["m"]["SpecularColor"] = f3()
+            elif k == "Ni": cur["m"]["IOR"] = atof(t[1])
+            elif k == "Pr": cur["m"]["Roughness"] = atof(t[1])
+            elif k == "Pm": cur["m"]["Metallic"] = atof(t[1])
+            elif k == "aniso": cur["m"]["Anisotropy"] = atof(t[1])
+            elif k == "anisor": cur["m"]["AnisotropyRotation"] = atof(t[1]) * (np.float32(180.0) / np.float32(3.14159265358979323846))
+            elif k == "map_Kd": cur["tp"]["base"] = fp2
+            elif k in ("norm", "map_Kn"): cur["tp"]["normal"] = fp2
+            elif k == "map_Pr": cur["tp"]["rough"] = fp2
+            elif k == "map_Pm": cur["tp"]["metal"] = fp2
+            elif k == "map_Ke": cur["tp"]["emissive"] = fp2
+
+    builds = []; group = ""; material = 0; need_new = True
+    for ln in _obj_lines(path):
+        t = ln.split()
+        if not t: continue
+        k = t[0]
+        if k == "v" and len(t) >= 4: P.append([atof(x) for x in t[1:4]])
+        elif k == "vn" and len(t) >= 4: N.append([atof(x) for x in t[1:4]])
+        elif k == "vt" and len(t) >= 2: T.append([atof(t[1]), atof(t[2]) if len(t) >= 3 else np.float32(0)])
+        elif k in ("o", "g"):
+            group = t[1] if len(t) > 1 else ""
+            if builds and len(builds[-1]["idx"]): need_new = True
+            elif builds: builds[-1]["name"] = group
+        elif k == "mtllib":
+            for f in t[1:]: load_mtl(base + "/" + f)
+        elif k == "usemtl":
+            found = 0
+            for i in range(1, len(mats)):
+                if len(t) > 1 and mats[i]["name"] == t[1]: found = i
+            if found != material:
+                material = found
+                if builds and len(builds[-1]["idx"]): need_new = True
+                elif builds: builds[-1]["material"] = material
+        elif k == "f" and len(t) >= 4:
+            if need_new or not builds:
+                builds.append(dict(name=group, material=material, index={}, verts=[], idx=[])); need_new = False
+            b = builds[-1]
+            fv = []
+            for tok in t[1:]:
+                parts = (tok.split("/") + ["", ""])[:3]
+                v, vt, vn = [int(x) if x not in ("",) and _is_int(x) else 0 for x in parts]
+                if v < 0: v = len(P) + v + 1
+                if vt < 0: vt = len(T) + vt + 1
+                if vn < 0: vn = len(N) + vn + 1
+                if v < 1 or v > len(P) or vt > len(T) or vn > len(N): raise ValueError("OBJ face index out of range")
+                fv.append((v, vt, vn))
+            for i in range(1, len(fv) - 1):
+                tri = [fv[0], fv[i], fv[i + 1]]
+                gn = (np.float32(0), np.float32(0), np.float32(0))
+                if any(q[2] == 0 for q in tri):
+                    a, bb, c = (np.array(P[q[0] - 1], np.float32) for q in tri)
+                    e1 = (bb - a).astype(np.float32); e2 = (c - a).astype(np.float32)
+                    g = np.array([np.float32(e1[1] * e2[2]) - np.float32(e1[2] * e2[1]), np.float32(e1[2] * e2[0]) - np.float32(e1[0] * e2[2]), np.float32(e1[0] * e2[1]) - np.float32(e1[1] * e2[0])], np.float32)
+                    ln2 = np.sqrt(np.float32(np.float32(g[0] * g[0]) + np.float32(g[1] * g[1])) + np.float32(g[2] * g[2]), dtype=np.float32)
+                    if ln2 > 0: g = (g / ln2).astype(np.float32)
+                    gn = tuple(g)
+                for q in tri:
+                    key = (q[0], q[1], q[2]) + (tuple(float(x) for x in gn) if q[2] == 0 else (0.0, 0.0, 0.0))
+                    if key not in b["index"]:
+                        b["index"][key] = len(b["verts"])
+                        nrm = np.array(N[q[2] - 1], np.float32) if q[2] else np.array(gn, np.float32)
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            inv = np.float32(1.0) / np.sqrt(np.float32(np.float32(nrm[0] * nrm[0]) + np.float32(nrm[1] * nrm[1])) + np.float32(nrm[2] * nrm[2]), dtype=np.float32)
+                            nrm = (nrm * inv).astype(np.float32)
+                        uv = (T[q[1] - 1][0], np.float32(1.0) - T[q[1] - 1][1]) if q[1] else (np.float32(0), np.float32(0))
+                        b["verts"].append((tuple(P[q[0] - 1]), tuple(nrm), uv))
+                    b["idx"].append(b["index"][key])
+    meshes, instances = [], []
+    for b in builds:
+        if not b["idx"]: continue
+        v = np.zeros(len(b["verts"]), dtype=VERTEX_DTYPE)
+        for i, (p_, n_, uv_) in enumerate(b["verts"]): v[i]["pos"] = p_; v[i]["nrm"] = n_; v[i]["uv"] = uv_
+        instances.append((FLIP_Y.astype(np.float32).T.reshape(-1).copy(), len(meshes), b["material"]))
+        meshes.append((v, np.array(b["idx"], np.uint32)))
+    if not meshes: raise ValueError("No meshes found in scene")
+    marr = np.zeros(len(mats), dtype=MATERIAL_DTYPE)
+    for i, m in enumerate(mats): marr[i] = m["m"]
+    textures, index_of = [], {}
+
+    def get_tex(path_, key_default, default_px, single):
+        key = path_ if path_ else key_default
+        if key not in index_of:
+            index_of[key] = len(textures)
+            if path_:
+                img = decode_image(path_)
+                if single: img = img[:, :, :1].copy()
+            else:
+                img = np.array(default_px, dtype=np.uint8).reshape(1, 1, -1)
+            textures.append(np.ascontiguousarray(img))
+        return index_of[key]
+    for i, m in enumerate(mats):
+        tp = m["tp"]
+        marr[i]["BaseColorTextureIndex"] = get_tex(tp["base"], "EMPTY_BASECOLOR_TEXTURE", [255, 255, 255, 255], False)
+        marr[i]["NormalTextureIndex"] = get_tex(tp["normal"], "EMPTY_NORMAL_TEXTURE", [128, 128, 255, 255], False)
+        marr[i]["RoughnessTextureIndex"] = get_tex(tp["rough"], "EMPTY_ROUGHNESS_TEXTURE", [255], True)
+        marr[i]["MetallicTextureIndex"] = get_tex(tp["metal"], "EMPTY_METALLIC_TEXTURE", [255], True)
+        marr[i]["EmissiveTextureIndex"] = get_tex(tp["emissive"], "EMPTY_EMISSIVE_TEXTURE", [255, 255, 255, 255], False)
+    view = np.eye(4); view[2, 3] = -5.0
+    return dict(meshes=meshes, materials=marr, material_names=[m["name"] for m in mats], textures=textures, instances=instances,
+                camera_view=view.astype(np.float32).T.reshape(-1).copy(), aspect=np.float32(16.0 / 9.0))
+
+
+def _is_int(x):
+    try: int(x); return True
+    except ValueError: return False
+
+
+def _c_atof(t):
+    """C atof(): longest valid numeric prefix, 0.0 if none."""
+    import re
+    m = re.match(r"\s*[+-]?(\d+\.?\d*([eE][+-]?\d+)?|\.\d+([eE][+-]?\d+)?)", t)
+    return float(m.group(0)) if m else 0.0
+
+
+def load_scene(path, decode_image=_decode_image):
+    """By extension, like AssetImporter::ImportScene."""
+    return load_obj(path, decode_image) if path.lower().endswith(".obj") else load_gltf(path, decode_image)
+
+
+# ------------------------------------------------------------------------------------------------
 # golden-fixture (de)serialisation: flat npz so GPU-box tests need neither /root/reference nor PIL
 # ------------------------------------------------------------------------------------------------
 def save_scene_npz(path, sc):

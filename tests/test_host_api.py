@@ -145,7 +145,7 @@ def test_bloom_mips_and_partition_helpers():
 
 
 def _compare_loader(path):
-    a = gltf_ref.load_gltf(path); b = pt.load_gltf(path)
+    a = gltf_ref.load_scene(path); b = pt.load_gltf(path)
     assert len(a["meshes"]) == len(b["meshes"]) and len(a["instances"]) == len(b["instances"]) and len(a["textures"]) == len(b["textures"])
     for (va, ia), (vb, ib) in zip(a["meshes"], b["meshes"]):
         assert np.array_equal(ia, ib)
@@ -434,3 +434,44 @@ def test_gltf_strips_and_fans_become_triangles(tmp_path):
     g["meshes"][0]["primitives"][0]["mode"] = 1
     p = str(tmp_path / "lines.gltf"); open(p, "w").write(json.dumps(g))
     with pytest.raises(pt.B200ptError): pt.load_gltf(p)
+
+
+def test_obj_mtl_import(tmp_path):
+    """Wavefront OBJ + MTL through the same entry point as glTF (AssetImporter::ImportScene picks the importer by extension): quads and n-gons
+    become fans, (v, vt, vn) triples are joined, missing normals are generated per face, uv is flipped, materials follow the keys the reference
+    reads (AssetImporterImpl.cpp:353-455) with assimp's OBJ defaults.  C++ loader == oracle-side loader, plus the expected values."""
+    from PIL import Image
+    rng = np.random.default_rng(8)
+    Image.fromarray(rng.integers(0, 256, (4, 6, 3), dtype=np.uint8), "RGB").save(tmp_path / "kd.png")
+    Image.fromarray(rng.integers(0, 256, (3, 3, 3), dtype=np.uint8), "RGB").save(tmp_path / "ke.png")
+    (tmp_path / "m.mtl").write_text(
+        "# materials\nnewmtl red\nKd 0.8 0.1 0.1\nKs 0.5 0.5 0.5\nNi 1.45\nPr 0.3\nPm 0.2\naniso 0.4\nanisor 0.5\nmap_Kd -bm 1.0 kd.png\n"
+        "newmtl lamp\nKd 1 1 1\nKe 5 4 3\nmap_Ke ke.png\nmap_bump ignored.png\n\nnewmtl unused\nKd 0 1 0\n")
+    (tmp_path / "s.obj").write_text(
+        "mtllib m.mtl\no floor\nv 0 0 0\nv 2 0 0\nv 2 0 2\nv 0 0 2\nv 1 1 1\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 1 0\n"
+        "f 1/1/1 2/2/1 3/3/1 4/4/1\n"                       # quad with uv + normals, default material
+        "usemtl red\nf 1 2 5\nf -4//1 -3//1 -1//1 \\\n  -5//1\n"   # no normals at all -> generated; negative indices + line continuation
+        "g lampgroup\nusemtl lamp\nf 3/3 4/4 5/1\n")
+    p = str(tmp_path / "s.obj")
+    _compare_loader(p)
+    b = pt.load_gltf(p)
+    m = np.frombuffer(b["materials_bytes"].tobytes(), gltf_ref.MATERIAL_DTYPE)
+    assert len(m) == 4                                           # DefaultMaterial + 3 newmtl
+    assert np.allclose(m["BaseColor"][0], 0.6) and m["IOR"][0] == 1.0 and m["Metallic"][0] == 0.0 and m["Roughness"][0] == 1.0 and np.all(m["SpecularColor"][0] == 0)
+    assert np.allclose(m["BaseColor"][1], [0.8, 0.1, 0.1]) and abs(m["IOR"][1] - 1.45) < 1e-6 and abs(m["Roughness"][1] - 0.3) < 1e-6 and abs(m["Metallic"][1] - 0.2) < 1e-6
+    assert abs(m["AnisotropyRotation"][1] - np.degrees(0.5)) < 1e-4 and np.allclose(m["EmissiveColor"][2], [5, 4, 3])
+    assert b["textures"][m["BaseColorTextureIndex"][1]].shape == (4, 6, 4) and b["textures"][m["EmissiveTextureIndex"][2]].shape == (3, 3, 4)
+    assert b["textures"][m["NormalTextureIndex"][2]].shape == (1, 1, 4)          # map_bump is a height map: ignored
+    assert len(b["meshes"]) == 3 and [int(i[2]) for i in b["instances"]] == [0, 1, 2]
+    v0, i0 = b["meshes"][0]
+    assert len(v0) == 4 and list(i0) == [0, 1, 2, 0, 2, 3]                       # fan of the quad, vertices joined
+    assert np.allclose(v0["uv"][2], [1, 0]) and np.allclose(v0["nrm"], [[0, 1, 0]] * 4)   # v flipped
+    v1, i1 = b["meshes"][1]
+    assert len(i1) == 3 + 6                                                       # a triangle + a fanned quad
+    assert np.allclose(np.linalg.norm(v1["nrm"], axis=1), 1.0, atol=1e-6)
+    assert np.linalg.det(b["instances"][0][0].reshape(4, 4).T[:3, :3]) < 0        # Y flip
+    # unsupported extension / broken face index -> error codes
+    (tmp_path / "bad.obj").write_text("v 0 0 0\nf 1 2 3\n")
+    with pytest.raises(pt.B200ptError): pt.load_gltf(str(tmp_path / "bad.obj"))
+    (tmp_path / "x.fbx").write_text("nope")
+    with pytest.raises(pt.B200ptError): pt.load_gltf(str(tmp_path / "x.fbx"))

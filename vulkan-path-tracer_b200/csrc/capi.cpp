@@ -44,7 +44,7 @@ int32_t b200pt_set_scene_file(b200pt_handle h, const char *path) {
     if (!path) return B200PT_ERR_WRONG_ARGUMENTS;
     return guard(h, [&](Engine &e) {
         HostScene sc; std::string err;
-        if (!load_gltf_scene(path, sc, err)) throw CudaError{ B200PT_ERR_INIT_FAILED, "Failed to import scene: " + err };
+        if (!load_scene_file(path, sc, err)) throw CudaError{ B200PT_ERR_INIT_FAILED, "Failed to import scene: " + err };
         e.set_scene(std::move(sc));
     });
 }
@@ -238,7 +238,7 @@ int32_t b200pt_load_gltf(const char *path, b200pt_scene_desc **out) {
     OwnedScene *o = new (std::nothrow) OwnedScene(); if (!o) return B200PT_ERR_OUT_OF_MEMORY;
     std::string err;
     try {
-        if (!load_gltf_scene(path, o->host, err)) { g_err = err; delete o; return B200PT_ERR_INIT_FAILED; }
+        if (!load_scene_file(path, o->host, err)) { g_err = err; delete o; return B200PT_ERR_INIT_FAILED; }
         for (auto &m : o->host.meshes) o->meshes.push_back({ m.vertices.data(), m.indices.data(), (uint32_t)m.vertices.size(), (uint32_t)m.indices.size() });
         for (auto &t : o->host.textures) o->textures.push_back({ t.width, t.height, t.channels, 0, t.data.data() });
     } catch (...) { delete o; return B200PT_ERR_UNKNOWN; }

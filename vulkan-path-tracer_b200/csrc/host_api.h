@@ -25,7 +25,9 @@ struct HostScene {
     float camera_view[16];
     float camera_aspect = 1.0f;
 };
-bool load_gltf_scene(const std::string &path, HostScene &out, std::string &err);
+bool load_gltf_scene(const std::string &path, HostScene &out, std::string &err);   // .gltf / .glb
+bool load_obj_scene(const std::string &path, HostScene &out, std::string &err);    // .obj + .mtl (assimp semantics from upstream knowledge)
+bool load_scene_file(const std::string &path, HostScene &out, std::string &err);   // by extension, like AssetImporter::ImportScene
 bool scene_from_desc(const b200pt_scene_desc *d, HostScene &out, std::string &err);
 
 // ---- env_camera.cpp ----

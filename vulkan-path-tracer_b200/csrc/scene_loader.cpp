@@ -137,6 +137,37 @@ static bool read_all(const std::string &path, std::vector<uint8_t> &out) {
     return got == out.size();
 }
 
+// ---- texture table in PathTracer::SetScene order (PathTracer.cpp:228-408): per material base, normal, roughness, metallic, emissive; a path is
+// loaded once, missing slots share the 1x1 defaults white / (128,128,255) (PathTracer.cpp:1557-1621); roughness / metallic keep the R channel (Q8)
+struct TexPaths { std::string base, normal, rough, metal, emissive; };
+static bool build_texture_table(HostScene &sc, const std::vector<TexPaths> &tps, std::string &err) {
+    std::map<std::string, uint32_t> index_of;
+    auto get_tex = [&](const std::string &p, const char *def_key, std::vector<uint8_t> def_px, bool single, uint32_t &out_idx) -> bool {
+        const std::string key = p.empty() ? def_key : p;
+        auto it = index_of.find(key);
+        if (it != index_of.end()) { out_idx = it->second; return true; }
+        HostTexture t;
+        if (!p.empty()) {
+            std::vector<uint8_t> rgba; uint32_t w, h;
+            if (!decode_image_rgba8(p, w, h, rgba, err)) return false;
+            t.width = w; t.height = h;
+            if (single) { t.channels = 1; t.data.resize((size_t)w * h); for (size_t i = 0; i < (size_t)w * h; i++) t.data[i] = rgba[i * 4]; }   // R channel (Q8)
+            else { t.channels = 4; t.data = std::move(rgba); }
+        } else { t.width = t.height = 1; t.channels = (uint32_t)def_px.size(); t.data = def_px; }
+        out_idx = (uint32_t)sc.textures.size(); index_of[key] = out_idx; sc.textures.push_back(std::move(t));
+        return true;
+    };
+    for (size_t i = 0; i < sc.materials.size(); i++) {
+        b200pt_material &m = sc.materials[i];
+        if (!get_tex(tps[i].base, "EMPTY_BASECOLOR_TEXTURE", { 255, 255, 255, 255 }, false, m.BaseColorTextureIndex)) return false;
+        if (!get_tex(tps[i].normal, "EMPTY_NORMAL_TEXTURE", { 128, 128, 255, 255 }, false, m.NormalTextureIndex)) return false;
+        if (!get_tex(tps[i].rough, "EMPTY_ROUGHNESS_TEXTURE", { 255 }, true, m.RoughnessTextureIndex)) return false;
+        if (!get_tex(tps[i].metal, "EMPTY_METALLIC_TEXTURE", { 255 }, true, m.MetallicTextureIndex)) return false;
+        if (!get_tex(tps[i].emissive, "EMPTY_EMISSIVE_TEXTURE", { 255, 255, 255, 255 }, false, m.EmissiveTextureIndex)) return false;
+    }
+    return true;
+}
+
 // base64 payload of a "data:<mime>;base64,<payload>" URI (glTF 2.0 spec 3.6.1.1); assimp's glTF2 importer decodes these transparently
 static bool decode_data_uri(const std::string &uri, std::vector<uint8_t> &out) {
     const size_t k = uri.find(";base64,");
@@ -290,7 +321,6 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
     const JVal *mats = g.get("materials"), *texs = g.get("textures"), *imgs = g.get("images");
     size_t nmat = mats ? mats->size() : 0;
     bool need_default = false; for (int m : mesh_material) if (m < 0) need_default = true;
-    struct TexPaths { std::string base, normal, rough, metal, emissive; };
     std::vector<TexPaths> tps;
     bool embedded_image = false;
     auto tex_path = [&](const JVal *ti) -> std::string {
@@ -324,31 +354,7 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
         tps.push_back(tp);
     }
     if (embedded_image) { err = "embedded (bufferView / data: URI) textures are not supported: the reference loads textures from files next to the model only"; return false; }
-    // ---- texture table in PathTracer::SetScene order (PathTracer.cpp:228-408)
-    std::map<std::string, uint32_t> index_of;
-    auto get_tex = [&](const std::string &p, const char *def_key, std::vector<uint8_t> def_px, bool single, uint32_t &out_idx) -> bool {
-        const std::string key = p.empty() ? def_key : p;
-        auto it = index_of.find(key);
-        if (it != index_of.end()) { out_idx = it->second; return true; }
-        HostTexture t;
-        if (!p.empty()) {
-            std::vector<uint8_t> rgba; uint32_t w, h;
-            if (!decode_image_rgba8(p, w, h, rgba, err)) return false;
-            t.width = w; t.height = h;
-            if (single) { t.channels = 1; t.data.resize((size_t)w * h); for (size_t i = 0; i < (size_t)w * h; i++) t.data[i] = rgba[i * 4]; }   // R channel (Q8)
-            else { t.channels = 4; t.data = std::move(rgba); }
-        } else { t.width = t.height = 1; t.channels = (uint32_t)def_px.size(); t.data = def_px; }
-        out_idx = (uint32_t)sc.textures.size(); index_of[key] = out_idx; sc.textures.push_back(std::move(t));
-        return true;
-    };
-    for (size_t i = 0; i < sc.materials.size(); i++) {
-        b200pt_material &m = sc.materials[i];
-        if (!get_tex(tps[i].base, "EMPTY_BASECOLOR_TEXTURE", { 255, 255, 255, 255 }, false, m.BaseColorTextureIndex)) return false;
-        if (!get_tex(tps[i].normal, "EMPTY_NORMAL_TEXTURE", { 128, 128, 255, 255 }, false, m.NormalTextureIndex)) return false;
-        if (!get_tex(tps[i].rough, "EMPTY_ROUGHNESS_TEXTURE", { 255 }, true, m.RoughnessTextureIndex)) return false;
-        if (!get_tex(tps[i].metal, "EMPTY_METALLIC_TEXTURE", { 255 }, true, m.MetallicTextureIndex)) return false;
-        if (!get_tex(tps[i].emissive, "EMPTY_EMISSIVE_TEXTURE", { 255, 255, 255, 255 }, false, m.EmissiveTextureIndex)) return false;
-    }
+    if (!build_texture_table(sc, tps, err)) return false;
 
     // ---- nodes -> instances + first camera (:220-262, :547-642)
     const JVal *nodes = g.get("nodes"), *scenes = g.get("scenes"), *cams = g.get("cameras");
@@ -420,6 +426,179 @@ bool scene_from_desc(const b200pt_scene_desc *d, HostScene &sc, std::string &err
     memcpy(sc.camera_view, d->camera_view, sizeof sc.camera_view);
     sc.camera_aspect = d->camera_aspect > 0.0f ? d->camera_aspect : 1.0f;
     return true;
+}
+
+
+// ================================================================================================ Wavefront OBJ / MTL
+// The reference imports every format through assimp (AssetImporterImpl.cpp:82-97: Triangulate | GenNormals | GenUVCoords | CalcTangentSpace |
+// JoinIdenticalVertices | SortByPType | OptimizeMeshes | OptimizeGraph | FlipUVs) and then reads a fixed set of material keys (:353-455).
+// This reader restates that path for OBJ.  PARITY UNPINNED: assimp is not available here and the reference ships no OBJ asset, so the
+// importer-specific parts below follow assimp 6.0.2's ObjFileParser / ObjFileMtlImporter from upstream knowledge:
+//   geometry   one mesh per (object / group, material) run; polygons -> triangle fans; a face vertex is (v, vt, vn), merged when all three
+//              agree (JoinIdenticalVertices); faces without vn get their flat face normal (GenNormals runs on unshared vertices);
+//              uv = (u, 1 - v) (FlipUVs); vertices in first-use order; one instance per mesh, Transform = diag(1,-1,1,1) (:233-247)
+//   materials  index 0 = assimp's "DefaultMaterial" (Kd 0.6), then the newmtl entries in file order.  Keys the reference reads:
+//              COLOR_DIFFUSE <- Kd (0.6), COLOR_EMISSIVE <- Ke (0), COLOR_SPECULAR <- Ks (0), REFRACTI <- Ni (1.0: always set by the importer),
+//              ROUGHNESS_FACTOR <- Pr (absent -> 1), METALLIC_FACTOR <- Pm (absent -> 0), ANISOTROPY_FACTOR <- aniso, ANISOTROPY_ROTATION <- anisor
+//              (radians -> degrees, :404-414); no transmission / emissive-intensity keys.  Textures: DIFFUSE <- map_Kd, NORMALS <- norm / map_Kn,
+//              DIFFUSE_ROUGHNESS <- map_Pr, METALNESS <- map_Pm, EMISSIVE <- map_Ke (map_bump / bump go to HEIGHT, which the reference ignores).
+//   camera     none in OBJ: the reference's default lookAt((0,0,5), 0, +Y), aspect 16:9 (PathTracer.cpp:171-178)
+namespace {
+struct ObjMtl { std::string name; b200pt_material m; TexPaths tp; bool has_pr = false, has_pm = false; };
+void obj_default_material(b200pt_material &o) {
+    memset(&o, 0, sizeof o);
+    for (int k = 0; k < 3; k++) { o.BaseColor[k] = 0.6f; o.SpecularColor[k] = 0.0f; o.MediumColor[k] = 1.0f; }
+    o.Metallic = 0.0f; o.Roughness = 1.0f; o.IOR = 1.0f;
+}
+std::vector<std::string> obj_tokens(const std::string &line) {
+    std::vector<std::string> t; size_t i = 0;
+    while (i < line.size()) {
+        while (i < line.size() && (line[i] == ' ' || line[i] == '\t' || line[i] == '\r')) i++;
+        size_t j = i; while (j < line.size() && line[j] != ' ' && line[j] != '\t' && line[j] != '\r') j++;
+        if (j > i) t.push_back(line.substr(i, j - i));
+        i = j;
+    }
+    return t;
+}
+bool obj_lines(const std::string &path, std::vector<std::string> &out) {
+    std::vector<uint8_t> d; if (!read_all(path, d)) return false;
+    std::string cur;
+    for (size_t i = 0; i <= d.size(); i++) {
+        const char c = i < d.size() ? (char)d[i] : '\n';
+        if (c == '\n') {
+            if (!cur.empty() && cur.back() == '\r') cur.pop_back();
+            if (!cur.empty() && cur.back() == '\\') { cur.pop_back(); cur.push_back(' '); continue; }   // line continuation
+            const size_t h = cur.find('#'); if (h != std::string::npos) cur.erase(h);
+            out.push_back(cur); cur.clear();
+        } else cur.push_back(c);
+    }
+    return true;
+}
+bool load_mtl(const std::string &path, const std::string &base, std::vector<ObjMtl> &mats, std::string &err) {
+    std::vector<std::string> lines;
+    if (!obj_lines(path, lines)) { err = "cannot read material library " + path; return false; }
+    ObjMtl *cur = nullptr;
+    auto f3v = [](const std::vector<std::string> &t, float out[3]) { for (int k = 0; k < 3; k++) out[k] = (float)atof(t[(size_t)std::min<size_t>(1 + k, t.size() - 1)].c_str()); };
+    for (const std::string &ln : lines) {
+        const std::vector<std::string> t = obj_tokens(ln);
+        if (t.empty()) continue;
+        if (t[0] == "newmtl") { mats.emplace_back(); cur = &mats.back(); obj_default_material(cur->m); cur->name = t.size() > 1 ? t[1] : ""; continue; }
+        if (!cur || t.size() < 2) continue;
+        const std::string &k = t[0];
+        const std::string file = base + "/" + t.back();                     // options (-bm, -o, ...) precede the file name
+        if (k == "Kd") f3v(t, cur->m.BaseColor);
+        else if (k == "Ke") f3v(t, cur->m.EmissiveColor);
+        else if (k == "Ks") f3v(t, cur->m.SpecularColor);
+        else if (k == "Ni") cur->m.IOR = (float)atof(t[1].c_str());
+        else if (k == "Pr") cur->m.Roughness = (float)atof(t[1].c_str());
+        else if (k == "Pm") cur->m.Metallic = (float)atof(t[1].c_str());
+        else if (k == "aniso") cur->m.Anisotropy = (float)atof(t[1].c_str());
+        else if (k == "anisor") cur->m.AnisotropyRotation = (float)atof(t[1].c_str()) * (180.0f / 3.14159265358979323846f);
+        else if (k == "map_Kd") cur->tp.base = file;
+        else if (k == "norm" || k == "map_Kn") cur->tp.normal = file;
+        else if (k == "map_Pr") cur->tp.rough = file;
+        else if (k == "map_Pm") cur->tp.metal = file;
+        else if (k == "map_Ke") cur->tp.emissive = file;
+    }
+    return true;
+}
+} // namespace
+
+bool load_obj_scene(const std::string &path, HostScene &sc, std::string &err) {
+    std::vector<std::string> lines;
+    if (!obj_lines(path, lines)) { err = "cannot read " + path; return false; }
+    std::string base = path; { size_t k = base.find_last_of("/\\"); base = (k == std::string::npos) ? "." : base.substr(0, k); }
+    std::vector<float> P, N, T;                                             // v, vn, vt pools
+    std::vector<ObjMtl> mats; { ObjMtl d; d.name = "DefaultMaterial"; obj_default_material(d.m); mats.push_back(d); }
+    struct Key { int v, t, n; float gn[3]; bool operator<(const Key &o) const { if (v != o.v) return v < o.v; if (t != o.t) return t < o.t; if (n != o.n) return n < o.n; return memcmp(gn, o.gn, sizeof gn) < 0; } };
+    struct Build { std::string name; uint32_t material; std::map<Key, uint32_t> index; HostMesh mesh; };
+    std::vector<Build> builds;
+    std::string group; uint32_t material = 0; bool need_new = true;
+    auto current = [&]() -> Build & {
+        if (need_new || builds.empty()) { builds.emplace_back(); builds.back().name = group; builds.back().material = material; builds.back().mesh.name = group; need_new = false; }
+        return builds.back();
+    };
+    for (const std::string &ln : lines) {
+        const std::vector<std::string> t = obj_tokens(ln);
+        if (t.empty()) continue;
+        const std::string &k = t[0];
+        if (k == "v" && t.size() >= 4) { for (int c = 1; c <= 3; c++) P.push_back((float)atof(t[(size_t)c].c_str())); }
+        else if (k == "vn" && t.size() >= 4) { for (int c = 1; c <= 3; c++) N.push_back((float)atof(t[(size_t)c].c_str())); }
+        else if (k == "vt" && t.size() >= 2) { T.push_back((float)atof(t[1].c_str())); T.push_back(t.size() >= 3 ? (float)atof(t[2].c_str()) : 0.0f); }
+        else if (k == "o" || k == "g") { group = t.size() > 1 ? t[1] : ""; if (!builds.empty() && !builds.back().mesh.indices.empty()) need_new = true; else if (!builds.empty()) { builds.back().name = group; builds.back().mesh.name = group; } }
+        else if (k == "mtllib") { for (size_t i = 1; i < t.size(); i++) if (!load_mtl(base + "/" + t[i], base, mats, err)) return false; }
+        else if (k == "usemtl") {
+            uint32_t found = 0; for (size_t i = 1; i < mats.size(); i++) if (t.size() > 1 && mats[i].name == t[1]) found = (uint32_t)i;
+            if (found != material) { material = found; if (!builds.empty() && !builds.back().mesh.indices.empty()) need_new = true; else if (!builds.empty()) builds.back().material = material; }
+        }
+        else if (k == "f" && t.size() >= 4) {
+            Build &b = current();
+            std::vector<Key> fv;
+            for (size_t i = 1; i < t.size(); i++) {
+                Key key{ 0, 0, 0, { 0, 0, 0 } };
+                int part = 0; std::string num;
+                const std::string tok = t[i] + "/";
+                for (char c : tok) {
+                    if (c == '/') { const int val = num.empty() ? 0 : atoi(num.c_str()); if (part == 0) key.v = val; else if (part == 1) key.t = val; else if (part == 2) key.n = val; part++; num.clear(); }
+                    else num.push_back(c);
+                }
+                const int nv = (int)(P.size() / 3), nt = (int)(T.size() / 2), nn = (int)(N.size() / 3);
+                if (key.v < 0) key.v = nv + key.v + 1; if (key.t < 0) key.t = nt + key.t + 1; if (key.n < 0) key.n = nn + key.n + 1;
+                if (key.v < 1 || key.v > nv || key.t > nt || key.n > nn) { err = "OBJ face index out of range"; return false; }
+                fv.push_back(key);
+            }
+            for (size_t i = 1; i + 1 < fv.size(); i++) {                  // triangle fan
+                Key tri[3] = { fv[0], fv[i], fv[i + 1] };
+                if (!tri[0].n || !tri[1].n || !tri[2].n) {                 // GenNormals: flat face normal for vertices that have none
+                    const float *a = &P[(size_t)(tri[0].v - 1) * 3], *bb = &P[(size_t)(tri[1].v - 1) * 3], *c = &P[(size_t)(tri[2].v - 1) * 3];
+                    const float e1[3] = { bb[0] - a[0], bb[1] - a[1], bb[2] - a[2] }, e2[3] = { c[0] - a[0], c[1] - a[1], c[2] - a[2] };
+                    float g[3] = { e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0] };
+                    const float len = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+                    if (len > 0.0f) { g[0] /= len; g[1] /= len; g[2] /= len; }
+                    for (Key &q : tri) if (!q.n) { q.gn[0] = g[0]; q.gn[1] = g[1]; q.gn[2] = g[2]; }
+                }
+                for (const Key &q : tri) {
+                    auto it = b.index.find(q);
+                    uint32_t idx;
+                    if (it != b.index.end()) idx = it->second;
+                    else {
+                        idx = (uint32_t)b.mesh.vertices.size(); b.index[q] = idx;
+                        b200pt_vertex v; memset(&v, 0, sizeof v);
+                        for (int c = 0; c < 3; c++) v.Position[c] = P[(size_t)(q.v - 1) * 3 + c];
+                        float nx, ny, nz;
+                        if (q.n) { nx = N[(size_t)(q.n - 1) * 3]; ny = N[(size_t)(q.n - 1) * 3 + 1]; nz = N[(size_t)(q.n - 1) * 3 + 2]; } else { nx = q.gn[0]; ny = q.gn[1]; nz = q.gn[2]; }
+                        const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);       // glm::normalize (:165)
+                        v.Normal[0] = nx * inv; v.Normal[1] = ny * inv; v.Normal[2] = nz * inv;
+                        if (q.t) { v.TexCoord[0] = T[(size_t)(q.t - 1) * 2]; v.TexCoord[1] = 1.0f - T[(size_t)(q.t - 1) * 2 + 1]; }   // FlipUVs
+                        b.mesh.vertices.push_back(v);
+                    }
+                    b.mesh.indices.push_back(idx);
+                }
+            }
+        }
+    }
+    for (auto &b : builds) if (!b.mesh.indices.empty()) {
+        b200pt_instance in; M4 flip = m4_identity(); flip.m[1][1] = -1.0f; m4_to_colmajor(flip, in.Transform);
+        in.MeshIndex = (uint32_t)sc.meshes.size(); in.MaterialIndex = b.material;
+        sc.meshes.push_back(std::move(b.mesh)); sc.instances.push_back(in);
+    }
+    if (sc.meshes.empty()) { err = "No meshes found in scene"; return false; }
+    std::vector<TexPaths> tps;
+    for (const ObjMtl &m : mats) { sc.materials.push_back(m.m); sc.material_names.push_back(m.name); tps.push_back(m.tp); }
+    if (!build_texture_table(sc, tps, err)) return false;
+    M4 v = m4_identity(); v.m[2][3] = -5.0f; m4_to_colmajor(v, sc.camera_view); sc.camera_aspect = 16.0f / 9.0f;   // PathTracer.cpp:171-178
+    return true;
+}
+
+// AssetImporter::ImportScene (AssetImporterImpl.cpp:82-97): the importer is picked by the file extension
+bool load_scene_file(const std::string &path, HostScene &sc, std::string &err) {
+    const size_t dot = path.find_last_of('.');
+    std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
+    for (char &c : ext) c = (char)tolower((unsigned char)c);
+    if (ext == "obj") return load_obj_scene(path, sc, err);
+    if (ext == "gltf" || ext == "glb") return load_gltf_scene(path, sc, err);
+    err = "unsupported scene format ." + ext + " (glTF 2.0 .gltf / .glb and Wavefront .obj are implemented)";
+    return false;
 }
 
 } // namespace b200pt
