@@ -126,6 +126,7 @@ def load_gltf(path, decode_image=_decode_image):
             elif mode == 6:                                  # TRIANGLE_FAN
                 idx = np.array([(idx[0], idx[f + 1], idx[f + 2]) for f in range(max(len(idx) - 2, 0))], np.uint32).reshape(-1)
             idx = idx[:len(idx) // 3 * 3]
+            if len(idx) == 0 or n == 0: raise ValueError("primitive without triangles")
             if "NORMAL" in at:
                 nr = _accessor(g, buffers, at["NORMAL"]).astype(np.float32)
             else:

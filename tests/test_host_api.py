@@ -475,3 +475,30 @@ def test_obj_mtl_import(tmp_path):
     with pytest.raises(pt.B200ptError): pt.load_gltf(str(tmp_path / "bad.obj"))
     (tmp_path / "x.fbx").write_text("nope")
     with pytest.raises(pt.B200ptError): pt.load_gltf(str(tmp_path / "x.fbx"))
+
+
+def test_decoders_and_importers_survive_corrupted_files(tmp_path):
+    """Texture / scene files are untrusted input: flipped bytes, truncation and insertions must come back as error codes (or as a decoded
+    image), never as a crash or an exception across the C-ABI.  (The same corpus generator was run under ASan / UBSan during development:
+    it found an unchecked Huffman-table size and overflow in the IDCT of garbage coefficients, both fixed.)"""
+    from PIL import Image
+    rng = np.random.default_rng(123)
+    img = (rng.random((29, 41, 3)) * 255).astype(np.uint8)
+    Image.fromarray(img).save(tmp_path / "b.jpg", quality=80); Image.fromarray(img).save(tmp_path / "p.jpg", quality=80, progressive=True)
+    Image.fromarray(img).save(tmp_path / "a.png"); util.write_rgbe(str(tmp_path / "e.hdr"), rng.random((7, 33, 3)).astype(np.float32) * 4)
+    util.write_synthetic_gltf(tmp_path)
+    (tmp_path / "o.obj").write_text("mtllib m.mtl\\nv 0 0 0\\nv 1 0 0\\nv 0 1 0\\nvt 0 0\\nvn 0 0 1\\nusemtl a\\nf 1/1/1 2/1/1 3/1/1\\n"); (tmp_path / "m.mtl").write_text("newmtl a\\nKd 1 0 0\\n")
+    files = {"b.jpg": pt.decode_image, "p.jpg": pt.decode_image, "a.png": pt.decode_image, "e.hdr": pt.decode_hdr, "s.gltf": pt.load_gltf, "o.obj": pt.load_gltf}
+    ok = bad = 0
+    for it in range(480):
+        name = list(files)[it % len(files)]; raw = bytearray((tmp_path / name).read_bytes())
+        mode = int(rng.integers(0, 3))
+        if mode == 0:
+            for _ in range(int(rng.integers(1, 6))): raw[int(rng.integers(0, len(raw)))] = int(rng.integers(0, 256))
+        elif mode == 1: raw = raw[:int(rng.integers(1, len(raw)))]
+        else:
+            a = int(rng.integers(0, len(raw))); raw[a:a] = bytes(rng.integers(0, 256, int(rng.integers(1, 9)), dtype=np.uint8))
+        fn = tmp_path / ("mut" + os.path.splitext(name)[1]); fn.write_bytes(bytes(raw))
+        try: files[name](str(fn)); ok += 1
+        except pt.B200ptError: bad += 1
+    assert ok + bad == 480 and bad > 100

@@ -183,7 +183,7 @@ def partition_rows(H, rank, world, band):
 def decode_image(path):
     w, h, p = C.c_uint32(), C.c_uint32(), C.c_void_p()
     r = lib().b200pt_decode_image_file(path.encode(), C.byref(w), C.byref(h), C.byref(p))
-    if r != OK: raise B200ptError(r, lib().b200pt_last_error(None).decode())
+    if r != OK: raise B200ptError(r, lib().b200pt_last_error(None).decode(errors="replace"))
     a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 4)).copy()
     lib().b200pt_free(p)
     return a
@@ -192,7 +192,7 @@ def decode_image(path):
 def decode_hdr(path):
     w, h, p = C.c_uint32(), C.c_uint32(), C.c_void_p()
     r = lib().b200pt_decode_hdr_file(path.encode(), C.byref(w), C.byref(h), C.byref(p))
-    if r != OK: raise B200ptError(r, lib().b200pt_last_error(None).decode())
+    if r != OK: raise B200ptError(r, lib().b200pt_last_error(None).decode(errors="replace"))
     a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(h.value, w.value, 4)).copy()
     lib().b200pt_free(p)
     return a
@@ -238,7 +238,7 @@ def load_gltf(path):
     """C++ loader -> python dict in the same shape as oracle.gltf_ref.load_gltf (for loader parity tests)."""
     pd = C.POINTER(SceneDesc)()
     r = lib().b200pt_load_gltf(path.encode(), C.byref(pd))
-    if r != OK: raise B200ptError(r, lib().b200pt_last_error(None).decode())
+    if r != OK: raise B200ptError(r, lib().b200pt_last_error(None).decode(errors="replace"))
     d = pd.contents
     vdt = np.dtype([("pos", "<f4", 3), ("nrm", "<f4", 3), ("uv", "<f4", 2)])
     meshes = []
@@ -266,7 +266,7 @@ class PathTracer:
     def __init__(self, device=0):
         self.L = lib(); self.h = C.c_void_p()
         r = self.L.b200pt_create(device, C.byref(self.h))
-        if r != OK: raise B200ptError(r, self.L.b200pt_last_error(None).decode())
+        if r != OK: raise B200ptError(r, self.L.b200pt_last_error(None).decode(errors="replace"))
         self._keep = []
 
     def close(self):
@@ -277,7 +277,7 @@ class PathTracer:
         except Exception: pass
 
     def _ck(self, r):
-        if r != OK: raise B200ptError(r, self.L.b200pt_last_error(self.h).decode())
+        if r != OK: raise B200ptError(r, self.L.b200pt_last_error(self.h).decode(errors="replace"))
 
     # ---- volumes: PathTracer::AddVolume / SetVolume / RemoveVolume / SetPhaseFunction (homogeneous AABB volumes)
     @staticmethod

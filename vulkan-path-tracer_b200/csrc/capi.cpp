@@ -203,15 +203,19 @@ int32_t b200pt_scene_stats(b200pt_handle h, uint32_t *a, uint32_t *b, uint32_t *
 int32_t b200pt_decode_image_file(const char *path, uint32_t *w, uint32_t *hh, uint8_t **out) {
     if (!path || !w || !hh || !out) return B200PT_ERR_WRONG_ARGUMENTS;
     std::vector<uint8_t> px; std::string err;
-    if (!decode_image_rgba8(path, *w, *hh, px, err)) { g_err = err; return B200PT_ERR_INIT_FAILED; }
-    *out = (uint8_t *)malloc(px.size()); if (!*out) return B200PT_ERR_OUT_OF_MEMORY;
+    try { if (!decode_image_rgba8(path, *w, *hh, px, err)) { g_err = err; return B200PT_ERR_INIT_FAILED; } }   // no exception crosses the boundary (Error.h:14-72)
+    catch (const std::bad_alloc &) { g_err = "out of memory while decoding " + std::string(path); return B200PT_ERR_OUT_OF_MEMORY; }
+    catch (...) { g_err = "unexpected failure while decoding " + std::string(path); return B200PT_ERR_UNKNOWN; }
+    *out = (uint8_t *)malloc(px.size() ? px.size() : 1); if (!*out) return B200PT_ERR_OUT_OF_MEMORY;
     memcpy(*out, px.data(), px.size()); return B200PT_OK;
 }
 int32_t b200pt_decode_hdr_file(const char *path, uint32_t *w, uint32_t *hh, float **out) {
     if (!path || !w || !hh || !out) return B200PT_ERR_WRONG_ARGUMENTS;
     std::vector<float> px; std::string err;
-    if (!decode_hdr_rgba32f(path, *w, *hh, px, err)) { g_err = err; return B200PT_ERR_INIT_FAILED; }
-    *out = (float *)malloc(px.size() * 4); if (!*out) return B200PT_ERR_OUT_OF_MEMORY;
+    try { if (!decode_hdr_rgba32f(path, *w, *hh, px, err)) { g_err = err; return B200PT_ERR_INIT_FAILED; } }
+    catch (const std::bad_alloc &) { g_err = "out of memory while decoding " + std::string(path); return B200PT_ERR_OUT_OF_MEMORY; }
+    catch (...) { g_err = "unexpected failure while decoding " + std::string(path); return B200PT_ERR_UNKNOWN; }
+    *out = (float *)malloc(px.size() ? px.size() * 4 : 4); if (!*out) return B200PT_ERR_OUT_OF_MEMORY;
     memcpy(*out, px.data(), px.size() * 4); return B200PT_OK;
 }
 int32_t b200pt_write_png(const char *path, uint32_t w, uint32_t hh, const uint8_t *rgba) {
@@ -241,7 +245,8 @@ int32_t b200pt_load_gltf(const char *path, b200pt_scene_desc **out) {
         if (!load_scene_file(path, o->host, err)) { g_err = err; delete o; return B200PT_ERR_INIT_FAILED; }
         for (auto &m : o->host.meshes) o->meshes.push_back({ m.vertices.data(), m.indices.data(), (uint32_t)m.vertices.size(), (uint32_t)m.indices.size() });
         for (auto &t : o->host.textures) o->textures.push_back({ t.width, t.height, t.channels, 0, t.data.data() });
-    } catch (...) { delete o; return B200PT_ERR_UNKNOWN; }
+    } catch (const std::bad_alloc &) { delete o; g_err = "out of memory while importing the scene"; return B200PT_ERR_OUT_OF_MEMORY; }
+    catch (...) { delete o; g_err = "unexpected failure while importing the scene"; return B200PT_ERR_UNKNOWN; }
     memset(&o->desc, 0, sizeof o->desc);
     o->desc.meshes = o->meshes.data(); o->desc.mesh_count = (uint32_t)o->meshes.size();
     o->desc.materials = o->host.materials.data(); o->desc.material_count = (uint32_t)o->host.materials.size();

@@ -54,6 +54,7 @@ static bool decode_png(const std::vector<uint8_t> &d, uint32_t &W, uint32_t &H, 
         pos += 12 + (size_t)len;
     }
     if (!have_ihdr || W == 0 || H == 0) { err = "missing IHDR"; return false; }
+    if (W > 65535u || H > 65535u || (uint64_t)W * H > (1ull << 28)) { err = "PNG dimensions out of range"; return false; }   // texture side limit of the reference's image path
     if (interlace > 1) { err = "unknown PNG interlace method"; return false; }
     int chans = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!chans || !(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) { err = "unsupported PNG format"; return false; }
@@ -165,6 +166,7 @@ const uint8_t kZig[64 + 15] = { 0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11
                                 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63 };
 
 bool build_huff(Huff &h, const uint8_t *counts) {
+    { int total = 0; for (int i = 0; i < 16; i++) total += counts[i]; if (total > 256) return false; }   // a corrupt DHT must not run past the 256-symbol tables
     int k = 0;
     for (int i = 0; i < 16; i++) for (int j = 0; j < counts[i]; j++) h.size[k++] = (uint8_t)(i + 1);
     h.size[k] = 0;
@@ -305,11 +307,12 @@ bool decode_block_prog_ac(Jpeg &j, short data[64], const Huff &hac) {
     }
     return true;
 }
-inline uint8_t clamp8(int x) { if ((unsigned)x > 255) { if (x < 0) return 0; if (x > 255) return 255; } return (uint8_t)x; }
+inline uint8_t clamp8(long long x) { if (x < 0) return 0; if (x > 255) return 255; return (uint8_t)x; }
 #define F2F(x) ((int)(((x) * 4096 + 0.5)))
 #define FSH(x) ((x) * 4096)
+// 64-bit temporaries: identical results for every valid stream (nothing there exceeds 31 bits), no signed overflow on corrupt ones
 #define IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7) \
-    int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3; \
+    long long t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3; \
     p2 = s2; p3 = s6; p1 = (p2 + p3) * F2F(0.5411961f); t2 = p1 + p3 * F2F(-1.847759065f); t3 = p1 + p2 * F2F(0.765366865f); \
     p2 = s0; p3 = s4; t0 = FSH(p2 + p3); t1 = FSH(p2 - p3); x0 = t0 + t3; x3 = t0 - t3; x1 = t1 + t2; x2 = t1 - t2; \
     t0 = s7; t1 = s5; t2 = s3; t3 = s1; p3 = t0 + t2; p4 = t1 + t3; p1 = t0 + t3; p2 = t1 + t2; p5 = (p3 + p4) * F2F(1.175875602f); \
@@ -324,8 +327,8 @@ void idct_block(uint8_t *out, int stride, short data[64]) {
         } else {
             IDCT_1D(d[0], d[8], d[16], d[24], d[32], d[40], d[48], d[56])
             x0 += 512; x1 += 512; x2 += 512; x3 += 512;
-            v[0] = (x0 + t3) >> 10; v[56] = (x0 - t3) >> 10; v[8] = (x1 + t2) >> 10; v[48] = (x1 - t2) >> 10;
-            v[16] = (x2 + t1) >> 10; v[40] = (x2 - t1) >> 10; v[24] = (x3 + t0) >> 10; v[32] = (x3 - t0) >> 10;
+            v[0] = (int)((x0 + t3) >> 10); v[56] = (int)((x0 - t3) >> 10); v[8] = (int)((x1 + t2) >> 10); v[48] = (int)((x1 - t2) >> 10);
+            v[16] = (int)((x2 + t1) >> 10); v[40] = (int)((x2 - t1) >> 10); v[24] = (int)((x3 + t0) >> 10); v[32] = (int)((x3 - t0) >> 10);
         }
     }
     v = val; uint8_t *o = out;
@@ -369,7 +372,7 @@ bool jpeg_decode(Jpeg &j, std::vector<uint8_t> &rgba) {
         int L = u16(j.p); const uint8_t *d = j.p + 2, *de = j.p + L;
         if (de > j.end) { j.err = "truncated JPEG"; return false; }
         if (m == 0xDB) { while (d < de) { int q = *d++; int p16 = q >> 4, t = q & 15; if (t > 3) { j.err = "bad DQT"; return false; } for (int i = 0; i < 64; i++) { j.dq[t][kZig[i]] = (uint16_t)(p16 ? u16(d) : *d); d += p16 ? 2 : 1; } } }
-        else if (m == 0xC4) { while (d < de) { int q = *d++; int tc = q >> 4, th = q & 15; if (tc > 1 || th > 3) { j.err = "bad DHT"; return false; } const uint8_t *counts = d; int n = 0; for (int i = 0; i < 16; i++) n += counts[i]; d += 16; Huff &h = tc ? j.ac[th] : j.dc[th]; if (!build_huff(h, counts)) { j.err = "bad huffman table"; return false; } memcpy(h.values, d, (size_t)n); d += n; } }
+        else if (m == 0xC4) { while (d < de) { int q = *d++; int tc = q >> 4, th = q & 15; if (tc > 1 || th > 3) { j.err = "bad DHT"; return false; } if (d + 16 > de) { j.err = "truncated DHT"; return false; } const uint8_t *counts = d; int n = 0; for (int i = 0; i < 16; i++) n += counts[i]; d += 16; if (n > 256 || d + n > de) { j.err = "bad DHT"; return false; } Huff &h = tc ? j.ac[th] : j.dc[th]; if (!build_huff(h, counts)) { j.err = "bad huffman table"; return false; } memcpy(h.values, d, (size_t)n); d += n; } }
         else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
             if (d[0] != 8) { j.err = "only 8-bit JPEG"; return false; }
             j.progressive = (m == 0xC2);
@@ -377,6 +380,7 @@ bool jpeg_decode(Jpeg &j, std::vector<uint8_t> &rgba) {
             if (j.ncomp != 1 && j.ncomp != 3) { j.err = "unsupported JPEG component count"; return false; }
             for (int i = 0; i < j.ncomp; i++) { Comp &c = j.c[i]; c.id = d[6 + i * 3]; c.h = d[7 + i * 3] >> 4; c.v = d[7 + i * 3] & 15; c.tq = d[8 + i * 3]; if (!c.h || !c.v || c.h > 4 || c.v > 4 || c.tq > 3) { j.err = "bad SOF"; return false; } j.hmax = std::max(j.hmax, c.h); j.vmax = std::max(j.vmax, c.v); }
             if (!j.W || !j.H) { j.err = "JPEG without size"; return false; }
+            if ((uint64_t)j.W * j.H > (1ull << 28)) { j.err = "JPEG dimensions out of range"; return false; }
             const int mcuw = j.hmax * 8, mcuh = j.vmax * 8;
             j.mcux = ((int)j.W + mcuw - 1) / mcuw; j.mcuy = ((int)j.H + mcuh - 1) / mcuh;
             for (int i = 0; i < j.ncomp; i++) {

@@ -288,6 +288,7 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
             }
             hm.indices.resize(hm.indices.size() / 3 * 3);
             for (uint32_t ix : hm.indices) if (ix >= n) { err = "index out of range"; return false; }
+            if (hm.indices.empty() || n == 0) { err = "primitive without triangles"; return false; }
             if (!has_nrm) {
                 // aiProcess_GenNormals (AssetImporterImpl.cpp:82-97) = assimp 6.0.2 GenFaceNormalsProcess (from upstream knowledge):
                 // every face writes NormalizeSafe(cross(v1 - v0, v2 - v0)) to its three vertices, so a shared vertex keeps the normal of the
