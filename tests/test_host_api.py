@@ -255,6 +255,11 @@ def test_bvh4_collapse_rejects_bad_arguments_and_leaf_root():
     assert len(n4) == 0 and d == 0
     with pytest.raises(B.B200ptError):
         B.bvh4_collapse(nodes2, 99)
+    # not a tree: a child index outside the array, a cycle -> zero nodes, no crash / endless loop
+    bad = nodes2.copy(); bad[0]["c0"] = 1000
+    assert len(B.bvh4_collapse(bad, 0)[0]) == 0
+    cyc = nodes2.copy(); cyc[1]["c0"] = 0
+    assert len(B.bvh4_collapse(cyc, 0)[0]) == 0
 
 
 def test_volume_struct_and_defaults_without_gpu():

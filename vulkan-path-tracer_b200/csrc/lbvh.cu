@@ -352,7 +352,9 @@ uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t ro
     if (root2 < 0 || n_nodes2 == 0) return 0;
     struct Slot { int32_t child; float lo[3], hi[3]; };
     auto area = [](const Slot &s) { const float dx = s.hi[0] - s.lo[0], dy = s.hi[1] - s.lo[1], dz = s.hi[2] - s.lo[2]; return dx * dy + dy * dz + dz * dx; };
+    bool bad = false;                                                       // a child index outside the array or a cycle: not a tree
     auto slots_of = [&](int32_t n, Slot &a, Slot &b) {
+        if ((uint32_t)n >= n_nodes2) { bad = true; n = 0; }
         const BvhNode &N = nodes2[n];
         a.child = N.c0; b.child = N.c1;
         for (int k = 0; k < 3; k++) { a.lo[k] = N.lo0[k]; a.hi[k] = N.hi0[k]; b.lo[k] = N.lo1[k]; b.hi[k] = N.hi1[k]; }
@@ -362,6 +364,7 @@ uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t ro
     queue.push_back({ root2, 1 });
     int max_d = 1;
     for (size_t i = 0; i < queue.size(); i++) {
+        if (bad || queue.size() > (size_t)n_nodes2) { if (depth4) *depth4 = 0; return 0; }   // every BVH4 node consumes at least one BVH2 node
         const int32_t n2 = queue[i].first; const int dep = queue[i].second;
         if (dep > max_d) max_d = dep;
         Slot sl[4]; int ns = 2;
@@ -387,6 +390,7 @@ uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t ro
             o._pad[k] = 0;
         }
     }
+    if (bad || queue.size() > (size_t)n_nodes2) { if (depth4) *depth4 = 0; return 0; }
     if (depth4) *depth4 = max_d;
     return (uint32_t)queue.size();
 }
