@@ -227,6 +227,12 @@ int32_t b200pt_scene_stats(b200pt_handle h, uint32_t *triangles, uint32_t *bvh_n
  * Returns the node count in *n_nodes4_out (0 when root2 is a leaf) and the BVH4 depth in *depth_out. */
 int32_t b200pt_bvh4_collapse(const void *nodes2, uint32_t n_nodes2, int32_t root2, void *nodes4_out, uint32_t *n_nodes4_out, int32_t *depth_out);
 
+/* Opt-in tree-quality pass (B200PT_BVH_SAH=1 at SetScene time): binned-SAH rebuild of the inner nodes above the leaves of the GPU LBVH.
+ * Pure CPU code, exposed for tests and offline experiments.  nodes2 / nodes_out: n_nodes2 x 64-B BVH2 nodes (layout as in
+ * b200pt_bvh4_collapse); *n_out = leaves - 1 nodes written in depth-first order with root 0 (0 if nothing could be rebuilt);
+ * sah_before_after[2]: surface-area-heuristic cost of the input and of the output, relative to the root box. */
+int32_t b200pt_bvh2_sah_rebuild(const void *nodes2, uint32_t n_nodes2, int32_t root2, void *nodes_out, uint32_t *n_out, int32_t *depth_out, double *sah_before_after);
+
 /* ---- standalone codecs of the loader / image-output API (no GPU needed) ---- */
 /* stbi_load(.., STBI_rgb_alpha) / stbi_loadf semantics (AssetImporterImpl.cpp:494-545); free with b200pt_free */
 int32_t b200pt_decode_image_file(const char *path, uint32_t *width, uint32_t *height, uint8_t **rgba_out);

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round-2 measurement of the opt-in tree-quality pass (B200PT_BVH_SAH=1): run under gpurun on ONE GPU, e.g.
+#   gpurun --timeout 900 -- 'bash profiles/next_round_sah.sh'
+# Model forecast (tools/bvh_lab.py, profiles/r01_bvh_lab_*.json): node visits per ray -26..-33 % on BreakfastRoom, -41..-44 % on viking_room.
+set -u
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "sah_rebuild" --runxfail 2>&1 | tail -5 > gpurun_out/sah_parity.txt
+for wl in breakfast_1080p_d8 viking_1080sq_d8; do
+  for sah in 0 1; do
+    B200PT_BVH_SAH=$sah timeout 200 python bench.py --workload $wl --steps 10 --warmup 3 2> gpurun_out/sah_${wl}_${sah}.err | tail -1 > gpurun_out/sah_${wl}_${sah}.json
+  done
+done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/sah_*_?.json")):
+    try: r = json.loads(open(f).read()); print(f, r["value"], r["unit"], r["roofline"]["frac"])
+    except Exception as e: print(f, "unreadable", e)
+PY

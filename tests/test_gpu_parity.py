@@ -480,3 +480,27 @@ def test_volume_api_and_traversal_shapes(pt, monkeypatch):
     assert T.L.b200pt_add_density_data_to_volume(T.h, 0, b"smoke.vdb") == P.ERR_NOT_IMPLEMENTED
     for _ in range(P.MAX_VOLUMES): T.add_volume(**vol)
     with pytest.raises(P.B200ptError): T.add_volume(**vol)
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="opt-in pass added after round 1's GPU budget was spent: the host rebuild is unit-tested on the CPU "
+                                        "(test_host_api.py), the end-to-end render has not run on a B200 yet")
+@pytest.mark.parametrize("name,depth", [("viking_room", 8), ("breakfast_room", 8)])
+def test_opt_in_sah_rebuild_returns_the_same_image(pt, name, depth, monkeypatch):
+    """B200PT_BVH_SAH=1 (csrc/lbvh.cu: lbvh_refine_sah) only re-arranges the inner nodes above the LBVH's leaves: every ray finds the same
+    closest triangle, so work counters are identical and the image differs at most where two triangles tie at exactly the same distance
+    (the first one met wins, and the two trees meet them in a different order)."""
+    W, H, frames = 160, 120, 3
+    out = {}
+    for sah in ("0", "1"):
+        for wide in ("0", "1"):
+            monkeypatch.setenv("B200PT_BVH_SAH", sah); monkeypatch.setenv("B200PT_TRAV", "dyn"); monkeypatch.setenv("B200PT_WIDE", wide)
+            T = util.product_tracer(name, W, H, MaxDepth=depth)
+            T.path_trace(frames, util.BASE_SEED)
+            c = T.counters()
+            out[sah, wide] = (T.get_hdr().copy(), {k: c[k] for k in ("paths", "extend_rays", "surface_hits", "misses")})
+    ref_img, ref_c = out["0", "0"]
+    for k, (img, c) in out.items():
+        same = np.all(img.view(np.uint32) == ref_img.view(np.uint32), axis=-1).mean()
+        assert same >= 0.999 and util.rel_l2(img[..., :3], ref_img[..., :3]) < 2e-3, (k, same)
+        assert abs(c["surface_hits"] - ref_c["surface_hits"]) <= 1e-4 * ref_c["surface_hits"] and c["paths"] == ref_c["paths"], (k, c, ref_c)

@@ -262,6 +262,70 @@ def test_bvh4_collapse_rejects_bad_arguments_and_leaf_root():
     assert len(B.bvh4_collapse(cyc, 0)[0]) == 0
 
 
+def _bvh2_leaf_sets(nodes, root=0):
+    """node index -> (set of leaf refs beneath child0, child1), plus every child box; iterative post-order."""
+    under = {}
+    order, stack = [], [root]
+    while stack:
+        n = stack.pop(); order.append(n)
+        for c in (int(nodes[n]["c0"]), int(nodes[n]["c1"])):
+            if c >= 0: stack.append(c)
+    for n in reversed(order):
+        sides = []
+        for c in (int(nodes[n]["c0"]), int(nodes[n]["c1"])):
+            sides.append({c} if c < 0 else under[c][0] | under[c][1])
+        under[n] = sides
+    return under, order
+
+
+@pytest.mark.parametrize("n_leaves,chain", [(2, False), (3, False), (64, False), (3000, False), (60, True)])
+def test_bvh2_sah_rebuild_keeps_leaves_and_tightens_the_tree(n_leaves, chain):
+    """Opt-in tree-quality pass (lbvh.cu: bvh2_sah_rebuild_host): same leaf references with the same boxes, every child box the exact
+    union of the leaf boxes beneath it, depth-first layout with root 0, exact depth, and a surface-area cost that does not get worse
+    (random input trees: far better)."""
+    from vpt_b200 import binding as B
+    rng = np.random.default_rng(100 + n_leaves)
+    nodes2, refs = _random_bvh2(n_leaves, rng, chain)
+    leaf_box = {}
+    for n in nodes2:
+        for c, lo, hi in ((int(n["c0"]), n["lo0"], n["hi0"]), (int(n["c1"]), n["lo1"], n["hi1"])):
+            if c < 0: leaf_box[c] = (lo.copy(), hi.copy())
+    out, depth, (sah0, sah1) = B.bvh2_sah_rebuild(nodes2, 0)
+    assert len(out) == n_leaves - 1
+    under, order = _bvh2_leaf_sets(out, 0)
+    assert sorted(order) == list(range(len(out)))                               # every node reachable exactly once
+    assert sorted(under[0][0] | under[0][1]) == sorted(refs) and not (under[0][0] & under[0][1])
+    dep = {0: 1}
+    for n in order:                                                             # pre-order: parents before children
+        for k, c in enumerate((int(out[n]["c0"]), int(out[n]["c1"]))):
+            lo, hi = (out[n]["lo1"], out[n]["hi1"]) if k else (out[n]["lo0"], out[n]["hi0"])
+            boxes = [leaf_box[r] for r in under[n][k]]
+            assert np.array_equal(lo, np.min([b[0] for b in boxes], axis=0)) and np.array_equal(hi, np.max([b[1] for b in boxes], axis=0))
+            if c >= 0:
+                assert c > n                                                    # children come later in the array
+                dep[c] = dep[n] + 1
+        if int(out[n]["c0"]) >= 0: assert int(out[n]["c0"]) == n + 1            # depth-first: the left child follows its parent
+    assert depth == max(dep.values())
+    assert sah1 <= sah0 * (1.0 + 1e-6)
+    if n_leaves >= 64: assert sah1 < 0.6 * sah0 and depth <= 4 * int(np.ceil(np.log2(n_leaves)))
+    # idempotent in cost: rebuilding the rebuilt tree does not change its cost
+    out2, depth2, (s0, s1) = B.bvh2_sah_rebuild(out, 0)
+    assert abs(s0 - sah1) <= 1e-9 * max(1.0, sah1) and s1 <= s0 * (1.0 + 1e-6)
+
+
+def test_bvh2_sah_rebuild_rejects_bad_input():
+    from vpt_b200 import binding as B
+    rng = np.random.default_rng(2)
+    nodes2, _ = _random_bvh2(5, rng)
+    assert len(B.bvh2_sah_rebuild(nodes2, -3)[0]) == 0                            # leaf root
+    with pytest.raises(B.B200ptError):
+        B.bvh2_sah_rebuild(nodes2, 77)
+    bad = nodes2.copy(); bad[0]["c1"] = 1000
+    assert len(B.bvh2_sah_rebuild(bad, 0)[0]) == 0
+    cyc = nodes2.copy(); cyc[1]["c0"] = 0
+    assert len(B.bvh2_sah_rebuild(cyc, 0)[0]) == 0
+
+
 def test_volume_struct_and_defaults_without_gpu():
     """b200pt_volume mirrors PathTracer::Volume (PT/PathTracer.h:36-70): layout and defaults are checked on the CPU."""
     import ctypes as C

@@ -143,6 +143,7 @@ def lib():
             "b200pt_write_png": [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p],
             "b200pt_build_env_alias": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_float)],
             "b200pt_bvh4_collapse": [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)],
+            "b200pt_bvh2_sah_rebuild": [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_void_p],
             "b200pt_load_gltf": [C.c_char_p, C.POINTER(C.POINTER(SceneDesc))], "b200pt_free_scene": [C.POINTER(SceneDesc)],
         }
         for name, args in sig.items():
@@ -217,6 +218,16 @@ def bvh4_collapse(nodes2, root2=0):
     r = lib().b200pt_bvh4_collapse(_p(nodes2), len(nodes2), int(root2), _p(out), C.byref(n4), C.byref(d))
     if r != OK: raise B200ptError(r, "bvh4_collapse")
     return out[:n4.value].copy(), d.value
+
+
+def bvh2_sah_rebuild(nodes2, root2=0):
+    """Opt-in binned-SAH rebuild of the inner nodes (csrc/lbvh.cu: bvh2_sah_rebuild_host).  Returns (BVH2_DTYPE array, depth, (sah_before, sah_after))."""
+    nodes2 = np.ascontiguousarray(nodes2, BVH2_DTYPE)
+    out = np.zeros(len(nodes2), BVH2_DTYPE)
+    n, d = C.c_uint32(), C.c_int32(); sah = np.zeros(2, np.float64)
+    r = lib().b200pt_bvh2_sah_rebuild(_p(nodes2), len(nodes2), int(root2), _p(out), C.byref(n), C.byref(d), _p(sah))
+    if r != OK: raise B200ptError(r, "bvh2_sah_rebuild")
+    return out[:n.value].copy(), d.value, (float(sah[0]), float(sah[1]))
 
 
 def build_env_alias(rgba):

@@ -230,6 +230,16 @@ int32_t b200pt_bvh4_collapse(const void *nodes2, uint32_t n_nodes2, int32_t root
     if (depth_out) *depth_out = d;
     return B200PT_OK;
 }
+int32_t b200pt_bvh2_sah_rebuild(const void *nodes2, uint32_t n_nodes2, int32_t root2, void *out, uint32_t *n_out, int32_t *depth_out, double *sah) {
+    if (!nodes2 || !out || !n_out || !n_nodes2) return B200PT_ERR_WRONG_ARGUMENTS;
+    if (root2 >= 0 && (uint32_t)root2 >= n_nodes2) return B200PT_ERR_WRONG_ARGUMENTS;
+    int d = 0; double c[2] = { 0.0, 0.0 };
+    try { *n_out = b200pt::bvh2_sah_rebuild_host(static_cast<const b200pt::BvhNode *>(nodes2), n_nodes2, root2, static_cast<b200pt::BvhNode *>(out), &d, c); }
+    catch (...) { return B200PT_ERR_OUT_OF_MEMORY; }
+    if (depth_out) *depth_out = d;
+    if (sah) { sah[0] = c[0]; sah[1] = c[1]; }
+    return B200PT_OK;
+}
 int32_t b200pt_build_env_alias(float *rgba, uint32_t w, uint32_t hh, void *alias, float *sum) {
     if (!rgba || !w || !hh || !alias) return B200PT_ERR_WRONG_ARGUMENTS;
     float s = build_env_alias(rgba, w, hh, (uint2 *)alias); if (sum) *sum = s; return B200PT_OK;

@@ -45,6 +45,10 @@ void lbvh_free(LbvhResult *r);
 // BVH2 -> BVH4 on the host (pure CPU code, unit-tested without a GPU through b200pt_bvh4_collapse).  `out` must hold n_nodes2 entries.
 // Returns the number of BVH4 nodes written (0 if the root is a leaf), *depth4 = depth of the BVH4 (root = 1).
 uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, Bvh4Node *out, int *depth4);
+// Opt-in binned-SAH rebuild of the inner nodes above the LBVH's leaves (pure CPU code, unit-tested through b200pt_bvh2_sah_rebuild).
+// `out` must hold n_nodes2 entries; returns the node count (0 = nothing rebuilt), *depth, sah[0/1] = SAH cost before / after.
+uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, BvhNode *out, int *depth, double sah[2]);
+int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2]);    // download, rebuild, upload in place (cudaError_t as int)
 // Downloads r->nodes, collapses, uploads r->nodes4 (own allocation).  Returns cudaError_t as int; leaves nodes4 = nullptr if the root is a leaf.
 int lbvh_build_wide(LbvhResult *r, cudaStream_t st);
 

@@ -10,6 +10,7 @@
 //   [ BvhNode x max(N-1,1) | BvhTri x N ]   nodes: 64 B, both child boxes in the parent; tris: 48 B, Morton order.
 #include "kernels.h"
 #include <vector>
+#include <algorithm>
 #include <cstdio>
 
 namespace b200pt {
@@ -395,6 +396,106 @@ uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t ro
     return (uint32_t)queue.size();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Binned-SAH rebuild of the BVH2 topology above the LBVH's leaves (host, OPT-IN: B200PT_BVH_SAH=1, see Engine::upload_scene).
+// the traversal kernels are bound by the number of node / triangle visits of the Morton-order tree, not by their
+// loop shape.  The leaves (<= 4 consecutive references each, with the padded boxes the LBVH stored for them) are kept as they are; only the
+// inner nodes are rebuilt top-down with a 16-bin surface-area heuristic over the leaf-box centroids (cost = area x references on each
+// side, all three axes tried, median split of the longest axis when the bins cannot separate the leaves).  Child boxes are exact unions
+// of leaf boxes, so the result is as conservative as the input and returns identical hits.  Output: nodes in depth-first order, root = 0.
+// Returns the node count (leaves - 1; 0 if the root is a leaf or the input is not a tree), *depth = new depth, sah[0/1] = SAH cost before / after.
+// ------------------------------------------------------------------------------------------------
+uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, BvhNode *out, int *depth, double sah[2]) {
+    if (depth) *depth = 0;
+    if (sah) sah[0] = sah[1] = 0.0;
+    if (root2 < 0 || n_nodes2 == 0 || (uint32_t)root2 >= n_nodes2) return 0;
+    struct Leaf { int32_t ref; float lo[3], hi[3], c[3]; uint32_t count; };
+    std::vector<Leaf> leaves; leaves.reserve(n_nodes2 + 1);
+    auto area = [](const float lo[3], const float hi[3]) { const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2]; return 2.0 * (dx * dy + dy * dz + dz * dx); };
+    double cost_in = 0.0;
+    {   // collect the leaves (and the SAH cost of the input tree, relative to the root box)
+        std::vector<int32_t> stack{ root2 }; size_t visited = 0;
+        while (!stack.empty()) {
+            const int32_t n = stack.back(); stack.pop_back();
+            if ((uint32_t)n >= n_nodes2 || ++visited > (size_t)n_nodes2) return 0;             // not a tree
+            const BvhNode &N = nodes2[n];
+            for (int k = 0; k < 2; k++) {
+                const int32_t c = k ? N.c1 : N.c0; const float *lo = k ? N.lo1 : N.lo0, *hi = k ? N.hi1 : N.hi0;
+                if (c >= 0) { cost_in += area(lo, hi); stack.push_back(c); }
+                else {
+                    Leaf L; L.ref = c; L.count = ((uint32_t)(~c) & 3u) + 1u;
+                    for (int a = 0; a < 3; a++) { L.lo[a] = lo[a]; L.hi[a] = hi[a]; L.c[a] = 0.5f * (lo[a] + hi[a]); }
+                    cost_in += area(lo, hi) * L.count;
+                    leaves.push_back(L);
+                }
+            }
+        }
+    }
+    const uint32_t nl = (uint32_t)leaves.size();
+    if (nl < 2 || nl - 1 > n_nodes2) return 0;
+    auto bounds = [&](uint32_t b, uint32_t e, float lo[3], float hi[3]) {
+        for (int a = 0; a < 3; a++) { lo[a] = 3.0e38f; hi[a] = -3.0e38f; }
+        for (uint32_t i = b; i < e; i++) for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], leaves[i].lo[a]); hi[a] = fmaxf(hi[a], leaves[i].hi[a]); }
+    };
+    struct Task { uint32_t b, e; int32_t node; int side; int dep; };       // leaves [b, e) become child `side` of `node` (-1: the root)
+    std::vector<Task> tasks{ { 0, nl, -1, 0, 1 } };
+    uint32_t n_out = 0; int max_d = 1; double cost_out = 0.0;
+    constexpr int NB = 16;
+    while (!tasks.empty()) {
+        const Task t = tasks.back(); tasks.pop_back();
+        // split [b, e)
+        float clo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, chi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
+        for (uint32_t i = t.b; i < t.e; i++) for (int a = 0; a < 3; a++) { clo[a] = fminf(clo[a], leaves[i].c[a]); chi[a] = fmaxf(chi[a], leaves[i].c[a]); }
+        int best_axis = -1, best_bin = -1; double best_cost = 1e300;
+        for (int a = 0; a < 3; a++) {
+            const float ext = chi[a] - clo[a];
+            if (!(ext > 0.0f)) continue;
+            float blo[NB][3], bhi[NB][3]; uint32_t bcnt[NB];
+            for (int k = 0; k < NB; k++) { bcnt[k] = 0; for (int q = 0; q < 3; q++) { blo[k][q] = 3.0e38f; bhi[k][q] = -3.0e38f; } }
+            const float scale = (float)NB / ext;
+            for (uint32_t i = t.b; i < t.e; i++) {
+                int k = (int)((leaves[i].c[a] - clo[a]) * scale); if (k >= NB) k = NB - 1; if (k < 0) k = 0;
+                bcnt[k] += leaves[i].count;
+                for (int q = 0; q < 3; q++) { blo[k][q] = fminf(blo[k][q], leaves[i].lo[q]); bhi[k][q] = fmaxf(bhi[k][q], leaves[i].hi[q]); }
+            }
+            double rarea[NB]; uint32_t rcnt[NB];
+            { float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f }; uint32_t c = 0;
+              for (int k = NB - 1; k >= 1; k--) { if (bcnt[k]) for (int q = 0; q < 3; q++) { lo[q] = fminf(lo[q], blo[k][q]); hi[q] = fmaxf(hi[q], bhi[k][q]); } c += bcnt[k]; rcnt[k] = c; rarea[k] = c ? area(lo, hi) : 0.0; } }
+            float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f }; uint32_t c = 0;
+            for (int k = 0; k < NB - 1; k++) {                              // split between bin k and k + 1
+                if (bcnt[k]) for (int q = 0; q < 3; q++) { lo[q] = fminf(lo[q], blo[k][q]); hi[q] = fmaxf(hi[q], bhi[k][q]); }
+                c += bcnt[k];
+                if (!c || !rcnt[k + 1]) continue;
+                const double cost = area(lo, hi) * c + rarea[k + 1] * rcnt[k + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
+            }
+        }
+        uint32_t mid;
+        if (best_axis >= 0) {
+            const float ext = chi[best_axis] - clo[best_axis], scale = (float)NB / ext;
+            auto bin_of = [&](const Leaf &L) { int k = (int)((L.c[best_axis] - clo[best_axis]) * scale); if (k >= NB) k = NB - 1; if (k < 0) k = 0; return k; };
+            mid = (uint32_t)(std::partition(leaves.begin() + t.b, leaves.begin() + t.e, [&](const Leaf &L) { return bin_of(L) <= best_bin; }) - leaves.begin());
+        } else mid = t.b;
+        if (mid == t.b || mid == t.e) {                                     // identical centroids: median split in index order
+            mid = t.b + (t.e - t.b) / 2;
+        }
+        const uint32_t me = n_out++;
+        if (me >= n_nodes2) return 0;
+        BvhNode &N = out[me]; N._pad[0] = N._pad[1] = 0;
+        bounds(t.b, mid, N.lo0, N.hi0); bounds(mid, t.e, N.lo1, N.hi1);
+        if (t.node >= 0) { if (t.side) out[t.node].c1 = (int32_t)me; else out[t.node].c0 = (int32_t)me; }
+        if (t.dep > max_d) max_d = t.dep;
+        if (mid - t.b == 1) { N.c0 = leaves[t.b].ref; cost_out += area(N.lo0, N.hi0) * leaves[t.b].count; } else { cost_out += area(N.lo0, N.hi0); }
+        if (t.e - mid == 1) { N.c1 = leaves[mid].ref; cost_out += area(N.lo1, N.hi1) * leaves[mid].count; } else { cost_out += area(N.lo1, N.hi1); }
+        // right first so that the left subtree is emitted right after its parent (depth-first layout)
+        if (t.e - mid > 1) tasks.push_back({ mid, t.e, (int32_t)me, 1, t.dep + 1 });
+        if (mid - t.b > 1) tasks.push_back({ t.b, mid, (int32_t)me, 0, t.dep + 1 });
+    }
+    if (depth) *depth = max_d;
+    if (sah) { float lo[3], hi[3]; bounds(0, nl, lo, hi); const double ra = area(lo, hi); sah[0] = ra > 0 ? cost_in / ra : 0.0; sah[1] = ra > 0 ? cost_out / ra : 0.0; }
+    return n_out;
+}
+
 int lbvh_build_wide(LbvhResult *r, cudaStream_t st) {
     r->nodes4 = nullptr; r->n_nodes4 = 0; r->depth4 = 0;
     if (!r->nodes || r->root < 0 || r->n_nodes == 0) return 0;
@@ -409,6 +510,23 @@ int lbvh_build_wide(LbvhResult *r, cudaStream_t st) {
     LBVH_CHECK(cudaMemcpyAsync(r->nodes4, h4.data(), (size_t)n4 * sizeof(Bvh4Node), cudaMemcpyHostToDevice, st));
     LBVH_CHECK(cudaStreamSynchronize(st));
     r->n_nodes4 = n4; r->depth4 = d4;
+    return 0;
+}
+
+// Opt-in (B200PT_BVH_SAH=1): rebuild the inner nodes in place with bvh2_sah_rebuild_host.  The live node count is unchanged (leaves - 1),
+// so the rebuilt array fits the existing allocation; root becomes 0 and max_depth the new depth.  A no-op for one-leaf scenes.
+int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2]) {
+    if (sah) sah[0] = sah[1] = 0.0;
+    if (!r->nodes || r->root < 0 || r->n_nodes == 0) return 0;
+    std::vector<BvhNode> h2(r->n_nodes), out(r->n_nodes);
+    LBVH_CHECK(cudaMemcpyAsync(h2.data(), r->nodes, (size_t)r->n_nodes * sizeof(BvhNode), cudaMemcpyDeviceToHost, st));
+    LBVH_CHECK(cudaStreamSynchronize(st));
+    int depth = 0;
+    const uint32_t n = bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, out.data(), &depth, sah);
+    if (n == 0) return 0;
+    LBVH_CHECK(cudaMemcpyAsync(r->nodes, out.data(), (size_t)n * sizeof(BvhNode), cudaMemcpyHostToDevice, st));
+    LBVH_CHECK(cudaStreamSynchronize(st));
+    r->root = 0; r->max_depth = depth;
     return 0;
 }
 
