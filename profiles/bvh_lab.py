@@ -8,7 +8,7 @@ agree with the GPU build to within the rounding of the keys; treat the visit cou
 bvh_traverse.cuh: pop a node, slab-test both child boxes against [0, t_closest], descend into the nearer child first, test a leaf's
 triangles when it is reached.  Rays: camera rays of the scene's own camera plus one cosine-distributed bounce ray from every hit.
 
-usage: python tools/bvh_lab.py tests/golden/breakfast_room.npz [--rays 20000] [--out profiles/r01_bvh_lab_breakfast.json]
+usage: python profiles/bvh_lab.py tests/golden/breakfast_room.npz [--rays 20000] [--out profiles/r01_bvh_lab_breakfast.json]
 """
 import argparse
 import json
@@ -19,18 +19,29 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import gltf_ref, orc                                        # noqa: E402  (scene fixtures + camera maths only)
-from vpt_b200 import binding as B                                        # noqa: E402
+from vpt_b200 import binding as B                                        # noqa: E402  (host-only entry points: no GPU needed)
 
 LEAF_MAX, SPLIT_MAX = 4, 16
 
 
+def load_fixture(path):
+    """tests/golden/*.npz scene fixture (flat arrays, see tests/golden/make_golden.py) or any file the product's loader reads."""
+    if path.endswith(".npz"):
+        z = np.load(path, allow_pickle=False)
+        meshes = [(np.asarray(z[f"mesh{i}_v"], np.float32)[:, :3], np.asarray(z[f"mesh{i}_i"])) for i in range(int(z["n_meshes"]))]
+        inst = [(z["inst_xf"][i], int(z["inst_mesh"][i])) for i in range(len(z["inst_mesh"]))]
+        return dict(meshes=meshes, instances=inst, camera_view=np.asarray(z["camera_view"], np.float32), aspect=float(z["aspect"]))
+    sc = B.load_gltf(path)                                               # the product's own C++ loader
+    meshes = [(np.ascontiguousarray(v["pos"], np.float32), np.asarray(i)) for v, i in sc["meshes"]]
+    return dict(meshes=meshes, instances=[(x, m) for x, m, _ in sc["instances"]], camera_view=sc["camera_view"], aspect=float(sc["aspect"]))
+
+
 def world_triangles(sc):
     out = []
-    for xf, mi, _ in sc["instances"]:
-        v, idx = sc["meshes"][mi]
+    for xf, mi in sc["instances"]:
+        P0, idx = sc["meshes"][mi]
         M = np.asarray(xf, np.float32).reshape(4, 4).T                   # column-major 4x4
-        P = v["pos"].astype(np.float32) @ M[:3, :3].T + M[:3, 3]
+        P = P0 @ M[:3, :3].T + M[:3, 3]
         out.append(P[idx.reshape(-1, 3)])
     return np.concatenate(out).astype(np.float32)                        # [T, 3, 3]
 
@@ -198,7 +209,7 @@ def traverse(nodes, tris, O, D, tmax=None):
 
 
 def make_rays(sc, n_rays, rng):
-    vi, pi = orc.camera_from_view(sc["camera_view"], sc["aspect"])
+    vi, pi = B.camera_from_view(sc["camera_view"], sc["aspect"])
     vi = np.asarray(vi, np.float64).reshape(4, 4).T; pi = np.asarray(pi, np.float64).reshape(4, 4).T
     uv = rng.random((n_rays, 2)) * 2 - 1
     tgt = (pi @ np.concatenate([uv, np.ones((n_rays, 1)), np.ones((n_rays, 1))], 1).T).T
@@ -224,7 +235,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("scene"); ap.add_argument("--rays", type=int, default=20000); ap.add_argument("--out", default=None); ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args()
-    sc = gltf_ref.load_scene_npz(a.scene) if a.scene.endswith(".npz") else gltf_ref.load_scene(a.scene)
+    sc = load_fixture(a.scene)
     rng = np.random.default_rng(a.seed)
     tri = world_triangles(sc)
     t0 = time.time()

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Is the DEVICE code of the working tree byte-identical to a given commit's?  (Used when host code changes without a GPU at hand: the GPU
-# test results of <commit> then still describe the device code of the working tree.)   usage: tools/sass_identity.sh <commit>
+# test results of <commit> then still describe the device code of the working tree.)   usage: profiles/sass_identity.sh <commit>
 set -eu
 ref=${1:?commit}
 root=$(cd "$(dirname "$0")/.." && pwd)
