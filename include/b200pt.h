@@ -233,6 +233,11 @@ int32_t b200pt_bvh4_collapse(const void *nodes2, uint32_t n_nodes2, int32_t root
  * sah_before_after[2]: surface-area-heuristic cost of the input and of the output, relative to the root box. */
 int32_t b200pt_bvh2_sah_rebuild(const void *nodes2, uint32_t n_nodes2, int32_t root2, void *nodes_out, uint32_t *n_out, int32_t *depth_out, double *sah_before_after);
 
+/* Second opt-in level (B200PT_BVH_SAH=2): binned-SAH build from the per-slot reference boxes; leaves of <= 4 references are re-formed.
+ * ref_boxes: n x 6 floats (lo xyz, hi xyz); nodes_out: room for n - 1 nodes; perm_out[new slot] = old slot; trav_cost = price of a node
+ * visit in triangle tests (1.0 = classic SAH).  *n_out = 0 when n <= 4 (one leaf) or a box is inverted / NaN. */
+int32_t b200pt_bvh2_sah_build(const float *ref_boxes, uint32_t n, float trav_cost, void *nodes_out, uint32_t *perm_out, uint32_t *n_out, int32_t *depth_out, double *sah_cost);
+
 /* ---- standalone codecs of the loader / image-output API (no GPU needed) ---- */
 /* stbi_load(.., STBI_rgb_alpha) / stbi_loadf semantics (AssetImporterImpl.cpp:494-545); free with b200pt_free */
 int32_t b200pt_decode_image_file(const char *path, uint32_t *width, uint32_t *height, uint8_t **rgba_out);

@@ -233,7 +233,8 @@ def stats(name, n_vis, t_tests):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("scene"); ap.add_argument("--rays", type=int, default=20000); ap.add_argument("--out", default=None); ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("scene"); ap.add_argument("--rays", type=int, default=20000); ap.add_argument("--out", default=None); ap.add_argument("--seed", type=int, default=1); ap.add_argument("--table", action="store_true")
+    ap.add_argument("--trav-cost", type=float, nargs="*", default=[1.0], help="node-visit price(s) for the full SAH build (mode 2)")
     a = ap.parse_args()
     sc = load_fixture(a.scene)
     rng = np.random.default_rng(a.seed)
@@ -252,15 +253,30 @@ def main():
     res = {"scene": os.path.basename(a.scene), "triangles": int(len(tri)), "references": int(len(rb)), "lbvh_nodes": int(len(lb)), "lbvh_depth": tree_depth(lb),
            "sah_nodes": int(len(sah)), "sah_depth": int(depth_sah), "sah_cost_lbvh": c0, "sah_cost_rebuilt": c1,
            "host_seconds": {"numpy_lbvh_mirror": round(t_lbvh, 2), "sah_rebuild_cxx": round(t_sah, 3)}, "rays": []}
+    trees = [("lbvh", lb, rtris), ("sah_inner", sah, rtris)]
+    for tc in a.trav_cost:
+        t0 = time.time()
+        full, perm, d_full, c_full = B.bvh2_sah_build(rb.reshape(-1, 6), tc)
+        res[f"sah_full_tc{tc:g}"] = {"nodes": int(len(full)), "depth": int(d_full), "sah_cost": c_full, "host_seconds": round(time.time() - t0, 3)}
+        trees.append((f"sah_full_tc{tc:g}", full, rtris[perm]))
     O, D = make_rays(sc, a.rays, rng)
-    tA, nA, kA = traverse(lb, rtris, O, D); tB, nB, kB = traverse(sah, rtris, O, D)
-    assert np.array_equal(np.isfinite(tA), np.isfinite(tB)) and np.allclose(tA[np.isfinite(tA)], tB[np.isfinite(tB)], rtol=1e-9, atol=1e-12), "the two trees must return identical hits"
-    res["rays"] += [dict(stats("camera", nA, kA), tree="lbvh"), dict(stats("camera", nB, kB), tree="sah")]
-    O2, D2 = bounce_rays(O, D, tA, rng)
-    tA2, nA2, kA2 = traverse(lb, rtris, O2, D2); tB2, nB2, kB2 = traverse(sah, rtris, O2, D2)
-    assert np.array_equal(np.isfinite(tA2), np.isfinite(tB2)) and np.allclose(tA2[np.isfinite(tA2)], tB2[np.isfinite(tB2)], rtol=1e-9, atol=1e-12)
-    res["rays"] += [dict(stats("bounce", nA2, kA2), tree="lbvh"), dict(stats("bounce", nB2, kB2), tree="sah")]
-    print(json.dumps(res, indent=1))
+    base = None
+    for name, nodes, tt in trees:
+        t, nv, kt = traverse(nodes, tt, O, D)
+        if base is None: base = t
+        assert np.array_equal(np.isfinite(t), np.isfinite(base)) and np.allclose(t[np.isfinite(t)], base[np.isfinite(base)], rtol=1e-9, atol=1e-12), "all trees must return identical hits"
+        res["rays"].append(dict(stats("camera", nv, kt), tree=name))
+    O2, D2 = bounce_rays(O, D, base, rng)
+    base2 = None
+    for name, nodes, tt in trees:
+        t, nv, kt = traverse(nodes, tt, O2, D2)
+        if base2 is None: base2 = t
+        assert np.array_equal(np.isfinite(t), np.isfinite(base2)) and np.allclose(t[np.isfinite(t)], base2[np.isfinite(base2)], rtol=1e-9, atol=1e-12)
+        res["rays"].append(dict(stats("bounce", nv, kt), tree=name))
+    if a.table:
+        for r in res["rays"]: print(f'{r["set"]:7s} {r["tree"]:18s} nodes {r["nodes_mean"]:6.2f} (p99 {r["nodes_p99"]:5.0f})  tris {r["tris_mean"]:5.2f} (p99 {r["tris_p99"]:4.0f})')
+    else:
+        print(json.dumps(res, indent=1))
     if a.out:
         with open(a.out, "w") as f: json.dump(res, f, indent=1)
 

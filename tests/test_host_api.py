@@ -326,6 +326,75 @@ def test_bvh2_sah_rebuild_rejects_bad_input():
     assert len(B.bvh2_sah_rebuild(cyc, 0)[0]) == 0
 
 
+@pytest.mark.parametrize("n,tc", [(5, 1.0), (6, 1.0), (257, 1.0), (5000, 1.0), (5000, 3.0)])
+def test_bvh2_sah_build_from_reference_boxes(n, tc):
+    """Second opt-in level (lbvh.cu: bvh2_sah_build_host): perm is a permutation, the leaves tile [0, n) with <= 4 slots each, child boxes
+    contain the padded union of the reference boxes beneath them, layout is depth-first, and a ray walk through the tree finds the
+    same closest hits as brute force over all triangles."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(util.ROOT, "profiles"))
+    import bvh_lab
+    from vpt_b200 import binding as B
+    rng = np.random.default_rng(n)
+    ctr = rng.random((n, 1, 3)).astype(np.float32) * 4 - 2
+    tri = (ctr + 0.15 * (rng.random((n, 3, 3)).astype(np.float32) - 0.5)).astype(np.float32)
+    rb = np.concatenate([tri.min(1), tri.max(1)], 1)
+    nodes, perm, depth, cost = B.bvh2_sah_build(rb, tc)
+    assert sorted(perm.tolist()) == list(range(n)) and 1 <= len(nodes) <= n - 1 and cost > 0
+    ext = np.abs(rb).max(); pabs = np.float32(2e-6) * ext
+    covered = np.zeros(n, np.int32); dep = {0: 1}
+    under = {}
+    for i in range(len(nodes) - 1, -1, -1):                                      # children come later: a reverse sweep is a post-order
+        sides = []
+        for k, c in enumerate((int(nodes[i]["c0"]), int(nodes[i]["c1"]))):
+            if c < 0:
+                r = ~c; first, cnt = r >> 2, (r & 3) + 1
+                assert cnt <= 4 and first + cnt <= n
+                covered[first:first + cnt] += 1
+                lo, hi = rb[perm[first:first + cnt], :3].min(0), rb[perm[first:first + cnt], 3:].max(0)
+            else:
+                assert i < c < len(nodes)
+                lo, hi = under[c]
+            blo, bhi = (nodes[i]["lo1"], nodes[i]["hi1"]) if k else (nodes[i]["lo0"], nodes[i]["hi0"])
+            pad = np.float32(4e-7) * np.maximum(np.abs(lo), np.abs(hi)) + pabs
+            assert np.all(blo <= lo - 0.5 * pad) and np.all(bhi >= hi + 0.5 * pad) and np.all(blo >= lo - 2 * pad) and np.all(bhi <= hi + 2 * pad)
+            sides.append((lo, hi))
+        under[i] = (np.minimum(sides[0][0], sides[1][0]), np.maximum(sides[0][1], sides[1][1]))
+    assert np.all(covered == 1)
+    for i in range(len(nodes)):
+        for c in (int(nodes[i]["c0"]), int(nodes[i]["c1"])):
+            if c >= 0: dep[c] = dep[i] + 1
+        if int(nodes[i]["c0"]) >= 0: assert int(nodes[i]["c0"]) == i + 1
+    assert depth == max(dep.values()) and depth <= 6 * int(np.ceil(np.log2(n))) + 2
+    # identical closest hits: tree walk vs brute force
+    R = 400
+    O = (rng.random((R, 3)) * 6 - 3); D = tri[rng.integers(0, n, R)].mean(1) + 0.02 * rng.normal(size=(R, 3)) - O    # aimed at triangles, so most rays hit
+    D /= np.linalg.norm(D, axis=1, keepdims=True)
+    t_tree, _, _ = bvh_lab.traverse(nodes, tri[perm], O, D)
+    t_brute = np.full(R, np.inf)
+    E1, E2 = (tri[:, 1] - tri[:, 0]).astype(np.float64), (tri[:, 2] - tri[:, 0]).astype(np.float64); A = tri[:, 0].astype(np.float64)
+    for r in range(R):
+        p = np.cross(D[r], E2); det = (E1 * p).sum(1); ok = np.abs(det) > 1e-30; idet = 1.0 / np.where(ok, det, 1.0)
+        sv = O[r] - A; u = (sv * p).sum(1) * idet; q = np.cross(sv, E1); v = (q * D[r]).sum(1) * idet; tt = (E2 * q).sum(1) * idet
+        hit = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (tt > 1e-6)
+        if hit.any(): t_brute[r] = tt[hit].min()
+    assert np.array_equal(np.isfinite(t_tree), np.isfinite(t_brute)) and np.allclose(t_tree[np.isfinite(t_tree)], t_brute[np.isfinite(t_brute)], rtol=1e-12)
+    assert np.isfinite(t_brute).sum() > R // 4
+
+
+def test_bvh2_sah_build_rejects_degenerate_input():
+    from vpt_b200 import binding as B
+    rb = np.zeros((4, 6), np.float32)
+    assert len(B.bvh2_sah_build(rb)[0]) == 0                                      # one leaf: the caller keeps what it has
+    rb = np.zeros((9, 6), np.float32); rb[:, 3:] = 1.0                            # identical boxes: median splits, still a valid tree
+    nodes, perm, depth, _ = B.bvh2_sah_build(rb)
+    assert len(nodes) >= 2 and sorted(perm.tolist()) == list(range(9))
+    bad = rb.copy(); bad[3, 0] = np.nan
+    assert len(B.bvh2_sah_build(bad)[0]) == 0
+    inv = rb.copy(); inv[2, 3] = -5.0
+    assert len(B.bvh2_sah_build(inv)[0]) == 0
+
+
 def test_volume_struct_and_defaults_without_gpu():
     """b200pt_volume mirrors PathTracer::Volume (PT/PathTracer.h:36-70): layout and defaults are checked on the CPU."""
     import ctypes as C

@@ -143,6 +143,7 @@ def lib():
             "b200pt_write_png": [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p],
             "b200pt_build_env_alias": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_float)],
             "b200pt_bvh4_collapse": [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)],
+            "b200pt_bvh2_sah_build": [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_double)],
             "b200pt_bvh2_sah_rebuild": [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_void_p],
             "b200pt_load_gltf": [C.c_char_p, C.POINTER(C.POINTER(SceneDesc))], "b200pt_free_scene": [C.POINTER(SceneDesc)],
         }
@@ -228,6 +229,16 @@ def bvh2_sah_rebuild(nodes2, root2=0):
     r = lib().b200pt_bvh2_sah_rebuild(_p(nodes2), len(nodes2), int(root2), _p(out), C.byref(n), C.byref(d), _p(sah))
     if r != OK: raise B200ptError(r, "bvh2_sah_rebuild")
     return out[:n.value].copy(), d.value, (float(sah[0]), float(sah[1]))
+
+
+def bvh2_sah_build(ref_boxes, trav_cost=1.0):
+    """Full binned-SAH build from reference boxes [n, 6] (csrc/lbvh.cu: bvh2_sah_build_host).  Returns (nodes, perm, depth, sah_cost)."""
+    rb = np.ascontiguousarray(ref_boxes, np.float32).reshape(-1, 6)
+    out = np.zeros(max(len(rb) - 1, 1), BVH2_DTYPE); perm = np.zeros(len(rb), np.uint32)
+    n, d, c = C.c_uint32(), C.c_int32(), C.c_double()
+    r = lib().b200pt_bvh2_sah_build(_p(rb), len(rb), C.c_float(trav_cost), _p(out), _p(perm), C.byref(n), C.byref(d), C.byref(c))
+    if r != OK: raise B200ptError(r, "bvh2_sah_build")
+    return out[:n.value].copy(), perm, d.value, c.value
 
 
 def build_env_alias(rgba):

@@ -240,6 +240,15 @@ int32_t b200pt_bvh2_sah_rebuild(const void *nodes2, uint32_t n_nodes2, int32_t r
     if (sah) { sah[0] = c[0]; sah[1] = c[1]; }
     return B200PT_OK;
 }
+int32_t b200pt_bvh2_sah_build(const float *ref_boxes, uint32_t n, float trav_cost, void *out, uint32_t *perm, uint32_t *n_out, int32_t *depth_out, double *sah_cost) {
+    if (!ref_boxes || !out || !perm || !n_out || !n || !(trav_cost >= 0.0f)) return B200PT_ERR_WRONG_ARGUMENTS;
+    int d = 0; double c = 0.0;
+    try { *n_out = b200pt::bvh2_sah_build_host(ref_boxes, n, trav_cost, static_cast<b200pt::BvhNode *>(out), perm, &d, &c); }
+    catch (...) { return B200PT_ERR_OUT_OF_MEMORY; }
+    if (depth_out) *depth_out = d;
+    if (sah_cost) *sah_cost = c;
+    return B200PT_OK;
+}
 int32_t b200pt_build_env_alias(float *rgba, uint32_t w, uint32_t hh, void *alias, float *sum) {
     if (!rgba || !w || !hh || !alias) return B200PT_ERR_WRONG_ARGUMENTS;
     float s = build_env_alias(rgba, w, hh, (uint2 *)alias); if (sum) *sum = s; return B200PT_OK;

@@ -122,13 +122,15 @@ void Engine::upload_scene() {
     }
     CK(cudaMalloc(&d_textures_, dt.size() * sizeof(DevTexture))); CK(cudaMemcpy(d_textures_, dt.data(), dt.size() * sizeof(DevTexture), cudaMemcpyHostToDevice));
     // acceleration structure: GPU LBVH over the flattened instances
-    int r = lbvh_build(d_verts_, d_indices_, d_meshes_, d_instances_, h_instances_.data(), h_meshes_.data(), (uint32_t)h_instances_.size(), n_tris_, &bvh_, stream_);
+    int sah_mode = 0;                                                       // opt-in tree-quality pass; same hits, fewer node visits
+    if (const char *e = getenv("B200PT_BVH_SAH")) sah_mode = e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0);
+    int r = lbvh_build(d_verts_, d_indices_, d_meshes_, d_instances_, h_instances_.data(), h_meshes_.data(), (uint32_t)h_instances_.size(), n_tris_, &bvh_, stream_, sah_mode == 2);
     if (r != 0) throw CudaError{ B200PT_ERR_CUDA, std::string("lbvh_build failed: ") + cudaGetErrorString((cudaError_t)r) };
-    if (const char *e = getenv("B200PT_BVH_SAH"); e && e[0] == '1') {      // opt-in tree-quality pass; same hits, fewer node visits
+    if (sah_mode) {
         double sah[2];
-        r = lbvh_refine_sah(&bvh_, stream_, sah);
+        r = lbvh_refine_sah(&bvh_, stream_, sah, sah_mode);
         if (r != 0) throw CudaError{ B200PT_ERR_CUDA, std::string("lbvh_refine_sah failed: ") + cudaGetErrorString((cudaError_t)r) };
-        if (getenv("B200PT_DEBUG")) fprintf(stderr, "[b200pt] SAH rebuild of the inner nodes: cost %.3f -> %.3f, depth %d\n", sah[0], sah[1], bvh_.max_depth);
+        if (getenv("B200PT_DEBUG")) fprintf(stderr, "[b200pt] SAH pass (mode %d): cost %.3f -> %.3f, depth %d\n", sah_mode, sah[0], sah[1], bvh_.max_depth);
     }
     ds_.verts = d_verts_; ds_.indices = d_indices_; ds_.meshes = d_meshes_; ds_.instances = d_instances_; ds_.materials = d_materials_;
     ds_.textures = d_textures_; ds_.emissive = d_emissive_; ds_.nodes = bvh_.nodes; ds_.tris = bvh_.tris; ds_.shade_tris = bvh_.shade; ds_.tri_slot = bvh_.tri_slot;

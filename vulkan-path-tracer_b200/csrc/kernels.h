@@ -36,11 +36,12 @@ void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, cons
 
 // ---- LBVH build (lbvh.cu): world-space flattening of the two-level TLAS/BLAS ----
 struct LbvhResult { ShadeTri *shade; uint32_t *tri_slot; BvhNode *nodes; BvhTri *tris; uint32_t n_nodes, n_tris; int32_t root; int max_depth; size_t bytes;
-                    Bvh4Node *nodes4; uint32_t n_nodes4; int depth4; };
+                    Bvh4Node *nodes4; uint32_t n_nodes4; int depth4;
+                    float *h_ref_box; uint32_t n_prims; };                 // host copy of the per-slot reference boxes (only when asked for), triangle count
 // Builds into ONE contiguous allocation [nodes | tris] (so small scenes can be staged to smem with one bulk copy).
 // Returns cudaError_t as int.
 int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const DevMesh *d_meshes, const DevInstance *d_instances,
-               const DevInstance *h_instances, const DevMesh *h_meshes, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st);
+               const DevInstance *h_instances, const DevMesh *h_meshes, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st, bool keep_ref_boxes = false);
 void lbvh_free(LbvhResult *r);
 // BVH2 -> BVH4 on the host (pure CPU code, unit-tested without a GPU through b200pt_bvh4_collapse).  `out` must hold n_nodes2 entries.
 // Returns the number of BVH4 nodes written (0 if the root is a leaf), *depth4 = depth of the BVH4 (root = 1).
@@ -48,7 +49,11 @@ uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t ro
 // Opt-in binned-SAH rebuild of the inner nodes above the LBVH's leaves (pure CPU code, unit-tested through b200pt_bvh2_sah_rebuild).
 // `out` must hold n_nodes2 entries; returns the node count (0 = nothing rebuilt), *depth, sah[0/1] = SAH cost before / after.
 uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, BvhNode *out, int *depth, double sah[2]);
-int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2]);    // download, rebuild, upload in place (cudaError_t as int)
+// Full binned-SAH build from per-slot reference boxes (n x 6 floats); leaves are re-formed, perm[new slot] = old slot; see lbvh.cu.
+uint32_t bvh2_sah_build_host(const float *ref_boxes, uint32_t n, float trav_cost, BvhNode *out, uint32_t *perm, int *depth, double *sah_cost);
+// mode 1: inner nodes only (download, rebuild, upload in place); mode 2: full build from r->h_ref_box, reference slots and tri_slot permuted
+// (falls back to mode 1 when the boxes were not kept).  Returns cudaError_t as int.
+int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode = 1);
 // Downloads r->nodes, collapses, uploads r->nodes4 (own allocation).  Returns cudaError_t as int; leaves nodes4 = nullptr if the root is a leaf.
 int lbvh_build_wide(LbvhResult *r, cudaStream_t st);
 

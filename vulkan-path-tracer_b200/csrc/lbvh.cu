@@ -10,6 +10,8 @@
 //   [ BvhNode x max(N-1,1) | BvhTri x N ]   nodes: 64 B, both child boxes in the parent; tris: 48 B, Morton order.
 #include "kernels.h"
 #include <vector>
+#include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include <cstdio>
 
@@ -397,21 +399,75 @@ uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t ro
 }
 
 // ------------------------------------------------------------------------------------------------
-// Binned-SAH rebuild of the BVH2 topology above the LBVH's leaves (host, OPT-IN: B200PT_BVH_SAH=1, see Engine::upload_scene).
+// Tree-quality passes on the host (OPT-IN: B200PT_BVH_SAH=1 or 2, see Engine::upload_scene and lbvh_refine_sah).
 // the traversal kernels are bound by the number of node / triangle visits of the Morton-order tree, not by their
-// loop shape.  The leaves (<= 4 consecutive references each, with the padded boxes the LBVH stored for them) are kept as they are; only the
-// inner nodes are rebuilt top-down with a 16-bin surface-area heuristic over the leaf-box centroids (cost = area x references on each
-// side, all three axes tried, median split of the longest axis when the bins cannot separate the leaves).  Child boxes are exact unions
-// of leaf boxes, so the result is as conservative as the input and returns identical hits.  Output: nodes in depth-first order, root = 0.
-// Returns the node count (leaves - 1; 0 if the root is a leaf or the input is not a tree), *depth = new depth, sah[0/1] = SAH cost before / after.
+// loop shape.  Both passes build top-down with a 16-bin surface-area heuristic over box centroids (cost = area x references on each side,
+// all three axes tried, median split in index order when the bins cannot separate the items) and emit nodes depth-first with root 0.
+//   bvh2_sah_rebuild_host  (mode 1): the LBVH's leaves (<= 4 consecutive slots, with the padded boxes stored for them) are kept; only the
+//                          inner nodes above them are rebuilt.  Child boxes are exact unions of leaf boxes: same hits, triangle order untouched.
+//   bvh2_sah_build_host    (mode 2): built from the per-slot reference boxes; leaves are re-formed (<= 4 references, a small range stays a
+//                          leaf when that is cheaper than splitting it), which permutes the reference slots (perm[new slot] = old slot).
 // ------------------------------------------------------------------------------------------------
+namespace {
+struct SahItem { int32_t ref; uint32_t count; float lo[3], hi[3], c[3]; };
+inline double sah_area(const float lo[3], const float hi[3]) { const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2]; return 2.0 * (dx * dy + dy * dz + dz * dx); }
+inline void sah_bounds(const std::vector<SahItem> &it, uint32_t b, uint32_t e, float lo[3], float hi[3]) {
+    for (int a = 0; a < 3; a++) { lo[a] = 3.0e38f; hi[a] = -3.0e38f; }
+    for (uint32_t i = b; i < e; i++) for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], it[i].lo[a]); hi[a] = fmaxf(hi[a], it[i].hi[a]); }
+}
+// Partitions it[b, e) in place and returns mid (b < mid < e).  *cost = area(left) x count(left) + area(right) x count(right) of the split taken.
+uint32_t sah_split(std::vector<SahItem> &it, uint32_t b, uint32_t e, double *cost) {
+    constexpr int NB = 16;
+    float clo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, chi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
+    for (uint32_t i = b; i < e; i++) for (int a = 0; a < 3; a++) { clo[a] = fminf(clo[a], it[i].c[a]); chi[a] = fmaxf(chi[a], it[i].c[a]); }
+    int best_axis = -1, best_bin = -1; double best_cost = 1e300;
+    for (int a = 0; a < 3; a++) {
+        const float ext = chi[a] - clo[a];
+        if (!(ext > 0.0f)) continue;
+        float blo[NB][3], bhi[NB][3]; uint32_t bcnt[NB];
+        for (int k = 0; k < NB; k++) { bcnt[k] = 0; for (int q = 0; q < 3; q++) { blo[k][q] = 3.0e38f; bhi[k][q] = -3.0e38f; } }
+        const float scale = (float)NB / ext;
+        for (uint32_t i = b; i < e; i++) {
+            int k = (int)((it[i].c[a] - clo[a]) * scale); if (k >= NB) k = NB - 1; if (k < 0) k = 0;
+            bcnt[k] += it[i].count;
+            for (int q = 0; q < 3; q++) { blo[k][q] = fminf(blo[k][q], it[i].lo[q]); bhi[k][q] = fmaxf(bhi[k][q], it[i].hi[q]); }
+        }
+        double rarea[NB]; uint32_t rcnt[NB];
+        { float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f }; uint32_t c = 0;
+          for (int k = NB - 1; k >= 1; k--) { if (bcnt[k]) for (int q = 0; q < 3; q++) { lo[q] = fminf(lo[q], blo[k][q]); hi[q] = fmaxf(hi[q], bhi[k][q]); } c += bcnt[k]; rcnt[k] = c; rarea[k] = c ? sah_area(lo, hi) : 0.0; } }
+        float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f }; uint32_t c = 0;
+        for (int k = 0; k < NB - 1; k++) {                                  // split between bin k and k + 1
+            if (bcnt[k]) for (int q = 0; q < 3; q++) { lo[q] = fminf(lo[q], blo[k][q]); hi[q] = fmaxf(hi[q], bhi[k][q]); }
+            c += bcnt[k];
+            if (!c || !rcnt[k + 1]) continue;
+            const double cst = sah_area(lo, hi) * c + rarea[k + 1] * rcnt[k + 1];
+            if (cst < best_cost) { best_cost = cst; best_axis = a; best_bin = k; }
+        }
+    }
+    uint32_t mid = b;
+    if (best_axis >= 0) {
+        const float ext = chi[best_axis] - clo[best_axis], scale = (float)NB / ext;
+        auto bin_of = [&](const SahItem &L) { int k = (int)((L.c[best_axis] - clo[best_axis]) * scale); if (k >= NB) k = NB - 1; if (k < 0) k = 0; return k; };
+        mid = (uint32_t)(std::partition(it.begin() + b, it.begin() + e, [&](const SahItem &L) { return bin_of(L) <= best_bin; }) - it.begin());
+    }
+    if (mid == b || mid == e) {                                             // identical centroids: median split in index order
+        mid = b + (e - b) / 2;
+        float lo[3], hi[3]; uint32_t cl = 0, cr = 0;
+        for (uint32_t i = b; i < mid; i++) cl += it[i].count;
+        for (uint32_t i = mid; i < e; i++) cr += it[i].count;
+        sah_bounds(it, b, mid, lo, hi); best_cost = sah_area(lo, hi) * cl; sah_bounds(it, mid, e, lo, hi); best_cost += sah_area(lo, hi) * cr;
+    }
+    if (cost) *cost = best_cost;
+    return mid;
+}
+} // namespace
+
+// Returns the node count (leaves - 1; 0 if the root is a leaf or the input is not a tree), *depth = new depth, sah[0/1] = SAH cost before / after.
 uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, BvhNode *out, int *depth, double sah[2]) {
     if (depth) *depth = 0;
     if (sah) sah[0] = sah[1] = 0.0;
     if (root2 < 0 || n_nodes2 == 0 || (uint32_t)root2 >= n_nodes2) return 0;
-    struct Leaf { int32_t ref; float lo[3], hi[3], c[3]; uint32_t count; };
-    std::vector<Leaf> leaves; leaves.reserve(n_nodes2 + 1);
-    auto area = [](const float lo[3], const float hi[3]) { const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2]; return 2.0 * (dx * dy + dy * dz + dz * dx); };
+    std::vector<SahItem> leaves; leaves.reserve(n_nodes2 + 1);
     double cost_in = 0.0;
     {   // collect the leaves (and the SAH cost of the input tree, relative to the root box)
         std::vector<int32_t> stack{ root2 }; size_t visited = 0;
@@ -421,11 +477,11 @@ uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t
             const BvhNode &N = nodes2[n];
             for (int k = 0; k < 2; k++) {
                 const int32_t c = k ? N.c1 : N.c0; const float *lo = k ? N.lo1 : N.lo0, *hi = k ? N.hi1 : N.hi0;
-                if (c >= 0) { cost_in += area(lo, hi); stack.push_back(c); }
+                if (c >= 0) { cost_in += sah_area(lo, hi); stack.push_back(c); }
                 else {
-                    Leaf L; L.ref = c; L.count = ((uint32_t)(~c) & 3u) + 1u;
+                    SahItem L; L.ref = c; L.count = ((uint32_t)(~c) & 3u) + 1u;
                     for (int a = 0; a < 3; a++) { L.lo[a] = lo[a]; L.hi[a] = hi[a]; L.c[a] = 0.5f * (lo[a] + hi[a]); }
-                    cost_in += area(lo, hi) * L.count;
+                    cost_in += sah_area(lo, hi) * L.count;
                     leaves.push_back(L);
                 }
             }
@@ -433,66 +489,85 @@ uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t
     }
     const uint32_t nl = (uint32_t)leaves.size();
     if (nl < 2 || nl - 1 > n_nodes2) return 0;
-    auto bounds = [&](uint32_t b, uint32_t e, float lo[3], float hi[3]) {
-        for (int a = 0; a < 3; a++) { lo[a] = 3.0e38f; hi[a] = -3.0e38f; }
-        for (uint32_t i = b; i < e; i++) for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], leaves[i].lo[a]); hi[a] = fmaxf(hi[a], leaves[i].hi[a]); }
-    };
     struct Task { uint32_t b, e; int32_t node; int side; int dep; };       // leaves [b, e) become child `side` of `node` (-1: the root)
     std::vector<Task> tasks{ { 0, nl, -1, 0, 1 } };
     uint32_t n_out = 0; int max_d = 1; double cost_out = 0.0;
-    constexpr int NB = 16;
     while (!tasks.empty()) {
         const Task t = tasks.back(); tasks.pop_back();
-        // split [b, e)
-        float clo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, chi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
-        for (uint32_t i = t.b; i < t.e; i++) for (int a = 0; a < 3; a++) { clo[a] = fminf(clo[a], leaves[i].c[a]); chi[a] = fmaxf(chi[a], leaves[i].c[a]); }
-        int best_axis = -1, best_bin = -1; double best_cost = 1e300;
-        for (int a = 0; a < 3; a++) {
-            const float ext = chi[a] - clo[a];
-            if (!(ext > 0.0f)) continue;
-            float blo[NB][3], bhi[NB][3]; uint32_t bcnt[NB];
-            for (int k = 0; k < NB; k++) { bcnt[k] = 0; for (int q = 0; q < 3; q++) { blo[k][q] = 3.0e38f; bhi[k][q] = -3.0e38f; } }
-            const float scale = (float)NB / ext;
-            for (uint32_t i = t.b; i < t.e; i++) {
-                int k = (int)((leaves[i].c[a] - clo[a]) * scale); if (k >= NB) k = NB - 1; if (k < 0) k = 0;
-                bcnt[k] += leaves[i].count;
-                for (int q = 0; q < 3; q++) { blo[k][q] = fminf(blo[k][q], leaves[i].lo[q]); bhi[k][q] = fmaxf(bhi[k][q], leaves[i].hi[q]); }
-            }
-            double rarea[NB]; uint32_t rcnt[NB];
-            { float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f }; uint32_t c = 0;
-              for (int k = NB - 1; k >= 1; k--) { if (bcnt[k]) for (int q = 0; q < 3; q++) { lo[q] = fminf(lo[q], blo[k][q]); hi[q] = fmaxf(hi[q], bhi[k][q]); } c += bcnt[k]; rcnt[k] = c; rarea[k] = c ? area(lo, hi) : 0.0; } }
-            float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f }; uint32_t c = 0;
-            for (int k = 0; k < NB - 1; k++) {                              // split between bin k and k + 1
-                if (bcnt[k]) for (int q = 0; q < 3; q++) { lo[q] = fminf(lo[q], blo[k][q]); hi[q] = fmaxf(hi[q], bhi[k][q]); }
-                c += bcnt[k];
-                if (!c || !rcnt[k + 1]) continue;
-                const double cost = area(lo, hi) * c + rarea[k + 1] * rcnt[k + 1];
-                if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
-            }
-        }
-        uint32_t mid;
-        if (best_axis >= 0) {
-            const float ext = chi[best_axis] - clo[best_axis], scale = (float)NB / ext;
-            auto bin_of = [&](const Leaf &L) { int k = (int)((L.c[best_axis] - clo[best_axis]) * scale); if (k >= NB) k = NB - 1; if (k < 0) k = 0; return k; };
-            mid = (uint32_t)(std::partition(leaves.begin() + t.b, leaves.begin() + t.e, [&](const Leaf &L) { return bin_of(L) <= best_bin; }) - leaves.begin());
-        } else mid = t.b;
-        if (mid == t.b || mid == t.e) {                                     // identical centroids: median split in index order
-            mid = t.b + (t.e - t.b) / 2;
-        }
+        const uint32_t mid = sah_split(leaves, t.b, t.e, nullptr);
         const uint32_t me = n_out++;
         if (me >= n_nodes2) return 0;
         BvhNode &N = out[me]; N._pad[0] = N._pad[1] = 0;
-        bounds(t.b, mid, N.lo0, N.hi0); bounds(mid, t.e, N.lo1, N.hi1);
+        sah_bounds(leaves, t.b, mid, N.lo0, N.hi0); sah_bounds(leaves, mid, t.e, N.lo1, N.hi1);
         if (t.node >= 0) { if (t.side) out[t.node].c1 = (int32_t)me; else out[t.node].c0 = (int32_t)me; }
         if (t.dep > max_d) max_d = t.dep;
-        if (mid - t.b == 1) { N.c0 = leaves[t.b].ref; cost_out += area(N.lo0, N.hi0) * leaves[t.b].count; } else { cost_out += area(N.lo0, N.hi0); }
-        if (t.e - mid == 1) { N.c1 = leaves[mid].ref; cost_out += area(N.lo1, N.hi1) * leaves[mid].count; } else { cost_out += area(N.lo1, N.hi1); }
+        if (mid - t.b == 1) { N.c0 = leaves[t.b].ref; cost_out += sah_area(N.lo0, N.hi0) * leaves[t.b].count; } else { cost_out += sah_area(N.lo0, N.hi0); }
+        if (t.e - mid == 1) { N.c1 = leaves[mid].ref; cost_out += sah_area(N.lo1, N.hi1) * leaves[mid].count; } else { cost_out += sah_area(N.lo1, N.hi1); }
         // right first so that the left subtree is emitted right after its parent (depth-first layout)
         if (t.e - mid > 1) tasks.push_back({ mid, t.e, (int32_t)me, 1, t.dep + 1 });
         if (mid - t.b > 1) tasks.push_back({ t.b, mid, (int32_t)me, 0, t.dep + 1 });
     }
     if (depth) *depth = max_d;
-    if (sah) { float lo[3], hi[3]; bounds(0, nl, lo, hi); const double ra = area(lo, hi); sah[0] = ra > 0 ? cost_in / ra : 0.0; sah[1] = ra > 0 ? cost_out / ra : 0.0; }
+    if (sah) { float lo[3], hi[3]; sah_bounds(leaves, 0, nl, lo, hi); const double ra = sah_area(lo, hi); sah[0] = ra > 0 ? cost_in / ra : 0.0; sah[1] = ra > 0 ? cost_out / ra : 0.0; }
+    return n_out;
+}
+
+// ref_boxes: n x 6 floats (lo xyz, hi xyz) per reference slot, unpadded.  out: room for n - 1 nodes; perm: n entries, perm[new slot] = old slot.
+// Child boxes get k_emit's padding (4e-7 relative + 2e-6 x the largest |coordinate| of the scene), so the FMA slab test stays conservative.
+// trav_cost: price of one node visit in units of one triangle test (1.0: the classic SAH; larger keeps bigger leaves).
+// Returns the node count (0 when n <= LBVH_LEAF_MAX: the whole scene is one leaf and the caller keeps what it has); *sah_cost relative to the root box.
+uint32_t bvh2_sah_build_host(const float *ref_boxes, uint32_t n, float trav_cost, BvhNode *out, uint32_t *perm, int *depth, double *sah_cost) {
+    if (depth) *depth = 0;
+    if (sah_cost) *sah_cost = 0.0;
+    if (!ref_boxes || !out || !perm || n <= (uint32_t)LBVH_LEAF_MAX || n >= (1u << 28)) return 0;   // leaf references keep the slot in 28 bits
+    std::vector<SahItem> it(n);
+    float ext = 0.0f;
+    for (uint32_t i = 0; i < n; i++) {
+        SahItem &I = it[i]; I.ref = (int32_t)i; I.count = 1;
+        for (int a = 0; a < 3; a++) {
+            I.lo[a] = ref_boxes[(size_t)i * 6 + a]; I.hi[a] = ref_boxes[(size_t)i * 6 + 3 + a]; I.c[a] = 0.5f * (I.lo[a] + I.hi[a]);
+            if (!(I.lo[a] <= I.hi[a])) return 0;                            // NaN or inverted box
+            ext = fmaxf(ext, fmaxf(fabsf(I.lo[a]), fabsf(I.hi[a])));
+        }
+    }
+    const float pabs = 2e-6f * ext + 1e-30f;
+    auto padded = [&](uint32_t b, uint32_t e, float lo[3], float hi[3]) {
+        sah_bounds(it, b, e, lo, hi);
+        for (int a = 0; a < 3; a++) { const float p = 4e-7f * fmaxf(fabsf(lo[a]), fabsf(hi[a])) + pabs; lo[a] -= p; hi[a] += p; }
+    };
+    struct Task { uint32_t b, e; int32_t node; int side; int dep; };
+    std::vector<Task> tasks{ { 0, n, -1, 0, 1 } };
+    uint32_t n_out = 0; int max_d = 1; double cost_out = 0.0;
+    while (!tasks.empty()) {
+        const Task t = tasks.back(); tasks.pop_back();
+        const uint32_t mid = sah_split(it, t.b, t.e, nullptr);
+        const uint32_t me = n_out++;
+        if (me + 1 >= n) return 0;
+        BvhNode &N = out[me]; N._pad[0] = N._pad[1] = 0;
+        if (t.node >= 0) { if (t.side) out[t.node].c1 = (int32_t)me; else out[t.node].c0 = (int32_t)me; }
+        if (t.dep > max_d) max_d = t.dep;
+        bool inner[2];
+        for (int s = 0; s < 2; s++) {
+            const uint32_t x = s ? mid : t.b, y = s ? t.e : mid, cnt = y - x;
+            float *lo = s ? N.lo1 : N.lo0, *hi = s ? N.hi1 : N.hi0;
+            padded(x, y, lo, hi);
+            bool leaf = cnt == 1;
+            if (!leaf && cnt <= (uint32_t)LBVH_LEAF_MAX) {                  // small range: leaf unless splitting it is cheaper
+                float rlo[3], rhi[3]; sah_bounds(it, x, y, rlo, rhi);
+                double split_cost; sah_split(it, x, y, &split_cost);         // (reorders inside the range only)
+                const double a = sah_area(rlo, rhi);
+                leaf = (double)cnt * a <= (double)trav_cost * a + split_cost;
+            }
+            inner[s] = !leaf;
+            const double a = sah_area(lo, hi);
+            if (leaf) { (s ? N.c1 : N.c0) = ~(int32_t)((x << 2) | (cnt - 1)); cost_out += a * cnt; } else cost_out += a;
+        }
+        if (inner[1]) tasks.push_back({ mid, t.e, (int32_t)me, 1, t.dep + 1 });
+        if (inner[0]) tasks.push_back({ t.b, mid, (int32_t)me, 0, t.dep + 1 });
+    }
+    for (uint32_t i = 0; i < n; i++) perm[i] = (uint32_t)it[i].ref;
+    if (depth) *depth = max_d;
+    if (sah_cost) { float lo[3], hi[3]; sah_bounds(it, 0, n, lo, hi); const double ra = sah_area(lo, hi); *sah_cost = ra > 0 ? cost_out / ra : 0.0; }
     return n_out;
 }
 
@@ -513,15 +588,42 @@ int lbvh_build_wide(LbvhResult *r, cudaStream_t st) {
     return 0;
 }
 
-// Opt-in (B200PT_BVH_SAH=1): rebuild the inner nodes in place with bvh2_sah_rebuild_host.  The live node count is unchanged (leaves - 1),
-// so the rebuilt array fits the existing allocation; root becomes 0 and max_depth the new depth.  A no-op for one-leaf scenes.
-int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2]) {
+// Opt-in (B200PT_BVH_SAH=1 / 2).  Mode 1 rebuilds the inner nodes in place with bvh2_sah_rebuild_host: the live node count is unchanged
+// (leaves - 1), so the rebuilt array fits the existing allocation.  Mode 2 builds from the kept per-slot reference boxes with
+// bvh2_sah_build_host (at most slots - 1 nodes: fits as well), then permutes the 48-B triangle slots to the new leaf order and re-derives
+// tri_slot (global triangle id -> one of its slots) from the ids stored in the slots.  Root becomes 0, max_depth the new depth.
+// A no-op for one-leaf scenes.
+int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode) {
     if (sah) sah[0] = sah[1] = 0.0;
     if (!r->nodes || r->root < 0 || r->n_nodes == 0) return 0;
     std::vector<BvhNode> h2(r->n_nodes), out(r->n_nodes);
     LBVH_CHECK(cudaMemcpyAsync(h2.data(), r->nodes, (size_t)r->n_nodes * sizeof(BvhNode), cudaMemcpyDeviceToHost, st));
     LBVH_CHECK(cudaStreamSynchronize(st));
     int depth = 0;
+    if (mode == 2 && r->h_ref_box && r->n_tris > (uint32_t)LBVH_LEAF_MAX && r->n_tris - 1 <= r->n_nodes) {
+        std::vector<uint32_t> perm(r->n_tris);
+        double c_new = 0.0, c_old[2] = { 0.0, 0.0 };
+        { std::vector<BvhNode> scratch(r->n_nodes); int d; bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, scratch.data(), &d, c_old); }   // cost of the LBVH, for the log
+        const uint32_t n = bvh2_sah_build_host(r->h_ref_box, r->n_tris, 1.0f, out.data(), perm.data(), &depth, &c_new);
+        if (n != 0) {
+            std::vector<BvhTri> t_old(r->n_tris), t_new(r->n_tris);
+            LBVH_CHECK(cudaMemcpyAsync(t_old.data(), r->tris, (size_t)r->n_tris * sizeof(BvhTri), cudaMemcpyDeviceToHost, st));
+            LBVH_CHECK(cudaStreamSynchronize(st));
+            std::vector<uint32_t> slot(r->n_prims, 0u);
+            for (uint32_t i = 0; i < r->n_tris; i++) {
+                t_new[i] = t_old[perm[i]];
+                uint32_t gid; memcpy(&gid, &t_new[i].a.w, 4);
+                if (gid < r->n_prims) slot[gid] = i;
+            }
+            LBVH_CHECK(cudaMemcpyAsync(r->tris, t_new.data(), (size_t)r->n_tris * sizeof(BvhTri), cudaMemcpyHostToDevice, st));
+            LBVH_CHECK(cudaMemcpyAsync(r->tri_slot, slot.data(), (size_t)r->n_prims * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            LBVH_CHECK(cudaMemcpyAsync(r->nodes, out.data(), (size_t)n * sizeof(BvhNode), cudaMemcpyHostToDevice, st));
+            LBVH_CHECK(cudaStreamSynchronize(st));
+            r->root = 0; r->max_depth = depth;
+            if (sah) { sah[0] = c_old[0]; sah[1] = c_new; }
+            return 0;
+        }
+    }
     const uint32_t n = bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, out.data(), &depth, sah);
     if (n == 0) return 0;
     LBVH_CHECK(cudaMemcpyAsync(r->nodes, out.data(), (size_t)n * sizeof(BvhNode), cudaMemcpyHostToDevice, st));
@@ -537,12 +639,14 @@ void lbvh_free(LbvhResult *r) {
     if (r->shade) cudaFree(r->shade);
     if (r->tri_slot) cudaFree(r->tri_slot);
     r->shade = nullptr; r->tri_slot = nullptr;
+    if (r->h_ref_box) free(r->h_ref_box);
+    r->h_ref_box = nullptr; r->n_prims = 0;
     r->nodes = nullptr; r->tris = nullptr; r->n_nodes = r->n_tris = 0; r->bytes = 0;
 }
 
 int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const DevMesh *d_meshes, const DevInstance *d_instances,
-               const DevInstance *, const DevMesh *, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st) {
-    out->shade = nullptr; out->tri_slot = nullptr;
+               const DevInstance *, const DevMesh *, uint32_t n_instances, uint32_t n_tris, LbvhResult *out, cudaStream_t st, bool keep_ref_boxes) {
+    out->shade = nullptr; out->tri_slot = nullptr; out->h_ref_box = nullptr; out->n_prims = n_tris;
     out->nodes = nullptr; out->tris = nullptr; out->n_nodes = 0; out->n_tris = n_tris; out->root = 0; out->max_depth = 1; out->bytes = 0;
     out->nodes4 = nullptr; out->n_nodes4 = 0; out->depth4 = 0;
     if (n_tris == 0 || n_instances == 0) return (int)cudaErrorInvalidValue;
@@ -628,6 +732,10 @@ int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const De
                 if (!is_leaf(hr[node])) stack.push_back({ hr[node], dep + 1 });
             }
         }
+    }
+    if (keep_ref_boxes && n_int) {                                          // opt-in SAH build (lbvh_refine_sah mode 2) works from these
+        out->h_ref_box = static_cast<float *>(malloc((size_t)n * 6 * sizeof(float)));
+        if (out->h_ref_box) LBVH_CHECK(cudaMemcpy(out->h_ref_box, leaf_box, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost));
     }
     cudaFree(tmp); cudaFree(aabb); cudaFree(bounds); cudaFree(ksplit); cudaFree(ref_off);
     cudaFree(ref_box); cudaFree(ref_tri); cudaFree(leaf_box); cudaFree(node_box);
