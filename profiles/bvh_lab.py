@@ -208,6 +208,86 @@ def traverse(nodes, tris, O, D, tmax=None):
     return t, n_vis, t_tests
 
 
+def collapse_wide(nodes, K):
+    """Greedy BVH2 -> K-wide collapse (the rule of lbvh.cu: bvh4_collapse_host: keep replacing the inner child of largest area by its two
+    children until K slots are filled).  Returns (child [n, K] with EMPTY = INT32_MIN, lo [n, K, 3], hi [n, K, 3]), breadth-first."""
+    EMPTY = -(1 << 31)
+    c = np.stack([nodes["c0"], nodes["c1"]], 1).astype(np.int64)
+    lo = np.stack([nodes["lo0"], nodes["lo1"]], 1); hi = np.stack([nodes["hi0"], nodes["hi1"]], 1)
+    ext = hi - lo; area = ext[..., 0] * ext[..., 1] + ext[..., 1] * ext[..., 2] + ext[..., 2] * ext[..., 0]
+    queue = [0]; out_c, out_src = [], []
+    i = 0
+    while i < len(queue):
+        n2 = queue[i]; i += 1
+        slots = [(n2, 0), (n2, 1)]
+        while len(slots) < K:
+            best, ba = -1, -1.0
+            for k, (n, s) in enumerate(slots):
+                if c[n, s] >= 0 and area[n, s] > ba: ba, best = area[n, s], k
+            if best < 0: break
+            n, s_ = slots[best]; ch = int(c[n, s_])
+            slots[best] = (ch, 0); slots.append((ch, 1))
+        cc = []
+        for n, s_ in slots:
+            ch = int(c[n, s_])
+            if ch >= 0: cc.append(len(queue)); queue.append(ch)
+            else: cc.append(ch)
+        out_c.append(cc + [EMPTY] * (K - len(slots))); out_src.append(slots + [(0, 0)] * (K - len(slots)))
+    child = np.array(out_c, np.int64); src = np.array(out_src, np.int64)
+    wlo = lo[src[..., 0], src[..., 1]].astype(np.float64); whi = hi[src[..., 0], src[..., 1]].astype(np.float64)
+    empty = child == EMPTY
+    wlo[empty] = 3.0e38; whi[empty] = -3.0e38
+    return child, wlo, whi
+
+
+def traverse_wide(wide, tris, O, D):
+    """K-wide walk: pop a node, slab-test its K children, visit the hit children nearest first (leaves are tested when reached, with the
+    interval re-checked against the current closest hit; inner children go on the stack, farthest first)."""
+    child, wlo, whi = wide
+    K = child.shape[1]; EMPTY = -(1 << 31)
+    R = len(O); inv = 1.0 / np.where(np.abs(D) > 1e-20, D, 1e-20)
+    t = np.full(R, np.inf); n_vis = np.zeros(R, np.int64); t_tests = np.zeros(R, np.int64)
+    stack = np.zeros((R, 64 * K // 2), np.int64); sp = np.ones(R, np.int64)
+    A, E1, E2 = tris[:, 0].astype(np.float64), (tris[:, 1] - tris[:, 0]).astype(np.float64), (tris[:, 2] - tris[:, 0]).astype(np.float64)
+
+    def leaf(rays, ref):
+        r = ~ref; first = r >> 2; cnt = (r & 3) + 1
+        for j in range(4):
+            m = cnt > j
+            if not m.any(): break
+            ri = rays[m]; ti = first[m] + j
+            t_tests[ri] += 1
+            o, d = O[ri], D[ri]
+            p = np.cross(d, E2[ti]); det = (E1[ti] * p).sum(1); ok = np.abs(det) > 1e-30; idet = 1.0 / np.where(ok, det, 1.0)
+            sv = o - A[ti]; u = (sv * p).sum(1) * idet; q = np.cross(sv, E1[ti]); v = (d * q).sum(1) * idet; tt = (E2[ti] * q).sum(1) * idet
+            hit = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (tt > 1e-6) & (tt < t[ri])
+            t[ri[hit]] = tt[hit]
+
+    active = np.arange(R)
+    while len(active):
+        sp[active] -= 1
+        n = stack[active, sp[active]]
+        n_vis[active] += 1
+        o, iv = O[active][:, None, :], inv[active][:, None, :]
+        a = (wlo[n] - o) * iv; b = (whi[n] - o) * iv
+        tn = np.maximum(np.minimum(a, b).max(2), 0.0); tf = np.maximum(a, b).min(2)
+        ch = child[n]
+        hit = (tn <= np.minimum(tf, t[active][:, None])) & (ch != EMPTY)
+        key = np.where(hit, tn, np.inf)
+        order = np.argsort(key, axis=1, kind="stable")
+        for j in range(K):                                               # leaves, nearest first
+            col = order[:, j]; rows = np.arange(len(active))
+            m = hit[rows, col] & (ch[rows, col] < 0) & (key[rows, col] <= t[active])
+            if m.any(): leaf(active[m], ch[rows[m], col[m]])
+        for j in range(K - 1, -1, -1):                                   # inner children, farthest pushed first
+            col = order[:, j]; rows = np.arange(len(active))
+            m = hit[rows, col] & (ch[rows, col] >= 0)
+            if m.any():
+                ri = active[m]; stack[ri, sp[ri]] = ch[rows[m], col[m]]; sp[ri] += 1
+        active = active[sp[active] > 0]
+    return t, n_vis, t_tests
+
+
 def make_rays(sc, n_rays, rng):
     vi, pi = B.camera_from_view(sc["camera_view"], sc["aspect"])
     vi = np.asarray(vi, np.float64).reshape(4, 4).T; pi = np.asarray(pi, np.float64).reshape(4, 4).T
@@ -233,7 +313,7 @@ def stats(name, n_vis, t_tests):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("scene"); ap.add_argument("--rays", type=int, default=20000); ap.add_argument("--out", default=None); ap.add_argument("--seed", type=int, default=1); ap.add_argument("--table", action="store_true")
+    ap.add_argument("scene"); ap.add_argument("--rays", type=int, default=20000); ap.add_argument("--out", default=None); ap.add_argument("--seed", type=int, default=1); ap.add_argument("--table", action="store_true"); ap.add_argument("--wide", type=int, nargs="*", default=[], help="also model K-wide collapses of every tree (4, 8)")
     ap.add_argument("--trav-cost", type=float, nargs="*", default=[1.0], help="node-visit price(s) for the full SAH build (mode 2)")
     a = ap.parse_args()
     sc = load_fixture(a.scene)
@@ -259,6 +339,10 @@ def main():
         full, perm, d_full, c_full = B.bvh2_sah_build(rb.reshape(-1, 6), tc)
         res[f"sah_full_tc{tc:g}"] = {"nodes": int(len(full)), "depth": int(d_full), "sah_cost": c_full, "host_seconds": round(time.time() - t0, 3)}
         trees.append((f"sah_full_tc{tc:g}", full, rtris[perm]))
+    wides = []
+    for K in a.wide:
+        for name, nodes, tt in trees:
+            wides.append((f"{name}/bvh{K}", collapse_wide(nodes, K), tt))
     O, D = make_rays(sc, a.rays, rng)
     base = None
     for name, nodes, tt in trees:
@@ -266,11 +350,19 @@ def main():
         if base is None: base = t
         assert np.array_equal(np.isfinite(t), np.isfinite(base)) and np.allclose(t[np.isfinite(t)], base[np.isfinite(base)], rtol=1e-9, atol=1e-12), "all trees must return identical hits"
         res["rays"].append(dict(stats("camera", nv, kt), tree=name))
+    for name, w, tt in wides:
+        t, nv, kt = traverse_wide(w, tt, O, D)
+        assert np.array_equal(np.isfinite(t), np.isfinite(base)) and np.allclose(t[np.isfinite(t)], base[np.isfinite(base)], rtol=1e-9, atol=1e-12)
+        res["rays"].append(dict(stats("camera", nv, kt), tree=name))
     O2, D2 = bounce_rays(O, D, base, rng)
     base2 = None
     for name, nodes, tt in trees:
         t, nv, kt = traverse(nodes, tt, O2, D2)
         if base2 is None: base2 = t
+        assert np.array_equal(np.isfinite(t), np.isfinite(base2)) and np.allclose(t[np.isfinite(t)], base2[np.isfinite(base2)], rtol=1e-9, atol=1e-12)
+        res["rays"].append(dict(stats("bounce", nv, kt), tree=name))
+    for name, w, tt in wides:
+        t, nv, kt = traverse_wide(w, tt, O2, D2)
         assert np.array_equal(np.isfinite(t), np.isfinite(base2)) and np.allclose(t[np.isfinite(t)], base2[np.isfinite(base2)], rtol=1e-9, atol=1e-12)
         res["rays"].append(dict(stats("bounce", nv, kt), tree=name))
     if a.table:
