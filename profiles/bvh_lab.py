@@ -288,6 +288,21 @@ def traverse_wide(wide, tris, O, D):
     return t, n_vis, t_tests
 
 
+def quantize_wide(wide, bits=8):
+    """Parent-relative quantisation of the child boxes (CWBVH-style): per node an origin and a power-of-two scale per axis, child planes
+    rounded outwards to `bits` bits.  Models what a compressed wide node would cost in extra visits."""
+    child, wlo, whi = wide
+    EMPTY = -(1 << 31); used = child != EMPTY
+    lo = np.where(used[..., None], wlo, np.inf).min(1); hi = np.where(used[..., None], whi, -np.inf).max(1)
+    qmax = (1 << bits) - 1
+    e = np.ceil(np.log2(np.maximum(hi - lo, 1e-30) / qmax)); scale = np.exp2(e)[:, None, :]
+    qlo = np.floor((wlo - lo[:, None, :]) / scale); qhi = np.ceil((whi - lo[:, None, :]) / scale)
+    dlo = lo[:, None, :] + np.clip(qlo, 0, qmax) * scale; dhi = lo[:, None, :] + np.clip(qhi, 0, qmax) * scale
+    dlo[~used] = 3.0e38; dhi[~used] = -3.0e38
+    assert np.all(dlo[used] <= wlo[used]) and np.all(dhi[used] >= whi[used])
+    return child, dlo, dhi
+
+
 def make_rays(sc, n_rays, rng):
     vi, pi = B.camera_from_view(sc["camera_view"], sc["aspect"])
     vi = np.asarray(vi, np.float64).reshape(4, 4).T; pi = np.asarray(pi, np.float64).reshape(4, 4).T
@@ -313,7 +328,7 @@ def stats(name, n_vis, t_tests):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("scene"); ap.add_argument("--rays", type=int, default=20000); ap.add_argument("--out", default=None); ap.add_argument("--seed", type=int, default=1); ap.add_argument("--table", action="store_true"); ap.add_argument("--wide", type=int, nargs="*", default=[], help="also model K-wide collapses of every tree (4, 8)")
+    ap.add_argument("scene"); ap.add_argument("--rays", type=int, default=20000); ap.add_argument("--out", default=None); ap.add_argument("--seed", type=int, default=1); ap.add_argument("--table", action="store_true"); ap.add_argument("--quantize", type=int, default=0, help="also model the wide trees with child boxes quantised to this many bits"); ap.add_argument("--wide", type=int, nargs="*", default=[], help="also model K-wide collapses of every tree (4, 8)")
     ap.add_argument("--trav-cost", type=float, nargs="*", default=[1.0], help="node-visit price(s) for the full SAH build (mode 2)")
     a = ap.parse_args()
     sc = load_fixture(a.scene)
@@ -342,7 +357,9 @@ def main():
     wides = []
     for K in a.wide:
         for name, nodes, tt in trees:
-            wides.append((f"{name}/bvh{K}", collapse_wide(nodes, K), tt))
+            w = collapse_wide(nodes, K)
+            wides.append((f"{name}/bvh{K}", w, tt))
+            if a.quantize: wides.append((f"{name}/bvh{K}q{a.quantize}", quantize_wide(w, a.quantize), tt))
     O, D = make_rays(sc, a.rays, rng)
     base = None
     for name, nodes, tt in trees:
@@ -366,7 +383,7 @@ def main():
         assert np.array_equal(np.isfinite(t), np.isfinite(base2)) and np.allclose(t[np.isfinite(t)], base2[np.isfinite(base2)], rtol=1e-9, atol=1e-12)
         res["rays"].append(dict(stats("bounce", nv, kt), tree=name))
     if a.table:
-        for r in res["rays"]: print(f'{r["set"]:7s} {r["tree"]:18s} nodes {r["nodes_mean"]:6.2f} (p99 {r["nodes_p99"]:5.0f})  tris {r["tris_mean"]:5.2f} (p99 {r["tris_p99"]:4.0f})')
+        for r in res["rays"]: print(f'{r["set"]:7s} {r["tree"]:24s} nodes {r["nodes_mean"]:6.2f} (p99 {r["nodes_p99"]:5.0f})  tris {r["tris_mean"]:5.2f} (p99 {r["tris_p99"]:4.0f})')
     else:
         print(json.dumps(res, indent=1))
     if a.out:
