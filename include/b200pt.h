@@ -238,6 +238,10 @@ int32_t b200pt_bvh2_sah_rebuild(const void *nodes2, uint32_t n_nodes2, int32_t r
  * visit in triangle tests (1.0 = classic SAH).  *n_out = 0 when n <= 4 (one leaf) or a box is inverted / NaN. */
 int32_t b200pt_bvh2_sah_build(const float *ref_boxes, uint32_t n, float trav_cost, void *nodes_out, uint32_t *perm_out, uint32_t *n_out, int32_t *depth_out, double *sah_cost);
 
+/* Third opt-in level (B200PT_BVH_SAH=3 = level 2 followed by this): insertion-based refinement of a BVH2 -- the `fraction` largest nodes
+ * are re-inserted where they add the least surface area, `passes` times.  Leaves are kept; output conventions as b200pt_bvh2_sah_rebuild. */
+int32_t b200pt_bvh2_reinsert(const void *nodes2, uint32_t n_nodes2, int32_t root2, void *nodes_out, int32_t passes, float fraction, uint32_t *n_out, int32_t *depth_out, double *sah_before_after);
+
 /* ---- standalone codecs of the loader / image-output API (no GPU needed) ---- */
 /* stbi_load(.., STBI_rgb_alpha) / stbi_loadf semantics (AssetImporterImpl.cpp:494-545); free with b200pt_free */
 int32_t b200pt_decode_image_file(const char *path, uint32_t *width, uint32_t *height, uint8_t **rgba_out);

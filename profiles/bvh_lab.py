@@ -328,7 +328,7 @@ def stats(name, n_vis, t_tests):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("scene"); ap.add_argument("--rays", type=int, default=20000); ap.add_argument("--out", default=None); ap.add_argument("--seed", type=int, default=1); ap.add_argument("--table", action="store_true"); ap.add_argument("--quantize", type=int, default=0, help="also model the wide trees with child boxes quantised to this many bits"); ap.add_argument("--wide", type=int, nargs="*", default=[], help="also model K-wide collapses of every tree (4, 8)")
+    ap.add_argument("scene"); ap.add_argument("--rays", type=int, default=20000); ap.add_argument("--out", default=None); ap.add_argument("--seed", type=int, default=1); ap.add_argument("--table", action="store_true"); ap.add_argument("--reinsert", type=float, nargs=2, action="append", default=[], metavar=("PASSES", "FRACTION"), help="also refine the full SAH tree by re-insertion"); ap.add_argument("--quantize", type=int, default=0, help="also model the wide trees with child boxes quantised to this many bits"); ap.add_argument("--wide", type=int, nargs="*", default=[], help="also model K-wide collapses of every tree (4, 8)")
     ap.add_argument("--trav-cost", type=float, nargs="*", default=[1.0], help="node-visit price(s) for the full SAH build (mode 2)")
     a = ap.parse_args()
     sc = load_fixture(a.scene)
@@ -354,6 +354,11 @@ def main():
         full, perm, d_full, c_full = B.bvh2_sah_build(rb.reshape(-1, 6), tc)
         res[f"sah_full_tc{tc:g}"] = {"nodes": int(len(full)), "depth": int(d_full), "sah_cost": c_full, "host_seconds": round(time.time() - t0, 3)}
         trees.append((f"sah_full_tc{tc:g}", full, rtris[perm]))
+        for passes, frac in a.reinsert:
+            t0 = time.time()
+            ri, d_ri, (c_a, c_b) = B.bvh2_reinsert(full, 0, int(passes), frac)
+            res[f"reinsert_p{int(passes)}_f{frac:g}"] = {"depth": int(d_ri), "sah_cost": [c_a, c_b], "host_seconds": round(time.time() - t0, 3)}
+            trees.append((f"full+ri p{int(passes)} f{frac:g}", ri, rtris[perm]))
     wides = []
     for K in a.wide:
         for name, nodes, tt in trees:

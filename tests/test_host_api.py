@@ -278,6 +278,49 @@ def _bvh2_leaf_sets(nodes, root=0):
     return under, order
 
 
+@pytest.mark.parametrize("n_leaves,chain", [(3, False), (4, False), (64, False), (3000, False), (60, True)])
+def test_bvh2_reinsert_keeps_leaves_and_lowers_the_cost(n_leaves, chain):
+    """Third opt-in level (lbvh.cu: bvh2_reinsert_host): same leaf references with the same boxes, every child box the exact union of the
+    leaf boxes beneath it, depth-first layout with root 0, exact depth, surface-area cost never worse -- starting from a random tree and
+    from the binned-SAH tree (little left to find on uniformly scattered boxes; 11 % on BreakfastRoom, profiles/r01_bvh_lab_breakfast.json)."""
+    from vpt_b200 import binding as B
+    rng = np.random.default_rng(500 + n_leaves)
+    nodes2, refs = _random_bvh2(n_leaves, rng, chain)
+    leaf_box = {}
+    for n in nodes2:
+        for c, lo, hi in ((int(n["c0"]), n["lo0"], n["hi0"]), (int(n["c1"]), n["lo1"], n["hi1"])):
+            if c < 0: leaf_box[c] = (lo.copy(), hi.copy())
+    sah_tree = B.bvh2_sah_rebuild(nodes2, 0)[0]
+    for start, passes, frac in ((nodes2, 2, 0.5), (sah_tree, 3, 0.25), (nodes2, 0, 0.5)):
+        out, depth, (c0, c1) = B.bvh2_reinsert(start, 0, passes, frac)
+        assert len(out) == n_leaves - 1
+        under, order = _bvh2_leaf_sets(out, 0)
+        assert sorted(order) == list(range(len(out)))
+        assert sorted(under[0][0] | under[0][1]) == sorted(refs) and not (under[0][0] & under[0][1])
+        dep = {0: 1}
+        for n in order:
+            for k, c in enumerate((int(out[n]["c0"]), int(out[n]["c1"]))):
+                lo, hi = (out[n]["lo1"], out[n]["hi1"]) if k else (out[n]["lo0"], out[n]["hi0"])
+                boxes = [leaf_box[r] for r in under[n][k]]
+                assert np.array_equal(lo, np.min([b[0] for b in boxes], axis=0)) and np.array_equal(hi, np.max([b[1] for b in boxes], axis=0))
+                if c >= 0:
+                    assert c > n; dep[c] = dep[n] + 1
+            if int(out[n]["c0"]) >= 0: assert int(out[n]["c0"]) == n + 1
+        assert depth == max(dep.values())
+        assert c1 <= c0 * (1.0 + 1e-5)
+        if passes == 0: assert abs(c1 - c0) <= 1e-5 * c0                         # no pass: the tree comes back re-laid-out, cost unchanged
+        if n_leaves >= 3000 and start is nodes2 and passes: assert c1 < 0.5 * c0
+    with pytest.raises(B.B200ptError):
+        B.bvh2_reinsert(nodes2, 0, passes=-1)
+    with pytest.raises(B.B200ptError):
+        B.bvh2_reinsert(nodes2, 0, fraction=1.5)
+    bad = nodes2.copy(); bad[0]["c1"] = 10 ** 6                                  # child index outside the array
+    assert len(B.bvh2_reinsert(bad, 0)[0]) == 0
+    if n_leaves >= 4:
+        cyc = nodes2.copy(); cyc[1]["c0"] = 0                                      # a cycle
+        assert len(B.bvh2_reinsert(cyc, 0)[0]) == 0
+
+
 @pytest.mark.parametrize("n_leaves,chain", [(2, False), (3, False), (64, False), (3000, False), (60, True)])
 def test_bvh2_sah_rebuild_keeps_leaves_and_tightens_the_tree(n_leaves, chain):
     """Opt-in tree-quality pass (lbvh.cu: bvh2_sah_rebuild_host): same leaf references with the same boxes, every child box the exact

@@ -144,6 +144,7 @@ def lib():
             "b200pt_build_env_alias": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_float)],
             "b200pt_bvh4_collapse": [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)],
             "b200pt_bvh2_sah_build": [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_double)],
+            "b200pt_bvh2_reinsert": [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_void_p],
             "b200pt_bvh2_sah_rebuild": [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_void_p],
             "b200pt_load_gltf": [C.c_char_p, C.POINTER(C.POINTER(SceneDesc))], "b200pt_free_scene": [C.POINTER(SceneDesc)],
         }
@@ -239,6 +240,16 @@ def bvh2_sah_build(ref_boxes, trav_cost=1.0):
     r = lib().b200pt_bvh2_sah_build(_p(rb), len(rb), C.c_float(trav_cost), _p(out), _p(perm), C.byref(n), C.byref(d), C.byref(c))
     if r != OK: raise B200ptError(r, "bvh2_sah_build")
     return out[:n.value].copy(), perm, d.value, c.value
+
+
+def bvh2_reinsert(nodes2, root2=0, passes=2, fraction=0.25):
+    """Insertion-based refinement (csrc/lbvh.cu: bvh2_reinsert_host).  Returns (BVH2_DTYPE array, depth, (sah_before, sah_after))."""
+    nodes2 = np.ascontiguousarray(nodes2, BVH2_DTYPE)
+    out = np.zeros(len(nodes2), BVH2_DTYPE)
+    n, d = C.c_uint32(), C.c_int32(); sah = np.zeros(2, np.float64)
+    r = lib().b200pt_bvh2_reinsert(_p(nodes2), len(nodes2), int(root2), _p(out), int(passes), C.c_float(fraction), C.byref(n), C.byref(d), _p(sah))
+    if r != OK: raise B200ptError(r, "bvh2_reinsert")
+    return out[:n.value].copy(), d.value, (float(sah[0]), float(sah[1]))
 
 
 def build_env_alias(rgba):

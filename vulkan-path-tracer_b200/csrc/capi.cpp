@@ -249,6 +249,16 @@ int32_t b200pt_bvh2_sah_build(const float *ref_boxes, uint32_t n, float trav_cos
     if (sah_cost) *sah_cost = c;
     return B200PT_OK;
 }
+int32_t b200pt_bvh2_reinsert(const void *nodes2, uint32_t n_nodes2, int32_t root2, void *out, int32_t passes, float fraction, uint32_t *n_out, int32_t *depth_out, double *sah) {
+    if (!nodes2 || !out || !n_out || !n_nodes2 || passes < 0 || passes > 64 || !(fraction >= 0.0f && fraction <= 1.0f)) return B200PT_ERR_WRONG_ARGUMENTS;
+    if (root2 >= 0 && (uint32_t)root2 >= n_nodes2) return B200PT_ERR_WRONG_ARGUMENTS;
+    int d = 0; double c[2] = { 0.0, 0.0 };
+    try { *n_out = b200pt::bvh2_reinsert_host(static_cast<const b200pt::BvhNode *>(nodes2), n_nodes2, root2, static_cast<b200pt::BvhNode *>(out), passes, fraction, &d, c); }
+    catch (...) { return B200PT_ERR_OUT_OF_MEMORY; }
+    if (depth_out) *depth_out = d;
+    if (sah) { sah[0] = c[0]; sah[1] = c[1]; }
+    return B200PT_OK;
+}
 int32_t b200pt_build_env_alias(float *rgba, uint32_t w, uint32_t hh, void *alias, float *sum) {
     if (!rgba || !w || !hh || !alias) return B200PT_ERR_WRONG_ARGUMENTS;
     float s = build_env_alias(rgba, w, hh, (uint2 *)alias); if (sum) *sum = s; return B200PT_OK;

@@ -49,10 +49,12 @@ uint32_t bvh4_collapse_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t ro
 // Opt-in binned-SAH rebuild of the inner nodes above the LBVH's leaves (pure CPU code, unit-tested through b200pt_bvh2_sah_rebuild).
 // `out` must hold n_nodes2 entries; returns the node count (0 = nothing rebuilt), *depth, sah[0/1] = SAH cost before / after.
 uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, BvhNode *out, int *depth, double sah[2]);
+// Insertion-based refinement of any BVH2 (leaves kept); same output conventions as bvh2_sah_rebuild_host.
+uint32_t bvh2_reinsert_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, BvhNode *out, int passes, float fraction, int *depth, double sah[2]);
 // Full binned-SAH build from per-slot reference boxes (n x 6 floats); leaves are re-formed, perm[new slot] = old slot; see lbvh.cu.
 uint32_t bvh2_sah_build_host(const float *ref_boxes, uint32_t n, float trav_cost, BvhNode *out, uint32_t *perm, int *depth, double *sah_cost);
 // mode 1: inner nodes only (download, rebuild, upload in place); mode 2: full build from r->h_ref_box, reference slots and tri_slot permuted
-// (falls back to mode 1 when the boxes were not kept).  Returns cudaError_t as int.
+// (falls back to mode 1 when the boxes were not kept); mode 3: mode 2 + insertion-based refinement.  Returns cudaError_t as int.
 int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode = 1);
 // Downloads r->nodes, collapses, uploads r->nodes4 (own allocation).  Returns cudaError_t as int; leaves nodes4 = nullptr if the root is a leaf.
 int lbvh_build_wide(LbvhResult *r, cudaStream_t st);

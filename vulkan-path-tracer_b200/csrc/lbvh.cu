@@ -512,6 +512,125 @@ uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t
     return n_out;
 }
 
+// Insertion-based refinement (after Bittner, Hapala, Havran 2013, "Fast insertion-based optimization of bounding volume hierarchies"):
+// the nodes of largest surface area are taken out of the tree one at a time (the sibling takes the parent's place) and put back at the
+// position that adds the least surface area, found by a branch-and-bound descent from the root.  Leaves (references and their stored,
+// padded boxes) are untouched, inner boxes are unions of leaf boxes: same hits.  `passes` sweeps over the `fraction` largest nodes each.
+// Output as in bvh2_sah_rebuild_host (depth-first, root 0, same node count).  Returns 0 when the input is not a tree or has < 3 leaves.
+uint32_t bvh2_reinsert_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t root2, BvhNode *out, int passes, float fraction, int *depth, double sah[2]) {
+    if (depth) *depth = 0;
+    if (sah) sah[0] = sah[1] = 0.0;
+    if (root2 < 0 || n_nodes2 == 0 || (uint32_t)root2 >= n_nodes2 || !out) return 0;
+    struct T { float lo[3], hi[3]; int parent, c[2]; int32_t ref; float area; };   // leaves: c = {-1, -1}, ref < 0
+    std::vector<T> t; t.reserve(2 * (size_t)n_nodes2 + 1);
+    auto set_area = [](T &x) { x.area = (float)sah_area(x.lo, x.hi); };
+    {   // pointer tree with a box per node; element 0 is the root
+        struct E { int32_t n2; int parent; int side; };
+        std::vector<E> stack{ { root2, -1, 0 } }; size_t visited = 0;
+        while (!stack.empty()) {
+            const E e = stack.back(); stack.pop_back();
+            if ((uint32_t)e.n2 >= n_nodes2 || ++visited > (size_t)n_nodes2) return 0;
+            const BvhNode &N = nodes2[e.n2];
+            const int me = (int)t.size(); t.push_back(T{});
+            t[me].parent = e.parent; t[me].ref = 0; t[me].c[0] = t[me].c[1] = -1;
+            for (int a = 0; a < 3; a++) { t[me].lo[a] = fminf(N.lo0[a], N.lo1[a]); t[me].hi[a] = fmaxf(N.hi0[a], N.hi1[a]); }
+            set_area(t[me]);
+            if (e.parent >= 0) t[e.parent].c[e.side] = me;
+            for (int k = 0; k < 2; k++) {
+                const int32_t c = k ? N.c1 : N.c0;
+                if (c >= 0) stack.push_back({ c, me, k });
+                else {
+                    const int lf = (int)t.size(); t.push_back(T{});
+                    t[lf].parent = me; t[lf].ref = c; t[lf].c[0] = t[lf].c[1] = -1; t[me].c[k] = lf;
+                    for (int a = 0; a < 3; a++) { t[lf].lo[a] = k ? N.lo1[a] : N.lo0[a]; t[lf].hi[a] = k ? N.hi1[a] : N.hi0[a]; }
+                    set_area(t[lf]);
+                }
+            }
+        }
+    }
+    const uint32_t n_all = (uint32_t)t.size(), n_inner = n_all / 2;            // a full binary tree: inner = leaves - 1
+    if (n_all < 5 || n_inner > n_nodes2) return 0;
+    auto weight = [&](const T &x) { return x.c[0] < 0 ? (double)(((uint32_t)(~x.ref) & 3u) + 1u) : 1.0; };
+    auto cost = [&]() { double c = 0.0; for (uint32_t i = 1; i < n_all; i++) c += (double)t[i].area * weight(t[i]); return c; };
+    int root = 0;
+    const double root_area = t[0].area, cost_in = cost();
+    auto refit_up = [&](int n) {
+        while (n >= 0) {
+            T &x = t[n]; const T &a = t[x.c[0]], &b = t[x.c[1]];
+            bool same = true;
+            for (int k = 0; k < 3; k++) {
+                const float lo = fminf(a.lo[k], b.lo[k]), hi = fmaxf(a.hi[k], b.hi[k]);
+                if (lo != x.lo[k] || hi != x.hi[k]) same = false;
+                x.lo[k] = lo; x.hi[k] = hi;
+            }
+            if (same) break;
+            set_area(x); n = x.parent;
+        }
+    };
+    auto union_area = [&](const T &a, const T &b) {
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; k++) { lo[k] = fminf(a.lo[k], b.lo[k]); hi[k] = fmaxf(a.hi[k], b.hi[k]); }
+        return (float)sah_area(lo, hi);
+    };
+    std::vector<std::pair<float, int>> heap;                                  // (-induced cost, node): std::push_heap keeps the smallest induced cost on top
+    std::vector<std::pair<float, int>> cand;
+    for (int pass = 0; pass < passes; pass++) {
+        cand.clear();
+        for (uint32_t i = 0; i < n_all; i++) if ((int)i != root && t[i].parent != root) cand.push_back({ t[i].area, (int)i });
+        const size_t take = std::min(cand.size(), (size_t)((double)cand.size() * fraction) + 1);
+        std::partial_sort(cand.begin(), cand.begin() + take, cand.end(), [](const std::pair<float, int> &a, const std::pair<float, int> &b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+        for (size_t ci = 0; ci < take; ci++) {
+            const int n = cand[ci].second, p = t[n].parent;
+            if (n == root || p < 0 || p == root) continue;                      // the tree changes under the sweep
+            const int g = t[p].parent, sib = t[p].c[0] == n ? t[p].c[1] : t[p].c[0];
+            // take n (and its parent p) out: the sibling moves up
+            t[g].c[t[g].c[0] == p ? 0 : 1] = sib; t[sib].parent = g;
+            refit_up(g);
+            // branch and bound for the cheapest position
+            int best = sib; float best_cost = 3.0e38f;
+            heap.clear(); heap.push_back({ -0.0f, root });
+            const float na = t[n].area;
+            while (!heap.empty()) {
+                std::pop_heap(heap.begin(), heap.end()); const float induced = -heap.back().first; const int x = heap.back().second; heap.pop_back();
+                if (induced + na >= best_cost) break;
+                const float direct = union_area(t[x], t[n]), total = induced + direct;
+                if (total < best_cost) { best_cost = total; best = x; }
+                const float child_induced = total - t[x].area;
+                if (t[x].c[0] >= 0 && child_induced + na < best_cost) {
+                    heap.push_back({ -child_induced, t[x].c[0] }); std::push_heap(heap.begin(), heap.end());
+                    heap.push_back({ -child_induced, t[x].c[1] }); std::push_heap(heap.begin(), heap.end());
+                }
+            }
+            // put it back: p becomes the parent of (best, n)
+            const int bp = t[best].parent;
+            t[p].parent = bp; t[p].c[0] = best; t[p].c[1] = n; t[best].parent = p; t[n].parent = p;
+            if (bp >= 0) t[bp].c[t[bp].c[0] == best ? 0 : 1] = p; else root = p;
+            for (int k = 0; k < 3; k++) { t[p].lo[k] = 3.0e38f; t[p].hi[k] = -3.0e38f; }      // force the refit to start here
+            refit_up(p);
+        }
+    }
+    // emit depth-first from the (possibly new) root
+    struct Task { int n; int32_t parent; int side; int dep; };
+    std::vector<Task> tasks{ { root, -1, 0, 1 } };
+    uint32_t n_out = 0; int max_d = 1; double cost_out = 0.0;
+    while (!tasks.empty()) {
+        const Task k = tasks.back(); tasks.pop_back();
+        const uint32_t me = n_out++;
+        if (me >= n_nodes2) return 0;
+        BvhNode &N = out[me]; N._pad[0] = N._pad[1] = 0;
+        if (k.parent >= 0) { if (k.side) out[k.parent].c1 = (int32_t)me; else out[k.parent].c0 = (int32_t)me; }
+        if (k.dep > max_d) max_d = k.dep;
+        const T &a = t[t[k.n].c[0]], &b = t[t[k.n].c[1]];
+        for (int q = 0; q < 3; q++) { N.lo0[q] = a.lo[q]; N.hi0[q] = a.hi[q]; N.lo1[q] = b.lo[q]; N.hi1[q] = b.hi[q]; }
+        cost_out += (double)a.area * weight(a) + (double)b.area * weight(b);
+        if (b.c[0] >= 0) tasks.push_back({ t[k.n].c[1], (int32_t)me, 1, k.dep + 1 }); else N.c1 = b.ref;
+        if (a.c[0] >= 0) tasks.push_back({ t[k.n].c[0], (int32_t)me, 0, k.dep + 1 }); else N.c0 = a.ref;
+    }
+    if (depth) *depth = max_d;
+    if (sah) { sah[0] = root_area > 0 ? cost_in / root_area : 0.0; sah[1] = root_area > 0 ? cost_out / root_area : 0.0; }
+    return n_out;
+}
+
 // ref_boxes: n x 6 floats (lo xyz, hi xyz) per reference slot, unpadded.  out: room for n - 1 nodes; perm: n entries, perm[new slot] = old slot.
 // Child boxes get k_emit's padding (4e-7 relative + 2e-6 x the largest |coordinate| of the scene), so the FMA slab test stays conservative.
 // trav_cost: price of one node visit in units of one triangle test (1.0: the classic SAH; larger keeps bigger leaves).
@@ -588,7 +707,7 @@ int lbvh_build_wide(LbvhResult *r, cudaStream_t st) {
     return 0;
 }
 
-// Opt-in (B200PT_BVH_SAH=1 / 2).  Mode 1 rebuilds the inner nodes in place with bvh2_sah_rebuild_host: the live node count is unchanged
+// Opt-in (B200PT_BVH_SAH=1 / 2 / 3; 3 = 2 followed by bvh2_reinsert_host, 3 passes over the largest quarter of the nodes).  Mode 1 rebuilds the inner nodes in place with bvh2_sah_rebuild_host: the live node count is unchanged
 // (leaves - 1), so the rebuilt array fits the existing allocation.  Mode 2 builds from the kept per-slot reference boxes with
 // bvh2_sah_build_host (at most slots - 1 nodes: fits as well), then permutes the 48-B triangle slots to the new leaf order and re-derives
 // tri_slot (global triangle id -> one of its slots) from the ids stored in the slots.  Root becomes 0, max_depth the new depth.
@@ -600,12 +719,18 @@ int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode) {
     LBVH_CHECK(cudaMemcpyAsync(h2.data(), r->nodes, (size_t)r->n_nodes * sizeof(BvhNode), cudaMemcpyDeviceToHost, st));
     LBVH_CHECK(cudaStreamSynchronize(st));
     int depth = 0;
-    if (mode == 2 && r->h_ref_box && r->n_tris > (uint32_t)LBVH_LEAF_MAX && r->n_tris - 1 <= r->n_nodes) {
+    auto reinsert = [&](uint32_t n_in, double *cost_after) {                  // mode 3: insertion-based refinement of `out`, result back in `out`
+        std::vector<BvhNode> tmp(r->n_nodes); int d2 = 0; double c2[2];
+        const uint32_t m = bvh2_reinsert_host(out.data(), n_in, 0, tmp.data(), 3, 0.25f, &d2, c2);
+        if (m == n_in) { std::copy(tmp.begin(), tmp.begin() + m, out.begin()); depth = d2; if (cost_after) *cost_after = c2[1]; }
+    };
+    if (mode >= 2 && r->h_ref_box && r->n_tris > (uint32_t)LBVH_LEAF_MAX && r->n_tris - 1 <= r->n_nodes) {
         std::vector<uint32_t> perm(r->n_tris);
         double c_new = 0.0, c_old[2] = { 0.0, 0.0 };
         { std::vector<BvhNode> scratch(r->n_nodes); int d; bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, scratch.data(), &d, c_old); }   // cost of the LBVH, for the log
         const uint32_t n = bvh2_sah_build_host(r->h_ref_box, r->n_tris, 1.0f, out.data(), perm.data(), &depth, &c_new);
         if (n != 0) {
+            if (mode >= 3) reinsert(n, &c_new);
             std::vector<BvhTri> t_old(r->n_tris), t_new(r->n_tris);
             LBVH_CHECK(cudaMemcpyAsync(t_old.data(), r->tris, (size_t)r->n_tris * sizeof(BvhTri), cudaMemcpyDeviceToHost, st));
             LBVH_CHECK(cudaStreamSynchronize(st));
@@ -626,6 +751,7 @@ int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode) {
     }
     const uint32_t n = bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, out.data(), &depth, sah);
     if (n == 0) return 0;
+    if (mode >= 3) reinsert(n, sah ? &sah[1] : nullptr);
     LBVH_CHECK(cudaMemcpyAsync(r->nodes, out.data(), (size_t)n * sizeof(BvhNode), cudaMemcpyHostToDevice, st));
     LBVH_CHECK(cudaStreamSynchronize(st));
     r->root = 0; r->max_depth = depth;
