@@ -349,6 +349,12 @@ def main():
            "sah_nodes": int(len(sah)), "sah_depth": int(depth_sah), "sah_cost_lbvh": c0, "sah_cost_rebuilt": c1,
            "host_seconds": {"numpy_lbvh_mirror": round(t_lbvh, 2), "sah_rebuild_cxx": round(t_sah, 3)}, "rays": []}
     trees = [("lbvh", lb, rtris), ("sah_inner", sah, rtris)]
+    for passes, frac in a.reinsert:                                      # engine levels 4 (inner rebuild + re-insertion) and 5 (re-insertion alone)
+        for tag, src in (("sah_inner+ri", sah), ("lbvh+ri", lb)):
+            t0 = time.time()
+            ri, d_ri, (c_a, c_b) = B.bvh2_reinsert(src, 0, int(passes), frac)
+            res[f"{tag}_p{int(passes)}_f{frac:g}"] = {"depth": int(d_ri), "sah_cost": [c_a, c_b], "host_seconds": round(time.time() - t0, 3)}
+            trees.append((f"{tag} p{int(passes)} f{frac:g}", ri, rtris))
     for tc in a.trav_cost:
         t0 = time.time()
         full, perm, d_full, c_full = B.bvh2_sah_build(rb.reshape(-1, 6), tc)

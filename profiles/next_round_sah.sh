@@ -6,7 +6,7 @@ set -u
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "sah_rebuild" --runxfail 2>&1 | tail -5 > gpurun_out/sah_parity.txt
 for wl in breakfast_1080p_d8 viking_1080sq_d8; do
-  for sah in 0 1 2 3; do
+  for sah in 0 1 2 3 4 5; do
     B200PT_BVH_SAH=$sah timeout 200 python bench.py --workload $wl --steps 10 --warmup 3 2> gpurun_out/sah_${wl}_${sah}.err | tail -1 > gpurun_out/sah_${wl}_${sah}.json
   done
 done

@@ -487,12 +487,12 @@ def test_volume_api_and_traversal_shapes(pt, monkeypatch):
                                         "(test_host_api.py), the end-to-end render has not run on a B200 yet")
 @pytest.mark.parametrize("name,depth", [("viking_room", 8), ("breakfast_room", 8)])
 def test_opt_in_sah_rebuild_returns_the_same_image(pt, name, depth, monkeypatch):
-    """B200PT_BVH_SAH=1 / 2 / 3 (csrc/lbvh.cu: lbvh_refine_sah) only re-arranges the hierarchy above the same triangles: every ray finds the same
+    """B200PT_BVH_SAH=1..5 (csrc/lbvh.cu: lbvh_refine_sah) only re-arranges the hierarchy above the same triangles: every ray finds the same
     closest triangle, so work counters are identical and the image differs at most where two triangles tie at exactly the same distance
     (the first one met wins, and the two trees meet them in a different order)."""
     W, H, frames = 160, 120, 3
     out = {}
-    for sah in ("0", "1", "2", "3"):                                             # 1: inner nodes rebuilt; 2: leaves re-formed as well (slots permuted); 3: + re-insertion
+    for sah in ("0", "1", "2", "3", "4", "5"):                                   # 1: inner nodes rebuilt; 2: leaves re-formed as well (slots permuted); 3: 2 + re-insertion; 4: 1 + re-insertion; 5: re-insertion only
         for wide in ("0", "1"):
             monkeypatch.setenv("B200PT_BVH_SAH", sah); monkeypatch.setenv("B200PT_TRAV", "dyn"); monkeypatch.setenv("B200PT_WIDE", wide)
             T = util.product_tracer(name, W, H, MaxDepth=depth)

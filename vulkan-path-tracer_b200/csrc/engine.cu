@@ -123,8 +123,8 @@ void Engine::upload_scene() {
     CK(cudaMalloc(&d_textures_, dt.size() * sizeof(DevTexture))); CK(cudaMemcpy(d_textures_, dt.data(), dt.size() * sizeof(DevTexture), cudaMemcpyHostToDevice));
     // acceleration structure: GPU LBVH over the flattened instances
     int sah_mode = 0;                                                       // opt-in tree-quality pass; same hits, fewer node visits
-    if (const char *e = getenv("B200PT_BVH_SAH")) sah_mode = (e[0] >= '1' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : 0;
-    int r = lbvh_build(d_verts_, d_indices_, d_meshes_, d_instances_, h_instances_.data(), h_meshes_.data(), (uint32_t)h_instances_.size(), n_tris_, &bvh_, stream_, sah_mode >= 2);
+    if (const char *e = getenv("B200PT_BVH_SAH")) sah_mode = (e[0] >= '1' && e[0] <= '5' && e[1] == 0) ? e[0] - '0' : 0;
+    int r = lbvh_build(d_verts_, d_indices_, d_meshes_, d_instances_, h_instances_.data(), h_meshes_.data(), (uint32_t)h_instances_.size(), n_tris_, &bvh_, stream_, sah_mode == 2 || sah_mode == 3);
     if (r != 0) throw CudaError{ B200PT_ERR_CUDA, std::string("lbvh_build failed: ") + cudaGetErrorString((cudaError_t)r) };
     if (sah_mode) {
         double sah[2];

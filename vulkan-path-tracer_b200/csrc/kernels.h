@@ -54,7 +54,7 @@ uint32_t bvh2_reinsert_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t ro
 // Full binned-SAH build from per-slot reference boxes (n x 6 floats); leaves are re-formed, perm[new slot] = old slot; see lbvh.cu.
 uint32_t bvh2_sah_build_host(const float *ref_boxes, uint32_t n, float trav_cost, BvhNode *out, uint32_t *perm, int *depth, double *sah_cost);
 // mode 1: inner nodes only (download, rebuild, upload in place); mode 2: full build from r->h_ref_box, reference slots and tri_slot permuted
-// (falls back to mode 1 when the boxes were not kept); mode 3: mode 2 + insertion-based refinement.  Returns cudaError_t as int.
+// (falls back to mode 1 when the boxes were not kept); mode 3: mode 2 + insertion-based refinement; 4: mode 1 + refinement; 5: refinement only.  Returns cudaError_t as int.
 int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode = 1);
 // Downloads r->nodes, collapses, uploads r->nodes4 (own allocation).  Returns cudaError_t as int; leaves nodes4 = nullptr if the root is a leaf.
 int lbvh_build_wide(LbvhResult *r, cudaStream_t st);

@@ -707,7 +707,8 @@ int lbvh_build_wide(LbvhResult *r, cudaStream_t st) {
     return 0;
 }
 
-// Opt-in (B200PT_BVH_SAH=1 / 2 / 3; 3 = 2 followed by bvh2_reinsert_host, 3 passes over the largest quarter of the nodes).  Mode 1 rebuilds the inner nodes in place with bvh2_sah_rebuild_host: the live node count is unchanged
+// Opt-in (B200PT_BVH_SAH=1..5; 3 = 2 followed by bvh2_reinsert_host, 3 passes over the largest quarter of the nodes; 4 = 1 followed by the
+// same; 5 = re-insertion alone on the Morton-order tree -- 1, 4 and 5 leave the triangle slots where they are).  Mode 1 rebuilds the inner nodes in place with bvh2_sah_rebuild_host: the live node count is unchanged
 // (leaves - 1), so the rebuilt array fits the existing allocation.  Mode 2 builds from the kept per-slot reference boxes with
 // bvh2_sah_build_host (at most slots - 1 nodes: fits as well), then permutes the 48-B triangle slots to the new leaf order and re-derives
 // tri_slot (global triangle id -> one of its slots) from the ids stored in the slots.  Root becomes 0, max_depth the new depth.
@@ -719,18 +720,19 @@ int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode) {
     LBVH_CHECK(cudaMemcpyAsync(h2.data(), r->nodes, (size_t)r->n_nodes * sizeof(BvhNode), cudaMemcpyDeviceToHost, st));
     LBVH_CHECK(cudaStreamSynchronize(st));
     int depth = 0;
-    auto reinsert = [&](uint32_t n_in, double *cost_after) {                  // mode 3: insertion-based refinement of `out`, result back in `out`
+    auto reinsert = [&](uint32_t n_in, double *cost_after) {                  // modes 3, 4: insertion-based refinement of `out`, result back in `out`
         std::vector<BvhNode> tmp(r->n_nodes); int d2 = 0; double c2[2];
         const uint32_t m = bvh2_reinsert_host(out.data(), n_in, 0, tmp.data(), 3, 0.25f, &d2, c2);
         if (m == n_in) { std::copy(tmp.begin(), tmp.begin() + m, out.begin()); depth = d2; if (cost_after) *cost_after = c2[1]; }
     };
-    if (mode >= 2 && r->h_ref_box && r->n_tris > (uint32_t)LBVH_LEAF_MAX && r->n_tris - 1 <= r->n_nodes) {
+    const bool full = mode == 2 || mode == 3, refine = mode >= 3;
+    if (full && r->h_ref_box && r->n_tris > (uint32_t)LBVH_LEAF_MAX && r->n_tris - 1 <= r->n_nodes) {
         std::vector<uint32_t> perm(r->n_tris);
         double c_new = 0.0, c_old[2] = { 0.0, 0.0 };
         { std::vector<BvhNode> scratch(r->n_nodes); int d; bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, scratch.data(), &d, c_old); }   // cost of the LBVH, for the log
         const uint32_t n = bvh2_sah_build_host(r->h_ref_box, r->n_tris, 1.0f, out.data(), perm.data(), &depth, &c_new);
         if (n != 0) {
-            if (mode >= 3) reinsert(n, &c_new);
+            if (refine) reinsert(n, &c_new);
             std::vector<BvhTri> t_old(r->n_tris), t_new(r->n_tris);
             LBVH_CHECK(cudaMemcpyAsync(t_old.data(), r->tris, (size_t)r->n_tris * sizeof(BvhTri), cudaMemcpyDeviceToHost, st));
             LBVH_CHECK(cudaStreamSynchronize(st));
@@ -749,9 +751,13 @@ int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode) {
             return 0;
         }
     }
-    const uint32_t n = bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, out.data(), &depth, sah);
+    uint32_t n;
+    if (mode == 5) n = bvh2_reinsert_host(h2.data(), r->n_nodes, r->root, out.data(), 3, 0.25f, &depth, sah);   // the Morton-order tree refined directly
+    else {
+        n = bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, out.data(), &depth, sah);
+        if (n != 0 && refine) reinsert(n, sah ? &sah[1] : nullptr);
+    }
     if (n == 0) return 0;
-    if (mode >= 3) reinsert(n, sah ? &sah[1] : nullptr);
     LBVH_CHECK(cudaMemcpyAsync(r->nodes, out.data(), (size_t)n * sizeof(BvhNode), cudaMemcpyHostToDevice, st));
     LBVH_CHECK(cudaStreamSynchronize(st));
     r->root = 0; r->max_depth = depth;
