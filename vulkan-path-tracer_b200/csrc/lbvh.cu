@@ -590,7 +590,8 @@ uint32_t bvh2_reinsert_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t ro
             int best = sib; float best_cost = 3.0e38f;
             heap.clear(); heap.push_back({ -0.0f, root });
             const float na = t[n].area;
-            while (!heap.empty()) {
+            int budget = 8192;                                                  // bounds the search on pathological (heavily overlapping) scenes; any stop leaves a valid tree
+            while (!heap.empty() && budget-- > 0) {
                 std::pop_heap(heap.begin(), heap.end()); const float induced = -heap.back().first; const int x = heap.back().second; heap.pop_back();
                 if (induced + na >= best_cost) break;
                 const float direct = union_area(t[x], t[n]), total = induced + direct;
