@@ -92,7 +92,7 @@ def expand21(x):
     return x
 
 
-def morton_keys(rb, size_class=True):
+def morton_keys(rb, size_class=False):                 # LBVH_SIZE_CLASS is 0 in the product build (profiles/r01_variants.txt: rejected)
     lo, hi = rb[:, 0].min(0), rb[:, 1].max(0)
     ext = hi - lo
     c = 0.5 * (rb[:, 0] + rb[:, 1])
