@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 measurement of the opt-in tree-quality pass (B200PT_BVH_SAH=1): run under gpurun on ONE GPU, e.g.
 #   gpurun --timeout 900 -- 'bash profiles/next_round_sah.sh'
-# Model forecast (profiles/bvh_lab.py, profiles/r01_bvh_lab_*.json): node visits per ray -26..-33 % on BreakfastRoom, -41..-44 % on viking_room.
+# Model forecast (profiles/bvh_lab.py, profiles/r01_bvh_lab_*.json): BVH4 node visits per ray about -40 % on BreakfastRoom, BVH2 -25..-35 % on viking_room.
 set -u
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "sah_rebuild" --runxfail 2>&1 | tail -5 > gpurun_out/sah_parity.txt
