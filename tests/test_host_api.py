@@ -438,6 +438,24 @@ def test_bvh2_sah_build_rejects_degenerate_input():
     assert len(B.bvh2_sah_build(inv)[0]) == 0
 
 
+def test_refine_plumbing_with_cuda_shims(tmp_path):
+    """lbvh_refine_sah (the device-touching half of the opt-in tree passes) run on host arrays: tests/native/refine_plumbing.cpp replaces the
+    three CUDA copy calls by memcpy shims, then checks for modes 0..5 that every ray finds the same closest triangle as brute force, that
+    tri_slot survives the slot permutation of modes 2 / 3, root / max_depth bookkeeping and that a costlier tree is never uploaded."""
+    import shutil, subprocess
+    obj = os.path.join(util.ROOT, "vulkan-path-tracer_b200", "build", "lbvh.o")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(obj) or not os.path.exists(nvcc): pytest.skip("needs nvcc and the built lbvh.o")
+    exe = str(tmp_path / "refine_plumbing")
+    cmd = [nvcc, "--cudart", "shared", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-I" + os.path.join(util.ROOT, "vulkan-path-tracer_b200", "csrc"),
+           "-I" + os.path.join(util.ROOT, "include"), os.path.join(util.ROOT, "tests", "native", "refine_plumbing.cpp"), obj, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count(": ok,") == 36                                          # 6 scenes x modes 0..5
+
+
 def test_volume_struct_and_defaults_without_gpu():
     """b200pt_volume mirrors PathTracer::Volume (PT/PathTracer.h:36-70): layout and defaults are checked on the CPU."""
     import ctypes as C

@@ -732,8 +732,8 @@ int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode) {
         double c_new = 0.0, c_old[2] = { 0.0, 0.0 };
         { std::vector<BvhNode> scratch(r->n_nodes); int d; bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, scratch.data(), &d, c_old); }   // cost of the LBVH, for the log
         const uint32_t n = bvh2_sah_build_host(r->h_ref_box, r->n_tris, 1.0f, out.data(), perm.data(), &depth, &c_new);
-        if (n != 0) {
-            if (refine) reinsert(n, &c_new);
+        if (n != 0 && refine) reinsert(n, &c_new);
+        if (n != 0 && c_new < c_old[0]) {                                       // never trade the tree for a costlier one
             std::vector<BvhTri> t_old(r->n_tris), t_new(r->n_tris);
             LBVH_CHECK(cudaMemcpyAsync(t_old.data(), r->tris, (size_t)r->n_tris * sizeof(BvhTri), cudaMemcpyDeviceToHost, st));
             LBVH_CHECK(cudaStreamSynchronize(st));
@@ -752,13 +752,15 @@ int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode) {
             return 0;
         }
     }
-    uint32_t n;
-    if (mode == 5) n = bvh2_reinsert_host(h2.data(), r->n_nodes, r->root, out.data(), 3, 0.25f, &depth, sah);   // the Morton-order tree refined directly
+    uint32_t n; double cst[2] = { 0.0, 0.0 };
+    if (mode == 5) n = bvh2_reinsert_host(h2.data(), r->n_nodes, r->root, out.data(), 3, 0.25f, &depth, cst);   // the Morton-order tree refined directly
     else {
-        n = bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, out.data(), &depth, sah);
-        if (n != 0 && refine) reinsert(n, sah ? &sah[1] : nullptr);
+        n = bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, out.data(), &depth, cst);
+        if (n != 0 && refine) reinsert(n, &cst[1]);
     }
     if (n == 0) return 0;
+    if (sah) { sah[0] = cst[0]; sah[1] = cst[1] < cst[0] ? cst[1] : cst[0]; }
+    if (!(cst[1] < cst[0])) return 0;                                          // never trade the tree for a costlier one
     LBVH_CHECK(cudaMemcpyAsync(r->nodes, out.data(), (size_t)n * sizeof(BvhNode), cudaMemcpyHostToDevice, st));
     LBVH_CHECK(cudaStreamSynchronize(st));
     r->root = 0; r->max_depth = depth;
