@@ -721,9 +721,11 @@ int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode) {
     LBVH_CHECK(cudaMemcpyAsync(h2.data(), r->nodes, (size_t)r->n_nodes * sizeof(BvhNode), cudaMemcpyDeviceToHost, st));
     LBVH_CHECK(cudaStreamSynchronize(st));
     int depth = 0;
+    int ri_passes = 3; float ri_fraction = 0.25f;                              // B200PT_BVH_RI="passes,fraction" overrides (A/B runs)
+    if (const char *e = getenv("B200PT_BVH_RI")) { int p = 0; float f = 0.0f; if (sscanf(e, "%d,%f", &p, &f) == 2 && p >= 1 && p <= 16 && f > 0.0f && f <= 1.0f) { ri_passes = p; ri_fraction = f; } }
     auto reinsert = [&](uint32_t n_in, double *cost_after) {                  // modes 3, 4: insertion-based refinement of `out`, result back in `out`
         std::vector<BvhNode> tmp(r->n_nodes); int d2 = 0; double c2[2];
-        const uint32_t m = bvh2_reinsert_host(out.data(), n_in, 0, tmp.data(), 3, 0.25f, &d2, c2);
+        const uint32_t m = bvh2_reinsert_host(out.data(), n_in, 0, tmp.data(), ri_passes, ri_fraction, &d2, c2);
         if (m == n_in) { std::copy(tmp.begin(), tmp.begin() + m, out.begin()); depth = d2; if (cost_after) *cost_after = c2[1]; }
     };
     const bool full = mode == 2 || mode == 3, refine = mode >= 3;
@@ -753,7 +755,7 @@ int lbvh_refine_sah(LbvhResult *r, cudaStream_t st, double sah[2], int mode) {
         }
     }
     uint32_t n; double cst[2] = { 0.0, 0.0 };
-    if (mode == 5) n = bvh2_reinsert_host(h2.data(), r->n_nodes, r->root, out.data(), 3, 0.25f, &depth, cst);   // the Morton-order tree refined directly
+    if (mode == 5) n = bvh2_reinsert_host(h2.data(), r->n_nodes, r->root, out.data(), ri_passes, ri_fraction, &depth, cst);   // the Morton-order tree refined directly
     else {
         n = bvh2_sah_rebuild_host(h2.data(), r->n_nodes, r->root, out.data(), &depth, cst);
         if (n != 0 && refine) reinsert(n, &cst[1]);
