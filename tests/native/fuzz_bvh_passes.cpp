@@ -17,7 +17,7 @@ int main() {
     std::mt19937 rng(7);
     std::uniform_real_distribution<float> U(0.f, 1.f);
     for (int iter = 0; iter < 300; iter++) {
-        uint32_t n = 5 + rng() % (iter < 250 ? 400 : 20000);
+        uint32_t n = 5 + rng() % (iter < 250 ? 400 : (iter < 290 ? 20000 : 150000));   // the last ten are large enough for the thread pool of the rebuild
         std::vector<float> rb((size_t)n * 6);
         const int mode = iter % 4;
         for (uint32_t i = 0; i < n; i++) {

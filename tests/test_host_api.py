@@ -438,6 +438,21 @@ def test_bvh2_sah_build_rejects_degenerate_input():
     assert len(B.bvh2_sah_build(inv)[0]) == 0
 
 
+def test_bvh2_sah_rebuild_is_independent_of_the_thread_count(monkeypatch):
+    """The inner-node rebuild forks its large right subtrees onto host threads (node indices are known in advance: k leaves -> k - 1
+    nodes); the emitted array must not depend on how many threads took part."""
+    from vpt_b200 import binding as B
+    rng = np.random.default_rng(77)
+    nodes2, _ = _random_bvh2(40000, rng)
+    outs = []
+    for threads in ("1", "2", "5", "64"):
+        monkeypatch.setenv("B200PT_HOST_THREADS", threads)
+        out, depth, (c0, c1) = B.bvh2_sah_rebuild(nodes2, 0)
+        outs.append((out.tobytes(), depth, c1))
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and o[1] == outs[0][1] and abs(o[2] - outs[0][2]) <= 1e-9 * outs[0][2]
+
+
 def test_refine_plumbing_with_cuda_shims(tmp_path):
     """lbvh_refine_sah (the device-touching half of the opt-in tree passes) run on host arrays: tests/native/refine_plumbing.cpp replaces the
     three CUDA copy calls by memcpy shims, then checks for modes 0..5 that every ray finds the same closest triangle as brute force, that

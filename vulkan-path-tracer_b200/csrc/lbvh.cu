@@ -10,6 +10,10 @@
 //   [ BvhNode x max(N-1,1) | BvhTri x N ]   nodes: 64 B, both child boxes in the parent; tris: 48 B, Morton order.
 #include "kernels.h"
 #include <vector>
+#include <condition_variable>
+#include <mutex>
+#include <functional>
+#include <thread>
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
@@ -489,23 +493,61 @@ uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t
     }
     const uint32_t nl = (uint32_t)leaves.size();
     if (nl < 2 || nl - 1 > n_nodes2) return 0;
-    struct Task { uint32_t b, e; int32_t node; int side; int dep; };       // leaves [b, e) become child `side` of `node` (-1: the root)
-    std::vector<Task> tasks{ { 0, nl, -1, 0, 1 } };
-    uint32_t n_out = 0; int max_d = 1; double cost_out = 0.0;
-    while (!tasks.empty()) {
-        const Task t = tasks.back(); tasks.pop_back();
-        const uint32_t mid = sah_split(leaves, t.b, t.e, nullptr);
-        const uint32_t me = n_out++;
-        if (me >= n_nodes2) return 0;
-        BvhNode &N = out[me]; N._pad[0] = N._pad[1] = 0;
-        sah_bounds(leaves, t.b, mid, N.lo0, N.hi0); sah_bounds(leaves, mid, t.e, N.lo1, N.hi1);
-        if (t.node >= 0) { if (t.side) out[t.node].c1 = (int32_t)me; else out[t.node].c0 = (int32_t)me; }
-        if (t.dep > max_d) max_d = t.dep;
-        if (mid - t.b == 1) { N.c0 = leaves[t.b].ref; cost_out += sah_area(N.lo0, N.hi0) * leaves[t.b].count; } else { cost_out += sah_area(N.lo0, N.hi0); }
-        if (t.e - mid == 1) { N.c1 = leaves[mid].ref; cost_out += sah_area(N.lo1, N.hi1) * leaves[mid].count; } else { cost_out += sah_area(N.lo1, N.hi1); }
-        // right first so that the left subtree is emitted right after its parent (depth-first layout)
-        if (t.e - mid > 1) tasks.push_back({ mid, t.e, (int32_t)me, 1, t.dep + 1 });
-        if (mid - t.b > 1) tasks.push_back({ t.b, mid, (int32_t)me, 0, t.dep + 1 });
+    // A subtree over k leaves emits exactly k - 1 nodes, so every node index is known before its subtree is built: node `me` over [b, e) has its
+    // left child at me + 1 and its right child behind the left subtree.  Ranges of >= 1024 leaves go through a shared queue that a pool of
+    // host threads drains (disjoint leaf ranges, disjoint output ranges); smaller ones are finished by the thread that produced them.
+    // The emitted array does not depend on the thread count or the schedule; cost and depth are taken from it afterwards.
+    struct Range { uint32_t b, e, me; };
+    unsigned n_threads = std::thread::hardware_concurrency(); if (n_threads == 0) n_threads = 1;
+    if (const char *e = getenv("B200PT_HOST_THREADS")) { const int v = atoi(e); if (v >= 1) n_threads = (unsigned)v; }
+    if (n_threads > 64) n_threads = 64;
+    if (nl < 8192) n_threads = 1;
+    std::mutex mtx; std::condition_variable cv; std::vector<Range> shared{ { 0, nl, 0 } }; int active = 0;
+    auto worker = [&]() {
+        std::vector<Range> local;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mtx);
+                cv.wait(lk, [&] { return !shared.empty() || active == 0; });
+                if (shared.empty()) return;                                    // nothing queued and nobody working: done
+                local.push_back(shared.back()); shared.pop_back(); active++;
+            }
+            while (!local.empty()) {
+                const Range t = local.back(); local.pop_back();
+                const uint32_t mid = sah_split(leaves, t.b, t.e, nullptr);
+                BvhNode &N = out[t.me]; N._pad[0] = N._pad[1] = 0;
+                sah_bounds(leaves, t.b, mid, N.lo0, N.hi0); sah_bounds(leaves, mid, t.e, N.lo1, N.hi1);
+                const uint32_t nl_left = mid - t.b, nl_right = t.e - mid, left_me = t.me + 1, right_me = t.me + 1 + (nl_left > 1 ? nl_left - 1 : 0);
+                N.c0 = nl_left == 1 ? leaves[t.b].ref : (int32_t)left_me;
+                N.c1 = nl_right == 1 ? leaves[mid].ref : (int32_t)right_me;
+                const Range kid[2] = { { mid, t.e, right_me }, { t.b, mid, left_me } };   // left last: depth-first within a thread
+                for (const Range &k : kid) {
+                    if (k.e - k.b < 2) continue;
+                    if (n_threads > 1 && k.e - k.b >= 1024) { { std::lock_guard<std::mutex> lk(mtx); shared.push_back(k); } cv.notify_one(); }
+                    else local.push_back(k);
+                }
+            }
+            { std::lock_guard<std::mutex> lk(mtx); active--; }
+            cv.notify_all();
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (unsigned i = 1; i < n_threads; i++) { try { pool.emplace_back(worker); } catch (...) { break; } }   // no thread to be had: fewer workers
+        worker();
+        for (auto &th : pool) th.join();
+    }
+    const uint32_t n_out = nl - 1; int max_d = 1; double cost_out = 0.0;
+    {   // depth and cost of the emitted tree (children follow their parents: one forward sweep)
+        std::vector<int> dep(n_out, 0); dep[0] = 1;
+        for (uint32_t i = 0; i < n_out; i++) {
+            const BvhNode &N = out[i];
+            if (dep[i] > max_d) max_d = dep[i];
+            for (int k = 0; k < 2; k++) {
+                const int32_t c = k ? N.c1 : N.c0; const double a = sah_area(k ? N.lo1 : N.lo0, k ? N.hi1 : N.hi0);
+                if (c >= 0) { dep[c] = dep[i] + 1; cost_out += a; } else cost_out += a * (double)(((uint32_t)(~c) & 3u) + 1u);
+            }
+        }
     }
     if (depth) *depth = max_d;
     if (sah) { float lo[3], hi[3]; sah_bounds(leaves, 0, nl, lo, hi); const double ra = sah_area(lo, hi); sah[0] = ra > 0 ? cost_in / ra : 0.0; sah[1] = ra > 0 ? cost_out / ra : 0.0; }
