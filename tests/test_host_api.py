@@ -450,7 +450,16 @@ def test_bvh2_sah_rebuild_is_independent_of_the_thread_count(monkeypatch):
         out, depth, (c0, c1) = B.bvh2_sah_rebuild(nodes2, 0)
         outs.append((out.tobytes(), depth, c1))
     for o in outs[1:]:
-        assert o[0] == outs[0][0] and o[1] == outs[0][1] and abs(o[2] - outs[0][2]) <= 1e-9 * outs[0][2]
+        assert o[0] == outs[0][0] and o[1] == outs[0][1] and o[2] == outs[0][2]
+    # the full build (leaves re-formed: node blocks are compacted afterwards) as well
+    ctr = rng.random((60000, 3)).astype(np.float32); ext = (0.01 * rng.random((60000, 3))).astype(np.float32)
+    rb = np.concatenate([ctr - ext, ctr + ext], 1)
+    outs = []
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("B200PT_HOST_THREADS", threads)
+        nodes, perm, depth, cost = B.bvh2_sah_build(rb, 1.0)
+        outs.append((nodes.tobytes(), perm.tobytes(), depth, cost))
+    assert outs[1] == outs[0] and outs[2] == outs[0]
 
 
 def test_refine_plumbing_with_cuda_shims(tmp_path):

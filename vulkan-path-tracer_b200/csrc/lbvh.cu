@@ -464,6 +464,68 @@ uint32_t sah_split(std::vector<SahItem> &it, uint32_t b, uint32_t e, double *cos
     if (cost) *cost = best_cost;
     return mid;
 }
+// Top-down build of items [0, n) on a pool of host threads.  A subtree over k items emits at most k - 1 nodes, so node `me` over [b, e) keeps
+// its left subtree in the block starting at me + 1 and its right subtree in the block starting at me + (mid - b): every index is known
+// before the subtree is built, ranges of >= 1024 items go through a shared queue, smaller ones are finished by the thread that produced
+// them (disjoint item ranges, disjoint output blocks).  With `used` == nullptr the blocks are exact (k items -> k - 1 nodes); otherwise
+// used[i] marks the nodes written and the caller compacts the array (block order == depth-first order, so compaction keeps the layout).
+// The result does not depend on the thread count or the schedule.  P: bool leaf(x, y) / int32_t ref(x, y) / void box(x, y, lo, hi).
+template <class P>
+void sah_pool_build(std::vector<SahItem> &it, uint32_t n_items, BvhNode *out, uint8_t *used, P &pol) {
+    struct Range { uint32_t b, e, me; };
+    unsigned n_threads = std::thread::hardware_concurrency(); if (n_threads == 0) n_threads = 1;
+    if (const char *e = getenv("B200PT_HOST_THREADS")) { const int v = atoi(e); if (v >= 1) n_threads = (unsigned)v; }
+    if (n_threads > 64) n_threads = 64;
+    if (n_items < 8192) n_threads = 1;
+    std::mutex mtx; std::condition_variable cv; std::vector<Range> shared{ { 0, n_items, 0 } }; int active = 0;
+    auto worker = [&]() {
+        std::vector<Range> local;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mtx);
+                cv.wait(lk, [&] { return !shared.empty() || active == 0; });
+                if (shared.empty()) return;                                    // nothing queued and nobody working: done
+                local.push_back(shared.back()); shared.pop_back(); active++;
+            }
+            while (!local.empty()) {
+                const Range t = local.back(); local.pop_back();
+                const uint32_t mid = sah_split(it, t.b, t.e, nullptr);
+                BvhNode &N = out[t.me]; N._pad[0] = N._pad[1] = 0;
+                if (used) used[t.me] = 1;
+                pol.box(t.b, mid, N.lo0, N.hi0); pol.box(mid, t.e, N.lo1, N.hi1);
+                const uint32_t left_me = t.me + 1, right_me = t.me + (mid - t.b);
+                const bool left_leaf = pol.leaf(t.b, mid), right_leaf = pol.leaf(mid, t.e);
+                N.c0 = left_leaf ? pol.ref(t.b, mid) : (int32_t)left_me;
+                N.c1 = right_leaf ? pol.ref(mid, t.e) : (int32_t)right_me;
+                const Range kid[2] = { { mid, t.e, right_me }, { t.b, mid, left_me } };   // left last: depth-first within a thread
+                const bool is_leaf[2] = { right_leaf, left_leaf };
+                for (int k = 0; k < 2; k++) {
+                    if (is_leaf[k]) continue;
+                    if (n_threads > 1 && kid[k].e - kid[k].b >= 1024) { { std::lock_guard<std::mutex> lk(mtx); shared.push_back(kid[k]); } cv.notify_one(); }
+                    else local.push_back(kid[k]);
+                }
+            }
+            { std::lock_guard<std::mutex> lk(mtx); active--; }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned i = 1; i < n_threads; i++) { try { pool.emplace_back(worker); } catch (...) { break; } }   // no thread to be had: fewer workers
+    worker();
+    for (auto &th : pool) th.join();
+}
+// depth and SAH cost (unnormalised) of a tree whose children follow their parents: one forward sweep
+void tree_depth_cost(const BvhNode *out, uint32_t n_out, int *max_d, double *cost) {
+    std::vector<int> dep(n_out, 0); dep[0] = 1; *max_d = 1; *cost = 0.0;
+    for (uint32_t i = 0; i < n_out; i++) {
+        const BvhNode &N = out[i];
+        if (dep[i] > *max_d) *max_d = dep[i];
+        for (int k = 0; k < 2; k++) {
+            const int32_t c = k ? N.c1 : N.c0; const double a = sah_area(k ? N.lo1 : N.lo0, k ? N.hi1 : N.hi0);
+            if (c >= 0) { dep[c] = dep[i] + 1; *cost += a; } else *cost += a * (double)(((uint32_t)(~c) & 3u) + 1u);
+        }
+    }
+}
 } // namespace
 
 // Returns the node count (leaves - 1; 0 if the root is a leaf or the input is not a tree), *depth = new depth, sah[0/1] = SAH cost before / after.
@@ -493,62 +555,15 @@ uint32_t bvh2_sah_rebuild_host(const BvhNode *nodes2, uint32_t n_nodes2, int32_t
     }
     const uint32_t nl = (uint32_t)leaves.size();
     if (nl < 2 || nl - 1 > n_nodes2) return 0;
-    // A subtree over k leaves emits exactly k - 1 nodes, so every node index is known before its subtree is built: node `me` over [b, e) has its
-    // left child at me + 1 and its right child behind the left subtree.  Ranges of >= 1024 leaves go through a shared queue that a pool of
-    // host threads drains (disjoint leaf ranges, disjoint output ranges); smaller ones are finished by the thread that produced them.
-    // The emitted array does not depend on the thread count or the schedule; cost and depth are taken from it afterwards.
-    struct Range { uint32_t b, e, me; };
-    unsigned n_threads = std::thread::hardware_concurrency(); if (n_threads == 0) n_threads = 1;
-    if (const char *e = getenv("B200PT_HOST_THREADS")) { const int v = atoi(e); if (v >= 1) n_threads = (unsigned)v; }
-    if (n_threads > 64) n_threads = 64;
-    if (nl < 8192) n_threads = 1;
-    std::mutex mtx; std::condition_variable cv; std::vector<Range> shared{ { 0, nl, 0 } }; int active = 0;
-    auto worker = [&]() {
-        std::vector<Range> local;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mtx);
-                cv.wait(lk, [&] { return !shared.empty() || active == 0; });
-                if (shared.empty()) return;                                    // nothing queued and nobody working: done
-                local.push_back(shared.back()); shared.pop_back(); active++;
-            }
-            while (!local.empty()) {
-                const Range t = local.back(); local.pop_back();
-                const uint32_t mid = sah_split(leaves, t.b, t.e, nullptr);
-                BvhNode &N = out[t.me]; N._pad[0] = N._pad[1] = 0;
-                sah_bounds(leaves, t.b, mid, N.lo0, N.hi0); sah_bounds(leaves, mid, t.e, N.lo1, N.hi1);
-                const uint32_t nl_left = mid - t.b, nl_right = t.e - mid, left_me = t.me + 1, right_me = t.me + 1 + (nl_left > 1 ? nl_left - 1 : 0);
-                N.c0 = nl_left == 1 ? leaves[t.b].ref : (int32_t)left_me;
-                N.c1 = nl_right == 1 ? leaves[mid].ref : (int32_t)right_me;
-                const Range kid[2] = { { mid, t.e, right_me }, { t.b, mid, left_me } };   // left last: depth-first within a thread
-                for (const Range &k : kid) {
-                    if (k.e - k.b < 2) continue;
-                    if (n_threads > 1 && k.e - k.b >= 1024) { { std::lock_guard<std::mutex> lk(mtx); shared.push_back(k); } cv.notify_one(); }
-                    else local.push_back(k);
-                }
-            }
-            { std::lock_guard<std::mutex> lk(mtx); active--; }
-            cv.notify_all();
-        }
-    };
-    {
-        std::vector<std::thread> pool;
-        for (unsigned i = 1; i < n_threads; i++) { try { pool.emplace_back(worker); } catch (...) { break; } }   // no thread to be had: fewer workers
-        worker();
-        for (auto &th : pool) th.join();
-    }
+    struct KeepLeaves {                                                     // the LBVH's leaves stay as they are: k leaves -> exactly k - 1 nodes
+        std::vector<SahItem> &it;
+        bool leaf(uint32_t x, uint32_t y) { return y - x == 1; }
+        int32_t ref(uint32_t x, uint32_t) { return it[x].ref; }
+        void box(uint32_t x, uint32_t y, float *lo, float *hi) { sah_bounds(it, x, y, lo, hi); }
+    } pol{ leaves };
+    sah_pool_build(leaves, nl, out, nullptr, pol);
     const uint32_t n_out = nl - 1; int max_d = 1; double cost_out = 0.0;
-    {   // depth and cost of the emitted tree (children follow their parents: one forward sweep)
-        std::vector<int> dep(n_out, 0); dep[0] = 1;
-        for (uint32_t i = 0; i < n_out; i++) {
-            const BvhNode &N = out[i];
-            if (dep[i] > max_d) max_d = dep[i];
-            for (int k = 0; k < 2; k++) {
-                const int32_t c = k ? N.c1 : N.c0; const double a = sah_area(k ? N.lo1 : N.lo0, k ? N.hi1 : N.hi0);
-                if (c >= 0) { dep[c] = dep[i] + 1; cost_out += a; } else cost_out += a * (double)(((uint32_t)(~c) & 3u) + 1u);
-            }
-        }
-    }
+    tree_depth_cost(out, n_out, &max_d, &cost_out);
     if (depth) *depth = max_d;
     if (sah) { float lo[3], hi[3]; sah_bounds(leaves, 0, nl, lo, hi); const double ra = sah_area(lo, hi); sah[0] = ra > 0 ? cost_in / ra : 0.0; sah[1] = ra > 0 ? cost_out / ra : 0.0; }
     return n_out;
@@ -693,40 +708,39 @@ uint32_t bvh2_sah_build_host(const float *ref_boxes, uint32_t n, float trav_cost
         }
     }
     const float pabs = 2e-6f * ext + 1e-30f;
-    auto padded = [&](uint32_t b, uint32_t e, float lo[3], float hi[3]) {
-        sah_bounds(it, b, e, lo, hi);
-        for (int a = 0; a < 3; a++) { const float p = 4e-7f * fmaxf(fabsf(lo[a]), fabsf(hi[a])) + pabs; lo[a] -= p; hi[a] += p; }
-    };
-    struct Task { uint32_t b, e; int32_t node; int side; int dep; };
-    std::vector<Task> tasks{ { 0, n, -1, 0, 1 } };
-    uint32_t n_out = 0; int max_d = 1; double cost_out = 0.0;
-    while (!tasks.empty()) {
-        const Task t = tasks.back(); tasks.pop_back();
-        const uint32_t mid = sah_split(it, t.b, t.e, nullptr);
-        const uint32_t me = n_out++;
-        if (me + 1 >= n) return 0;
-        BvhNode &N = out[me]; N._pad[0] = N._pad[1] = 0;
-        if (t.node >= 0) { if (t.side) out[t.node].c1 = (int32_t)me; else out[t.node].c0 = (int32_t)me; }
-        if (t.dep > max_d) max_d = t.dep;
-        bool inner[2];
-        for (int s = 0; s < 2; s++) {
-            const uint32_t x = s ? mid : t.b, y = s ? t.e : mid, cnt = y - x;
-            float *lo = s ? N.lo1 : N.lo0, *hi = s ? N.hi1 : N.hi0;
-            padded(x, y, lo, hi);
-            bool leaf = cnt == 1;
-            if (!leaf && cnt <= (uint32_t)LBVH_LEAF_MAX) {                  // small range: leaf unless splitting it is cheaper
-                float rlo[3], rhi[3]; sah_bounds(it, x, y, rlo, rhi);
-                double split_cost; sah_split(it, x, y, &split_cost);         // (reorders inside the range only)
-                const double a = sah_area(rlo, rhi);
-                leaf = (double)cnt * a <= (double)trav_cost * a + split_cost;
-            }
-            inner[s] = !leaf;
-            const double a = sah_area(lo, hi);
-            if (leaf) { (s ? N.c1 : N.c0) = ~(int32_t)((x << 2) | (cnt - 1)); cost_out += a * cnt; } else cost_out += a;
+    struct FormLeaves {                                                     // a range of <= LBVH_LEAF_MAX references stays a leaf unless splitting it is cheaper
+        std::vector<SahItem> &it; float pabs, trav_cost;
+        bool leaf(uint32_t x, uint32_t y) {
+            const uint32_t cnt = y - x;
+            if (cnt == 1) return true;
+            if (cnt > (uint32_t)LBVH_LEAF_MAX) return false;
+            float rlo[3], rhi[3]; sah_bounds(it, x, y, rlo, rhi);
+            double split_cost; sah_split(it, x, y, &split_cost);               // (reorders inside the range only)
+            const double a = sah_area(rlo, rhi);
+            return (double)cnt * a <= (double)trav_cost * a + split_cost;
         }
-        if (inner[1]) tasks.push_back({ mid, t.e, (int32_t)me, 1, t.dep + 1 });
-        if (inner[0]) tasks.push_back({ t.b, mid, (int32_t)me, 0, t.dep + 1 });
+        int32_t ref(uint32_t x, uint32_t y) { return ~(int32_t)((x << 2) | (y - x - 1)); }
+        void box(uint32_t x, uint32_t y, float *lo, float *hi) {
+            sah_bounds(it, x, y, lo, hi);
+            for (int a = 0; a < 3; a++) { const float p = 4e-7f * fmaxf(fabsf(lo[a]), fabsf(hi[a])) + pabs; lo[a] -= p; hi[a] += p; }
+        }
+    } pol{ it, pabs, trav_cost };
+    std::vector<uint8_t> used(n - 1, 0);
+    sah_pool_build(it, n, out, used.data(), pol);
+    uint32_t n_out = 0;
+    {   // compact the blocks (ascending index == depth-first order) and renumber the children
+        std::vector<uint32_t> remap(n - 1, 0);
+        for (uint32_t i = 0; i + 1 < n; i++) if (used[i]) remap[i] = n_out++;
+        for (uint32_t i = 0; i + 1 < n; i++) {
+            if (!used[i]) continue;
+            BvhNode N = out[i];
+            if (N.c0 >= 0) N.c0 = (int32_t)remap[N.c0];
+            if (N.c1 >= 0) N.c1 = (int32_t)remap[N.c1];
+            out[remap[i]] = N;                                                   // remap[i] <= i: never overwrites a node still to be moved
+        }
     }
+    int max_d = 1; double cost_out = 0.0;
+    tree_depth_cost(out, n_out, &max_d, &cost_out);
     for (uint32_t i = 0; i < n; i++) perm[i] = (uint32_t)it[i].ref;
     if (depth) *depth = max_d;
     if (sah_cost) { float lo[3], hi[3]; sah_bounds(it, 0, n, lo, hi); const double ra = sah_area(lo, hi); *sah_cost = ra > 0 ? cost_out / ra : 0.0; }
