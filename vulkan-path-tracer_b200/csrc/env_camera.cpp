@@ -123,11 +123,13 @@ uint32_t bloom_mip_sizes(uint32_t W, uint32_t H, uint32_t wh[20]) {
 }
 
 uint32_t partition_global_row(uint32_t local_row, uint32_t rank, uint32_t world, uint32_t band) {
-    if (!world) world = 1; if (!band) band = 1;
+    if (!world) world = 1;
+    if (!band) band = 1;
     return ((local_row / band) * world + rank) * band + local_row % band;
 }
 uint32_t partition_local_rows(uint32_t H, uint32_t rank, uint32_t world, uint32_t band) {
-    if (!world) world = 1; if (!band) band = 1;
+    if (!world) world = 1;
+    if (!band) band = 1;
     uint32_t n = 0;
     for (uint32_t y0 = rank * band; y0 < H; y0 += world * band) n += std::min(band, H - y0);
     return n;

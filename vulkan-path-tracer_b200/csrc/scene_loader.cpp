@@ -544,7 +544,9 @@ bool load_obj_scene(const std::string &path, HostScene &sc, std::string &err) {
                     else num.push_back(c);
                 }
                 const int nv = (int)(P.size() / 3), nt = (int)(T.size() / 2), nn = (int)(N.size() / 3);
-                if (key.v < 0) key.v = nv + key.v + 1; if (key.t < 0) key.t = nt + key.t + 1; if (key.n < 0) key.n = nn + key.n + 1;
+                if (key.v < 0) key.v = nv + key.v + 1;
+                if (key.t < 0) key.t = nt + key.t + 1;
+                if (key.n < 0) key.n = nn + key.n + 1;
                 if (key.v < 1 || key.v > nv || key.t > nt || key.n > nn) { err = "OBJ face index out of range"; return false; }
                 fv.push_back(key);
             }
