@@ -66,7 +66,7 @@ def test_png_roundtrip_and_decoder_vs_pil(tmp_path):
         assert np.array_equal(pt.decode_image(q), np.asarray(Image.open(q).convert("RGBA")))
     q = str(tmp_path / "pal.png"); Image.fromarray(img[..., :3], "RGB").quantize(17).save(q)
     assert np.array_equal(pt.decode_image(q), np.asarray(Image.open(q).convert("RGBA")))
-    q = str(tmp_path / "i16.png"); Image.fromarray((img[..., 0].astype(np.uint16) << 8) | 7, "I;16").save(q)
+    q = str(tmp_path / "i16.png"); Image.fromarray((img[..., 0].astype(np.uint16) << 8) | 7).save(q)     # uint16 -> mode "I;16"
     assert np.array_equal(pt.decode_image(q)[..., 0], img[..., 0])          # 16 -> 8 keeps the high byte
 
 
