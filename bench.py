@@ -352,6 +352,10 @@ def main():
     dprof = diff_counters(ca, cb)
     kms = {k: cb["ms_" + k] for k in ("raygen", "extend", "shade", "connect", "resolve")}
     ab = algorithmic_bytes(dprof)
+    fused = kms["connect"] == 0.0 and dprof["shadow_rays"] > 0      # fused bounce kernel (k_shade_hit<CLASS, ., 2>): shade + NEE queries + epilogue + next TraceRay
+    if fused:                                                        # its algorithmic bytes = the three per-bounce stages it replaces (SURVEY 8d model unchanged)
+        ab["shade"] = ab["shade"] + ab["connect"] + 44 * max(dprof["extend_rays"] - dprof["paths"], 0)
+        ab["extend"] = 44 * dprof["paths"]; ab["connect"] = 0
     dom = max(kms, key=lambda k: kms[k])
     n_launch = {"raygen": cb["waves"], "resolve": cb["waves"]}
     launches_dom = n_launch.get(dom, cb["bounces"])
@@ -360,7 +364,7 @@ def main():
     seg_per_path = dprof["extend_rays"] / max(dprof["paths"], 1)
     pipeline_bytes = ab["total"]
     step_ms_prof = sum(kms.values())
-    kname = {"shade": "k_shade_hit (+k_shade_miss)", "extend": "k_extend", "connect": "k_connect", "raygen": "k_raygen", "resolve": "k_resolve"}[dom]
+    kname = {"shade": "k_shade_hit<CLASS,.,2> fused bounce kernel: shade + NEE queries + roulette + next TraceRay (+k_shade_miss)" if fused else "k_shade_hit<CLASS> (+k_shade_miss)", "extend": "k_extend", "connect": "k_connect", "raygen": "k_raygen", "resolve": "k_resolve"}[dom]
     traffic = None                                # DRAM bytes per launch of that kernel from the committed ncu --set full capture, if any
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))

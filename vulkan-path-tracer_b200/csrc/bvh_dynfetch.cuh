@@ -32,7 +32,7 @@ constexpr int DYN_SPILL = 96;                       // overflow entries behind t
 __device__ __forceinline__ void dyn_init(DynRay &r, float3 o, float3 d, float tmin, float tmax, float tmax_test, uint32_t target,
                                          int root, uint32_t s_base, uint32_t s_step) {
     r.o = o; r.d = d;
-    r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.inv = f3(slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z));
     r.oi = f3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
     r.tmin = tmin; r.tmax = tmax; r.tmax_test = tmax_test;
     r.t = tmax; r.u = 0.0f; r.v = 0.0f; r.gid = DYN_NONE; r.target = target;

@@ -79,6 +79,11 @@ __device__ __forceinline__ float3 normalize_ray(float3 a) {
 #endif
     return f3(__fmul_rn(a.x, inv), __fmul_rn(a.y, inv), __fmul_rn(a.z, inv));
 }
+// Reciprocal of a ray-direction component for the slab tests.  A component that is exactly 0 (axis-aligned NEE / mirror directions) would give
+// inv = inf, and the FMA slab form n*inv - o*inv then evaluates inf - inf = NaN for a box that straddles the origin on that axis: fmaxf/fminf drop
+// the NaN and the subtree is culled (a false miss).  |d| < 1e-30 is replaced by copysign(1e-30, d): every plane distance stays finite or a
+// correctly signed infinity (|n|, |o| < 3e8), the slab interval is unchanged for all practical purposes; the triangle test keeps the exact d.
+__device__ __forceinline__ float slab_rcp(float d) { return 1.0f / (fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d); }
 __device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3 o, float3 d, float tmin, float tmax, float &t, float &u, float &v) {
     const float3 p = cross_fma(d, e2);
     const float det = dot_fma(e1, p);
@@ -105,12 +110,14 @@ __device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3
 template <bool SMEM, bool ANYHIT, bool COUNT = false, bool TARGET = false, bool FMA_SLABS = false>
 __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, float tmin, float tmax, HitRec &h,
                                           int *stack, int stride, int max_stack, uint32_t *n_nodes = nullptr, uint32_t *n_tris = nullptr,
-                                          uint32_t target_gid = 0xFFFFFFFFu) {
-    const float tmax_test = TARGET ? __uint_as_float(__float_as_uint(tmax) + 1u) : tmax;   // TARGET: admit t == tmax (tmax > 0)
+                                          uint32_t target_gid = 0xFFFFFFFFu, float tmax_test_in = -1.0f) {
+    // TARGET: admit t == tmax (tmax > 0).  A caller that serves both query kinds with one copy of this loop (k_shade_hit<.., FUSE>) passes the
+    // acceptance bound itself: nextafter(tL) for a light ray, tmax for a sky ray (whose target 0xFFFFFFFF makes every t < tmax an occluder).
+    const float tmax_test = TARGET ? (tmax_test_in >= 0.0f ? tmax_test_in : __uint_as_float(__float_as_uint(tmax) + 1u)) : tmax;
     h.slot = 0xFFFFFFFFu; h.gid = 0xFFFFFFFFu; h.t = tmax; h.u = 0.0f; h.v = 0.0f;
     uint32_t best_gid = 0xFFFFFFFFu;
     bool found = false;
-    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float3 inv = f3(slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z));
     const float3 oi = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
     const uint32_t s_base = smem_u32(stack), s_step = (uint32_t)stride * 4u, s_limit = s_base + (uint32_t)max_stack * s_step;
     uint32_t s_top = s_base;                                               // address of the next free stack entry

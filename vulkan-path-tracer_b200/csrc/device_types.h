@@ -109,6 +109,7 @@ struct DevScene {
     const float2 *env_row_cos;     // per env-map row py: { cos(py*stepTheta), cos(py*stepTheta + stepTheta) } (SH/Sampler.slang:329-331), host-evaluated
     const float *lut_reflect, *lut_refract_out, *lut_refract_in;
     const uint32_t *tri_slot;      // global triangle id -> one of its BvhTri slots (light-ray visibility test in k_connect)
+    const uint8_t *tri_class;      // global triangle id -> shading class of its material (MaterialClass): selects the hit queue / k_shade_hit instantiation
     const BvhNode *nodes;
     const Bvh4Node *nodes4;        // BVH4 collapse of `nodes` (nullptr when the scene is traversed as BVH2), root = node 0
     const BvhTri *tris;
@@ -122,6 +123,22 @@ struct DevScene {
     uint32_t bvh_bytes;      // nodes+tris size if they are contiguous and small enough to stage in smem, else 0
     uint32_t _pad;
 };
+
+// Shading classes = the lobe sets of SH/Material.slang:169-177 that a material can ever sample or evaluate.  The lobe probabilities are
+// pm = Metallic, pd = (1-Metallic)(1-Transmission), pg = (1-Metallic)Transmission (normalised); when the metallic texture is 1x1 they are
+// per-material constants, and for the three pure cases two of them are EXACTLY 0, so the corresponding lobe code contributes exact zeros and
+// can be compiled out of that class's kernel (k_shade_hit<CLASS>).  k_extend sorts hits into one queue per class (material-sorted shading).
+enum MaterialClass : uint32_t { MC_DIFFUSE = 0,   // Metallic*texel == 0 and Transmission == 0: diffuse + dielectric specular
+                                MC_METAL = 1,     // Metallic*texel == 1: metallic lobe only
+                                MC_GLASS = 2,     // Metallic*texel == 0 and Transmission == 1: glass reflect + refract
+                                MC_GENERAL = 3,   // anything else (mixed lobes, textured metallic)
+                                MC_COUNT = 4 };
+// Control block (u32 words): [0],[1] live-path counts by bounce parity p; [8+p] / [10+p] fetch counters of k_extend_dyn / k_shadow_dyn;
+// [CTRL_Q + 8p + 0] miss-queue length, [CTRL_Q + 8p + 1 + c] hit-queue length of class c for a bounce of parity p.
+constexpr uint32_t CTRL_Q = 16u, CTRL_WORDS = 32u;
+constexpr uint32_t Q_NONE = 7u;   // queue code of an inactive lane
+// The hit / miss queues of one bounce: entries are indices into the dense PathState arrays.  Class c owns hit[c * cap .. c * cap + count_c).
+struct Queues { uint32_t *miss; uint32_t *hit; uint32_t cap; };
 
 struct DevConfig {          // PT/PathTracer.h:271-302 (the fields the surface integrator reads)
     float VI[16], PI[16];

@@ -31,7 +31,7 @@ Engine::Engine(int device) : device_(device) {
     for (int i = 0; i < 4; i++) view_inv_[i * 5] = proj_inv_[i * 5] = 1.0f;
     CK(cudaMalloc(&d_ctr_, sizeof(WaveCounters)));
     CK(cudaMemset(d_ctr_, 0, sizeof(WaveCounters)));
-    CK(cudaMalloc(&d_counts_, 16 * sizeof(uint32_t)));
+    CK(cudaMalloc(&d_counts_, CTRL_WORDS * sizeof(uint32_t)));
     CK(cudaMallocHost(&h_count_, 4 * sizeof(uint32_t)));
     memset(&last_, 0, sizeof last_);
 }
@@ -41,7 +41,7 @@ Engine::~Engine() {
     if (stream_) cudaStreamSynchronize(stream_);
     free_scene(); free_wave(); free_post();
     dfree(d_env_); dfree(d_alias_); dfree(d_env_row_cos_); for (auto &l : d_luts_) dfree(l);
-    dfree(d_image_); dfree(d_ctr_); dfree(d_counts_); dfree(d_volumes_);
+    dfree(d_image_); dfree(d_ctr_); dfree(d_counts_); dfree(d_volumes_); dfree(d_tri_class_);
     if (h_count_) cudaFreeHost(h_count_);
     if (ev_[0]) cudaEventDestroy(ev_[0]); if (ev_[1]) cudaEventDestroy(ev_[1]);
     for (auto &e : prof_ev_) cudaEventDestroy(e);
@@ -50,7 +50,7 @@ Engine::~Engine() {
 }
 
 void Engine::free_scene() {
-    dfree(d_verts_); dfree(d_indices_); dfree(d_meshes_); dfree(d_instances_); dfree(d_materials_); dfree(d_textures_); dfree(d_emissive_); dfree(d_em_tris_); dfree(d_em_tri_base_);
+    dfree(d_verts_); dfree(d_indices_); dfree(d_meshes_); dfree(d_instances_); dfree(d_materials_); dfree(d_textures_); dfree(d_emissive_); dfree(d_em_tris_); dfree(d_em_tri_base_); dfree(d_tri_class_);
     for (auto &p : d_texdata_) if (p) cudaFree(p);
     d_texdata_.clear();
     lbvh_free(&bvh_);
@@ -122,8 +122,11 @@ void Engine::upload_scene() {
     }
     CK(cudaMalloc(&d_textures_, dt.size() * sizeof(DevTexture))); CK(cudaMemcpy(d_textures_, dt.data(), dt.size() * sizeof(DevTexture), cudaMemcpyHostToDevice));
     // acceleration structure: GPU LBVH over the flattened instances
-    int sah_mode = 0;                                                       // opt-in tree-quality pass; same hits, fewer node visits
-    if (const char *e = getenv("B200PT_BVH_SAH")) sah_mode = (e[0] >= '1' && e[0] <= '5' && e[1] == 0) ? e[0] - '0' : 0;
+    // tree-quality pass over the GPU LBVH: same hits, fewer node visits / triangle tests.  Level 3 (full binned-SAH build + insertion-based
+    // refinement) measured best on every workload (profiles/r02_sah_levels.txt: BreakfastRoom +12 %, viking_room +28 %, glass +11 %, Cornell +5 %);
+    // B200PT_BVH_SAH=0..5 overrides (0 = plain LBVH).
+    int sah_mode = 3;
+    if (const char *e = getenv("B200PT_BVH_SAH")) sah_mode = (e[0] >= '0' && e[0] <= '5' && e[1] == 0) ? e[0] - '0' : 3;
     int r = lbvh_build(d_verts_, d_indices_, d_meshes_, d_instances_, h_instances_.data(), h_meshes_.data(), (uint32_t)h_instances_.size(), n_tris_, &bvh_, stream_, sah_mode == 2 || sah_mode == 3);
     if (r != 0) throw CudaError{ B200PT_ERR_CUDA, std::string("lbvh_build failed: ") + cudaGetErrorString((cudaError_t)r) };
     if (sah_mode) {
@@ -133,6 +136,8 @@ void Engine::upload_scene() {
         if (getenv("B200PT_DEBUG")) fprintf(stderr, "[b200pt] SAH pass (mode %d): cost %.3f -> %.3f, depth %d\n", sah_mode, sah[0], sah[1], bvh_.max_depth);
     }
     ds_.verts = d_verts_; ds_.indices = d_indices_; ds_.meshes = d_meshes_; ds_.instances = d_instances_; ds_.materials = d_materials_;
+    CK(cudaMalloc(&d_tri_class_, std::max<size_t>(1, n_tris_)));
+    rebuild_tri_class();
     ds_.textures = d_textures_; ds_.emissive = d_emissive_; ds_.nodes = bvh_.nodes; ds_.tris = bvh_.tris; ds_.shade_tris = bvh_.shade; ds_.tri_slot = bvh_.tri_slot;
     ds_.n_tris = bvh_.n_tris; ds_.n_nodes = bvh_.n_nodes; ds_.root = bvh_.root; ds_.bvh_bytes = bvh_.bytes <= 0xFFFFFFFFull ? (uint32_t)bvh_.bytes : 0;
     ds_.nodes4 = nullptr;
@@ -164,6 +169,30 @@ DevMaterial Engine::make_dev_material(const b200pt_material &m) const {
     if (texel(m.MetallicTextureIndex, v)) { d.const_mask |= 8u; d.cmetal = v.x; }
     if (texel(m.EmissiveTextureIndex, v)) { d.const_mask |= 16u; d.cemis = v; }
     return d;
+}
+
+// Shading class of every triangle (device_types.h: MaterialClass): decides the hit queue k_extend appends to and the k_shade_hit<CLASS>
+// instantiation that shades it.  Uses the same products the device evaluates (Metallic * texel, material_apply_texels in shading.cuh).
+void Engine::rebuild_tri_class() {
+    std::vector<uint8_t> cls(scene_.materials.size(), (uint8_t)MC_GENERAL);
+    for (size_t i = 0; i < scene_.materials.size(); i++) {
+        const DevMaterial dm = make_dev_material(scene_.materials[i]);
+        if (!(dm.const_mask & 8u)) continue;                                // metallic texture is not 1x1: the lobe set depends on the texel
+        const float metal = dm.m.Metallic * dm.cmetal, T = dm.m.Transmission;
+        if (metal == 1.0f) cls[i] = (uint8_t)MC_METAL;
+        else if (metal == 0.0f && T == 0.0f) cls[i] = (uint8_t)MC_DIFFUSE;
+        else if (metal == 0.0f && T == 1.0f) cls[i] = (uint8_t)MC_GLASS;
+    }
+    if (const char *e = getenv("B200PT_CLASSES")) { if (atoi(e) == 0) std::fill(cls.begin(), cls.end(), (uint8_t)MC_GENERAL); }   // A/B: one general queue
+    std::vector<uint8_t> tc(std::max<size_t>(1, n_tris_), (uint8_t)MC_GENERAL);
+    class_mask_ = 0;
+    for (size_t i = 0; i < scene_.instances.size(); i++) {
+        const uint8_t c = cls[scene_.instances[i].MaterialIndex];
+        const uint32_t first = h_instances_[i].tri_base, cnt = h_meshes_[scene_.instances[i].MeshIndex].tri_count;
+        if (cnt) { class_mask_ |= 1u << c; std::fill(tc.begin() + first, tc.begin() + first + cnt, c); }
+    }
+    CK(cudaMemcpy(d_tri_class_, tc.data(), tc.size(), cudaMemcpyHostToDevice));
+    ds_.tri_class = d_tri_class_;
 }
 
 // emissive-mesh list: PathTracer.cpp:458-469 (+ SetMaterial maintenance :712-810); keyed on constant EmissiveColor != 0 (Q16)
@@ -222,6 +251,7 @@ void Engine::set_material(uint32_t idx, const b200pt_material &m) {
     scene_.materials[idx] = m;
     { const DevMaterial dm = make_dev_material(m); CK(cudaMemcpy(d_materials_ + idx, &dm, sizeof dm, cudaMemcpyHostToDevice)); launch_prepare_materials(d_materials_, idx, 1, stream_); CK(cudaStreamSynchronize(stream_)); }
     rebuild_emissive();
+    rebuild_tri_class();
     reset();
 }
 
@@ -336,7 +366,7 @@ void Engine::ensure_image() {
 void Engine::free_wave() {
     for (auto &p : ps_) { dfree(p.org_pdf); dfree(p.dir_rng); dfree(p.thr_depth); dfree(p.rad_slot); dfree(p.medium); dfree(p.medium_g); dfree(p.vol_depth); }
     dfree(so_.hit); dfree(so_.bxdf_pdf); dfree(so_.e0); dfree(so_.sky_o); dfree(so_.sky_d); dfree(so_.sky_c); dfree(so_.lit_o); dfree(so_.lit_d); dfree(so_.lit_c);
-    dfree(d_sample_buf_); dfree(d_rng_carry_); dfree(d_q_hit_); dfree(d_q_miss_); dfree(d_disp_[0]); dfree(d_disp_[1]);
+    dfree(d_sample_buf_); dfree(d_rng_carry_); dfree(d_q_hit_[0]); dfree(d_q_hit_[1]); dfree(d_q_miss_[0]); dfree(d_q_miss_[1]); dfree(d_disp_[0]); dfree(d_disp_[1]);
     for (auto &hp : h_disp_) if (hp) { cudaFreeHost(hp); hp = nullptr; }
     wave_cap_ = 0;
 }
@@ -349,7 +379,7 @@ void Engine::ensure_wave(size_t cap) {
     a4(so_.hit); a4(so_.bxdf_pdf); a4(so_.e0); a4(so_.sky_o); a4(so_.sky_d); a4(so_.sky_c); a4(so_.lit_o); a4(so_.lit_d); a4(so_.lit_c);
     a4(d_sample_buf_);
     CK(cudaMalloc(&d_rng_carry_, cap * sizeof(uint32_t)));
-    CK(cudaMalloc(&d_q_hit_, cap * sizeof(uint32_t))); CK(cudaMalloc(&d_q_miss_, cap * sizeof(uint32_t)));
+    for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_q_hit_[i], (size_t)MC_COUNT * cap * sizeof(uint32_t))); CK(cudaMalloc(&d_q_miss_[i], cap * sizeof(uint32_t))); }   // one hit queue per material class, ping-pong for the fused bounce kernel
     for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); CK(cudaMallocHost(&h_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); }
     wave_cap_ = cap;
 }
@@ -409,7 +439,17 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     PathState pst[2] = { ps_[0], ps_[1] };                    // payload.VolumeDepth travels only while the scene has volumes
     if (!n_vol) { pst[0].vol_depth = nullptr; pst[1].vol_depth = nullptr; }
     bool medium = false;                                      // can a path random-walk inside a mesh without gaining Depth?
-    for (const auto &m : scene_.materials) if (m.Transmission > 0.0f && m.Metallic < 1.0f && m.MediumDensity > 0.0f && m.MediumAnisotropy != 1.0f) medium = true;
+    // Conservative: the device-side metallic value is Metallic * texel, so the constant factor alone cannot rule refraction out, and a negative
+    // density (not validated by the reference either) scatters on every segment.  A false positive only costs a 4-byte read-back per 16 bounces.
+    for (const auto &m : scene_.materials) if (m.Transmission > 0.0f && m.MediumDensity != 0.0f && m.MediumAnisotropy != 1.0f) medium = true;
+
+    // Fused bounce kernels (LaunchCfg::fuse) need the BVH in shared memory and no volumes; they ping-pong the queues and the hit records
+    // (the kernel that consumes bounce k's queue fills bounce k+1's), the unfused pipeline uses buffer 0 only.
+    const int fuse = n_vol ? 0 : lc_.fuse;
+    const uint32_t cmask = n_vol ? (class_mask_ | (1u << MC_GENERAL)) : class_mask_;   // volume events ride in the general queue
+    const uint32_t qcap = (uint32_t)wave_cap_;
+    const int qsel[2] = { 0, fuse == 2 ? 1 : 0 };
+    float4 *const hitb[2] = { so_.hit, fuse == 2 ? so_.bxdf_pdf : so_.hit };
 
     CK(cudaEventRecord(ev_[0], stream_));
     uint64_t launches = 0; uint32_t waves = 0, bounces_total = 0;
@@ -431,11 +471,14 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                 if (!medium && cfg_.MaxDepth - std::min(cfg_.MaxDepth, k) < chunk) chunk = cfg_.MaxDepth - std::min(cfg_.MaxDepth, k);
                 if (chunk == 0) break;
                 for (uint32_t b = 0; b < chunk; b++, k++) {
-                    if (n_vol) { launch_volume_decide(lc_, ds_, pst[cur], so_, d_counts_, k & 1u, stream_); launches += 2; }   // + k_shade_volume
-                    launch_extend(lc_, ds_, pst[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_ctr_, k == 0, stream_); mark(1);
-                    launch_shade(lc_, ds_, dc, pst[cur], so_, d_counts_, k & 1u, d_q_hit_, d_q_miss_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(2);
-                    launch_connect(lc_, ds_, dc, pst[cur], pst[cur ^ 1], so_, d_counts_, k & 1u, d_q_hit_, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); mark(3);
-                    cur ^= 1; launches += lc_.trav_dyn ? 5 : 4;
+                    const uint32_t par = k & 1u;
+                    const Queues qc{ d_q_miss_[qsel[par]], d_q_hit_[qsel[par]], qcap }, qn{ d_q_miss_[qsel[par ^ 1u]], d_q_hit_[qsel[par ^ 1u]], qcap };
+                    if (n_vol) { launch_volume_decide(lc_, ds_, pst[cur], so_, d_counts_, par, stream_); launches++; }
+                    if (fuse != 2 || k == 0) { launch_extend(lc_, ds_, pst[cur], hitb[par], d_counts_, par, qc, d_ctr_, k == 0, stream_); launches++; } mark(1);
+                    launches += launch_shade(lc_, ds_, dc, pst[cur], pst[cur ^ 1], so_, hitb[par], hitb[par ^ 1u], d_counts_, par, qc, qn, d_sample_buf_, d_rng_carry_, d_ctr_,
+                                             fuse, cmask, stream_); mark(2);
+                    if (!fuse) { launch_connect(lc_, ds_, dc, pst[cur], pst[cur ^ 1], so_, d_counts_, par, qc, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); launches += lc_.trav_dyn ? 2 : 1; } mark(3);
+                    cur ^= 1;
                 }
                 if (!medium && k >= cfg_.MaxDepth) break;    // every surviving path has Depth >= MaxDepth: provably empty
                 CK(cudaMemcpyAsync(h_count_, d_counts_ + (k & 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));

@@ -71,6 +71,7 @@ private:
     void free_scene();
     void upload_scene();
     void rebuild_emissive();
+    void rebuild_tri_class();                       // per-triangle shading class (MaterialClass) + the set of classes present in the scene
     void upload_volumes();
     DevMaterial make_dev_material(const b200pt_material &m) const;
     void ensure_image();
@@ -107,6 +108,7 @@ private:
     LbvhResult bvh_{};
     LaunchCfg lc_{};
     uint32_t n_tris_ = 0, n_emissive_ = 0;
+    uint8_t *d_tri_class_ = nullptr; uint32_t class_mask_ = 0;   // bit c: some triangle's material is of MaterialClass c
 
     // framebuffer + post
     float4 *d_image_ = nullptr; size_t image_pixels_ = 0;
@@ -118,7 +120,7 @@ private:
     // wave buffers
     size_t wave_cap_ = 0;
     PathState ps_[2]{}; ShadeOut so_{};
-    float4 *d_sample_buf_ = nullptr; uint32_t *d_rng_carry_ = nullptr; uint32_t *d_q_hit_ = nullptr, *d_q_miss_ = nullptr; uint32_t *d_counts_ = nullptr; DevDispatch *d_disp_[2] = { nullptr, nullptr };
+    float4 *d_sample_buf_ = nullptr; uint32_t *d_rng_carry_ = nullptr; uint32_t *d_q_hit_[2] = { nullptr, nullptr }, *d_q_miss_[2] = { nullptr, nullptr }; uint32_t *d_counts_ = nullptr; DevDispatch *d_disp_[2] = { nullptr, nullptr };
     DevDispatch *h_disp_[2] = { nullptr, nullptr }; uint32_t *h_count_ = nullptr;
     WaveCounters *d_ctr_ = nullptr;
     b200pt_counters last_{};

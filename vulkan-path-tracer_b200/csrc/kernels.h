@@ -17,18 +17,23 @@ struct LaunchCfg {
     int grid_shadow;    // persistent grid of k_shadow_dyn
     bool wide;          // the dynamic-fetch kernels walk the BVH4 (DevScene::nodes4)
     int dyn_stack;      // shared-memory stack entries per thread of the dynamic-fetch kernels (BVH4: overflow goes to local memory)
+    int fuse;           // 0: k_shade_hit + k_connect; 1: NEE queries + path epilogue inside k_shade_hit; 2: + the next segment's TraceRay (one kernel per bounce and class)
+    int grid_bounce;    // persistent grid of the fused k_shade_hit instantiations (BVH + stacks in shared memory)
 };
 
 int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, LaunchCfg *lc);
 void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P, uint32_t first_sample,
                    const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *ctrl, WaveCounters *ctr, cudaStream_t st);
-void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, uint32_t *ctrl, uint32_t parity, uint32_t *q_hit, uint32_t *q_miss,
+void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, float4 *hit_out, uint32_t *ctrl, uint32_t parity, Queues q,
                    WaveCounters *ctr, bool primary, cudaStream_t st);
-void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity,
-                  const uint32_t *q_hit, const uint32_t *q_miss, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st);      // k_shade_miss + k_shade_hit
+// k_shade_miss + k_shade_hit<CLASS> for every class in class_mask (+ k_shade_volume); returns the number of kernels launched.
+// fuse != 0: the bounce is finished inside k_shade_hit (dst, q_next, hit_out are written), launch_connect is not called.
+int launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, PathState dst, ShadeOut so, const float4 *hit_in, float4 *hit_out,
+                 uint32_t *ctrl, uint32_t parity, Queues q, Queues q_next, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr,
+                 int fuse, uint32_t class_mask, cudaStream_t st);
 void launch_volume_decide(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity, cudaStream_t st);   // before launch_extend when the scene has volumes
 void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,
-                    uint32_t *ctrl, uint32_t parity, const uint32_t *q_hit, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st);
+                    uint32_t *ctrl, uint32_t parity, Queues q, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st);
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
                     const float4 *sample_buf, float4 *image, cudaStream_t st);
 void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, const float *org, const float *dir, float tmin, float tmax,

@@ -41,10 +41,12 @@ __device__ __forceinline__ float3 xf_point_rn(const float *m, float x, float y, 
 }
 
 __device__ __forceinline__ void atomic_min_f(float *addr, float v) {   // works for any sign via ordered ints
+    v += 0.0f;                                                           // -0.0 -> +0.0: its bit pattern (INT_MIN) would win every signed atomicMin
     if (v >= 0.0f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
     else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
 __device__ __forceinline__ void atomic_max_f(float *addr, float v) {
+    v += 0.0f;
     if (v >= 0.0f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
     else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }

@@ -225,19 +225,27 @@ bool load_gltf_scene(const std::string &path, HostScene &sc, std::string &err) {
     auto accessor = [&](int idx, int want_comps, std::vector<float> *fout, std::vector<uint32_t> *uout, size_t &count) -> bool {
         if (!accs || !views || idx < 0 || (size_t)idx >= accs->size()) { err = "bad accessor index"; return false; }
         const JVal &a = (*accs)[idx];
-        int ct = (int)a.num("componentType", 0); count = (size_t)a.num("count", 0);
+        auto to_sz = [](double v) { return (v >= 0.0 && v < 4294967296.0) ? (size_t)v : (size_t)-1; };   // untrusted JSON numbers: no UB casts, no 64-bit wrap
+        int ct = (int)a.num("componentType", 0); count = to_sz(a.num("count", 0));
+        if (count == (size_t)-1) { err = "bad accessor count"; return false; }
         const JVal *ty = a.get("type"); if (!ty) { err = "accessor without type"; return false; }
         int nc = ty->s == "SCALAR" ? 1 : ty->s == "VEC2" ? 2 : ty->s == "VEC3" ? 3 : ty->s == "VEC4" ? 4 : 0;
         if (nc != want_comps) { err = "unexpected accessor type " + ty->s; return false; }
         int bvi = (int)a.num("bufferView", -1); if (bvi < 0 || (size_t)bvi >= views->size()) { err = "sparse/empty accessors not supported"; return false; }
         const JVal &bv = (*views)[bvi];
-        size_t off = (size_t)bv.num("byteOffset", 0) + (size_t)a.num("byteOffset", 0);
+        const size_t off_v = to_sz(bv.num("byteOffset", 0)), off_a = to_sz(a.num("byteOffset", 0));
+        if (off_v == (size_t)-1 || off_a == (size_t)-1) { err = "bad byteOffset"; return false; }
+        size_t off = off_v + off_a;
         int csz = (ct == 5120 || ct == 5121) ? 1 : (ct == 5122 || ct == 5123) ? 2 : (ct == 5125 || ct == 5126) ? 4 : 0;
         if (!csz) { err = "bad componentType"; return false; }
-        size_t stride = (size_t)bv.num("byteStride", 0); if (!stride) stride = (size_t)csz * nc;
+        size_t stride = to_sz(bv.num("byteStride", 0)); if (!stride) stride = (size_t)csz * nc;
         int bi = (int)bv.num("buffer", 0); if ((size_t)bi >= buffers.size()) { err = "bad buffer index"; return false; }
         const std::vector<uint8_t> &buf = buffers[bi];
-        if (count && off + (count - 1) * stride + (size_t)csz * nc > buf.size()) { err = "accessor out of range"; return false; }
+        {   // all in division form: count / offsets come from untrusted JSON doubles and the products can wrap in 64 bits
+            const size_t elem = (size_t)csz * nc;
+            if (stride < elem || stride > 4096) { err = "bad byteStride"; return false; }
+            if (count && (off > buf.size() || elem > buf.size() - off || count - 1 > (buf.size() - off - elem) / stride)) { err = "accessor out of range"; return false; }
+        }
         const bool norm = a.get("normalized") && a.get("normalized")->b;
         if (fout) fout->resize(count * nc);
         if (uout) uout->resize(count * nc);

@@ -367,39 +367,49 @@ __device__ __forceinline__ float ggx_d(const BsdfCtx &c, float3 H) {            
     float e = (H.x * H.x) / c.ax2 + (H.y * H.y) / c.ay2 + H.z * H.z;
     return 1.0f / (c.dnorm * (e * e));
 }
+// Lobe sets (template parameter LOBES of the functions below): a material class (device_types.h: MaterialClass) whose lobe probability is
+// exactly 0 contributes exact zeros through `b * p` and `pdf * p` for every finite b, so that lobe's code is dropped from the class's kernel.
+constexpr uint32_t LB_M = 1u, LB_D = 2u, LB_G = 4u, LB_ALL = 7u;
+__host__ __device__ constexpr uint32_t class_lobes(uint32_t mc) { return mc == MC_DIFFUSE ? LB_D : (mc == MC_METAL ? LB_M : (mc == MC_GLASS ? LB_G : LB_ALL)); }
+template <uint32_t LOBES = LB_ALL>
 __device__ __forceinline__ void bsdf_ctx_init(BsdfCtx &c, const Mat &m, const DevScene &sc, const DevConfig &cfg, float3 V) {
     c.pm = m.pm; c.pd = m.pd; c.pg = m.pg;                                   // :169-177 (material_apply_texels)
     c.ax2 = m.Ax * m.Ax; c.ay2 = m.Ay * m.Ay; c.dnorm = PT_PI * m.Ax * m.Ay;
     c.GV = ggx_g1(m, V);
     c.reflEC = 1.0f; c.glassEC = 0.0f; c.metalEC = f3(1.0f);
     if (cfg.UseEnergyCompensation) {
-        const bool inside = m.Eta > 1.0f;
-        const float layer = (clampf(m.IOR, 1.0001f, 2.0f) - 1.0f) * 32.0f;
-        c.glassEC = lut_sample(inside ? sc.lut_refract_in : sc.lut_refract_out, 128, 128, 32, sqrtf(V.z), m.Roughness, layer);
-        c.reflEC = lut_sample(sc.lut_reflect, 64, 64, 32, V.z, m.Roughness, m.Anisotropy * 32.0f);
-        const float ec = (1.0f - c.reflEC) / c.reflEC;
-        c.metalEC = f3(1.0f) + m.BaseColor * f3(ec);
+        if (LOBES & LB_G) {
+            const bool inside = m.Eta > 1.0f;
+            const float layer = (clampf(m.IOR, 1.0001f, 2.0f) - 1.0f) * 32.0f;
+            c.glassEC = lut_sample(inside ? sc.lut_refract_in : sc.lut_refract_out, 128, 128, 32, sqrtf(V.z), m.Roughness, layer);
+        }
+        if (LOBES & (LB_M | LB_D)) {
+            c.reflEC = lut_sample(sc.lut_reflect, 64, 64, 32, V.z, m.Roughness, m.Anisotropy * 32.0f);
+            const float ec = (1.0f - c.reflEC) / c.reflEC;
+            c.metalEC = f3(1.0f) + m.BaseColor * f3(ec);
+        }
     }
     c.diffuse = m.BaseColor * PT_1_OVER_PI;
     c.fourVz = 4.0f * V.z;
 }
 // :167-279 (+ :281-387): EvaluateBSDF(V, L)
+template <uint32_t LOBES = LB_ALL>
 __device__ __forceinline__ Eval eval_bsdf(const Mat &m, const BsdfCtx &c, const DevConfig &cfg, float3 V, float3 L) {
     const bool refracted = L.z < 0.0f;
     Eval out; out.BxDF = f3(0.0f); out.PDF = 0.0f;
     if (!refracted) {
         const float3 H = normalize(V + L);
         const float VdotH = dot(V, H);
-        const float F = dielectric_fresnel(fabsf(VdotH), m.Eta);                  // :202
+        float F = 0.0f;
+        if (LOBES & (LB_D | LB_G)) F = dielectric_fresnel(fabsf(VdotH), m.Eta);   // :202
         // EvaluateReflection (:331-351) shared by the metallic, dielectric-specular and glass-reflect lobes
-        float rpdf = 0.0f, DGG = 0.0f; bool refl = false; float D = 0.0f, GL = 0.0f;
+        float rpdf = 0.0f; bool refl = false; float D = 0.0f, GL = 0.0f;
         if (!(L.z <= 1e-5f)) {
             refl = true;
             D = ggx_d(c, H); GL = ggx_g1(m, L);
             rpdf = (c.GV * fmaxf(VdotH, 0.0f) * D / V.z) / (4.0f * VdotH);
         }
-        (void)DGG;
-        {   // metallic :291-308
+        if (LOBES & LB_M) {   // metallic :291-308
             float3 b = f3(0.0f);
             if (refl) {
                 const float3 Fm = mix3(m.BaseColor, m.SpecularColor, schlick_fresnel(VdotH));
@@ -408,25 +418,25 @@ __device__ __forceinline__ Eval eval_bsdf(const Mat &m, const BsdfCtx &c, const 
             if (cfg.UseEnergyCompensation) b = c.metalEC * b;
             out.BxDF = out.BxDF + b * c.pm; out.PDF += rpdf * c.pm;
         }
-        {   // diffuse :281-289
+        if (LOBES & LB_D) {   // diffuse :281-289
             float pdf = L.z * PT_1_OVER_PI;
             const float3 brdf = c.diffuse * L.z;
             pdf *= (L.z > 0.0f) ? 1.0f : 0.0f;
             out.BxDF = out.BxDF + (brdf * c.pd) * (1.0f - F); out.PDF += pdf * c.pd * (1.0f - F);
         }
         float3 spec = f3(0.0f);
-        if (refl) spec = (((m.SpecularColor * D) * c.GV) * GL) / c.fourVz;
-        {   // dielectric specular :310-323
+        if ((LOBES & (LB_D | LB_G)) && refl) spec = (((m.SpecularColor * D) * c.GV) * GL) / c.fourVz;
+        if (LOBES & LB_D) {   // dielectric specular :310-323
             float3 b = spec;
             if (cfg.UseEnergyCompensation) b = b / c.reflEC;
             out.BxDF = out.BxDF + (b * c.pd) * F; out.PDF += rpdf * c.pd * F;
         }
-        {   // glass reflect :237-251
+        if (LOBES & LB_G) {   // glass reflect :237-251
             float3 b = spec;
             if (cfg.UseEnergyCompensation && c.glassEC > 0.01f) b = b / c.glassEC;
             out.BxDF = out.BxDF + (b * c.pg) * F; out.PDF += rpdf * c.pg * F;
         }
-    } else {
+    } else if (LOBES & LB_G) {   // pg == 0 (no glass lobe): every term below is multiplied by an exact 0
         float3 H = normalize(V * m.Eta + L);
         if (H.z < 0.0f) H = -H;
         const float VdotH = dot(V, H), LdotH = dot(L, H);
@@ -455,13 +465,16 @@ __device__ __forceinline__ Eval eval_bsdf(const Mat &m, const BsdfCtx &c, const 
 // :94-165
 // Direction part of SampleBSDF (:94-160).  Returns false for the "invalid reflection/refraction direction" early-outs
 // (:152-160); the BxDF/PDF of a valid direction come from EvaluateBSDF(V, L) (:163), evaluated by the caller.
+// LOBES: with pm == 0 the test x1 < pm never holds (x1 >= 0); with pd == 0 the test x1 < pm + pd repeats x1 < pm.  The glass branch stays
+// in every class: x1 can be exactly 1.0 (Q12), which falls through to it even when pg == 0.
+template <uint32_t LOBES = LB_ALL>
 __device__ __forceinline__ bool sample_bsdf_direction(const Mat &m, const BsdfCtx &c, Rng &rng, float3 V, float3 H, float3 &Lout) {
     const float pm = c.pm, pd = c.pd;
     float F = dielectric_fresnel(dot(V, H), m.Eta);
     float x1 = rng.next();
     float3 L; bool refracted = false;
-    if (x1 < pm) L = normalize(reflect3(-V, H));
-    else if (x1 < pm + pd) {
+    if ((LOBES & LB_M) && x1 < pm) L = normalize(reflect3(-V, H));
+    else if ((LOBES & LB_D) && x1 < pm + pd) {
         if (rng.next() < F) L = normalize(reflect3(-V, H));
         else L = normalize(random_sphere(rng) + f3(0.0f, 0.0f, 1.0f));
     } else {

@@ -6,13 +6,15 @@
 //   k_raygen   camera sample + payload init                    SH/RayGen.slang:12-63
 //   per bounce:
 //     k_extend   closest-hit traversal of the live paths       SH/RayGen.slang:68-72,90 (TraceRay)
-//                + hit / miss queue split (ballot compaction)
+//                + sort into the miss queue and one hit queue per MATERIAL CLASS (lobe set)
 //     k_shade_miss  miss shading of the miss queue             SH/Miss.slang:8-76
-//     k_shade_hit   closest-hit shading of the hit queue,      SH/ClosestHit.slang:20-378
-//                   emits <=2 NEE shadow requests
+//     k_shade_hit<CLASS>  closest-hit shading of one class's   SH/ClosestHit.slang:20-378
+//                   hit queue, emits <=2 NEE shadow requests
 //     k_connect  shadow rays, payload.Emitted assembly,        SH/ClosestHit.slang:139,171-176,326-372
 //                luminance clamp, throughput, Russian          SH/RayGen.slang:92-113
 //                roulette, ballot/prefix-sum compaction
+//   scenes whose BVH is staged in shared memory by TMA run the bounce as ONE kernel per class (k_shade_hit<CLASS, ., 2>):
+//   shading + both NEE shadow queries + roulette + the next segment's closest-hit query + queue append.
 //   k_resolve  NaN/Inf rejection + running mean                SH/RayGen.slang:116-159
 //
 // Every path owns one sample slot, so radiance accumulation needs no atomics and is deterministic.
@@ -35,10 +37,7 @@ __host__ __device__ inline uint32_t part_global_row(uint32_t local_row, uint32_t
     return (blk * world + rank) * band + in;
 }
 
-// ------------------------------------------------------------------------------------------------
-// control block (device memory, u32): [0],[1] live-path counts (ping-pong by bounce parity p = bounce & 1),
-//                                     [2+2p] hit-queue length, [3+2p] miss-queue length of a bounce with parity p
-// ------------------------------------------------------------------------------------------------
+// control block (device memory, u32): device_types.h (CTRL_Q)
 
 // ------------------------------------------------------------------------------------------------
 // k_raygen
@@ -91,16 +90,52 @@ __global__ void __launch_bounds__(256) k_raygen(DevConfig cfg, const DevDispatch
         ps.rad_slot[j] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(j));
         if (ps.vol_depth) ps.vol_depth[j] = 0u;                             // payload.VolumeDepth = 0 (SH/RayGen.slang:61)
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[0] = n; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; ctrl[4] = 0; ctrl[5] = 0; ctrl[8] = 0; ctrl[9] = 0; ctrl[10] = 0; ctrl[11] = 0; atomicAdd(&ctr->paths, (unsigned long long)n); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { for (uint32_t w = 0; w < CTRL_WORDS; w++) ctrl[w] = 0; ctrl[0] = n; atomicAdd(&ctr->paths, (unsigned long long)n); }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_extend : closest hit for every live path; splits the live list into a hit queue and a miss queue
-//            (warp ballot + prefix sum, one atomic per warp and queue) so the two shading kernels run converged
+// queue helpers (device_types.h: Queues, CTRL_Q).  Queue codes: 0 = miss, 1 + c = hit of material class c, Q_NONE = inactive lane.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ctrl_reset_parity(uint32_t *ctrl, uint32_t q) {   // counters of a bounce with parity q (called by ONE thread, before any writer of that bounce)
+    ctrl[q] = 0; ctrl[8u + q] = 0; ctrl[10u + q] = 0;
+    #pragma unroll
+    for (uint32_t c = 0; c < 1u + MC_COUNT; c++) ctrl[CTRL_Q + 8u * q + c] = 0;
+}
+// All hit queues of one bounce seen as one list of n entries (k_connect, k_shadow_dyn, k_shade_volume walk every hit whatever its class)
+struct HitSpan { uint32_t p1, p2, p3, n; };
+__device__ __forceinline__ HitSpan hit_span(const uint32_t *ctrl, uint32_t parity) {
+    const uint32_t *c = ctrl + CTRL_Q + 8u * parity + 1u;
+    HitSpan h; h.p1 = c[0]; h.p2 = h.p1 + c[1]; h.p3 = h.p2 + c[2]; h.n = h.p3 + c[3];
+    return h;
+}
+__device__ __forceinline__ uint32_t hit_entry(const Queues &q, const HitSpan &h, uint32_t j) {
+    const uint32_t c = (uint32_t)(j >= h.p1) + (uint32_t)(j >= h.p2) + (uint32_t)(j >= h.p3);
+    const uint32_t base = c == 0u ? 0u : (c == 1u ? h.p1 : (c == 2u ? h.p2 : h.p3));
+    return q.hit[(size_t)c * q.cap + (j - base)];
+}
+__device__ __forceinline__ uint32_t hit_code(const DevScene &sc, uint32_t gid) {   // queue code of a hit on triangle gid
+    return 1u + (gid == VOLUME_EVENT ? (uint32_t)MC_GENERAL : (uint32_t)__ldg(sc.tri_class + gid));
+}
+// Warp-level append of one entry per lane (code Q_NONE = nothing): the lowest lane of every code group reserves room for its group with one
+// atomic -- a single atomic instruction with up to five distinct addresses per warp.  Must be called by all 32 lanes.
+__device__ __forceinline__ void queue_append(uint32_t code, uint32_t entry, uint32_t *qc, const Queues &q, uint32_t lane) {
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, code);
+    const int leader = __ffs((int)peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader && code != Q_NONE) base = atomicAdd(qc + code, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    const uint32_t k = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    if (code == 0u) q.miss[k] = entry;
+    else if (code != Q_NONE) q.hit[(size_t)(code - 1u) * q.cap + k] = entry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_extend : closest hit for every live path; sorts the live list into the miss queue and one hit queue per material class
+//            (material-sorted shading: every k_shade_hit<CLASS> warp runs one lobe set, converged)
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM, bool PRIMARY>   // PRIMARY: camera rays (origin anywhere) -> exact slab arithmetic; later bounces start on scene surfaces -> FMA slabs
-__global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, ShadeOut so, uint32_t *__restrict__ ctrl, uint32_t parity,
-                                                 uint32_t *__restrict__ q_hit, uint32_t *__restrict__ q_miss, int max_stack, WaveCounters *ctr) {
+__global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, float4 *__restrict__ hit_out, uint32_t *__restrict__ ctrl, uint32_t parity,
+                                                 Queues q, int max_stack, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
@@ -109,281 +144,440 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, Shade
     if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
     else bv = global_bvh(sc);
     const uint32_t n = ctrl[parity];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {                              // counters of the NEXT bounce (last used two bounces ago)
-        ctrl[parity ^ 1u] = 0; ctrl[2u + 2u * (parity ^ 1u)] = 0; ctrl[3u + 2u * (parity ^ 1u)] = 0; ctrl[8u + (parity ^ 1u)] = 0; ctrl[10u + (parity ^ 1u)] = 0;
-    }
-    unsigned long long *q_count = reinterpret_cast<unsigned long long *>(ctrl + 2u + 2u * parity);   // {hit count (low), miss count (high)}, 8-byte aligned
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl_reset_parity(ctrl, parity ^ 1u);   // counters of the NEXT bounce (last used two bounces ago)
+    uint32_t *qc = ctrl + CTRL_Q + 8u * parity;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt = (1u << lane) - 1u;
-    // Queue append without block barriers and with few atomics (ncu round 1: returning per-warp atomics on two hot addresses were
+    // Queue append without block barriers and with few atomics (ncu round 1: returning per-warp atomics on hot addresses were
     // 51 % of this kernel's stalls; the block-level scan that replaced them left 2.9 warps/issue parked on __syncthreads).
     // A block owns SEGMENTS of K*256 consecutive paths (grid-stride over segments); in iteration `it` its 8 warps cover 256
     // consecutive paths (neighbouring pixels -> shared BVH nodes in L1), each warp traces its K rays without ever waiting for the
-    // others, lane `it` keeps the hit/miss ballots of iteration `it` in registers, then ONE 64-bit atomic per warp reserves room in
-    // both queues for all K iterations.  K adapts to the live count so small waves still fill the GPU.
+    // others.  Every lane keeps the queue codes of its K rays (3 bits each), lane `it` keeps the per-queue counts of iteration `it`
+    // (6 bits x 5 queues, one redux), then ONE atomic instruction per warp (lanes 0..4, one address each) reserves room in all five
+    // queues for all K iterations.  K adapts to the live count so small waves still fill the GPU.
     const uint32_t K = min(8u, max(1u, n / (gridDim.x * blockDim.x * 2u)));
     const uint32_t seg_paths = K * blockDim.x, n_seg = (n + seg_paths - 1u) / seg_paths;
     for (uint32_t seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
         const uint32_t base_i = seg * seg_paths + (threadIdx.x & ~31u);     // first path of this warp in iteration 0
-        uint32_t my_bh = 0, my_bm = 0, ch = 0, cm = 0;
+        uint32_t codes = 0u, my_cnts = 0u, totA = 0u, totB = 0u;            // totA: queues 0..2, totB: queues 3..4 (10-bit fields, <= 256 each)
         uint32_t i = base_i + lane;
         float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
         if (i < n) { o4 = ps.org_pdf[i]; d4 = ps.dir_rng[i]; }
         for (uint32_t it = 0; it < K; it++, i += blockDim.x) {
-            if (base_i + it * blockDim.x >= n) break;                               // warp-uniform
+            if (base_i + it * blockDim.x >= n) { codes |= Q_NONE << (3u * it); continue; }   // warp-uniform
             const bool active = i < n;
-            bool hit = false;
+            uint32_t code = Q_NONE;
             float4 o4n = make_float4(0, 0, 0, 0), d4n = o4n;
             if (it + 1u < K && i + blockDim.x < n) { o4n = ps.org_pdf[i + blockDim.x]; d4n = ps.dir_rng[i + blockDim.x]; }   // software pipelining of the state loads
-            if (active && sc.n_volumes && __float_as_uint(so.hit[i].w) == VOLUME_EVENT) {
-                hit = true;                                                 // scattered inside a volume (k_volume_decide): no TraceRay, SH/RayGen.slang:86-90
+            if (active && sc.n_volumes && __float_as_uint(hit_out[i].w) == VOLUME_EVENT) {
+                code = 1u + MC_GENERAL;                                     // scattered inside a volume (k_volume_decide): no TraceRay, SH/RayGen.slang:86-90
             } else if (active) {
                 const float3 rd = normalize_ray(f3(d4));                    // SH/RayGen.slang:70
                 HitRec h;
-                hit = bvh_trace<SMEM, false, false, false, !PRIMARY>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
-                so.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
+                const bool hit = bvh_trace<SMEM, false, false, false, !PRIMARY>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
+                hit_out[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
+                code = hit ? hit_code(sc, h.gid) : 0u;
             }
             o4 = o4n; d4 = d4n;
-            const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
-            if (lane == it) { my_bh = bh; my_bm = bm; }
-            ch += (uint32_t)__popc(bh); cm += (uint32_t)__popc(bm);
+            const uint32_t cn = __reduce_add_sync(0xFFFFFFFFu, code != Q_NONE ? 1u << (6u * code) : 0u);
+            codes |= code << (3u * it);
+            if (lane == it) my_cnts = cn;
+            totA += (cn & 63u) | (((cn >> 6) & 63u) << 10) | (((cn >> 12) & 63u) << 20);
+            totB += ((cn >> 18) & 63u) | (((cn >> 24) & 63u) << 10);
         }
-        unsigned long long base = 0ull;
-        if (lane == 0 && (ch | cm)) base = atomicAdd(q_count, ((unsigned long long)cm << 32) | (unsigned long long)ch);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        uint32_t oh = (uint32_t)base, om = (uint32_t)(base >> 32);
+        uint32_t base = 0u;
+        {
+            const uint32_t mytot = lane < 3u ? (totA >> (10u * lane)) & 1023u : (lane < 5u ? (totB >> (10u * (lane - 3u))) & 1023u : 0u);
+            if (mytot) base = atomicAdd(qc + lane, mytot);
+        }
+        uint32_t runA = 0u, runB = 0u;
         i = base_i + lane;
         for (uint32_t it = 0; it < K; it++, i += blockDim.x) {
-            const uint32_t bh = __shfl_sync(0xFFFFFFFFu, my_bh, (int)it), bm = __shfl_sync(0xFFFFFFFFu, my_bm, (int)it);
-            if ((bh >> lane) & 1u) q_hit[oh + __popc(bh & lt)] = i;
-            else if ((bm >> lane) & 1u) q_miss[om + __popc(bm & lt)] = i;
-            oh += (uint32_t)__popc(bh); om += (uint32_t)__popc(bm);
+            const uint32_t code = (codes >> (3u * it)) & 7u;
+            const uint32_t cn = __shfl_sync(0xFFFFFFFFu, my_cnts, (int)it);
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, code);
+            const uint32_t b = __shfl_sync(0xFFFFFFFFu, base, (int)(code < 5u ? code : 0u));
+            if (code != Q_NONE) {
+                const uint32_t run = code < 3u ? (runA >> (10u * code)) & 1023u : (runB >> (10u * (code - 3u))) & 1023u;
+                const uint32_t k = b + run + (uint32_t)__popc(peers & lt);
+                if (code == 0u) q.miss[k] = i; else q.hit[(size_t)(code - 1u) * q.cap + k] = i;
+            }
+            runA += (cn & 63u) | (((cn >> 6) & 63u) << 10) | (((cn >> 12) & 63u) << 20);
+            runB += ((cn >> 18) & 63u) | (((cn >> 24) & 63u) << 10);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->extend_rays, (unsigned long long)n);
+}
+
+// SH/Miss.slang:8-76 + the ray-gen epilogue for a path whose segment missed (shared by k_shade_miss and the fused bounce kernel's tail)
+__device__ __forceinline__ void finish_missed_path(const DevScene &sc, const DevConfig &cfg, float3 dir, uint32_t rng_state, float4 t4, float4 r4, float payPDF,
+                                                   float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry) {
+    const uint32_t depth = __float_as_uint(t4.w) & 0x7FFFFFFFu;
+    float4 c;
+    if (cfg.ShowEnvMapDirectly || depth > 0) {
+        float3 r = rotate3_cs(dir, f3(1, 0, 0), cfg.cosAl, -cfg.sinAl);    // Rotate(dir, X, -altitude): cos is even, sin odd
+        r = rotate3_cs(r, f3(0, 1, 0), cfg.cosAz, -cfg.sinAz);
+        float u, v; direction_to_uv(r, u, v);
+        c = env_sample(sc, u, v);
+    } else c = make_float4(0, 0, 0, 1);
+    float3 em = f3(c.x * cfg.EnvironmentIntensity, c.y * cfg.EnvironmentIntensity, c.z * cfg.EnvironmentIntensity);
+    if (cfg.FurnaceTestMode) em = f3(1.0f);
+    if (cfg.EnableSkyMIS && depth > 0) em = em * power_heuristic(payPDF, c.w);
+    // SH/RayGen.slang:92-102 with payload.Depth == MAX_DEPTH (!= 1): the contribution is always luminance-clamped (Q3)
+    float3 contribution = em * f3(t4);
+    const float lum = dot(contribution, f3(0.212671f, 0.715160f, 0.072169f));
+    contribution = contribution * (cfg.MaxLuminance / fmaxf(lum, cfg.MaxLuminance));
+    const float3 rad = f3(r4) + contribution;
+    Rng rng; rng.s = rng_state;
+    (void)rng.next();                                                       // the Russian-roulette draw of this segment (:111) still advances the stream
+    const uint32_t slot = __float_as_uint(r4.w);
+    const bool ok = !isinf(rad.x) && !isinf(rad.y) && !isinf(rad.z) && !isnan(rad.x) && !isnan(rad.y) && !isnan(rad.z);   // :116
+    float4 acc = sample_buf[slot];
+    if (ok) { acc.x += rad.x; acc.y += rad.y; acc.z += rad.z; }
+    sample_buf[slot] = acc;
+    rng_carry[slot] = rng.s;
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_shade_miss : SH/Miss.slang:8-76 for the miss queue.  A miss always ends the path (Depth = MAX_DEPTH), so the
 //                ray-gen epilogue (SH/RayGen.slang:92-128) is applied here and the path never reaches k_connect.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, PathState ps, const uint32_t *__restrict__ ctrl, uint32_t parity,
+__global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, PathState ps, uint32_t *__restrict__ ctrl, uint32_t parity, uint32_t reset_next,
                                                      const uint32_t *__restrict__ q_miss, float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry,
                                                      WaveCounters *ctr) {
-    const uint32_t n = ctrl[3u + 2u * parity];
+    const uint32_t n = ctrl[CTRL_Q + 8u * parity];
+    // fused pipeline (k_bounce): this is the first kernel of the bounce, so it clears the counters the bounce kernels are about to fill
+    if (reset_next && blockIdx.x == 0 && threadIdx.x == 0) ctrl_reset_parity(ctrl, parity ^ 1u);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const uint32_t i = q_miss[j];
         const float4 d4 = ps.dir_rng[i], t4 = ps.thr_depth[i], r4 = ps.rad_slot[i];
-        const uint32_t depth = __float_as_uint(t4.w) & 0x7FFFFFFFu;
-        const float payPDF = ps.org_pdf[i].w;
-        float4 c;
-        if (cfg.ShowEnvMapDirectly || depth > 0) {
-            float3 r = rotate3_cs(f3(d4), f3(1, 0, 0), cfg.cosAl, -cfg.sinAl);   // Rotate(dir, X, -altitude): cos is even, sin odd
-            r = rotate3_cs(r, f3(0, 1, 0), cfg.cosAz, -cfg.sinAz);
-            float u, v; direction_to_uv(r, u, v);
-            c = env_sample(sc, u, v);
-        } else c = make_float4(0, 0, 0, 1);
-        float3 em = f3(c.x * cfg.EnvironmentIntensity, c.y * cfg.EnvironmentIntensity, c.z * cfg.EnvironmentIntensity);
-        if (cfg.FurnaceTestMode) em = f3(1.0f);
-        if (cfg.EnableSkyMIS && depth > 0) em = em * power_heuristic(payPDF, c.w);
-        // SH/RayGen.slang:92-102 with payload.Depth == MAX_DEPTH (!= 1): the contribution is always luminance-clamped (Q3)
-        float3 contribution = em * f3(t4);
+        finish_missed_path(sc, cfg, f3(d4), __float_as_uint(d4.w), t4, r4, ps.org_pdf[i].w, sample_buf, rng_carry);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr->misses, (unsigned long long)n); atomicAdd(&ctr->shade_invocations, (unsigned long long)n); }
+}
+
+// SH/RayGen.slang:92-113 for a path that was shaded at a hit: contribution (luminance clamp unless Depth == 1, Q3), throughput update, Russian
+// roulette (Q4), loop condition.  Returns whether the path continues; a finished path is folded into its sample slot (:116-128).
+__device__ __forceinline__ bool path_epilogue(const DevConfig &cfg, float3 emitted, float4 b4, uint32_t newDepth, float4 thr4, float4 r4, Rng &rng,
+                                              float3 &thr, float3 &rad, float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry) {
+    thr = f3(thr4); rad = f3(r4);
+    float3 contribution = emitted * thr;
+    if (newDepth != 1u) {                                                   // Q3
         const float lum = dot(contribution, f3(0.212671f, 0.715160f, 0.072169f));
-        contribution = contribution * (cfg.MaxLuminance / fmaxf(lum, cfg.MaxLuminance));
-        const float3 rad = f3(r4) + contribution;
-        Rng rng; rng.s = __float_as_uint(d4.w);
-        (void)rng.next();                                                   // the Russian-roulette draw of this segment (:111) still advances the stream
+        const float scale = cfg.MaxLuminance / fmaxf(lum, cfg.MaxLuminance);
+        contribution = contribution * scale;
+    }
+    rad = rad + contribution;
+    thr = thr * (f3(b4) / b4.w);
+    float p = fmaxf(thr.x, fmaxf(thr.y, thr.z));
+    p = fminf(p, 1.0f);
+    const float u = rng.next();                                             // Q4
+    bool alive = !(p < u);
+    if (alive) thr = thr / p;
+    alive = alive && (newDepth < cfg.MaxDepth);                             // loop condition :66
+    if (!alive) {                                                           // path finished: :116-128 (+ carry RNG for SampleCount > 1)
         const uint32_t slot = __float_as_uint(r4.w);
-        const bool ok = !isinf(rad.x) && !isinf(rad.y) && !isinf(rad.z) && !isnan(rad.x) && !isnan(rad.y) && !isnan(rad.z);   // :116
+        const bool ok = !isinf(rad.x) && !isinf(rad.y) && !isinf(rad.z) && !isnan(rad.x) && !isnan(rad.y) && !isnan(rad.z);
         float4 acc = sample_buf[slot];
         if (ok) { acc.x += rad.x; acc.y += rad.y; acc.z += rad.z; }
         sample_buf[slot] = acc;
         rng_carry[slot] = rng.s;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr->misses, (unsigned long long)n); atomicAdd(&ctr->shade_invocations, (unsigned long long)n); }
+    return alive;
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_shade_hit : SH/ClosestHit.slang:20-378 for the hit queue
+// k_shade_hit<CLASS, VOL, FUSE> : SH/ClosestHit.slang:20-378 for the hit queue of one material class.
+//   FUSE == 0  writes the new ray + payload in place and <= 2 NEE shadow requests; k_connect (or k_shadow_dyn + k_connect) finishes the bounce.
+//   FUSE >= 1  "k_bounce" for scenes whose BVH is staged in shared memory (no volumes): each NEE request is traced the moment it is built
+//              (one copy of the any-hit traversal inside the rolled NEE loop), then SH/RayGen.slang:92-113 runs in the same thread and the
+//              survivor is written compacted to the other PathState buffer -- no request / payload round trip through HBM, no k_connect.
+//   FUSE == 2  additionally traces the survivor's NEXT segment (the next bounce's k_extend) and appends it to the next bounce's miss / class
+//              queues: one kernel per (bounce, class), 80 B read + 84 B written per continuing path.
 // ------------------------------------------------------------------------------------------------
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 5
 #endif
-template <bool VOL>   // VOL: the scene has AABB volumes (volumes.cuh) -- volume events in the hit queue are skipped, NEE terms get the transmittance
-__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so,
-                                                    const uint32_t *__restrict__ ctrl, uint32_t parity, const uint32_t *__restrict__ q_hit, WaveCounters *ctr) {
-    const uint32_t n = ctrl[2u + 2u * parity];
-    uint32_t n_med = 0;
+#ifndef BOUNCE_MIN_BLOCKS
+#define BOUNCE_MIN_BLOCKS 5
+#endif
+template <uint32_t CLASS, bool VOL, int FUSE>   // VOL: the scene has AABB volumes (volumes.cuh) -- volume events in the hit queue are skipped, NEE terms get the transmittance
+__global__ void __launch_bounds__(128, FUSE ? BOUNCE_MIN_BLOCKS : SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc, DevConfig cfg, PathState ps, PathState dst, ShadeOut so,
+                                                    const float4 *__restrict__ hit_in, float4 *__restrict__ hit_out,
+                                                    uint32_t *__restrict__ ctrl, uint32_t parity, Queues q, Queues q_next,
+                                                    float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry, int max_stack, WaveCounters *ctr) {
+    constexpr uint32_t LOBES = class_lobes(CLASS);
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
+    const int stride = blockDim.x;
+    BvhView bv;
+    if (FUSE) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
+    const uint32_t n = ctrl[CTRL_Q + 8u * parity + 1u + CLASS];
+    const uint32_t *__restrict__ q_hit = q.hit + (size_t)CLASS * q.cap;
+    uint32_t *qc_next = ctrl + CTRL_Q + 8u * (parity ^ 1u);
+    uint32_t *n_next_ptr = ctrl + (parity ^ 1u);
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t n_med = 0, n_shadow = 0, n_ext = 0;
     const float4 zero4 = make_float4(0, 0, 0, 0);
     // The queue entry and the hit record of the NEXT path of this thread are fetched one iteration ahead (two dependent DRAM
     // round trips off the critical path for 5 registers); its path-state lines are pulled towards L2 meanwhile.
     const uint32_t jstep = gridDim.x * blockDim.x;
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t i_nx = 0; float4 h4_nx = zero4;
-    if (j < n) { i_nx = q_hit[j]; h4_nx = so.hit[i_nx]; }
-    for (; j < n; j += jstep) {
+    if (j < n) { i_nx = q_hit[j]; h4_nx = hit_in[i_nx]; }
+    const uint32_t n_loop = FUSE ? ((n + 31u) & ~31u) : n;                  // fused: warps stay converged for the compaction collectives
+    for (; j < n_loop; j += jstep) {
+        const bool valid = j < n;
+        // ---- results of the shading part, consumed by the fused tail
+        bool shaded = false;                                                // this lane holds a path whose bounce must be finished (fused)
+        float3 emitted = f3(0.0f), newO = f3(0.0f), newD = f3(0.0f);
+        float4 b4 = zero4; uint32_t newDflags = 0u; Rng rng; rng.s = 0u;
+        bool entered = false;
+        const DevMaterial *cmp = nullptr;
         const uint32_t i = i_nx;
-        const float4 h4 = h4_nx;
-        const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
-        const uint32_t dflags = __float_as_uint(ps.thr_depth[i].w);
-        if (j + jstep < n) {
-            i_nx = q_hit[j + jstep]; h4_nx = so.hit[i_nx];
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.org_pdf + i_nx));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.dir_rng + i_nx));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.thr_depth + i_nx));
-        }
-        const uint32_t depth = dflags & 0x7FFFFFFFu;
-        const bool inMedium = (dflags >> 31) != 0u;
-        const float3 payOrigin = f3(o4), payDir = f3(d4);
-        const float payPDF = o4.w;
-        Rng rng; rng.s = __float_as_uint(d4.w);
-        const uint32_t gid = __float_as_uint(h4.w);                            // global triangle id of the hit
-        if (VOL && gid == VOLUME_EVENT) continue;                           // a volume scattering event: k_shade_volume
+        if (valid) do {
+            const float4 h4 = h4_nx;
+            const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
+            const uint32_t dflags = __float_as_uint(ps.thr_depth[i].w);
+            if (j + jstep < n) {
+                i_nx = q_hit[j + jstep]; h4_nx = hit_in[i_nx];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.org_pdf + i_nx));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.dir_rng + i_nx));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.thr_depth + i_nx));
+            }
+            const uint32_t depth = dflags & 0x7FFFFFFFu;
+            const bool inMedium = (dflags >> 31) != 0u;
+            const float3 payOrigin = f3(o4), payDir = f3(d4);
+            const float payPDF = o4.w;
+            rng.s = __float_as_uint(d4.w);
+            const uint32_t gid = __float_as_uint(h4.w);                        // global triangle id of the hit
+            if (VOL && gid == VOLUME_EVENT) break;                          // a volume scattering event: k_shade_volume
 
-        // The sky-NEE draws are the first draws of a hit outside a medium: take them now and put the alias-table load in flight.
-        EnvPick ep;
-        const bool envEarly = cfg.EnableSkyMIS && !inMedium;
-        if (envEarly) sample_env_begin(sc, rng, ep);
+            // The sky-NEE draws are the first draws of a hit outside a medium: take them now and put the alias-table load in flight.
+            EnvPick ep;
+            const bool envEarly = cfg.EnableSkyMIS && !inMedium;
+            if (envEarly) sample_env_begin(sc, rng, ep);
 
-        const float3 rd = normalize(payDir);                                // WorldRayDirection()
-        float4 g[7];                                                        // one 112-B gather: vertices + ids of the hit triangle
-        {
-            const float4 *gp = reinterpret_cast<const float4 *>(sc.shade_tris + gid);
-            #pragma unroll
-            for (int q = 0; q < 7; q++) g[q] = __ldg(gp + q);
-        }
-        const uint32_t inst = __float_as_uint(g[0].w);
-        const DevInstance &in = sc.instances[inst];
-        const DevMaterial &cm = sc.materials[__float_as_uint(g[2].w)];
-        Surface sf;
-        surface_init(sf, sc, cfg, in, g, h4.y, h4.z, rd, cm);
-        Mat m;
-        material_init(m, sc, cfg, cm, sf);
-        const bool isLight = m.EmissiveColor.x > 0.0f || m.EmissiveColor.y > 0.0f || m.EmissiveColor.z > 0.0f;   // :65
-        surface_rotate_tangents(sf, m.AnisotropyRotation);                  // :67
+            const float3 rd = normalize(payDir);                                // WorldRayDirection()
+            float4 g[7];                                                        // one 112-B gather: vertices + ids of the hit triangle
+            {
+                const float4 *gp = reinterpret_cast<const float4 *>(sc.shade_tris + gid);
+                #pragma unroll
+                for (int qq = 0; qq < 7; qq++) g[qq] = __ldg(gp + qq);
+            }
+            const uint32_t inst = __float_as_uint(g[0].w);
+            const DevInstance &in = sc.instances[inst];
+            const DevMaterial &cm = sc.materials[__float_as_uint(g[2].w)];
+            cmp = &cm;
+            Surface sf;
+            surface_init(sf, sc, cfg, in, g, h4.y, h4.z, rd, cm);
+            Mat m;
+            material_init(m, sc, cfg, cm, sf);
+            const bool isLight = m.EmissiveColor.x > 0.0f || m.EmissiveColor.y > 0.0f || m.EmissiveColor.z > 0.0f;   // :65
+            surface_rotate_tangents(sf, m.AnisotropyRotation);                  // :67
 
-        bool newInMedium = inMedium;
-        if (inMedium) {                                                     // :80-116 (Q6)
-            const float4 med = ps.medium[i]; const float med_g = ps.medium_g[i];
-            const float dist = length(payOrigin - sf.WorldPos);
-            if (med_g == 1.0f) {
-                // Beer-law BxDF is overwritten below (:323) -- nothing observable happens here.
+            bool newInMedium = inMedium;
+            if (inMedium) {                                                     // :80-116 (Q6)
+                const float4 med = ps.medium[i]; const float med_g = ps.medium_g[i];
+                const float dist = length(payOrigin - sf.WorldPos);
+                if (med_g == 1.0f) {
+                    // Beer-law BxDF is overwritten below (:323) -- nothing observable happens here.
+                } else {
+                    const float sd = -logf(rng.next()) / med.w;
+                    if (sd < dist) {
+                        const float3 no = payOrigin + payDir * sd;
+                        const float3 nd = sample_henyey_greenstein(rng, payDir, med_g);
+                        n_med++;
+                        if (FUSE) {                                             // Depth and InMedium unchanged, no NEE, stale PDF (Q6)
+                            newO = no; newD = nd; b4 = make_float4(med.x, med.y, med.z, payPDF); newDflags = dflags; shaded = true;
+                        } else {
+                            ps.org_pdf[i] = make_float4(no.x, no.y, no.z, payPDF);
+                            ps.dir_rng[i] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(rng.s));
+                            so.bxdf_pdf[i] = make_float4(med.x, med.y, med.z, payPDF);
+                            so.e0[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(dflags));
+                        }
+                        break;
+                    }
+                }
+            }
+
+            // emission :265-317 (no RNG draws: evaluated before the NEE/BSDF loop so the corner positions and the ray origin die here)
+            float3 e0 = f3(0.0f);
+            if (cfg.EnableMeshMIS) {
+                if (depth == 0 && isLight) e0 = e0 + m.EmissiveColor;
+                else if (isLight) {
+                    const float3 w1 = xf_point(in.o2w, sf.P1), w2 = xf_point(in.o2w, sf.P2), w3 = xf_point(in.o2w, sf.P3);
+                    const float area = length(cross(w2 - w1, w3 - w1)) * 0.5f;
+                    const float3 dl = sf.WorldPos - payOrigin;
+                    const float d2 = dot(dl, dl);
+                    const float cosTheta = fabsf(dot(sf.Normal, normalize(payOrigin - sf.WorldPos)));
+                    float lp = (1.0f / (float)sc.n_emissive) * (1.0f / (float)in.emissive_tri_count) * (1.0f / area) * (d2 / cosTheta);
+                    lp = fmaxf(lp, cfg.EmissiveMeshSamplingPDFBias);
+                    e0 = e0 + m.EmissiveColor * power_heuristic(payPDF, lp);
+                }
+            } else e0 = e0 + m.EmissiveColor;
+            emitted = e0;
+
+            float3 V = normalize(-rd);
+            V = sf.world_to_tangent(V);
+            BsdfCtx bc;
+            bsdf_ctx_init<LOBES>(bc, m, sc, cfg, V);
+            // Three uses of EvaluateBSDF(V, .) per hit -- sky NEE (:125-147, :326-358), light NEE (:154-184, :360-372) and the sampled
+            // direction (SampleBSDF :94-165) -- run as ONE rolled loop in the reference's RNG order (sky draws, light draws, BSDF draws):
+            // a single copy of the BSDF code stays in the kernel, and each NEE request is built and stored (or, fused, traced) inside its
+            // own iteration so its direction / radiance / pdf registers die there.
+            Eval evS; evS.BxDF = f3(0.0f); evS.PDF = 0.0f;
+            float3 Ls = f3(0.0f); bool validDir = false;
+            uint32_t reqMask = 0u;                                              // bit 0: sky request stored, bit 1: light request stored
+            #pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                float3 toW = f3(0.0f), dk = f3(0.0f); float4 lv = zero4; uint32_t lgid = 0xFFFFFFFFu;
+                bool need = false;
+                if (k == 0) {
+                    if (cfg.EnableSkyMIS) {
+                        if (!envEarly) sample_env_begin(sc, rng, ep);
+                        sample_env_finish(sc, cfg, ep, toW, lv);
+                        lv.x *= cfg.EnvironmentIntensity; lv.y *= cfg.EnvironmentIntensity; lv.z *= cfg.EnvironmentIntensity;   // Q7
+                        dk = sf.world_to_tangent(toW);
+                        need = lv.w > 0.0f;
+                    }
+                } else if (k == 1) {
+                    if (cfg.EnableMeshMIS && !isLight) {
+                        sample_emissive(sc, rng, sf.WorldPos, toW, lv, lgid);
+                        if (lv.w > 0.0f) { dk = sf.world_to_tangent(toW); need = true; }
+                    }
+                } else {
+                    const float3 H = ggx_sample_vndf(rng, V, m.Ax, m.Ay);           // :191-204
+                    validDir = sample_bsdf_direction<LOBES>(m, bc, rng, V, H, Ls);
+                    dk = Ls; need = validDir;
+                }
+                Eval e; e.BxDF = f3(0.0f); e.PDF = 0.0f;
+                if (need) e = eval_bsdf<LOBES>(m, bc, cfg, V, dk);
+                if (k == 2) { evS = e; break; }
+                // NEE term (added iff the shadow query allows) :326-372
+                if (need && e.PDF > 0.0f) {
+                    const float3 c = (((e.BxDF * 1.0f) * f3(lv)) / lv.w) * power_heuristic(lv.w, e.PDF);
+                    const float3 ro = (k == 0) ? sf.WorldPos + sf.Normal * 1e-5f : sf.WorldPos + toW * 1e-2f;   // :139, :171
+                    if (FUSE) {
+                        //   sky   (SH/ClosestHit.slang:139 + :326-358): any hit in (1e-4, 1e6) occludes;
+                        //   light (:171-176 + :360-372): the closest hit must be the sampled triangle.  Equivalent occlusion form: the ray hits
+                        //         that triangle at tL and nothing lies in front of it (ties at tL resolve to the lower triangle id, exactly like
+                        //         the closest-hit query) -- bounded by tL and free to stop at the first occluder.
+                        // Both run through the TARGET any-hit query: for the sky ray target = 0xFFFFFFFF and tmax_test = tmax = 1e6.
+                        float tmax = 1000000.0f, tmax_test = 1000000.0f; bool go = true;
+                        if (k == 1) {
+                            const float4 *tp = bv.tris + (size_t)__ldg(sc.tri_slot + lgid) * 3;
+                            const float4 ta = tp[0], tb = tp[1], tc = tp[2];
+                            float tL, uL, vL;
+                            go = tri_test(f3(ta), f3(tb), f3(tc), ro, toW, 0.0001f, 1000000.0f, tL, uL, vL);
+                            tmax = tL; tmax_test = __uint_as_float(__float_as_uint(tL) + 1u);
+                        }
+                        n_shadow++;
+                        if (go) {
+                            HitRec hs;
+                            const bool occluded = bvh_trace<true, true, false, true, true>(bv, ro, toW, 0.0001f, tmax, hs, stack, stride, max_stack, nullptr, nullptr, lgid, tmax_test);
+                            if (!occluded) emitted = emitted + c;
+                        }
+                    } else {
+                        float4 *const po = (k == 0) ? so.sky_o : so.lit_o, *const pd = (k == 0) ? so.sky_d : so.lit_d, *const pc = (k == 0) ? so.sky_c : so.lit_c;
+                        po[i] = make_float4(ro.x, ro.y, ro.z, 1.0f);
+                        pd[i] = make_float4(toW.x, toW.y, toW.z, __uint_as_float(lgid));        // .w of the light request: id of the sampled triangle
+                        pc[i] = make_float4(c.x, c.y, c.z, 0.0f);
+                        reqMask |= 1u << k;
+                    }
+                }
+            }
+            BSample ss;
+            ss.L = validDir ? Ls : f3(0.0f); ss.BxDF = evS.BxDF; ss.PDF = evS.PDF;
+            const bool wasRefracted = ss.L.z < 0.0f;
+            const float3 scatterW = sf.tangent_to_world(ss.L);
+            if (!wasRefracted && dot(scatterW, sf.GeometryNormal) < 0.0f) { ss.PDF = 0.0f; ss.BxDF = f3(0.0f); }   // :220-225
+            if (wasRefracted && sf.HitFromInside) newInMedium = false;          // :227-238
+            else if (wasRefracted && !sf.HitFromInside) {                       // entering: the medium parameters are re-read from the material
+                newInMedium = true;                                             // record here instead of being carried through the loop above
+                entered = true;
+                if (!FUSE) {
+                    const b200pt_material &mm = cm.m;
+                    const float3 mc = cfg.FurnaceTestMode ? f3(1.0f) : f3(mm.MediumColor[0], mm.MediumColor[1], mm.MediumColor[2]);   // SH/Material.slang:78-86
+                    ps.medium[i] = make_float4(mc.x, mc.y, mc.z, mm.MediumDensity); ps.medium_g[i] = mm.MediumAnisotropy;
+                }
+            }
+
+            // payload write :319-324, :375-376
+            const float off = -1e-3f * (wasRefracted ? 1.0f : 0.0f) + 1e-3f * (wasRefracted ? 0.0f : 1.0f);
+            const float3 no = sf.WorldPos + sf.Normal * off;
+            const bool invalid = ss.PDF <= 0.0f;
+            const uint32_t newDepth = invalid ? PT_MAX_DEPTH + depth : depth + 1u;   // MAX_DEPTH*(invalid) + (Depth + 1*(!invalid))
+            if (FUSE) {
+                newO = no; newD = scatterW; b4 = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
+                newDflags = newDepth | (newInMedium ? 0x80000000u : 0u); shaded = true;
             } else {
-                const float sd = -logf(rng.next()) / med.w;
-                if (sd < dist) {
-                    const float3 no = payOrigin + payDir * sd;
-                    const float3 nd = sample_henyey_greenstein(rng, payDir, med_g);
-                    ps.org_pdf[i] = make_float4(no.x, no.y, no.z, payPDF);
-                    ps.dir_rng[i] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(rng.s));
-                    so.bxdf_pdf[i] = make_float4(med.x, med.y, med.z, payPDF);       // stale PDF (Q6)
-                    so.e0[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(dflags));   // Depth and InMedium unchanged, no shadow request
-                    n_med++;
-                    continue;
+                if (VOL && reqMask) {                                           // volumes cast shadows on the NEE terms: transmittance from the NEW origin (:332-333, :364)
+                    if (reqMask & 1u) { const float T = volumes_transmittance(sc, no, f3(so.sky_d[i])); const float4 c = so.sky_c[i]; so.sky_c[i] = make_float4(c.x * T, c.y * T, c.z * T, 0.0f); }
+                    if (reqMask & 2u) { const float T = volumes_transmittance(sc, no, f3(so.lit_d[i])); const float4 c = so.lit_c[i]; so.lit_c[i] = make_float4(c.x * T, c.y * T, c.z * T, 0.0f); }
                 }
+                ps.org_pdf[i] = make_float4(no.x, no.y, no.z, ss.PDF);
+                ps.dir_rng[i] = make_float4(scatterW.x, scatterW.y, scatterW.z, __uint_as_float(rng.s));
+                so.bxdf_pdf[i] = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
+                so.e0[i] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(newDepth | (reqMask << 29) | (newInMedium ? 0x80000000u : 0u)));   // bits 29/30: stored shadow requests
             }
-        }
+        } while (false);
 
-        // emission :265-317 (no RNG draws: evaluated before the NEE/BSDF loop so the corner positions and the ray origin die here)
-        float3 e0 = f3(0.0f);
-        if (cfg.EnableMeshMIS) {
-            if (depth == 0 && isLight) e0 = e0 + m.EmissiveColor;
-            else if (isLight) {
-                const float3 w1 = xf_point(in.o2w, sf.P1), w2 = xf_point(in.o2w, sf.P2), w3 = xf_point(in.o2w, sf.P3);
-                const float area = length(cross(w2 - w1, w3 - w1)) * 0.5f;
-                const float3 dl = sf.WorldPos - payOrigin;
-                const float d2 = dot(dl, dl);
-                const float cosTheta = fabsf(dot(sf.Normal, normalize(payOrigin - sf.WorldPos)));
-                float lp = (1.0f / (float)sc.n_emissive) * (1.0f / (float)in.emissive_tri_count) * (1.0f / area) * (d2 / cosTheta);
-                lp = fmaxf(lp, cfg.EmissiveMeshSamplingPDFBias);
-                e0 = e0 + m.EmissiveColor * power_heuristic(payPDF, lp);
+        if (FUSE) {
+            // ---- SH/RayGen.slang:92-113, then (FUSE == 2) the next segment's TraceRay, then compaction into the other PathState buffer
+            bool alive = false;
+            float4 r4 = zero4; float3 thr = f3(0.0f), rad = f3(0.0f);
+            if (shaded) {
+                const float4 thr4 = ps.thr_depth[i]; r4 = ps.rad_slot[i];
+                alive = path_epilogue(cfg, emitted, b4, newDflags & 0x7FFFFFFFu, thr4, r4, rng, thr, rad, sample_buf, rng_carry);
             }
-        } else e0 = e0 + m.EmissiveColor;
-
-        float3 V = normalize(-rd);
-        V = sf.world_to_tangent(V);
-        BsdfCtx bc;
-        bsdf_ctx_init(bc, m, sc, cfg, V);
-        // Three uses of EvaluateBSDF(V, .) per hit -- sky NEE (:125-147, :326-358), light NEE (:154-184, :360-372) and the sampled
-        // direction (SampleBSDF :94-165) -- run as ONE rolled loop in the reference's RNG order (sky draws, light draws, BSDF draws):
-        // a single copy of the BSDF code stays in the kernel, and each NEE request is built and stored inside its own iteration so
-        // its direction / radiance / pdf registers die there.  NEE is evaluated eagerly; visibility is resolved in k_connect.
-        Eval evS; evS.BxDF = f3(0.0f); evS.PDF = 0.0f;
-        float3 Ls = f3(0.0f); bool validDir = false;
-        uint32_t reqMask = 0u;                                              // bit 0: sky request stored, bit 1: light request stored
-        #pragma unroll 1
-        for (int k = 0; k < 3; k++) {
-            float3 toW = f3(0.0f), dk = f3(0.0f); float4 lv = zero4; uint32_t lgid = 0xFFFFFFFFu;
-            bool need = false;
-            if (k == 0) {
-                if (cfg.EnableSkyMIS) {
-                    if (!envEarly) sample_env_begin(sc, rng, ep);
-                    sample_env_finish(sc, cfg, ep, toW, lv);
-                    lv.x *= cfg.EnvironmentIntensity; lv.y *= cfg.EnvironmentIntensity; lv.z *= cfg.EnvironmentIntensity;   // Q7
-                    dk = sf.world_to_tangent(toW);
-                    need = lv.w > 0.0f;
+            uint32_t code = Q_NONE; HitRec h; h.t = 0.0f; h.u = 0.0f; h.v = 0.0f; h.gid = 0xFFFFFFFFu;
+            if (FUSE == 2 && alive) {
+                const float3 rd2 = normalize_ray(newD);                     // SH/RayGen.slang:70-72 of the next loop iteration
+                const bool hit = bvh_trace<true, false, false, false, true>(bv, newO, rd2, 0.01f, 100000.0f, h, stack, stride, max_stack);
+                code = hit ? hit_code(sc, h.gid) : 0u;
+                n_ext++;
+            }
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
+            if (ballot) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(n_next_ptr, (uint32_t)__popc(ballot));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                const uint32_t k = base + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+                if (alive) {
+                    dst.org_pdf[k] = make_float4(newO.x, newO.y, newO.z, b4.w);
+                    dst.dir_rng[k] = make_float4(newD.x, newD.y, newD.z, __uint_as_float(rng.s));
+                    dst.thr_depth[k] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(newDflags));
+                    dst.rad_slot[k] = make_float4(rad.x, rad.y, rad.z, r4.w);
+                    if (newDflags >> 31) {
+                        float4 mv; float mg;
+                        if (entered) {
+                            const b200pt_material &mm = cmp->m;
+                            const float3 mc = cfg.FurnaceTestMode ? f3(1.0f) : f3(mm.MediumColor[0], mm.MediumColor[1], mm.MediumColor[2]);   // SH/Material.slang:78-86
+                            mv = make_float4(mc.x, mc.y, mc.z, mm.MediumDensity); mg = mm.MediumAnisotropy;
+                        } else { mv = ps.medium[i]; mg = ps.medium_g[i]; }
+                        dst.medium[k] = mv; dst.medium_g[k] = mg;
+                    }
+                    if (FUSE == 2) hit_out[k] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
                 }
-            } else if (k == 1) {
-                if (cfg.EnableMeshMIS && !isLight) {
-                    sample_emissive(sc, rng, sf.WorldPos, toW, lv, lgid);
-                    if (lv.w > 0.0f) { dk = sf.world_to_tangent(toW); need = true; }
-                }
-            } else {
-                const float3 H = ggx_sample_vndf(rng, V, m.Ax, m.Ay);           // :191-204
-                validDir = sample_bsdf_direction(m, bc, rng, V, H, Ls);
-                dk = Ls; need = validDir;
-            }
-            Eval e; e.BxDF = f3(0.0f); e.PDF = 0.0f;
-            if (need) e = eval_bsdf(m, bc, cfg, V, dk);
-            if (k == 2) { evS = e; break; }
-            // NEE request (added in k_connect iff the shadow query allows) :326-372
-            if (need && e.PDF > 0.0f) {
-                const float3 c = (((e.BxDF * 1.0f) * f3(lv)) / lv.w) * power_heuristic(lv.w, e.PDF);
-                const float3 ro = (k == 0) ? sf.WorldPos + sf.Normal * 1e-5f : sf.WorldPos + toW * 1e-2f;   // :139, :171
-                float4 *const po = (k == 0) ? so.sky_o : so.lit_o, *const pd = (k == 0) ? so.sky_d : so.lit_d, *const pc = (k == 0) ? so.sky_c : so.lit_c;
-                po[i] = make_float4(ro.x, ro.y, ro.z, 1.0f);
-                pd[i] = make_float4(toW.x, toW.y, toW.z, __uint_as_float(lgid));        // .w of the light request: id of the sampled triangle
-                pc[i] = make_float4(c.x, c.y, c.z, 0.0f);
-                reqMask |= 1u << k;
+                if (FUSE == 2) queue_append(code, k, qc_next, q_next, lane);
             }
         }
-        BSample ss;
-        ss.L = validDir ? Ls : f3(0.0f); ss.BxDF = evS.BxDF; ss.PDF = evS.PDF;
-        const bool wasRefracted = ss.L.z < 0.0f;
-        const float3 scatterW = sf.tangent_to_world(ss.L);
-        if (!wasRefracted && dot(scatterW, sf.GeometryNormal) < 0.0f) { ss.PDF = 0.0f; ss.BxDF = f3(0.0f); }   // :220-225
-        if (wasRefracted && sf.HitFromInside) newInMedium = false;          // :227-238
-        else if (wasRefracted && !sf.HitFromInside) {                       // entering: the medium parameters are re-read from the material
-            newInMedium = true;                                             // record here instead of being carried through the loop above
-            const b200pt_material &mm = cm.m;
-            const float3 mc = cfg.FurnaceTestMode ? f3(1.0f) : f3(mm.MediumColor[0], mm.MediumColor[1], mm.MediumColor[2]);   // SH/Material.slang:78-86
-            ps.medium[i] = make_float4(mc.x, mc.y, mc.z, mm.MediumDensity); ps.medium_g[i] = mm.MediumAnisotropy;
-        }
-
-        // payload write :319-324, :375-376
-        const float off = -1e-3f * (wasRefracted ? 1.0f : 0.0f) + 1e-3f * (wasRefracted ? 0.0f : 1.0f);
-        const float3 no = sf.WorldPos + sf.Normal * off;
-        const bool invalid = ss.PDF <= 0.0f;
-        const uint32_t newDepth = invalid ? PT_MAX_DEPTH + depth : depth + 1u;   // MAX_DEPTH*(invalid) + (Depth + 1*(!invalid))
-        if (VOL && reqMask) {                                               // volumes cast shadows on the NEE terms: transmittance from the NEW origin (:332-333, :364)
-            if (reqMask & 1u) { const float T = volumes_transmittance(sc, no, f3(so.sky_d[i])); const float4 c = so.sky_c[i]; so.sky_c[i] = make_float4(c.x * T, c.y * T, c.z * T, 0.0f); }
-            if (reqMask & 2u) { const float T = volumes_transmittance(sc, no, f3(so.lit_d[i])); const float4 c = so.lit_c[i]; so.lit_c[i] = make_float4(c.x * T, c.y * T, c.z * T, 0.0f); }
-        }
-        ps.org_pdf[i] = make_float4(no.x, no.y, no.z, ss.PDF);
-        ps.dir_rng[i] = make_float4(scatterW.x, scatterW.y, scatterW.z, __uint_as_float(rng.s));
-        so.bxdf_pdf[i] = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
-        so.e0[i] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(newDepth | (reqMask << 29) | (newInMedium ? 0x80000000u : 0u)));   // bits 29/30: stored shadow requests
     }
-    for (int o = 16; o > 0; o >>= 1) n_med += __shfl_down_sync(0xFFFFFFFFu, n_med, o);
-    if ((threadIdx.x & 31) == 0 && n_med) atomicAdd(&ctr->medium_events, (unsigned long long)n_med);
+    for (int o = 16; o > 0; o >>= 1) { n_med += __shfl_down_sync(0xFFFFFFFFu, n_med, o); n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o); n_ext += __shfl_down_sync(0xFFFFFFFFu, n_ext, o); }
+    if (lane == 0 && n_med) atomicAdd(&ctr->medium_events, (unsigned long long)n_med);
+    if (FUSE && lane == 0 && n_shadow) atomicAdd(&ctr->shadow_rays, (unsigned long long)n_shadow);
+    if (FUSE == 2 && lane == 0 && n_ext) atomicAdd(&ctr->extend_rays, (unsigned long long)n_ext);
     if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr->shade_invocations, (unsigned long long)n); atomicAdd(&ctr->surface_hits, (unsigned long long)n); }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_connect : shadow queries + SH/RayGen.slang:92-113 + stream compaction of the survivors
+// k_connect : shadow queries + SH/RayGen.slang:92-113 + stream compaction of the survivors (unfused pipeline; walks every hit queue)
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM, bool TRACE>   // TRACE = false: k_shadow_dyn already cleared the request bits of occluded rays; only the join / roulette / compaction runs here
 __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, PathState src, PathState dst, ShadeOut so,
-                                                  uint32_t *__restrict__ ctrl, uint32_t parity, const uint32_t *__restrict__ q_hit,
+                                                  uint32_t *__restrict__ ctrl, uint32_t parity, Queues q,
                                                   float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry,
                                                   int max_stack, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -393,7 +587,8 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
     BvhView bv;
     if (SMEM && TRACE) bv = stage_bvh_smem(sc, smem + (size_t)max_stack * blockDim.x * sizeof(int), &bar);
     else bv = global_bvh(sc);
-    const uint32_t n = ctrl[2u + 2u * parity];                               // paths that hit a surface this bounce (misses ended in k_shade_miss)
+    const HitSpan span = hit_span(ctrl, parity);
+    const uint32_t n = span.n;                                              // paths that hit a surface this bounce (misses ended in k_shade_miss)
     uint32_t *n_next_ptr = ctrl + (parity ^ 1u);
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t n_shadow = 0;
@@ -401,11 +596,11 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
         const bool active = j < n;
         bool alive = false;
-        float4 o4, d4, r4, thr4; uint32_t newDflags = 0; Rng rng; rng.s = 0;
+        float4 o4, d4, r4; uint32_t newDflags = 0; Rng rng; rng.s = 0;
         float3 thr = f3(0.0f), rad = f3(0.0f);
         uint32_t i = 0;
         if (active) {
-            i = q_hit[j];
+            i = hit_entry(q, span, j);
             const float4 e4 = so.e0[i];
             uint32_t pending = (__float_as_uint(e4.w) >> 29) & 3u;         // bit 0: sky request, bit 1: light request (k_shade_hit)
             newDflags = __float_as_uint(e4.w) & 0x9FFFFFFFu;
@@ -444,34 +639,11 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
                 }
             }
             // the path state is fetched only now: nothing but the emission and the request bits is live across the traversal loop
-            thr4 = src.thr_depth[i]; r4 = src.rad_slot[i];
+            const float4 thr4 = src.thr_depth[i]; r4 = src.rad_slot[i];
             o4 = src.org_pdf[i]; d4 = src.dir_rng[i];
             const float4 b4 = so.bxdf_pdf[i];
             rng.s = __float_as_uint(d4.w);
-            thr = f3(thr4); rad = f3(r4);
-            // SH/RayGen.slang:92-113
-            float3 contribution = emitted * thr;
-            if (newDepth != 1u) {                                           // Q3
-                const float lum = dot(contribution, f3(0.212671f, 0.715160f, 0.072169f));
-                const float scale = cfg.MaxLuminance / fmaxf(lum, cfg.MaxLuminance);
-                contribution = contribution * scale;
-            }
-            rad = rad + contribution;
-            thr = thr * (f3(b4) / b4.w);
-            float p = fmaxf(thr.x, fmaxf(thr.y, thr.z));
-            p = fminf(p, 1.0f);
-            const float u = rng.next();                                     // Q4
-            alive = !(p < u);
-            if (alive) thr = thr / p;
-            alive = alive && (newDepth < cfg.MaxDepth);                      // loop condition :66
-            if (!alive) {                                                   // path finished: :116-128 (+ carry RNG for SampleCount > 1)
-                const uint32_t slot = __float_as_uint(r4.w);
-                const bool ok = !isinf(rad.x) && !isinf(rad.y) && !isinf(rad.z) && !isnan(rad.x) && !isnan(rad.y) && !isnan(rad.z);
-                float4 acc = sample_buf[slot];
-                if (ok) { acc.x += rad.x; acc.y += rad.y; acc.z += rad.z; }
-                sample_buf[slot] = acc;
-                rng_carry[slot] = rng.s;
-            }
+            alive = path_epilogue(cfg, emitted, b4, newDepth, thr4, r4, rng, thr, rad, sample_buf, rng_carry);
         }
         // ---- warp ballot + prefix-sum compaction of the live paths
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
@@ -499,9 +671,8 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
 //   control block additions: ctrl[8+p] = fetch counter of k_extend_dyn, ctrl[10+p] = fetch counter of k_shadow_dyn (p = bounce parity)
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM, bool PRIMARY, bool WIDE>   // WIDE: BVH4 nodes (sc.nodes4) instead of the BVH2
-__global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, ShadeOut so, uint32_t *__restrict__ ctrl, uint32_t parity,
-                                                     uint32_t *__restrict__ q_hit, uint32_t *__restrict__ q_miss, int max_stack, int thresh,
-                                                     WaveCounters *ctr) {
+__global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, float4 *__restrict__ hit_out, uint32_t *__restrict__ ctrl, uint32_t parity,
+                                                     Queues q, int max_stack, int thresh, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
@@ -511,13 +682,12 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, S
     else bv = global_bvh(sc);
     const uint32_t n = ctrl[parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) {                              // counters of the NEXT bounce (last used two bounces ago)
-        const uint32_t q = parity ^ 1u;
-        ctrl[q] = 0; ctrl[2u + 2u * q] = 0; ctrl[3u + 2u * q] = 0; ctrl[8u + q] = 0; ctrl[10u + q] = 0;
+        ctrl_reset_parity(ctrl, parity ^ 1u);
         atomicAdd(&ctr->extend_rays, (unsigned long long)n);
     }
-    unsigned long long *q_count = reinterpret_cast<unsigned long long *>(ctrl + 2u + 2u * parity);
+    uint32_t *qc = ctrl + CTRL_Q + 8u * parity;
     uint32_t *fetch = ctrl + 8u + parity;
-    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t s_base = smem_u32(stack), s_step = blockDim.x * 4u, s_limit = s_base + (uint32_t)(max_stack + 1) * s_step;
     DynPool pool; pool.init(n, gridDim.x * (blockDim.x >> 5));
     DynRay r; r.cur = DYN_DONE; r.gid = DYN_NONE; r.t = 0.0f; r.u = 0.0f; r.v = 0.0f; r.s_top = s_base; r.n_spill = 0;
@@ -526,26 +696,20 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, S
     if (WIDE) bv.root = 0;                                                  // the BVH4 root is node 0 (bvh4_collapse_host)
     uint32_t i = DYN_NONE;
     while (true) {
-        // ---- commit finished rays: hit record + hit / miss queue entry (one 64-bit atomic per refill event)
+        // ---- commit finished rays: hit record + miss / class queue entry (one multi-address atomic per refill event)
         const bool fin = (r.cur == DYN_DONE);
         const bool have = fin && i != DYN_NONE;
         const bool hit = have && r.gid != DYN_NONE;
-        if (have && r.gid != VOLUME_EVENT) so.hit[i] = make_float4(hit ? r.t : -1.0f, r.u, r.v, __uint_as_float(r.gid));
-        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, have && !hit);
-        if (bh | bm) {
-            unsigned long long base = 0ull;
-            if (lane == 0) base = atomicAdd(q_count, ((unsigned long long)__popc(bm) << 32) | (unsigned long long)__popc(bh));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (hit) q_hit[(uint32_t)base + (uint32_t)__popc(bh & lt)] = i;
-            else if (have) q_miss[(uint32_t)(base >> 32) + (uint32_t)__popc(bm & lt)] = i;
-        }
+        if (have && r.gid != VOLUME_EVENT) hit_out[i] = make_float4(hit ? r.t : -1.0f, r.u, r.v, __uint_as_float(r.gid));
+        const uint32_t code = hit ? hit_code(sc, r.gid) : (have ? 0u : Q_NONE);
+        if (__ballot_sync(0xFFFFFFFFu, have)) queue_append(code, i, qc, q, lane);
         // ---- refill
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, fin);
         if (need) {
             const uint32_t idx = pool.take(need, lane, fetch);
             if (fin) {
                 i = idx;
-                if (i != DYN_NONE && sc.n_volumes && __float_as_uint(so.hit[i].w) == VOLUME_EVENT) {
+                if (i != DYN_NONE && sc.n_volumes && __float_as_uint(hit_out[i].w) == VOLUME_EVENT) {
                     r.gid = VOLUME_EVENT;                                   // scattered inside a volume (k_volume_decide): queued as a hit at the next commit, record kept
                 } else if (i != DYN_NONE) {
                     const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
@@ -570,12 +734,12 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, S
     }
 }
 
-// Shadow requests of the hit queue, compacted per warp: ring entry = (path index << 1) | kind (0 sky, 1 light).
+// Shadow requests of the hit queues, compacted per warp: ring entry = (path index << 1) | kind (0 sky, 1 light).
 // An occluded ray clears its request bit in e0.w (bit 29 sky, bit 30 light); k_connect<.., false> joins the surviving requests.
 constexpr size_t DYN_RING_BYTES = 8 * 128 * sizeof(uint32_t);              // per-CTA request rings of k_shadow_dyn (dynamic shared memory, after the stacks)
 template <bool SMEM, bool WIDE>
 __global__ void __launch_bounds__(256, 4) k_shadow_dyn(DevScene sc, ShadeOut so, uint32_t *__restrict__ ctrl, uint32_t parity,
-                                                     const uint32_t *__restrict__ q_hit, int max_stack, int thresh, WaveCounters *ctr) {
+                                                     Queues q, int max_stack, int thresh, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
@@ -585,7 +749,8 @@ __global__ void __launch_bounds__(256, 4) k_shadow_dyn(DevScene sc, ShadeOut so,
     BvhView bv;
     if (SMEM) bv = stage_bvh_smem(sc, smem + stack_bytes + DYN_RING_BYTES, &bar);
     else bv = global_bvh(sc);
-    const uint32_t n = ctrl[2u + 2u * parity];                               // hit-queue length of this bounce
+    const HitSpan span = hit_span(ctrl, parity);
+    const uint32_t n = span.n;                                              // total hit-queue length of this bounce
     uint32_t *fetch = ctrl + 10u + parity;
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     uint32_t *ring = ring_all + (threadIdx.x >> 5) * 128u;
@@ -605,7 +770,7 @@ __global__ void __launch_bounds__(256, 4) k_shadow_dyn(DevScene sc, ShadeOut so,
         while (tail - head < cnt && !pool.empty()) {
             const uint32_t j = pool.take(0xFFFFFFFFu, lane, fetch);
             uint32_t pend = 0, i = 0;
-            if (j != DYN_NONE) { i = q_hit[j]; pend = (__float_as_uint(so.e0[i].w) >> 29) & 3u; }
+            if (j != DYN_NONE) { i = hit_entry(q, span, j); pend = (__float_as_uint(so.e0[i].w) >> 29) & 3u; }
             const uint32_t c = (pend & 1u) + (pend >> 1);
             uint32_t incl = c;
             #pragma unroll
@@ -691,8 +856,9 @@ __global__ void __launch_bounds__(256) k_volume_decide(DevScene sc, PathState ps
 
 // EvaluateVolumeScatteringEvent (SH/RayGen.slang:265-380) for the flagged entries of the hit queue
 __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so, const uint32_t *__restrict__ ctrl, uint32_t parity,
-                                                      const uint32_t *__restrict__ q_hit, WaveCounters *ctr) {
-    const uint32_t n = ctrl[2u + 2u * parity];
+                                                      Queues q, WaveCounters *ctr) {
+    const uint32_t n = ctrl[CTRL_Q + 8u * parity + 1u + MC_GENERAL];          // volume events are queued with the general class (hit_code)
+    const uint32_t *__restrict__ q_hit = q.hit + (size_t)MC_GENERAL * q.cap;
     uint32_t n_ev = 0;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const uint32_t i = q_hit[j];
@@ -845,14 +1011,20 @@ static size_t trace_smem_bytes(const DevScene &sc, int max_stack, int threads, b
     return (size_t)max_stack * threads * sizeof(int) + (smem ? sc.bvh_bytes : 0);
 }
 
-static bool g_attr_done = false;
-static void set_attrs_once() {
-    if (g_attr_done) return;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, and the C-ABI lets one process drive several GPUs
+// (b200pt_create(device, ..)): the opt-in is tracked per device ordinal.
+static unsigned long long g_attr_done_mask = 0ull;
+static int set_attrs_for_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+    if (dev >= 0 && dev < 64 && ((g_attr_done_mask >> dev) & 1ull)) return 0;
     // opt-in dynamic shared memory: the 227 KB per-CTA limit covers static + dynamic, so each kernel gets 227 KB minus its static part
-    auto optin = [](const void *f) {
+    int rc = 0;
+    auto optin = [&rc](const void *f) {
         cudaFuncAttributes a{};
-        if (cudaFuncGetAttributes(&a, f) != cudaSuccess) return;
-        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)a.sharedSizeBytes);
+        cudaError_t e = cudaFuncGetAttributes(&a, f);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)a.sharedSizeBytes);
+        if (e != cudaSuccess && rc == 0) rc = (int)e;
     };
     optin((const void *)k_extend<true, true>); optin((const void *)k_extend<true, false>);
     optin((const void *)k_extend<false, true>); optin((const void *)k_extend<false, false>);
@@ -863,13 +1035,17 @@ static void set_attrs_once() {
     optin((const void *)k_shadow_dyn<true, false>); optin((const void *)k_shadow_dyn<false, false>); optin((const void *)k_shadow_dyn<false, true>);
     optin((const void *)k_trace_rays<true>); optin((const void *)k_trace_rays<false>);
     optin((const void *)k_volume_decide<true>); optin((const void *)k_volume_decide<false>);
+#define B200PT_OPTIN_BOUNCE(C) optin((const void *)k_shade_hit<C, false, 1>); optin((const void *)k_shade_hit<C, false, 2>);
+    B200PT_OPTIN_BOUNCE(MC_DIFFUSE) B200PT_OPTIN_BOUNCE(MC_METAL) B200PT_OPTIN_BOUNCE(MC_GLASS) B200PT_OPTIN_BOUNCE(MC_GENERAL)
+#undef B200PT_OPTIN_BOUNCE
     cudaGetLastError();
-    g_attr_done = true;
+    if (rc == 0 && dev >= 0 && dev < 64) g_attr_done_mask |= 1ull << dev;
+    return rc;
 }
 
 // grid sizing: persistent grids = SM count x resident CTAs per SM for the chosen shared-memory footprint
 int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, LaunchCfg *lc) {
-    set_attrs_once();
+    { const int a = set_attrs_for_current_device(); if (a != 0) return a; }
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceProp prop; cudaError_t e = cudaGetDeviceProperties(&prop, dev);
     if (e != cudaSuccess) return (int)e;
@@ -895,8 +1071,12 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
         lc->dyn_stack = need < cap ? need : cap;
         if (need - lc->dyn_stack > DYN_SPILL) lc->wide = false, lc->dyn_stack = lc->max_stack;   // deeper than shared column + overflow array: BVH2
     }
+    // fused bounce kernel (k_shade_hit<., ., 2>): scenes whose BVH is staged in shared memory and walked one ray per thread.  B200PT_FUSE=0|1|2 overrides
+    // (0: k_shade_hit + k_connect, 1: NEE queries and the path epilogue fused, k_extend separate, 2: next segment's TraceRay fused as well).
+    lc->fuse = (lc->bvh_in_smem && !lc->trav_dyn) ? 2 : 0;
+    if (const char *e = getenv("B200PT_FUSE")) { const int v = atoi(e); if (v >= 0 && v <= 2 && lc->bvh_in_smem && !lc->trav_dyn) lc->fuse = v; }
     const size_t sh_dyn = trace_smem_bytes(sc, lc->dyn_stack + 1, 256, lc->bvh_in_smem);
-    int occ_e = 0, occ_c = 0, occ_s = 0, occ_sh = 0;
+    int occ_e = 0, occ_c = 0, occ_s = 0, occ_sh = 0, occ_b = 0;
     if (lc->trav_dyn) {
         if (lc->wide) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend_dyn<false, false, true>, 256, sh_dyn);
@@ -918,15 +1098,17 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
     }
     if (occ_sh < 1) occ_sh = 1;
     lc->grid_shadow = sms * occ_sh;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade_hit<false>, 128, 0);
-    if (occ_e < 1) occ_e = 1; if (occ_c < 1) occ_c = 1; if (occ_s < 1) occ_s = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade_hit<MC_GENERAL, false, 0>, 128, 0);
+    if (lc->bvh_in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_shade_hit<MC_GENERAL, false, 2>, 128, trace_smem_bytes(sc, lc->max_stack, 128, true));
+    if (occ_e < 1) occ_e = 1; if (occ_c < 1) occ_c = 1; if (occ_s < 1) occ_s = 1; if (occ_b < 1) occ_b = 1;
     lc->grid_extend = sms * occ_e; lc->grid_connect = sms * occ_c;
     lc->grid_trace = sms * occ_e;
     lc->grid_shade = sms * occ_s;
+    lc->grid_bounce = sms * occ_b;
     lc->grid_light = sms * 8;
     if (getenv("B200PT_DEBUG"))
-        fprintf(stderr, "[b200pt] launch cfg: bvh depth %d (bvh4 %d) max_stack %d dyn_stack %d bvh_bytes %u smem %d dyn %d wide %d thresh %d | CTAs/SM extend %d connect %d shadow %d shade %d\n",
-                bvh_max_depth, bvh4_depth, lc->max_stack, lc->dyn_stack, sc.bvh_bytes, (int)lc->bvh_in_smem, (int)lc->trav_dyn, (int)lc->wide, lc->dyn_thresh, occ_e, occ_c, occ_sh, occ_s);
+        fprintf(stderr, "[b200pt] launch cfg: bvh depth %d (bvh4 %d) max_stack %d dyn_stack %d bvh_bytes %u smem %d dyn %d wide %d thresh %d fuse %d | CTAs/SM extend %d connect %d shadow %d shade %d bounce %d\n",
+                bvh_max_depth, bvh4_depth, lc->max_stack, lc->dyn_stack, sc.bvh_bytes, (int)lc->bvh_in_smem, (int)lc->trav_dyn, (int)lc->wide, lc->dyn_thresh, lc->fuse, occ_e, occ_c, occ_sh, occ_s, occ_b);
     return 0;
 }
 
@@ -934,13 +1116,13 @@ void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch 
                    const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *ctrl, WaveCounters *ctr, cudaStream_t st) {
     k_raygen<<<lc.grid_light, 256, 0, st>>>(cfg, disp, n_disp, P, first_sample, rng_carry, ps, sample_buf, ctrl, ctr);
 }
-void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, uint32_t *ctrl, uint32_t parity, uint32_t *q_hit, uint32_t *q_miss,
+void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, float4 *hit_out, uint32_t *ctrl, uint32_t parity, Queues q,
                    WaveCounters *ctr, bool primary, cudaStream_t st) {
-    set_attrs_once();
+    set_attrs_for_current_device();
     const bool smem = lc.bvh_in_smem;
     if (lc.trav_dyn) {
         const size_t sh = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem);
-#define B200PT_EXT_DYN(S, P, W) k_extend_dyn<S, P, W><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.dyn_stack, lc.dyn_thresh, ctr)
+#define B200PT_EXT_DYN(S, P, W) k_extend_dyn<S, P, W><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.dyn_stack, lc.dyn_thresh, ctr)
         if (lc.wide) { if (primary) B200PT_EXT_DYN(false, true, true); else B200PT_EXT_DYN(false, false, true); }
         else if (smem) { if (primary) B200PT_EXT_DYN(true, true, false); else B200PT_EXT_DYN(true, false, false); }
         else { if (primary) B200PT_EXT_DYN(false, true, false); else B200PT_EXT_DYN(false, false, false); }
@@ -949,42 +1131,54 @@ void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeO
     }
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
     if (smem) {
-        if (primary) k_extend<true, true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
-        else k_extend<true, false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+        if (primary) k_extend<true, true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
+        else k_extend<true, false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
     } else {
-        if (primary) k_extend<false, true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
-        else k_extend<false, false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, so, ctrl, parity, q_hit, q_miss, lc.max_stack, ctr);
+        if (primary) k_extend<false, true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
+        else k_extend<false, false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
     }
 }
-void launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity,
-                  const uint32_t *q_hit, const uint32_t *q_miss, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
-    k_shade_miss<<<lc.grid_light, 256, 0, st>>>(sc, cfg, ps, ctrl, parity, q_miss, sample_buf, rng_carry, ctr);
-    if (sc.n_volumes) k_shade_hit<true><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q_hit, ctr);
-    else k_shade_hit<false><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q_hit, ctr);
-    if (sc.n_volumes) k_shade_volume<<<lc.grid_light, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q_hit, ctr);
+// k_shade_miss + one k_shade_hit<CLASS> per material class present in the scene (+ k_shade_volume).  fuse (0 / 1 / 2): see k_shade_hit.
+// Returns the number of kernels launched.
+int launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, PathState dst, ShadeOut so, const float4 *hit_in, float4 *hit_out,
+                 uint32_t *ctrl, uint32_t parity, Queues q, Queues q_next, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr,
+                 int fuse, uint32_t class_mask, cudaStream_t st) {
+    set_attrs_for_current_device();
+    int launched = 1;
+    k_shade_miss<<<lc.grid_light, 256, 0, st>>>(sc, cfg, ps, ctrl, parity, fuse == 2 ? 1u : 0u, q.miss, sample_buf, rng_carry, ctr);
+    const size_t shb = trace_smem_bytes(sc, lc.max_stack, 128, true);
+#define B200PT_SHADE(C) do { if (class_mask & (1u << C)) { launched++;                                                                                              \
+        if (fuse == 2) k_shade_hit<C, false, 2><<<lc.grid_bounce, 128, shb, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr);      \
+        else if (fuse == 1) k_shade_hit<C, false, 1><<<lc.grid_bounce, 128, shb, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr); \
+        else if (sc.n_volumes) k_shade_hit<C, true, 0><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr);   \
+        else k_shade_hit<C, false, 0><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr); } } while (0)
+    B200PT_SHADE(MC_DIFFUSE); B200PT_SHADE(MC_METAL); B200PT_SHADE(MC_GLASS); B200PT_SHADE(MC_GENERAL);
+#undef B200PT_SHADE
+    if (sc.n_volumes) { launched++; k_shade_volume<<<lc.grid_light, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q, ctr); }
+    return launched;
 }
 void launch_volume_decide(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity, cudaStream_t st) {
-    set_attrs_once();
+    set_attrs_for_current_device();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
     if (smem) k_volume_decide<true><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, lc.max_stack);
     else k_volume_decide<false><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, lc.max_stack);
 }
 void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,
-                    uint32_t *ctrl, uint32_t parity, const uint32_t *q_hit, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
-    set_attrs_once();
+                    uint32_t *ctrl, uint32_t parity, Queues q, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
+    set_attrs_for_current_device();
     const bool smem = lc.bvh_in_smem;
     if (lc.trav_dyn) {                                                      // shadow rays in their own dynamic-fetch kernel, then the join without tracing
         const size_t shd = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem) + DYN_RING_BYTES_HOST;
-#define B200PT_SH_DYN(S, W) k_shadow_dyn<S, W><<<lc.grid_shadow, 256, shd, st>>>(sc, so, ctrl, parity, q_hit, lc.dyn_stack, lc.dyn_thresh, ctr)
+#define B200PT_SH_DYN(S, W) k_shadow_dyn<S, W><<<lc.grid_shadow, 256, shd, st>>>(sc, so, ctrl, parity, q, lc.dyn_stack, lc.dyn_thresh, ctr)
         if (lc.wide) B200PT_SH_DYN(false, true); else if (smem) B200PT_SH_DYN(true, false); else B200PT_SH_DYN(false, false);
 #undef B200PT_SH_DYN
-        k_connect<false, false><<<lc.grid_connect, 256, 0, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
+        k_connect<false, false><<<lc.grid_connect, 256, 0, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
         return;
     }
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_connect<true, true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
-    else k_connect<false, true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q_hit, sample_buf, rng_carry, lc.max_stack, ctr);
+    if (smem) k_connect<true, true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
+    else k_connect<false, true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
 }
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
                     const float4 *sample_buf, float4 *image, cudaStream_t st) {
@@ -992,7 +1186,7 @@ void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch
 }
 void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, const float *org, const float *dir, float tmin, float tmax,
                        float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, uint32_t *stats, cudaStream_t st) {
-    set_attrs_once();
+    set_attrs_for_current_device();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
     if (smem) k_trace_rays<true><<<lc.grid_trace, 256, sh, st>>>(sc, n, org, dir, tmin, tmax, t_out, prim_out, inst_out, uv_out, lc.max_stack, stats);
