@@ -112,6 +112,17 @@ def synthetic_env_4k():
     return gltf_ref.synthetic_env(4096, 2048, seed=3, sun=150000.0)
 
 
+def bench_config(workload, frames_per_step, steps, world, extra=None):
+    """`config` of the JSON line: the same keys in both arms (the driver compares them)."""
+    scene, W, H, depth = WORKLOADS[workload]
+    c = {"workload": workload, "scene": scene, "image": [W, H], "max_depth": depth, "spp_per_frame": 1, "frames_per_step": frames_per_step,
+         "spp_total": frames_per_step * steps, "partition": f"{BAND_ROWS}-row bands x {world} ranks",
+         "env_map": "synthetic 4096x2048 RGBA32F (128 MiB) + 64 MiB alias table",
+         "l2_policy": "inputs larger than L2 (env map + alias table 192 MiB, wavefront state of a 16.6 M-path wave > 1 GB vs 126 MB L2): no explicit flush"}
+    if extra: c.update(extra)
+    return c
+
+
 def algorithmic_bytes(c):
     """SURVEY.md 8(d) streaming model, per kernel, from the device counters of one step."""
     return {
@@ -128,33 +139,52 @@ def diff_counters(a, b):
     return {k: (b[k] - a[k]) for k in ("paths", "extend_rays", "shade_invocations", "surface_hits", "misses", "shadow_rays", "medium_events", "kernel_launches")}
 
 
+def cpu_arm_threads(info):
+    import math
+    return max(1, min(info["logical_cpus"], int(math.ceil(info["effective_cpus"]))))
+
+
+def cpu_arm_describe(info, nthreads, sample):
+    return {"cores": nthreads, "kind": "port", "sample": sample, "build": "oracle/liboracle_fast.so: gcc -O3 -march=native, compiled on this host",
+            "host": {"logical_cpus": info["logical_cpus"], "model": info["model"], "cgroup_cpu_max": info["cgroup_cpu_max"],
+                     "effective_cpus": info["effective_cpus"], "affinity_cpus": info.get("affinity_cpus")}}
+
+
 def run_reference(args):
-    """CPU arm: the oracle (port of the reference's Slang estimator) on all host cores; step = 1 frame."""
+    """CPU arm: the oracle (port of the reference's Slang estimator; the Vulkan reference cannot run here -- profiles/r02_vulkan_host_probe.txt),
+    -O3 -march=native build, one thread per CPU the cgroup quota grants; step = 1 frame; median of >= 3 timed repeats of the K steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import util
     from oracle import orc
+    orc.use_fast_build()
+    info = orc.host_cpu_info()
+    cores = cpu_arm_threads(info)
     scene, W, H, depth = WORKLOADS[args.workload]
     raw = synthetic_env_4k()
     env_pdf, alias, _ = orc.build_env_alias(raw)
     S = orc.Scene(util.scene_dict(scene), env_pdf, alias, util.luts())
     cfg = util.oracle_config(scene, MaxDepth=depth)
-    cores = os.cpu_count() or 1
     img = np.zeros((H, W, 4), np.float32)
     f = 0
     for _ in range(args.warmup):
         S.render(cfg, W, H, 1, BASE_SEED, frame0=f, image=img, nthreads=cores); f += 1
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        S.render(cfg, W, H, 1, BASE_SEED, frame0=f, image=img, nthreads=cores); f += 1
-    dt = time.perf_counter() - t0
+    reps = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            S.render(cfg, W, H, 1, BASE_SEED, frame0=f, image=img, nthreads=cores); f += 1
+        reps.append(time.perf_counter() - t0)
+    dt = sorted(reps)[1]
     v = W * H * args.steps / dt / 1e6
+    cb = cpu_arm_describe(info, cores, f"bounded sample: each step = 1 frame (1 spp of the full {W}x{H} image) of the workload's {args.frames_per_step}; "
+                                       f"{args.steps} steps, median of 3 repeats (pthreads over pixel rows)")
+    cb.update({"value": v, "unit": "Mpaths/s", "repeats_mpaths": [W * H * args.steps / r / 1e6 for r in reps]})
     out = {"impl": "reference", "metric": "Mpaths/sec", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": args.workload, "image": [W, H], "max_depth": depth, "spp_per_frame": 1, "frames_per_step": 1},
-           "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "port",
-                            "sample": f"{args.steps} frames x 1 spp of the full {W}x{H} image (oracle/liboracle.so, pthreads over pixel rows)"},
+           "config": bench_config(args.workload, args.frames_per_step, args.steps, max(args.gpus, 1)),   # the b200 arm's config; the bounded sample is in cpu_baseline.sample
+           "cpu_baseline": cb,
            "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out))
 
@@ -237,7 +267,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=128)
     ap.add_argument("--frames-in-flight", type=int, default=0)
     ap.add_argument("--workload", default="cornell_1080p_d8", choices=sorted(WORKLOADS) + ["post_4k", "lut_bake"])
-    ap.add_argument("--cpu-baseline-frames", type=int, default=6)
+    ap.add_argument("--cpu-baseline-frames", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3: args.warmup = 3
@@ -383,10 +413,9 @@ def main():
 
     out = {"metric": "Mpaths/sec", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": args.workload, "scene": scene, "image": [W, H], "max_depth": depth, "spp_per_frame": 1, "frames_per_step": F,
-                      "spp_total": F * args.steps, "partition": f"{BAND_ROWS}-row bands x {world} ranks", "env_map": "synthetic 4096x2048 RGBA32F (128 MiB) + 64 MiB alias table",
-                      "l2_policy": "working set > L2: env map 128 MiB + alias 64 MiB + wavefront state of a 16.6 M-path wave ~5 GB (126 MB L2), no explicit flush",
-                      "timing": "CUDA events on the launching stream, max over ranks", "wall_s": wall},
+           "config": bench_config(args.workload, F, args.steps, world),
+           "notes": {"l2_policy": "working set > L2: env map 128 MiB + alias 64 MiB + wavefront state of a 16.6 M-path wave (126 MB L2), no explicit flush",
+                     "timing": "CUDA events on the launching stream, max over ranks", "wall_s": wall},
            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
            "gpu_launches": int(dc["kernel_launches"]), "clocks": clocks, "roofline": roofline,
            "counters_per_step": {k: dc[k] / args.steps for k in dc}}
@@ -394,15 +423,20 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             from oracle import orc
+            orc.use_fast_build()
+            info = orc.host_cpu_info(); cores = cpu_arm_threads(info)
             env_pdf, alias, _ = orc.build_env_alias(raw)
             S = orc.Scene(util.scene_dict(scene), env_pdf, alias, util.luts())
             ocfg = util.oracle_config(scene, MaxDepth=depth)
-            cores = os.cpu_count() or 1
             n = args.cpu_baseline_frames
             S.render(ocfg, W, H, 1, BASE_SEED, nthreads=cores)
-            t0 = time.perf_counter(); S.render(ocfg, W, H, n, BASE_SEED, frame0=1, nthreads=cores); dt = time.perf_counter() - t0
-            out["cpu_baseline"] = {"value": W * H * n / dt / 1e6, "unit": "Mpaths/s", "cores": cores, "kind": "port",
-                                   "sample": f"{n} frames x 1 spp of the full {W}x{H} image (CPU oracle, all host cores)"}
+            reps = []
+            for r in range(3):
+                t0 = time.perf_counter(); S.render(ocfg, W, H, n, BASE_SEED, frame0=1 + r * n, nthreads=cores); reps.append(time.perf_counter() - t0)
+            dt = sorted(reps)[1]
+            cb = cpu_arm_describe(info, cores, f"{n} frames x 1 spp of the full {W}x{H} image, median of 3 repeats (CPU oracle)")
+            cb.update({"value": W * H * n / dt / 1e6, "unit": "Mpaths/s", "repeats_mpaths": [W * H * n / r / 1e6 for r in reps]})
+            out["cpu_baseline"] = cb
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -149,6 +149,30 @@ int32_t b200pt_remove_volume(b200pt_handle h, uint32_t index);                  
 int32_t b200pt_volume_count(b200pt_handle h, uint32_t *out);
 int32_t b200pt_get_volume(b200pt_handle h, uint32_t index, b200pt_volume *out);          /* GetVolumes()[index] */
 int32_t b200pt_add_density_data_to_volume(b200pt_handle h, uint32_t index, const char *vdb_path);   /* AddDensityDataToVolume: NOT_IMPLEMENTED */
+int32_t b200pt_remove_density_data_from_volume(b200pt_handle h, uint32_t index);                    /* RemoveDensityDataFromVolume: NOT_IMPLEMENTED */
+/* ---- atmosphere: the twelve setters / getters of PathTracer.h:129-144,170-181 (members :221-232) as one parameter block.
+ * The parameters are stored and returned like the reference's members (any set -> ResetPathTracing()); rendering WITH the atmosphere
+ * (SH/Atmosphere.slang, SH/RayGen.slang:382-471: delta tracking per colour channel, sun NEE) is a SURVEY 8f "next" row that is not built:
+ * b200pt_set_atmosphere with Enable != 0 returns B200PT_ERR_NOT_IMPLEMENTED and leaves the stored block unchanged. */
+typedef struct {
+    uint32_t Enable;                                    /* SetEnableAtmosphere (false)                         */
+    float    PlanetPosition[3];                         /* SetPlanetPosition   (0, 6360e3 + 1000, 0) metres    */
+    float    PlanetRadius;                              /* SetPlanetRadius     (6360e3)                        */
+    float    AtmosphereHeight;                          /* SetAtmosphereHeight (100e3)                         */
+    float    RayleighScatteringCoefficientMultiplier[3];/* (1, 1, 1)                                           */
+    float    MieScatteringCoefficientMultiplier[3];     /* (1, 1, 1)                                           */
+    float    OzoneAbsorptionCoefficientMultiplier[3];   /* (1, 1, 1)                                           */
+    float    RayleighDensityFalloff;                    /* (8000)                                              */
+    float    MieDensityFalloff;                         /* (1200)                                              */
+    float    OzoneDensityFalloff;                       /* (5000)                                              */
+    float    OzonePeak;                                 /* (22000)                                             */
+    float    SunColor[3];                               /* SetSunColor (1, 0.956, 0.88)                        */
+} b200pt_atmosphere;
+int32_t b200pt_default_atmosphere(b200pt_atmosphere *out);
+int32_t b200pt_set_atmosphere(b200pt_handle h, const b200pt_atmosphere *a);
+int32_t b200pt_get_atmosphere(b200pt_handle h, b200pt_atmosphere *out);
+/* PathTracer::GetTotalVertexCount / GetTotalIndexCount (PathTracer.h:122-123): summed over the loaded meshes */
+int32_t b200pt_get_total_counts(b200pt_handle h, uint64_t *vertex_count_out, uint64_t *index_count_out);
 /* PathTracer::SetPhaseFunction (PathTracer.h:76-81,168-169): 0 Henyey-Greenstein, 1 Draine, 2 Henyey-Greenstein + Draine */
 int32_t b200pt_set_phase_function(b200pt_handle h, uint32_t phase_function);
 int32_t b200pt_get_phase_function(b200pt_handle h, uint32_t *out);

@@ -56,7 +56,39 @@ class OrcPostConfig(C.Structure):
                 ("FalloffRange", C.c_float), ("MipCount", C.c_uint32)]
 
 
+_FAST = False
+
+
+def use_fast_build():
+    """bench.py's CPU arm only: time the -O3 -march=native build (oracle/Makefile target `fast`), compiled on this host.  Must be called before
+    the first lib() of the process; the parity tests never call it (they need the strict-IEEE, contraction-free build)."""
+    global _FAST
+    if _LIB is not None and not _FAST: raise RuntimeError("use_fast_build() after the strict oracle library was loaded")
+    _FAST = True
+
+
+def host_cpu_info():
+    """What the CPU arm really has: logical CPUs, model name, cgroup v2 CPU quota (the GPU boxes cap a 128-thread host at a few CPUs' worth of time)."""
+    info = {"logical_cpus": os.cpu_count() or 1, "model": None, "cgroup_cpu_max": None, "effective_cpus": float(os.cpu_count() or 1)}
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"): info["model"] = line.split(":", 1)[1].strip(); break
+    except OSError: pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        info["cgroup_cpu_max"] = f"{q} {per}"
+        if q != "max": info["effective_cpus"] = min(info["effective_cpus"], float(q) / float(per))
+    except (OSError, ValueError): pass
+    try: info["affinity_cpus"] = len(os.sched_getaffinity(0)); info["effective_cpus"] = min(info["effective_cpus"], float(info["affinity_cpus"]))
+    except (AttributeError, OSError): pass
+    return info
+
+
 def build(force=False):
+    if _FAST:
+        so = os.path.join(_HERE, "liboracle_fast.so")
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "fast"])      # always rebuilt: -march=native must match THIS host
+        return so
     so = os.path.join(_HERE, "liboracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("pt_oracle.c", "post_oracle.c", "io_oracle.c", "pt_oracle.h", "orc_math.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):

@@ -480,6 +480,22 @@ def test_refine_plumbing_with_cuda_shims(tmp_path):
     assert r.stdout.count(": ok,") == 36                                          # 6 scenes x modes 0..5
 
 
+def test_atmosphere_block_defaults_match_the_reference_members():
+    """b200pt_atmosphere = the twelve atmosphere members of PathTracer.h:221-232 behind their setters / getters (:129-144,170-181)."""
+    import ctypes as C
+    L = pt.lib()
+    a = pt.Atmosphere()
+    assert C.sizeof(a) == 88
+    assert L.b200pt_default_atmosphere(C.byref(a)) == pt.OK
+    assert a.Enable == 0 and tuple(a.PlanetPosition) == (0.0, np.float32(6360e3 + 1000.0), 0.0) and a.PlanetRadius == np.float32(6360e3)
+    assert a.AtmosphereHeight == 100e3 and tuple(a.SunColor) == (1.0, np.float32(0.956), np.float32(0.88))
+    assert (a.RayleighDensityFalloff, a.MieDensityFalloff, a.OzoneDensityFalloff, a.OzonePeak) == (8000.0, 1200.0, 5000.0, 22000.0)
+    for v in (a.RayleighScatteringCoefficientMultiplier, a.MieScatteringCoefficientMultiplier, a.OzoneAbsorptionCoefficientMultiplier): assert tuple(v) == (1.0, 1.0, 1.0)
+    assert L.b200pt_default_atmosphere(None) == pt.ERR_WRONG_ARGUMENTS
+    assert L.b200pt_set_atmosphere(None, C.byref(a)) == pt.ERR_WRONG_ARGUMENTS and L.b200pt_get_total_counts(None, None, None) == pt.ERR_WRONG_ARGUMENTS
+    assert L.b200pt_remove_density_data_from_volume(None, 0) == pt.ERR_NOT_IMPLEMENTED
+
+
 def test_volume_struct_and_defaults_without_gpu():
     """b200pt_volume mirrors PathTracer::Volume (PT/PathTracer.h:36-70): layout and defaults are checked on the CPU."""
     import ctypes as C

@@ -154,6 +154,13 @@ def lib():
     return _LIB
 
 
+class Atmosphere(C.Structure):      # b200pt_atmosphere (include/b200pt.h)
+    _fields_ = [("Enable", C.c_uint32), ("PlanetPosition", C.c_float * 3), ("PlanetRadius", C.c_float), ("AtmosphereHeight", C.c_float),
+                ("RayleighScatteringCoefficientMultiplier", C.c_float * 3), ("MieScatteringCoefficientMultiplier", C.c_float * 3),
+                ("OzoneAbsorptionCoefficientMultiplier", C.c_float * 3), ("RayleighDensityFalloff", C.c_float), ("MieDensityFalloff", C.c_float),
+                ("OzoneDensityFalloff", C.c_float), ("OzonePeak", C.c_float), ("SunColor", C.c_float * 3)]
+
+
 def declared_symbols():
     """Every function name declared in include/b200pt.h."""
     import re

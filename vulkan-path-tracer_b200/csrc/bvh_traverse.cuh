@@ -10,7 +10,7 @@
 
 namespace b200pt {
 
-struct BvhView { const float4 *nodes; const float4 *tris; int root; };
+struct BvhView { const float4 *nodes; const float4 *tris; int root; uint32_t n_flat; };   // n_flat != 0: no hierarchy, test slots [0, n_flat) in order (tiny scenes in shared memory)
 struct HitRec { float t, u, v; uint32_t slot; uint32_t gid; };   // slot: BvhTri (reference) slot; gid: triangle id in (instance, primitive) order
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+/sm_100a) ----
@@ -52,11 +52,22 @@ __device__ __forceinline__ BvhView stage_bvh_smem(const DevScene &sc, unsigned c
     BvhView v;
     v.nodes = reinterpret_cast<const float4 *>(dst);
     v.tris = reinterpret_cast<const float4 *>(dst + (size_t)sc.n_nodes * sizeof(BvhNode));
-    v.root = sc.root;
+    v.root = sc.root; v.n_flat = sc.n_flat;
     return v;
 }
+// Stage `bytes` (multiple of 16) of read-only data into shared memory: same TMA bulk-copy + mbarrier protocol, used for the BVH4 treelet.
+__device__ __forceinline__ void stage_bytes_smem(unsigned char *dst, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    if (threadIdx.x == 0) { mbar_init(bar, 1); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, bytes);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(src_gmem);
+        for (uint32_t off = 0; off < bytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, min(32768u, bytes - off), bar);
+    }
+    mbar_wait(bar, 0);
+}
 __device__ __forceinline__ BvhView global_bvh(const DevScene &sc) {
-    BvhView v; v.nodes = reinterpret_cast<const float4 *>(sc.nodes); v.tris = reinterpret_cast<const float4 *>(sc.tris); v.root = sc.root; return v;
+    BvhView v; v.nodes = reinterpret_cast<const float4 *>(sc.nodes); v.tris = reinterpret_cast<const float4 *>(sc.tris); v.root = sc.root; v.n_flat = 0u; return v;
 }
 
 template <bool SMEM> __device__ __forceinline__ float4 ld4(const float4 *p) {
@@ -117,6 +128,30 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
     h.slot = 0xFFFFFFFFu; h.gid = 0xFFFFFFFFu; h.t = tmax; h.u = 0.0f; h.v = 0.0f;
     uint32_t best_gid = 0xFFFFFFFFu;
     bool found = false;
+    // one triangle slot; returns true when an ANYHIT query is decided
+    auto test_slot = [&](uint32_t slot) -> bool {
+        if (COUNT) (*n_tris)++;
+        const float4 *tp = b.tris + (size_t)slot * 3;
+        const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
+        float t, u, v;
+        if (tri_test(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax_test, t, u, v)) {
+            const uint32_t gid = __float_as_uint(ta.w);
+            if (TARGET && !(t < tmax || gid < target_gid)) return false;
+            if (!found || t < h.t || (t == h.t && gid < best_gid)) {
+                found = true; h.t = t; h.u = u; h.v = v; h.slot = slot; h.gid = gid; best_gid = gid;
+                if (ANYHIT) return true;
+            }
+        }
+        return false;
+    };
+    // Flat mode (SMEM only): a scene of a handful of triangles (the 12-triangle Cornell box) is tested slot by slot with no hierarchy -- every
+    // lane walks the same slots (shared-memory broadcasts, no stack, no divergence), which costs fewer instructions than the ~4 node steps +
+    // ~2.4 triangle tests of the SAH tree at half-empty warps (profiles/r02_ncu_bounce_lines.txt).  Same tests, same tie rule: identical hits.
+    if (SMEM && b.n_flat) {
+        for (uint32_t slot = 0; slot < b.n_flat; slot++) if (test_slot(slot)) return true;
+        if (!found) h.t = -1.0f;
+        return found;
+    }
     const float3 inv = f3(slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z));
     const float3 oi = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
     const uint32_t s_base = smem_u32(stack), s_step = (uint32_t)stride * 4u, s_limit = s_base + (uint32_t)max_stack * s_step;
@@ -161,21 +196,7 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
         } else {
             const uint32_t ref = (uint32_t)(~cur);                            // leaf: up to 4 consecutive Morton slots
             const uint32_t first = ref >> 2, count = (ref & 3u) + 1u;
-            for (uint32_t q = 0; q < count; q++) {
-                const uint32_t slot = first + q;
-                if (COUNT) (*n_tris)++;
-                const float4 *tp = b.tris + (size_t)slot * 3;
-                const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
-                float t, u, v;
-                if (tri_test(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax_test, t, u, v)) {
-                    const uint32_t gid = __float_as_uint(ta.w);
-                    if (TARGET && !(t < tmax || gid < target_gid)) continue;
-                    if (!found || t < h.t || (t == h.t && gid < best_gid)) {
-                        found = true; h.t = t; h.u = u; h.v = v; h.slot = slot; h.gid = gid; best_gid = gid;
-                        if (ANYHIT) return true;
-                    }
-                }
-            }
+            for (uint32_t q = 0; q < count; q++) if (test_slot(first + q)) return true;
         }
         if (s_top == s_base) break;
         s_top -= s_step;

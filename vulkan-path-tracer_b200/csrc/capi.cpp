@@ -130,6 +130,29 @@ int32_t b200pt_get_volume(b200pt_handle h, uint32_t i, b200pt_volume *out) {
     return guard(h, [&](Engine &e) { if (i >= e.volumes().size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume index out of range" }; *out = e.volumes()[i]; });
 }
 int32_t b200pt_add_density_data_to_volume(b200pt_handle h, uint32_t, const char *) { if (h) h->err = "NanoVDB density data is not implemented (SURVEY 8f row 1: needs a NanoVDB reader)"; return B200PT_ERR_NOT_IMPLEMENTED; }
+int32_t b200pt_remove_density_data_from_volume(b200pt_handle h, uint32_t) { if (h) h->err = "NanoVDB density data is not implemented (SURVEY 8f row 1)"; return B200PT_ERR_NOT_IMPLEMENTED; }
+int32_t b200pt_default_atmosphere(b200pt_atmosphere *a) {          // PathTracer.h:221-232
+    if (!a) return B200PT_ERR_WRONG_ARGUMENTS;
+    memset(a, 0, sizeof *a);
+    a->Enable = 0; a->PlanetPosition[0] = 0.0f; a->PlanetPosition[1] = 6360e3f + 1000.0f; a->PlanetPosition[2] = 0.0f;
+    a->PlanetRadius = 6360e3f; a->AtmosphereHeight = 100e3f;
+    for (int k = 0; k < 3; k++) { a->RayleighScatteringCoefficientMultiplier[k] = 1.0f; a->MieScatteringCoefficientMultiplier[k] = 1.0f; a->OzoneAbsorptionCoefficientMultiplier[k] = 1.0f; }
+    a->RayleighDensityFalloff = 8000.0f; a->MieDensityFalloff = 1200.0f; a->OzoneDensityFalloff = 5000.0f; a->OzonePeak = 22000.0f;
+    a->SunColor[0] = 1.0f; a->SunColor[1] = 0.956f; a->SunColor[2] = 0.88f;
+    return B200PT_OK;
+}
+int32_t b200pt_set_atmosphere(b200pt_handle h, const b200pt_atmosphere *a) {
+    if (!a) return B200PT_ERR_WRONG_ARGUMENTS;
+    return guard(h, [&](Engine &e) {
+        if (a->Enable) throw CudaError{ B200PT_ERR_NOT_IMPLEMENTED, "rendering with the atmosphere (SH/Atmosphere.slang) is not implemented: Enable must be 0" };
+        e.set_atmosphere(*a);
+    });
+}
+int32_t b200pt_get_atmosphere(b200pt_handle h, b200pt_atmosphere *out) { if (!out) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { *out = e.atmosphere(); }); }
+int32_t b200pt_get_total_counts(b200pt_handle h, uint64_t *nv, uint64_t *ni) {
+    if (!nv || !ni) return B200PT_ERR_WRONG_ARGUMENTS;
+    return guard(h, [&](Engine &e) { uint64_t v = 0, i = 0; for (const auto &m : e.scene().meshes) { v += m.vertices.size(); i += m.indices.size(); } *nv = v; *ni = i; });
+}
 int32_t b200pt_set_phase_function(b200pt_handle h, uint32_t pf) { return guard(h, [&](Engine &e) { e.set_phase_function(pf); }); }
 int32_t b200pt_get_phase_function(b200pt_handle h, uint32_t *out) { if (!out) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { *out = e.phase_function(); }); }
 

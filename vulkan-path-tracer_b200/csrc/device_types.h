@@ -117,11 +117,12 @@ struct DevScene {
     const EmTri *em_tris;
     const uint32_t *em_tri_base;   // per emissive mesh: first EmTri
     const DevVolume *volumes;      // homogeneous AABB volumes (volumes.cuh), n_volumes entries
+    uint32_t uniform_class;        // the one MaterialClass every triangle has, or 0xFF (k_extend then looks tri_class up per hit)
     uint32_t n_volumes, phase_function;   // phase_function: 0 HG, 1 Draine, 2 HG + Draine (PT/PathTracer.h:76-81)
-    uint32_t n_emissive, envW, envH, n_tris, n_nodes;
+    uint32_t n_emissive, envW, envH, n_tris, n_nodes, n_nodes4;
     int32_t root;            // child-style reference of the root
     uint32_t bvh_bytes;      // nodes+tris size if they are contiguous and small enough to stage in smem, else 0
-    uint32_t _pad;
+    uint32_t n_flat;         // != 0: the scene has so few triangle slots that shared-memory traversals test them all in order, no hierarchy (bvh_traverse.cuh)
 };
 
 // Shading classes = the lobe sets of SH/Material.slang:169-177 that a material can ever sample or evaluate.  The lobe probabilities are

@@ -33,6 +33,7 @@ Engine::Engine(int device) : device_(device) {
     CK(cudaMemset(d_ctr_, 0, sizeof(WaveCounters)));
     CK(cudaMalloc(&d_counts_, CTRL_WORDS * sizeof(uint32_t)));
     CK(cudaMallocHost(&h_count_, 4 * sizeof(uint32_t)));
+    b200pt_default_atmosphere(&atmosphere_);
     memset(&last_, 0, sizeof last_);
 }
 
@@ -140,11 +141,17 @@ void Engine::upload_scene() {
     rebuild_tri_class();
     ds_.textures = d_textures_; ds_.emissive = d_emissive_; ds_.nodes = bvh_.nodes; ds_.tris = bvh_.tris; ds_.shade_tris = bvh_.shade; ds_.tri_slot = bvh_.tri_slot;
     ds_.n_tris = bvh_.n_tris; ds_.n_nodes = bvh_.n_nodes; ds_.root = bvh_.root; ds_.bvh_bytes = bvh_.bytes <= 0xFFFFFFFFull ? (uint32_t)bvh_.bytes : 0;
-    ds_.nodes4 = nullptr;
+    ds_.nodes4 = nullptr; ds_.n_nodes4 = 0;
     if (bvh_.bytes > 64u * 1024u) {                                         // scenes that traverse out of L2/HBM get the BVH4 (host collapse of the GPU-built BVH2)
         r = lbvh_build_wide(&bvh_, stream_);
         if (r != 0) throw CudaError{ B200PT_ERR_CUDA, std::string("lbvh_build_wide failed: ") + cudaGetErrorString((cudaError_t)r) };
-        ds_.nodes4 = bvh_.nodes4;
+        ds_.nodes4 = bvh_.nodes4; ds_.n_nodes4 = bvh_.n_nodes4;
+    }
+    // A handful of triangle slots (the 12-triangle Cornell box): shared-memory traversals test them in order, no hierarchy (bvh_traverse.cuh).
+    {
+        uint32_t flat_max = 16;
+        if (const char *e = getenv("B200PT_FLAT_MAX")) { const int v = atoi(e); if (v >= 0 && v <= 64) flat_max = (uint32_t)v; }
+        ds_.n_flat = (bvh_.n_tris <= flat_max) ? bvh_.n_tris : 0u;
     }
     int q = query_launch_cfg(ds_, bvh_.max_depth, bvh_.depth4, &lc_);
     if (q != 0) throw CudaError{ B200PT_ERR_CUDA, "query_launch_cfg failed" };
@@ -193,6 +200,8 @@ void Engine::rebuild_tri_class() {
     }
     CK(cudaMemcpy(d_tri_class_, tc.data(), tc.size(), cudaMemcpyHostToDevice));
     ds_.tri_class = d_tri_class_;
+    ds_.uniform_class = 0xFFu;
+    for (uint32_t c = 0; c < MC_COUNT; c++) if (class_mask_ == (1u << c)) ds_.uniform_class = c;
 }
 
 // emissive-mesh list: PathTracer.cpp:458-469 (+ SetMaterial maintenance :712-810); keyed on constant EmissiveColor != 0 (Q16)
@@ -601,9 +610,19 @@ void Engine::post_process() {
     bool fused = mips >= 2;
     if (const char *e = getenv("B200PT_POST_FUSED")) { if (atoi(e) == 0) fused = false; }
     if (fused) {
+        // passes ls..mips-1 (every mip whose finer neighbour holds <= 160 K pixels) run inside one cluster launch (k_bloom_small); B200PT_POST_SMALL=0 restores one launch per pass
+        uint32_t ls = mips;
+        for (uint32_t i = 2; i < mips; i++) if ((uint64_t)mip_wh_[2 * (i - 1)] * mip_wh_[2 * (i - 1) + 1] <= 160u * 1024u) { ls = i; break; }
+        if (const char *e = getenv("B200PT_POST_SMALL")) { if (atoi(e) == 0) ls = mips; }
+        if (mips > 16) ls = mips;
         launch_bloom_down_first(d_image_, W_, H_, d_mips_[1], mip_wh_[2], mip_wh_[3], p, stream_);                               // :200-226, i == 0 and i == 1
-        for (uint32_t i = 2; i < mips; i++) launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_);
-        for (uint32_t i = mips - 1; i > 1; i--) launch_bloom_up(d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], p, stream_);   // :229-235
+        for (uint32_t i = 2; i < ls; i++) launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_);
+        if (ls < mips) {
+            SmallMips sm{}; sm.first = (int)ls; sm.last = (int)mips - 1;
+            for (uint32_t i = ls - 1; i < mips; i++) { sm.mip[i] = d_mips_[i]; sm.w[i] = (int)mip_wh_[2 * i]; sm.h[i] = (int)mip_wh_[2 * i + 1]; }
+            launch_bloom_small(sm, p, stream_);
+        }
+        for (uint32_t i = ls - 1; i > 1; i--) launch_bloom_up(d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], p, stream_);   // :229-235
         launch_bloom_final(d_image_, d_mips_[1], mip_wh_[2], mip_wh_[3], d_ldr_, keep_bloom_ ? d_mips_[0] : nullptr, W_, H_, p, stream_);   // last up pass + :238-245
         bloom_valid_ = keep_bloom_;
     } else {

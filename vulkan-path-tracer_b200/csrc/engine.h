@@ -29,6 +29,8 @@ public:
     const std::vector<b200pt_volume> &volumes() const { return volumes_; }
     void set_phase_function(uint32_t pf);
     uint32_t phase_function() const { return phase_function_; }
+    void set_atmosphere(const b200pt_atmosphere &a) { atmosphere_ = a; reset(); }     // parameters only (PathTracer.h:170-181); rendering with it is not built
+    const b200pt_atmosphere &atmosphere() const { return atmosphere_; }
     const HostScene &scene() const { return scene_; }
     bool has_scene() const { return has_scene_; }
     void set_camera(const float vi[16], const float pi[16]);
@@ -105,6 +107,7 @@ private:
     std::vector<DevInstance> h_instances_; std::vector<DevMesh> h_meshes_;
     float4 *d_env_ = nullptr; uint2 *d_alias_ = nullptr; float2 *d_env_row_cos_ = nullptr; float *d_luts_[3] = { nullptr, nullptr, nullptr };
     std::vector<b200pt_volume> volumes_; uint32_t phase_function_ = 0; DevVolume *d_volumes_ = nullptr;
+    b200pt_atmosphere atmosphere_{};
     LbvhResult bvh_{};
     LaunchCfg lc_{};
     uint32_t n_tris_ = 0, n_emissive_ = 0;

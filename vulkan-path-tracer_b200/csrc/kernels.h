@@ -17,6 +17,9 @@ struct LaunchCfg {
     int grid_shadow;    // persistent grid of k_shadow_dyn
     bool wide;          // the dynamic-fetch kernels walk the BVH4 (DevScene::nodes4)
     int dyn_stack;      // shared-memory stack entries per thread of the dynamic-fetch kernels (BVH4: overflow goes to local memory)
+    bool big;           // bvh_in_smem with a BVH > 64 KiB: one 512-thread CTA per SM for k_extend and the fused bounce kernels
+    int extend_threads; // CTA size of k_extend (256, big: 512)
+    int n_top4;         // BVH4 nodes (top levels, breadth-first prefix) staged into shared memory by the dynamic-fetch kernels
     int fuse;           // 0: k_shade_hit + k_connect; 1: NEE queries + path epilogue inside k_shade_hit; 2: + the next segment's TraceRay (one kernel per bounce and class)
     int grid_bounce;    // persistent grid of the fused k_shade_hit instantiations (BVH + stacks in shared memory)
 };
@@ -71,6 +74,9 @@ void launch_bloom_down(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst,
 // fused chain: threshold folded into the first down pass (mip 0 is never written) and [last up pass + threshold + tonemap] in one kernel
 void launch_bloom_down_first(const float4 *hdr, uint32_t W, uint32_t H, float4 *mip1, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st);
 void launch_bloom_final(const float4 *hdr, const float4 *mip1, uint32_t mw, uint32_t mh, uchar4 *ldr, float4 *mip0_out, uint32_t W, uint32_t H, PostParams p, cudaStream_t st);
+// passes first..last of the chain (down first..last, then up last..first) in one cluster launch; mip[i] / w[i] / h[i] for i in [first-1, last]
+struct SmallMips { float4 *mip[16]; int w[16], h[16]; int first, last; };
+void launch_bloom_small(const SmallMips &m, PostParams p, cudaStream_t st);
 void launch_bloom_up(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st);
 void launch_tonemap(const float4 *hdr, const float4 *bloom0, uchar4 *ldr, uint32_t W, uint32_t H, PostParams p, cudaStream_t st);
 void launch_prepare_materials(DevMaterial *mats, uint32_t first, uint32_t count, cudaStream_t st);   // fills DevMaterial::pre0..pre3

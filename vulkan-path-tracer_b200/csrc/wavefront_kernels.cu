@@ -134,7 +134,7 @@ __device__ __forceinline__ void queue_append(uint32_t code, uint32_t entry, uint
 //            (material-sorted shading: every k_shade_hit<CLASS> warp runs one lobe set, converged)
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM, bool PRIMARY>   // PRIMARY: camera rays (origin anywhere) -> exact slab arithmetic; later bounces start on scene surfaces -> FMA slabs
-__global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, float4 *__restrict__ hit_out, uint32_t *__restrict__ ctrl, uint32_t parity,
+__global__ void __launch_bounds__(512) k_extend(DevScene sc, PathState ps, float4 *__restrict__ hit_out, uint32_t *__restrict__ ctrl, uint32_t parity,
                                                  Queues q, int max_stack, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
@@ -157,6 +157,48 @@ __global__ void __launch_bounds__(256) k_extend(DevScene sc, PathState ps, float
     // queues for all K iterations.  K adapts to the live count so small waves still fill the GPU.
     const uint32_t K = min(8u, max(1u, n / (gridDim.x * blockDim.x * 2u)));
     const uint32_t seg_paths = K * blockDim.x, n_seg = (n + seg_paths - 1u) / seg_paths;
+    // Scenes whose materials all fall into ONE class (and have no volumes) need no per-hit class lookup and only two queues: lane `it` keeps the
+    // hit / miss ballots of iteration `it`, one 64-bit atomic reserves room in both (the miss count and the class's hit count are not adjacent
+    // words, so two lanes issue one 32-bit atomic each in the same instruction).
+    const bool uniform = sc.uniform_class != 0xFFu && sc.n_volumes == 0u;
+    if (uniform) {
+        uint32_t *const q_hit_u = q.hit + (size_t)sc.uniform_class * q.cap;
+        for (uint32_t seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+            const uint32_t base_i = seg * seg_paths + (threadIdx.x & ~31u);
+            uint32_t my_bh = 0, my_bm = 0, ch = 0, cm = 0;
+            uint32_t i = base_i + lane;
+            float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
+            if (i < n) { o4 = ps.org_pdf[i]; d4 = ps.dir_rng[i]; }
+            for (uint32_t it = 0; it < K; it++, i += blockDim.x) {
+                if (base_i + it * blockDim.x >= n) break;                           // warp-uniform
+                const bool active = i < n;
+                bool hit = false;
+                float4 o4n = make_float4(0, 0, 0, 0), d4n = o4n;
+                if (it + 1u < K && i + blockDim.x < n) { o4n = ps.org_pdf[i + blockDim.x]; d4n = ps.dir_rng[i + blockDim.x]; }
+                if (active) {
+                    const float3 rd = normalize_ray(f3(d4));                    // SH/RayGen.slang:70
+                    HitRec h;
+                    hit = bvh_trace<SMEM, false, false, false, !PRIMARY>(bv, f3(o4), rd, 0.01f, 100000.0f, h, stack, stride, max_stack);   // :71-72
+                    hit_out[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.gid));
+                }
+                o4 = o4n; d4 = d4n;
+                const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit), bm = __ballot_sync(0xFFFFFFFFu, active && !hit);
+                if (lane == it) { my_bh = bh; my_bm = bm; }
+                ch += (uint32_t)__popc(bh); cm += (uint32_t)__popc(bm);
+            }
+            uint32_t base = 0u;
+            if (lane == 0u && cm) base = atomicAdd(qc, cm);
+            else if (lane == 1u && ch) base = atomicAdd(qc + 1u + sc.uniform_class, ch);
+            uint32_t om = __shfl_sync(0xFFFFFFFFu, base, 0), oh = __shfl_sync(0xFFFFFFFFu, base, 1);
+            i = base_i + lane;
+            for (uint32_t it = 0; it < K; it++, i += blockDim.x) {
+                const uint32_t bh = __shfl_sync(0xFFFFFFFFu, my_bh, (int)it), bm = __shfl_sync(0xFFFFFFFFu, my_bm, (int)it);
+                if ((bh >> lane) & 1u) q_hit_u[oh + __popc(bh & lt)] = i;
+                else if ((bm >> lane) & 1u) q.miss[om + __popc(bm & lt)] = i;
+                oh += (uint32_t)__popc(bh); om += (uint32_t)__popc(bm);
+            }
+        }
+    } else
     for (uint32_t seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
         const uint32_t base_i = seg * seg_paths + (threadIdx.x & ~31u);     // first path of this warp in iteration 0
         uint32_t codes = 0u, my_cnts = 0u, totA = 0u, totB = 0u;            // totA: queues 0..2, totB: queues 3..4 (10-bit fields, <= 256 each)
@@ -301,8 +343,9 @@ __device__ __forceinline__ bool path_epilogue(const DevConfig &cfg, float3 emitt
 #ifndef BOUNCE_MIN_BLOCKS
 #define BOUNCE_MIN_BLOCKS 5
 #endif
-template <uint32_t CLASS, bool VOL, int FUSE>   // VOL: the scene has AABB volumes (volumes.cuh) -- volume events in the hit queue are skipped, NEE terms get the transmittance
-__global__ void __launch_bounds__(128, FUSE ? BOUNCE_MIN_BLOCKS : SHADE_MIN_BLOCKS) k_shade_hit(DevScene sc, DevConfig cfg, PathState ps, PathState dst, ShadeOut so,
+// BIG: 512-thread CTAs, one per SM -- for BVHs of 64..~170 KiB, which fit shared memory only once per SM (config 4's glass scene: 108 KiB).
+template <uint32_t CLASS, bool VOL, int FUSE, bool BIG = false>   // VOL: the scene has AABB volumes (volumes.cuh) -- volume events in the hit queue are skipped, NEE terms get the transmittance
+__global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_BLOCKS : SHADE_MIN_BLOCKS)) k_shade_hit(DevScene sc, DevConfig cfg, PathState ps, PathState dst, ShadeOut so,
                                                     const float4 *__restrict__ hit_in, float4 *__restrict__ hit_out,
                                                     uint32_t *__restrict__ ctrl, uint32_t parity, Queues q, Queues q_next,
                                                     float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry, int max_stack, WaveCounters *ctr) {
@@ -576,7 +619,7 @@ __global__ void __launch_bounds__(128, FUSE ? BOUNCE_MIN_BLOCKS : SHADE_MIN_BLOC
 // k_connect : shadow queries + SH/RayGen.slang:92-113 + stream compaction of the survivors (unfused pipeline; walks every hit queue)
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM, bool TRACE>   // TRACE = false: k_shadow_dyn already cleared the request bits of occluded rays; only the join / roulette / compaction runs here
-__global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, PathState src, PathState dst, ShadeOut so,
+__global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, PathState src, PathState dst, ShadeOut so,
                                                   uint32_t *__restrict__ ctrl, uint32_t parity, Queues q,
                                                   float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry,
                                                   int max_stack, WaveCounters *ctr) {
@@ -672,14 +715,16 @@ __global__ void __launch_bounds__(256) k_connect(DevScene sc, DevConfig cfg, Pat
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM, bool PRIMARY, bool WIDE>   // WIDE: BVH4 nodes (sc.nodes4) instead of the BVH2
 __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, float4 *__restrict__ hit_out, uint32_t *__restrict__ ctrl, uint32_t parity,
-                                                     Queues q, int max_stack, int thresh, WaveCounters *ctr) {
+                                                     Queues q, int max_stack, int thresh, int n_top, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
     stack[0] = DYN_DONE;
     BvhView bv;
+    const float4 *top = reinterpret_cast<const float4 *>(smem + (size_t)(max_stack + 1) * blockDim.x * sizeof(int));   // BVH4 treelet (WIDE, n_top > 0)
     if (SMEM) bv = stage_bvh_smem(sc, smem + (size_t)(max_stack + 1) * blockDim.x * sizeof(int), &bar);
     else bv = global_bvh(sc);
+    if (WIDE && n_top > 0) stage_bytes_smem(smem + (size_t)(max_stack + 1) * blockDim.x * sizeof(int), sc.nodes4, (uint32_t)n_top * (uint32_t)sizeof(Bvh4Node), &bar);
     const uint32_t n = ctrl[parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) {                              // counters of the NEXT bounce (last used two bounces ago)
         ctrl_reset_parity(ctrl, parity ^ 1u);
@@ -725,7 +770,7 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, f
         }
         const int thr_now = pool.empty() ? 1 : thresh;
         do {
-            if (WIDE) { while (r.cur >= 0) dyn_node4_step<!PRIMARY>(nodes4, r, s_step, s_limit, spill); }
+            if (WIDE) { while (r.cur >= 0) dyn_node4_step<!PRIMARY>(nodes4, top, n_top, r, s_step, s_limit, spill); }
             else { while (r.cur >= 0) dyn_node_step<SMEM, !PRIMARY>(bv, r, s_step, s_limit); }
             __syncwarp();
             while (r.cur < 0 && r.cur != DYN_DONE) dyn_leaf_step<SMEM, false, WIDE>(bv, r, s_step, spill);
@@ -739,7 +784,7 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, f
 constexpr size_t DYN_RING_BYTES = 8 * 128 * sizeof(uint32_t);              // per-CTA request rings of k_shadow_dyn (dynamic shared memory, after the stacks)
 template <bool SMEM, bool WIDE>
 __global__ void __launch_bounds__(256, 4) k_shadow_dyn(DevScene sc, ShadeOut so, uint32_t *__restrict__ ctrl, uint32_t parity,
-                                                     Queues q, int max_stack, int thresh, WaveCounters *ctr) {
+                                                     Queues q, int max_stack, int thresh, int n_top, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
@@ -747,8 +792,10 @@ __global__ void __launch_bounds__(256, 4) k_shadow_dyn(DevScene sc, ShadeOut so,
     const size_t stack_bytes = (size_t)(max_stack + 1) * blockDim.x * sizeof(int);
     uint32_t *ring_all = reinterpret_cast<uint32_t *>(smem + stack_bytes);  // 128 entries per warp
     BvhView bv;
+    const float4 *top = reinterpret_cast<const float4 *>(smem + stack_bytes + DYN_RING_BYTES);   // BVH4 treelet (WIDE, n_top > 0)
     if (SMEM) bv = stage_bvh_smem(sc, smem + stack_bytes + DYN_RING_BYTES, &bar);
     else bv = global_bvh(sc);
+    if (WIDE && n_top > 0) stage_bytes_smem(smem + stack_bytes + DYN_RING_BYTES, sc.nodes4, (uint32_t)n_top * (uint32_t)sizeof(Bvh4Node), &bar);
     const HitSpan span = hit_span(ctrl, parity);
     const uint32_t n = span.n;                                              // total hit-queue length of this bounce
     uint32_t *fetch = ctrl + 10u + parity;
@@ -813,7 +860,7 @@ __global__ void __launch_bounds__(256, 4) k_shadow_dyn(DevScene sc, ShadeOut so,
         if (act == 0u) { if (tail == head && pool.empty()) break; else continue; }
         const int thr_now = (tail == head && pool.empty()) ? 1 : thresh;
         do {
-            if (WIDE) { while (r.cur >= 0) dyn_node4_step<true>(nodes4, r, s_step, s_limit, spill); }
+            if (WIDE) { while (r.cur >= 0) dyn_node4_step<true>(nodes4, top, n_top, r, s_step, s_limit, spill); }
             else { while (r.cur >= 0) dyn_node_step<SMEM, true>(bv, r, s_step, s_limit); }
             __syncwarp();
             while (r.cur < 0 && r.cur != DYN_DONE) {
@@ -1035,7 +1082,7 @@ static int set_attrs_for_current_device() {
     optin((const void *)k_shadow_dyn<true, false>); optin((const void *)k_shadow_dyn<false, false>); optin((const void *)k_shadow_dyn<false, true>);
     optin((const void *)k_trace_rays<true>); optin((const void *)k_trace_rays<false>);
     optin((const void *)k_volume_decide<true>); optin((const void *)k_volume_decide<false>);
-#define B200PT_OPTIN_BOUNCE(C) optin((const void *)k_shade_hit<C, false, 1>); optin((const void *)k_shade_hit<C, false, 2>);
+#define B200PT_OPTIN_BOUNCE(C) optin((const void *)k_shade_hit<C, false, 1>); optin((const void *)k_shade_hit<C, false, 2>); optin((const void *)k_shade_hit<C, false, 2, true>);
     B200PT_OPTIN_BOUNCE(MC_DIFFUSE) B200PT_OPTIN_BOUNCE(MC_METAL) B200PT_OPTIN_BOUNCE(MC_GLASS) B200PT_OPTIN_BOUNCE(MC_GENERAL)
 #undef B200PT_OPTIN_BOUNCE
     cudaGetLastError();
@@ -1051,8 +1098,17 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
     if (e != cudaSuccess) return (int)e;
     const int sms = prop.multiProcessorCount;
     lc->max_stack = bvh_max_depth + 2; if (lc->max_stack < 4) lc->max_stack = 4; if (lc->max_stack > 64) lc->max_stack = 64;
-    lc->bvh_in_smem = sc.bvh_bytes > 0 && sc.bvh_bytes <= 64u * 1024u && (sc.bvh_bytes % 16u) == 0;
-    const size_t sh = trace_smem_bytes(sc, lc->max_stack, 256, lc->bvh_in_smem);
+    // Whole BVH in shared memory: <= 64 KiB -> several CTAs per SM (Cornell: 1.3 KiB); up to what fits beside the stacks of ONE 512-thread CTA per SM
+    // -> "big" mode (config 4's glass scene: 108 KiB): k_extend and the fused bounce kernels run 512-thread CTAs.  B200PT_SMEM_BIG=0 turns big mode off.
+    const bool aligned = sc.bvh_bytes > 0 && (sc.bvh_bytes % 16u) == 0;
+    const bool fits_small = aligned && sc.bvh_bytes <= 64u * 1024u;
+    bool fits_big = aligned && !fits_small && (size_t)sc.bvh_bytes + (size_t)lc->max_stack * 512u * sizeof(int) <= 226u * 1024u;
+    if (const char *e = getenv("B200PT_SMEM_BIG")) { if (atoi(e) == 0) fits_big = false; }
+    lc->bvh_in_smem = fits_small || fits_big;
+    lc->big = fits_big;
+    lc->extend_threads = fits_big ? 512 : 256;
+    const size_t sh = trace_smem_bytes(sc, lc->max_stack, lc->extend_threads, lc->bvh_in_smem);
+    const size_t sh256 = trace_smem_bytes(sc, lc->max_stack, 256, lc->bvh_in_smem);
     // traversal shape: dynamic-fetch while-while kernels (bvh_dynfetch.cuh) over the BVH4 when the BVH lives in L2/HBM, one ray per thread
     // over the BVH2 when the whole BVH sits in shared memory (tiny scenes: no divergence or latency to recover).
     // Overrides: B200PT_TRAV=classic|dyn, B200PT_WIDE=0|1, B200PT_DYN_THRESH=1..32, B200PT_WIDE_STACK=<shared-memory stack entries>.
@@ -1073,9 +1129,20 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
     }
     // fused bounce kernel (k_shade_hit<., ., 2>): scenes whose BVH is staged in shared memory and walked one ray per thread.  B200PT_FUSE=0|1|2 overrides
     // (0: k_shade_hit + k_connect, 1: NEE queries and the path epilogue fused, k_extend separate, 2: next segment's TraceRay fused as well).
-    lc->fuse = (lc->bvh_in_smem && !lc->trav_dyn) ? 2 : 0;
-    if (const char *e = getenv("B200PT_FUSE")) { const int v = atoi(e); if (v >= 0 && v <= 2 && lc->bvh_in_smem && !lc->trav_dyn) lc->fuse = v; }
-    const size_t sh_dyn = trace_smem_bytes(sc, lc->dyn_stack + 1, 256, lc->bvh_in_smem);
+    // Measured (profiles/r02_variants.txt): on the Cornell box the fused kernels are SLOWER than k_extend + k_shade_hit + k_connect (87.4 / 82.5 vs 77.2 ms
+    // per step) -- the traffic they save was never the bound (DRAM 13 % busy), while the shadow / extend traversals now run inside half-empty warps
+    // (22 of 32 lanes per instruction) of a 65 KB kernel.  They stay available as an opt-in.
+    lc->fuse = 0;
+    if (const char *e = getenv("B200PT_FUSE")) { const int v = atoi(e); if (v >= 0 && v <= 2 && lc->bvh_in_smem && !lc->trav_dyn) lc->fuse = (lc->big && v == 1) ? 2 : v; }
+    // BVH4 treelet in shared memory (bvh_dynfetch.cuh): the first n_top4 nodes (breadth-first order = the top levels).  B200PT_TOP_KB sizes it (0 = off).
+    lc->n_top4 = 0;
+    if (lc->wide) {
+        int kb = 40;
+        if (const char *e = getenv("B200PT_TOP_KB")) { const int v = atoi(e); if (v >= 0 && v <= 160) kb = v; }
+        const uint32_t want = (uint32_t)kb * 1024u / (uint32_t)sizeof(Bvh4Node);
+        lc->n_top4 = (int)(want < sc.n_nodes4 ? want : sc.n_nodes4);
+    }
+    const size_t sh_dyn = trace_smem_bytes(sc, lc->dyn_stack + 1, 256, lc->bvh_in_smem) + (size_t)lc->n_top4 * sizeof(Bvh4Node);
     int occ_e = 0, occ_c = 0, occ_s = 0, occ_sh = 0, occ_b = 0;
     if (lc->trav_dyn) {
         if (lc->wide) {
@@ -1090,8 +1157,8 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
         }
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<false, false>, 256, 0);
     } else if (lc->bvh_in_smem) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<true, false>, 256, sh);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<true, true>, 256, sh);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<true, false>, lc->extend_threads, sh);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<true, true>, lc->extend_threads, sh);
     } else {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_extend<false, false>, 256, sh);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_connect<false, true>, 256, sh);
@@ -1099,16 +1166,17 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
     if (occ_sh < 1) occ_sh = 1;
     lc->grid_shadow = sms * occ_sh;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_shade_hit<MC_GENERAL, false, 0>, 128, 0);
-    if (lc->bvh_in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_shade_hit<MC_GENERAL, false, 2>, 128, trace_smem_bytes(sc, lc->max_stack, 128, true));
+    if (lc->big) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_shade_hit<MC_GENERAL, false, 2, true>, 512, trace_smem_bytes(sc, lc->max_stack, 512, true));
+    else if (lc->bvh_in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_shade_hit<MC_GENERAL, false, 2>, 128, trace_smem_bytes(sc, lc->max_stack, 128, true));
     if (occ_e < 1) occ_e = 1; if (occ_c < 1) occ_c = 1; if (occ_s < 1) occ_s = 1; if (occ_b < 1) occ_b = 1;
     lc->grid_extend = sms * occ_e; lc->grid_connect = sms * occ_c;
-    lc->grid_trace = sms * occ_e;
+    { int occ_t = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, lc->bvh_in_smem ? k_trace_rays<true> : k_trace_rays<false>, 256, sh256); lc->grid_trace = sms * (occ_t < 1 ? 1 : occ_t); }
     lc->grid_shade = sms * occ_s;
     lc->grid_bounce = sms * occ_b;
     lc->grid_light = sms * 8;
     if (getenv("B200PT_DEBUG"))
-        fprintf(stderr, "[b200pt] launch cfg: bvh depth %d (bvh4 %d) max_stack %d dyn_stack %d bvh_bytes %u smem %d dyn %d wide %d thresh %d fuse %d | CTAs/SM extend %d connect %d shadow %d shade %d bounce %d\n",
-                bvh_max_depth, bvh4_depth, lc->max_stack, lc->dyn_stack, sc.bvh_bytes, (int)lc->bvh_in_smem, (int)lc->trav_dyn, (int)lc->wide, lc->dyn_thresh, lc->fuse, occ_e, occ_c, occ_sh, occ_s, occ_b);
+        fprintf(stderr, "[b200pt] launch cfg: bvh depth %d (bvh4 %d) max_stack %d dyn_stack %d bvh_bytes %u smem %d dyn %d wide %d (treelet %d nodes) thresh %d fuse %d big %d | CTAs/SM extend %d connect %d shadow %d shade %d bounce %d\n",
+                bvh_max_depth, bvh4_depth, lc->max_stack, lc->dyn_stack, sc.bvh_bytes, (int)lc->bvh_in_smem, (int)lc->trav_dyn, (int)lc->wide, lc->n_top4, lc->dyn_thresh, lc->fuse, (int)lc->big, occ_e, occ_c, occ_sh, occ_s, occ_b);
     return 0;
 }
 
@@ -1121,18 +1189,18 @@ void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, float4
     set_attrs_for_current_device();
     const bool smem = lc.bvh_in_smem;
     if (lc.trav_dyn) {
-        const size_t sh = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem);
-#define B200PT_EXT_DYN(S, P, W) k_extend_dyn<S, P, W><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.dyn_stack, lc.dyn_thresh, ctr)
+        const size_t sh = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem) + (size_t)lc.n_top4 * sizeof(Bvh4Node);
+#define B200PT_EXT_DYN(S, P, W) k_extend_dyn<S, P, W><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.dyn_stack, lc.dyn_thresh, lc.n_top4, ctr)
         if (lc.wide) { if (primary) B200PT_EXT_DYN(false, true, true); else B200PT_EXT_DYN(false, false, true); }
         else if (smem) { if (primary) B200PT_EXT_DYN(true, true, false); else B200PT_EXT_DYN(true, false, false); }
         else { if (primary) B200PT_EXT_DYN(false, true, false); else B200PT_EXT_DYN(false, false, false); }
 #undef B200PT_EXT_DYN
         return;
     }
-    const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
+    const size_t sh = trace_smem_bytes(sc, lc.max_stack, lc.extend_threads, smem);
     if (smem) {
-        if (primary) k_extend<true, true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
-        else k_extend<true, false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
+        if (primary) k_extend<true, true><<<lc.grid_extend, lc.extend_threads, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
+        else k_extend<true, false><<<lc.grid_extend, lc.extend_threads, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
     } else {
         if (primary) k_extend<false, true><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
         else k_extend<false, false><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.max_stack, ctr);
@@ -1146,9 +1214,10 @@ int launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, 
     set_attrs_for_current_device();
     int launched = 1;
     k_shade_miss<<<lc.grid_light, 256, 0, st>>>(sc, cfg, ps, ctrl, parity, fuse == 2 ? 1u : 0u, q.miss, sample_buf, rng_carry, ctr);
-    const size_t shb = trace_smem_bytes(sc, lc.max_stack, 128, true);
+    const size_t shb = trace_smem_bytes(sc, lc.max_stack, lc.big ? 512 : 128, true);
 #define B200PT_SHADE(C) do { if (class_mask & (1u << C)) { launched++;                                                                                              \
-        if (fuse == 2) k_shade_hit<C, false, 2><<<lc.grid_bounce, 128, shb, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr);      \
+        if (fuse == 2 && lc.big) k_shade_hit<C, false, 2, true><<<lc.grid_bounce, 512, shb, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr); \
+        else if (fuse == 2) k_shade_hit<C, false, 2><<<lc.grid_bounce, 128, shb, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr);      \
         else if (fuse == 1) k_shade_hit<C, false, 1><<<lc.grid_bounce, 128, shb, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr); \
         else if (sc.n_volumes) k_shade_hit<C, true, 0><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr);   \
         else k_shade_hit<C, false, 0><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr); } } while (0)
@@ -1169,15 +1238,15 @@ void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cf
     set_attrs_for_current_device();
     const bool smem = lc.bvh_in_smem;
     if (lc.trav_dyn) {                                                      // shadow rays in their own dynamic-fetch kernel, then the join without tracing
-        const size_t shd = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem) + DYN_RING_BYTES_HOST;
-#define B200PT_SH_DYN(S, W) k_shadow_dyn<S, W><<<lc.grid_shadow, 256, shd, st>>>(sc, so, ctrl, parity, q, lc.dyn_stack, lc.dyn_thresh, ctr)
+        const size_t shd = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem) + DYN_RING_BYTES_HOST + (size_t)lc.n_top4 * sizeof(Bvh4Node);
+#define B200PT_SH_DYN(S, W) k_shadow_dyn<S, W><<<lc.grid_shadow, 256, shd, st>>>(sc, so, ctrl, parity, q, lc.dyn_stack, lc.dyn_thresh, lc.n_top4, ctr)
         if (lc.wide) B200PT_SH_DYN(false, true); else if (smem) B200PT_SH_DYN(true, false); else B200PT_SH_DYN(false, false);
 #undef B200PT_SH_DYN
         k_connect<false, false><<<lc.grid_connect, 256, 0, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
         return;
     }
-    const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_connect<true, true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
+    const size_t sh = trace_smem_bytes(sc, lc.max_stack, smem ? lc.extend_threads : 256, smem);
+    if (smem) k_connect<true, true><<<lc.grid_connect, lc.extend_threads, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
     else k_connect<false, true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
 }
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
