@@ -682,6 +682,29 @@ float orc_bake_reflect_texel(uint32_t tx, uint32_t ty, uint32_t tz, uint32_t sam
     }
     return (float)(total / samples);
 }
+/* Exploration hook for the shipped-table study (tests/test_oracle_kat.py, profiles/r02_lut_corner_study.txt): the reflect estimator of
+ * LookupReflect.slang:52-82 at explicit parameters, with the two thresholds of the sample loop exposed (reference: lz_min = 0, EvaluateReflection's 1e-5). */
+float orc_bake_reflect_params(float viewCosine, float roughness, float anisotropy, float lz_min, uint32_t samples, uint32_t seed) {
+    float aspect = sqrtf(1.0f - sqrtf(anisotropy) * 0.9f);
+    Mat m; memset(&m, 0, sizeof m);
+    m.Anisotropy = anisotropy; m.Roughness = roughness; m.BaseColor = v3s(1.0f);
+    m.Ax = fmaxf(0.0001f, roughness / aspect); m.Ay = fmaxf(0.0001f, roughness * aspect);
+    Rng rng = { seed };
+    double total = 0.0;
+    for (uint32_t i = 0; i < samples; i++) {
+        float xy = sqrtf(1.0f - viewCosine * viewCosine);
+        float phi = rng_f(&rng) * ORC_2PI;
+        v3 V = v3normalize(V3(xy * cosf(phi), xy * sinf(phi), viewCosine));
+        v3 H = rng_ggx_vndf(&rng, V, m.Ax, m.Ay);
+        v3 L = v3normalize(v3reflect(v3neg(V), H));
+        if (L.z <= lz_min) continue;
+        Eval e = eval_reflection(&m, V, L, v3s(1.0f));
+        if (e.PDF <= 0.0f) continue;
+        if (isnan(e.BxDF.x) || isinf(e.BxDF.x)) continue;
+        total += e.BxDF.x / e.PDF;
+    }
+    return (float)(total / samples);
+}
 float orc_bake_refract_texel(uint32_t tx, uint32_t ty, uint32_t tz, int above_surface, uint32_t samples, uint32_t seed) {
     const float SX = 128.0f, SY = 128.0f, SZ = 32.0f;                        /* PT/Application.cpp:54,67 */
     Rng rng = { ty + tx * tx + seed };
@@ -921,6 +944,33 @@ static v3 rng_draine(Rng *r, v3 incident, float g, float a) {
         cosTheta = (1.0f + g2 - q * q) / (2.0f * g);
     }
     return phase_frame(incident, cosTheta, 2.0f * ORC_PI * ry);
+}
+/* Conditioning study of the Draine inversion above (tests/test_oracle_kat.py::test_draine_inversion_is_ill_conditioned_in_fp32): the SAME
+ * expression tree evaluated in fp32 (what the shader, this oracle and the CUDA kernel do) and in fp64.  T4a and sqrt(-4 T4b^3 + T4a^2) are
+ * of magnitude 1e3..1e9 and nearly cancel, so the fp32 value of cos(theta) carries an error far above one ulp: two correct fp32 implementations
+ * that round differently (FMA contraction, libm) disagree on the scattered direction by more than 1e-4 in a few per cent of the draws. */
+#define DRAINE_COS(T, SQRT, POW, rx, g, a, out) do {                                                                              \
+        const T g2 = g * g, g3 = g * g2, g4 = g2 * g2, g6 = g2 * g4;                                                              \
+        const T pgp1_2 = ((T)1 + g2) * ((T)1 + g2);                                                                               \
+        const T T1a = -a + a * g4;                                                                                                \
+        const T T1a3 = T1a * T1a * T1a;                                                                                           \
+        const T T2 = (T)-1296 * ((T)-1 + g2) * (a - a * g2) * (T1a) * ((T)4 * g2 + a * pgp1_2);                                    \
+        const T T3 = (T)3 * g2 * ((T)1 + g * ((T)-1 + (T)2 * rx)) + a * ((T)2 + g2 + g3 * ((T)1 + (T)2 * g2) * ((T)-1 + (T)2 * rx)); \
+        const T T4a = (T)432 * T1a3 + T2 + (T)432 * (a - a * g2) * T3 * T3;                                                       \
+        const T T4b = (T)-144 * a * g2 + (T)288 * a * g4 - (T)144 * a * g6;                                                       \
+        const T T4b3 = T4b * T4b * T4b;                                                                                           \
+        const T T4 = T4a + SQRT((T)-4 * T4b3 + T4a * T4a);                                                                        \
+        const T T4p3 = POW(T4, (T)1 / (T)3);                                                                                      \
+        const T cbrt2 = POW((T)2, (T)1 / (T)3);                                                                                   \
+        const T T6 = ((T)2 * T1a + ((T)48 * cbrt2 * (-(a * g2) + (T)2 * a * g4 - a * g6)) / T4p3 + T4p3 / ((T)3 * cbrt2)) / (a - a * g2); \
+        const T T5 = (T)6 * ((T)1 + g2) + T6;                                                                                     \
+        const T q = (T)-0.5 * SQRT(T5) + SQRT((T)6 * ((T)1 + g2) - ((T)8 * T3) / (a * ((T)-1 + g2) * SQRT(T5)) - T6) / (T)2;       \
+        out = ((T)1 + g2 - q * q) / ((T)2 * g);                                                                                    \
+    } while (0)
+void orc_draine_cos_theta(float rx, float g, float a, float *cos32, double *cos64) {
+    float c32; DRAINE_COS(float, sqrtf, powf, rx, g, a, c32);
+    const double rxd = rx, gd = g, ad = a; double c64; DRAINE_COS(double, sqrt, pow, rxd, gd, ad, c64);
+    *cos32 = c32; *cos64 = c64;
 }
 /* droplet-size fit of SH/Volume.slang:389-400 / SH/Sampler.slang:278-295 */
 static void hg_draine_fit(float d, float *GHG, float *GD, float *ALPHA_D, float *W_D) {

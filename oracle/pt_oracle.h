@@ -95,6 +95,8 @@ void     orc_aces_fitted(const float in[3], float out[3]);             /* SH/Pos
 
 /* one texel of the reference's energy-compensation LUT baker (SH/LookupReflect.slang, SH/LookupRefract.slang) */
 float    orc_bake_reflect_texel(uint32_t tx, uint32_t ty, uint32_t tz, uint32_t samples, uint32_t seed);
+void orc_draine_cos_theta(float rx, float g, float a, float *cos32, double *cos64);
+float orc_bake_reflect_params(float viewCosine, float roughness, float anisotropy, float lz_min, uint32_t samples, uint32_t seed);
 float    orc_bake_refract_texel(uint32_t tx, uint32_t ty, uint32_t tz, int above_surface, uint32_t samples, uint32_t seed);
 float    orc_bake_lut_texel(int kind, uint32_t SX, uint32_t SY, uint32_t SZ, uint32_t tx, uint32_t ty, uint32_t tz, uint32_t sample_count, uint32_t seed);
 

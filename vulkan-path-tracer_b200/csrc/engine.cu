@@ -610,10 +610,11 @@ void Engine::post_process() {
     bool fused = mips >= 2;
     if (const char *e = getenv("B200PT_POST_FUSED")) { if (atoi(e) == 0) fused = false; }
     if (fused) {
-        // passes ls..mips-1 (every mip whose finer neighbour holds <= 160 K pixels) run inside one cluster launch (k_bloom_small); B200PT_POST_SMALL=0 restores one launch per pass
+        // passes ls..mips-1 (every mip whose finer neighbour holds <= 160 K pixels) can run inside one cluster launch (k_bloom_small)
+        // Measured at 3840x2160 (profiles/r02_variants.txt): 0.323 ms with the cluster kernel against 0.302 ms with one launch per pass (8 CTAs walk mips that
+        // 148 SMs finish faster than the launches cost) -> OPT-IN (B200PT_POST_SMALL=1).
         uint32_t ls = mips;
-        for (uint32_t i = 2; i < mips; i++) if ((uint64_t)mip_wh_[2 * (i - 1)] * mip_wh_[2 * (i - 1) + 1] <= 160u * 1024u) { ls = i; break; }
-        if (const char *e = getenv("B200PT_POST_SMALL")) { if (atoi(e) == 0) ls = mips; }
+        if (const char *e = getenv("B200PT_POST_SMALL")) { if (atoi(e) == 1) for (uint32_t i = 2; i < mips; i++) if ((uint64_t)mip_wh_[2 * (i - 1)] * mip_wh_[2 * (i - 1) + 1] <= 160u * 1024u) { ls = i; break; } }
         if (mips > 16) ls = mips;
         launch_bloom_down_first(d_image_, W_, H_, d_mips_[1], mip_wh_[2], mip_wh_[3], p, stream_);                               // :200-226, i == 0 and i == 1
         for (uint32_t i = 2; i < ls; i++) launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_);

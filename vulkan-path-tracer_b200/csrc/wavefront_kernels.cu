@@ -1099,11 +1099,13 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
     const int sms = prop.multiProcessorCount;
     lc->max_stack = bvh_max_depth + 2; if (lc->max_stack < 4) lc->max_stack = 4; if (lc->max_stack > 64) lc->max_stack = 64;
     // Whole BVH in shared memory: <= 64 KiB -> several CTAs per SM (Cornell: 1.3 KiB); up to what fits beside the stacks of ONE 512-thread CTA per SM
-    // -> "big" mode (config 4's glass scene: 108 KiB): k_extend and the fused bounce kernels run 512-thread CTAs.  B200PT_SMEM_BIG=0 turns big mode off.
+    // -> "big" mode (config 4's glass scene: 108 KiB): k_extend, k_connect and the fused bounce kernels run 512-thread CTAs.
     const bool aligned = sc.bvh_bytes > 0 && (sc.bvh_bytes % 16u) == 0;
     const bool fits_small = aligned && sc.bvh_bytes <= 64u * 1024u;
-    bool fits_big = aligned && !fits_small && (size_t)sc.bvh_bytes + (size_t)lc->max_stack * 512u * sizeof(int) <= 226u * 1024u;
-    if (const char *e = getenv("B200PT_SMEM_BIG")) { if (atoi(e) == 0) fits_big = false; }
+    // Measured on config 4's glass scene (profiles/r02_variants.txt): 856 Mpaths/s with the one-ray-per-thread kernels over the shared-memory BVH (8-16 warps
+    // per SM, divergent LDS) against 940 with the dynamic-fetch kernels over L2 -> big mode is OPT-IN (B200PT_SMEM_BIG=1).
+    bool fits_big = false;
+    if (const char *e = getenv("B200PT_SMEM_BIG")) { if (atoi(e) == 1) fits_big = aligned && !fits_small && (size_t)sc.bvh_bytes + (size_t)lc->max_stack * 512u * sizeof(int) <= 226u * 1024u; }
     lc->bvh_in_smem = fits_small || fits_big;
     lc->big = fits_big;
     lc->extend_threads = fits_big ? 512 : 256;
@@ -1137,7 +1139,9 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
     // BVH4 treelet in shared memory (bvh_dynfetch.cuh): the first n_top4 nodes (breadth-first order = the top levels).  B200PT_TOP_KB sizes it (0 = off).
     lc->n_top4 = 0;
     if (lc->wide) {
-        int kb = 40;
+        // Measured on BreakfastRoom (profiles/r02_variants.txt): 1376 Mpaths/s without, 1292 / 1161 / 881 with 40 / 80 / 120 KiB -- the generic loads that serve
+        // treelet and L2 lanes in one instruction cost more than the L1 hits they replace, and the footprint costs occupancy -> OPT-IN.
+        int kb = 0;
         if (const char *e = getenv("B200PT_TOP_KB")) { const int v = atoi(e); if (v >= 0 && v <= 160) kb = v; }
         const uint32_t want = (uint32_t)kb * 1024u / (uint32_t)sizeof(Bvh4Node);
         lc->n_top4 = (int)(want < sc.n_nodes4 ? want : sc.n_nodes4);
