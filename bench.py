@@ -189,48 +189,104 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def post_row_block(H, rank, world):
+    """contiguous block of output rows of rank `rank` (boundaries on multiples of 8 rows)"""
+    cut = lambda r: (H * r // world + 7) // 8 * 8 if r < world else H
+    return min(cut(rank), H), min(cut(rank + 1), H)
+
+
 def run_post(args):
-    """configs[4]: 3840x2160 HDR accumulate + bloom (10 mips) + tonemap, post only; GB/s against the unfused 174.7 B/pixel model."""
+    """BASELINE configs[4]: 3840x2160 HDR accumulate + bloom (10 mips) + tonemap, post only, on 1 / 2 / 4 / 8 GPUs.  A step = one frame: every rank folds a new
+    radiance frame into the accumulation image on the rows its block depends on (b200pt_accumulate_rows), runs the bloom chain + tonemap for its block of
+    output rows (b200pt_post_process_rows: halo rows recomputed, no exchange) and, for N > 1, the RGBA8 blocks are gathered on rank 0 (one NCCL gather).
+    value = GB/s by the reference's pass-per-pass byte model (174.7 B/pixel) over the whole image / time, max over ranks."""
     import torch
+    import torch.distributed as dist
     import util
     import vpt_b200 as pt
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, H = 3840, 2160
     rng = np.random.default_rng(7)
     hdr = np.ones((H, W, 4), np.float32); hdr[..., :3] = (np.exp(rng.normal(0, 1.5, (H, W, 3))) * 0.5).astype(np.float32)
     for _ in range(64):
         y, x = rng.integers(0, H - 5), rng.integers(0, W - 5); hdr[y:y + 5, x:x + 5, :3] = 500.0
-    T = pt.PathTracer(0)
+    T = pt.PathTracer(local)
     T.set_scene(util.scene_dict("cornell_box")); T.resize(W, H)
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); T.set_stream(stream.cuda_stream)
     T.set_hdr(hdr)
-    iters = 100
-    for _ in range(max(args.warmup, 3)): T.post_process()
-    torch.cuda.synchronize()
+    frame = torch.from_numpy(hdr).cuda()                         # the "new frame" folded in every step (resident in HBM)
+    y0, y1 = post_row_block(H, rank, world)
+    in0, in1 = T.post_input_rows(y0, y1)
+    blk_rows = max(post_row_block(H, r, world)[1] - post_row_block(H, r, world)[0] for r in range(world))
+    blk = torch.zeros((blk_rows, W, 4), dtype=torch.uint8, device="cuda")
+    gathered = [torch.zeros_like(blk) for _ in range(world)] if (world > 1 and rank == 0) else None
+    fidx = [1]
+
+    def step():
+        T.accumulate_rows(frame.data_ptr(), fidx[0], in0, in1); fidx[0] += 1
+        T.post_process_rows(y0, y1)
+        if world > 1:
+            T.get_ldr_rows_into_device(y0, y1, blk.data_ptr())
+            dist.gather(blk, gathered, dst=0)
+
+    def barrier():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local); sampler.start()
+    iters = max(args.steps, 8) * 25
+    for _ in range(max(args.warmup, 3) * 5): step()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     ev0.record(stream)
-    for _ in range(iters): T.post_process()
-    ev1.record(stream); torch.cuda.synchronize()
+    for _ in range(iters): step()
+    ev1.record(stream); barrier()
+    sampler.mark_end()
+    clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1) / iters
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1: dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    # e2e: the frame comes from pinned HOST memory every step and the RGBA8 result goes back to the host
+    host_frame = torch.from_numpy(hdr).pin_memory(); host_ldr = torch.empty((y1 - y0, W, 4), dtype=torch.uint8).pin_memory()
+    def e2e_step():
+        frame[in0:in1].copy_(host_frame[in0:in1], non_blocking=True)
+        step()
+        T.get_ldr_rows(y0, y1, host_ldr.numpy())
+    e2e_step(); barrier()
+    n_e2e = 20
+    t0 = time.perf_counter()
+    for _ in range(n_e2e): e2e_step()
+    barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
+    if world > 1: dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
     mips = pt.bloom_mip_sizes(W, H)
     px = [w * h for w, h in mips]
-    # unfused pass structure (SURVEY 8d): threshold R16+W16 per px0; down i: one compulsory read of mip i-1 + write of mip i;
-    # up i: read mip i + RMW mip i-1; tonemap: read hdr + bloom, write rgba8
-    bytes_model = 32 * px[0] + sum(16 * px[i - 1] + 16 * px[i] for i in range(1, len(px))) + sum(16 * px[i] + 32 * px[i - 1] for i in range(1, len(px))) + (16 + 16 + 4) * px[0]
-    # what the fused chain (default; B200PT_POST_FUSED=0 restores the pass structure) really has to move: mip 0 is never materialised --
-    # first down pass reads the HDR image, the final kernel reads HDR + mip 1 and writes RGBA8; the passes between mips >= 1 are unchanged
-    fused = os.environ.get("B200PT_POST_FUSED", "1") != "0"
-    bytes_fused = (16 * px[0] + 16 * px[1]) + sum(16 * px[i - 1] + 16 * px[i] for i in range(2, len(px))) + sum(16 * px[i] + 32 * px[i - 1] for i in range(2, len(px))) + (16 * px[0] + 16 * px[1] + 4 * px[0])
+    # reference pass structure (SURVEY 8d): accumulate RMW 32 B/px; threshold R16+W16; down i: read mip i-1 + write mip i; up i: read mip i + RMW mip i-1; tonemap: hdr + bloom -> rgba8
+    bytes_model = 32 * px[0] + 32 * px[0] + sum(16 * px[i - 1] + 16 * px[i] for i in range(1, len(px))) + sum(16 * px[i] + 32 * px[i - 1] for i in range(1, len(px))) + (16 + 16 + 4) * px[0]
+    # what the fused chain really has to move for the WHOLE image: accumulate (frame read + image RMW = 48 B/px), first down pass reads the image, the final kernel reads image + mip 1 and writes RGBA8
+    bytes_fused = 48 * px[0] + (16 * px[0] + 16 * px[1]) + sum(16 * px[i - 1] + 16 * px[i] for i in range(2, len(px))) + sum(16 * px[i] + 32 * px[i - 1] for i in range(2, len(px))) + (16 * px[0] + 16 * px[1] + 4 * px[0])
     peak, kind = measured_peak()
     gbs = bytes_model / (ms * 1e-3) / 1e9
-    moved = (bytes_fused if fused else bytes_model) / (ms * 1e-3) / 1e9
-    print(json.dumps({"metric": "post chain GB/s (3840x2160 bloom 10 mips + tonemap)", "value": gbs, "unit": "GB/s", "n_gpus": 1, "steps": iters, "warmup": max(args.warmup, 3),
-                      "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "post_4k", "image": [W, H], "mips": mips, "bytes_per_pixel_model": bytes_model / px[0], "chain": "fused" if fused else "pass-per-pass",
-                                 "bytes_per_pixel_moved": (bytes_fused if fused else bytes_model) / px[0],
-                                 "note": "value = the reference's pass-per-pass byte model (SURVEY 8d, 174.7 B/px) / time: the fused chain moves fewer bytes, so value may exceed the HBM peak; roofline.achieved counts the bytes the chain really moves"},
-                      "roofline": {"bound": "hbm", "kernel": "post chain (k_bloom_down<first> .. k_bloom_final)" if fused else "post chain (threshold / down / up / tonemap)",
-                                   "achieved": moved, "peak": peak, "peak_kind": kind, "unit": "GB/s", "frac": moved / peak, "traffic": None,
-                                   "pass_per_pass_model_gbs": gbs}}))
+    moved = bytes_fused / (ms * 1e-3) / 1e9
+    if rank == 0:
+        print(json.dumps({"metric": "post chain GB/s (3840x2160 HDR accumulate + bloom 10 mips + tonemap)", "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": iters, "warmup": max(args.warmup, 3) * 5,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "post_4k", "image": [W, H], "mips": mips, "bytes_per_pixel_model": bytes_model / px[0], "chain": "fused, row blocks + recomputed halo",
+                                     "bytes_per_pixel_moved": bytes_fused / px[0], "row_block_rank0": [y0, y1], "input_rows_rank0": [in0, in1],
+                                     "l2_policy": "inputs larger than L2 (HDR image 133 MB + frame 133 MB vs 126 MB L2), no explicit flush",
+                                     "note": "value = the reference's pass-per-pass byte model (SURVEY 8d, 174.7 B/px) / time: the fused chain moves fewer bytes, so value may exceed N x the HBM peak; roofline.achieved counts the bytes the chain really moves, per GPU"},
+                          "e2e": {"value": bytes_model / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int((in1 - in0) * W * 16), "d2h_bytes_per_step": int((y1 - y0) * W * 4), "steps": n_e2e},
+                          "gpu_launches": int(iters * (1 + 2 * (len(px) - 1))), "clocks": clocks,
+                          "roofline": {"bound": "hbm", "kernel": "post chain (k_accumulate, k_bloom_down_first .. k_bloom_final)", "achieved": moved / world, "peak": peak, "peak_kind": kind, "unit": "GB/s",
+                                       "frac": moved / world / peak, "traffic": None, "pass_per_pass_model_gbs": gbs}}))
+    if world > 1: dist.destroy_process_group()
 
 
 def run_lut_bake(args):

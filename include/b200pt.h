@@ -218,6 +218,17 @@ int32_t b200pt_post_set_tonemap(b200pt_handle h, const b200pt_tonemap *t);  /* S
 int32_t b200pt_post_set_bloom(b200pt_handle h, const b200pt_bloom *b);      /* SetBloomData */
 int32_t b200pt_post_process(b200pt_handle h);                               /* PostProcess(cmd); input = GetOutputImage() */
 int32_t b200pt_get_ldr(b200pt_handle h, uint8_t *dst_rgba8, int32_t dst_is_device); /* GetOutputImageView() -> RGBA8 */
+/* Multi-GPU post pass (BASELINE config 5; no reference equivalent): PostProcess for output rows [y0, y1) only.  Every rank holds the full HDR input
+ * (b200pt_set_hdr) and recomputes the few halo rows of each bloom mip its block depends on, so the rows equal those of b200pt_post_process bit for
+ * bit and no exchange is needed before the final gather of the RGBA8 blocks.  b200pt_get_ldr_rows copies rows [y0, y1) (packed, (y1-y0)*W*4 bytes);
+ * with a device destination the copy is asynchronous on the handle's stream. */
+int32_t b200pt_post_process_rows(b200pt_handle h, uint32_t y0, uint32_t y1);
+/* The "HDR accumulate" stage of config 5 as a stand-alone pass (SH/RayGen.slang:130-137; inside b200pt_path_trace the same rule runs in k_resolve):
+ * rows [y0, y1) of a full-size RGBA32F frame in DEVICE memory are folded into the accumulation image with lerp(prev, new, 1 / (frame_index + 1)).
+ * b200pt_post_input_rows reports which HDR rows b200pt_post_process_rows(y0, y1) reads (block + halo), i.e. the rows a rank has to accumulate. */
+int32_t b200pt_accumulate_rows(b200pt_handle h, const float *frame_rgba32f_device, uint32_t frame_index, uint32_t y0, uint32_t y1);
+int32_t b200pt_post_input_rows(b200pt_handle h, uint32_t y0, uint32_t y1, uint32_t *in_y0, uint32_t *in_y1);
+int32_t b200pt_get_ldr_rows(b200pt_handle h, uint32_t y0, uint32_t y1, uint8_t *dst_rgba8, int32_t dst_is_device);
 int32_t b200pt_get_bloom(b200pt_handle h, float *dst_rgba32f);              /* bloom mip 0 after the up pass (test hook) */
 int32_t b200pt_bloom_mip_sizes(uint32_t width, uint32_t height, uint32_t *wh_out20, uint32_t *levels_out);
 /* Editor::SaveToFile (Editor.cpp:815-843): RGBA8 -> PNG, row stride W*4 */

@@ -59,3 +59,13 @@ def test_reference_arm_prints_the_contract_line_and_idle_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "3"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_post_row_blocks_partition_the_image():
+    import bench
+    for H in (2160, 1080, 389):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [bench.post_row_block(H, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == H
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:])) and all(b[1] > b[0] for b in blocks)
+            assert all(b[0] % 8 == 0 for b in blocks)

@@ -501,6 +501,29 @@ def test_volume_api_and_traversal_shapes(pt, monkeypatch):
     with pytest.raises(P.B200ptError): T.add_volume(**vol)
 
 
+@pytest.mark.parametrize("W,H,world", [(517, 389, 2), (640, 360, 3), (1280, 720, 8)])
+def test_post_row_blocks_equal_the_full_image_pass(pt, W, H, world):
+    """BASELINE config 5 on N GPUs: every rank post-processes one block of output rows (b200pt_post_process_rows) from the full HDR input,
+    recomputing the halo rows of each bloom mip its block depends on.  The union of the blocks must equal b200pt_post_process bit for bit --
+    including blocks whose boundaries are not multiples of the 8-row tiles, and mips so small that every block needs all of them."""
+    rng = np.random.default_rng(11)
+    hdr = np.ones((H, W, 4), np.float32); hdr[..., :3] = (np.exp(rng.normal(0, 1.5, (H, W, 3))) * 0.6).astype(np.float32)
+    for _ in range(12):
+        y, x = rng.integers(0, H - 4), rng.integers(0, W - 4); hdr[y:y + 4, x:x + 4, :3] = 300.0
+    T = util.product_tracer("cornell_box", W, H)
+    T.set_hdr(hdr); T.post_process(); full = T.get_ldr().copy()
+    assert full[..., :3].std() > 10
+    cuts = [round(H * r / world) for r in range(world + 1)]; cuts[1] += 3 if world > 1 and cuts[1] + 3 < cuts[2] else 0   # one unaligned boundary
+    out = np.zeros_like(full)
+    for r in range(world):
+        T2 = util.product_tracer("cornell_box", W, H)                      # a fresh handle per "rank": nothing of the other blocks' mips is there
+        T2.set_hdr(hdr); T2.post_process_rows(cuts[r], cuts[r + 1])
+        out[cuts[r]:cuts[r + 1]] = T2.get_ldr_rows(cuts[r], cuts[r + 1])
+    assert np.array_equal(out, full), int((out != full).any(axis=-1).sum())
+    with pytest.raises(pt.B200ptError): T.post_process_rows(5, 5)
+    with pytest.raises(pt.B200ptError): T.post_process_rows(0, H + 1)
+
+
 def _mixed_materials_edit(T):
     """one rough conductor, one glass object with a scattering medium inside, one textureless mixed-lobe material: all four material classes"""
     n = T.material_count()

@@ -472,6 +472,23 @@ class PathTracer:
         if out is None: out = np.empty((h, w, 4), np.uint8)
         self._ck(self.L.b200pt_get_ldr(self.h, _p(out), 0)); return out
 
+    def accumulate_rows(self, frame_device_ptr, frame_index, y0, y1):
+        self._ck(self.L.b200pt_accumulate_rows(self.h, C.c_void_p(frame_device_ptr), C.c_uint32(frame_index), C.c_uint32(y0), C.c_uint32(y1)))
+
+    def post_input_rows(self, y0, y1):
+        a, b = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.b200pt_post_input_rows(self.h, C.c_uint32(y0), C.c_uint32(y1), C.byref(a), C.byref(b))); return a.value, b.value
+
+    def post_process_rows(self, y0, y1): self._ck(self.L.b200pt_post_process_rows(self.h, C.c_uint32(y0), C.c_uint32(y1)))
+
+    def get_ldr_rows(self, y0, y1, out=None):
+        w, h = self.size()
+        if out is None: out = np.empty((y1 - y0, w, 4), np.uint8)
+        self._ck(self.L.b200pt_get_ldr_rows(self.h, C.c_uint32(y0), C.c_uint32(y1), _p(out), 0)); return out
+
+    def get_ldr_rows_into_device(self, y0, y1, device_ptr):
+        self._ck(self.L.b200pt_get_ldr_rows(self.h, C.c_uint32(y0), C.c_uint32(y1), C.c_void_p(device_ptr), 1))
+
     def get_bloom(self):
         w, h = self.size(); out = np.empty((h, w, 4), np.float32)
         self._ck(self.L.b200pt_get_bloom(self.h, _p(out))); return out

@@ -178,6 +178,15 @@ int32_t b200pt_get_counters(b200pt_handle h, b200pt_counters *out) { if (!out) r
 int32_t b200pt_post_set_tonemap(b200pt_handle h, const b200pt_tonemap *t) { if (!t) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.set_tonemap(*t); }); }
 int32_t b200pt_post_set_bloom(b200pt_handle h, const b200pt_bloom *b) { if (!b) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.set_bloom(*b); }); }
 int32_t b200pt_post_process(b200pt_handle h) { return guard(h, [&](Engine &e) { e.post_process(); }); }
+int32_t b200pt_accumulate_rows(b200pt_handle h, const float *frame_device, uint32_t frame_index, uint32_t y0, uint32_t y1) {
+    return guard(h, [&](Engine &e) { e.accumulate_rows(reinterpret_cast<const float4 *>(frame_device), frame_index, y0, y1); });
+}
+int32_t b200pt_post_input_rows(b200pt_handle h, uint32_t y0, uint32_t y1, uint32_t *in0, uint32_t *in1) {
+    if (!in0 || !in1) return B200PT_ERR_WRONG_ARGUMENTS;
+    return guard(h, [&](Engine &e) { e.post_input_rows(y0, y1, in0, in1); });
+}
+int32_t b200pt_post_process_rows(b200pt_handle h, uint32_t y0, uint32_t y1) { return guard(h, [&](Engine &e) { e.post_process_rows(y0, y1); }); }
+int32_t b200pt_get_ldr_rows(b200pt_handle h, uint32_t y0, uint32_t y1, uint8_t *dst, int32_t dev) { return guard(h, [&](Engine &e) { e.get_ldr_rows(y0, y1, dst, dev != 0); }); }
 int32_t b200pt_get_ldr(b200pt_handle h, uint8_t *dst, int32_t dev) { if (!dst) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.get_ldr(dst, dev != 0); }); }
 int32_t b200pt_get_bloom(b200pt_handle h, float *dst) { if (!dst) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.get_bloom(dst); }); }
 int32_t b200pt_bloom_mip_sizes(uint32_t w, uint32_t hh, uint32_t *wh, uint32_t *levels) { if (!wh || !levels || !w || !hh) return B200PT_ERR_WRONG_ARGUMENTS; *levels = bloom_mip_sizes(w, hh, wh); return B200PT_OK; }

@@ -153,7 +153,13 @@ void Engine::upload_scene() {
         if (const char *e = getenv("B200PT_FLAT_MAX")) { const int v = atoi(e); if (v >= 0 && v <= 64) flat_max = (uint32_t)v; }
         ds_.n_flat = (bvh_.n_tris <= flat_max) ? bvh_.n_tris : 0u;
     }
+    for (int k = 0; k < 3; k++) {                                           // ray-sort grid over the scene box (k_ray_sort_keys)
+        const float ext = bvh_.scene_bounds[3 + k] - bvh_.scene_bounds[k];
+        ds_.sort_lo[k] = bvh_.scene_bounds[k]; ds_.sort_scale[k] = ext > 0.0f ? 32.0f / ext : 0.0f;
+    }
     int q = query_launch_cfg(ds_, bvh_.max_depth, bvh_.depth4, &lc_);
+    sort_rays_ = lc_.trav_dyn && !lc_.bvh_in_smem;                          // scenes traversed out of L2 by the dynamic-fetch kernels; B200PT_SORT=0|1 overrides
+    if (const char *e = getenv("B200PT_SORT")) sort_rays_ = atoi(e) != 0 && lc_.trav_dyn;
     if (q != 0) throw CudaError{ B200PT_ERR_CUDA, "query_launch_cfg failed" };
 }
 
@@ -375,6 +381,7 @@ void Engine::ensure_image() {
 void Engine::free_wave() {
     for (auto &p : ps_) { dfree(p.org_pdf); dfree(p.dir_rng); dfree(p.thr_depth); dfree(p.rad_slot); dfree(p.medium); dfree(p.medium_g); dfree(p.vol_depth); }
     dfree(so_.hit); dfree(so_.bxdf_pdf); dfree(so_.e0); dfree(so_.sky_o); dfree(so_.sky_d); dfree(so_.sky_c); dfree(so_.lit_o); dfree(so_.lit_d); dfree(so_.lit_c);
+    dfree(d_sort_key_rank_); dfree(d_sort_hist_); dfree(d_sort_offs_); dfree(d_order_);
     dfree(d_sample_buf_); dfree(d_rng_carry_); dfree(d_q_hit_[0]); dfree(d_q_hit_[1]); dfree(d_q_miss_[0]); dfree(d_q_miss_[1]); dfree(d_disp_[0]); dfree(d_disp_[1]);
     for (auto &hp : h_disp_) if (hp) { cudaFreeHost(hp); hp = nullptr; }
     wave_cap_ = 0;
@@ -388,6 +395,9 @@ void Engine::ensure_wave(size_t cap) {
     a4(so_.hit); a4(so_.bxdf_pdf); a4(so_.e0); a4(so_.sky_o); a4(so_.sky_d); a4(so_.sky_c); a4(so_.lit_o); a4(so_.lit_d); a4(so_.lit_c);
     a4(d_sample_buf_);
     CK(cudaMalloc(&d_rng_carry_, cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&d_sort_key_rank_, cap * sizeof(uint2))); CK(cudaMalloc(&d_order_, cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&d_sort_hist_, SORT_BINS * sizeof(uint32_t))); CK(cudaMalloc(&d_sort_offs_, SORT_BINS * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(d_sort_hist_, 0, SORT_BINS * sizeof(uint32_t), stream_));
     for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_q_hit_[i], (size_t)MC_COUNT * cap * sizeof(uint32_t))); CK(cudaMalloc(&d_q_miss_[i], cap * sizeof(uint32_t))); }   // one hit queue per material class, ping-pong for the fused bounce kernel
     for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); CK(cudaMallocHost(&h_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); }
     wave_cap_ = cap;
@@ -483,7 +493,9 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                     const uint32_t par = k & 1u;
                     const Queues qc{ d_q_miss_[qsel[par]], d_q_hit_[qsel[par]], qcap }, qn{ d_q_miss_[qsel[par ^ 1u]], d_q_hit_[qsel[par ^ 1u]], qcap };
                     if (n_vol) { launch_volume_decide(lc_, ds_, pst[cur], so_, d_counts_, par, stream_); launches++; }
-                    if (fuse != 2 || k == 0) { launch_extend(lc_, ds_, pst[cur], hitb[par], d_counts_, par, qc, d_ctr_, k == 0, stream_); launches++; } mark(1);
+                    const bool sorted = sort_rays_ && k >= 1;            // camera rays are pixel-coherent already
+                    if (sorted) { launch_ray_sort(lc_, ds_, pst[cur], d_counts_, par, d_sort_key_rank_, d_sort_hist_, d_sort_offs_, d_order_, stream_); launches += 3; }
+                    if (fuse != 2 || k == 0) { launch_extend(lc_, ds_, pst[cur], hitb[par], d_counts_, par, qc, d_ctr_, k == 0, sorted ? d_order_ : nullptr, stream_); launches++; } mark(1);
                     launches += launch_shade(lc_, ds_, dc, pst[cur], pst[cur ^ 1], so_, hitb[par], hitb[par ^ 1u], d_counts_, par, qc, qn, d_sample_buf_, d_rng_carry_, d_ctr_,
                                              fuse, cmask, stream_); mark(2);
                     if (!fuse) { launch_connect(lc_, ds_, dc, pst[cur], pst[cur ^ 1], so_, d_counts_, par, qc, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); launches += lc_.trav_dyn ? 2 : 1; } mark(3);
@@ -538,7 +550,8 @@ void Engine::get_hdr(float *dst, bool dev) {
     CK(cudaSetDevice(device_));
     if (!d_image_ || !dst) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "no image" };
     CK(cudaMemcpyAsync(dst, d_image_, (size_t)W_ * local_rows_ * sizeof(float4), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream_));
-    CK(cudaStreamSynchronize(stream_));
+    if (!dev) CK(cudaStreamSynchronize(stream_));        // a device destination stays asynchronous on the engine's stream: the NCCL gather that follows is stream-ordered,
+                                                          // and the host can already enqueue the next wave (no per-step bubble on multi-GPU runs)
 }
 void Engine::set_hdr(const float *src, bool dev) {
     CK(cudaSetDevice(device_));
@@ -596,11 +609,42 @@ void Engine::ensure_post() {
     CK(cudaMalloc(&d_ldr_, (size_t)W_ * H_ * sizeof(uchar4)));
     post_w_ = W_; post_h_ = H_;
 }
-void Engine::post_process() {
+void Engine::accumulate_rows(const float4 *d_frame, uint32_t frame_index, uint32_t y0, uint32_t y1) {
+    CK(cudaSetDevice(device_));
+    if (!d_image_ || !d_frame || y0 >= y1 || y1 > H_ || world_ != 1) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "accumulate_rows: no image / bad rows / partitioned image" };
+    launch_accumulate(d_frame, d_image_, y0 * W_, (y1 - y0) * W_, frame_index, lc_.grid_light > 0 ? lc_.grid_light : 1184, stream_);
+    CK(cudaGetLastError());
+}
+// HDR rows read by post_process_rows(y0, y1): the final kernel's rows y0-1 .. y1-1 and the first down pass's taps 2y-2 .. 2y+1 over D[1]
+void Engine::post_input_rows(uint32_t y0, uint32_t y1, uint32_t *in0, uint32_t *in1) {
+    if (y0 >= y1 || y1 > H_) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_input_rows: bad row range" };
+    ensure_post();
+    const uint32_t levels = (uint32_t)d_mips_.size(), mips = std::min(std::max(bloom_.MipCount, 1u), levels);
+    int lo = std::max((int)y0 - 1, 0), hi = (int)y1 - 1;
+    if (mips >= 2) {
+        int U[24][2], D[24][2];
+        auto clampr = [&](int v, uint32_t i) { return std::min(std::max(v, 0), (int)mip_wh_[2 * i + 1] - 1); };
+        U[1][0] = clampr(lo / 2 - 1, 1); U[1][1] = clampr(hi / 2 + 2, 1);
+        for (uint32_t i = 2; i < mips; i++) { U[i][0] = clampr(U[i - 1][0] / 2 - 1, i); U[i][1] = clampr(U[i - 1][1] / 2 + 2, i); }
+        D[mips - 1][0] = U[mips - 1][0]; D[mips - 1][1] = U[mips - 1][1];
+        for (uint32_t i = mips - 1; i-- > 1;) { D[i][0] = std::min(U[i][0], clampr(2 * D[i + 1][0] - 2, i)); D[i][1] = std::max(U[i][1], clampr(2 * D[i + 1][1] + 1, i)); }
+        lo = std::min(lo, std::max(2 * D[1][0] - 2, 0)); hi = std::max(hi, std::min(2 * D[1][1] + 1, (int)H_ - 1));
+    }
+    *in0 = (uint32_t)lo; *in1 = (uint32_t)hi + 1u;
+}
+void Engine::post_process() { post_process_rows(0, H_); }
+
+// Row-block post pass (BASELINE config 5 on 2 / 4 / 8 GPUs): rank r holds the full HDR image and produces output rows [y0, y1) only.  The bloom chain is
+// evaluated on exactly the rows those outputs depend on -- per mip i the rows U[i] whose post-up value is read and the rows D[i] whose down
+// result is read (U[i] plus the taps of the next down pass) -- so the block equals the same rows of the full-image pass bit for bit (tested)
+// without any exchange: the halo is recomputed, ~4 rows per level next to a block of H / (N 2^i) rows, the whole mip once it is a few rows tall.
+void Engine::post_process_rows(uint32_t y0, uint32_t y1) {
     CK(cudaSetDevice(device_));
     if (!d_image_ || !W_ || !H_) throw CudaError{ B200PT_ERR_NO_SCENE, "PostProcess without an input image" };
     if (world_ != 1) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_process needs the full image: gather the bands first (world must be 1)" };
+    if (y0 >= y1 || y1 > H_) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_process_rows: bad row range" };
     ensure_post();
+    const bool whole = (y0 == 0 && y1 == H_);
     const uint32_t levels = (uint32_t)d_mips_.size();
     const uint32_t mips = std::min(std::max(bloom_.MipCount, 1u), levels);                      // :195
     const PostParams p{ tonemap_.Exposure, tonemap_.Gamma, bloom_.BloomThreshold, bloom_.BloomStrength, bloom_.FalloffRange };
@@ -609,23 +653,39 @@ void Engine::post_process() {
     // same RGBA8 image bit for bit (tested).
     bool fused = mips >= 2;
     if (const char *e = getenv("B200PT_POST_FUSED")) { if (atoi(e) == 0) fused = false; }
+    if (!fused && !whole) throw CudaError{ B200PT_ERR_NOT_IMPLEMENTED, "post_process_rows needs the fused chain (MipCount >= 2, B200PT_POST_FUSED unset)" };
     if (fused) {
-        // passes ls..mips-1 (every mip whose finer neighbour holds <= 160 K pixels) can run inside one cluster launch (k_bloom_small)
-        // Measured at 3840x2160 (profiles/r02_variants.txt): 0.323 ms with the cluster kernel against 0.302 ms with one launch per pass (8 CTAs walk mips that
-        // 148 SMs finish faster than the launches cost) -> OPT-IN (B200PT_POST_SMALL=1).
+        // needed row ranges, inclusive: U[i] post-up rows of mip i, D[i] down-result rows of mip i (i = 1 .. mips-1)
+        int U[24][2], D[24][2];
+        auto hgt = [&](uint32_t i) { return (int)mip_wh_[2 * i + 1]; };
+        auto clampr = [&](int v, uint32_t i) { return std::min(std::max(v, 0), hgt(i) - 1); };
+        {   // mip 0 rows the final kernel builds for outputs [y0, y1): y-1 .. y (bilinear bloom fetch); their up-sample term reads mip 1 rows yy/2 - 1 .. yy/2 + 2
+            const int a = std::max((int)y0 - 1, 0), b = (int)y1 - 1;
+            U[1][0] = clampr(a / 2 - 1, 1); U[1][1] = clampr(b / 2 + 2, 1);
+        }
+        for (uint32_t i = 2; i < mips; i++) { U[i][0] = clampr(U[i - 1][0] / 2 - 1, i); U[i][1] = clampr(U[i - 1][1] / 2 + 2, i); }   // up pass i: dst rows U[i-1] read src rows y/2 - 1 .. y/2 + 2
+        D[mips - 1][0] = U[mips - 1][0]; D[mips - 1][1] = U[mips - 1][1];
+        for (uint32_t i = mips - 1; i-- > 1;) {                                                 // down pass i+1: dst rows D[i+1] read src rows 2y - 2 .. 2y + 1
+            D[i][0] = std::min(U[i][0], clampr(2 * D[i + 1][0] - 2, i)); D[i][1] = std::max(U[i][1], clampr(2 * D[i + 1][1] + 1, i));
+        }
+        auto rows_of = [&](const int r[2], int out[2]) { out[0] = r[0]; out[1] = r[1] + 1; };
+        // the small end of the chain inside one cluster launch (k_bloom_small): measured slower at 3840x2160 (0.323 vs 0.302 ms, profiles/r02_variants.txt) -> OPT-IN, whole image only
         uint32_t ls = mips;
-        if (const char *e = getenv("B200PT_POST_SMALL")) { if (atoi(e) == 1) for (uint32_t i = 2; i < mips; i++) if ((uint64_t)mip_wh_[2 * (i - 1)] * mip_wh_[2 * (i - 1) + 1] <= 160u * 1024u) { ls = i; break; } }
+        if (whole) if (const char *e = getenv("B200PT_POST_SMALL")) { if (atoi(e) == 1) for (uint32_t i = 2; i < mips; i++) if ((uint64_t)mip_wh_[2 * (i - 1)] * mip_wh_[2 * (i - 1) + 1] <= 160u * 1024u) { ls = i; break; } }
         if (mips > 16) ls = mips;
-        launch_bloom_down_first(d_image_, W_, H_, d_mips_[1], mip_wh_[2], mip_wh_[3], p, stream_);                               // :200-226, i == 0 and i == 1
-        for (uint32_t i = 2; i < ls; i++) launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_);
+        int r[2];
+        rows_of(D[1], r);
+        launch_bloom_down_first(d_image_, W_, H_, d_mips_[1], mip_wh_[2], mip_wh_[3], p, stream_, whole ? nullptr : r);                               // :200-226, i == 0 and i == 1
+        for (uint32_t i = 2; i < ls; i++) { rows_of(D[i], r); launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_, whole ? nullptr : r); }
         if (ls < mips) {
             SmallMips sm{}; sm.first = (int)ls; sm.last = (int)mips - 1;
             for (uint32_t i = ls - 1; i < mips; i++) { sm.mip[i] = d_mips_[i]; sm.w[i] = (int)mip_wh_[2 * i]; sm.h[i] = (int)mip_wh_[2 * i + 1]; }
             launch_bloom_small(sm, p, stream_);
         }
-        for (uint32_t i = ls - 1; i > 1; i--) launch_bloom_up(d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], p, stream_);   // :229-235
-        launch_bloom_final(d_image_, d_mips_[1], mip_wh_[2], mip_wh_[3], d_ldr_, keep_bloom_ ? d_mips_[0] : nullptr, W_, H_, p, stream_);   // last up pass + :238-245
-        bloom_valid_ = keep_bloom_;
+        for (uint32_t i = ls - 1; i > 1; i--) { rows_of(U[i - 1], r); launch_bloom_up(d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], p, stream_, whole ? nullptr : r); }   // :229-235
+        r[0] = (int)y0; r[1] = (int)y1;
+        launch_bloom_final(d_image_, d_mips_[1], mip_wh_[2], mip_wh_[3], d_ldr_, (keep_bloom_ && whole) ? d_mips_[0] : nullptr, W_, H_, p, stream_, whole ? nullptr : r);   // last up pass + :238-245
+        bloom_valid_ = keep_bloom_ && whole;
     } else {
         launch_bloom_threshold(d_image_, d_mips_[0], W_ * H_, p, lc_.grid_light > 0 ? lc_.grid_light : 1184, stream_);            // :200-226, i == 0
         for (uint32_t i = 1; i < mips; i++) launch_bloom_down(d_mips_[i - 1], mip_wh_[2 * (i - 1)], mip_wh_[2 * (i - 1) + 1], d_mips_[i], mip_wh_[2 * i], mip_wh_[2 * i + 1], p, stream_);
@@ -634,6 +694,12 @@ void Engine::post_process() {
         bloom_valid_ = true;
     }
     CK(cudaGetLastError());
+}
+void Engine::get_ldr_rows(uint32_t y0, uint32_t y1, uint8_t *dst, bool dev) {
+    CK(cudaSetDevice(device_));
+    if (!d_ldr_ || !dst || y0 >= y1 || y1 > H_) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_process has not run / bad row range" };
+    CK(cudaMemcpyAsync(dst, reinterpret_cast<const uint8_t *>(d_ldr_) + (size_t)y0 * W_ * 4, (size_t)(y1 - y0) * W_ * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream_));
+    if (!dev) CK(cudaStreamSynchronize(stream_));
 }
 void Engine::get_ldr(uint8_t *dst, bool dev) {
     CK(cudaSetDevice(device_));

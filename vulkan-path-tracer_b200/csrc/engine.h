@@ -59,7 +59,12 @@ public:
     // PostProcessor
     void set_tonemap(const b200pt_tonemap &t) { tonemap_ = t; }
     void set_bloom(const b200pt_bloom &b) { bloom_ = b; }
+    // HDR accumulate as a stand-alone pass (config 5): rows [y0, y1) of a full-size device frame are folded into the accumulation image (frame_index = frames already in it)
+    void accumulate_rows(const float4 *d_frame, uint32_t frame_index, uint32_t y0, uint32_t y1);
+    void post_input_rows(uint32_t y0, uint32_t y1, uint32_t *in0, uint32_t *in1);   // HDR rows that post_process_rows(y0, y1) reads
     void post_process();
+    void post_process_rows(uint32_t y0, uint32_t y1);             // output rows [y0, y1) only (multi-GPU post pass); equals the same rows of post_process()
+    void get_ldr_rows(uint32_t y0, uint32_t y1, uint8_t *dst, bool dst_is_device);   // device destination: asynchronous on the engine's stream
     void get_ldr(uint8_t *dst, bool dst_is_device);
     void get_bloom(float *dst);
 
@@ -126,6 +131,8 @@ private:
     float4 *d_sample_buf_ = nullptr; uint32_t *d_rng_carry_ = nullptr; uint32_t *d_q_hit_[2] = { nullptr, nullptr }, *d_q_miss_[2] = { nullptr, nullptr }; uint32_t *d_counts_ = nullptr; DevDispatch *d_disp_[2] = { nullptr, nullptr };
     DevDispatch *h_disp_[2] = { nullptr, nullptr }; uint32_t *h_count_ = nullptr;
     WaveCounters *d_ctr_ = nullptr;
+    uint2 *d_sort_key_rank_ = nullptr; uint32_t *d_sort_hist_ = nullptr, *d_sort_offs_ = nullptr, *d_order_ = nullptr;   // ray sort of incoherent bounces (launch_ray_sort)
+    bool sort_rays_ = false;
     b200pt_counters last_{};
 };
 

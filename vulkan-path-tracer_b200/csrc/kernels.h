@@ -28,7 +28,12 @@ int query_launch_cfg(const DevScene &sc, int bvh_max_depth, int bvh4_depth, Laun
 void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P, uint32_t first_sample,
                    const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *ctrl, WaveCounters *ctr, cudaStream_t st);
 void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, float4 *hit_out, uint32_t *ctrl, uint32_t parity, Queues q,
-                   WaveCounters *ctr, bool primary, cudaStream_t st);
+                   WaveCounters *ctr, bool primary, const uint32_t *order, cudaStream_t st);
+// Ray sort for the dynamic-fetch traversal of incoherent bounces: order[0..n) = the live paths of parity `parity` sorted by (origin cell, direction octant).
+// key_rank: n x uint2 scratch, hist / offs: SORT_BINS words each (hist must be zero on entry and is zero again on exit).
+constexpr uint32_t SORT_BINS = 1u << 18;
+void launch_ray_sort(const LaunchCfg &lc, const DevScene &sc, PathState ps, const uint32_t *ctrl, uint32_t parity, uint2 *key_rank, uint32_t *hist, uint32_t *offs,
+                     uint32_t *order, cudaStream_t st);
 // k_shade_miss + k_shade_hit<CLASS> for every class in class_mask (+ k_shade_volume); returns the number of kernels launched.
 // fuse != 0: the bounce is finished inside k_shade_hit (dst, q_next, hit_out are written), launch_connect is not called.
 int launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, PathState dst, ShadeOut so, const float4 *hit_in, float4 *hit_out,
@@ -45,7 +50,8 @@ void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, cons
 // ---- LBVH build (lbvh.cu): world-space flattening of the two-level TLAS/BLAS ----
 struct LbvhResult { ShadeTri *shade; uint32_t *tri_slot; BvhNode *nodes; BvhTri *tris; uint32_t n_nodes, n_tris; int32_t root; int max_depth; size_t bytes;
                     Bvh4Node *nodes4; uint32_t n_nodes4; int depth4;
-                    float *h_ref_box; uint32_t n_prims; };                 // host copy of the per-slot reference boxes (only when asked for), triangle count
+                    float *h_ref_box; uint32_t n_prims;
+                    float scene_bounds[6]; };                              // lo.xyz, hi.xyz of all triangles (world space)                 // host copy of the per-slot reference boxes (only when asked for), triangle count
 // Builds into ONE contiguous allocation [nodes | tris] (so small scenes can be staged to smem with one bulk copy).
 // Returns cudaError_t as int.
 int lbvh_build(const b200pt_vertex *d_verts, const uint32_t *d_indices, const DevMesh *d_meshes, const DevInstance *d_instances,
@@ -69,15 +75,17 @@ int lbvh_build_wide(LbvhResult *r, cudaStream_t st);
 
 // ---- post chain (post_kernels.cu) ----
 struct PostParams { float Exposure, Gamma, BloomThreshold, BloomStrength, FalloffRange; };
+void launch_accumulate(const float4 *frame, float4 *image, uint32_t first, uint32_t count, uint32_t frame_index, int grid, cudaStream_t st);   // running mean of pixels [first, first + count)
 void launch_bloom_threshold(const float4 *hdr, float4 *mip0, uint32_t npix, PostParams p, int grid, cudaStream_t st);
-void launch_bloom_down(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st);
+// rows (optional): {first, end} row range of the destination the launch computes (multi-GPU post pass); nullptr = all rows
+void launch_bloom_down(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st, const int *rows = nullptr);
 // fused chain: threshold folded into the first down pass (mip 0 is never written) and [last up pass + threshold + tonemap] in one kernel
-void launch_bloom_down_first(const float4 *hdr, uint32_t W, uint32_t H, float4 *mip1, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st);
-void launch_bloom_final(const float4 *hdr, const float4 *mip1, uint32_t mw, uint32_t mh, uchar4 *ldr, float4 *mip0_out, uint32_t W, uint32_t H, PostParams p, cudaStream_t st);
+void launch_bloom_down_first(const float4 *hdr, uint32_t W, uint32_t H, float4 *mip1, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st, const int *rows = nullptr);
+void launch_bloom_final(const float4 *hdr, const float4 *mip1, uint32_t mw, uint32_t mh, uchar4 *ldr, float4 *mip0_out, uint32_t W, uint32_t H, PostParams p, cudaStream_t st, const int *rows = nullptr);
 // passes first..last of the chain (down first..last, then up last..first) in one cluster launch; mip[i] / w[i] / h[i] for i in [first-1, last]
 struct SmallMips { float4 *mip[16]; int w[16], h[16]; int first, last; };
 void launch_bloom_small(const SmallMips &m, PostParams p, cudaStream_t st);
-void launch_bloom_up(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st);
+void launch_bloom_up(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st, const int *rows = nullptr);
 void launch_tonemap(const float4 *hdr, const float4 *bloom0, uchar4 *ldr, uint32_t W, uint32_t H, PostParams p, cudaStream_t st);
 void launch_prepare_materials(DevMaterial *mats, uint32_t first, uint32_t count, cudaStream_t st);   // fills DevMaterial::pre0..pre3
 // lut_baker.cu : kind 0 = reflect, 1 = refract hit-from-outside, 2 = refract hit-from-inside; partial holds slices * SX*SY*SZ floats

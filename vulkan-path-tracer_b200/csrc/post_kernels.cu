@@ -42,9 +42,11 @@ __global__ void __launch_bounds__(256) k_bloom_threshold(const float4 *__restric
 }
 
 // BloomDownSample.slang:46-64 : taps 2*xy + (a,b), a,b in [-2,1], clamp, /25, *strength (Q14).
-__global__ void __launch_bounds__(256) k_bloom_down(const float4 *__restrict__ src, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= dw || y >= dh) return;
+// Every chain kernel works on a ROW RANGE [y0, y1) of its destination (the whole image by default): a multi-GPU post pass gives each rank a block
+// of output rows plus the halo rows the later passes read (Engine::post_process_rows).
+__global__ void __launch_bounds__(256) k_bloom_down(const float4 *__restrict__ src, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p, int y0, int y1) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= y1) return;
     float3 acc = f3(0.0f);
     #pragma unroll
     for (int a = -2; a < 2; a++) {
@@ -61,9 +63,9 @@ __global__ void __launch_bounds__(256) k_bloom_down(const float4 *__restrict__ s
 // needs the 66 x 18 HDR texels around it; each is thresholded ONCE into shared memory (it feeds up to 4 outputs) and the 16 taps of an
 // output are read from there in the reference's order.  Clamping happens on the load, so tile slot (lx, ly) always holds the texel the
 // clamped tap coordinate 2*x0 - 2 + lx would fetch.
-__global__ void __launch_bounds__(256) k_bloom_down_first(const float4 *__restrict__ hdr, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p) {
+__global__ void __launch_bounds__(256) k_bloom_down_first(const float4 *__restrict__ hdr, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p, int row0, int row1) {
     __shared__ float tr[18][66], tg[18][66], tb[18][66];
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const int x0 = blockIdx.x * 32, y0 = row0 + blockIdx.y * 8;
     const float start = p.BloomThreshold - p.FalloffRange, end = p.BloomThreshold + p.FalloffRange;
     for (int k = threadIdx.x; k < 66 * 18; k += 256) {
         const int lx = k % 66, ly = k / 66;
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(256) k_bloom_down_first(const float4 *__restri
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int x = x0 + tx, y = y0 + ty;
-    if (x >= dw || y >= dh) return;
+    if (x >= dw || y >= row1) return;
     float3 acc = f3(0.0f);
     #pragma unroll
     for (int a = -2; a < 2; a++) {
@@ -102,9 +104,9 @@ __device__ __forceinline__ float3 bloom_up_taps(const float4 *__restrict__ src, 
     return f3(bloom_scale(acc.x, strength), bloom_scale(acc.y, strength), bloom_scale(acc.z, strength));
 }
 // ... added to the finer mip in place
-__global__ void __launch_bounds__(256) k_bloom_up(const float4 *__restrict__ src, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= dw || y >= dh) return;
+__global__ void __launch_bounds__(256) k_bloom_up(const float4 *__restrict__ src, int sw, int sh, float4 *__restrict__ dst, int dw, int dh, PostParams p, int y0, int y1) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= y1) return;
     const float3 u = bloom_up_taps(src, sw, sh, x, y, p.BloomStrength);
     const float4 cur = dst[(size_t)y * dw + x];
     dst[(size_t)y * dw + x] = make_float4(__fadd_rn(u.x, cur.x), __fadd_rn(u.y, cur.y), __fadd_rn(u.z, cur.z), 1.0f);
@@ -169,11 +171,11 @@ __global__ void __launch_bounds__(256) k_tonemap(const float4 *__restrict__ hdr,
 // shared memory from the HDR image and mip 1 and consumed on the spot: HBM sees the HDR read, the small mip-1 read and the RGBA8 write.
 // mip0_out (optional) receives the tile interior so GetBloom-style consumers can still see mip 0.
 __global__ void __launch_bounds__(256) k_bloom_final(const float4 *__restrict__ hdr, const float4 *__restrict__ mip1, int mw, int mh,
-                                                     uchar4 *__restrict__ ldr, float4 *__restrict__ mip0_out, int W, int H, PostParams p) {
+                                                     uchar4 *__restrict__ ldr, float4 *__restrict__ mip0_out, int W, int H, PostParams p, int row0, int row1) {
     __shared__ float4 tile[9][34];      // bloom mip 0 (rgb), halo at row / column 0
     __shared__ float4 tile_h[9][34];    // HDR texel of the same pixel
     __shared__ float4 up[5][18];        // the up-sampled term: it depends on (x/2, y/2) only, so the 33 x 9 pixels share <= 17 x 5 values
-    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 8;
+    const int tx0 = blockIdx.x * 32, ty0 = row0 + blockIdx.y * 8;
     const int mx0 = clampi(tx0 - 1, 0, W - 1) / 2, my0 = clampi(ty0 - 1, 0, H - 1) / 2;
     const float start = p.BloomThreshold - p.FalloffRange, end = p.BloomThreshold + p.FalloffRange;
     for (int k = threadIdx.x; k < 17 * 5; k += 256) {
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(256) k_bloom_final(const float4 *__restrict__ 
     }
     __syncthreads();
     const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
-    if (x >= W || y >= H) return;
+    if (x >= W || y >= row1) return;
     const BloomTap t = bloom_tap(x, y, W, H);                               // x0 in {x-1, x}, x1 = x0 + 1 (clamped): inside the tile + halo
     const int lx0 = t.x0 - (tx0 - 1), lx1 = t.x1 - (tx0 - 1), ly0 = t.y0 - (ty0 - 1), ly1 = t.y1 - (ty0 - 1);
     const int cx = (threadIdx.x & 31) + 1, cy = (threadIdx.x >> 5) + 1;
@@ -256,24 +258,45 @@ __global__ void __cluster_dims__(SMALL_CLUSTER, 1, 1) __launch_bounds__(1024) k_
 }
 void launch_bloom_small(const SmallMips &m, PostParams p, cudaStream_t st) { k_bloom_small<<<SMALL_CLUSTER, 1024, 0, st>>>(m, p); }
 
+// SH/RayGen.slang:130-137 as a stand-alone pass: fold one frame's radiance image into the accumulation image with the running-mean rule
+// lerp(prev, new, 1 / (FrameCount + 1)) -- the "HDR accumulate" stage of BASELINE config 5 (inside PathTrace the same rule runs in k_resolve).
+__global__ void __launch_bounds__(256) k_accumulate(const float4 *__restrict__ frame, float4 *__restrict__ image, uint32_t first, uint32_t count, uint32_t frame_index) {
+    const float a = 1.0f / (float)(frame_index + 1u);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const float4 s4 = frame[first + i];
+        float3 c = f3(s4);
+        if (frame_index > 0u) c = mix3(f3(image[first + i]), c, a);
+        image[first + i] = make_float4(c.x, c.y, c.z, 1.0f);
+    }
+}
+void launch_accumulate(const float4 *frame, float4 *image, uint32_t first, uint32_t count, uint32_t frame_index, int grid, cudaStream_t st) {
+    if (count) k_accumulate<<<grid, 256, 0, st>>>(frame, image, first, count, frame_index);
+}
+
 void launch_bloom_threshold(const float4 *hdr, float4 *mip0, uint32_t npix, PostParams p, int grid, cudaStream_t st) {
     k_bloom_threshold<<<grid, 256, 0, st>>>(hdr, mip0, npix, p);
 }
-void launch_bloom_down(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st) {
-    dim3 g((dw + 31) / 32, (dh + 7) / 8);
-    k_bloom_down<<<g, 256, 0, st>>>(src, (int)sw, (int)sh, dst, (int)dw, (int)dh, p);
+// rows == nullptr: the whole destination; else rows[0] <= y < rows[1]
+static inline void row_range(const int *rows, uint32_t h, int &y0, int &y1) { y0 = rows ? rows[0] : 0; y1 = rows ? rows[1] : (int)h; if (y0 < 0) y0 = 0; if (y1 > (int)h) y1 = (int)h; }
+void launch_bloom_down(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st, const int *rows) {
+    int y0, y1; row_range(rows, dh, y0, y1); if (y1 <= y0) return;
+    dim3 g((dw + 31) / 32, (y1 - y0 + 7) / 8);
+    k_bloom_down<<<g, 256, 0, st>>>(src, (int)sw, (int)sh, dst, (int)dw, (int)dh, p, y0, y1);
 }
-void launch_bloom_down_first(const float4 *hdr, uint32_t W, uint32_t H, float4 *mip1, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st) {
-    dim3 g((dw + 31) / 32, (dh + 7) / 8);
-    k_bloom_down_first<<<g, 256, 0, st>>>(hdr, (int)W, (int)H, mip1, (int)dw, (int)dh, p);
+void launch_bloom_down_first(const float4 *hdr, uint32_t W, uint32_t H, float4 *mip1, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st, const int *rows) {
+    int y0, y1; row_range(rows, dh, y0, y1); if (y1 <= y0) return;
+    dim3 g((dw + 31) / 32, (y1 - y0 + 7) / 8);
+    k_bloom_down_first<<<g, 256, 0, st>>>(hdr, (int)W, (int)H, mip1, (int)dw, (int)dh, p, y0, y1);
 }
-void launch_bloom_final(const float4 *hdr, const float4 *mip1, uint32_t mw, uint32_t mh, uchar4 *ldr, float4 *mip0_out, uint32_t W, uint32_t H, PostParams p, cudaStream_t st) {
-    dim3 g((W + 31) / 32, (H + 7) / 8);
-    k_bloom_final<<<g, 256, 0, st>>>(hdr, mip1, (int)mw, (int)mh, ldr, mip0_out, (int)W, (int)H, p);
+void launch_bloom_final(const float4 *hdr, const float4 *mip1, uint32_t mw, uint32_t mh, uchar4 *ldr, float4 *mip0_out, uint32_t W, uint32_t H, PostParams p, cudaStream_t st, const int *rows) {
+    int y0, y1; row_range(rows, H, y0, y1); if (y1 <= y0) return;
+    dim3 g((W + 31) / 32, (y1 - y0 + 7) / 8);
+    k_bloom_final<<<g, 256, 0, st>>>(hdr, mip1, (int)mw, (int)mh, ldr, mip0_out, (int)W, (int)H, p, y0, y1);
 }
-void launch_bloom_up(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st) {
-    dim3 g((dw + 31) / 32, (dh + 7) / 8);
-    k_bloom_up<<<g, 256, 0, st>>>(src, (int)sw, (int)sh, dst, (int)dw, (int)dh, p);
+void launch_bloom_up(const float4 *src, uint32_t sw, uint32_t sh, float4 *dst, uint32_t dw, uint32_t dh, PostParams p, cudaStream_t st, const int *rows) {
+    int y0, y1; row_range(rows, dh, y0, y1); if (y1 <= y0) return;
+    dim3 g((dw + 31) / 32, (y1 - y0 + 7) / 8);
+    k_bloom_up<<<g, 256, 0, st>>>(src, (int)sw, (int)sh, dst, (int)dw, (int)dh, p, y0, y1);
 }
 void launch_tonemap(const float4 *hdr, const float4 *bloom0, uchar4 *ldr, uint32_t W, uint32_t H, PostParams p, cudaStream_t st) {
     dim3 g((W + 31) / 32, (H + 7) / 8);

@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM, bool PRIMARY, bool WIDE>   // WIDE: BVH4 nodes (sc.nodes4) instead of the BVH2
 __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, float4 *__restrict__ hit_out, uint32_t *__restrict__ ctrl, uint32_t parity,
-                                                     Queues q, int max_stack, int thresh, int n_top, WaveCounters *ctr) {
+                                                     Queues q, int max_stack, int thresh, int n_top, const uint32_t *__restrict__ order, WaveCounters *ctr) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, f
         if (need) {
             const uint32_t idx = pool.take(need, lane, fetch);
             if (fin) {
-                i = idx;
+                i = (order != nullptr && idx != DYN_NONE) ? order[idx] : idx;   // sorted bounce: the pool hands out positions of the sorted list (k_ray_sort_*)
                 if (i != DYN_NONE && sc.n_volumes && __float_as_uint(hit_out[i].w) == VOLUME_EVENT) {
                     r.gid = VOLUME_EVENT;                                   // scattered inside a volume (k_volume_decide): queued as a hit at the next commit, record kept
                 } else if (i != DYN_NONE) {
@@ -776,6 +776,51 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, f
             while (r.cur < 0 && r.cur != DYN_DONE) dyn_leaf_step<SMEM, false, WIDE>(bv, r, s_step, spill);
             act = __ballot_sync(0xFFFFFFFFu, r.cur != DYN_DONE);
         } while (__popc(act) >= thr_now);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ray sort (scenes traversed out of L2): after the first bounce the live list is in compaction order -- neighbouring lanes hold unrelated rays,
+// every warp of k_extend_dyn touches 32 different parts of a 40 MB BVH.  A counting sort of the path INDICES by an 18-bit key (15-bit Morton
+// code of the origin's cell in a 32^3 grid over the scene box | direction octant) costs three light passes (~0.3 ms per 16 M paths) and hands
+// k_extend_dyn spatially coherent rays; the hit queues it fills inherit the order, so k_shadow_dyn's origins are coherent too.  The path state
+// itself is not moved.  Order inside a bin is whatever the atomics return: paths are independent, the image does not depend on it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t morton_spread5(uint32_t v) {           // 5 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000100Fu; v = (v | (v << 4)) & 0x000010C3u; v = (v | (v << 2)) & 0x00001249u; return v;
+}
+__global__ void __launch_bounds__(256) k_ray_sort_keys(DevScene sc, PathState ps, const uint32_t *__restrict__ ctrl, uint32_t parity,
+                                                        uint2 *__restrict__ key_rank, uint32_t *__restrict__ hist) {
+    const uint32_t n = ctrl[parity];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
+        const int cx = min(31, max(0, (int)((o4.x - sc.sort_lo[0]) * sc.sort_scale[0])));
+        const int cy = min(31, max(0, (int)((o4.y - sc.sort_lo[1]) * sc.sort_scale[1])));
+        const int cz = min(31, max(0, (int)((o4.z - sc.sort_lo[2]) * sc.sort_scale[2])));
+        const uint32_t cell = morton_spread5((uint32_t)cx) | (morton_spread5((uint32_t)cy) << 1) | (morton_spread5((uint32_t)cz) << 2);
+        const uint32_t oct = (d4.x < 0.0f ? 1u : 0u) | (d4.y < 0.0f ? 2u : 0u) | (d4.z < 0.0f ? 4u : 0u);
+        const uint32_t key = (cell << 3) | oct;
+        key_rank[i] = make_uint2(key, atomicAdd(hist + key, 1u));
+    }
+}
+__global__ void __launch_bounds__(1024) k_ray_sort_scan(uint32_t *__restrict__ hist, uint32_t *__restrict__ offs) {   // one block: exclusive scan of SORT_BINS counts, hist cleared
+    __shared__ uint32_t part[1024];
+    constexpr uint32_t PER = SORT_BINS / 1024u;
+    const uint32_t t = threadIdx.x, b0 = t * PER;
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < PER; k++) sum += hist[b0 + k];
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) { const uint32_t v = t >= o ? part[t - o] : 0u; __syncthreads(); part[t] += v; __syncthreads(); }
+    uint32_t run = part[t] - sum;
+    for (uint32_t k = 0; k < PER; k++) { const uint32_t c = hist[b0 + k]; offs[b0 + k] = run; run += c; hist[b0 + k] = 0u; }
+}
+__global__ void __launch_bounds__(256) k_ray_sort_scatter(const uint32_t *__restrict__ ctrl, uint32_t parity, const uint2 *__restrict__ key_rank,
+                                                           const uint32_t *__restrict__ offs, uint32_t *__restrict__ order) {
+    const uint32_t n = ctrl[parity];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 kr = key_rank[i];
+        order[__ldg(offs + kr.x) + kr.y] = i;
     }
 }
 
@@ -1188,13 +1233,19 @@ void launch_raygen(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch 
                    const uint32_t *rng_carry, PathState ps, float4 *sample_buf, uint32_t *ctrl, WaveCounters *ctr, cudaStream_t st) {
     k_raygen<<<lc.grid_light, 256, 0, st>>>(cfg, disp, n_disp, P, first_sample, rng_carry, ps, sample_buf, ctrl, ctr);
 }
+void launch_ray_sort(const LaunchCfg &lc, const DevScene &sc, PathState ps, const uint32_t *ctrl, uint32_t parity, uint2 *key_rank, uint32_t *hist, uint32_t *offs,
+                     uint32_t *order, cudaStream_t st) {
+    k_ray_sort_keys<<<lc.grid_light, 256, 0, st>>>(sc, ps, ctrl, parity, key_rank, hist);
+    k_ray_sort_scan<<<1, 1024, 0, st>>>(hist, offs);
+    k_ray_sort_scatter<<<lc.grid_light, 256, 0, st>>>(ctrl, parity, key_rank, offs, order);
+}
 void launch_extend(const LaunchCfg &lc, const DevScene &sc, PathState ps, float4 *hit_out, uint32_t *ctrl, uint32_t parity, Queues q,
-                   WaveCounters *ctr, bool primary, cudaStream_t st) {
+                   WaveCounters *ctr, bool primary, const uint32_t *order, cudaStream_t st) {
     set_attrs_for_current_device();
     const bool smem = lc.bvh_in_smem;
     if (lc.trav_dyn) {
         const size_t sh = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem) + (size_t)lc.n_top4 * sizeof(Bvh4Node);
-#define B200PT_EXT_DYN(S, P, W) k_extend_dyn<S, P, W><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.dyn_stack, lc.dyn_thresh, lc.n_top4, ctr)
+#define B200PT_EXT_DYN(S, P, W) k_extend_dyn<S, P, W><<<lc.grid_extend, 256, sh, st>>>(sc, ps, hit_out, ctrl, parity, q, lc.dyn_stack, lc.dyn_thresh, lc.n_top4, order, ctr)
         if (lc.wide) { if (primary) B200PT_EXT_DYN(false, true, true); else B200PT_EXT_DYN(false, false, true); }
         else if (smem) { if (primary) B200PT_EXT_DYN(true, true, false); else B200PT_EXT_DYN(true, false, false); }
         else { if (primary) B200PT_EXT_DYN(false, true, false); else B200PT_EXT_DYN(false, false, false); }
