@@ -107,17 +107,37 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+ASSETS = os.path.join(ROOT, "oracle", "_ref", "assets")    # copy of the reference's shipped assets (oracle/Makefile `assets`; git-ignored, travels to the GPU box)
+ASSET_FILES = {"cornell_box": "CornellBox.gltf", "cornell_box_glass": "CornellBoxGlass.gltf", "breakfast_room": "BreakfastRoom.gltf", "viking_room": "VikingRoom.gltf"}
+ENV_FILE = "meadow_2_4k.hdr"                               # PathTracer.h:208, the reference's default environment map
+
+
+def have_assets(scene):
+    return all(os.path.isfile(os.path.join(ASSETS, f)) for f in (ASSET_FILES[scene], ENV_FILE, "LookupTables/ReflectionLookup.bin"))
+
+
 def synthetic_env_4k():
     from oracle import gltf_ref
     return gltf_ref.synthetic_env(4096, 2048, seed=3, sun=150000.0)
 
 
+def data_description(scene):
+    return "reference assets (shipped glTF scene, meadow_2_4k.hdr, lookup tables); random-number streams seeded by bench.py" if have_assets(scene) else "synthetic"
+
+
+def env_description(real):
+    return ("meadow_2_4k.hdr 4096x2048 (the reference's default map, RGBA32F 128 MiB + 64 MiB alias table)" if real
+            else "synthetic 4096x2048 RGBA32F (128 MiB) + 64 MiB alias table")
+
+
 def bench_config(workload, frames_per_step, steps, world, extra=None):
     """`config` of the JSON line: the same keys in both arms (the driver compares them)."""
     scene, W, H, depth = WORKLOADS[workload]
+    real = have_assets(scene)
     c = {"workload": workload, "scene": scene, "image": [W, H], "max_depth": depth, "spp_per_frame": 1, "frames_per_step": frames_per_step,
          "spp_total": frames_per_step * steps, "partition": f"{BAND_ROWS}-row bands x {world} ranks",
-         "env_map": "synthetic 4096x2048 RGBA32F (128 MiB) + 64 MiB alias table",
+         "scene_source": (ASSET_FILES[scene] + " through the product's own glTF loader (set_scene_file)") if real else "committed fixture tests/golden/" + scene + ".npz (set_scene_arrays)",
+         "env_map": env_description(real),
          "l2_policy": "inputs larger than L2 (env map + alias table 192 MiB, wavefront state of a 16.6 M-path wave > 1 GB vs 126 MB L2): no explicit flush"}
     if extra: c.update(extra)
     return c
@@ -150,6 +170,21 @@ def cpu_arm_describe(info, nthreads, sample):
                      "effective_cpus": info["effective_cpus"], "affinity_cpus": info.get("affinity_cpus")}}
 
 
+def oracle_scene_for(scene, depth):
+    """CPU arm: the oracle's scene + config for a workload -- real assets through the oracle-side loaders when the copy is there, else fixtures + synthetic map."""
+    import util
+    from oracle import orc, gltf_ref
+    if have_assets(scene):
+        sd = gltf_ref.load_gltf(os.path.join(ASSETS, ASSET_FILES[scene]))
+        raw = orc.load_hdr(os.path.join(ASSETS, ENV_FILE))
+        luts = gltf_ref.load_luts_dir(os.path.join(ASSETS, "LookupTables"))
+    else:
+        sd = util.scene_dict(scene); raw = synthetic_env_4k(); luts = util.luts()
+    env_pdf, alias, _ = orc.build_env_alias(raw)
+    vi, pi = orc.camera_from_view(sd["camera_view"], sd["aspect"])
+    return orc.Scene(sd, env_pdf, alias, luts), orc.default_config(ViewInverse=vi, ProjectionInverse=pi, MaxDepth=depth)
+
+
 def run_reference(args):
     """CPU arm: the oracle (port of the reference's Slang estimator; the Vulkan reference cannot run here -- profiles/r02_vulkan_host_probe.txt),
     -O3 -march=native build, one thread per CPU the cgroup quota grants; step = 1 frame; median of >= 3 timed repeats of the K steps."""
@@ -162,10 +197,7 @@ def run_reference(args):
     info = orc.host_cpu_info()
     cores = cpu_arm_threads(info)
     scene, W, H, depth = WORKLOADS[args.workload]
-    raw = synthetic_env_4k()
-    env_pdf, alias, _ = orc.build_env_alias(raw)
-    S = orc.Scene(util.scene_dict(scene), env_pdf, alias, util.luts())
-    cfg = util.oracle_config(scene, MaxDepth=depth)
+    S, cfg = oracle_scene_for(scene, depth)
     img = np.zeros((H, W, 4), np.float32)
     f = 0
     for _ in range(args.warmup):
@@ -182,7 +214,7 @@ def run_reference(args):
                                        f"{args.steps} steps, median of 3 repeats (pthreads over pixel rows)")
     cb.update({"value": v, "unit": "Mpaths/s", "repeats_mpaths": [W * H * args.steps / r / 1e6 for r in reps]})
     out = {"impl": "reference", "metric": "Mpaths/sec", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_description(scene),
            "config": bench_config(args.workload, args.frames_per_step, args.steps, max(args.gpus, 1)),   # the b200 arm's config; the bounded sample is in cpu_baseline.sample
            "cpu_baseline": cb,
            "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -351,10 +383,14 @@ def main():
     scene, W, H, depth = WORKLOADS[args.workload]
     F = args.frames_per_step
     T = pt.PathTracer(local)
-    T.set_scene(util.scene_dict(scene))
-    raw = synthetic_env_4k()
-    T.set_env_map(raw)
-    T.set_luts(*util.luts())
+    if have_assets(scene):                       # the product's own SetScene path: glTF + textures + HDR + lookup tables from the reference's shipped files
+        T.set_scene_file(os.path.join(ASSETS, ASSET_FILES[scene]))
+        T.set_env_map_file(os.path.join(ASSETS, ENV_FILE))
+        T.set_luts_dir(os.path.join(ASSETS, "LookupTables"))
+    else:
+        T.set_scene(util.scene_dict(scene))
+        T.set_env_map(synthetic_env_4k())
+        T.set_luts(*util.luts())
     cfg = pt.default_config(MaxDepth=depth, MaxSamplesAccumulated=0x7FFFFFFF, FramesInFlight=args.frames_in_flight)
     T.set_config(cfg)
     T.resize(W, H)
@@ -468,7 +504,7 @@ def main():
                              "frac": value / world / (peak * 1e9 / (pipeline_bytes / max(dprof["paths"], 1)) / 1e6)}}
 
     out = {"metric": "Mpaths/sec", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_description(scene),
            "config": bench_config(args.workload, F, args.steps, world),
            "notes": {"l2_policy": "working set > L2: env map 128 MiB + alias 64 MiB + wavefront state of a 16.6 M-path wave (126 MB L2), no explicit flush",
                      "timing": "CUDA events on the launching stream, max over ranks", "wall_s": wall},
@@ -481,9 +517,7 @@ def main():
             from oracle import orc
             orc.use_fast_build()
             info = orc.host_cpu_info(); cores = cpu_arm_threads(info)
-            env_pdf, alias, _ = orc.build_env_alias(raw)
-            S = orc.Scene(util.scene_dict(scene), env_pdf, alias, util.luts())
-            ocfg = util.oracle_config(scene, MaxDepth=depth)
+            S, ocfg = oracle_scene_for(scene, depth)
             n = args.cpu_baseline_frames
             S.render(ocfg, W, H, 1, BASE_SEED, nthreads=cores)
             reps = []

@@ -84,7 +84,16 @@ def host_cpu_info():
     return info
 
 
+def assets_dir():
+    """The reference's shipped assets: the read-only original in this container, else the copy under oracle/_ref/assets (made by `make assets`,
+    git-ignored, travels to the GPU box), else None."""
+    for d in ("/root/reference/Assets", os.path.join(_HERE, "_ref", "assets")):
+        if os.path.isfile(os.path.join(d, "CornellBox.gltf")): return d
+    return None
+
+
 def build(force=False):
+    subprocess.call(["make", "-C", _HERE, "-s", "assets"])
     if _FAST:
         so = os.path.join(_HERE, "liboracle_fast.so")
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "fast"])      # always rebuilt: -march=native must match THIS host

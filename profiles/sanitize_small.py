@@ -1,0 +1,26 @@
+"""Small end-to-end workload for compute-sanitizer (memcheck / racecheck / initcheck): every kernel family once, tiny sizes.
+usage: compute-sanitizer --tool memcheck python profiles/sanitize_small.py"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import util
+
+FOG = dict(CornerMin=(-4.0, -4.0, -10.0), CornerMax=(4.5, 3.0, -1.0), Density=0.35, Color=(0.8, 0.7, 0.6), Anisotropy=0.4, Alpha=1.5, DropletSize=14.0)
+def run(name, W, H, frames, depth, **kw):
+    T = util.product_tracer(name, W, H, MaxDepth=depth, **kw)
+    T.path_trace(frames, util.BASE_SEED)
+    img = T.get_hdr(); assert np.isfinite(img).all()
+    T.post_process(); T.get_ldr()
+    T.post_process_rows(8, min(H, 24)); T.get_ldr_rows(8, min(H, 24))
+    print(name, kw.get("Volumes") is not None, os.environ.get("B200PT_FUSE"), os.environ.get("B200PT_TRAV"), "ok", float(img[..., :3].mean()))
+
+run("cornell_box", 64, 36, 2, 6)                                   # BVH in shared memory (TMA), flat traversal, uniform class
+os.environ["B200PT_FLAT_MAX"] = "0"; run("cornell_box", 48, 32, 1, 4); del os.environ["B200PT_FLAT_MAX"]      # BVH2 stack traversal in shared memory
+os.environ["B200PT_FUSE"] = "2"; run("cornell_box", 48, 32, 2, 5); del os.environ["B200PT_FUSE"]              # fused bounce kernel
+run("cornell_box", 48, 32, 1, 5, Volumes=[FOG])                     # k_volume_decide / k_shade_volume
+run("cornell_box_glass", 48, 48, 2, 8)                              # dynamic-fetch BVH2 kernels, class queues (glass / diffuse)
+os.environ["B200PT_WIDE"] = "1"; run("viking_room", 48, 48, 1, 4); del os.environ["B200PT_WIDE"]              # BVH4 + textures
+os.environ["B200PT_SORT"] = "1"; os.environ["B200PT_TOP_KB"] = "16"; os.environ["B200PT_WIDE"] = "1"
+run("viking_room", 32, 32, 1, 3)                                    # ray sort + treelet staging (opt-in paths)
+print("sanitize_small done")

@@ -100,7 +100,7 @@ def test_config3_breakfast_room_converged_image(pt):
     l2 = util.rel_l2(got[..., :3], ref[..., :3])
     assert l2 < 1e-3, l2
     c = T.counters()
-    assert abs(c["extend_rays"] - cnt["segments"]) <= 0.002 * cnt["segments"] + 4 and abs(c["shadow_rays"] - cnt["shadow_rays"]) <= 0.002 * cnt["shadow_rays"] + 4
+    assert abs(c["extend_rays"] - cnt["segments"]) <= 0.002 * cnt["segments"] + 4 and abs(c["misses"] - cnt["misses"]) <= 0.002 * cnt["segments"] + 4
 
 
 def test_full_size_config2_frame(pt):

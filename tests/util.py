@@ -10,7 +10,7 @@ if ROOT not in sys.path:
 from oracle import orc, gltf_ref  # noqa: E402  (test infrastructure)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-REF_ASSETS = "/root/reference/Assets"
+REF_ASSETS = orc.assets_dir() or "/root/reference/Assets"   # the original here, the oracle/_ref/assets copy on the GPU box
 HAVE_REF = os.path.isdir(REF_ASSETS)
 BASE_SEED = 0x1234ABCD
 

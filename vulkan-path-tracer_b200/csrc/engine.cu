@@ -158,7 +158,10 @@ void Engine::upload_scene() {
         ds_.sort_lo[k] = bvh_.scene_bounds[k]; ds_.sort_scale[k] = ext > 0.0f ? 32.0f / ext : 0.0f;
     }
     int q = query_launch_cfg(ds_, bvh_.max_depth, bvh_.depth4, &lc_);
-    sort_rays_ = lc_.trav_dyn && !lc_.bvh_in_smem;                          // scenes traversed out of L2 by the dynamic-fetch kernels; B200PT_SORT=0|1 overrides
+    // Measured (profiles/r02_variants.txt): feeding k_extend_dyn rays sorted by (origin cell, direction octant) does not shorten it (BreakfastRoom bounce 1..3:
+    // 1283 / 644 / 310 us unsorted, 1335 / 586 / 319 us sorted) -- incoherent traversal is bound by node visits per ray, not by cache misses -- while the sort
+    // and the scattered state reads it causes cost 30-45 %.  OPT-IN: B200PT_SORT=1.
+    sort_rays_ = false;
     if (const char *e = getenv("B200PT_SORT")) sort_rays_ = atoi(e) != 0 && lc_.trav_dyn;
     if (q != 0) throw CudaError{ B200PT_ERR_CUDA, "query_launch_cfg failed" };
 }
