@@ -391,16 +391,19 @@ void Engine::free_wave() {
 }
 static const uint32_t kMaxDispatchTable = 1u << 16;
 void Engine::ensure_wave(size_t cap) {
-    if (cap <= wave_cap_) return;
+    if (cap <= wave_cap_ && (!sort_rays_ || d_order_ != nullptr)) return;
+    cap = std::max(cap, wave_cap_);
     free_wave();
     auto a4 = [&](float4 *&p) { CK(cudaMalloc(&p, cap * sizeof(float4))); };
     for (auto &p : ps_) { a4(p.org_pdf); a4(p.dir_rng); a4(p.thr_depth); a4(p.rad_slot); a4(p.medium); CK(cudaMalloc(&p.medium_g, cap * sizeof(float))); CK(cudaMalloc(&p.vol_depth, cap * sizeof(uint32_t))); }
     a4(so_.hit); a4(so_.bxdf_pdf); a4(so_.e0); a4(so_.sky_o); a4(so_.sky_d); a4(so_.sky_c); a4(so_.lit_o); a4(so_.lit_d); a4(so_.lit_c);
     a4(d_sample_buf_);
     CK(cudaMalloc(&d_rng_carry_, cap * sizeof(uint32_t)));
-    CK(cudaMalloc(&d_sort_key_rank_, cap * sizeof(uint2))); CK(cudaMalloc(&d_order_, cap * sizeof(uint32_t)));
-    CK(cudaMalloc(&d_sort_hist_, SORT_BINS * sizeof(uint32_t))); CK(cudaMalloc(&d_sort_offs_, SORT_BINS * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(d_sort_hist_, 0, SORT_BINS * sizeof(uint32_t), stream_));
+    if (sort_rays_) {                                                        // opt-in ray sort (B200PT_SORT=1): 12 B per path + two bin tables
+        CK(cudaMalloc(&d_sort_key_rank_, cap * sizeof(uint2))); CK(cudaMalloc(&d_order_, cap * sizeof(uint32_t)));
+        CK(cudaMalloc(&d_sort_hist_, SORT_BINS * sizeof(uint32_t))); CK(cudaMalloc(&d_sort_offs_, SORT_BINS * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(d_sort_hist_, 0, SORT_BINS * sizeof(uint32_t), stream_));
+    }
     for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_q_hit_[i], (size_t)MC_COUNT * cap * sizeof(uint32_t))); CK(cudaMalloc(&d_q_miss_[i], cap * sizeof(uint32_t))); }   // one hit queue per material class, ping-pong for the fused bounce kernel
     for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); CK(cudaMallocHost(&h_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); }
     wave_cap_ = cap;
@@ -437,7 +440,18 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     const uint32_t P = (S == 1) ? W_ * local_rows_ : ((W_ + S - 1) / S) * ((H_ + S - 1) / S);
     if (P == 0) { dispatch_count_ += todo; frame_count_ = (uint32_t)(dispatch_count_ / S2); samples_accumulated_ = frame_count_ * cfg_.SamplesPerFrame; return samples_accumulated_ >= cfg_.MaxSamplesAccumulated; }
     uint32_t F = cfg_.FramesInFlight;
-    if (F == 0) { const uint64_t target = 16ull << 20; F = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, target / P)); }
+    if (F == 0) {
+        // Auto wave size: up to 128 M paths (~48 GB of wavefront state at ~380 B per path; capped to a quarter of the free HBM).  Late bounces of a wave are bound by the
+        // latency chain of their longest rays (a ~150-200 us floor per traversal launch on BreakfastRoom, profiles/r02_variants.txt), so the wave must be large
+        // enough to amortise it: measured 16 M -> 32 M -> 64 M paths: BreakfastRoom 1385 -> 1593 -> 1727 Mpaths/s, glass 929 -> 991 -> 1002, Cornell 3415 -> 3535 -> 3590.
+        uint64_t target = 128ull << 20;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const uint64_t have = (uint64_t)wave_cap_ * 400ull;                                   // what this engine already holds counts as available
+            target = std::min<uint64_t>(target, std::max<uint64_t>(1ull << 20, ((uint64_t)free_b + have) / 4ull / 400ull));
+        }
+        F = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(256, target / P));
+    }
     F = std::min(F, todo);
     if ((size_t)F * P > wave_cap_) { CK(cudaStreamSynchronize(stream_)); }
     ensure_wave((size_t)F * P);
@@ -496,7 +510,7 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                     const uint32_t par = k & 1u;
                     const Queues qc{ d_q_miss_[qsel[par]], d_q_hit_[qsel[par]], qcap }, qn{ d_q_miss_[qsel[par ^ 1u]], d_q_hit_[qsel[par ^ 1u]], qcap };
                     if (n_vol) { launch_volume_decide(lc_, ds_, pst[cur], so_, d_counts_, par, stream_); launches++; }
-                    const bool sorted = sort_rays_ && k >= 1;            // camera rays are pixel-coherent already
+                    const bool sorted = sort_rays_ && d_order_ != nullptr && k >= 1;   // camera rays are pixel-coherent already
                     if (sorted) { launch_ray_sort(lc_, ds_, pst[cur], d_counts_, par, d_sort_key_rank_, d_sort_hist_, d_sort_offs_, d_order_, stream_); launches += 3; }
                     if (fuse != 2 || k == 0) { launch_extend(lc_, ds_, pst[cur], hitb[par], d_counts_, par, qc, d_ctr_, k == 0, sorted ? d_order_ : nullptr, stream_); launches++; } mark(1);
                     launches += launch_shade(lc_, ds_, dc, pst[cur], pst[cur ^ 1], so_, hitb[par], hitb[par ^ 1u], d_counts_, par, qc, qn, d_sample_buf_, d_rng_carry_, d_ctr_,
