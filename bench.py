@@ -455,6 +455,13 @@ def main():
         if world == 1:
             T.post_process(); T.get_ldr(ldr_host)   # bloom + tonemap + RGBA8 read-back (image-output path)
     e2e_steps = max(2, min(args.steps, 4))
+    if os.environ.get("B200PT_BENCH_E2E_BREAKDOWN"):   # where does an end-to-end step spend its host time?  (stderr, not part of the JSON line)
+        def tm(label, fn):
+            t = time.perf_counter(); fn(); torch.cuda.synchronize(); sys.stderr.write(f"[e2e] {label}: {(time.perf_counter() - t) * 1e3:.2f} ms\n")
+        for _ in range(2):
+            tm("set_config", lambda: T.set_config(cfg)); tm("set_partition", lambda: T.set_partition(rank, world, BAND_ROWS))
+            tm("path_trace", lambda: T.path_trace(F, BASE_SEED)); tm("gather", gather); tm("get_hdr", lambda: T.get_hdr(hdr_host))
+            if world == 1: tm("post_process", T.post_process); tm("get_ldr", lambda: T.get_ldr(ldr_host))
     e2e_step(); barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps): e2e_step()

@@ -31,8 +31,11 @@ Engine::Engine(int device) : device_(device) {
     for (int i = 0; i < 4; i++) view_inv_[i * 5] = proj_inv_[i * 5] = 1.0f;
     CK(cudaMalloc(&d_ctr_, sizeof(WaveCounters)));
     CK(cudaMemset(d_ctr_, 0, sizeof(WaveCounters)));
-    CK(cudaMalloc(&d_counts_, CTRL_WORDS * sizeof(uint32_t)));
-    CK(cudaMallocHost(&h_count_, 4 * sizeof(uint32_t)));
+    for (int c = 0; c < 2; c++) {
+        CK(cudaMalloc(&wb_[c].counts, CTRL_WORDS * sizeof(uint32_t))); CK(cudaMallocHost(&wb_[c].h_count, 4 * sizeof(uint32_t)));
+        CK(cudaStreamCreateWithFlags(&aux_stream_[c], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&resolved_ev_[c], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming));
     b200pt_default_atmosphere(&atmosphere_);
     memset(&last_, 0, sizeof last_);
 }
@@ -42,8 +45,13 @@ Engine::~Engine() {
     if (stream_) cudaStreamSynchronize(stream_);
     free_scene(); free_wave(); free_post();
     dfree(d_env_); dfree(d_alias_); dfree(d_env_row_cos_); for (auto &l : d_luts_) dfree(l);
-    dfree(d_image_); dfree(d_ctr_); dfree(d_counts_); dfree(d_volumes_); dfree(d_tri_class_);
-    if (h_count_) cudaFreeHost(h_count_);
+    dfree(d_image_); dfree(d_ctr_); dfree(d_volumes_); dfree(d_tri_class_);
+    for (int c = 0; c < 2; c++) {
+        dfree(wb_[c].counts); if (wb_[c].h_count) cudaFreeHost(wb_[c].h_count);
+        if (aux_stream_[c]) { cudaStreamSynchronize(aux_stream_[c]); cudaStreamDestroy(aux_stream_[c]); }
+        if (resolved_ev_[c]) cudaEventDestroy(resolved_ev_[c]);
+    }
+    if (fork_ev_) cudaEventDestroy(fork_ev_);
     if (ev_[0]) cudaEventDestroy(ev_[0]); if (ev_[1]) cudaEventDestroy(ev_[1]);
     for (auto &e : prof_ev_) cudaEventDestroy(e);
     if (table_ev_[0]) cudaEventDestroy(table_ev_[0]); if (table_ev_[1]) cudaEventDestroy(table_ev_[1]);
@@ -382,29 +390,41 @@ void Engine::ensure_image() {
 }
 
 void Engine::free_wave() {
-    for (auto &p : ps_) { dfree(p.org_pdf); dfree(p.dir_rng); dfree(p.thr_depth); dfree(p.rad_slot); dfree(p.medium); dfree(p.medium_g); dfree(p.vol_depth); }
-    dfree(so_.hit); dfree(so_.bxdf_pdf); dfree(so_.e0); dfree(so_.sky_o); dfree(so_.sky_d); dfree(so_.sky_c); dfree(so_.lit_o); dfree(so_.lit_d); dfree(so_.lit_c);
+    for (auto &B : wb_) {
+        for (auto &p : B.ps) { dfree(p.org_pdf); dfree(p.dir_rng); dfree(p.thr_depth); dfree(p.rad_slot); dfree(p.medium); dfree(p.medium_g); dfree(p.vol_depth); }
+        dfree(B.so.hit); dfree(B.so.bxdf_pdf); dfree(B.so.e0); dfree(B.so.sky_o); dfree(B.so.sky_d); dfree(B.so.sky_c); dfree(B.so.lit_o); dfree(B.so.lit_d); dfree(B.so.lit_c);
+        dfree(B.sample_buf); dfree(B.rng_carry); dfree(B.q_hit[0]); dfree(B.q_hit[1]); dfree(B.q_miss[0]); dfree(B.q_miss[1]);
+        B.cap = 0;
+    }
     dfree(d_sort_key_rank_); dfree(d_sort_hist_); dfree(d_sort_offs_); dfree(d_order_);
-    dfree(d_sample_buf_); dfree(d_rng_carry_); dfree(d_q_hit_[0]); dfree(d_q_hit_[1]); dfree(d_q_miss_[0]); dfree(d_q_miss_[1]); dfree(d_disp_[0]); dfree(d_disp_[1]);
+    dfree(d_disp_[0]); dfree(d_disp_[1]);
     for (auto &hp : h_disp_) if (hp) { cudaFreeHost(hp); hp = nullptr; }
     wave_cap_ = 0;
 }
 static const uint32_t kMaxDispatchTable = 1u << 16;
-void Engine::ensure_wave(size_t cap) {
-    if (cap <= wave_cap_ && (!sort_rays_ || d_order_ != nullptr)) return;
+void Engine::ensure_wave(size_t cap, int contexts) {
+    bool ok = cap <= wave_cap_ && (!sort_rays_ || d_order_ != nullptr);
+    for (int c = 0; c < contexts; c++) ok = ok && wb_[c].cap >= cap;
+    if (ok) return;
+    for (auto &st : aux_stream_) CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(stream_));
     cap = std::max(cap, wave_cap_);
     free_wave();
     auto a4 = [&](float4 *&p) { CK(cudaMalloc(&p, cap * sizeof(float4))); };
-    for (auto &p : ps_) { a4(p.org_pdf); a4(p.dir_rng); a4(p.thr_depth); a4(p.rad_slot); a4(p.medium); CK(cudaMalloc(&p.medium_g, cap * sizeof(float))); CK(cudaMalloc(&p.vol_depth, cap * sizeof(uint32_t))); }
-    a4(so_.hit); a4(so_.bxdf_pdf); a4(so_.e0); a4(so_.sky_o); a4(so_.sky_d); a4(so_.sky_c); a4(so_.lit_o); a4(so_.lit_d); a4(so_.lit_c);
-    a4(d_sample_buf_);
-    CK(cudaMalloc(&d_rng_carry_, cap * sizeof(uint32_t)));
-    if (sort_rays_) {                                                        // opt-in ray sort (B200PT_SORT=1): 12 B per path + two bin tables
+    for (int c = 0; c < contexts; c++) {
+        WaveBuf &B = wb_[c];
+        for (auto &p : B.ps) { a4(p.org_pdf); a4(p.dir_rng); a4(p.thr_depth); a4(p.rad_slot); a4(p.medium); CK(cudaMalloc(&p.medium_g, cap * sizeof(float))); CK(cudaMalloc(&p.vol_depth, cap * sizeof(uint32_t))); }
+        a4(B.so.hit); a4(B.so.bxdf_pdf); a4(B.so.e0); a4(B.so.sky_o); a4(B.so.sky_d); a4(B.so.sky_c); a4(B.so.lit_o); a4(B.so.lit_d); a4(B.so.lit_c);
+        a4(B.sample_buf);
+        CK(cudaMalloc(&B.rng_carry, cap * sizeof(uint32_t)));
+        for (int i = 0; i < 2; i++) { CK(cudaMalloc(&B.q_hit[i], (size_t)MC_COUNT * cap * sizeof(uint32_t))); CK(cudaMalloc(&B.q_miss[i], cap * sizeof(uint32_t))); }   // one hit queue per material class, ping-pong for the fused bounce kernel
+        B.cap = cap;
+    }
+    if (sort_rays_) {                                                        // opt-in ray sort (B200PT_SORT=1, single context): 12 B per path + two bin tables
         CK(cudaMalloc(&d_sort_key_rank_, cap * sizeof(uint2))); CK(cudaMalloc(&d_order_, cap * sizeof(uint32_t)));
         CK(cudaMalloc(&d_sort_hist_, SORT_BINS * sizeof(uint32_t))); CK(cudaMalloc(&d_sort_offs_, SORT_BINS * sizeof(uint32_t)));
         CK(cudaMemsetAsync(d_sort_hist_, 0, SORT_BINS * sizeof(uint32_t), stream_));
     }
-    for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_q_hit_[i], (size_t)MC_COUNT * cap * sizeof(uint32_t))); CK(cudaMalloc(&d_q_miss_[i], cap * sizeof(uint32_t))); }   // one hit queue per material class, ping-pong for the fused bounce kernel
     for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); CK(cudaMallocHost(&h_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); }
     wave_cap_ = cap;
 }
@@ -439,22 +459,27 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
 
     const uint32_t P = (S == 1) ? W_ * local_rows_ : ((W_ + S - 1) / S) * ((H_ + S - 1) / S);
     if (P == 0) { dispatch_count_ += todo; frame_count_ = (uint32_t)(dispatch_count_ / S2); samples_accumulated_ = frame_count_ * cfg_.SamplesPerFrame; return samples_accumulated_ >= cfg_.MaxSamplesAccumulated; }
+    // Two waves in flight (two contexts, two internal streams): the late bounces of a wave are bound by the latency chain of their longest rays (a ~150-200 us floor
+    // per traversal launch on BreakfastRoom, profiles/r02_variants.txt), during which most SMs idle -- the next wave's full-machine bounces fill them.
+    // B200PT_OVERLAP=0 runs one wave at a time (also used while profiling per-kernel times and with the opt-in ray sort).
+    bool overlap = !profiling_ && !sort_rays_;
+    if (const char *e = getenv("B200PT_OVERLAP")) { if (atoi(e) == 0) overlap = false; }
     uint32_t F = cfg_.FramesInFlight;
     if (F == 0) {
-        // Auto wave size: up to 128 M paths (~48 GB of wavefront state at ~380 B per path; capped to a quarter of the free HBM).  Late bounces of a wave are bound by the
-        // latency chain of their longest rays (a ~150-200 us floor per traversal launch on BreakfastRoom, profiles/r02_variants.txt), so the wave must be large
-        // enough to amortise it: measured 16 M -> 32 M -> 64 M paths: BreakfastRoom 1385 -> 1593 -> 1727 Mpaths/s, glass 929 -> 991 -> 1002, Cornell 3415 -> 3535 -> 3590.
-        uint64_t target = 128ull << 20;
+        // Auto wave size: up to 64 M paths per context (~24 GB of wavefront state at ~380 B per path; all contexts capped to a quarter of the free HBM): large enough
+        // to amortise the floors above.  Measured 16 M -> 32 M -> 64 M paths: BreakfastRoom 1385 -> 1593 -> 1727 Mpaths/s, glass 929 -> 991 -> 1002, Cornell 3415 -> 3535 -> 3590.
+        uint64_t target = 64ull << 20;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const uint64_t have = (uint64_t)wave_cap_ * 400ull;                                   // what this engine already holds counts as available
-            target = std::min<uint64_t>(target, std::max<uint64_t>(1ull << 20, ((uint64_t)free_b + have) / 4ull / 400ull));
+            uint64_t have = 0; for (const auto &B : wb_) have += (uint64_t)B.cap * 400ull;       // what this engine already holds counts as available
+            target = std::min<uint64_t>(target, std::max<uint64_t>(1ull << 20, ((uint64_t)free_b + have) / 4ull / 400ull / (overlap ? 2ull : 1ull)));
         }
         F = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(256, target / P));
     }
     F = std::min(F, todo);
-    if ((size_t)F * P > wave_cap_) { CK(cudaStreamSynchronize(stream_)); }
-    ensure_wave((size_t)F * P);
+    const uint32_t n_waves = (todo + F - 1) / F;
+    const int n_ctx = (overlap && n_waves >= 2) ? 2 : 1;
+    ensure_wave((size_t)F * P, n_ctx);
     // double-buffered dispatch tables: the host copy is reusable once ITS upload (two calls ago) has executed
     table_sel_ ^= 1;
     DevDispatch *h_disp = h_disp_[table_sel_], *d_disp = d_disp_[table_sel_];
@@ -472,8 +497,6 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     const DevConfig dc = make_dev_config();
 
     const uint32_t n_vol = ds_.n_volumes;
-    PathState pst[2] = { ps_[0], ps_[1] };                    // payload.VolumeDepth travels only while the scene has volumes
-    if (!n_vol) { pst[0].vol_depth = nullptr; pst[1].vol_depth = nullptr; }
     bool medium = false;                                      // can a path random-walk inside a mesh without gaining Depth?
     // Conservative: the device-side metallic value is Metallic * texel, so the constant factor alone cannot rule refraction out, and a negative
     // density (not validated by the reference either) scatters on every segment.  A false positive only costs a 4-byte read-back per 16 bounces.
@@ -485,9 +508,9 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     const uint32_t cmask = n_vol ? (class_mask_ | (1u << MC_GENERAL)) : class_mask_;   // volume events ride in the general queue
     const uint32_t qcap = (uint32_t)wave_cap_;
     const int qsel[2] = { 0, fuse == 2 ? 1 : 0 };
-    float4 *const hitb[2] = { so_.hit, fuse == 2 ? so_.bxdf_pdf : so_.hit };
 
     CK(cudaEventRecord(ev_[0], stream_));
+    if (n_ctx == 2) { CK(cudaEventRecord(fork_ev_, stream_)); for (auto &st : aux_stream_) CK(cudaStreamWaitEvent(st, fork_ev_, 0)); }
     uint64_t launches = 0; uint32_t waves = 0, bounces_total = 0;
     std::vector<int> prof_kind; size_t prof_n = 0;            // kind: 0 raygen 1 extend 2 shade 3 connect 4 resolve
     auto mark = [&](int kind) {
@@ -496,10 +519,17 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
         CK(cudaEventRecord(prof_ev_[prof_n++], stream_)); prof_kind.push_back(kind);
     };
     mark(-1);
-    for (uint32_t w0 = 0; w0 < todo; w0 += F) {
+    uint32_t wi = 0;
+    for (uint32_t w0 = 0; w0 < todo; w0 += F, wi++) {
         const uint32_t nd = std::min(F, todo - w0);
+        const int ctx = n_ctx == 2 ? (int)(wi & 1u) : 0;
+        WaveBuf &B = wb_[ctx];
+        cudaStream_t st = n_ctx == 2 ? aux_stream_[ctx] : stream_;
+        PathState pst[2] = { B.ps[0], B.ps[1] };              // payload.VolumeDepth travels only while the scene has volumes
+        if (!n_vol) { pst[0].vol_depth = nullptr; pst[1].vol_depth = nullptr; }
+        float4 *const hitb[2] = { B.so.hit, fuse == 2 ? B.so.bxdf_pdf : B.so.hit };
         for (uint32_t s = 0; s < cfg_.SamplesPerFrame; s++) {
-            launch_raygen(lc_, dc, d_disp + w0, nd, P, s == 0 ? 1u : 0u, d_rng_carry_, pst[0], d_sample_buf_, d_counts_, d_ctr_, stream_);
+            launch_raygen(lc_, dc, d_disp + w0, nd, P, s == 0 ? 1u : 0u, B.rng_carry, pst[0], B.sample_buf, B.counts, d_ctr_, st);
             launches++; mark(0);
             int cur = 0; uint32_t k = 0;
             for (;;) {
@@ -508,27 +538,31 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                 if (chunk == 0) break;
                 for (uint32_t b = 0; b < chunk; b++, k++) {
                     const uint32_t par = k & 1u;
-                    const Queues qc{ d_q_miss_[qsel[par]], d_q_hit_[qsel[par]], qcap }, qn{ d_q_miss_[qsel[par ^ 1u]], d_q_hit_[qsel[par ^ 1u]], qcap };
-                    if (n_vol) { launch_volume_decide(lc_, ds_, pst[cur], so_, d_counts_, par, stream_); launches++; }
+                    const Queues qc{ B.q_miss[qsel[par]], B.q_hit[qsel[par]], qcap }, qn{ B.q_miss[qsel[par ^ 1u]], B.q_hit[qsel[par ^ 1u]], qcap };
+                    if (n_vol) { launch_volume_decide(lc_, ds_, pst[cur], B.so, B.counts, par, st); launches++; }
                     const bool sorted = sort_rays_ && d_order_ != nullptr && k >= 1;   // camera rays are pixel-coherent already
-                    if (sorted) { launch_ray_sort(lc_, ds_, pst[cur], d_counts_, par, d_sort_key_rank_, d_sort_hist_, d_sort_offs_, d_order_, stream_); launches += 3; }
-                    if (fuse != 2 || k == 0) { launch_extend(lc_, ds_, pst[cur], hitb[par], d_counts_, par, qc, d_ctr_, k == 0, sorted ? d_order_ : nullptr, stream_); launches++; } mark(1);
-                    launches += launch_shade(lc_, ds_, dc, pst[cur], pst[cur ^ 1], so_, hitb[par], hitb[par ^ 1u], d_counts_, par, qc, qn, d_sample_buf_, d_rng_carry_, d_ctr_,
-                                             fuse, cmask, stream_); mark(2);
-                    if (!fuse) { launch_connect(lc_, ds_, dc, pst[cur], pst[cur ^ 1], so_, d_counts_, par, qc, d_sample_buf_, d_rng_carry_, d_ctr_, stream_); launches += lc_.trav_dyn ? 2 : 1; } mark(3);
+                    if (sorted) { launch_ray_sort(lc_, ds_, pst[cur], B.counts, par, d_sort_key_rank_, d_sort_hist_, d_sort_offs_, d_order_, st); launches += 3; }
+                    if (fuse != 2 || k == 0) { launch_extend(lc_, ds_, pst[cur], hitb[par], B.counts, par, qc, d_ctr_, k == 0, sorted ? d_order_ : nullptr, st); launches++; } mark(1);
+                    launches += launch_shade(lc_, ds_, dc, pst[cur], pst[cur ^ 1], B.so, hitb[par], hitb[par ^ 1u], B.counts, par, qc, qn, B.sample_buf, B.rng_carry, d_ctr_,
+                                             fuse, cmask, st); mark(2);
+                    if (!fuse) { launch_connect(lc_, ds_, dc, pst[cur], pst[cur ^ 1], B.so, B.counts, par, qc, B.sample_buf, B.rng_carry, d_ctr_, st); launches += lc_.trav_dyn ? 2 : 1; } mark(3);
                     cur ^= 1;
                 }
                 if (!medium && k >= cfg_.MaxDepth) break;    // every surviving path has Depth >= MaxDepth: provably empty
-                CK(cudaMemcpyAsync(h_count_, d_counts_ + (k & 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-                CK(cudaStreamSynchronize(stream_));
-                if (h_count_[0] == 0) break;
+                CK(cudaMemcpyAsync(B.h_count, B.counts + (k & 1u), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (B.h_count[0] == 0) break;
                 if (k > (1u << 20)) break;                    // runaway guard
             }
             bounces_total += k;
         }
-        launch_resolve(lc_, dc, d_disp + w0, nd, P, d_sample_buf_, d_image_, stream_);
+        // the running mean folds the waves in dispatch order: wave wi's resolve waits for wave wi-1's (the other stream)
+        if (n_ctx == 2 && wi > 0) CK(cudaStreamWaitEvent(st, resolved_ev_[ctx ^ 1], 0));
+        launch_resolve(lc_, dc, d_disp + w0, nd, P, B.sample_buf, d_image_, st);
+        if (n_ctx == 2) CK(cudaEventRecord(resolved_ev_[ctx], st));
         launches++; waves++; mark(4);
     }
+    if (n_ctx == 2) for (int c = 0; c < 2; c++) CK(cudaStreamWaitEvent(stream_, resolved_ev_[c], 0));   // join: everything after this call sees the finished image
     CK(cudaEventRecord(ev_[1], stream_));
     CK(cudaGetLastError());
     dispatch_count_ += todo;

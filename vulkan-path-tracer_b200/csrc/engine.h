@@ -82,7 +82,7 @@ private:
     void upload_volumes();
     DevMaterial make_dev_material(const b200pt_material &m) const;
     void ensure_image();
-    void ensure_wave(size_t capacity);
+    void ensure_wave(size_t capacity, int contexts);
     void free_wave();
     void ensure_post();
     void free_post();
@@ -125,11 +125,19 @@ private:
     std::vector<float4 *> d_mips_; std::vector<uint32_t> mip_wh_; uchar4 *d_ldr_ = nullptr; uint32_t post_w_ = 0, post_h_ = 0;
     bool keep_bloom_ = false, bloom_valid_ = false;   // fused post chain: mip 0 is written only once get_bloom() has been used
 
-    // wave buffers
-    size_t wave_cap_ = 0;
-    PathState ps_[2]{}; ShadeOut so_{};
-    float4 *d_sample_buf_ = nullptr; uint32_t *d_rng_carry_ = nullptr; uint32_t *d_q_hit_[2] = { nullptr, nullptr }, *d_q_miss_[2] = { nullptr, nullptr }; uint32_t *d_counts_ = nullptr; DevDispatch *d_disp_[2] = { nullptr, nullptr };
-    DevDispatch *h_disp_[2] = { nullptr, nullptr }; uint32_t *h_count_ = nullptr;
+    // wave buffers: one context per wave in flight.  Two contexts on two internal streams let the latency-bound tail of wave w (late bounces: few, long rays)
+    // overlap the full-machine head of wave w+1; k_resolve runs in dispatch order (events), so the image does not depend on it.
+    struct WaveBuf {
+        PathState ps[2]{}; ShadeOut so{};
+        float4 *sample_buf = nullptr; uint32_t *rng_carry = nullptr; uint32_t *q_hit[2] = { nullptr, nullptr }, *q_miss[2] = { nullptr, nullptr };
+        uint32_t *counts = nullptr, *h_count = nullptr;
+        size_t cap = 0;
+    };
+    WaveBuf wb_[2];
+    cudaStream_t aux_stream_[2] = { nullptr, nullptr }; cudaEvent_t resolved_ev_[2] = { nullptr, nullptr }, fork_ev_ = nullptr;
+    size_t wave_cap_ = 0;                           // capacity (paths) of every allocated context
+    DevDispatch *d_disp_[2] = { nullptr, nullptr };
+    DevDispatch *h_disp_[2] = { nullptr, nullptr };
     WaveCounters *d_ctr_ = nullptr;
     uint2 *d_sort_key_rank_ = nullptr; uint32_t *d_sort_hist_ = nullptr, *d_sort_offs_ = nullptr, *d_order_ = nullptr;   // ray sort of incoherent bounces (launch_ray_sort)
     bool sort_rays_ = false;
