@@ -410,7 +410,7 @@ def main():
         dist.gather(band, gathered, dst=0)
 
     def step():
-        T.path_trace(F, BASE_SEED)
+        T.path_trace(F, BASE_SEED)               # asynchronous: waves of consecutive steps overlap on the handle's internal streams
         gather()
 
     def barrier():
@@ -427,6 +427,7 @@ def main():
     t0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps): step()
+    T.flush()                                    # the end event must sit behind every launched wave (device-side wait, no host sync)
     ev1.record(stream)
     barrier()
     wall = time.perf_counter() - t0

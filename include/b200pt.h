@@ -193,6 +193,12 @@ uint32_t b200pt_partition_local_row_count(uint32_t height, uint32_t rank, uint32
 int32_t b200pt_path_trace(b200pt_handle h, uint32_t dispatches, uint32_t base_seed, int32_t *done_out);
 int32_t b200pt_samples_accumulated(b200pt_handle h, uint32_t *out);         /* GetSamplesAccumulated */
 int32_t b200pt_synchronize(b200pt_handle h);
+/* b200pt_path_trace is ASYNCHRONOUS: it returns once the waves are enqueued (two waves are in flight on the handle's internal streams so that the
+ * latency-bound tail of one overlaps the head of the next, also across calls).  Every later call on the handle that touches the image (get_hdr,
+ * post_process, set_hdr, checkpoints, ...) is ordered behind them automatically.  Work the CALLER enqueues on the handle's stream -- its own kernels
+ * on b200pt_hdr_device_ptr, a timing event -- needs b200pt_flush first: it makes the stream wait (on the device, no host synchronisation) for
+ * everything launched so far.  b200pt_synchronize additionally blocks the host. */
+int32_t b200pt_flush(b200pt_handle h);
 /* Run all work of this handle on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the handle's own
  * stream).  Lets a host framework order its collectives / events against the render without extra synchronisation. */
 int32_t b200pt_set_stream(b200pt_handle h, void *cuda_stream);

@@ -465,6 +465,8 @@ class PathTracer:
 
     def set_bloom(self, threshold=2.0, strength=1.0, mips=10, falloff=5.0): self._ck(self.L.b200pt_post_set_bloom(self.h, C.byref(Bloom(threshold, strength, mips, falloff))))
 
+    def flush(self): self._ck(self.L.b200pt_flush(self.h))
+
     def post_process(self): self._ck(self.L.b200pt_post_process(self.h))
 
     def get_ldr(self, out=None):

@@ -164,6 +164,7 @@ uint32_t b200pt_partition_local_row_count(uint32_t H, uint32_t r, uint32_t w, ui
 int32_t b200pt_path_trace(b200pt_handle h, uint32_t dispatches, uint32_t seed, int32_t *done) {
     return guard(h, [&](Engine &e) { bool d = e.path_trace(dispatches, seed); if (done) *done = d ? 1 : 0; });
 }
+int32_t b200pt_flush(b200pt_handle h) { return guard(h, [&](Engine &e) { e.flush(); }); }
 int32_t b200pt_samples_accumulated(b200pt_handle h, uint32_t *out) { if (!out) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { *out = e.samples_accumulated(); }); }
 int32_t b200pt_synchronize(b200pt_handle h) { return guard(h, [&](Engine &e) { e.synchronize(); }); }
 int32_t b200pt_set_stream(b200pt_handle h, void *s) { return guard(h, [&](Engine &e) { e.set_stream((cudaStream_t)s); }); }

@@ -15,6 +15,7 @@ void Engine::check(cudaError_t e, const char *what) const {
 }
 #define CK(x) check((x), #x)
 
+static const uint32_t kMaxDispatchTable = 1u << 16;
 template <class T> static void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
 
 Engine::Engine(int device) : device_(device) {
@@ -24,7 +25,6 @@ Engine::Engine(int device) : device_(device) {
     if (device < 0 || device >= n) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "device ordinal out of range" };
     CK(cudaSetDevice(device_));
     CK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking)); stream_ = own_stream_;
-    CK(cudaEventCreateWithFlags(&table_ev_[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&table_ev_[1], cudaEventDisableTiming));
     CK(cudaEventCreate(&ev_[0])); CK(cudaEventCreate(&ev_[1]));
     b200pt_default_config(&cfg_);
     memset(view_inv_, 0, sizeof view_inv_); memset(proj_inv_, 0, sizeof proj_inv_);
@@ -34,14 +34,17 @@ Engine::Engine(int device) : device_(device) {
     for (int c = 0; c < 2; c++) {
         CK(cudaMalloc(&wb_[c].counts, CTRL_WORDS * sizeof(uint32_t))); CK(cudaMallocHost(&wb_[c].h_count, 4 * sizeof(uint32_t)));
         CK(cudaStreamCreateWithFlags(&aux_stream_[c], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&resolved_ev_[c], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&wb_[c].disp_ev, cudaEventDisableTiming));
+        CK(cudaMalloc(&wb_[c].d_disp, kMaxDispatchTable * sizeof(DevDispatch))); CK(cudaMallocHost(&wb_[c].h_disp, kMaxDispatchTable * sizeof(DevDispatch)));
     }
-    CK(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&image_free_ev_, cudaEventDisableTiming));
     b200pt_default_atmosphere(&atmosphere_);
     memset(&last_, 0, sizeof last_);
 }
 
 Engine::~Engine() {
     cudaSetDevice(device_);
+    for (auto &st : aux_stream_) if (st) cudaStreamSynchronize(st);
     if (stream_) cudaStreamSynchronize(stream_);
     free_scene(); free_wave(); free_post();
     dfree(d_env_); dfree(d_alias_); dfree(d_env_row_cos_); for (auto &l : d_luts_) dfree(l);
@@ -50,12 +53,22 @@ Engine::~Engine() {
         dfree(wb_[c].counts); if (wb_[c].h_count) cudaFreeHost(wb_[c].h_count);
         if (aux_stream_[c]) { cudaStreamSynchronize(aux_stream_[c]); cudaStreamDestroy(aux_stream_[c]); }
         if (resolved_ev_[c]) cudaEventDestroy(resolved_ev_[c]);
+        if (wb_[c].disp_ev) cudaEventDestroy(wb_[c].disp_ev);
+        dfree(wb_[c].d_disp); if (wb_[c].h_disp) cudaFreeHost(wb_[c].h_disp);
     }
-    if (fork_ev_) cudaEventDestroy(fork_ev_);
+    if (image_free_ev_) cudaEventDestroy(image_free_ev_);
     if (ev_[0]) cudaEventDestroy(ev_[0]); if (ev_[1]) cudaEventDestroy(ev_[1]);
     for (auto &e : prof_ev_) cudaEventDestroy(e);
-    if (table_ev_[0]) cudaEventDestroy(table_ev_[0]); if (table_ev_[1]) cudaEventDestroy(table_ev_[1]);
     if (own_stream_) cudaStreamDestroy(own_stream_);
+}
+
+void Engine::sync_all() {
+    for (auto &st : aux_stream_) if (st) CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(stream_));
+}
+void Engine::join_waves() {
+    if (wave_seq_ == 0) return;
+    for (auto &e : resolved_ev_) CK(cudaStreamWaitEvent(stream_, e, 0));    // an event that was never recorded counts as complete
 }
 
 void Engine::free_scene() {
@@ -69,7 +82,7 @@ void Engine::free_scene() {
 // PathTracer::SetScene (PathTracer.cpp:158-676)
 void Engine::set_scene(HostScene &&scene) {
     CK(cudaSetDevice(device_));
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     free_scene();
     scene_ = std::move(scene);
     // capacity limits of the reference (PathTracer.h:192-195, asserts PathTracer.cpp:182-184)
@@ -273,7 +286,7 @@ void Engine::set_material(uint32_t idx, const b200pt_material &m) {
     if (idx >= scene_.materials.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "material index out of range" };
     const uint32_t tix[5] = { m.BaseColorTextureIndex, m.NormalTextureIndex, m.RoughnessTextureIndex, m.MetallicTextureIndex, m.EmissiveTextureIndex };
     for (uint32_t t : tix) if (t >= scene_.textures.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "texture index out of range" };
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     scene_.materials[idx] = m;
     { const DevMaterial dm = make_dev_material(m); CK(cudaMemcpy(d_materials_ + idx, &dm, sizeof dm, cudaMemcpyHostToDevice)); launch_prepare_materials(d_materials_, idx, 1, stream_); CK(cudaStreamSynchronize(stream_)); }
     rebuild_emissive();
@@ -289,7 +302,7 @@ static void check_volume(const b200pt_volume &v) {
 }
 void Engine::upload_volumes() {
     CK(cudaSetDevice(device_));
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     if (!d_volumes_) CK(cudaMalloc(&d_volumes_, B200PT_MAX_VOLUMES * sizeof(DevVolume)));
     std::vector<DevVolume> dv(volumes_.size());
     for (size_t i = 0; i < volumes_.size(); i++) {
@@ -328,7 +341,7 @@ void Engine::set_phase_function(uint32_t pf) {
 void Engine::set_env_map(uint32_t w, uint32_t h, const float *rgba) {
     CK(cudaSetDevice(device_));
     if (!w || !h || !rgba || (uint64_t)w * h > 0x7FFFFFFFull) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "bad environment map" };
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     std::vector<float> px(rgba, rgba + (size_t)w * h * 4);
     std::vector<uint2> alias((size_t)w * h);
     build_env_alias(px.data(), w, h, alias.data());
@@ -349,7 +362,7 @@ void Engine::set_env_map(uint32_t w, uint32_t h, const float *rgba) {
 void Engine::set_luts(const float *refl, const float *rout, const float *rin) {
     CK(cudaSetDevice(device_));
     if (!refl || !rout || !rin) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "null LUT" };
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     const size_t n[3] = { 64 * 64 * 32, 128 * 128 * 32, 128 * 128 * 32 }; const float *src[3] = { refl, rout, rin };
     for (int i = 0; i < 3; i++) { dfree(d_luts_[i]); CK(cudaMalloc(&d_luts_[i], n[i] * 4)); CK(cudaMemcpy(d_luts_[i], src[i], n[i] * 4, cudaMemcpyHostToDevice)); }
     ds_.lut_reflect = d_luts_[0]; ds_.lut_refract_out = d_luts_[1]; ds_.lut_refract_in = d_luts_[2];
@@ -370,7 +383,7 @@ void Engine::reset() { dispatch_count_ = 0; frame_count_ = 0; samples_accumulate
 void Engine::resize(uint32_t w, uint32_t h) {                                                  // PathTracer::ResizeImage
     if (!w || !h || w > 65535 || h > 65535) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "bad image size" };
     CK(cudaSetDevice(device_));
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     W_ = w; H_ = h; local_rows_ = partition_local_rows(H_, rank_, world_, band_);
     ensure_image(); reset();
 }
@@ -378,7 +391,7 @@ void Engine::set_partition(uint32_t rank, uint32_t world, uint32_t band) {
     if (!world || rank >= world || !band) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "bad partition" };
     if (world > 1 && cfg_.ScreenChunkCount > 1) throw CudaError{ B200PT_ERR_NOT_IMPLEMENTED, "ScreenChunkCount > 1 cannot be combined with a multi-GPU partition" };
     CK(cudaSetDevice(device_));
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     rank_ = rank; world_ = world; band_ = band;
     if (W_ && H_) { local_rows_ = partition_local_rows(H_, rank_, world_, band_); ensure_image(); }
     reset();
@@ -397,17 +410,13 @@ void Engine::free_wave() {
         B.cap = 0;
     }
     dfree(d_sort_key_rank_); dfree(d_sort_hist_); dfree(d_sort_offs_); dfree(d_order_);
-    dfree(d_disp_[0]); dfree(d_disp_[1]);
-    for (auto &hp : h_disp_) if (hp) { cudaFreeHost(hp); hp = nullptr; }
     wave_cap_ = 0;
 }
-static const uint32_t kMaxDispatchTable = 1u << 16;
 void Engine::ensure_wave(size_t cap, int contexts) {
     bool ok = cap <= wave_cap_ && (!sort_rays_ || d_order_ != nullptr);
     for (int c = 0; c < contexts; c++) ok = ok && wb_[c].cap >= cap;
     if (ok) return;
-    for (auto &st : aux_stream_) CK(cudaStreamSynchronize(st));
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     cap = std::max(cap, wave_cap_);
     free_wave();
     auto a4 = [&](float4 *&p) { CK(cudaMalloc(&p, cap * sizeof(float4))); };
@@ -425,7 +434,6 @@ void Engine::ensure_wave(size_t cap, int contexts) {
         CK(cudaMalloc(&d_sort_hist_, SORT_BINS * sizeof(uint32_t))); CK(cudaMalloc(&d_sort_offs_, SORT_BINS * sizeof(uint32_t)));
         CK(cudaMemsetAsync(d_sort_hist_, 0, SORT_BINS * sizeof(uint32_t), stream_));
     }
-    for (int i = 0; i < 2; i++) { CK(cudaMalloc(&d_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); CK(cudaMallocHost(&h_disp_[i], kMaxDispatchTable * sizeof(DevDispatch))); }
     wave_cap_ = cap;
 }
 
@@ -460,8 +468,13 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     const uint32_t P = (S == 1) ? W_ * local_rows_ : ((W_ + S - 1) / S) * ((H_ + S - 1) / S);
     if (P == 0) { dispatch_count_ += todo; frame_count_ = (uint32_t)(dispatch_count_ / S2); samples_accumulated_ = frame_count_ * cfg_.SamplesPerFrame; return samples_accumulated_ >= cfg_.MaxSamplesAccumulated; }
     // Two waves in flight (two contexts, two internal streams): the late bounces of a wave are bound by the latency chain of their longest rays (a ~150-200 us floor
-    // per traversal launch on BreakfastRoom, profiles/r02_variants.txt), during which most SMs idle -- the next wave's full-machine bounces fill them.
-    // B200PT_OVERLAP=0 runs one wave at a time (also used while profiling per-kernel times and with the opt-in ray sort).
+    // per traversal launch on BreakfastRoom, profiles/r02_variants.txt), during which most SMs idle -- the next wave's full-machine bounces fill them.  Waves are
+    // numbered across calls (wave_seq_): wave w runs in context w & 1 on internal stream w & 1 and its k_resolve waits for wave w - 1's, so the running mean folds
+    // the frames in dispatch order whatever overlaps.  The join with the caller's stream is LAZY: path_trace returns with the waves in flight, and whatever touches
+    // the image afterwards (get_hdr, post_process, set_hdr, checkpoints, ...) first makes the caller's stream wait for the resolves (join_waves); the next call's
+    // resolves in turn wait for what the caller enqueued on the image in between (image_free_ev_).  So consecutive path_trace calls -- the steps of a multi-GPU
+    // run, each followed by an NCCL gather of the bands -- overlap as well: the gather of step k runs beside the first bounces of step k + 1.
+    // B200PT_OVERLAP=0 runs one wave at a time on the caller's stream (also used while profiling per-kernel times and with the opt-in ray sort).
     bool overlap = !profiling_ && !sort_rays_;
     if (const char *e = getenv("B200PT_OVERLAP")) { if (atoi(e) == 0) overlap = false; }
     uint32_t F = cfg_.FramesInFlight;
@@ -477,24 +490,13 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
         F = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(256, target / P));
     }
     F = std::min(F, todo);
-    const uint32_t n_waves = (todo + F - 1) / F;
-    const int n_ctx = (overlap && n_waves >= 2) ? 2 : 1;
+    { const uint32_t n_waves = (todo + F - 1) / F; F = (todo + n_waves - 1) / n_waves; }          // equal waves: 128 frames at F = 123 become 64 + 64, not 123 + 5
+    const int n_ctx = overlap ? 2 : 1;
     ensure_wave((size_t)F * P, n_ctx);
-    // double-buffered dispatch tables: the host copy is reusable once ITS upload (two calls ago) has executed
-    table_sel_ ^= 1;
-    DevDispatch *h_disp = h_disp_[table_sel_], *d_disp = d_disp_[table_sel_];
-    CK(cudaEventSynchronize(table_ev_[table_sel_]));
-
-    for (uint32_t i = 0; i < todo; i++) {
-        const uint64_t d = dispatch_count_ + i;
-        h_disp[i].FrameCount = (uint32_t)(d / S2);
-        h_disp[i].Seed = [](uint32_t in) { uint32_t st = in * 747796405u + 2891336453u; uint32_t w = ((st >> ((st >> 28u) + 4u)) ^ st) * 277803737u; return (w >> 22u) ^ w; }(base_seed + (uint32_t)d);
-        h_disp[i].ChunkIndex = (uint32_t)(d % S2);
-        h_disp[i]._pad = 0;
-    }
-    CK(cudaMemcpyAsync(d_disp, h_disp, todo * sizeof(DevDispatch), cudaMemcpyHostToDevice, stream_));
-    CK(cudaEventRecord(table_ev_[table_sel_], stream_));
+    if (!overlap) join_waves();                               // single-stream mode runs on the caller's stream, behind whatever the internal streams still hold
+    else CK(cudaEventRecord(image_free_ev_, stream_));        // what the caller has enqueued on the image so far (gather copy, post chain, set_hdr) precedes this call's resolves
     const DevConfig dc = make_dev_config();
+    auto pcg = [](uint32_t in) { uint32_t st = in * 747796405u + 2891336453u; uint32_t w = ((st >> ((st >> 28u) + 4u)) ^ st) * 277803737u; return (w >> 22u) ^ w; };
 
     const uint32_t n_vol = ds_.n_volumes;
     bool medium = false;                                      // can a path random-walk inside a mesh without gaining Depth?
@@ -509,8 +511,6 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     const uint32_t qcap = (uint32_t)wave_cap_;
     const int qsel[2] = { 0, fuse == 2 ? 1 : 0 };
 
-    CK(cudaEventRecord(ev_[0], stream_));
-    if (n_ctx == 2) { CK(cudaEventRecord(fork_ev_, stream_)); for (auto &st : aux_stream_) CK(cudaStreamWaitEvent(st, fork_ev_, 0)); }
     uint64_t launches = 0; uint32_t waves = 0, bounces_total = 0;
     std::vector<int> prof_kind; size_t prof_n = 0;            // kind: 0 raygen 1 extend 2 shade 3 connect 4 resolve
     auto mark = [&](int kind) {
@@ -519,17 +519,26 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
         CK(cudaEventRecord(prof_ev_[prof_n++], stream_)); prof_kind.push_back(kind);
     };
     mark(-1);
-    uint32_t wi = 0;
-    for (uint32_t w0 = 0; w0 < todo; w0 += F, wi++) {
+    cudaStream_t last_st = stream_;
+    for (uint32_t w0 = 0; w0 < todo; w0 += F) {
         const uint32_t nd = std::min(F, todo - w0);
-        const int ctx = n_ctx == 2 ? (int)(wi & 1u) : 0;
+        const int ctx = overlap ? (int)(wave_seq_ & 1ull) : 0;
         WaveBuf &B = wb_[ctx];
-        cudaStream_t st = n_ctx == 2 ? aux_stream_[ctx] : stream_;
+        cudaStream_t st = overlap ? aux_stream_[ctx] : stream_;
+        if (w0 == 0) CK(cudaEventRecord(ev_[0], st));
+        // this wave's slice of the dispatch table (PathTracer.cpp:127-150: FrameCount, Seed = PCG(seed + dispatch), ChunkIndex) travels on the wave's own stream
+        CK(cudaEventSynchronize(B.disp_ev));                  // the pinned copy is reusable once ITS last upload has executed
+        for (uint32_t i = 0; i < nd; i++) {
+            const uint64_t d = dispatch_count_ + w0 + i;
+            B.h_disp[i].FrameCount = (uint32_t)(d / S2); B.h_disp[i].Seed = pcg(base_seed + (uint32_t)d); B.h_disp[i].ChunkIndex = (uint32_t)(d % S2); B.h_disp[i]._pad = 0;
+        }
+        CK(cudaMemcpyAsync(B.d_disp, B.h_disp, nd * sizeof(DevDispatch), cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(B.disp_ev, st));
         PathState pst[2] = { B.ps[0], B.ps[1] };              // payload.VolumeDepth travels only while the scene has volumes
         if (!n_vol) { pst[0].vol_depth = nullptr; pst[1].vol_depth = nullptr; }
         float4 *const hitb[2] = { B.so.hit, fuse == 2 ? B.so.bxdf_pdf : B.so.hit };
         for (uint32_t s = 0; s < cfg_.SamplesPerFrame; s++) {
-            launch_raygen(lc_, dc, d_disp + w0, nd, P, s == 0 ? 1u : 0u, B.rng_carry, pst[0], B.sample_buf, B.counts, d_ctr_, st);
+            launch_raygen(lc_, dc, B.d_disp, nd, P, s == 0 ? 1u : 0u, B.rng_carry, pst[0], B.sample_buf, B.counts, d_ctr_, st);
             launches++; mark(0);
             int cur = 0; uint32_t k = 0;
             for (;;) {
@@ -556,14 +565,19 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
             }
             bounces_total += k;
         }
-        // the running mean folds the waves in dispatch order: wave wi's resolve waits for wave wi-1's (the other stream)
-        if (n_ctx == 2 && wi > 0) CK(cudaStreamWaitEvent(st, resolved_ev_[ctx ^ 1], 0));
-        launch_resolve(lc_, dc, d_disp + w0, nd, P, B.sample_buf, d_image_, st);
-        if (n_ctx == 2) CK(cudaEventRecord(resolved_ev_[ctx], st));
+        // the running mean folds the waves in dispatch order: this wave's resolve waits for the previous wave's (the other stream, possibly an earlier call)
+        // and for whatever the caller enqueued on the image before this call
+        if (overlap) {
+            if (wave_seq_ > 0) CK(cudaStreamWaitEvent(st, resolved_ev_[ctx ^ 1], 0));
+            CK(cudaStreamWaitEvent(st, image_free_ev_, 0));
+        }
+        launch_resolve(lc_, dc, B.d_disp, nd, P, B.sample_buf, d_image_, st);
+        CK(cudaEventRecord(resolved_ev_[ctx], st));
+        wave_seq_++;
         launches++; waves++; mark(4);
+        last_st = st;
     }
-    if (n_ctx == 2) for (int c = 0; c < 2; c++) CK(cudaStreamWaitEvent(stream_, resolved_ev_[c], 0));   // join: everything after this call sees the finished image
-    CK(cudaEventRecord(ev_[1], stream_));
+    CK(cudaEventRecord(ev_[1], last_st));                     // ms_total: first kernel of the first wave .. resolve of the last (counters() synchronises before reading it)
     CK(cudaGetLastError());
     dispatch_count_ += todo;
     frame_count_ = (uint32_t)(dispatch_count_ / S2);                     // PathTracer.cpp:152
@@ -580,15 +594,15 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
 
 void Engine::set_stream(cudaStream_t s) {
     CK(cudaSetDevice(device_));
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     stream_ = s ? s : own_stream_;
 }
 
-void Engine::synchronize() { CK(cudaSetDevice(device_)); CK(cudaStreamSynchronize(stream_)); CK(cudaGetLastError()); }
+void Engine::synchronize() { CK(cudaSetDevice(device_)); sync_all(); CK(cudaGetLastError()); }
 
 b200pt_counters Engine::counters() {
     CK(cudaSetDevice(device_));
-    CK(cudaStreamSynchronize(stream_));
+    sync_all();
     WaveCounters wc; CK(cudaMemcpy(&wc, d_ctr_, sizeof wc, cudaMemcpyDeviceToHost));
     b200pt_counters c = last_;
     c.paths = wc.paths; c.extend_rays = wc.extend_rays; c.shade_invocations = wc.shade_invocations; c.surface_hits = wc.surface_hits;
@@ -600,6 +614,7 @@ b200pt_counters Engine::counters() {
 void Engine::get_hdr(float *dst, bool dev) {
     CK(cudaSetDevice(device_));
     if (!d_image_ || !dst) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "no image" };
+    join_waves();
     CK(cudaMemcpyAsync(dst, d_image_, (size_t)W_ * local_rows_ * sizeof(float4), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream_));
     if (!dev) CK(cudaStreamSynchronize(stream_));        // a device destination stays asynchronous on the engine's stream: the NCCL gather that follows is stream-ordered,
                                                           // and the host can already enqueue the next wave (no per-step bubble on multi-GPU runs)
@@ -607,6 +622,7 @@ void Engine::get_hdr(float *dst, bool dev) {
 void Engine::set_hdr(const float *src, bool dev) {
     CK(cudaSetDevice(device_));
     if (!d_image_ || !src) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "no image" };
+    join_waves();
     CK(cudaMemcpyAsync(d_image_, src, (size_t)W_ * local_rows_ * sizeof(float4), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
     CK(cudaStreamSynchronize(stream_));
 }
@@ -663,6 +679,7 @@ void Engine::ensure_post() {
 void Engine::accumulate_rows(const float4 *d_frame, uint32_t frame_index, uint32_t y0, uint32_t y1) {
     CK(cudaSetDevice(device_));
     if (!d_image_ || !d_frame || y0 >= y1 || y1 > H_ || world_ != 1) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "accumulate_rows: no image / bad rows / partitioned image" };
+    join_waves();
     launch_accumulate(d_frame, d_image_, y0 * W_, (y1 - y0) * W_, frame_index, lc_.grid_light > 0 ? lc_.grid_light : 1184, stream_);
     CK(cudaGetLastError());
 }
@@ -695,6 +712,7 @@ void Engine::post_process_rows(uint32_t y0, uint32_t y1) {
     if (world_ != 1) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_process needs the full image: gather the bands first (world must be 1)" };
     if (y0 >= y1 || y1 > H_) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "post_process_rows: bad row range" };
     ensure_post();
+    join_waves();
     const bool whole = (y0 == 0 && y1 == H_);
     const uint32_t levels = (uint32_t)d_mips_.size();
     const uint32_t mips = std::min(std::max(bloom_.MipCount, 1u), levels);                      // :195

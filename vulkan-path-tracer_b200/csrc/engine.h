@@ -46,6 +46,7 @@ public:
     // PathTracer::PathTrace x dispatches; returns true when all samples are accumulated
     bool path_trace(uint32_t dispatches, uint32_t base_seed);
     void synchronize();
+    void flush() { check(cudaSetDevice(device_), "cudaSetDevice"); join_waves(); }   // device-side: the caller's stream waits for every launched wave
     void set_stream(cudaStream_t s);
     void set_profiling(bool on) { profiling_ = on; }
     void get_hdr(float *dst, bool dst_is_device);
@@ -93,7 +94,6 @@ private:
     cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
     bool profiling_ = false;
     std::vector<cudaEvent_t> prof_ev_;
-    int table_sel_ = 0; cudaEvent_t table_ev_[2] = { nullptr, nullptr };
     cudaEvent_t ev_[2] = { nullptr, nullptr };
 
     HostScene scene_;
@@ -131,13 +131,15 @@ private:
         PathState ps[2]{}; ShadeOut so{};
         float4 *sample_buf = nullptr; uint32_t *rng_carry = nullptr; uint32_t *q_hit[2] = { nullptr, nullptr }, *q_miss[2] = { nullptr, nullptr };
         uint32_t *counts = nullptr, *h_count = nullptr;
+        DevDispatch *d_disp = nullptr, *h_disp = nullptr; cudaEvent_t disp_ev = nullptr;   // this context's slice of the dispatch table (pinned host copy reusable once disp_ev has fired)
         size_t cap = 0;
     };
     WaveBuf wb_[2];
-    cudaStream_t aux_stream_[2] = { nullptr, nullptr }; cudaEvent_t resolved_ev_[2] = { nullptr, nullptr }, fork_ev_ = nullptr;
+    cudaStream_t aux_stream_[2] = { nullptr, nullptr }; cudaEvent_t resolved_ev_[2] = { nullptr, nullptr }, image_free_ev_ = nullptr;
+    uint64_t wave_seq_ = 0;                         // waves launched so far: wave w runs in context w & 1 and resolves after wave w - 1
     size_t wave_cap_ = 0;                           // capacity (paths) of every allocated context
-    DevDispatch *d_disp_[2] = { nullptr, nullptr };
-    DevDispatch *h_disp_[2] = { nullptr, nullptr };
+    void sync_all();                                // the caller's stream AND the internal wave streams are idle
+    void join_waves();                              // work enqueued on the caller's stream from here on sees every launched wave resolved into the image
     WaveCounters *d_ctr_ = nullptr;
     uint2 *d_sort_key_rank_ = nullptr; uint32_t *d_sort_hist_ = nullptr, *d_sort_offs_ = nullptr, *d_order_ = nullptr;   // ray sort of incoherent bounces (launch_ray_sort)
     bool sort_rays_ = false;
