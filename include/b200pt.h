@@ -128,7 +128,7 @@ int32_t b200pt_reset(b200pt_handle h);                                      /* R
  * SH/RayGen.slang:162-380): free-flight sampling against the geometry distance, phase-function scattering with sky / light NEE, and
  * analytic transmittance on the NEE terms of surface hits.  Heterogeneous (NanoVDB) density / temperature data is not:
  * DensityDataIndex must be -1 and b200pt_add_density_data_to_volume returns B200PT_ERR_NOT_IMPLEMENTED.  At most B200PT_MAX_VOLUMES. */
-#define B200PT_MAX_VOLUMES 16
+#define B200PT_MAX_VOLUMES 100   /* the reference sorts into float distances[100] (RayGen.slang:165) */
 typedef struct {                         /* PathTracer::Volume, PT/PathTracer.h:36-70 (defaults in comments) */
     float CornerMin[3], CornerMax[3];    /* AABB in world space (-1 / +1)      */
     float Color[3];                      /* scattering albedo (0.8)            */

@@ -73,7 +73,7 @@ class Volume(C.Structure):     # b200pt_volume (PathTracer::Volume, PT/PathTrace
                 ("_reserved", C.c_uint32)]
 
 
-MAX_VOLUMES = 16
+MAX_VOLUMES = 100
 
 
 class Tonemap(C.Structure):

@@ -16,7 +16,7 @@
 namespace b200pt {
 
 constexpr uint32_t VOLUME_EVENT = 0xFFFFFFFEu;      // so.hit[i].w of a path that scattered inside a volume this segment
-constexpr int MAX_VOLUMES = 16;                      // per-ray sort arrays live in registers / local memory (the reference allows 100)
+constexpr int MAX_VOLUMES = 100;                     // RayGen.slang:165-166 (float distances[100]; int indices[100]): the per-ray sort arrays live in local memory
 
 struct VolIsect { float Near, Far; };
 // SH/Volume.slang:188-211 (the x/y/z mix-up of the max / min chains is the reference's)
