@@ -159,7 +159,7 @@ __device__ __forceinline__ bool dyn_leaf_step(const BvhView &b, DynRay &r, uint3
     const float4 *tp = b.tris + (size_t)slot * 3;
     const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
     float t, u, v;
-    if (tri_test(f3(ta), f3(tb), f3(tc), r.o, r.d, r.tmin, r.tmax_test, t, u, v)) {
+    if (tri_test<!ANYHIT>(f3(ta), f3(tb), f3(tc), r.o, r.d, r.tmin, r.tmax_test, t, u, v)) {
         const uint32_t gid = __float_as_uint(ta.w);
         if (ANYHIT) {
             if (t < r.tmax || gid < r.target) { r.cur = DYN_DONE; return true; }

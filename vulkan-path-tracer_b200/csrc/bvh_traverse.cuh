@@ -95,14 +95,17 @@ __device__ __forceinline__ float3 normalize_ray(float3 a) {
 // the NaN and the subtree is culled (a false miss).  |d| < 1e-30 is replaced by copysign(1e-30, d): every plane distance stays finite or a
 // correctly signed infinity (|n|, |o| < 3e8), the slab interval is unchanged for all practical purposes; the triangle test keeps the exact d.
 __device__ __forceinline__ float slab_rcp(float d) { return 1.0f / (fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d); }
-// Branch-free: in the traversal loops some lane of a warp passes the u and v tests for nearly every triangle (ncu, flat Cornell walk: 95 % / 77 % of the
-// warps enter the second / third stage), so early-outs saved no warp instructions and cost three branch + reconvergence pairs per test.  Every lane now
-// evaluates u, v and t with the SAME operations and roundings as before and the acceptance is one predicate (NaN / inf from det == 0 fail every comparison).
+// EARLY = false (any-hit shadow queries): branch-free.  In those loops some lane of a warp passes the u and v tests for nearly every triangle (ncu, flat Cornell
+// walk: 95 % / 77 % of the warps enter the second / third stage), so early-outs saved no warp instructions and cost three branch + reconvergence pairs per test
+// (k_connect 20.8 -> 19.0 ms per Cornell step).  EARLY = true (closest-hit queries of coherent extension rays): neighbouring rays fail the same test together and
+// the early-outs do skip work (k_extend 13.8 -> 12.7 ms).  Both forms evaluate u, v and t with the SAME operations and roundings: identical results.
 // 1 / det is the raw reciprocal approximation (MUFU.RCP, 1 ulp) in the default build -- the same precision class as the 2-ulp division it replaces
 // (Makefile: -prec-div=false), without the denormal / overflow rescaling around it; PRECISE=1 keeps the IEEE division.
+template <bool EARLY = false>
 __device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3 o, float3 d, float tmin, float tmax, float &t, float &u, float &v) {
     const float3 p = cross_fma(d, e2);
     const float det = dot_fma(e1, p);
+    if (EARLY && det == 0.0f) return false;
 #ifdef B200PT_PRECISE
     const float inv = 1.0f / det;
 #else
@@ -110,9 +113,12 @@ __device__ __forceinline__ bool tri_test(float3 v0, float3 e1, float3 e2, float3
 #endif
     const float3 tv = f3(__fsub_rn(o.x, v0.x), __fsub_rn(o.y, v0.y), __fsub_rn(o.z, v0.z));
     u = __fmul_rn(dot_fma(tv, p), inv);
+    if (EARLY && !(u >= 0.0f && u <= 1.0f)) return false;
     const float3 q = cross_fma(tv, e1);
     v = __fmul_rn(dot_fma(d, q), inv);
+    if (EARLY && !(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
     t = __fmul_rn(dot_fma(e2, q), inv);
+    if (EARLY) return (t > tmin && t < tmax);
     return (det != 0.0f) & (u >= 0.0f) & (u <= 1.0f) & (v >= 0.0f) & (__fadd_rn(u, v) <= 1.0f) & (t > tmin) & (t < tmax);
 }
 
@@ -140,7 +146,7 @@ __device__ __forceinline__ bool bvh_trace(const BvhView &b, float3 o, float3 d, 
         const float4 *tp = b.tris + (size_t)slot * 3;
         const float4 ta = ld4<SMEM>(tp), tb = ld4<SMEM>(tp + 1), tc = ld4<SMEM>(tp + 2);
         float t, u, v;
-        if (tri_test(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax_test, t, u, v)) {
+        if (tri_test<!ANYHIT>(f3(ta), f3(tb), f3(tc), o, d, tmin, tmax_test, t, u, v)) {
             const uint32_t gid = __float_as_uint(ta.w);
             if (TARGET && !(t < tmax || gid < target_gid)) return false;
             if (!found || t < h.t || (t == h.t && gid < best_gid)) {
