@@ -150,10 +150,11 @@ int32_t b200pt_volume_count(b200pt_handle h, uint32_t *out);
 int32_t b200pt_get_volume(b200pt_handle h, uint32_t index, b200pt_volume *out);          /* GetVolumes()[index] */
 int32_t b200pt_add_density_data_to_volume(b200pt_handle h, uint32_t index, const char *vdb_path);   /* AddDensityDataToVolume: NOT_IMPLEMENTED */
 int32_t b200pt_remove_density_data_from_volume(b200pt_handle h, uint32_t index);                    /* RemoveDensityDataFromVolume: NOT_IMPLEMENTED */
-/* ---- atmosphere: the twelve setters / getters of PathTracer.h:129-144,170-181 (members :221-232) as one parameter block.
- * The parameters are stored and returned like the reference's members (any set -> ResetPathTracing()); rendering WITH the atmosphere
- * (SH/Atmosphere.slang, SH/RayGen.slang:382-471: delta tracking per colour channel, sun NEE) is a SURVEY 8f "next" row that is not built:
- * b200pt_set_atmosphere with Enable != 0 returns B200PT_ERR_NOT_IMPLEMENTED and leaves the stored block unchanged. */
+/* ---- atmosphere: the twelve setters / getters of PathTracer.h:129-144,170-181 (members :221-232) as one parameter block; any set ->
+ * ResetPathTracing().  Enable != 0 renders with the reference's atmosphere (SH/Atmosphere.slang, SH/RayGen.slang:76-84,212-255,382-471): a miss
+ * emits nothing, the sky NEE samples the sun disk (direction from SkyRotationAzimuth / Altitude), Rayleigh / Mie / ozone events are found by delta
+ * tracking on one colour channel (the path is split at its first atmosphere event), and sky NEE terms are attenuated by a ratio-tracked
+ * transmittance.  Parity-tested against the CPU oracle (tests/test_gpu_parity.py::test_atmosphere_matches_oracle). */
 typedef struct {
     uint32_t Enable;                                    /* SetEnableAtmosphere (false)                         */
     float    PlanetPosition[3];                         /* SetPlanetPosition   (0, 6360e3 + 1000, 0) metres    */

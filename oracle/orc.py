@@ -44,7 +44,13 @@ class OrcConfig(C.Structure):
                 ("EmissiveMeshSamplingPDFBias", C.c_float), ("ScreenSplitCount", C.c_uint32),
                 ("EnableSkyMIS", C.c_uint32), ("EnableMeshMIS", C.c_uint32), ("ShowEnvMapDirectly", C.c_uint32),
                 ("UseOnlyGeometryNormals", C.c_uint32), ("UseEnergyCompensation", C.c_uint32), ("FurnaceTestMode", C.c_uint32),
-                ("PhaseFunction", C.c_uint32), ("VolumesCount", C.c_uint32), ("Volumes", C.c_void_p)]
+                ("PhaseFunction", C.c_uint32), ("VolumesCount", C.c_uint32), ("Volumes", C.c_void_p),
+                ("EnableAtmosphere", C.c_uint32), ("_padA", C.c_uint32),
+                ("PlanetPosition", C.c_float * 3), ("PlanetRadius", C.c_float), ("AtmosphereHeight", C.c_float),
+                ("RayleighScatteringCoefficientMultiplier", C.c_float * 3), ("MieScatteringCoefficientMultiplier", C.c_float * 3),
+                ("OzoneAbsorptionCoefficientMultiplier", C.c_float * 3),
+                ("RayleighDensityFalloff", C.c_float), ("MieDensityFalloff", C.c_float), ("OzoneDensityFalloff", C.c_float), ("OzonePeak", C.c_float),
+                ("SunColor", C.c_float * 3)]
 
 
 class OrcCounters(C.Structure):
@@ -206,6 +212,8 @@ def default_config(**kw):
             for i in range(16): getattr(c, k)[i] = float(v[i])
         elif k == "Volumes":
             set_volumes(c, v)
+        elif k in ("PlanetPosition", "RayleighScatteringCoefficientMultiplier", "MieScatteringCoefficientMultiplier", "OzoneAbsorptionCoefficientMultiplier", "SunColor"):
+            for i in range(3): getattr(c, k)[i] = float(v[i])
         else:
             setattr(c, k, v)
     return c

@@ -358,6 +358,7 @@ typedef struct {
     uint32_t Depth; Rng Sampler;
     int InMedium; float MediumDensity, MediumAnisotropy; v3 MediumColor, MediumEmissiveColor;
     int VolumeDepth;                                                            /* SH/RTCommon.slang Payload::VolumeDepth, reset per sample (SH/RayGen.slang:61) */
+    int ColorChannel;                                                           /* SH/RTCommon.slang:26-29: -1 = all channels, 0/1/2 after an atmosphere event split the ray */
 } Payload;
 
 static inline float power_heuristic(float a, float b) { return (a * a) / ((a * a) + (b * b)); } /* SH/RTCommon.slang:124-127 */
@@ -1023,6 +1024,8 @@ static float vol_scatter_distance(const OrcVolume *v, v3 o, v3 d, Rng *rng, floa
 static int does_ray_intersect(const OrcScene *sc, v3 o, v3 d, uint32_t *tri, uint32_t *inst, uint64_t *shadow_rays);
 static void sample_env(const OrcScene *sc, const OrcConfig *cfg, Rng *rng, v3 *toLight, v4 *outValue);
 static void sample_emissive(const OrcScene *sc, Rng *rng, v3 pos, v3 *toLight, v4 *colorPDF, uint32_t *tri, uint32_t *inst);
+static void importance_sample_sky(const OrcScene *sc, const OrcConfig *cfg, Rng *rng, v3 *toLight, v4 *outValue);
+static v3 atm_transmittance_nee(const OrcConfig *c, Payload *pl, v3 ro, v3 rd);
 /* EvaluateVolumeScatteringEvent, SH/RayGen.slang:265-380 */
 static void volume_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, float scatterDistance, int vi, OrcCounters *cnt) {
     const OrcVolume *v = &cfg->Volumes[vi];
@@ -1031,7 +1034,7 @@ static void volume_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Paylo
     pl->Emitted = V3(v->EmissiveColor[0], v->EmissiveColor[1], v->EmissiveColor[2]);   /* + temperature emission: 0 without grid data */
     v3 toSky = V3(0, 0, 0); v4 sky = { 0, 0, 0, 0 };
     if (cfg->EnableSkyMIS) {
-        sample_env(sc, cfg, &pl->Sampler, &toSky, &sky);
+        importance_sample_sky(sc, cfg, &pl->Sampler, &toSky, &sky);
         sky.x *= cfg->EnvironmentIntensity; sky.y *= cfg->EnvironmentIntensity; sky.z *= cfg->EnvironmentIntensity;   /* :277 (Q7 again) */
         uint32_t t0, t1;
         if (does_ray_intersect(sc, pl->Origin, toSky, &t0, &t1, &cnt->shadow_rays)) { v4 z = { 0, 0, 0, 0 }; sky = z; }
@@ -1047,10 +1050,11 @@ static void volume_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Paylo
     const float phaseS = vol_phase(cfg, v, pl->Direction, newDir, pl->VolumeDepth);
     if (cfg->EnableSkyMIS && sky.w > 0.0f) {
         float ph = vol_phase(cfg, v, pl->Direction, toSky, pl->VolumeDepth);
-        float T = volumes_transmittance(cfg, pl->Origin, toSky);
+        v3 T = v3s(volumes_transmittance(cfg, pl->Origin, toSky));
+        if (cfg->EnableAtmosphere) T = v3mul(T, atm_transmittance_nee(cfg, pl, pl->Origin, toSky));   /* :328-342 */
         v3 bx = v3scale(color, ph);
         if (ph > 0.0f)
-            pl->Emitted = v3add(pl->Emitted, v3scale(v3mul(v3mul(v3s(T), bx), v3divs(V3(sky.x, sky.y, sky.z), sky.w)), power_heuristic(sky.w, ph)));
+            pl->Emitted = v3add(pl->Emitted, v3scale(v3mul(v3mul(T, bx), v3divs(V3(sky.x, sky.y, sky.z), sky.w)), power_heuristic(sky.w, ph)));
     }
     if (cfg->EnableMeshMIS && light.w > 0.0f) {
         float ph = vol_phase(cfg, v, pl->Direction, toLight, pl->VolumeDepth);
@@ -1067,7 +1071,190 @@ static void volume_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Paylo
     cnt->medium_events++;
 }
 static Hit trace_bvh(const OrcScene *s, v3 o, v3 d, float tmin, float tmax);
-/* ScatteredInVolume, SH/RayGen.slang:162-263 (atmosphere off) */
+
+/* ------------------------------------------------------------------------------------------------
+ * Atmosphere (ENABLE_ATMOSPHERE): SH/Atmosphere.slang, SH/RayGen.slang:382-471, SH/Sampler.slang:196-215,430-476, SH/RTCommon.slang:174-211
+ * ---------------------------------------------------------------------------------------------- */
+static const float ATM_C_RAYLEIGH[3] = { 5.802f * 1e-6f, 13.558f * 1e-6f, 33.100f * 1e-6f };        /* Atmosphere.slang:7 */
+static const float ATM_C_MIE_SCATTERING = 3.996f * 1e-6f, ATM_C_MIE_ABSORPTION = 4.40f * 1e-6f;    /* :8-9 */
+static const float ATM_C_OZONE[3] = { 0.650f * 1e-6f, 1.881f * 1e-6f, 0.085f * 1e-6f };             /* :11 */
+typedef struct { float x, y; } v2;
+static v2 intersect_sphere(v3 ro, v3 rd, v3 center, float radius) {                                  /* RTCommon.slang:174-193 */
+    ro = v3sub(ro, center);
+    float a = v3dot(rd, rd);
+    float b = 2.0f * v3dot(ro, rd);
+    float c = v3dot(ro, ro) - radius * radius;
+    float disc = b * b - 4.0f * a * c;
+    v2 r = { -1.0f, -1.0f };
+    if (disc < 0.0f) return r;
+    r.x = (-b - sqrtf(disc)) / (2.0f * a);
+    r.y = (-b + sqrtf(disc)) / (2.0f * a);
+    return r;
+}
+static inline v3 atm_planet(const OrcConfig *c) { return V3(c->PlanetPosition[0], c->PlanetPosition[1], c->PlanetPosition[2]); }
+static float atm_height(const OrcConfig *c, v3 p) { return v3length(v3sub(p, atm_planet(c))) - c->PlanetRadius; }   /* Atmosphere.slang:13-16 */
+static float atm_rayleigh_density(const OrcConfig *c, float h) { return expf(-h / c->RayleighDensityFalloff); }
+static float atm_mie_density(const OrcConfig *c, float h) { return expf(-h / c->MieDensityFalloff); }
+static float atm_ozone_density(const OrcConfig *c, float h) { return expf(-(fabsf(h - c->OzonePeak) / c->OzoneDensityFalloff)); }
+static void atm_coefficients(const OrcConfig *c, int ch, float *kr, float *km, float *ko) {
+    const float C_MIE = ATM_C_MIE_SCATTERING + ATM_C_MIE_ABSORPTION;                                 /* :10 */
+    *kr = ATM_C_RAYLEIGH[ch] * c->RayleighScatteringCoefficientMultiplier[ch];
+    *km = C_MIE * c->MieScatteringCoefficientMultiplier[ch];
+    *ko = ATM_C_OZONE[ch] * c->OzoneAbsorptionCoefficientMultiplier[ch];
+}
+/* CalculateTransmittanceThroughAtmosphere, Atmosphere.slang:33-104: ratio tracking with Russian roulette on ONE colour channel; returns a
+ * vector that is zero in the other two channels */
+static v3 atm_transmittance(const OrcConfig *c, Rng *rng, v3 ro, v3 rd, int ch) {
+    v2 pi = intersect_sphere(ro, rd, atm_planet(c), c->PlanetRadius);
+    if (pi.y > 0.0f) return v3s(0.0f);                                                               /* occluded by the planet */
+    v2 ai = intersect_sphere(ro, rd, atm_planet(c), c->PlanetRadius + c->AtmosphereHeight);
+    float tMin = fmaxf(ai.x, 0.0f), tMax = ai.y;
+    if (tMax < 0.0f) return v3s(1.0f);
+    float kr, km, ko; atm_coefficients(c, ch, &kr, &km, &ko);
+    float majorant = atm_rayleigh_density(c, 0.0f) * kr + atm_mie_density(c, 0.0f) * km + atm_ozone_density(c, c->OzonePeak) * ko;
+    if (majorant <= 0.0f) return v3s(1.0f);
+    float t = 0.0f, T = 1.0f;
+    for (int i = 0; i < 1000; i++) {
+        float deltaT = -logf(1.0f - rng_f(rng)) / majorant;
+        t += deltaT;
+        if (t >= tMax - tMin) break;
+        float h = atm_height(c, v3add(ro, v3scale(rd, t + tMin)));
+        if (h < 0.0f) break;
+        float dr = atm_rayleigh_density(c, h) * kr, dm = atm_mie_density(c, h) * km, dz = atm_ozone_density(c, h) * ko;
+        T *= 1.0f - (dr + dm + dz) / majorant;
+        float p = T;
+        if (rng_f(rng) > p) { T = 0.0f; break; }
+        T /= p;
+    }
+    v3 out = v3s(0.0f);
+    if (ch == 0) out.x = T; else if (ch == 1) out.y = T; else out.z = T;
+    return out;
+}
+/* the NEE transmittance of SH/ClosestHit.slang:335-349 / SH/RayGen.slang:328-342: three walks while the ray is unsplit, one after */
+static v3 atm_transmittance_nee(const OrcConfig *c, Payload *pl, v3 ro, v3 rd) {
+    if (pl->ColorChannel == -1) {
+        v3 T;
+        T.x = atm_transmittance(c, &pl->Sampler, ro, rd, 0).x;
+        T.y = atm_transmittance(c, &pl->Sampler, ro, rd, 1).y;
+        T.z = atm_transmittance(c, &pl->Sampler, ro, rd, 2).z;
+        return T;
+    }
+    return atm_transmittance(c, &pl->Sampler, ro, rd, pl->ColorChannel);
+}
+/* SampleAtmosphereScatterDistance, Atmosphere.slang:114-201: delta tracking; *component: -1 none, 0 Rayleigh, 1 Mie, 2 ozone */
+static float atm_sample_scatter_distance(const OrcConfig *c, Rng *rng, v3 ro, v3 rd, int ch, int *component) {
+    v2 ai = intersect_sphere(ro, rd, atm_planet(c), c->PlanetRadius + c->AtmosphereHeight);
+    float tMinA = fmaxf(ai.x, 0.0f), tMaxA = ai.y;
+    *component = -1;
+    v2 pi = intersect_sphere(ro, rd, atm_planet(c), c->PlanetRadius);
+    float tMinPlanet = pi.x;
+    if (tMaxA < 0.0f) return -1.0f;
+    float kr, km, ko; atm_coefficients(c, ch, &kr, &km, &ko);
+    float majorant = atm_rayleigh_density(c, 0.0f) * kr + atm_mie_density(c, 0.0f) * km + atm_ozone_density(c, c->OzonePeak) * ko;
+    if (majorant <= 0.0f) return -1.0f;
+    float t = tMinA;
+    for (int i = 0; i < 1000; i++) {
+        float deltaT = -logf(1.0f - rng_f(rng)) / majorant;
+        t += deltaT;
+        if (t >= tMaxA) break;
+        if (tMinPlanet > 0.0f && t >= tMinPlanet) break;
+        float h = atm_height(c, v3add(ro, v3scale(rd, t)));
+        float dr = atm_rayleigh_density(c, h) * kr, dm = atm_mie_density(c, h) * km, dz = atm_ozone_density(c, h) * ko;
+        float density = dr + dm + dz;
+        if (density / majorant < rng_f(rng)) continue;                                               /* null collision */
+        float pr = dr / density, pm = dm / density;
+        float x = rng_f(rng);
+        if (x <= pr) *component = 0; else if (x <= pr + pm) *component = 1; else *component = 2;
+        return t;
+    }
+    return -1.0f;
+}
+static float phase_rayleigh(v3 V, v3 L) { float ct = v3dot(V, L); return (3.0f / (16.0f * ORC_PI)) * (1.0f + ct * ct); }   /* RTCommon.slang:197-201 */
+static float phase_mie_approx(v3 V, v3 L, float g) {                                                 /* RTCommon.slang:204-211 */
+    float ct = v3dot(V, L);
+    g = fminf(g, 0.9381f);
+    float k = 1.55f * g - 0.55f * g * g * g;
+    float kc = k * ct;
+    return (1.0f - k * k) / ((4.0f * ORC_PI) * (1.0f - kc) * (1.0f - kc));
+}
+static float phase_hg(v3 V, v3 L, float g);
+static v3 phase_frame(v3 incident, float cosTheta, float phi);
+static v3 rng_rayleigh(Rng *r, v3 incident) {                                                        /* Sampler.slang:196-215 */
+    float rx = rng_f(r), ry = rng_f(r);
+    float a = 2.0f * rx - 1.0f;
+    float u = -powf(2.0f * a + sqrtf(4.0f * powf(a, 2.0f) + 1.0f), 1.0f / 3.0f);
+    float cosTheta = u - (1.0f / u);
+    return phase_frame(incident, cosTheta, 2.0f * ORC_PI * ry);
+}
+/* SampleSunDisk(0.004675), Sampler.slang:430-463 (ImportanceSampleSky with ENABLE_ATMOSPHERE, :465-476) */
+static void sample_sun_disk(const OrcConfig *c, Rng *rng, v3 *toLight, v4 *colorPDF) {
+    const float sunTheta = 0.004675f;
+    float az = c->SkyRotationAzimuth / 180.0f * ORC_PI, al = c->SkyRotationAltitude / 180.0f * ORC_PI;
+    v3 sunDir = orc_rotate(V3(0.0f, 0.0f, -1.0f), V3(1.0f, 0.0f, 0.0f), al);
+    sunDir = orc_rotate(sunDir, V3(0.0f, 1.0f, 0.0f), az);
+    float cosThetaMax = cosf(sunTheta);
+    float phi = 2.0f * ORC_PI * rng_f(rng);
+    float cosTheta = orc_lerp(cosThetaMax, 1.0f, rng_f(rng));
+    float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+    v3 local = V3(cosf(phi) * sinTheta, sinf(phi) * sinTheta, cosTheta);
+    v3 w = v3normalize(sunDir);
+    v3 up = fabsf(w.z) < 0.999f ? V3(0, 0, 1) : V3(1, 0, 0);
+    v3 u = v3normalize(v3cross(up, w));
+    v3 v = v3cross(w, u);
+    *toLight = v3add(v3add(v3scale(u, local.x), v3scale(v, local.y)), v3scale(w, local.z));
+    float solidAngle = 2.0f * ORC_PI * (1.0f - cosThetaMax);
+    colorPDF->w = 1.0f / solidAngle;
+    colorPDF->x = 2e5f * c->SunColor[0] * c->EnvironmentIntensity; colorPDF->y = 2e5f * c->SunColor[1] * c->EnvironmentIntensity; colorPDF->z = 2e5f * c->SunColor[2] * c->EnvironmentIntensity;
+}
+static void sample_env(const OrcScene *sc, const OrcConfig *cfg, Rng *rng, v3 *toLight, v4 *outValue);
+static void importance_sample_sky(const OrcScene *sc, const OrcConfig *cfg, Rng *rng, v3 *toLight, v4 *outValue) {   /* Sampler.slang:465-476 */
+    if (cfg->EnableAtmosphere) sample_sun_disk(cfg, rng, toLight, outValue);
+    else sample_env(sc, cfg, rng, toLight, outValue);
+}
+static int does_ray_intersect(const OrcScene *sc, v3 o, v3 d, uint32_t *tri, uint32_t *inst, uint64_t *shadow_rays);
+static float volumes_transmittance(const OrcConfig *cfg, v3 o, v3 d);
+/* EvaluateAtmosphereScatteringEvent, SH/RayGen.slang:382-471 */
+static void atmosphere_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, float scatterDistance, int component, OrcCounters *cnt) {
+    pl->Origin = v3add(pl->Origin, v3scale(pl->Direction, scatterDistance));
+    v3 newDir;
+    if (component == 0) newDir = rng_rayleigh(&pl->Sampler, pl->Direction);
+    else if (component == 1) newDir = rng_henyey_greenstein(&pl->Sampler, pl->Direction, 0.85f);
+    else newDir = pl->Direction;                                                                     /* ozone only absorbs */
+    const float C_MIE = ATM_C_MIE_SCATTERING + ATM_C_MIE_ABSORPTION;
+    if (cfg->EnableSkyMIS) {
+        v3 toSun; v4 cp;
+        importance_sample_sky(sc, cfg, &pl->Sampler, &toSun, &cp);
+        cp.x *= cfg->EnvironmentIntensity; cp.y *= cfg->EnvironmentIntensity; cp.z *= cfg->EnvironmentIntensity;
+        uint32_t t0, t1;
+        int obscured = does_ray_intersect(sc, pl->Origin, toSun, &t0, &t1, &cnt->shadow_rays);
+        v3 T = v3s(0.0f);
+        if (!obscured) {
+            T = atm_transmittance(cfg, &pl->Sampler, pl->Origin, toSun, pl->ColorChannel);
+            T = v3scale(T, volumes_transmittance(cfg, pl->Origin, toSun));
+        }
+        v3 col = v3divs(V3(cp.x, cp.y, cp.z), cp.w);
+        if (component == 0) {
+            float ph = phase_rayleigh(pl->Direction, toSun);
+            pl->Emitted = v3add(pl->Emitted, v3mul(v3scale(T, ph), col));
+            float pn = phase_rayleigh(pl->Direction, newDir);
+            pl->BxDF = v3s(pn); pl->PDF = pn;
+        } else if (component == 1) {
+            float ph = phase_hg(pl->Direction, toSun, 0.85f);
+            pl->Emitted = v3add(pl->Emitted, v3mul(v3scale(T, ph), col));
+            float att = ATM_C_MIE_ABSORPTION / C_MIE;
+            float pn = phase_hg(pl->Direction, newDir, 0.85f);
+            pl->BxDF = v3s(pn * (1.0f - att)); pl->PDF = pn;
+        } else { pl->BxDF = v3s(0.0f); pl->PDF = 1.0f; }
+    } else {
+        if (component == 0) { float pn = phase_rayleigh(pl->Direction, newDir); pl->BxDF = v3s(pn); pl->PDF = pn; }
+        else { float att = ATM_C_MIE_ABSORPTION / C_MIE; pl->BxDF = v3s(phase_mie_approx(pl->Direction, newDir, 0.85f) * att); pl->PDF = phase_hg(pl->Direction, newDir, 0.85f); }
+    }
+    pl->Direction = newDir;
+    pl->Depth++;
+    cnt->medium_events++;
+}
+
+/* ScatteredInVolume, SH/RayGen.slang:162-263 */
 #define ORC_MAX_VOLUMES 100
 static int scattered_in_volume(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, OrcCounters *cnt) {
     float distances[ORC_MAX_VOLUMES]; int indices[ORC_MAX_VOLUMES];
@@ -1087,8 +1274,18 @@ static int scattered_in_volume(const OrcScene *sc, const OrcConfig *cfg, Payload
         float t = vol_scatter_distance(&cfg->Volumes[indices[i]], pl->Origin, pl->Direction, &pl->Sampler, scatterDistance);
         if (t >= 0.0f && (t < scatterDistance || scatterDistance < 0.0f)) { scatterDistance = t; scattered = indices[i]; }
     }
+    int component = -1, colorChannel = pl->ColorChannel;
+    if (cfg->EnableAtmosphere) {                                                 /* :212-236 */
+        if (colorChannel == -1) {
+            float pick = rng_f(&pl->Sampler);
+            colorChannel = pick < 0.33333f ? 0 : (pick < 0.66666f ? 1 : 2);
+        }
+        float ta = atm_sample_scatter_distance(cfg, &pl->Sampler, pl->Origin, pl->Direction, colorChannel, &component);
+        if (ta >= 0.0f && (ta < scatterDistance || scatterDistance < 0.0f)) { scatterDistance = ta; scattered = -2; }
+    }
     if (scatterDistance >= 0.0f && (distanceToGeometry < 0.0f || scatterDistance < distanceToGeometry)) {
-        volume_scatter_event(sc, cfg, pl, scatterDistance, scattered, cnt);
+        if (scattered == -2) { pl->ColorChannel = colorChannel; atmosphere_scatter_event(sc, cfg, pl, scatterDistance, component, cnt); }
+        else volume_scatter_event(sc, cfg, pl, scatterDistance, scattered, cnt);
         return 1;
     }
     return 0;
@@ -1130,7 +1327,7 @@ static void closest_hit(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, v
     /* sky NEE :125-147 */
     v3 toSkyW = V3(0, 0, 0), toSkyT = V3(0, 0, 0); v4 sky = { 0, 0, 0, 0 }; int canHitSky = 0;
     if (cfg->EnableSkyMIS) {
-        sample_env(sc, cfg, &pl->Sampler, &toSkyW, &sky);
+        importance_sample_sky(sc, cfg, &pl->Sampler, &toSkyW, &sky);
         sky.x *= cfg->EnvironmentIntensity; sky.y *= cfg->EnvironmentIntensity; sky.z *= cfg->EnvironmentIntensity; /* Q7 */
         toSkyT = surf_world_to_tangent(&sf, toSkyW);
         uint32_t t0, t1;
@@ -1198,9 +1395,10 @@ static void closest_hit(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, v
     /* NEE accumulation :326-372 (volume transmittance == 1 with VolumesCount == 0, SH/Volume.slang:419-446) */
     if (cfg->EnableSkyMIS && canHitSky) {
         float pdf = sky.w;
-        const float T = cfg->VolumesCount ? volumes_transmittance(cfg, pl->Origin, toSkyW) : 1.0f;      /* :332-333 */
+        v3 T = v3s(cfg->VolumesCount ? volumes_transmittance(cfg, pl->Origin, toSkyW) : 1.0f);     /* :332-333 */
+        if (cfg->EnableAtmosphere) T = v3mul(T, atm_transmittance_nee(cfg, pl, pl->Origin, toSkyW));    /* :335-349: consumes random numbers whenever the sky is visible */
         if (sky.w > 0.0f && skyEval.PDF > 0.0f) {
-            v3 c = v3divs(v3mul(v3scale(skyEval.BxDF, T), V3(sky.x, sky.y, sky.z)), pdf);
+            v3 c = v3divs(v3mul(v3mul(skyEval.BxDF, T), V3(sky.x, sky.y, sky.z)), pdf);
             pl->Emitted = v3add(pl->Emitted, v3scale(c, power_heuristic(pdf, skyEval.PDF)));
         }
     }
@@ -1215,6 +1413,7 @@ static void closest_hit(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, v
 
 /* Miss: SH/Miss.slang:8-76 */
 static void miss_shader(const OrcScene *sc, const OrcConfig *cfg, Payload *pl) {
+    if (cfg->EnableAtmosphere) { pl->Depth = ORC_MAX_DEPTH; return; }           /* :11-14: the sky is the in-scattered sun light, a miss emits nothing */
     v4 c;
     if (cfg->ShowEnvMapDirectly || pl->Depth > 0) {
         float az = cfg->SkyRotationAzimuth / 180.0f * ORC_PI, al = cfg->SkyRotationAltitude / 180.0f * ORC_PI;
@@ -1256,14 +1455,15 @@ static v3 trace_one_sample(const OrcScene *sc, const OrcConfig *cfg, Payload *pl
     direction = v3normalize(v3sub(focus, origin));
 
     pl->Depth = 0; pl->Origin = origin; pl->Direction = direction;
-    pl->BxDF = v3s(1.0f); pl->PDF = 1.0f; pl->Emitted = v3s(0.0f); pl->InMedium = 0; pl->VolumeDepth = 0;
+    pl->BxDF = v3s(1.0f); pl->PDF = 1.0f; pl->Emitted = v3s(0.0f); pl->InMedium = 0; pl->VolumeDepth = 0; pl->ColorChannel = -1;
     v3 throughput = v3s(1.0f), pathLight = v3s(0.0f);
     cnt->paths++;
     while (pl->Depth < cfg->MaxDepth) {
         v3 ro = pl->Origin, rd = v3normalize(pl->Direction);
         pl->Emitted = v3s(0.0f);
+        if (cfg->EnableAtmosphere && atm_height(cfg, pl->Origin) < 0.0f) break;    /* :76-84: below the surface of the planet */
         cnt->segments++;
-        if (!(cfg->VolumesCount && scattered_in_volume(sc, cfg, pl, cnt))) {         /* :86-90 */
+        if (!((cfg->VolumesCount || cfg->EnableAtmosphere) && scattered_in_volume(sc, cfg, pl, cnt))) {         /* :86-90 */
             Hit h = trace_bvh(sc, ro, rd, 0.01f, 100000.0f);
             if (h.hit) closest_hit(sc, cfg, pl, rd, &h, cnt);
             else { miss_shader(sc, cfg, pl); cnt->misses++; }
@@ -1290,6 +1490,7 @@ void orc_sample_pixel(const OrcScene *s, const OrcConfig *cfg, uint32_t W, uint3
     pl.Sampler.seed = y + W * x + seed;                                         /* :28 (Q13) */
     OrcCounters c; memset(&c, 0, sizeof(c));
     v3 l = trace_one_sample(s, cfg, &pl, W, H, x, y, &c);
+    if (pl.ColorChannel == 0) { l.y = 0.0f; l.z = 0.0f; } else if (pl.ColorChannel == 1) { l.x = 0.0f; l.z = 0.0f; } else if (pl.ColorChannel == 2) { l.x = 0.0f; l.y = 0.0f; }
     out_rgb[0] = l.x; out_rgb[1] = l.y; out_rgb[2] = l.z;
     if (segments_out) *segments_out = (uint32_t)c.segments;
 }
@@ -1316,7 +1517,10 @@ static void *render_thread(void *arg) {
             v3 acc = v3s(0.0f);
             for (uint32_t i = 0; i < cfg->SampleCount; i++) {
                 v3 l = trace_one_sample(j->s, cfg, &pl, j->W, j->H, x, y, &j->cnt);
-                if (!isinf(l.x) && !isinf(l.y) && !isinf(l.z) && !isnan(l.x) && !isnan(l.y) && !isnan(l.z)) acc = v3add(acc, l); /* :116 */
+                if (!isinf(l.x) && !isinf(l.y) && !isinf(l.z) && !isnan(l.x) && !isnan(l.y) && !isnan(l.z)) {   /* :116-128 */
+                    if (pl.ColorChannel == -1) acc = v3add(acc, l);
+                    else if (pl.ColorChannel == 0) acc.x += l.x; else if (pl.ColorChannel == 1) acc.y += l.y; else acc.z += l.z;   /* a split ray carries one channel */
+                }
             }
             acc = v3divs(acc, (float)cfg->SampleCount);
             v3 color;
@@ -1378,6 +1582,12 @@ void orc_default_config(OrcConfig *c) {                                         
     c->EmissiveMeshSamplingPDFBias = 0.0f; c->ScreenSplitCount = 1;
     c->EnableSkyMIS = 1; c->EnableMeshMIS = 1; c->ShowEnvMapDirectly = 1; c->UseOnlyGeometryNormals = 0;
     c->UseEnergyCompensation = 1; c->FurnaceTestMode = 0;
+    /* atmosphere, PT/PathTracer.h:221-232 */
+    c->EnableAtmosphere = 0; c->PlanetPosition[0] = 0.0f; c->PlanetPosition[1] = 6360e3f + 1000.0f; c->PlanetPosition[2] = 0.0f;
+    c->PlanetRadius = 6360e3f; c->AtmosphereHeight = 100e3f;
+    for (int k = 0; k < 3; k++) { c->RayleighScatteringCoefficientMultiplier[k] = 1.0f; c->MieScatteringCoefficientMultiplier[k] = 1.0f; c->OzoneAbsorptionCoefficientMultiplier[k] = 1.0f; }
+    c->RayleighDensityFalloff = 8000.0f; c->MieDensityFalloff = 1200.0f; c->OzoneDensityFalloff = 5000.0f; c->OzonePeak = 22000.0f;
+    c->SunColor[0] = 1.0f; c->SunColor[1] = 0.956f; c->SunColor[2] = 0.88f;
 }
 
 /* PT/PathTracer.cpp:1137-1332 (Q1 kept: lowEnergyCounter++ before the store) */

@@ -81,6 +81,12 @@ typedef struct {                                                             /* 
     uint32_t PhaseFunction;       /* 0 Henyey-Greenstein, 1 Draine, 2 Henyey-Greenstein + Draine (PT/PathTracer.h:76-81) */
     uint32_t VolumesCount;
     const OrcVolume *Volumes;
+    /* atmosphere: ENABLE_ATMOSPHERE define (PT/PathTracer.cpp:636-637) + UBO fields SH/Bindings.slang:26-37, defaults PT/PathTracer.h:221-232 */
+    uint32_t EnableAtmosphere; uint32_t _padA;
+    float PlanetPosition[3], PlanetRadius, AtmosphereHeight;
+    float RayleighScatteringCoefficientMultiplier[3], MieScatteringCoefficientMultiplier[3], OzoneAbsorptionCoefficientMultiplier[3];
+    float RayleighDensityFalloff, MieDensityFalloff, OzoneDensityFalloff, OzonePeak;
+    float SunColor[3];
 } OrcConfig;
 
 typedef struct { uint64_t paths, segments, surface_hits, misses, shadow_rays, medium_events; } OrcCounters;   /* medium_events: scattering events inside a mesh medium or an AABB volume */

@@ -19,6 +19,8 @@ run("cornell_box", 64, 36, 2, 6)                                   # BVH in shar
 os.environ["B200PT_FLAT_MAX"] = "0"; run("cornell_box", 48, 32, 1, 4); del os.environ["B200PT_FLAT_MAX"]      # BVH2 stack traversal in shared memory
 os.environ["B200PT_FUSE"] = "2"; run("cornell_box", 48, 32, 2, 5); del os.environ["B200PT_FUSE"]              # fused bounce kernel
 run("cornell_box", 48, 32, 1, 5, Volumes=[FOG])                     # k_volume_decide / k_shade_volume
+run("cornell_box", 48, 32, 2, 5, EnableAtmosphere=1, SkyRotationAltitude=-30.0)                       # atmosphere: sun NEE, delta tracking, transmittance walks
+run("cornell_box", 40, 30, 1, 5, EnableAtmosphere=1, SkyRotationAltitude=-20.0, Volumes=[FOG])        # atmosphere + homogeneous volume
 run("cornell_box_glass", 48, 48, 2, 8)                              # dynamic-fetch BVH2 kernels, class queues (glass / diffuse)
 os.environ["B200PT_WIDE"] = "1"; run("viking_room", 48, 48, 1, 4); del os.environ["B200PT_WIDE"]              # BVH4 + textures
 os.environ["B200PT_SORT"] = "1"; os.environ["B200PT_TOP_KB"] = "16"; os.environ["B200PT_WIDE"] = "1"

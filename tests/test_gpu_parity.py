@@ -468,6 +468,48 @@ def test_homogeneous_volumes_match_oracle(pt, name, depth, pf, vols):
     assert util.rel_l2(got[..., :3], ref[..., :3]) < 1e-3            # measured 1.5e-7 .. 1.1e-4 over the five cases
 
 
+ATM_CASES = [("cornell_box", 8, dict(SkyRotationAltitude=-30.0), None),
+             ("cornell_box", 8, dict(SkyRotationAltitude=-8.0, SkyRotationAzimuth=40.0, EnableSkyMIS=0), None),
+             ("cornell_box", 6, dict(SkyRotationAltitude=-50.0, MieScatteringCoefficientMultiplier=(30.0, 30.0, 30.0), RayleighDensityFalloff=6000.0), [FOG]),
+             ("viking_room", 6, dict(SkyRotationAltitude=-35.0, SkyRotationAzimuth=200.0, SunColor=(1.0, 0.8, 0.6)), None)]
+
+
+@pytest.mark.parametrize("name,depth,kw,vols", ATM_CASES)
+def test_atmosphere_matches_oracle(pt, name, depth, kw, vols):
+    """the reference's atmosphere (SH/Atmosphere.slang, SH/RayGen.slang:76-84,212-255,382-471, SH/Sampler.slang:430-476) through
+    b200pt_set_atmosphere -- sun-disk sky NEE, delta-tracked Rayleigh / Mie / ozone events on one colour channel with the ray split at the first
+    event, ratio-tracked transmittance that consumes random numbers only when the sun is visible, per-channel accumulation, a miss emitting
+    nothing; alone, without sky MIS (the approximated-Mie branch), together with a homogeneous volume, on a textured scene traversed out of L2.
+    1 spp at a matched seed (the draw order is the reference's), event / segment counters, then the accumulated image at the 1e-3 bar."""
+    extra = dict(kw, EnableAtmosphere=1)
+    if vols: extra["Volumes"] = vols
+    W, H = 128, 96
+    ref, got, cnt, T = _render_both(pt, name, W, H, 1, MaxDepth=depth, **extra)
+    assert np.isfinite(got).all() and np.all(got[..., 3] == 1.0) and ref[..., :3].max() > 0
+    a, b = ref[..., :3].astype(np.float64), got[..., :3].astype(np.float64)
+    close = np.all(np.abs(a - b) <= 1e-4 * np.maximum(np.abs(a), 1e-2), axis=-1)
+    print(f"atmosphere matched-seed agreement {name} {kw}: {close.mean():.5f}")
+    assert close.mean() > 0.99, (name, kw, close.mean())
+    c = T.counters()
+    assert cnt["medium_events"] > 300                                       # atmosphere (and volume) scattering events did happen
+    assert abs(c["medium_events"] - cnt["medium_events"]) <= 0.003 * cnt["medium_events"] + 4
+    assert abs(c["extend_rays"] - cnt["segments"]) <= 0.003 * cnt["segments"] + 4
+    a = T.get_atmosphere(); assert a.Enable == 1
+    for bad in (dict(PlanetRadius=0.0), dict(RayleighDensityFalloff=-1.0), dict(AtmosphereHeight=-5.0)):                 # rejected whole, state untouched
+        with pytest.raises(pt.B200ptError) as ei: T.set_atmosphere(**bad)
+        assert ei.value.code == pt.ERR_WRONG_ARGUMENTS and T.get_atmosphere().PlanetRadius == a.PlanetRadius and T.samples_accumulated() == 1
+    ref, got, cnt, T = _render_both(pt, name, 96, 72, 64, MaxDepth=depth, **extra)
+    l2 = util.rel_l2(got[..., :3], ref[..., :3])
+    print(f"atmosphere accumulated rel L2 {name} {kw}: {l2:.3e}")
+    assert l2 < 1e-3, l2
+    # switching the atmosphere off again restores the environment-map render (SetEnableAtmosphere(false) -> ResetPathTracing)
+    T.set_atmosphere(Enable=0); assert T.samples_accumulated() == 0
+    T.path_trace(2, util.BASE_SEED); off = T.get_hdr().copy()
+    T2 = util.product_tracer(name, 96, 72, MaxDepth=depth, **({"Volumes": vols} if vols else {}), **{k: v for k, v in kw.items() if k not in util.ATMOSPHERE_KEYS})
+    T2.path_trace(2, util.BASE_SEED)
+    assert np.array_equal(off.view(np.uint32), T2.get_hdr().view(np.uint32))
+
+
 def test_volume_api_and_traversal_shapes(pt, monkeypatch):
     """PathTracer::AddVolume / SetVolume / RemoveVolume / GetVolumes / SetPhaseFunction (PathTracer.h:157-169) behind the C-ABI; a scene with
     volumes renders bit-identically under both traversal shapes; removing the volumes restores the volume-free image exactly."""

@@ -48,6 +48,8 @@ def oracle_config(name, **kw):
     return orc.default_config(ViewInverse=vi, ProjectionInverse=pi, **kw)
 
 
+ATMOSPHERE_KEYS = ("EnableAtmosphere", "PlanetPosition", "PlanetRadius", "AtmosphereHeight", "RayleighScatteringCoefficientMultiplier", "MieScatteringCoefficientMultiplier",
+                   "OzoneAbsorptionCoefficientMultiplier", "RayleighDensityFalloff", "MieDensityFalloff", "OzoneDensityFalloff", "OzonePeak", "SunColor")
 _ORC2PT = {"SampleCount": "SamplesPerFrame", "EnvironmentIntensity": "SkyIntensity", "ScreenSplitCount": "ScreenChunkCount"}
 
 
@@ -60,6 +62,8 @@ def product_tracer(name, W, H, env=None, device=0, **cfg_kw):
     t.set_env_map(raw)
     t.set_luts(*luts())
     cfg = pt.default_config()
+    atm = {k: cfg_kw.pop(k) for k in list(cfg_kw) if k in ATMOSPHERE_KEYS}        # oracle config names == b200pt_atmosphere names (Enable aside)
+    if atm: t.set_atmosphere(**{("Enable" if k == "EnableAtmosphere" else k): v for k, v in atm.items()})
     for k, v in cfg_kw.items():
         if k == "Volumes":                       # homogeneous AABB volumes: list of dicts (oracle.orc.VOLUME_DEFAULTS keys)
             for vol in v: t.add_volume(**vol)

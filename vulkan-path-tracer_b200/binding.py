@@ -465,6 +465,18 @@ class PathTracer:
 
     def set_bloom(self, threshold=2.0, strength=1.0, mips=10, falloff=5.0): self._ck(self.L.b200pt_post_set_bloom(self.h, C.byref(Bloom(threshold, strength, mips, falloff))))
 
+    def get_atmosphere(self):
+        a = Atmosphere(); self._ck(self.L.b200pt_get_atmosphere(self.h, C.byref(a))); return a
+
+    def set_atmosphere(self, **kw):
+        """fields of b200pt_atmosphere (the reference's twelve atmosphere setters); unnamed fields keep their current value"""
+        a = self.get_atmosphere()
+        for k, v in kw.items():
+            if k in ("PlanetPosition", "RayleighScatteringCoefficientMultiplier", "MieScatteringCoefficientMultiplier", "OzoneAbsorptionCoefficientMultiplier", "SunColor"):
+                for i in range(3): getattr(a, k)[i] = float(v[i])
+            else: setattr(a, k, v)
+        self._ck(self.L.b200pt_set_atmosphere(self.h, C.byref(a)))
+
     def flush(self): self._ck(self.L.b200pt_flush(self.h))
 
     def post_process(self): self._ck(self.L.b200pt_post_process(self.h))

@@ -144,7 +144,8 @@ int32_t b200pt_default_atmosphere(b200pt_atmosphere *a) {          // PathTracer
 int32_t b200pt_set_atmosphere(b200pt_handle h, const b200pt_atmosphere *a) {
     if (!a) return B200PT_ERR_WRONG_ARGUMENTS;
     return guard(h, [&](Engine &e) {
-        if (a->Enable) throw CudaError{ B200PT_ERR_NOT_IMPLEMENTED, "rendering with the atmosphere (SH/Atmosphere.slang) is not implemented: Enable must be 0" };
+        if (!(a->PlanetRadius > 0.0f) || !(a->AtmosphereHeight >= 0.0f) || !(a->RayleighDensityFalloff > 0.0f) || !(a->MieDensityFalloff > 0.0f) || !(a->OzoneDensityFalloff > 0.0f))
+            throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "atmosphere: radius and density falloffs must be positive" };
         e.set_atmosphere(*a);
     });
 }

@@ -118,6 +118,7 @@ struct DevScene {
     const uint32_t *em_tri_base;   // per emissive mesh: first EmTri
     const DevVolume *volumes;      // homogeneous AABB volumes (volumes.cuh), n_volumes entries
     uint32_t uniform_class;        // the one MaterialClass every triangle has, or 0xFF (k_extend then looks tri_class up per hit)
+    uint32_t pre_pass;             // k_volume_decide runs before k_extend (the scene has volumes or the atmosphere is on): hit records may hold VOLUME_EVENT / DEAD_EVENT
     uint32_t n_volumes, phase_function;   // phase_function: 0 HG, 1 Draine, 2 HG + Draine (PT/PathTracer.h:76-81)
     uint32_t n_emissive, envW, envH, n_tris, n_nodes, n_nodes4;
     int32_t root;            // child-style reference of the root
@@ -152,6 +153,13 @@ struct DevConfig {          // PT/PathTracer.h:271-302 (the fields the surface i
     uint32_t W, H;           // full image size
     uint32_t rank, world, band_rows, local_rows;
     float cosAz, sinAz, cosAl, sinAl;   // cos/sin(SkyRotation{Azimuth,Altitude} / 180 * PI), evaluated on the host
+    // atmosphere (ENABLE_ATMOSPHERE + SH/Bindings.slang:26-37; csrc/atmosphere.cuh)
+    uint32_t EnableAtmosphere;
+    float PlanetPosition[3], PlanetRadius, AtmosphereHeight;
+    float RayleighMult[3], MieMult[3], OzoneMult[3];
+    float RayleighDensityFalloff, MieDensityFalloff, OzoneDensityFalloff, OzonePeak;
+    float SunColor[3];
+    float cosSunTheta;       // cos(0.004675), SH/Sampler.slang:469 (host-evaluated)
 };
 
 struct DevDispatch { uint32_t FrameCount, Seed, ChunkIndex, _pad; };   // PT/PathTracer.h:304-309

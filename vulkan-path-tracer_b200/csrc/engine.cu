@@ -445,6 +445,14 @@ DevConfig Engine::make_dev_config() const {
     d.EnvironmentIntensity = cfg_.SkyIntensity; d.EmissiveMeshSamplingPDFBias = cfg_.EmissiveMeshSamplingPDFBias; d.ScreenSplitCount = cfg_.ScreenChunkCount;
     d.EnableSkyMIS = cfg_.EnableSkyMIS; d.EnableMeshMIS = cfg_.EnableMeshMIS; d.ShowEnvMapDirectly = cfg_.ShowEnvMapDirectly;
     d.UseOnlyGeometryNormals = cfg_.UseOnlyGeometryNormals; d.UseEnergyCompensation = cfg_.UseEnergyCompensation; d.FurnaceTestMode = cfg_.FurnaceTestMode;
+    {   // atmosphere block (PathTracer.h:221-232 -> SH/Bindings.slang:26-37)
+        const b200pt_atmosphere &a = atmosphere_;
+        d.EnableAtmosphere = a.Enable ? 1u : 0u; d.PlanetRadius = a.PlanetRadius; d.AtmosphereHeight = a.AtmosphereHeight;
+        for (int k = 0; k < 3; k++) { d.PlanetPosition[k] = a.PlanetPosition[k]; d.RayleighMult[k] = a.RayleighScatteringCoefficientMultiplier[k]; d.MieMult[k] = a.MieScatteringCoefficientMultiplier[k];
+                                      d.OzoneMult[k] = a.OzoneAbsorptionCoefficientMultiplier[k]; d.SunColor[k] = a.SunColor[k]; }
+        d.RayleighDensityFalloff = a.RayleighDensityFalloff; d.MieDensityFalloff = a.MieDensityFalloff; d.OzoneDensityFalloff = a.OzoneDensityFalloff; d.OzonePeak = a.OzonePeak;
+        d.cosSunTheta = cosf(0.004675f);
+    }
     { const float az = cfg_.SkyRotationAzimuth / 180.0f * 3.1415926535897F, al = cfg_.SkyRotationAltitude / 180.0f * 3.1415926535897F;   // SH/Sampler.slang:338-339
       d.cosAz = cosf(az); d.sinAz = sinf(az); d.cosAl = cosf(al); d.sinAl = sinf(al); }
     d.W = W_; d.H = H_; d.rank = rank_; d.world = world_; d.band_rows = band_; d.local_rows = local_rows_;
@@ -499,6 +507,8 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
     auto pcg = [](uint32_t in) { uint32_t st = in * 747796405u + 2891336453u; uint32_t w = ((st >> ((st >> 28u) + 4u)) ^ st) * 277803737u; return (w >> 22u) ^ w; };
 
     const uint32_t n_vol = ds_.n_volumes;
+    const bool pre = n_vol != 0u || atmosphere_.Enable != 0u;   // k_volume_decide + k_shade_volume run: volumes and / or the atmosphere (csrc/atmosphere.cuh)
+    ds_.pre_pass = pre ? 1u : 0u;
     bool medium = false;                                      // can a path random-walk inside a mesh without gaining Depth?
     // Conservative: the device-side metallic value is Metallic * texel, so the constant factor alone cannot rule refraction out, and a negative
     // density (not validated by the reference either) scatters on every segment.  A false positive only costs a 4-byte read-back per 16 bounces.
@@ -506,8 +516,8 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
 
     // Fused bounce kernels (LaunchCfg::fuse) need the BVH in shared memory and no volumes; they ping-pong the queues and the hit records
     // (the kernel that consumes bounce k's queue fills bounce k+1's), the unfused pipeline uses buffer 0 only.
-    const int fuse = n_vol ? 0 : lc_.fuse;
-    const uint32_t cmask = n_vol ? (class_mask_ | (1u << MC_GENERAL)) : class_mask_;   // volume events ride in the general queue
+    const int fuse = pre ? 0 : lc_.fuse;
+    const uint32_t cmask = pre ? (class_mask_ | (1u << MC_GENERAL)) : class_mask_;   // volume / atmosphere events ride in the general queue
     const uint32_t qcap = (uint32_t)wave_cap_;
     const int qsel[2] = { 0, fuse == 2 ? 1 : 0 };
 
@@ -548,7 +558,7 @@ bool Engine::path_trace(uint32_t dispatches, uint32_t base_seed) {
                 for (uint32_t b = 0; b < chunk; b++, k++) {
                     const uint32_t par = k & 1u;
                     const Queues qc{ B.q_miss[qsel[par]], B.q_hit[qsel[par]], qcap }, qn{ B.q_miss[qsel[par ^ 1u]], B.q_hit[qsel[par ^ 1u]], qcap };
-                    if (n_vol) { launch_volume_decide(lc_, ds_, pst[cur], B.so, B.counts, par, st); launches++; }
+                    if (pre) { launch_volume_decide(lc_, ds_, dc, pst[cur], B.so, B.counts, par, B.sample_buf, B.rng_carry, st); launches++; }
                     const bool sorted = sort_rays_ && d_order_ != nullptr && k >= 1;   // camera rays are pixel-coherent already
                     if (sorted) { launch_ray_sort(lc_, ds_, pst[cur], B.counts, par, d_sort_key_rank_, d_sort_hist_, d_sort_offs_, d_order_, st); launches += 3; }
                     if (fuse != 2 || k == 0) { launch_extend(lc_, ds_, pst[cur], hitb[par], B.counts, par, qc, d_ctr_, k == 0, sorted ? d_order_ : nullptr, st); launches++; } mark(1);

@@ -21,7 +21,7 @@
 // All per-path state is SoA float4 (coalesced 16-B lanes); live paths are kept dense by compaction.
 #include "bvh_traverse.cuh"
 #include "bvh_dynfetch.cuh"
-#include "volumes.cuh"
+#include "atmosphere.cuh"
 #include "kernels.h"
 #include <cstdio>
 #include <cstdlib>
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(512) k_extend(DevScene sc, PathState ps, float
     // Scenes whose materials all fall into ONE class (and have no volumes) need no per-hit class lookup and only two queues: lane `it` keeps the
     // hit / miss ballots of iteration `it`, one 64-bit atomic reserves room in both (the miss count and the class's hit count are not adjacent
     // words, so two lanes issue one 32-bit atomic each in the same instruction).
-    const bool uniform = sc.uniform_class != 0xFFu && sc.n_volumes == 0u;
+    const bool uniform = sc.uniform_class != 0xFFu && sc.pre_pass == 0u;
     if (uniform) {
         uint32_t *const q_hit_u = q.hit + (size_t)sc.uniform_class * q.cap;
         for (uint32_t seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
@@ -211,8 +211,11 @@ __global__ void __launch_bounds__(512) k_extend(DevScene sc, PathState ps, float
             uint32_t code = Q_NONE;
             float4 o4n = make_float4(0, 0, 0, 0), d4n = o4n;
             if (it + 1u < K && i + blockDim.x < n) { o4n = ps.org_pdf[i + blockDim.x]; d4n = ps.dir_rng[i + blockDim.x]; }   // software pipelining of the state loads
-            if (active && sc.n_volumes && __float_as_uint(hit_out[i].w) == VOLUME_EVENT) {
-                code = 1u + MC_GENERAL;                                     // scattered inside a volume (k_volume_decide): no TraceRay, SH/RayGen.slang:86-90
+            const uint32_t pre = (active && sc.pre_pass) ? __float_as_uint(hit_out[i].w) : 0u;   // k_volume_decide's verdict on this segment
+            if (pre == VOLUME_EVENT) {
+                code = 1u + MC_GENERAL;                                     // scattered inside a volume / the atmosphere: no TraceRay, SH/RayGen.slang:86-90
+            } else if (pre == DEAD_EVENT) {
+                code = Q_NONE;                                              // finished in k_volume_decide (below the planet surface): nothing to queue
             } else if (active) {
                 const float3 rd = normalize_ray(f3(d4));                    // SH/RayGen.slang:70
                 HitRec h;
@@ -251,20 +254,27 @@ __global__ void __launch_bounds__(512) k_extend(DevScene sc, PathState ps, float
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->extend_rays, (unsigned long long)n);
 }
 
+// SH/RayGen.slang:116-128: an unsplit path adds all of pathLight, a path split by an atmosphere event only its colour channel
+__device__ __forceinline__ void add_path_light(float4 &acc, float3 rad, int channel) {
+    if (channel < 0) { acc.x += rad.x; acc.y += rad.y; acc.z += rad.z; }
+    else if (channel == 0) acc.x += rad.x; else if (channel == 1) acc.y += rad.y; else acc.z += rad.z;
+}
 // SH/Miss.slang:8-76 + the ray-gen epilogue for a path whose segment missed (shared by k_shade_miss and the fused bounce kernel's tail)
 __device__ __forceinline__ void finish_missed_path(const DevScene &sc, const DevConfig &cfg, float3 dir, uint32_t rng_state, float4 t4, float4 r4, float payPDF,
                                                    float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry) {
-    const uint32_t depth = __float_as_uint(t4.w) & 0x7FFFFFFFu;
+    const uint32_t depth = __float_as_uint(t4.w) & DEPTH_MASK;
+    const int channel = dflags_channel(__float_as_uint(t4.w));
     float4 c;
-    if (cfg.ShowEnvMapDirectly || depth > 0) {
+    if (cfg.EnableAtmosphere) c = make_float4(0, 0, 0, 1);                  // SH/Miss.slang:11-14: with the atmosphere a miss emits nothing
+    else if (cfg.ShowEnvMapDirectly || depth > 0) {
         float3 r = rotate3_cs(dir, f3(1, 0, 0), cfg.cosAl, -cfg.sinAl);    // Rotate(dir, X, -altitude): cos is even, sin odd
         r = rotate3_cs(r, f3(0, 1, 0), cfg.cosAz, -cfg.sinAz);
         float u, v; direction_to_uv(r, u, v);
         c = env_sample(sc, u, v);
     } else c = make_float4(0, 0, 0, 1);
     float3 em = f3(c.x * cfg.EnvironmentIntensity, c.y * cfg.EnvironmentIntensity, c.z * cfg.EnvironmentIntensity);
-    if (cfg.FurnaceTestMode) em = f3(1.0f);
-    if (cfg.EnableSkyMIS && depth > 0) em = em * power_heuristic(payPDF, c.w);
+    if (cfg.FurnaceTestMode && !cfg.EnableAtmosphere) em = f3(1.0f);
+    if (cfg.EnableSkyMIS && depth > 0 && !cfg.EnableAtmosphere) em = em * power_heuristic(payPDF, c.w);
     // SH/RayGen.slang:92-102 with payload.Depth == MAX_DEPTH (!= 1): the contribution is always luminance-clamped (Q3)
     float3 contribution = em * f3(t4);
     const float lum = dot(contribution, f3(0.212671f, 0.715160f, 0.072169f));
@@ -275,7 +285,7 @@ __device__ __forceinline__ void finish_missed_path(const DevScene &sc, const Dev
     const uint32_t slot = __float_as_uint(r4.w);
     const bool ok = !isinf(rad.x) && !isinf(rad.y) && !isinf(rad.z) && !isnan(rad.x) && !isnan(rad.y) && !isnan(rad.z);   // :116
     float4 acc = sample_buf[slot];
-    if (ok) { acc.x += rad.x; acc.y += rad.y; acc.z += rad.z; }
+    if (ok) add_path_light(acc, rad, channel);
     sample_buf[slot] = acc;
     rng_carry[slot] = rng.s;
 }
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(256) k_shade_miss(DevScene sc, DevConfig cfg, 
 
 // SH/RayGen.slang:92-113 for a path that was shaded at a hit: contribution (luminance clamp unless Depth == 1, Q3), throughput update, Russian
 // roulette (Q4), loop condition.  Returns whether the path continues; a finished path is folded into its sample slot (:116-128).
-__device__ __forceinline__ bool path_epilogue(const DevConfig &cfg, float3 emitted, float4 b4, uint32_t newDepth, float4 thr4, float4 r4, Rng &rng,
+__device__ __forceinline__ bool path_epilogue(const DevConfig &cfg, float3 emitted, float4 b4, uint32_t newDepth, int channel, float4 thr4, float4 r4, Rng &rng,
                                               float3 &thr, float3 &rad, float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry) {
     thr = f3(thr4); rad = f3(r4);
     float3 contribution = emitted * thr;
@@ -321,7 +331,7 @@ __device__ __forceinline__ bool path_epilogue(const DevConfig &cfg, float3 emitt
         const uint32_t slot = __float_as_uint(r4.w);
         const bool ok = !isinf(rad.x) && !isinf(rad.y) && !isinf(rad.z) && !isnan(rad.x) && !isnan(rad.y) && !isnan(rad.z);
         float4 acc = sample_buf[slot];
-        if (ok) { acc.x += rad.x; acc.y += rad.y; acc.z += rad.z; }
+        if (ok) add_path_light(acc, rad, channel);
         sample_buf[slot] = acc;
         rng_carry[slot] = rng.s;
     }
@@ -389,7 +399,8 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.dir_rng + i_nx));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ps.thr_depth + i_nx));
             }
-            const uint32_t depth = dflags & 0x7FFFFFFFu;
+            const uint32_t depth = dflags & DEPTH_MASK;
+            const uint32_t chanBits = dflags & CHANNEL_MASK;           // colour channel of a path split by an atmosphere event (0 = unsplit)
             const bool inMedium = (dflags >> 31) != 0u;
             const float3 payOrigin = f3(o4), payDir = f3(d4);
             const float payPDF = o4.w;
@@ -399,7 +410,7 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
 
             // The sky-NEE draws are the first draws of a hit outside a medium: take them now and put the alias-table load in flight.
             EnvPick ep;
-            const bool envEarly = cfg.EnableSkyMIS && !inMedium;
+            const bool envEarly = cfg.EnableSkyMIS && !inMedium && !cfg.EnableAtmosphere;   // (with the atmosphere the sky sample is the sun disk: no table load to hide)
             if (envEarly) sample_env_begin(sc, rng, ep);
 
             const float3 rd = normalize(payDir);                                // WorldRayDirection()
@@ -479,8 +490,11 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
                 bool need = false;
                 if (k == 0) {
                     if (cfg.EnableSkyMIS) {
-                        if (!envEarly) sample_env_begin(sc, rng, ep);
-                        sample_env_finish(sc, cfg, ep, toW, lv);
+                        if (cfg.EnableAtmosphere) sample_sun_disk(cfg, rng, toW, lv);   // ImportanceSampleSky under ENABLE_ATMOSPHERE (SH/Sampler.slang:465-476)
+                        else {
+                            if (!envEarly) sample_env_begin(sc, rng, ep);
+                            sample_env_finish(sc, cfg, ep, toW, lv);
+                        }
                         lv.x *= cfg.EnvironmentIntensity; lv.y *= cfg.EnvironmentIntensity; lv.z *= cfg.EnvironmentIntensity;   // Q7
                         dk = sf.world_to_tangent(toW);
                         need = lv.w > 0.0f;
@@ -498,9 +512,11 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
                 Eval e; e.BxDF = f3(0.0f); e.PDF = 0.0f;
                 if (need) e = eval_bsdf<LOBES>(m, bc, cfg, V, dk);
                 if (k == 2) { evS = e; break; }
-                // NEE term (added iff the shadow query allows) :326-372
-                if (need && e.PDF > 0.0f) {
-                    const float3 c = (((e.BxDF * 1.0f) * f3(lv)) / lv.w) * power_heuristic(lv.w, e.PDF);
+                // NEE term (added iff the shadow query allows) :326-372.  With the atmosphere on, the sky query is issued even when its term is zero:
+                // k_connect draws the transmittance walk whenever the sun is VISIBLE (SH/ClosestHit.slang:335-349 sits outside the pdf tests)
+                const bool contributes = need && e.PDF > 0.0f;
+                if (contributes || (k == 0 && cfg.EnableAtmosphere && cfg.EnableSkyMIS)) {
+                    const float3 c = contributes ? (((e.BxDF * 1.0f) * f3(lv)) / lv.w) * power_heuristic(lv.w, e.PDF) : f3(0.0f);
                     const float3 ro = (k == 0) ? sf.WorldPos + sf.Normal * 1e-5f : sf.WorldPos + toW * 1e-2f;   // :139, :171
                     if (FUSE) {
                         //   sky   (SH/ClosestHit.slang:139 + :326-358): any hit in (1e-4, 1e6) occludes;
@@ -554,7 +570,7 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
             const uint32_t newDepth = invalid ? PT_MAX_DEPTH + depth : depth + 1u;   // MAX_DEPTH*(invalid) + (Depth + 1*(!invalid))
             if (FUSE) {
                 newO = no; newD = scatterW; b4 = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
-                newDflags = newDepth | (newInMedium ? 0x80000000u : 0u); shaded = true;
+                newDflags = newDepth | chanBits | (newInMedium ? 0x80000000u : 0u); shaded = true;
             } else {
                 if (VOL && reqMask) {                                           // volumes cast shadows on the NEE terms: transmittance from the NEW origin (:332-333, :364)
                     if (reqMask & 1u) { const float T = volumes_transmittance(sc, no, f3(so.sky_d[i])); const float4 c = so.sky_c[i]; so.sky_c[i] = make_float4(c.x * T, c.y * T, c.z * T, 0.0f); }
@@ -563,7 +579,7 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
                 ps.org_pdf[i] = make_float4(no.x, no.y, no.z, ss.PDF);
                 ps.dir_rng[i] = make_float4(scatterW.x, scatterW.y, scatterW.z, __uint_as_float(rng.s));
                 so.bxdf_pdf[i] = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
-                so.e0[i] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(newDepth | (reqMask << 29) | (newInMedium ? 0x80000000u : 0u)));   // bits 29/30: stored shadow requests
+                so.e0[i] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(newDepth | chanBits | (reqMask << 29) | (newInMedium ? 0x80000000u : 0u)));   // bits 29/30: stored shadow requests
             }
         } while (false);
 
@@ -573,7 +589,7 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
             float4 r4 = zero4; float3 thr = f3(0.0f), rad = f3(0.0f);
             if (shaded) {
                 const float4 thr4 = ps.thr_depth[i]; r4 = ps.rad_slot[i];
-                alive = path_epilogue(cfg, emitted, b4, newDflags & 0x7FFFFFFFu, thr4, r4, rng, thr, rad, sample_buf, rng_carry);
+                alive = path_epilogue(cfg, emitted, b4, newDflags & DEPTH_MASK, dflags_channel(newDflags), thr4, r4, rng, thr, rad, sample_buf, rng_carry);
             }
             uint32_t code = Q_NONE; HitRec h; h.t = 0.0f; h.u = 0.0f; h.v = 0.0f; h.gid = 0xFFFFFFFFu;
             if (FUSE == 2 && alive) {
@@ -647,8 +663,13 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
             const float4 e4 = so.e0[i];
             uint32_t pending = (__float_as_uint(e4.w) >> 29) & 3u;         // bit 0: sky request, bit 1: light request (k_shade_hit)
             newDflags = __float_as_uint(e4.w) & 0x9FFFFFFFu;
-            const uint32_t newDepth = newDflags & 0x7FFFFFFFu;
+            const uint32_t newDepth = newDflags & DEPTH_MASK;
+            const int channel = dflags_channel(newDflags);
             float3 emitted = f3(e4);
+            // Atmosphere: a visible sun costs the path a transmittance walk on its own RNG stream, BEFORE the roulette draw (SH/ClosestHit.slang:335-349,
+            // SH/RayGen.slang:328-342,415-422) -- so the new origin and the RNG state are fetched up front instead of after the queries.
+            const bool atm = cfg.EnableAtmosphere != 0u;
+            if (atm) { o4 = src.org_pdf[i]; d4 = src.dir_rng[i]; rng.s = __float_as_uint(d4.w); }
             // Request words are read when needed: the light request after the sky query, a contribution only if its ray came out
             // unoccluded, the path state after both queries -- little is live across the traversal loops.
             // (One resumable loop serving both rays of a lane, if-if style, was measured 1.6x SLOWER than two tight while-while loops.)
@@ -658,7 +679,11 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
             //         the closest-hit query) -- bounded by tL and free to stop at the first occluder.
             if (TRACE) n_shadow += (pending & 1u) + (pending >> 1);
             if (!TRACE) {                                                   // surviving bits = unoccluded requests, joined in the reference's order
-                if (pending & 1u) emitted = emitted + f3(so.sky_c[i]);
+                if (pending & 1u) {
+                    float3 c = f3(so.sky_c[i]);
+                    if (atm) c = c * atm_transmittance_nee(cfg, rng, f3(o4), f3(so.sky_d[i]), channel);
+                    emitted = emitted + c;
+                }
                 if (pending & 2u) emitted = emitted + f3(so.lit_c[i]);
                 pending = 0u;
             }
@@ -667,7 +692,11 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
             if (pending & 1u) {
                 HitRec h;
                 const bool occluded = bvh_trace<SMEM, true, false, false, true>(bv, f3(so4), f3(sd4), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
-                if (!occluded) emitted = emitted + f3(so.sky_c[i]);
+                if (!occluded) {
+                    float3 c = f3(so.sky_c[i]);
+                    if (atm) c = c * atm_transmittance_nee(cfg, rng, f3(o4), f3(sd4), channel);
+                    emitted = emitted + c;
+                }
             }
             if (pending & 2u) {
                 const float4 lo4 = so.lit_o[i], ld4_ = so.lit_d[i];
@@ -683,10 +712,9 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
             }
             // the path state is fetched only now: nothing but the emission and the request bits is live across the traversal loop
             const float4 thr4 = src.thr_depth[i]; r4 = src.rad_slot[i];
-            o4 = src.org_pdf[i]; d4 = src.dir_rng[i];
+            if (!atm) { o4 = src.org_pdf[i]; d4 = src.dir_rng[i]; rng.s = __float_as_uint(d4.w); }
             const float4 b4 = so.bxdf_pdf[i];
-            rng.s = __float_as_uint(d4.w);
-            alive = path_epilogue(cfg, emitted, b4, newDepth, thr4, r4, rng, thr, rad, sample_buf, rng_carry);
+            alive = path_epilogue(cfg, emitted, b4, newDepth, channel, thr4, r4, rng, thr, rad, sample_buf, rng_carry);
         }
         // ---- warp ballot + prefix-sum compaction of the live paths
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, alive);
@@ -754,8 +782,11 @@ __global__ void __launch_bounds__(256) k_extend_dyn(DevScene sc, PathState ps, f
             const uint32_t idx = pool.take(need, lane, fetch);
             if (fin) {
                 i = (order != nullptr && idx != DYN_NONE) ? order[idx] : idx;   // sorted bounce: the pool hands out positions of the sorted list (k_ray_sort_*)
-                if (i != DYN_NONE && sc.n_volumes && __float_as_uint(hit_out[i].w) == VOLUME_EVENT) {
-                    r.gid = VOLUME_EVENT;                                   // scattered inside a volume (k_volume_decide): queued as a hit at the next commit, record kept
+                const uint32_t pre = (i != DYN_NONE && sc.pre_pass) ? __float_as_uint(hit_out[i].w) : 0u;
+                if (pre == VOLUME_EVENT) {
+                    r.gid = VOLUME_EVENT;                                   // scattered inside a volume / the atmosphere (k_volume_decide): queued as a hit at the next commit, record kept
+                } else if (pre == DEAD_EVENT) {
+                    i = DYN_NONE;                                           // finished in k_volume_decide: the lane takes no ray this round
                 } else if (i != DYN_NONE) {
                     const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
                     const float3 rd = normalize_ray(f3(d4));                // SH/RayGen.slang:70
@@ -923,7 +954,8 @@ __global__ void __launch_bounds__(256, 4) k_shadow_dyn(DevScene sc, ShadeOut so,
 // k_volume_decide / k_shade_volume : homogeneous AABB volumes (volumes.cuh; SH/RayGen.slang:162-380)
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM>
-__global__ void __launch_bounds__(256) k_volume_decide(DevScene sc, PathState ps, ShadeOut so, const uint32_t *__restrict__ ctrl, uint32_t parity, int max_stack) {
+__global__ void __launch_bounds__(256) k_volume_decide(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so, const uint32_t *__restrict__ ctrl, uint32_t parity, int max_stack,
+                                                        float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     int *stack = reinterpret_cast<int *>(smem) + threadIdx.x;
@@ -935,18 +967,44 @@ __global__ void __launch_bounds__(256) k_volume_decide(DevScene sc, PathState ps
         const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
         const float3 o = f3(o4), d = f3(d4);
         Rng rng; rng.s = __float_as_uint(d4.w);
+        if (cfg.EnableAtmosphere && atm_height(cfg, o) < 0.0f) {            // SH/RayGen.slang:76-84: below the surface of the planet -> the path loop breaks (no roulette draw)
+            const float4 t4 = ps.thr_depth[i], r4 = ps.rad_slot[i];
+            const float3 rad = f3(r4);
+            const uint32_t slot = __float_as_uint(r4.w);
+            const bool ok = !isinf(rad.x) && !isinf(rad.y) && !isinf(rad.z) && !isnan(rad.x) && !isnan(rad.y) && !isnan(rad.z);
+            float4 acc = sample_buf[slot];
+            if (ok) add_path_light(acc, rad, dflags_channel(__float_as_uint(t4.w)));
+            sample_buf[slot] = acc; rng_carry[slot] = rng.s;
+            so.hit[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(DEAD_EVENT));
+            continue;
+        }
         HitRec h;                                                           // GetDistanceToGeometry (SH/RTCommon.slang:86-100): payload.Direction as is, tmin 1e-5, tmax 1e6
         const bool found = bvh_trace<SMEM, false>(bv, o, d, 0.00001f, 1000000.0f, h, stack, (int)blockDim.x, max_stack);
         const float distanceToGeometry = found ? h.t : -1.0f;
         int vi = -1;
-        const float sd = volumes_free_flight(sc, o, d, rng, vi);            // :164-209
+        float sd = volumes_free_flight(sc, o, d, rng, vi);                  // :164-209
+        if (cfg.EnableAtmosphere) {                                         // :212-236: channel pick (while unsplit), delta tracking on that channel
+            const uint32_t dflags = __float_as_uint(ps.thr_depth[i].w);
+            int channel = dflags_channel(dflags);
+            if (channel < 0) { const float pick = rng.next(); channel = pick < 0.33333f ? 0 : (pick < 0.66666f ? 1 : 2); }
+            int component = -1;
+            const float ta = atm_sample_scatter_distance(cfg, rng, o, d, channel, component);
+            if (ta >= 0.0f && (ta < sd || sd < 0.0f)) {
+                sd = ta; vi = -2 - component;                               // the atmosphere scattered first: event code -2 (Rayleigh) / -3 (Mie) / -4 (ozone)
+                if (distanceToGeometry < 0.0f || sd < distanceToGeometry) {  // the event will happen: the ray is split to this channel from now on (:244)
+                    float4 t4 = ps.thr_depth[i];
+                    t4.w = __uint_as_float((dflags & ~CHANNEL_MASK) | ((uint32_t)(channel + 1) << CHANNEL_SHIFT));
+                    ps.thr_depth[i] = t4;
+                }
+            }
+        }
         ps.dir_rng[i] = make_float4(d4.x, d4.y, d4.z, __uint_as_float(rng.s));
         const bool ev = sd >= 0.0f && (distanceToGeometry < 0.0f || sd < distanceToGeometry);   // :236
         so.hit[i] = ev ? make_float4(sd, __int_as_float(vi), 0.0f, __uint_as_float(VOLUME_EVENT)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
-// EvaluateVolumeScatteringEvent (SH/RayGen.slang:265-380) for the flagged entries of the hit queue
+// EvaluateVolumeScatteringEvent (SH/RayGen.slang:265-380) / EvaluateAtmosphereScatteringEvent (:382-471) for the flagged entries of the hit queue
 __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg, PathState ps, ShadeOut so, const uint32_t *__restrict__ ctrl, uint32_t parity,
                                                       Queues q, WaveCounters *ctr) {
     const uint32_t n = ctrl[CTRL_Q + 8u * parity + 1u + MC_GENERAL];          // volume events are queued with the general class (hit_code)
@@ -960,14 +1018,52 @@ __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg
         const float4 o4 = ps.org_pdf[i], d4 = ps.dir_rng[i];
         const uint32_t dflags = __float_as_uint(ps.thr_depth[i].w);
         Rng rng; rng.s = __float_as_uint(d4.w);
-        const DevVolume v = sc.volumes[__float_as_int(h4.y)];
-        const float3 dir = f3(d4), color = f3(v.color_alpha);
-        const float3 origin = f3(o4) + dir * h4.x;                          // :267
+        const float3 dir = f3(d4);
+        const float3 origin = f3(o4) + dir * h4.x;                          // :267 / :384
+        const int code = __float_as_int(h4.y);
+        if (code <= -2) {                                                   // ---- atmosphere event
+            const int component = -2 - code;
+            float3 newDir;
+            if (component == 0) newDir = sample_rayleigh(rng, dir);
+            else if (component == 1) newDir = sample_henyey_greenstein(rng, dir, 0.85f);
+            else newDir = dir;                                              // ozone only absorbs
+            const float C_MIE_ABS = 4.40f * 1e-6f, C_MIE = 3.996f * 1e-6f + 4.40f * 1e-6f;
+            float3 bx; float pdf; uint32_t reqMask = 0u;
+            if (cfg.EnableSkyMIS) {                                         // :403-446
+                float3 toSun; float4 cp;
+                sample_sun_disk(cfg, rng, toSun, cp);
+                cp.x *= cfg.EnvironmentIntensity; cp.y *= cfg.EnvironmentIntensity; cp.z *= cfg.EnvironmentIntensity;
+                const float3 col = f3(cp) / cp.w;
+                float ph = 0.0f;
+                if (component == 0) { ph = phase_rayleigh(dir, toSun); const float pn = phase_rayleigh(dir, newDir); bx = f3(pn); pdf = pn; }
+                else if (component == 1) { ph = phase_hg(dir, toSun, 0.85f); const float att = C_MIE_ABS / C_MIE; const float pn = phase_hg(dir, newDir, 0.85f); bx = f3(pn * (1.0f - att)); pdf = pn; }
+                else { bx = f3(0.0f); pdf = 1.0f; }
+                // the sun query is always issued: its transmittance walk is drawn whenever the sun is visible (:415-422); k_connect multiplies by it
+                const float Tv = volumes_transmittance(sc, origin, toSun);
+                const float3 c = (f3(Tv) * ph) * col;
+                so.sky_o[i] = make_float4(origin.x, origin.y, origin.z, 1.0f);
+                so.sky_d[i] = make_float4(toSun.x, toSun.y, toSun.z, __uint_as_float(0xFFFFFFFFu));
+                so.sky_c[i] = make_float4(c.x, c.y, c.z, 0.0f);
+                reqMask = 1u;
+            } else {                                                        // :447-461
+                if (component == 0) { const float pn = phase_rayleigh(dir, newDir); bx = f3(pn); pdf = pn; }
+                else { const float att = C_MIE_ABS / C_MIE; bx = f3(phase_mie_approx(dir, newDir, 0.85f) * att); pdf = phase_hg(dir, newDir, 0.85f); }
+            }
+            const uint32_t newDepth = (dflags & DEPTH_MASK) + 1u;           // :470 (VolumeDepth untouched)
+            ps.org_pdf[i] = make_float4(origin.x, origin.y, origin.z, pdf);
+            ps.dir_rng[i] = make_float4(newDir.x, newDir.y, newDir.z, __uint_as_float(rng.s));
+            so.bxdf_pdf[i] = make_float4(bx.x, bx.y, bx.z, pdf);
+            so.e0[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(newDepth | (dflags & (0x80000000u | CHANNEL_MASK)) | (reqMask << 29)));
+            continue;
+        }
+        const DevVolume v = sc.volumes[code];
+        const float3 color = f3(v.color_alpha);
         const int vdepth = (int)ps.vol_depth[i];
         const float3 emitted = f3(v.emis_droplet);                          // :268 (no temperature grid)
         float3 toSky = f3(0.0f), toLight = f3(0.0f); float4 sky = make_float4(0, 0, 0, 0), light = sky; uint32_t lgid = 0xFFFFFFFFu;
         if (cfg.EnableSkyMIS) {                                             // :273-287
-            EnvPick ep; sample_env_begin(sc, rng, ep); sample_env_finish(sc, cfg, ep, toSky, sky);
+            if (cfg.EnableAtmosphere) sample_sun_disk(cfg, rng, toSky, sky);
+            else { EnvPick ep; sample_env_begin(sc, rng, ep); sample_env_finish(sc, cfg, ep, toSky, sky); }
             sky.x *= cfg.EnvironmentIntensity; sky.y *= cfg.EnvironmentIntensity; sky.z *= cfg.EnvironmentIntensity;   // Q7 again (:277)
         }
         if (cfg.EnableMeshMIS) sample_emissive(sc, rng, origin, toLight, light, lgid);   // :294-308
@@ -978,9 +1074,9 @@ __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg
         // :319-369 are added by k_connect iff the query comes out clear (sky: any hit occludes; light: the sampled triangle must be the closest hit)
         if (cfg.EnableSkyMIS && sky.w > 0.0f) {
             const float ph = vol_phase(sc.phase_function, v, dir, toSky, vdepth);
-            if (ph > 0.0f) {
+            if (ph > 0.0f || cfg.EnableAtmosphere) {                        // atmosphere: the query decides whether the transmittance walk is drawn (:328-342), even for a zero term
                 const float T = volumes_transmittance(sc, origin, toSky);
-                const float3 c = ((f3(T) * (color * ph)) * (f3(sky) / sky.w)) * power_heuristic(sky.w, ph);
+                const float3 c = ph > 0.0f ? ((f3(T) * (color * ph)) * (f3(sky) / sky.w)) * power_heuristic(sky.w, ph) : f3(0.0f);
                 so.sky_o[i] = make_float4(origin.x, origin.y, origin.z, 1.0f);
                 so.sky_d[i] = make_float4(toSky.x, toSky.y, toSky.z, __uint_as_float(0xFFFFFFFFu));
                 so.sky_c[i] = make_float4(c.x, c.y, c.z, 0.0f);
@@ -998,11 +1094,11 @@ __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg
                 reqMask |= 2u;
             }
         }
-        const uint32_t newDepth = (dflags & 0x7FFFFFFFu) + 1u;              // :377
+        const uint32_t newDepth = (dflags & DEPTH_MASK) + 1u;               // :377
         ps.org_pdf[i] = make_float4(origin.x, origin.y, origin.z, phaseS);  // payload.PDF = phase (:374)
         ps.dir_rng[i] = make_float4(newDir.x, newDir.y, newDir.z, __uint_as_float(rng.s));
         so.bxdf_pdf[i] = make_float4(color.x * phaseS, color.y * phaseS, color.z * phaseS, phaseS);
-        so.e0[i] = make_float4(emitted.x, emitted.y, emitted.z, __uint_as_float(newDepth | (dflags & 0x80000000u) | (reqMask << 29)));
+        so.e0[i] = make_float4(emitted.x, emitted.y, emitted.z, __uint_as_float(newDepth | (dflags & (0x80000000u | CHANNEL_MASK)) | (reqMask << 29)));
         ps.vol_depth[i] = (uint32_t)(vdepth + 1);                           // :378
     }
     for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xFFFFFFFFu, n_ev, o);
@@ -1274,19 +1370,20 @@ int launch_shade(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, 
         if (fuse == 2 && lc.big) k_shade_hit<C, false, 2, true><<<lc.grid_bounce, 512, shb, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr); \
         else if (fuse == 2) k_shade_hit<C, false, 2><<<lc.grid_bounce, 128, shb, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr);      \
         else if (fuse == 1) k_shade_hit<C, false, 1><<<lc.grid_bounce, 128, shb, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr); \
-        else if (sc.n_volumes) k_shade_hit<C, true, 0><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr);   \
+        else if (sc.pre_pass) k_shade_hit<C, true, 0><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr);   \
         else k_shade_hit<C, false, 0><<<lc.grid_shade, 128, 0, st>>>(sc, cfg, ps, dst, so, hit_in, hit_out, ctrl, parity, q, q_next, sample_buf, rng_carry, lc.max_stack, ctr); } } while (0)
     B200PT_SHADE(MC_DIFFUSE); B200PT_SHADE(MC_METAL); B200PT_SHADE(MC_GLASS); B200PT_SHADE(MC_GENERAL);
 #undef B200PT_SHADE
-    if (sc.n_volumes) { launched++; k_shade_volume<<<lc.grid_light, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q, ctr); }
+    if (sc.pre_pass) { launched++; k_shade_volume<<<lc.grid_light, 128, 0, st>>>(sc, cfg, ps, so, ctrl, parity, q, ctr); }
     return launched;
 }
-void launch_volume_decide(const LaunchCfg &lc, const DevScene &sc, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity, cudaStream_t st) {
+void launch_volume_decide(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState ps, ShadeOut so, const uint32_t *ctrl, uint32_t parity,
+                          float4 *sample_buf, uint32_t *rng_carry, cudaStream_t st) {
     set_attrs_for_current_device();
     const bool smem = lc.bvh_in_smem;
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, 256, smem);
-    if (smem) k_volume_decide<true><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, lc.max_stack);
-    else k_volume_decide<false><<<lc.grid_trace, 256, sh, st>>>(sc, ps, so, ctrl, parity, lc.max_stack);
+    if (smem) k_volume_decide<true><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, ps, so, ctrl, parity, lc.max_stack, sample_buf, rng_carry);
+    else k_volume_decide<false><<<lc.grid_trace, 256, sh, st>>>(sc, cfg, ps, so, ctrl, parity, lc.max_stack, sample_buf, rng_carry);
 }
 void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cfg, PathState src, PathState dst, ShadeOut so,
                     uint32_t *ctrl, uint32_t parity, Queues q, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
