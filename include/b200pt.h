@@ -123,33 +123,57 @@ int32_t b200pt_camera_from_view(const float view[16], float aspect, float view_i
 int32_t b200pt_resize(b200pt_handle h, uint32_t width, uint32_t height);   /* ResizeImage */
 int32_t b200pt_get_size(b200pt_handle h, uint32_t *width, uint32_t *height);
 int32_t b200pt_reset(b200pt_handle h);                                      /* ResetPathTracing */
-/* ---- volumes: PathTracer::AddVolume / RemoveVolume / SetVolume / GetVolumes / SetPhaseFunction (PathTracer.h:36-81,157-166,
- * PathTracer.cpp:1334-1345,1518-1555).  Homogeneous AABB volumes are implemented (SH/Volume.slang with m_DensityDataIndex == -1,
- * SH/RayGen.slang:162-380): free-flight sampling against the geometry distance, phase-function scattering with sky / light NEE, and
- * analytic transmittance on the NEE terms of surface hits.  Heterogeneous (NanoVDB) density / temperature data is not:
- * DensityDataIndex must be -1 and b200pt_add_density_data_to_volume returns B200PT_ERR_NOT_IMPLEMENTED.  At most B200PT_MAX_VOLUMES. */
-#define B200PT_MAX_VOLUMES 100   /* the reference sorts into float distances[100] (RayGen.slang:165) */
+/* ---- volumes: PathTracer::AddVolume / RemoveVolume / SetVolume / GetVolumes / SetPhaseFunction / AddDensityDataToVolume /
+ * RemoveDensityDataFromVolume (PathTracer.h:36-81,157-166, PathTracer.cpp:1334-1555).  Homogeneous AABB volumes (SH/Volume.slang with
+ * m_DensityDataIndex == -1, SH/RayGen.slang:162-380): free-flight sampling against the geometry distance, phase-function scattering with sky /
+ * light NEE, analytic transmittance on the NEE terms.  Heterogeneous volumes (SH/Volume.slang:54-166,230-252,291-352,448-517): delta tracking
+ * against the 32^3 grid of majorants, ratio-tracked NEE transmittance on the path's own random stream, blackbody / coloured emission from the
+ * temperature data -- over a DENSE copy of the values the reference keeps in a NanoVDB buffer (b200pt_add_density_grid_to_volume).  Reading
+ * .vdb files needs OpenVDB (a vcpkg dependency of the reference, absent here): b200pt_add_density_data_to_volume returns NOT_IMPLEMENTED, the
+ * adapter reads the file with the reference's own OpenVDB and hands the values over.  At most B200PT_MAX_VOLUMES. */
+#define B200PT_MAX_VOLUMES 100   /* the reference sorts into float distances[100] (RayGen.slang:165); also MAX_HETEROGENEOUS_VOLUMES (PathTracer.h:195) */
 typedef struct {                         /* PathTracer::Volume, PT/PathTracer.h:36-70 (defaults in comments) */
-    float CornerMin[3], CornerMax[3];    /* AABB in world space (-1 / +1)      */
+    float CornerMin[3], CornerMax[3];    /* local AABB (-1 / +1); overwritten by b200pt_add_density_grid_to_volume (PathTracer.cpp:1408-1420) */
+    float Position[3], Scale[3];         /* (0 / 1): world AABB = Position + Corner * Scale (VolumeGPU's constructor, PathTracer.h:396-397) */
     float Color[3];                      /* scattering albedo (0.8)            */
     float EmissiveColor[3];              /* (0)                                */
-    float Density;                       /* extinction coefficient (1)         */
+    float TemperatureColor[3];           /* emission colour when UseBlackbody == 0 (1, 0.5, 0) */
+    float Density;                       /* extinction coefficient (1); scales the grid values of a heterogeneous volume */
     float Anisotropy;                    /* g of Henyey-Greenstein / Draine (0)*/
     float Alpha;                         /* Draine alpha (1)                   */
     float DropletSize;                   /* HG + Draine fit, micrometres (20)  */
-    int32_t DensityDataIndex;            /* -1 = homogeneous (only value accepted) */
-    uint32_t ApproximatedScatteringForClouds; /* anisotropy decays with the volume depth (0) */
-    float ApproximatedScatteringFalloff; /* (0.8) unused by homogeneous volumes */
-    uint32_t _reserved;
+    int32_t DensityDataIndex;            /* READ-ONLY: -1 = homogeneous, else the slot b200pt_add_density_grid_to_volume assigned (PathTracer.cpp:1512-1513); add / set ignore it */
+    float MaxDensityInTheGrid;           /* READ-ONLY (PathTracer.cpp:1393-1394) */
+    int32_t UseBlackbody;                /* (1) blackbody colour from the Kelvin range, else TemperatureColor */
+    int32_t HasTemperatureData;          /* READ-ONLY: the density data came with a temperature grid (PathTracer.h:398) */
+    float TemperatureGamma, TemperatureScale, EmissiveColorGamma;   /* (1, 1, 1) */
+    int32_t KelvinMin, KelvinMax;        /* (500, 8000) */
+    uint32_t ApproximatedScatteringForClouds; /* anisotropy / density decay with the depth (0) */
+    float ApproximatedScatteringFalloff; /* (0.8) */
+    float GridSharpness;                 /* (1) multiplies the normalised grid value before the clamp to [0, 1] */
 } b200pt_volume;
 int32_t b200pt_default_volume(b200pt_volume *out);
 int32_t b200pt_add_volume(b200pt_handle h, const b200pt_volume *volume);                 /* AddVolume  -> ResetPathTracing() */
-int32_t b200pt_set_volume(b200pt_handle h, uint32_t index, const b200pt_volume *volume); /* SetVolume  -> ResetPathTracing() */
+int32_t b200pt_set_volume(b200pt_handle h, uint32_t index, const b200pt_volume *volume); /* SetVolume  -> ResetPathTracing(); density data stays attached to the index */
 int32_t b200pt_remove_volume(b200pt_handle h, uint32_t index);                           /* RemoveVolume (later volumes move down one index) */
 int32_t b200pt_volume_count(b200pt_handle h, uint32_t *out);
 int32_t b200pt_get_volume(b200pt_handle h, uint32_t index, b200pt_volume *out);          /* GetVolumes()[index] */
-int32_t b200pt_add_density_data_to_volume(b200pt_handle h, uint32_t index, const char *vdb_path);   /* AddDensityDataToVolume: NOT_IMPLEMENTED */
-int32_t b200pt_remove_density_data_from_volume(b200pt_handle h, uint32_t index);                    /* RemoveDensityDataFromVolume: NOT_IMPLEMENTED */
+/* Density data of a heterogeneous volume: what AddDensityDataToVolume holds after openvdb::io::File::readGrid (PathTracer.cpp:1361-1406) --
+ * the "density" FloatGrid (and "temperature" / "flames") over the density grid's active-voxel bounding box. */
+typedef struct {
+    int32_t IndexMin[3];                 /* evalActiveVoxelBoundingBox().min() */
+    uint32_t Dim[3];                     /* evalActiveVoxelDim() */
+    const float *Density;                /* Dim[0]*Dim[1]*Dim[2] floats, x fastest: tree().getValue(IndexMin + (x, y, z)) */
+    const float *Temperature;            /* NULL, or the temperature grid's values at the same coordinates */
+    float TemperatureMin, TemperatureMax;/* tools::minMax of the temperature grid's active values (PathTracer.cpp:1403-1404); Min >= Max: taken from the array */
+    double VoxelSize;                    /* the density grid's index-to-world map: uniform scale ... */
+    double Translation[3];               /* ... and translation (identity: 1, {0, 0, 0}) */
+} b200pt_density_grid;
+int32_t b200pt_add_density_grid_to_volume(b200pt_handle h, uint32_t index, const b200pt_density_grid *grid);   /* AddDensityDataToVolume after the file read (PathTracer.cpp:1391-1515) -> ResetPathTracing() */
+int32_t b200pt_add_density_data_to_volume(b200pt_handle h, uint32_t index, const char *vdb_path);   /* AddDensityDataToVolume(filepath): NOT_IMPLEMENTED (needs OpenVDB) */
+int32_t b200pt_remove_density_data_from_volume(b200pt_handle h, uint32_t index);                    /* RemoveDensityDataFromVolume (PathTracer.cpp:1518-1528): homogeneous again, corners back to -1 / +1 */
+/* host half of b200pt_add_density_grid_to_volume (test hook, no GPU needed): the temperature-patched values, the 32^3 majorants, the AABB corners, MaxDensityInTheGrid */
+int32_t b200pt_prepare_density_grid(const b200pt_density_grid *grid, float *values_out, float *max_densities_out, float corner_min[3], float corner_max[3], float *max_density_in_the_grid);
 /* ---- atmosphere: the twelve setters / getters of PathTracer.h:129-144,170-181 (members :221-232) as one parameter block; any set ->
  * ResetPathTracing().  Enable != 0 renders with the reference's atmosphere (SH/Atmosphere.slang, SH/RayGen.slang:76-84,212-255,382-471): a miss
  * emits nothing, the sky NEE samples the sun disk (direction from SkyRotationAzimuth / Altitude), Rayleigh / Mie / ozone events are found by delta

@@ -33,7 +33,15 @@ class OrcSceneDesc(C.Structure):
 class OrcVolume(C.Structure):
     _fields_ = [("CornerMin", C.c_float * 3), ("CornerMax", C.c_float * 3), ("Color", C.c_float * 3), ("EmissiveColor", C.c_float * 3),
                 ("Density", C.c_float), ("Anisotropy", C.c_float), ("Alpha", C.c_float), ("DropletSize", C.c_float),
-                ("ApproximatedScattering", C.c_uint32), ("_pad", C.c_uint32)]
+                ("ApproximatedScattering", C.c_uint32), ("ApproximatedScatteringFalloff", C.c_float), ("TemperatureColor", C.c_float * 3),
+                ("DensityDataIndex", C.c_int32), ("MaxDensityInTheGrid", C.c_float), ("UseBlackbody", C.c_int32), ("HasTemperatureData", C.c_int32),
+                ("TemperatureGamma", C.c_float), ("TemperatureScale", C.c_float), ("EmissiveColorGamma", C.c_float),
+                ("KelvinMin", C.c_int32), ("KelvinMax", C.c_int32), ("GridSharpness", C.c_float)]
+
+
+class OrcGrid(C.Structure):
+    _fields_ = [("Values", C.c_void_p), ("MaxDensities", C.c_void_p), ("IndexMin", C.c_int32 * 3), ("Dim", C.c_uint32 * 3), ("WorldBBox", C.c_double * 6),
+                ("InvVoxelSize", C.c_float * 3), ("Translation", C.c_float * 3)]
 
 
 class OrcConfig(C.Structure):
@@ -50,7 +58,7 @@ class OrcConfig(C.Structure):
                 ("RayleighScatteringCoefficientMultiplier", C.c_float * 3), ("MieScatteringCoefficientMultiplier", C.c_float * 3),
                 ("OzoneAbsorptionCoefficientMultiplier", C.c_float * 3),
                 ("RayleighDensityFalloff", C.c_float), ("MieDensityFalloff", C.c_float), ("OzoneDensityFalloff", C.c_float), ("OzonePeak", C.c_float),
-                ("SunColor", C.c_float * 3)]
+                ("SunColor", C.c_float * 3), ("GridCount", C.c_uint32), ("Grids", C.c_void_p)]
 
 
 class OrcCounters(C.Structure):
@@ -125,6 +133,9 @@ def lib():
         L.orc_build_env_alias.restype = C.c_float; L.orc_build_env_alias.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_camera_from_view.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.orc_default_config.argtypes = [C.POINTER(OrcConfig)]
+        L.orc_grid_transmittance.restype = C.c_float; L.orc_grid_transmittance.argtypes = [C.POINTER(OrcConfig), C.c_uint32, C.c_void_p, C.c_void_p, C.c_float]
+        L.orc_grid_sample.restype = C.c_float; L.orc_grid_sample.argtypes = [C.POINTER(OrcConfig), C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_blackbody.restype = None; L.orc_blackbody.argtypes = [C.c_float, C.c_void_p]
         L.orc_load_hdr.restype = C.c_void_p; L.orc_load_hdr.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_scene_create.restype = C.c_void_p; L.orc_scene_create.argtypes = [C.POINTER(OrcSceneDesc)]
@@ -185,22 +196,70 @@ def camera_from_view(view16, aspect):
     return vi, pi
 
 
-VOLUME_DEFAULTS = dict(CornerMin=(-1.0, -1.0, -1.0), CornerMax=(1.0, 1.0, 1.0), Color=(0.8, 0.8, 0.8), EmissiveColor=(0.0, 0.0, 0.0),
-                       Density=1.0, Anisotropy=0.0, Alpha=1.0, DropletSize=20.0, ApproximatedScattering=0)   # PT/PathTracer.h:36-70
+VOLUME_DEFAULTS = dict(CornerMin=(-1.0, -1.0, -1.0), CornerMax=(1.0, 1.0, 1.0), Position=(0.0, 0.0, 0.0), Scale=(1.0, 1.0, 1.0), Color=(0.8, 0.8, 0.8),
+                       EmissiveColor=(0.0, 0.0, 0.0), TemperatureColor=(1.0, 0.5, 0.0), Density=1.0, Anisotropy=0.0, Alpha=1.0, DropletSize=20.0,
+                       UseBlackbody=1, TemperatureGamma=1.0, TemperatureScale=1.0, EmissiveColorGamma=1.0, KelvinMin=500, KelvinMax=8000,
+                       ApproximatedScattering=0, ApproximatedScatteringFalloff=0.8, GridSharpness=1.0, Grid=None)   # PT/PathTracer.h:36-70
+
+
+def prepare_density_grid(density, index_min=(0, 0, 0), temperature=None, voxel_size=1.0, translation=(0.0, 0.0, 0.0), temperature_range=None):
+    """AddDensityDataToVolume after the file read (PT/PathTracer.cpp:1391-1452) through orc_prepare_density_grid.  density / temperature: float32
+    arrays [z][y][x] over the active-voxel bbox whose minimum index coordinate is index_min (tree().getValue at every coordinate of the bbox);
+    voxel_size / translation: the grid's (uniform, axis-aligned) index-to-world map.  Returns the dict set_volumes' "Grid" key wants."""
+    vals = np.array(density, dtype=np.float32, order="C", copy=True)
+    dz, dy, dx = vals.shape
+    temp = None if temperature is None else np.ascontiguousarray(temperature, dtype=np.float32)
+    if temp is not None: assert temp.shape == vals.shape
+    tmin, tmax = (0.0, 0.0) if temp is None else ((float(temp.min()), float(temp.max())) if temperature_range is None else temperature_range)
+    imin = (C.c_int32 * 3)(*[int(v) for v in index_min]); dim = (C.c_uint32 * 3)(dx, dy, dz)
+    maj = np.zeros(32768, np.float32); cmin = (C.c_float * 3)(); cmax = (C.c_float * 3)(); mx = C.c_float()
+    L = lib()
+    L.orc_prepare_density_grid.restype = None
+    L.orc_prepare_density_grid(imin, dim, vals.ctypes.data_as(C.c_void_p), None if temp is None else temp.ctypes.data_as(C.c_void_p), C.c_float(tmin), C.c_float(tmax),
+                               maj.ctypes.data_as(C.c_void_p), cmin, cmax, C.byref(mx))
+    vs = float(voxel_size); tr = [float(t) for t in translation]
+    wb = [index_min[k] * vs + tr[k] for k in range(3)] + [(index_min[k] + (dx, dy, dz)[k]) * vs + tr[k] for k in range(3)]   # NanoVDB GridStats: [min, max + 1] through the map
+    return dict(values=vals, max_densities=maj, index_min=tuple(int(v) for v in index_min), dim=(dx, dy, dz), world_bbox=wb,
+                inv_voxel_size=np.float32(1.0 / vs), translation=tuple(np.float32(t) for t in tr), corner_min=tuple(cmin), corner_max=tuple(cmax),
+                max_density=mx.value, has_temperature=temp is not None,
+                source=dict(density=np.array(density, dtype=np.float32), index_min=tuple(int(v) for v in index_min), temperature=temp, voxel_size=vs,
+                            translation=tuple(tr), temperature_range=(tmin, tmax)))
 
 
 def set_volumes(cfg, volumes):
-    """Attach homogeneous AABB volumes (list of dicts with the VOLUME_DEFAULTS keys) to an OrcConfig; the array is kept alive on cfg."""
+    """Attach AABB volumes (list of dicts with the VOLUME_DEFAULTS keys) to an OrcConfig; the arrays are kept alive on cfg.  A volume whose "Grid" is a
+    prepare_density_grid() result is heterogeneous: its corners, MaxDensityInTheGrid and DensityDataIndex come from the grid (PathTracer.cpp:1408-1420,1512),
+    and the world AABB is Position + Corner * Scale in float32 (VolumeGPU's constructor, PT/PathTracer.h:396-397)."""
     arr = (OrcVolume * max(1, len(volumes)))()
+    grids = [v["Grid"] for v in volumes if v.get("Grid") is not None]
+    garr = (OrcGrid * max(1, len(grids)))()
+    gi = 0
     for i, v in enumerate(volumes):
         d = dict(VOLUME_DEFAULTS); d.update(v)
-        for k in ("CornerMin", "CornerMax", "Color", "EmissiveColor"):
+        g = d["Grid"]
+        if g is not None: d["CornerMin"], d["CornerMax"] = g["corner_min"], g["corner_max"]
+        pos, scl = np.array(d["Position"], np.float32), np.array(d["Scale"], np.float32)
+        lo = pos + np.array(d["CornerMin"], np.float32) * scl; hi = pos + np.array(d["CornerMax"], np.float32) * scl
+        for j in range(3): arr[i].CornerMin[j] = lo[j]; arr[i].CornerMax[j] = hi[j]
+        for k in ("Color", "EmissiveColor", "TemperatureColor"):
             for j in range(3): getattr(arr[i], k)[j] = float(d[k][j])
-        for k in ("Density", "Anisotropy", "Alpha", "DropletSize"): setattr(arr[i], k, float(d[k]))
-        arr[i].ApproximatedScattering = int(d["ApproximatedScattering"])
-    cfg._volumes_keepalive = arr
+        for k in ("Density", "Anisotropy", "Alpha", "DropletSize", "ApproximatedScatteringFalloff", "TemperatureGamma", "TemperatureScale", "EmissiveColorGamma", "GridSharpness"):
+            setattr(arr[i], k, float(d[k]))
+        for k in ("ApproximatedScattering", "UseBlackbody", "KelvinMin", "KelvinMax"): setattr(arr[i], k, int(d[k]))
+        arr[i].DensityDataIndex = -1; arr[i].MaxDensityInTheGrid = 0.0; arr[i].HasTemperatureData = 0
+        if g is not None:
+            G = garr[gi]
+            G.Values = g["values"].ctypes.data; G.MaxDensities = g["max_densities"].ctypes.data
+            for j in range(3):
+                G.IndexMin[j] = g["index_min"][j]; G.Dim[j] = g["dim"][j]; G.InvVoxelSize[j] = g["inv_voxel_size"]; G.Translation[j] = g["translation"][j]
+            for j in range(6): G.WorldBBox[j] = g["world_bbox"][j]
+            arr[i].DensityDataIndex = gi; arr[i].MaxDensityInTheGrid = g["max_density"]; arr[i].HasTemperatureData = int(g["has_temperature"])
+            gi += 1
+    cfg._volumes_keepalive = (arr, garr, grids)
     cfg.Volumes = C.cast(arr, C.c_void_p).value if volumes else None
     cfg.VolumesCount = len(volumes)
+    cfg.Grids = C.cast(garr, C.c_void_p).value if grids else None
+    cfg.GridCount = len(grids)
     return cfg
 
 

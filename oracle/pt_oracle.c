@@ -998,28 +998,170 @@ static float vol_phase(const OrcConfig *cfg, const OrcVolume *v, v3 V, v3 L, int
     float GHG, GD, AD, WD; hg_draine_fit(v->DropletSize, &GHG, &GD, &AD, &WD);
     return orc_lerp(phase_hg(V, L, GHG), phase_draine(V, L, GD, AD), WD);
 }
-/* Volume::CalculateVolumesTransmittance, SH/Volume.slang:419-446: analytic for homogeneous volumes (no random numbers) */
-static float volumes_transmittance(const OrcConfig *cfg, v3 o, v3 d) {
+/* ---- heterogeneous volumes: SH/Volume.slang:54-166,230-252,291-352,448-517 over OrcGrid (the dense restatement of the NanoVDB reads, pt_oracle.h) ---- */
+#define GRID_DIM 32                                                              /* MAX_DENSITY_GRID_DIM, SH/Volume.slang:11 */
+/* SampleNanoVDBBuffer, SH/Volume.slang:69-117: three raw PCG draws jitter the voxel */
+static float grid_sample(const OrcVolume *v, const OrcGrid *g, Rng *rng, v3 x) {
+    float minX = (float)g->WorldBBox[0], minY = (float)g->WorldBBox[1], minZ = (float)g->WorldBBox[2];
+    float maxX = (float)g->WorldBBox[3], maxY = (float)g->WorldBBox[4], maxZ = (float)g->WorldBBox[5];
+    int wmin[3] = { (int)floorf(minX), (int)floorf(minY), (int)floorf(minZ) }, wmax[3] = { (int)ceilf(maxX), (int)ceilf(maxY), (int)ceilf(maxZ) };
+    v3 np = V3((x.x - v->CornerMin[0]) / (v->CornerMax[0] - v->CornerMin[0]), (x.y - v->CornerMin[1]) / (v->CornerMax[1] - v->CornerMin[1]),
+               (x.z - v->CornerMin[2]) / (v->CornerMax[2] - v->CornerMin[2]));
+    np.y = 1.0f - np.y;                                                          /* :83 */
+    v3 gp = V3(np.x * (float)(wmax[0] - wmin[0]) + (float)wmin[0], np.y * (float)(wmax[1] - wmin[1]) + (float)wmin[1], np.z * (float)(wmax[2] - wmin[2]) + (float)wmin[2]);
+    /* pnanovdb_grid_world_to_indexf: (src - vecf) * invmatf (diagonal map), then pnanovdb_hdda_pos_to_ijk: floor */
+    v3 ip = V3((gp.x - g->Translation[0]) * g->InvVoxelSize[0], (gp.y - g->Translation[1]) * g->InvVoxelSize[1], (gp.z - g->Translation[2]) * g->InvVoxelSize[2]);
+    int c[3] = { (int)floorf(ip.x), (int)floorf(ip.y), (int)floorf(ip.z) };
+    c[0] = (int)((uint32_t)c[0] + (rng_pcg(rng) % 3u - 1u));                     /* :103-105 (unsigned wrap-around = -1 / 0 / +1) */
+    c[1] = (int)((uint32_t)c[1] + (rng_pcg(rng) % 3u - 1u));
+    c[2] = (int)((uint32_t)c[2] + (rng_pcg(rng) % 3u - 1u));
+    for (int k = 0; k < 3; k++) {                                                /* :108 clamp to the root bbox */
+        int lo = g->IndexMin[k], hi = g->IndexMin[k] + (int)g->Dim[k] - 1;
+        c[k] = c[k] < lo ? lo : (c[k] > hi ? hi : c[k]);
+    }
+    float value = g->Values[((size_t)(c[2] - g->IndexMin[2]) * g->Dim[1] + (size_t)(c[1] - g->IndexMin[1])) * g->Dim[0] + (size_t)(c[0] - g->IndexMin[0])];
+    return orc_clamp(value / v->MaxDensityInTheGrid * v->GridSharpness, 0.0f, 1.0f);   /* :116 */
+}
+static float vol_effective_density(const OrcVolume *v, float baseDensity, float rayDepth) {     /* :159-166 */
+    if (v->ApproximatedScattering != 0) return baseDensity * powf(v->ApproximatedScatteringFalloff, rayDepth);
+    return baseDensity;
+}
+typedef struct { v3 blockSize; float epsilon, tEnter, tExit; } VolCtx;
+typedef struct { int blockIndex; v3 minCorner, maxCorner; } VolBlock;
+static VolCtx vol_ctx(const OrcVolume *v, VolIsect is) {                         /* CreateTraversalContext, :119-128 */
+    VolCtx c;
+    v3 ext = V3(v->CornerMax[0] - v->CornerMin[0], v->CornerMax[1] - v->CornerMin[1], v->CornerMax[2] - v->CornerMin[2]);
+    c.blockSize = V3(ext.x / (float)GRID_DIM, ext.y / (float)GRID_DIM, ext.z / (float)GRID_DIM);
+    c.epsilon = 0.0001f * fmaxf(ext.x, fmaxf(ext.y, ext.z));
+    c.tEnter = fmaxf(is.Near, 0.0f); c.tExit = is.Far;
+    return c;
+}
+static VolBlock vol_block(const OrcVolume *v, v3 p, const VolCtx *c) {           /* CalculateBlockInfo, :131-147 */
+    VolBlock b;
+    v3 rel = V3((p.x - v->CornerMin[0]) / (v->CornerMax[0] - v->CornerMin[0]), (p.y - v->CornerMin[1]) / (v->CornerMax[1] - v->CornerMin[1]),
+                (p.z - v->CornerMin[2]) / (v->CornerMax[2] - v->CornerMin[2]));
+    int ix = (int)(rel.x * (float)GRID_DIM), iy = (int)(rel.y * (float)GRID_DIM), iz = (int)(rel.z * (float)GRID_DIM);
+    ix = ix < 0 ? 0 : (ix > GRID_DIM - 1 ? GRID_DIM - 1 : ix); iy = iy < 0 ? 0 : (iy > GRID_DIM - 1 ? GRID_DIM - 1 : iy); iz = iz < 0 ? 0 : (iz > GRID_DIM - 1 ? GRID_DIM - 1 : iz);
+    b.blockIndex = ix + iy * GRID_DIM + iz * GRID_DIM * GRID_DIM;
+    b.minCorner = V3(v->CornerMin[0] + c->blockSize.x * (float)ix, v->CornerMin[1] + c->blockSize.y * (float)iy, v->CornerMin[2] + c->blockSize.z * (float)iz);
+    b.maxCorner = v3add(b.minCorner, c->blockSize);
+    return b;
+}
+static VolIsect vol_intersect_v(v3 o, v3 d, v3 mn, v3 mx) { float a[3] = { mn.x, mn.y, mn.z }, b[3] = { mx.x, mx.y, mx.z }; return vol_intersect(o, d, a, b); }
+/* ProcessHeterogeneousVolumeScattering, SH/Volume.slang:291-352: delta tracking against the per-block majorants */
+static float vol_scatter_distance_grid(const OrcVolume *v, const OrcGrid *g, v3 o, v3 d, Rng *rng, float rayDepth, VolIsect is) {
+    VolCtx c = vol_ctx(v, is);
+    VolBlock b = vol_block(v, v3add(o, v3scale(d, c.tEnter + c.epsilon)), &c);
+    float t = 0.0f;
+    for (int i = 0; i < 10000; i++) {
+        v3 cur = v3add(o, v3scale(d, c.tEnter + t + c.epsilon));
+        VolIsect bi = vol_intersect_v(cur, d, b.minCorner, b.maxCorner);
+        float maxDensity = vol_effective_density(v, g->MaxDensities[b.blockIndex] * v->Density, rayDepth);
+        float sampled = -logf(rng_f(rng)) / maxDensity;
+        if (bi.Far <= 0.0f) {
+            t += c.epsilon;
+            if (c.tEnter + t > c.tExit) return -1.0f;
+            b = vol_block(v, v3add(o, v3scale(d, c.tEnter + t + c.epsilon)), &c);
+            continue;
+        }
+        float toExit = bi.Far - fmaxf(bi.Near, 0.0f);
+        if (sampled > toExit) {
+            t += toExit + c.epsilon;
+            if (c.tEnter + t > c.tExit) return -1.0f;
+            b = vol_block(v, v3add(o, v3scale(d, c.tEnter + t + c.epsilon)), &c);
+            continue;
+        }
+        t += sampled;
+        if (c.tEnter + t > c.tExit) return -1.0f;
+        v3 sp = v3add(o, v3scale(d, c.tEnter + t));
+        float dens = vol_effective_density(v, grid_sample(v, g, rng, sp) * v->Density, rayDepth);
+        if (dens / maxDensity < rng_f(rng)) continue;                            /* null collision */
+        return c.tEnter + t;
+    }
+    return -1.0f;
+}
+/* ProcessHeterogeneousVolumeTransmittance, SH/Volume.slang:448-517: ratio tracking with Russian roulette */
+static float vol_transmittance_grid(const OrcVolume *v, const OrcGrid *g, Rng *rng, v3 o, v3 d, float rayDepth, VolIsect is) {
+    VolCtx c = vol_ctx(v, is);
+    VolBlock b = vol_block(v, v3add(o, v3scale(d, c.tEnter + c.epsilon)), &c);
+    float T = 1.0f, t = 0.0f;
+    for (int j = 0; j < 1000; j++) {
+        v3 cur = v3add(o, v3scale(d, c.tEnter + t + c.epsilon));
+        VolIsect bi = vol_intersect_v(cur, d, b.minCorner, b.maxCorner);
+        float maxDensity = vol_effective_density(v, g->MaxDensities[b.blockIndex] * v->Density, rayDepth);
+        float sampled = -logf(rng_f(rng)) / maxDensity;
+        if (bi.Far <= 0.0f) {
+            t += c.epsilon;
+            if (c.tEnter + t > c.tExit) break;
+            b = vol_block(v, v3add(o, v3scale(d, c.tEnter + t + c.epsilon)), &c);
+            continue;
+        }
+        float toExit = bi.Far - fmaxf(bi.Near, 0.0f);
+        if (sampled > toExit) {
+            t += toExit + c.epsilon;
+            if (c.tEnter + t > c.tExit) break;
+            b = vol_block(v, v3add(o, v3scale(d, c.tEnter + t + c.epsilon)), &c);
+            continue;
+        }
+        t += sampled;
+        if (c.tEnter + t > c.tExit) break;
+        v3 ip = v3add(o, v3scale(d, c.tEnter + t));
+        float dens = vol_effective_density(v, grid_sample(v, g, rng, ip) * v->Density, rayDepth);
+        T *= 1.0f - (dens / maxDensity);
+        float p = T;
+        if (rng_f(rng) > p) return 0.0f;
+        T /= p;
+    }
+    return T;
+}
+/* Volume::CalculateVolumesTransmittance, SH/Volume.slang:419-446: analytic for homogeneous volumes, a random walk (on the payload's sampler) for
+ * each heterogeneous volume the ray crosses */
+static float volumes_transmittance(const OrcConfig *cfg, Rng *rng, v3 o, v3 d, float rayDepth) {
     float T = 1.0f;
     for (uint32_t i = 0; i < cfg->VolumesCount; i++) {
         const OrcVolume *v = &cfg->Volumes[i];
         VolIsect is = vol_intersect(o, d, v->CornerMin, v->CornerMax);
         is.Near = fmaxf(is.Near, 0.0f);
-        float len = is.Far - is.Near;
-        if (len > 0.0f) T *= expf(-v->Density * len);
+        if (v->DensityDataIndex >= 0 && is.Far >= 0.0f) {
+            T *= vol_transmittance_grid(v, &cfg->Grids[v->DensityDataIndex], rng, o, d, rayDepth, is);
+            if (T <= 0.0f) return 0.0f;
+        } else {
+            float len = is.Far - is.Near;
+            if (len > 0.0f) T *= expf(-v->Density * len);
+        }
     }
     return orc_clamp(T, 0.0f, 1.0f);
 }
 /* Volume::DoesRayScatterInVolume, SH/Volume.slang:254-289 (homogeneous branch: one random number when the ray crosses the box) */
-static float vol_scatter_distance(const OrcVolume *v, v3 o, v3 d, Rng *rng, float ignoreIfFartherThan) {
+static float vol_scatter_distance(const OrcConfig *cfg, const OrcVolume *v, v3 o, v3 d, Rng *rng, float rayDepth, float ignoreIfFartherThan) {
     VolIsect is = vol_intersect(o, d, v->CornerMin, v->CornerMax);
     if (is.Far < 0.0f) return -1.0f;
     if (ignoreIfFartherThan >= 0.0f && is.Near > ignoreIfFartherThan) return -1.0f;
     float inside = is.Far - fmaxf(is.Near, 0.0f);
     if (inside <= 0.0f) return -1.0f;
+    if (v->DensityDataIndex >= 0) return vol_scatter_distance_grid(v, &cfg->Grids[v->DensityDataIndex], o, d, rng, rayDepth, is);
     float sampled = -logf(rng_f(rng)) / v->Density;                             /* SH/Sampler.slang:425-428 */
     if (sampled < inside) return fmaxf(is.Near, 0.0f) + sampled;
     return -1.0f;
+}
+/* Blackbody, SH/RTCommon.slang:139-172 */
+static v3 blackbody(float temperature) {
+    float temp = temperature / 100.0f;
+    float r, g, b;
+    if (temp <= 66.0f) r = 255.0f; else r = 329.698727446f * powf(temp - 60.0f, -0.1332047592f);
+    if (temp <= 66.0f) g = 99.4708025861f * logf(temp) - 161.1195681661f; else g = 288.1221695283f * powf(temp - 60.0f, -0.0755148492f);
+    if (temp >= 66.0f) b = 255.0f; else if (temp <= 19.0f) b = 0.0f; else b = 138.5177312231f * logf(temp - 10.0f) - 305.0447927307f;
+    return V3(orc_clamp(r / 255.0f, 0.0f, 1.0f), orc_clamp(g / 255.0f, 0.0f, 1.0f), orc_clamp(b / 255.0f, 0.0f, 1.0f));
+}
+/* Volume::GetEmissionFromTemperatureAtPoint, SH/Volume.slang:230-252: the temperature is read from the DENSITY buffer (:235) */
+static v3 vol_temperature_emission(const OrcConfig *cfg, const OrcVolume *v, Rng *rng, v3 x) {
+    if (!v->HasTemperatureData) return v3s(0.0f);
+    float tn = grid_sample(v, &cfg->Grids[v->DensityDataIndex], rng, x);
+    v3 color;
+    if (v->UseBlackbody) color = blackbody(tn * (float)(v->KelvinMax - v->KelvinMin) + (float)v->KelvinMin);
+    else color = V3(v->TemperatureColor[0], v->TemperatureColor[1], v->TemperatureColor[2]);
+    float intensity = powf(tn, v->TemperatureGamma) * v->TemperatureScale;
+    return V3(intensity * powf(color.x, v->EmissiveColorGamma), intensity * powf(color.y, v->EmissiveColorGamma), intensity * powf(color.z, v->EmissiveColorGamma));
 }
 static int does_ray_intersect(const OrcScene *sc, v3 o, v3 d, uint32_t *tri, uint32_t *inst, uint64_t *shadow_rays);
 static void sample_env(const OrcScene *sc, const OrcConfig *cfg, Rng *rng, v3 *toLight, v4 *outValue);
@@ -1031,7 +1173,7 @@ static void volume_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Paylo
     const OrcVolume *v = &cfg->Volumes[vi];
     const v3 color = V3(v->Color[0], v->Color[1], v->Color[2]);
     pl->Origin = v3add(pl->Origin, v3scale(pl->Direction, scatterDistance));
-    pl->Emitted = V3(v->EmissiveColor[0], v->EmissiveColor[1], v->EmissiveColor[2]);   /* + temperature emission: 0 without grid data */
+    pl->Emitted = v3add(V3(v->EmissiveColor[0], v->EmissiveColor[1], v->EmissiveColor[2]), vol_temperature_emission(cfg, v, &pl->Sampler, pl->Origin));   /* :268 */
     v3 toSky = V3(0, 0, 0); v4 sky = { 0, 0, 0, 0 };
     if (cfg->EnableSkyMIS) {
         importance_sample_sky(sc, cfg, &pl->Sampler, &toSky, &sky);
@@ -1050,7 +1192,7 @@ static void volume_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Paylo
     const float phaseS = vol_phase(cfg, v, pl->Direction, newDir, pl->VolumeDepth);
     if (cfg->EnableSkyMIS && sky.w > 0.0f) {
         float ph = vol_phase(cfg, v, pl->Direction, toSky, pl->VolumeDepth);
-        v3 T = v3s(volumes_transmittance(cfg, pl->Origin, toSky));
+        v3 T = v3s(volumes_transmittance(cfg, &pl->Sampler, pl->Origin, toSky, (float)pl->VolumeDepth));      /* :326 */
         if (cfg->EnableAtmosphere) T = v3mul(T, atm_transmittance_nee(cfg, pl, pl->Origin, toSky));   /* :328-342 */
         v3 bx = v3scale(color, ph);
         if (ph > 0.0f)
@@ -1058,7 +1200,7 @@ static void volume_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Paylo
     }
     if (cfg->EnableMeshMIS && light.w > 0.0f) {
         float ph = vol_phase(cfg, v, pl->Direction, toLight, pl->VolumeDepth);
-        float T = volumes_transmittance(cfg, pl->Origin, toLight);
+        float T = volumes_transmittance(cfg, &pl->Sampler, pl->Origin, toLight, (float)(pl->VolumeDepth + 1));   /* :361 */
         v3 bx = v3scale(color, ph);
         if (ph > 0.0f)
             pl->Emitted = v3add(pl->Emitted, v3scale(v3mul(v3mul(v3s(T), bx), v3divs(V3(light.x, light.y, light.z), light.w)), power_heuristic(light.w, ph)));
@@ -1212,7 +1354,7 @@ static void importance_sample_sky(const OrcScene *sc, const OrcConfig *cfg, Rng 
     else sample_env(sc, cfg, rng, toLight, outValue);
 }
 static int does_ray_intersect(const OrcScene *sc, v3 o, v3 d, uint32_t *tri, uint32_t *inst, uint64_t *shadow_rays);
-static float volumes_transmittance(const OrcConfig *cfg, v3 o, v3 d);
+static float volumes_transmittance(const OrcConfig *cfg, Rng *rng, v3 o, v3 d, float rayDepth);
 /* EvaluateAtmosphereScatteringEvent, SH/RayGen.slang:382-471 */
 static void atmosphere_scatter_event(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, float scatterDistance, int component, OrcCounters *cnt) {
     pl->Origin = v3add(pl->Origin, v3scale(pl->Direction, scatterDistance));
@@ -1230,7 +1372,7 @@ static void atmosphere_scatter_event(const OrcScene *sc, const OrcConfig *cfg, P
         v3 T = v3s(0.0f);
         if (!obscured) {
             T = atm_transmittance(cfg, &pl->Sampler, pl->Origin, toSun, pl->ColorChannel);
-            T = v3scale(T, volumes_transmittance(cfg, pl->Origin, toSun));
+            T = v3scale(T, volumes_transmittance(cfg, &pl->Sampler, pl->Origin, toSun, (float)pl->VolumeDepth));   /* :421 */
         }
         v3 col = v3divs(V3(cp.x, cp.y, cp.z), cp.w);
         if (component == 0) {
@@ -1271,7 +1413,7 @@ static int scattered_in_volume(const OrcScene *sc, const OrcConfig *cfg, Payload
     const float distanceToGeometry = gh.hit ? gh.t : -1.0f;
     float scatterDistance = -1.0f; int scattered = -1;
     for (int i = 0; i < n; i++) {
-        float t = vol_scatter_distance(&cfg->Volumes[indices[i]], pl->Origin, pl->Direction, &pl->Sampler, scatterDistance);
+        float t = vol_scatter_distance(cfg, &cfg->Volumes[indices[i]], pl->Origin, pl->Direction, &pl->Sampler, (float)pl->Depth, scatterDistance);   /* :199: payload.Depth, not VolumeDepth */
         if (t >= 0.0f && (t < scatterDistance || scatterDistance < 0.0f)) { scatterDistance = t; scattered = indices[i]; }
     }
     int component = -1, colorChannel = pl->ColorChannel;
@@ -1395,7 +1537,7 @@ static void closest_hit(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, v
     /* NEE accumulation :326-372 (volume transmittance == 1 with VolumesCount == 0, SH/Volume.slang:419-446) */
     if (cfg->EnableSkyMIS && canHitSky) {
         float pdf = sky.w;
-        v3 T = v3s(cfg->VolumesCount ? volumes_transmittance(cfg, pl->Origin, toSkyW) : 1.0f);     /* :332-333 */
+        v3 T = v3s(cfg->VolumesCount ? volumes_transmittance(cfg, &pl->Sampler, pl->Origin, toSkyW, 0.0f) : 1.0f);     /* :332-333 */
         if (cfg->EnableAtmosphere) T = v3mul(T, atm_transmittance_nee(cfg, pl, pl->Origin, toSkyW));    /* :335-349: consumes random numbers whenever the sky is visible */
         if (sky.w > 0.0f && skyEval.PDF > 0.0f) {
             v3 c = v3divs(v3mul(v3mul(skyEval.BxDF, T), V3(sky.x, sky.y, sky.z)), pdf);
@@ -1403,7 +1545,7 @@ static void closest_hit(const OrcScene *sc, const OrcConfig *cfg, Payload *pl, v
         }
     }
     if (cfg->EnableMeshMIS && !isLight && canHitLight && light.w > 0.0f && lightEval.PDF > 0.0f) {
-        const float T = cfg->VolumesCount ? volumes_transmittance(cfg, pl->Origin, toLightW) : 1.0f;    /* :364 */
+        const float T = cfg->VolumesCount ? volumes_transmittance(cfg, &pl->Sampler, pl->Origin, toLightW, 0.0f) : 1.0f;    /* :364 */
         v3 c = v3divs(v3mul(v3scale(lightEval.BxDF, T), V3(light.x, light.y, light.z)), light.w);
         pl->Emitted = v3add(pl->Emitted, v3scale(c, power_heuristic(light.w, lightEval.PDF)));
     }
@@ -1694,3 +1836,46 @@ void orc_camera_from_view(const float view[16], float aspect, float viewInv_out[
     float pi_[16] = { 1.0f / A, 0, 0, 0, 0, 1.0f / B, 0, 0, 0, 0, 0, 1.0f / D, 0, 0, -1.0f, C / D };
     memcpy(projInv_out, pi_, sizeof(pi_));
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * AddDensityDataToVolume after the OpenVDB file read: PT/PathTracer.cpp:1391-1452
+ * ---------------------------------------------------------------------------------------------- */
+void orc_prepare_density_grid(const int32_t indexMin[3], const uint32_t dim[3], float *values, const float *temperature, float temperatureMin, float temperatureMax,
+                              float *maxDensities32, float cornerMin[3], float cornerMax[3], float *maxDensityInTheGrid) {
+    const size_t n = (size_t)dim[0] * dim[1] * dim[2];
+    float maxDensity = values[0];                                               /* tools::minMax(tree, true).max(), :1393 */
+    for (size_t i = 1; i < n; i++) if (values[i] > maxDensity) maxDensity = values[i];
+    *maxDensityInTheGrid = maxDensity;
+    float maxDim = 0.0f;                                                        /* :1411-1420: the AABB is the index bbox scaled into about [-1, 1] */
+    for (int k = 0; k < 3; k++) {
+        const int lo = indexMin[k], hi = indexMin[k] + (int)dim[k] - 1;
+        cornerMin[k] = (float)lo; cornerMax[k] = (float)hi;
+        const float m = fmaxf(fabsf((float)lo), fabsf((float)hi));
+        if (m > maxDim) maxDim = m;
+    }
+    for (int k = 0; k < 3; k++) { cornerMin[k] /= maxDim; cornerMax[k] /= maxDim; }
+    for (int i = 0; i < 32768; i++) maxDensities32[i] = 0.0f;
+    const int dx = (int)dim[0], dy = (int)dim[1], dz = (int)dim[2];
+    for (int z = 0; z < dz; z++)
+        for (int y = 0; y < dy; y++)
+            for (int x = 0; x < dx; x++) {
+                const size_t at = ((size_t)z * dy + (size_t)(dy - 1 - y)) * dx + (size_t)x;   /* :1432: Y flipped */
+                const float density = orc_clamp(values[at] / maxDensity, 0.0f, 1.0f);
+                const int cell = ((x * 32) / dx) + ((y * 32) / dy) * 32 + ((z * 32) / dz) * 1024;
+                if (maxDensities32[cell] < density) maxDensities32[cell] = density;
+                if (temperature) {                                              /* :1440-1450: the normalised temperature lands in the DENSITY grid */
+                    float t = fmaxf((temperature[at] - temperatureMin) / (temperatureMax - temperatureMin), 0.0f);
+                    if (t > 0.0f) values[at] = t;
+                }
+            }
+}
+float orc_grid_transmittance(const OrcConfig *cfg, uint32_t seed, const float o[3], const float d[3], float rayDepth) {
+    Rng r; r.seed = seed;
+    return volumes_transmittance(cfg, &r, V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), rayDepth);
+}
+float orc_grid_sample(const OrcConfig *cfg, uint32_t volume, uint32_t seed, const float x[3]) {
+    Rng r; r.seed = seed;
+    const OrcVolume *v = &cfg->Volumes[volume];
+    return grid_sample(v, &cfg->Grids[v->DensityDataIndex], &r, V3(x[0], x[1], x[2]));
+}
+void orc_blackbody(float kelvin, float out[3]) { v3 c = blackbody(kelvin); out[0] = c.x; out[1] = c.y; out[2] = c.z; }

@@ -56,15 +56,36 @@ typedef struct {
     const float *lut_refract_in;   /* 128x128x32               :201 */
 } OrcSceneDesc;
 
-/* Homogeneous AABB volume: the fields of VolumeGPU (PT/PathTracer.h:341-395, SH/Volume.slang:20-52) that a volume without NanoVDB
- * density data (m_DensityDataIndex == -1) reads. */
+/* AABB volume: the fields of VolumeGPU (PT/PathTracer.h:341-395, SH/Volume.slang:20-52).  DensityDataIndex == -1: homogeneous;
+ * >= 0: index into OrcConfig::Grids (heterogeneous: the density / temperature data AddDensityDataToVolume prepared, PT/PathTracer.cpp:1346-1516). */
 typedef struct {
     float CornerMin[3], CornerMax[3];
     float Color[3], EmissiveColor[3];
     float Density, Anisotropy, Alpha, DropletSize;
-    uint32_t ApproximatedScattering;     /* m_ApproximatedScattering: anisotropy decays with the volume depth (SH/Volume.slang:150-156) */
-    uint32_t _pad;
+    uint32_t ApproximatedScattering;     /* m_ApproximatedScattering: anisotropy / density decay with the depth (SH/Volume.slang:150-166) */
+    float ApproximatedScatteringFalloff; /* (0.8) */
+    float TemperatureColor[3];           /* (1, 0.5, 0) used when UseBlackbody == 0 */
+    int32_t DensityDataIndex;            /* (-1) */
+    float MaxDensityInTheGrid;           /* set by orc_prepare_density_grid */
+    int32_t UseBlackbody, HasTemperatureData;   /* (1, 0) */
+    float TemperatureGamma, TemperatureScale, EmissiveColorGamma;   /* (1, 1, 1) */
+    int32_t KelvinMin, KelvinMax;        /* (500, 8000) */
+    float GridSharpness;                 /* (1) */
 } OrcVolume;
+
+/* Density data of one heterogeneous volume.  The reference keeps it in a NanoVDB buffer built from an OpenVDB FloatGrid (OpenVDB 12.0.1 is a vcpkg
+ * dependency, VulkanHelper/vcpkg.json, absent from the reference tree -- and so is PNanoVDB.h, which SH/Volume.slang:6-7 includes).  What the shader
+ * reads from it (SH/Volume.slang:69-117) is restated here over a DENSE copy of the same values: pnanovdb_grid_get_world_bbox (the index bbox
+ * [min, max + 1] through the grid's map, NanoVDB GridStats), pnanovdb_grid_world_to_indexf (float inverse map), pnanovdb_hdda_pos_to_ijk (floor),
+ * pnanovdb_root_get_bbox_min/max (the active-voxel bbox) and a value read at an index coordinate inside that bbox. */
+typedef struct {
+    const float *Values;          /* [z][y][x] over the active-voxel bbox, x fastest: tree().getValue(IndexMin + (x, y, z)) AFTER the temperature patch of PathTracer.cpp:1437-1450 */
+    const float *MaxDensities;    /* 32 x 32 x 32 majorants, PathTracer.cpp:1414-1452 */
+    int32_t IndexMin[3];          /* evalActiveVoxelBoundingBox().min() */
+    uint32_t Dim[3];              /* evalActiveVoxelDim() */
+    double WorldBBox[6];          /* min xyz, max xyz */
+    float InvVoxelSize[3], Translation[3];   /* the float copies NanoVDB's Map keeps (mInvMatF diagonal, mVecF) */
+} OrcGrid;
 
 typedef struct {                                                             /* PT/PathTracer.h:271-309 subset */
     float ViewInverse[16];        /* column-major */
@@ -87,13 +108,23 @@ typedef struct {                                                             /* 
     float RayleighScatteringCoefficientMultiplier[3], MieScatteringCoefficientMultiplier[3], OzoneAbsorptionCoefficientMultiplier[3];
     float RayleighDensityFalloff, MieDensityFalloff, OzoneDensityFalloff, OzonePeak;
     float SunColor[3];
+    uint32_t GridCount;
+    const OrcGrid *Grids;         /* heterogeneous density data, indexed by OrcVolume::DensityDataIndex */
 } OrcConfig;
 
 typedef struct { uint64_t paths, segments, surface_hits, misses, shadow_rays, medium_events; } OrcCounters;   /* medium_events: scattering events inside a mesh medium or an AABB volume */
 
 typedef struct OrcScene OrcScene;
 
+/* AddDensityDataToVolume after the file read (PT/PathTracer.cpp:1391-1452): MaxDensityInTheGrid, the AABB corners, the 32^3 majorant grid, and the
+ * temperature patch (normalised temperature overwrites the density value wherever it is positive -- the shader samples emission from the DENSITY
+ * buffer, SH/Volume.slang:235-236).  values: Dim.x*Dim.y*Dim.z floats, patched in place; temperature may be NULL. */
+void orc_prepare_density_grid(const int32_t indexMin[3], const uint32_t dim[3], float *values, const float *temperature, float temperatureMin, float temperatureMax,
+                              float *maxDensities32, float cornerMin[3], float cornerMax[3], float *maxDensityInTheGrid);
 /* ---- KAT helpers ---- */
+float orc_grid_transmittance(const OrcConfig *cfg, uint32_t seed, const float o[3], const float d[3], float rayDepth);   /* CalculateVolumesTransmittance, one walk */
+float orc_grid_sample(const OrcConfig *cfg, uint32_t volume, uint32_t seed, const float x[3]);                           /* SampleNanoVDBBuffer */
+void orc_blackbody(float kelvin, float out[3]);                                                                         /* SH/RTCommon.slang:139-172 */
 uint32_t orc_pcg_hash(uint32_t seed);                                  /* SH/Sampler.slang:4-9 */
 void     orc_rng_floats(uint32_t seed, uint32_t n, float *out);        /* SH/Sampler.slang:38-43 */
 float    orc_dielectric_fresnel(float cosI, float eta);                /* SH/Material.slang:434-449 */

@@ -21,6 +21,13 @@ os.environ["B200PT_FUSE"] = "2"; run("cornell_box", 48, 32, 2, 5); del os.enviro
 run("cornell_box", 48, 32, 1, 5, Volumes=[FOG])                     # k_volume_decide / k_shade_volume
 run("cornell_box", 48, 32, 2, 5, EnableAtmosphere=1, SkyRotationAltitude=-30.0)                       # atmosphere: sun NEE, delta tracking, transmittance walks
 run("cornell_box", 40, 30, 1, 5, EnableAtmosphere=1, SkyRotationAltitude=-20.0, Volumes=[FOG])        # atmosphere + homogeneous volume
+def _het():
+    from oracle import orc
+    z, y, x = np.mgrid[0:20, 0:34, 0:36].astype(np.float32)
+    d = np.exp(-(((x - 18) / 9) ** 2 + ((y - 17) / 9) ** 2 + ((z - 10) / 6) ** 2)).astype(np.float32) * 2.0
+    return dict(Position=(0.2, -0.2, -5.5), Scale=(3.0, 3.0, 3.0), Density=4.0, Grid=orc.prepare_density_grid(d, index_min=(-18, -17, -10), temperature=d * 100.0))
+run("cornell_box", 40, 30, 1, 5, Volumes=[FOG, _het()])                                              # grid volume: delta tracking, ratio-tracked NEE transmittance in k_connect<.., true>
+run("cornell_box", 40, 30, 1, 5, EnableAtmosphere=1, SkyRotationAltitude=-20.0, Volumes=[_het()])    # ... under the atmosphere
 run("cornell_box_glass", 48, 48, 2, 8)                              # dynamic-fetch BVH2 kernels, class queues (glass / diffuse)
 os.environ["B200PT_WIDE"] = "1"; run("viking_room", 48, 48, 1, 4); del os.environ["B200PT_WIDE"]              # BVH4 + textures
 os.environ["B200PT_SORT"] = "1"; os.environ["B200PT_TOP_KB"] = "16"; os.environ["B200PT_WIDE"] = "1"

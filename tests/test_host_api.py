@@ -37,7 +37,8 @@ def test_null_arguments_are_rejected_not_crashed():
     assert L.b200pt_path_trace(None, 1, 0, None) == pt.ERR_WRONG_ARGUMENTS
     assert L.b200pt_set_scene_file(None, b"x") == pt.ERR_WRONG_ARGUMENTS
     assert L.b200pt_add_volume(None, None) == pt.ERR_WRONG_ARGUMENTS      # homogeneous volumes are implemented: a null volume is a bad argument
-    assert L.b200pt_add_density_data_to_volume(None, 0, None) == pt.ERR_NOT_IMPLEMENTED   # NanoVDB grids are not
+    assert L.b200pt_add_density_data_to_volume(None, 0, None) == pt.ERR_NOT_IMPLEMENTED   # .vdb files need OpenVDB; density data goes in through b200pt_add_density_grid_to_volume
+    assert L.b200pt_add_density_grid_to_volume(None, 0, None) == pt.ERR_WRONG_ARGUMENTS
     w, h, p = C.c_uint32(), C.c_uint32(), C.c_void_p()
     assert L.b200pt_decode_image_file(b"/nonexistent.png", C.byref(w), C.byref(h), C.byref(p)) == pt.ERR_INIT_FAILED
 
@@ -493,20 +494,55 @@ def test_atmosphere_block_defaults_match_the_reference_members():
     for v in (a.RayleighScatteringCoefficientMultiplier, a.MieScatteringCoefficientMultiplier, a.OzoneAbsorptionCoefficientMultiplier): assert tuple(v) == (1.0, 1.0, 1.0)
     assert L.b200pt_default_atmosphere(None) == pt.ERR_WRONG_ARGUMENTS
     assert L.b200pt_set_atmosphere(None, C.byref(a)) == pt.ERR_WRONG_ARGUMENTS and L.b200pt_get_total_counts(None, None, None) == pt.ERR_WRONG_ARGUMENTS
-    assert L.b200pt_remove_density_data_from_volume(None, 0) == pt.ERR_NOT_IMPLEMENTED
+    assert L.b200pt_remove_density_data_from_volume(None, 0) == pt.ERR_WRONG_ARGUMENTS
 
 
 def test_volume_struct_and_defaults_without_gpu():
     """b200pt_volume mirrors PathTracer::Volume (PT/PathTracer.h:36-70): layout and defaults are checked on the CPU."""
     import ctypes as C
     from vpt_b200 import binding as B
-    assert C.sizeof(B.Volume) == 80
+    assert C.sizeof(B.Volume) == 148 and C.sizeof(B.DensityGrid) == 80
     v = B.PathTracer.make_volume()
-    assert list(v.CornerMin) == [-1.0] * 3 and list(v.CornerMax) == [1.0] * 3
-    assert all(abs(c - 0.8) < 1e-7 for c in v.Color) and list(v.EmissiveColor) == [0.0] * 3
-    assert (v.Density, v.Anisotropy, v.Alpha, v.DropletSize, v.DensityDataIndex) == (1.0, 0.0, 1.0, 20.0, -1)
-    assert v.ApproximatedScatteringForClouds == 0 and abs(v.ApproximatedScatteringFalloff - 0.8) < 1e-7
+    assert list(v.CornerMin) == [-1.0] * 3 and list(v.CornerMax) == [1.0] * 3 and list(v.Position) == [0.0] * 3 and list(v.Scale) == [1.0] * 3
+    assert all(abs(c - 0.8) < 1e-7 for c in v.Color) and list(v.EmissiveColor) == [0.0] * 3 and list(v.TemperatureColor) == [1.0, 0.5, 0.0]
+    assert (v.Density, v.Anisotropy, v.Alpha, v.DropletSize, v.DensityDataIndex, v.MaxDensityInTheGrid) == (1.0, 0.0, 1.0, 20.0, -1, 0.0)
+    assert (v.UseBlackbody, v.HasTemperatureData, v.TemperatureGamma, v.TemperatureScale, v.EmissiveColorGamma, v.KelvinMin, v.KelvinMax) == (1, 0, 1.0, 1.0, 1.0, 500, 8000)
+    assert v.ApproximatedScatteringForClouds == 0 and abs(v.ApproximatedScatteringFalloff - 0.8) < 1e-7 and v.GridSharpness == 1.0
     assert B.lib().b200pt_default_volume(None) == B.ERR_WRONG_ARGUMENTS
+
+
+def test_density_grid_preparation_equals_the_oracle():
+    """The host half of AddDensityDataToVolume (PT/PathTracer.cpp:1391-1452) in csrc/density_grid.cpp against the oracle's restatement, bit for bit:
+    MaxDensityInTheGrid, the AABB scaled into [-1, 1], the 32^3 majorants gathered with Y flipped and integer cell arithmetic, and the reference's
+    temperature patch (normalised temperature written INTO the density grid wherever it is positive)."""
+    from vpt_b200 import binding as B
+    from oracle import orc
+    rs = np.random.RandomState(11)
+    for shape, imin, with_t in (((21, 37, 18), (-9, -20, -7), True), ((64, 40, 70), (3, -50, 10), False), ((5, 3, 2), (0, 0, 0), True)):
+        d = rs.rand(*shape).astype(np.float32) ** 3 * 4.0
+        d[rs.rand(*shape) < 0.4] = 0.0
+        t = (rs.rand(*shape).astype(np.float32) * 900.0 - 200.0) if with_t else None
+        if t is not None: t[rs.rand(*shape) < 0.5] = -200.0
+        g = orc.prepare_density_grid(d, index_min=imin, temperature=t, voxel_size=0.5, translation=(1.0, -2.0, 0.25))
+        vals, maj, cmin, cmax, mx = B.prepare_density_grid(d, index_min=imin, temperature=t, voxel_size=0.5, translation=(1.0, -2.0, 0.25))
+        assert mx == g["max_density"] == float(d.max()) and cmin == g["corner_min"] and cmax == g["corner_max"]
+        assert np.array_equal(vals.view(np.uint32), g["values"].view(np.uint32)) and np.array_equal(maj.view(np.uint32), g["max_densities"].view(np.uint32))
+        assert max(abs(c) for c in cmin + cmax) == 1.0                               # the largest |index coordinate| maps to 1
+        if with_t: assert (vals != d).any() and np.all(vals[t <= t.min()] == d[t <= t.min()])   # patched exactly where the normalised temperature is positive
+        else: assert np.array_equal(vals, d)
+    # a single hot voxel lands in the majorant cell of its FLIPPED row (PathTracer.cpp:1432-1436)
+    d = np.zeros((8, 16, 4), np.float32); d[2, 3, 1] = 7.0
+    _, maj, _, _, mx = B.prepare_density_grid(d)
+    cell = (1 * 32) // 4 + (((16 - 1 - 3) * 32) // 16) * 32 + ((2 * 32) // 8) * 1024
+    assert mx == 7.0 and maj[cell] == 1.0 and np.count_nonzero(maj) == 1
+    L = B.lib()
+    g, keep = B.make_density_grid(np.zeros((2, 2, 2), np.float32))
+    out = np.zeros(8, np.float32); m = np.zeros(32768, np.float32); c3 = (C.c_float * 3)(); f = C.c_float()
+    args = (out.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), c3, c3, C.byref(f))
+    assert L.b200pt_prepare_density_grid(C.byref(g), *args) == B.ERR_WRONG_ARGUMENTS          # no positive density
+    assert L.b200pt_prepare_density_grid(None, *args) == B.ERR_WRONG_ARGUMENTS
+    g, keep = B.make_density_grid(np.ones((2, 2, 2), np.float32), voxel_size=0.0)
+    assert L.b200pt_prepare_density_grid(C.byref(g), *args) == B.ERR_WRONG_ARGUMENTS
 
 
 def test_cli_renderer_builds_and_fails_loudly_without_a_gpu():

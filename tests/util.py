@@ -66,7 +66,9 @@ def product_tracer(name, W, H, env=None, device=0, **cfg_kw):
     if atm: t.set_atmosphere(**{("Enable" if k == "EnableAtmosphere" else k): v for k, v in atm.items()})
     for k, v in cfg_kw.items():
         if k == "Volumes":                       # homogeneous AABB volumes: list of dicts (oracle.orc.VOLUME_DEFAULTS keys)
-            for vol in v: t.add_volume(**vol)
+            for vi, vol in enumerate(v):
+                t.add_volume(**vol)
+                if vol.get("Grid") is not None: t.add_density_grid(vi, **vol["Grid"]["source"])   # the same arrays oracle.orc.prepare_density_grid was given
         elif k == "PhaseFunction":
             t.set_phase_function(v)
         else:

@@ -67,10 +67,39 @@ class Config(C.Structure):
 
 
 class Volume(C.Structure):     # b200pt_volume (PathTracer::Volume, PT/PathTracer.h:36-70)
-    _fields_ = [("CornerMin", C.c_float * 3), ("CornerMax", C.c_float * 3), ("Color", C.c_float * 3), ("EmissiveColor", C.c_float * 3),
+    _fields_ = [("CornerMin", C.c_float * 3), ("CornerMax", C.c_float * 3), ("Position", C.c_float * 3), ("Scale", C.c_float * 3),
+                ("Color", C.c_float * 3), ("EmissiveColor", C.c_float * 3), ("TemperatureColor", C.c_float * 3),
                 ("Density", C.c_float), ("Anisotropy", C.c_float), ("Alpha", C.c_float), ("DropletSize", C.c_float),
-                ("DensityDataIndex", C.c_int32), ("ApproximatedScatteringForClouds", C.c_uint32), ("ApproximatedScatteringFalloff", C.c_float),
-                ("_reserved", C.c_uint32)]
+                ("DensityDataIndex", C.c_int32), ("MaxDensityInTheGrid", C.c_float), ("UseBlackbody", C.c_int32), ("HasTemperatureData", C.c_int32),
+                ("TemperatureGamma", C.c_float), ("TemperatureScale", C.c_float), ("EmissiveColorGamma", C.c_float),
+                ("KelvinMin", C.c_int32), ("KelvinMax", C.c_int32),
+                ("ApproximatedScatteringForClouds", C.c_uint32), ("ApproximatedScatteringFalloff", C.c_float), ("GridSharpness", C.c_float)]
+
+
+class DensityGrid(C.Structure):   # b200pt_density_grid
+    _fields_ = [("IndexMin", C.c_int32 * 3), ("Dim", C.c_uint32 * 3), ("Density", C.c_void_p), ("Temperature", C.c_void_p),
+                ("TemperatureMin", C.c_float), ("TemperatureMax", C.c_float), ("VoxelSize", C.c_double), ("Translation", C.c_double * 3)]
+
+
+def make_density_grid(density, index_min=(0, 0, 0), temperature=None, voxel_size=1.0, translation=(0.0, 0.0, 0.0), temperature_range=None):
+    """b200pt_density_grid over numpy arrays [z][y][x] (float32); returns (struct, keep-alive tuple)."""
+    d = np.ascontiguousarray(density, dtype=np.float32)
+    t = None if temperature is None else np.ascontiguousarray(temperature, dtype=np.float32)
+    g = DensityGrid()
+    for k in range(3): g.IndexMin[k] = int(index_min[k]); g.Dim[k] = d.shape[2 - k]; g.Translation[k] = float(translation[k])
+    g.Density = d.ctypes.data; g.Temperature = None if t is None else t.ctypes.data
+    g.TemperatureMin, g.TemperatureMax = (0.0, 0.0) if temperature_range is None else temperature_range
+    g.VoxelSize = float(voxel_size)
+    return g, (d, t)
+
+
+def prepare_density_grid(density, **kw):
+    """b200pt_prepare_density_grid (host only): (values, max_densities[32768], corner_min, corner_max, max_density)"""
+    g, keep = make_density_grid(density, **kw)
+    vals = np.empty(keep[0].shape, np.float32); maj = np.empty(32768, np.float32); cmin = (C.c_float * 3)(); cmax = (C.c_float * 3)(); mx = C.c_float()
+    r = lib().b200pt_prepare_density_grid(C.byref(g), vals.ctypes.data_as(C.c_void_p), maj.ctypes.data_as(C.c_void_p), cmin, cmax, C.byref(mx))
+    if r != OK: raise B200ptError(r, "prepare_density_grid")
+    return vals, maj, tuple(cmin), tuple(cmax), mx.value
 
 
 MAX_VOLUMES = 100
@@ -124,7 +153,9 @@ def lib():
             "b200pt_save_checkpoint": [C.c_void_p, C.c_char_p], "b200pt_load_checkpoint": [C.c_void_p, C.c_char_p],
             "b200pt_default_volume": [C.c_void_p], "b200pt_set_volume": [C.c_void_p, C.c_uint32, C.c_void_p], "b200pt_remove_volume": [C.c_void_p, C.c_uint32],
             "b200pt_volume_count": [C.c_void_p, C.POINTER(C.c_uint32)], "b200pt_get_volume": [C.c_void_p, C.c_uint32, C.c_void_p],
-            "b200pt_add_density_data_to_volume": [C.c_void_p, C.c_uint32, C.c_char_p],
+            "b200pt_add_density_data_to_volume": [C.c_void_p, C.c_uint32, C.c_char_p], "b200pt_remove_density_data_from_volume": [C.c_void_p, C.c_uint32],
+            "b200pt_add_density_grid_to_volume": [C.c_void_p, C.c_uint32, C.c_void_p],
+            "b200pt_prepare_density_grid": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
             "b200pt_set_phase_function": [C.c_void_p, C.c_uint32], "b200pt_get_phase_function": [C.c_void_p, C.POINTER(C.c_uint32)],
             "b200pt_set_partition": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32], "b200pt_local_rows": [C.c_void_p, C.POINTER(C.c_uint32)],
             "b200pt_path_trace": [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)], "b200pt_samples_accumulated": [C.c_void_p, C.POINTER(C.c_uint32)],
@@ -326,10 +357,18 @@ class PathTracer:
         if r != OK: raise B200ptError(r, "default_volume")
         for k, val in kw.items():
             if k == "ApproximatedScattering": k = "ApproximatedScatteringForClouds"
-            if k in ("CornerMin", "CornerMax", "Color", "EmissiveColor"):
+            if k == "Grid": continue                                   # density data: add_density_grid after add_volume (tests/util.py)
+            if k in ("CornerMin", "CornerMax", "Position", "Scale", "Color", "EmissiveColor", "TemperatureColor"):
                 for j in range(3): getattr(v, k)[j] = float(val[j])
             else: setattr(v, k, val)
         return v
+
+    def add_density_grid(self, idx, density, **kw):
+        """AddDensityDataToVolume after the file read: density / temperature as numpy [z][y][x] (see make_density_grid)"""
+        g, keep = make_density_grid(density, **kw)
+        self._ck(self.L.b200pt_add_density_grid_to_volume(self.h, idx, C.byref(g)))
+
+    def remove_density_data(self, idx): self._ck(self.L.b200pt_remove_density_data_from_volume(self.h, idx))
 
     def add_volume(self, vol=None, **kw):
         v = vol if vol is not None else self.make_volume(**kw)

@@ -22,6 +22,8 @@ template <class F> static int32_t guard(b200pt_handle h, F &&f) {
     catch (...) { h->err = "unknown error"; return B200PT_ERR_UNKNOWN; }
 }
 
+static_assert(sizeof(b200pt_volume) == 148 && sizeof(b200pt_density_grid) == 80, "b200pt_volume / b200pt_density_grid layout (binding.py, INTEGRATION.md)");
+
 extern "C" {
 
 const char *b200pt_version(void) { return "b200pt 0.1 (sm_100a wavefront path tracer)"; }
@@ -116,9 +118,12 @@ int32_t b200pt_reset(b200pt_handle h) { return guard(h, [&](Engine &e) { e.reset
 int32_t b200pt_default_volume(b200pt_volume *v) {                                      /* PT/PathTracer.h:36-70 */
     if (!v) return B200PT_ERR_WRONG_ARGUMENTS;
     memset(v, 0, sizeof *v);
-    for (int k = 0; k < 3; k++) { v->CornerMin[k] = -1.0f; v->CornerMax[k] = 1.0f; v->Color[k] = 0.8f; v->EmissiveColor[k] = 0.0f; }
-    v->Density = 1.0f; v->Anisotropy = 0.0f; v->Alpha = 1.0f; v->DropletSize = 20.0f; v->DensityDataIndex = -1;
-    v->ApproximatedScatteringForClouds = 0; v->ApproximatedScatteringFalloff = 0.8f;
+    for (int k = 0; k < 3; k++) { v->CornerMin[k] = -1.0f; v->CornerMax[k] = 1.0f; v->Position[k] = 0.0f; v->Scale[k] = 1.0f; v->Color[k] = 0.8f; v->EmissiveColor[k] = 0.0f; }
+    v->TemperatureColor[0] = 1.0f; v->TemperatureColor[1] = 0.5f; v->TemperatureColor[2] = 0.0f;
+    v->Density = 1.0f; v->Anisotropy = 0.0f; v->Alpha = 1.0f; v->DropletSize = 20.0f; v->DensityDataIndex = -1; v->MaxDensityInTheGrid = 0.0f;
+    v->UseBlackbody = 1; v->HasTemperatureData = 0; v->TemperatureGamma = 1.0f; v->TemperatureScale = 1.0f; v->EmissiveColorGamma = 1.0f;
+    v->KelvinMin = 500; v->KelvinMax = 8000;
+    v->ApproximatedScatteringForClouds = 0; v->ApproximatedScatteringFalloff = 0.8f; v->GridSharpness = 1.0f;
     return B200PT_OK;
 }
 int32_t b200pt_add_volume(b200pt_handle h, const b200pt_volume *v) { if (!v) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.add_volume(*v); }); }
@@ -129,8 +134,19 @@ int32_t b200pt_get_volume(b200pt_handle h, uint32_t i, b200pt_volume *out) {
     if (!out) return B200PT_ERR_WRONG_ARGUMENTS;
     return guard(h, [&](Engine &e) { if (i >= e.volumes().size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume index out of range" }; *out = e.volumes()[i]; });
 }
-int32_t b200pt_add_density_data_to_volume(b200pt_handle h, uint32_t, const char *) { if (h) h->err = "NanoVDB density data is not implemented (SURVEY 8f row 1: needs a NanoVDB reader)"; return B200PT_ERR_NOT_IMPLEMENTED; }
-int32_t b200pt_remove_density_data_from_volume(b200pt_handle h, uint32_t) { if (h) h->err = "NanoVDB density data is not implemented (SURVEY 8f row 1)"; return B200PT_ERR_NOT_IMPLEMENTED; }
+int32_t b200pt_add_density_grid_to_volume(b200pt_handle h, uint32_t i, const b200pt_density_grid *g) { if (!g) return B200PT_ERR_WRONG_ARGUMENTS; return guard(h, [&](Engine &e) { e.add_density_grid(i, *g); }); }
+int32_t b200pt_add_density_data_to_volume(b200pt_handle h, uint32_t, const char *) { if (h) h->err = "reading .vdb files needs OpenVDB (not in this build): read the grid with the reference's OpenVDB and call b200pt_add_density_grid_to_volume"; return B200PT_ERR_NOT_IMPLEMENTED; }
+int32_t b200pt_remove_density_data_from_volume(b200pt_handle h, uint32_t i) { return guard(h, [&](Engine &e) { e.remove_density_data(i); }); }
+int32_t b200pt_prepare_density_grid(const b200pt_density_grid *g, float *values, float *maxd, float cmin[3], float cmax[3], float *max_density) {
+    if (!g || !values || !maxd || !cmin || !cmax || !max_density) return B200PT_ERR_WRONG_ARGUMENTS;
+    try {
+        PreparedGrid p; prepare_density_grid(*g, p);
+        std::copy(p.values.begin(), p.values.end(), values); std::copy(p.max_densities.begin(), p.max_densities.end(), maxd);
+        for (int k = 0; k < 3; k++) { cmin[k] = p.corner_min[k]; cmax[k] = p.corner_max[k]; }
+        *max_density = p.max_density;
+        return B200PT_OK;
+    } catch (const CudaError &e) { return e.code; } catch (...) { return B200PT_ERR_UNKNOWN; }
+}
 int32_t b200pt_default_atmosphere(b200pt_atmosphere *a) {          // PathTracer.h:221-232
     if (!a) return B200PT_ERR_WRONG_ARGUMENTS;
     memset(a, 0, sizeof *a);

@@ -91,10 +91,21 @@ static_assert(sizeof(ShadeTri) == 112, "ShadeTri is 112 B");
 //   r0 = p0.xyz | uv0.x   r1 = p1.xyz | uv0.y   r2 = p2.xyz | uv1.x   r3 = uv1.y uv2.x uv2.y | global triangle id (bits)
 struct EmTri { float4 r[4]; };
 
-// 80-byte homogeneous volume (VolumeGPU of PT/PathTracer.h:341-395 without the grid fields): mn_density = CornerMin | Density,
-// mx_g = CornerMax | Anisotropy, color_alpha = Color | Alpha, emis_droplet = EmissiveColor | DropletSize, flags.x = ApproximatedScattering
-struct DevVolume { float4 mn_density, mx_g, color_alpha, emis_droplet; uint4 flags; };
-static_assert(sizeof(DevVolume) == 80, "DevVolume is 80 B");
+// 128-byte volume (VolumeGPU of PT/PathTracer.h:341-395): mn_density = CornerMin | Density, mx_g = CornerMax | Anisotropy, color_alpha = Color | Alpha,
+// emis_droplet = EmissiveColor | DropletSize, flags = { ApproximatedScattering, HasTemperatureData, UseBlackbody, grid slot (0xFFFFFFFF: homogeneous) },
+// tcol_gamma = TemperatureColor | TemperatureGamma, tparams = { TemperatureScale, EmissiveColorGamma, ApproximatedScatteringFalloff, GridSharpness },
+// kelvin = { (float)KelvinMin, (float)(KelvinMax - KelvinMin), MaxDensityInTheGrid, - }
+struct DevVolume { float4 mn_density, mx_g, color_alpha, emis_droplet; uint4 flags; float4 tcol_gamma, tparams, kelvin; };
+static_assert(sizeof(DevVolume) == 128, "DevVolume is 128 B");
+// Density data of one heterogeneous volume (PT/PathTracer.cpp:1346-1516): a dense copy of the values the reference keeps in a NanoVDB buffer, the
+// 32^3 majorants, and the constants SampleNanoVDBBuffer (SH/Volume.slang:69-117) derives from the grid header on every call.
+struct DevGrid {
+    const float *values;       // [z][y][x] over the active-voxel bbox
+    const float *max_densities; // 32768
+    int imin[3]; int dim[3];   // root bbox: imin .. imin + dim - 1
+    float wmin[3], wext[3];    // (float)floor(world bbox min), (float)(ceil(world bbox max) - floor(world bbox min))
+    float inv_vs[3], trans[3]; // NanoVDB Map: mInvMatF diagonal, mVecF
+};
 
 struct DevScene {
     const b200pt_vertex *verts;
@@ -116,7 +127,9 @@ struct DevScene {
     const ShadeTri *shade_tris;
     const EmTri *em_tris;
     const uint32_t *em_tri_base;   // per emissive mesh: first EmTri
-    const DevVolume *volumes;      // homogeneous AABB volumes (volumes.cuh), n_volumes entries
+    const DevVolume *volumes;      // AABB volumes (volumes.cuh), n_volumes entries
+    const DevGrid *grids;          // density data of the heterogeneous ones (DevVolume::flags.w)
+    uint32_t n_grids;              // != 0: NEE transmittance is a random walk on the path's stream and moves from the shading kernels into k_connect
     uint32_t uniform_class;        // the one MaterialClass every triangle has, or 0xFF (k_extend then looks tri_class up per hit)
     uint32_t pre_pass;             // k_volume_decide runs before k_extend (the scene has volumes or the atmosphere is on): hit records may hold VOLUME_EVENT / DEAD_EVENT
     uint32_t n_volumes, phase_function;   // phase_function: 0 HG, 1 Draine, 2 HG + Draine (PT/PathTracer.h:76-81)

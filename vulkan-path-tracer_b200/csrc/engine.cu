@@ -48,7 +48,7 @@ Engine::~Engine() {
     if (stream_) cudaStreamSynchronize(stream_);
     free_scene(); free_wave(); free_post();
     dfree(d_env_); dfree(d_alias_); dfree(d_env_row_cos_); for (auto &l : d_luts_) dfree(l);
-    dfree(d_image_); dfree(d_ctr_); dfree(d_volumes_); dfree(d_tri_class_);
+    dfree(d_image_); dfree(d_ctr_); dfree(d_volumes_); dfree(d_grids_); grids_.clear(); dfree(d_tri_class_);
     for (int c = 0; c < 2; c++) {
         dfree(wb_[c].counts); if (wb_[c].h_count) cudaFreeHost(wb_[c].h_count);
         if (aux_stream_[c]) { cudaStreamSynchronize(aux_stream_[c]); cudaStreamDestroy(aux_stream_[c]); }
@@ -294,43 +294,97 @@ void Engine::set_material(uint32_t idx, const b200pt_material &m) {
     reset();
 }
 
-// PathTracer::AddVolume / SetVolume / RemoveVolume (PathTracer.cpp:1334-1345,1518-1555): homogeneous AABB volumes only
+// PathTracer::AddVolume / SetVolume / RemoveVolume / AddDensityDataToVolume / RemoveDensityDataFromVolume (PathTracer.cpp:1334-1555)
 static void check_volume(const b200pt_volume &v) {
-    if (v.DensityDataIndex != -1) throw CudaError{ B200PT_ERR_NOT_IMPLEMENTED, "heterogeneous (NanoVDB) volumes are not implemented: DensityDataIndex must be -1" };
-    for (int k = 0; k < 3; k++) if (!(v.CornerMin[k] <= v.CornerMax[k])) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume AABB: CornerMin > CornerMax" };
+    for (int k = 0; k < 3; k++) if (!(v.CornerMin[k] <= v.CornerMax[k]) || !(v.Scale[k] >= 0.0f)) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume AABB: CornerMin > CornerMax or negative Scale" };
     if (!(v.Density >= 0.0f)) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume density must be >= 0" };
 }
+Engine::GridData::~GridData() { cudaFree(d_values); cudaFree(d_max_densities); }
 void Engine::upload_volumes() {
     CK(cudaSetDevice(device_));
     sync_all();
     if (!d_volumes_) CK(cudaMalloc(&d_volumes_, B200PT_MAX_VOLUMES * sizeof(DevVolume)));
+    if (!d_grids_) CK(cudaMalloc(&d_grids_, B200PT_MAX_VOLUMES * sizeof(DevGrid)));
     std::vector<DevVolume> dv(volumes_.size());
+    std::vector<DevGrid> dg;
     for (size_t i = 0; i < volumes_.size(); i++) {
         const b200pt_volume &v = volumes_[i];
-        dv[i].mn_density = make_float4(v.CornerMin[0], v.CornerMin[1], v.CornerMin[2], v.Density);
-        dv[i].mx_g = make_float4(v.CornerMax[0], v.CornerMax[1], v.CornerMax[2], v.Anisotropy);
+        float lo[3], hi[3];                                                     // VolumeGPU's constructor, PathTracer.h:396-397
+        for (int k = 0; k < 3; k++) { lo[k] = v.Position[k] + (v.CornerMin[k] * v.Scale[k]); hi[k] = v.Position[k] + (v.CornerMax[k] * v.Scale[k]); }
+        dv[i].mn_density = make_float4(lo[0], lo[1], lo[2], v.Density);
+        dv[i].mx_g = make_float4(hi[0], hi[1], hi[2], v.Anisotropy);
         dv[i].color_alpha = make_float4(v.Color[0], v.Color[1], v.Color[2], v.Alpha);
         dv[i].emis_droplet = make_float4(v.EmissiveColor[0], v.EmissiveColor[1], v.EmissiveColor[2], v.DropletSize);
-        dv[i].flags = make_uint4(v.ApproximatedScatteringForClouds, 0u, 0u, 0u);
+        dv[i].tcol_gamma = make_float4(v.TemperatureColor[0], v.TemperatureColor[1], v.TemperatureColor[2], v.TemperatureGamma);
+        dv[i].tparams = make_float4(v.TemperatureScale, v.EmissiveColorGamma, v.ApproximatedScatteringFalloff, v.GridSharpness);
+        dv[i].kelvin = make_float4((float)v.KelvinMin, (float)(v.KelvinMax - v.KelvinMin), v.MaxDensityInTheGrid, 0.0f);
+        uint32_t slot = 0xFFFFFFFFu;
+        if (grids_[i]) {
+            const GridData &G = *grids_[i];
+            DevGrid g{};
+            g.values = G.d_values; g.max_densities = G.d_max_densities;
+            for (int k = 0; k < 3; k++) { g.imin[k] = G.host.imin[k]; g.dim[k] = G.host.dim[k]; g.wmin[k] = G.host.wmin[k]; g.wext[k] = G.host.wext[k]; g.inv_vs[k] = G.host.inv_vs[k]; g.trans[k] = G.host.trans[k]; }
+            slot = (uint32_t)dg.size(); dg.push_back(g);
+        }
+        dv[i].flags = make_uint4(v.ApproximatedScatteringForClouds, (uint32_t)(v.HasTemperatureData != 0), (uint32_t)(v.UseBlackbody != 0), slot);
     }
     if (!dv.empty()) CK(cudaMemcpy(d_volumes_, dv.data(), dv.size() * sizeof(DevVolume), cudaMemcpyHostToDevice));
+    if (!dg.empty()) CK(cudaMemcpy(d_grids_, dg.data(), dg.size() * sizeof(DevGrid), cudaMemcpyHostToDevice));
     ds_.volumes = d_volumes_; ds_.n_volumes = (uint32_t)dv.size(); ds_.phase_function = phase_function_;
+    ds_.grids = d_grids_; ds_.n_grids = (uint32_t)dg.size();
     reset();
+}
+// the three READ-ONLY members of b200pt_volume follow the density data attached to the index, whatever the caller's struct says
+static b200pt_volume with_grid_fields(b200pt_volume v, const b200pt_volume *keep) {
+    v.DensityDataIndex = keep ? keep->DensityDataIndex : -1;
+    v.MaxDensityInTheGrid = keep ? keep->MaxDensityInTheGrid : 0.0f;
+    v.HasTemperatureData = keep ? keep->HasTemperatureData : 0;
+    return v;
 }
 uint32_t Engine::add_volume(const b200pt_volume &v) {
     check_volume(v);
     if (volumes_.size() >= B200PT_MAX_VOLUMES) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "too many volumes (B200PT_MAX_VOLUMES)" };
-    volumes_.push_back(v); upload_volumes();
+    volumes_.push_back(with_grid_fields(v, nullptr)); grids_.push_back(nullptr); upload_volumes();
     return (uint32_t)volumes_.size() - 1u;
 }
 void Engine::set_volume(uint32_t idx, const b200pt_volume &v) {
     check_volume(v);
     if (idx >= volumes_.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume index out of range" };
-    volumes_[idx] = v; upload_volumes();
+    const b200pt_volume old = volumes_[idx];
+    volumes_[idx] = with_grid_fields(v, grids_[idx] ? &old : nullptr); upload_volumes();
 }
 void Engine::remove_volume(uint32_t idx) {
     if (idx >= volumes_.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume index out of range" };
-    volumes_.erase(volumes_.begin() + idx); upload_volumes();
+    sync_all();                                                                 // the grid's device buffers may still be read by waves in flight
+    volumes_.erase(volumes_.begin() + idx); grids_.erase(grids_.begin() + idx); upload_volumes();
+}
+void Engine::add_density_grid(uint32_t idx, const b200pt_density_grid &g) {
+    if (idx >= volumes_.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume index out of range" };   // PathTracer.cpp:1348-1352
+    auto G = std::make_shared<GridData>();
+    prepare_density_grid(g, G->host);
+    CK(cudaSetDevice(device_));
+    sync_all();
+    CK(cudaMalloc(&G->d_values, G->host.values.size() * sizeof(float)));
+    CK(cudaMalloc(&G->d_max_densities, G->host.max_densities.size() * sizeof(float)));
+    CK(cudaMemcpy(G->d_values, G->host.values.data(), G->host.values.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(G->d_max_densities, G->host.max_densities.data(), G->host.max_densities.size() * sizeof(float), cudaMemcpyHostToDevice));
+    b200pt_volume &v = volumes_[idx];
+    for (int k = 0; k < 3; k++) { v.CornerMin[k] = G->host.corner_min[k]; v.CornerMax[k] = G->host.corner_max[k]; }
+    v.MaxDensityInTheGrid = G->host.max_density;
+    v.HasTemperatureData = G->host.has_temperature ? 1 : 0;
+    v.DensityDataIndex = density_data_counter_;                                 // :1512-1513
+    density_data_counter_ = (density_data_counter_ + 1) % (int)B200PT_MAX_VOLUMES;
+    grids_[idx] = std::move(G);
+    upload_volumes();
+}
+void Engine::remove_density_data(uint32_t idx) {                                // PathTracer.cpp:1518-1528
+    if (idx >= volumes_.size()) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "volume index out of range" };
+    sync_all();
+    grids_[idx] = nullptr;
+    b200pt_volume &v = volumes_[idx];
+    v.DensityDataIndex = -1; v.MaxDensityInTheGrid = 0.0f; v.HasTemperatureData = 0;
+    for (int k = 0; k < 3; k++) { v.CornerMin[k] = -1.0f; v.CornerMax[k] = 1.0f; }
+    upload_volumes();
 }
 void Engine::set_phase_function(uint32_t pf) {
     if (pf > 2u) throw CudaError{ B200PT_ERR_WRONG_ARGUMENTS, "phase function: 0 HG, 1 Draine, 2 HG + Draine" };

@@ -7,8 +7,6 @@
 
 namespace b200pt {
 
-struct CudaError { int code; std::string what; };
-
 class Engine {
 public:
     explicit Engine(int device);
@@ -22,10 +20,12 @@ public:
     void set_config(const b200pt_config &c);
     const b200pt_config &config() const { return cfg_; }
     void set_material(uint32_t idx, const b200pt_material &m);
-    // PathTracer::AddVolume / SetVolume / RemoveVolume / SetPhaseFunction (homogeneous volumes, volumes.cuh)
+    // PathTracer::AddVolume / SetVolume / RemoveVolume / SetPhaseFunction / AddDensityDataToVolume / RemoveDensityDataFromVolume (volumes.cuh)
     uint32_t add_volume(const b200pt_volume &v);
     void set_volume(uint32_t idx, const b200pt_volume &v);
     void remove_volume(uint32_t idx);
+    void add_density_grid(uint32_t idx, const b200pt_density_grid &g);
+    void remove_density_data(uint32_t idx);
     const std::vector<b200pt_volume> &volumes() const { return volumes_; }
     void set_phase_function(uint32_t pf);
     uint32_t phase_function() const { return phase_function_; }
@@ -112,6 +112,9 @@ private:
     std::vector<DevInstance> h_instances_; std::vector<DevMesh> h_meshes_;
     float4 *d_env_ = nullptr; uint2 *d_alias_ = nullptr; float2 *d_env_row_cos_ = nullptr; float *d_luts_[3] = { nullptr, nullptr, nullptr };
     std::vector<b200pt_volume> volumes_; uint32_t phase_function_ = 0; DevVolume *d_volumes_ = nullptr;
+    struct GridData { PreparedGrid host; float *d_values = nullptr, *d_max_densities = nullptr; ~GridData(); };
+    std::vector<std::shared_ptr<GridData>> grids_;      // parallel to volumes_: density data of the heterogeneous ones (nullptr: homogeneous)
+    DevGrid *d_grids_ = nullptr; int density_data_counter_ = 0;   // PathTracer.cpp:1508-1513: slots are handed out round-robin
     b200pt_atmosphere atmosphere_{};
     LbvhResult bvh_{};
     LaunchCfg lc_{};

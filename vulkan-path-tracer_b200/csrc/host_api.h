@@ -8,6 +8,18 @@
 
 namespace b200pt {
 
+struct CudaError { int code; std::string what; };   // every failure crosses the C-ABI as a code + message (capi.cpp guard)
+
+// ---- density_grid.cpp: AddDensityDataToVolume after the file read (PT/PathTracer.cpp:1391-1452) ----
+struct PreparedGrid {
+    std::vector<float> values, max_densities;       // temperature-patched values [z][y][x]; 32^3 majorants
+    int imin[3], dim[3];
+    float corner_min[3], corner_max[3], max_density;
+    float wmin[3], wext[3], inv_vs[3], trans[3];    // SampleNanoVDBBuffer's per-grid constants (DevGrid)
+    bool has_temperature = false;
+};
+void prepare_density_grid(const b200pt_density_grid &g, PreparedGrid &out);
+
 // ---- image_codecs.cpp ----
 bool decode_image_rgba8(const std::string &path, uint32_t &W, uint32_t &H, std::vector<uint8_t> &rgba, std::string &err);
 bool decode_hdr_rgba32f(const std::string &path, uint32_t &W, uint32_t &H, std::vector<float> &rgba, std::string &err);

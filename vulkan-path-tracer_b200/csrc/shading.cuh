@@ -67,6 +67,7 @@ __device__ __forceinline__ uint32_t pcg_hash(uint32_t seed) {
 struct Rng {
     uint32_t s;
     __device__ __forceinline__ float next() { s = pcg_hash(s); return (float)s / 4294967296.0f; }   // float(UINT_MAX) == 2^32 (Q12)
+    __device__ __forceinline__ uint32_t next_u32() { s = pcg_hash(s); return s; }                    // Sampler::PCG(), SH/Sampler.slang:23-27
 };
 // SH/Sampler.slang:115-133
 __device__ __forceinline__ float3 random_sphere(Rng &r) {

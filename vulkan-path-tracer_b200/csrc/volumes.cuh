@@ -1,5 +1,5 @@
-// volumes.cuh -- homogeneous AABB volumes (the part that needs no NanoVDB grid).
-// Reference: SH/Volume.slang (the m_DensityDataIndex == -1 paths), SH/RayGen.slang:162-380 (ScatteredInVolume,
+// volumes.cuh -- AABB volumes: homogeneous, and heterogeneous over a dense copy of the density data (DevGrid).
+// Reference: SH/Volume.slang, SH/RayGen.slang:162-380 (ScatteredInVolume,
 // EvaluateVolumeScatteringEvent), phase functions SH/RTCommon.slang:214-228 with their samplers SH/Sampler.slang:169-295,
 // host API PT/PathTracer.h:36-81,157-166, PT/PathTracer.cpp:1334-1345.
 // Wavefront placement:
@@ -111,7 +111,91 @@ static __device__ __noinline__ float vol_phase(uint32_t phase_function, const De
     const HgDraineFit f = hg_draine_fit(v.emis_droplet.w);
     return mixf(phase_hg(V, L, f.GHG), phase_draine(V, L, f.GD, f.AD), f.WD);
 }
-// Volume::CalculateVolumesTransmittance, SH/Volume.slang:419-446: analytic for homogeneous volumes, no random numbers
+// ---- heterogeneous volumes: SH/Volume.slang:54-166,230-252,291-352,448-517 over DevGrid (a dense copy of what the reference's NanoVDB buffer returns) ----
+constexpr int GRID_DIM = 32;                                                                     // MAX_DENSITY_GRID_DIM, SH/Volume.slang:11
+// SampleNanoVDBBuffer, SH/Volume.slang:69-117: box -> [0, 1]^3 (Y flipped) -> the grid's integer world box -> index space (float inverse map) -> floor,
+// three raw PCG draws jitter the voxel by -1 / 0 / +1, clamp to the root bbox, read, normalise
+static __device__ __noinline__ float grid_sample(const DevVolume &v, const DevGrid &g, Rng &rng, float3 x) {
+    const float3 mn = f3(v.mn_density), mx = f3(v.mx_g);
+    float3 np = f3((x.x - mn.x) / (mx.x - mn.x), (x.y - mn.y) / (mx.y - mn.y), (x.z - mn.z) / (mx.z - mn.z));
+    np.y = 1.0f - np.y;
+    const float3 gp = f3(np.x * g.wext[0] + g.wmin[0], np.y * g.wext[1] + g.wmin[1], np.z * g.wext[2] + g.wmin[2]);
+    const float3 ip = f3((gp.x - g.trans[0]) * g.inv_vs[0], (gp.y - g.trans[1]) * g.inv_vs[1], (gp.z - g.trans[2]) * g.inv_vs[2]);
+    int c[3] = { (int)floorf(ip.x), (int)floorf(ip.y), (int)floorf(ip.z) };
+    c[0] = (int)((uint32_t)c[0] + (rng.next_u32() % 3u - 1u));
+    c[1] = (int)((uint32_t)c[1] + (rng.next_u32() % 3u - 1u));
+    c[2] = (int)((uint32_t)c[2] + (rng.next_u32() % 3u - 1u));
+#pragma unroll
+    for (int k = 0; k < 3; k++) c[k] = max(g.imin[k], min(g.imin[k] + g.dim[k] - 1, c[k]));
+    const float value = __ldg(g.values + ((size_t)(c[2] - g.imin[2]) * g.dim[1] + (size_t)(c[1] - g.imin[1])) * g.dim[0] + (size_t)(c[0] - g.imin[0]));
+    return clampf(value / v.kelvin.z * v.tparams.w, 0.0f, 1.0f);
+}
+__device__ __forceinline__ float vol_effective_density(const DevVolume &v, float base, float rayDepth) {   // SH/Volume.slang:159-166
+    if (v.flags.x != 0u) return base * pt_pow(v.tparams.z, rayDepth);
+    return base;
+}
+struct VolCtx { float3 blockSize; float epsilon, tEnter, tExit; };
+struct VolBlock { int blockIndex; float3 minCorner, maxCorner; };
+__device__ __forceinline__ VolCtx vol_ctx(const DevVolume &v, VolIsect is) {                     // CreateTraversalContext, :119-128
+    VolCtx c;
+    const float3 ext = f3(v.mx_g) - f3(v.mn_density);
+    c.blockSize = f3(ext.x / (float)GRID_DIM, ext.y / (float)GRID_DIM, ext.z / (float)GRID_DIM);
+    c.epsilon = 0.0001f * fmaxf(ext.x, fmaxf(ext.y, ext.z));
+    c.tEnter = fmaxf(is.Near, 0.0f); c.tExit = is.Far;
+    return c;
+}
+__device__ __forceinline__ VolBlock vol_block(const DevVolume &v, float3 p, const VolCtx &c) {  // CalculateBlockInfo, :131-147
+    const float3 mn = f3(v.mn_density), mx = f3(v.mx_g);
+    const float3 rel = f3((p.x - mn.x) / (mx.x - mn.x), (p.y - mn.y) / (mx.y - mn.y), (p.z - mn.z) / (mx.z - mn.z));
+    const int ix = max(0, min(GRID_DIM - 1, (int)(rel.x * (float)GRID_DIM))), iy = max(0, min(GRID_DIM - 1, (int)(rel.y * (float)GRID_DIM))),
+              iz = max(0, min(GRID_DIM - 1, (int)(rel.z * (float)GRID_DIM)));
+    VolBlock b;
+    b.blockIndex = ix + iy * GRID_DIM + iz * GRID_DIM * GRID_DIM;
+    b.minCorner = f3(mn.x + c.blockSize.x * (float)ix, mn.y + c.blockSize.y * (float)iy, mn.z + c.blockSize.z * (float)iz);
+    b.maxCorner = b.minCorner + c.blockSize;
+    return b;
+}
+// ProcessHeterogeneousVolumeScattering (:291-352, delta tracking, SCATTER) / ProcessHeterogeneousVolumeTransmittance (:448-517, ratio tracking with
+// Russian roulette) share the walk over the majorant blocks
+template <bool SCATTER>
+static __device__ __noinline__ float vol_grid_walk(const DevVolume &v, const DevGrid &g, Rng &rng, float3 o, float3 d, float rayDepth, VolIsect is) {
+    const VolCtx c = vol_ctx(v, is);
+    VolBlock b = vol_block(v, o + d * (c.tEnter + c.epsilon), c);
+    float T = 1.0f, t = 0.0f;
+    for (int i = 0; i < (SCATTER ? 10000 : 1000); i++) {
+        const float3 cur = o + d * (c.tEnter + t + c.epsilon);
+        const VolIsect bi = vol_intersect(cur, d, b.minCorner, b.maxCorner);
+        const float maxDensity = vol_effective_density(v, __ldg(g.max_densities + b.blockIndex) * v.mn_density.w, rayDepth);
+        const float sampled = -logf(rng.next()) / maxDensity;
+        if (bi.Far <= 0.0f) {                                                                    // the ray misses the block (precision): creep forward
+            t += c.epsilon;
+            if (c.tEnter + t > c.tExit) return SCATTER ? -1.0f : T;
+            b = vol_block(v, o + d * (c.tEnter + t + c.epsilon), c);
+            continue;
+        }
+        const float toExit = bi.Far - fmaxf(bi.Near, 0.0f);
+        if (sampled > toExit) {                                                                  // next block
+            t += toExit + c.epsilon;
+            if (c.tEnter + t > c.tExit) return SCATTER ? -1.0f : T;
+            b = vol_block(v, o + d * (c.tEnter + t + c.epsilon), c);
+            continue;
+        }
+        t += sampled;
+        if (c.tEnter + t > c.tExit) return SCATTER ? -1.0f : T;
+        const float dens = vol_effective_density(v, grid_sample(v, g, rng, o + d * (c.tEnter + t)) * v.mn_density.w, rayDepth);
+        if (SCATTER) {
+            if (dens / maxDensity < rng.next()) continue;                                        // null collision
+            return c.tEnter + t;
+        } else {
+            T *= 1.0f - (dens / maxDensity);
+            const float p = T;
+            if (rng.next() > p) return 0.0f;
+            T /= p;
+        }
+    }
+    return SCATTER ? -1.0f : T;
+}
+// Volume::CalculateVolumesTransmittance, SH/Volume.slang:419-446, scenes WITHOUT heterogeneous volumes: analytic, no random numbers (shading kernels)
 static __device__ __noinline__ float volumes_transmittance(const DevScene &sc, float3 o, float3 d) {
     float T = 1.0f;
     for (uint32_t i = 0; i < sc.n_volumes; i++) {
@@ -123,20 +207,40 @@ static __device__ __noinline__ float volumes_transmittance(const DevScene &sc, f
     }
     return clampf(T, 0.0f, 1.0f);
 }
+// the same with heterogeneous volumes present (k_connect, after the visibility query, on the path's own stream): a ratio-tracking walk per grid volume crossed
+static __device__ __noinline__ float volumes_transmittance_walk(const DevScene &sc, Rng &rng, float3 o, float3 d, float rayDepth) {
+    float T = 1.0f;
+    for (uint32_t i = 0; i < sc.n_volumes; i++) {
+        const DevVolume &v = sc.volumes[i];
+        VolIsect is = vol_intersect(v, o, d);
+        is.Near = fmaxf(is.Near, 0.0f);
+        if (v.flags.w != 0xFFFFFFFFu && is.Far >= 0.0f) {
+            T *= vol_grid_walk<false>(v, sc.grids[v.flags.w], rng, o, d, rayDepth, is);
+            if (T <= 0.0f) return 0.0f;
+        } else {
+            const float len = is.Far - is.Near;
+            if (len > 0.0f) T *= expf(-v.mn_density.w * len);
+        }
+    }
+    return clampf(T, 0.0f, 1.0f);
+}
+// NEE terms of the shading kernels: with grid volumes in the scene the factor is applied by k_connect instead (volumes_transmittance_walk)
+__device__ __forceinline__ float volumes_transmittance_shade(const DevScene &sc, float3 o, float3 d) { return sc.n_grids ? 1.0f : volumes_transmittance(sc, o, d); }
 // Volume::DoesRayScatterInVolume, SH/Volume.slang:254-289 (homogeneous branch: one random number when the ray crosses the box)
-__device__ __forceinline__ float vol_scatter_distance(const DevVolume &v, float3 o, float3 d, Rng &rng, float ignoreIfFartherThan) {
+__device__ __forceinline__ float vol_scatter_distance(const DevScene &sc, const DevVolume &v, float3 o, float3 d, Rng &rng, float rayDepth, float ignoreIfFartherThan) {
     const VolIsect is = vol_intersect(v, o, d);
     if (is.Far < 0.0f) return -1.0f;
     if (ignoreIfFartherThan >= 0.0f && is.Near > ignoreIfFartherThan) return -1.0f;
     const float inside = is.Far - fmaxf(is.Near, 0.0f);
     if (inside <= 0.0f) return -1.0f;
+    if (v.flags.w != 0xFFFFFFFFu) return vol_grid_walk<true>(v, sc.grids[v.flags.w], rng, o, d, rayDepth, is);
     const float sampled = -logf(rng.next()) / v.mn_density.w;                                    // SH/Sampler.slang:425-428
     if (sampled < inside) return fmaxf(is.Near, 0.0f) + sampled;
     return -1.0f;
 }
-// The free-flight part of ScatteredInVolume (SH/RayGen.slang:164-209): volumes visited in order of their (clamped) entry distance.
-// Returns the scatter distance (< 0: none) and the index of the volume that scattered.
-__device__ __forceinline__ float volumes_free_flight(const DevScene &sc, float3 o, float3 d, Rng &rng, int &scattered) {
+// The free-flight part of ScatteredInVolume (SH/RayGen.slang:164-209): volumes visited in order of their (clamped) entry distance; rayDepth is
+// payload.Depth (:199), not VolumeDepth.  Returns the scatter distance (< 0: none) and the index of the volume that scattered.
+__device__ __forceinline__ float volumes_free_flight(const DevScene &sc, float3 o, float3 d, Rng &rng, float rayDepth, int &scattered) {
     float distances[MAX_VOLUMES]; int indices[MAX_VOLUMES];
     const int n = (int)min(sc.n_volumes, (uint32_t)MAX_VOLUMES);
     for (int i = 0; i < n; i++) { const VolIsect is = vol_intersect(sc.volumes[i], o, d); distances[i] = fmaxf(0.0f, is.Near); indices[i] = i; }
@@ -145,10 +249,27 @@ __device__ __forceinline__ float volumes_free_flight(const DevScene &sc, float3 
             if (distances[j] < distances[i]) { const float td = distances[i]; const int ti = indices[i]; distances[i] = distances[j]; indices[i] = indices[j]; distances[j] = td; indices[j] = ti; }
     float scatterDistance = -1.0f; scattered = -1;
     for (int i = 0; i < n; i++) {
-        const float t = vol_scatter_distance(sc.volumes[indices[i]], o, d, rng, scatterDistance);
+        const float t = vol_scatter_distance(sc, sc.volumes[indices[i]], o, d, rng, rayDepth, scatterDistance);
         if (t >= 0.0f && (t < scatterDistance || scatterDistance < 0.0f)) { scatterDistance = t; scattered = indices[i]; }
     }
     return scatterDistance;
+}
+// Blackbody, SH/RTCommon.slang:139-172
+__device__ __forceinline__ float3 blackbody(float temperature) {
+    const float temp = temperature / 100.0f;
+    float r, g, b;
+    if (temp <= 66.0f) r = 255.0f; else r = 329.698727446f * pt_pow(temp - 60.0f, -0.1332047592f);
+    if (temp <= 66.0f) g = 99.4708025861f * logf(temp) - 161.1195681661f; else g = 288.1221695283f * pt_pow(temp - 60.0f, -0.0755148492f);
+    if (temp >= 66.0f) b = 255.0f; else if (temp <= 19.0f) b = 0.0f; else b = 138.5177312231f * logf(temp - 10.0f) - 305.0447927307f;
+    return f3(clampf(r / 255.0f, 0.0f, 1.0f), clampf(g / 255.0f, 0.0f, 1.0f), clampf(b / 255.0f, 0.0f, 1.0f));
+}
+// Volume::GetEmissionFromTemperatureAtPoint, SH/Volume.slang:230-252 (the temperature is read from the DENSITY buffer, :235)
+static __device__ __noinline__ float3 vol_temperature_emission(const DevScene &sc, const DevVolume &v, Rng &rng, float3 x) {
+    if (v.flags.y == 0u) return f3(0.0f);
+    const float tn = grid_sample(v, sc.grids[v.flags.w], rng, x);
+    const float3 color = v.flags.z ? blackbody(tn * v.kelvin.y + v.kelvin.x) : f3(v.tcol_gamma);
+    const float intensity = pt_pow(tn, v.tcol_gamma.w) * v.tparams.x;
+    return f3(intensity * pt_pow(color.x, v.tparams.y), intensity * pt_pow(color.y, v.tparams.y), intensity * pt_pow(color.z, v.tparams.y));
 }
 
 } // namespace b200pt

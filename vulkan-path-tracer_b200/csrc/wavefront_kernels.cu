@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
                 // NEE term (added iff the shadow query allows) :326-372.  With the atmosphere on, the sky query is issued even when its term is zero:
                 // k_connect draws the transmittance walk whenever the sun is VISIBLE (SH/ClosestHit.slang:335-349 sits outside the pdf tests)
                 const bool contributes = need && e.PDF > 0.0f;
-                if (contributes || (k == 0 && cfg.EnableAtmosphere && cfg.EnableSkyMIS)) {
+                if (contributes || (k == 0 && (cfg.EnableAtmosphere || (VOL && sc.n_grids)) && cfg.EnableSkyMIS)) {   // grid volumes: same reason (:332-333)
                     const float3 c = contributes ? (((e.BxDF * 1.0f) * f3(lv)) / lv.w) * power_heuristic(lv.w, e.PDF) : f3(0.0f);
                     const float3 ro = (k == 0) ? sf.WorldPos + sf.Normal * 1e-5f : sf.WorldPos + toW * 1e-2f;   // :139, :171
                     if (FUSE) {
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
                 newO = no; newD = scatterW; b4 = make_float4(ss.BxDF.x, ss.BxDF.y, ss.BxDF.z, ss.PDF);
                 newDflags = newDepth | chanBits | (newInMedium ? 0x80000000u : 0u); shaded = true;
             } else {
-                if (VOL && reqMask) {                                           // volumes cast shadows on the NEE terms: transmittance from the NEW origin (:332-333, :364)
+                if (VOL && reqMask && !sc.n_grids) {                            // volumes cast shadows on the NEE terms: transmittance from the NEW origin (:332-333, :364); with grid volumes k_connect walks it
                     if (reqMask & 1u) { const float T = volumes_transmittance(sc, no, f3(so.sky_d[i])); const float4 c = so.sky_c[i]; so.sky_c[i] = make_float4(c.x * T, c.y * T, c.z * T, 0.0f); }
                     if (reqMask & 2u) { const float T = volumes_transmittance(sc, no, f3(so.lit_d[i])); const float4 c = so.lit_c[i]; so.lit_c[i] = make_float4(c.x * T, c.y * T, c.z * T, 0.0f); }
                 }
@@ -634,7 +634,9 @@ __global__ void __launch_bounds__(BIG ? 512 : 128, BIG ? 1 : (FUSE ? BOUNCE_MIN_
 // ------------------------------------------------------------------------------------------------
 // k_connect : shadow queries + SH/RayGen.slang:92-113 + stream compaction of the survivors (unfused pipeline; walks every hit queue)
 // ------------------------------------------------------------------------------------------------
-template <bool SMEM, bool TRACE>   // TRACE = false: k_shadow_dyn already cleared the request bits of occluded rays; only the join / roulette / compaction runs here
+// WALKS: the atmosphere is on or the scene has grid volumes -- NEE terms then carry random transmittance walks (atmosphere.cuh, volumes.cuh); compiled out of
+// the plain instantiations, whose register budget (64) they would double
+template <bool SMEM, bool TRACE, bool WALKS = false>   // TRACE = false: k_shadow_dyn already cleared the request bits of occluded rays; only the join / roulette / compaction runs here
 __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, PathState src, PathState dst, ShadeOut so,
                                                   uint32_t *__restrict__ ctrl, uint32_t parity, Queues q,
                                                   float4 *__restrict__ sample_buf, uint32_t *__restrict__ rng_carry,
@@ -668,8 +670,25 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
             float3 emitted = f3(e4);
             // Atmosphere: a visible sun costs the path a transmittance walk on its own RNG stream, BEFORE the roulette draw (SH/ClosestHit.slang:335-349,
             // SH/RayGen.slang:328-342,415-422) -- so the new origin and the RNG state are fetched up front instead of after the queries.
-            const bool atm = cfg.EnableAtmosphere != 0u;
-            if (atm) { o4 = src.org_pdf[i]; d4 = src.dir_rng[i]; rng.s = __float_as_uint(d4.w); }
+            // Grid volumes: the same for their ratio-tracking walks (SH/Volume.slang:448-517), sky then light; rayDepth is 0 after a surface hit (:333,:364),
+            // VolumeDepth / VolumeDepth + 1 after a volume event (SH/RayGen.slang:326,361; k_shade_volume has already counted the event), VolumeDepth after
+            // an atmosphere event, where the atmosphere walk comes FIRST (:415-421).
+            const bool atm = WALKS && cfg.EnableAtmosphere != 0u, het = WALKS && sc.n_grids != 0u, walks = atm || het;
+            float skyDepth = 0.0f, litDepth = 0.0f; bool atmEvent = false;
+            if (walks) { o4 = src.org_pdf[i]; d4 = src.dir_rng[i]; rng.s = __float_as_uint(d4.w); }
+            if (het && pending) {
+                const float4 h4 = so.hit[i];
+                if (__float_as_uint(h4.w) == VOLUME_EVENT) {
+                    const float vd = (float)src.vol_depth[i];
+                    if (__float_as_int(h4.y) >= 0) { skyDepth = vd - 1.0f; litDepth = vd; } else { skyDepth = vd; atmEvent = true; }
+                }
+            }
+            auto sky_term = [&](float3 c, float3 dir) {
+                if (atmEvent) { c = c * atm_transmittance_nee(cfg, rng, f3(o4), dir, channel); return c * volumes_transmittance_walk(sc, rng, f3(o4), dir, skyDepth); }
+                if (het) c = c * volumes_transmittance_walk(sc, rng, f3(o4), dir, skyDepth);
+                if (atm) c = c * atm_transmittance_nee(cfg, rng, f3(o4), dir, channel);
+                return c;
+            };
             // Request words are read when needed: the light request after the sky query, a contribution only if its ray came out
             // unoccluded, the path state after both queries -- little is live across the traversal loops.
             // (One resumable loop serving both rays of a lane, if-if style, was measured 1.6x SLOWER than two tight while-while loops.)
@@ -679,12 +698,12 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
             //         the closest-hit query) -- bounded by tL and free to stop at the first occluder.
             if (TRACE) n_shadow += (pending & 1u) + (pending >> 1);
             if (!TRACE) {                                                   // surviving bits = unoccluded requests, joined in the reference's order
-                if (pending & 1u) {
-                    float3 c = f3(so.sky_c[i]);
-                    if (atm) c = c * atm_transmittance_nee(cfg, rng, f3(o4), f3(so.sky_d[i]), channel);
+                if (pending & 1u) emitted = emitted + (walks ? sky_term(f3(so.sky_c[i]), f3(so.sky_d[i])) : f3(so.sky_c[i]));
+                if (pending & 2u) {
+                    float3 c = f3(so.lit_c[i]);
+                    if (het) c = c * volumes_transmittance_walk(sc, rng, f3(o4), f3(so.lit_d[i]), litDepth);
                     emitted = emitted + c;
                 }
-                if (pending & 2u) emitted = emitted + f3(so.lit_c[i]);
                 pending = 0u;
             }
             float4 so4 = make_float4(0, 0, 0, 0), sd4 = so4;
@@ -692,11 +711,7 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
             if (pending & 1u) {
                 HitRec h;
                 const bool occluded = bvh_trace<SMEM, true, false, false, true>(bv, f3(so4), f3(sd4), 0.0001f, 1000000.0f, h, stack, stride, max_stack);
-                if (!occluded) {
-                    float3 c = f3(so.sky_c[i]);
-                    if (atm) c = c * atm_transmittance_nee(cfg, rng, f3(o4), f3(sd4), channel);
-                    emitted = emitted + c;
-                }
+                if (!occluded) emitted = emitted + (walks ? sky_term(f3(so.sky_c[i]), f3(sd4)) : f3(so.sky_c[i]));
             }
             if (pending & 2u) {
                 const float4 lo4 = so.lit_o[i], ld4_ = so.lit_d[i];
@@ -707,12 +722,16 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
                 if (tri_test(f3(ta), f3(tb), f3(tc), f3(lo4), f3(ld4_), 0.0001f, 1000000.0f, tL, uL, vL)) {
                     HitRec h;
                     const bool occluded = bvh_trace<SMEM, true, false, true, true>(bv, f3(lo4), f3(ld4_), 0.0001f, tL, h, stack, stride, max_stack, nullptr, nullptr, lgid);
-                    if (!occluded) emitted = emitted + f3(so.lit_c[i]);
+                    if (!occluded) {
+                        float3 c = f3(so.lit_c[i]);
+                        if (het) c = c * volumes_transmittance_walk(sc, rng, f3(o4), f3(ld4_), litDepth);
+                        emitted = emitted + c;
+                    }
                 }
             }
             // the path state is fetched only now: nothing but the emission and the request bits is live across the traversal loop
             const float4 thr4 = src.thr_depth[i]; r4 = src.rad_slot[i];
-            if (!atm) { o4 = src.org_pdf[i]; d4 = src.dir_rng[i]; rng.s = __float_as_uint(d4.w); }
+            if (!walks) { o4 = src.org_pdf[i]; d4 = src.dir_rng[i]; rng.s = __float_as_uint(d4.w); }
             const float4 b4 = so.bxdf_pdf[i];
             alive = path_epilogue(cfg, emitted, b4, newDepth, channel, thr4, r4, rng, thr, rad, sample_buf, rng_carry);
         }
@@ -982,9 +1001,10 @@ __global__ void __launch_bounds__(256) k_volume_decide(DevScene sc, DevConfig cf
         const bool found = bvh_trace<SMEM, false>(bv, o, d, 0.00001f, 1000000.0f, h, stack, (int)blockDim.x, max_stack);
         const float distanceToGeometry = found ? h.t : -1.0f;
         int vi = -1;
-        float sd = volumes_free_flight(sc, o, d, rng, vi);                  // :164-209
+        const uint32_t dflags0 = __float_as_uint(ps.thr_depth[i].w);
+        float sd = volumes_free_flight(sc, o, d, rng, (float)(dflags0 & DEPTH_MASK), vi);   // :164-209 (heterogeneous volumes: payload.Depth scales the density, :199)
         if (cfg.EnableAtmosphere) {                                         // :212-236: channel pick (while unsplit), delta tracking on that channel
-            const uint32_t dflags = __float_as_uint(ps.thr_depth[i].w);
+            const uint32_t dflags = dflags0;
             int channel = dflags_channel(dflags);
             if (channel < 0) { const float pick = rng.next(); channel = pick < 0.33333f ? 0 : (pick < 0.66666f ? 1 : 2); }
             int component = -1;
@@ -1039,7 +1059,7 @@ __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg
                 else if (component == 1) { ph = phase_hg(dir, toSun, 0.85f); const float att = C_MIE_ABS / C_MIE; const float pn = phase_hg(dir, newDir, 0.85f); bx = f3(pn * (1.0f - att)); pdf = pn; }
                 else { bx = f3(0.0f); pdf = 1.0f; }
                 // the sun query is always issued: its transmittance walk is drawn whenever the sun is visible (:415-422); k_connect multiplies by it
-                const float Tv = volumes_transmittance(sc, origin, toSun);
+                const float Tv = volumes_transmittance_shade(sc, origin, toSun);
                 const float3 c = (f3(Tv) * ph) * col;
                 so.sky_o[i] = make_float4(origin.x, origin.y, origin.z, 1.0f);
                 so.sky_d[i] = make_float4(toSun.x, toSun.y, toSun.z, __uint_as_float(0xFFFFFFFFu));
@@ -1059,7 +1079,7 @@ __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg
         const DevVolume v = sc.volumes[code];
         const float3 color = f3(v.color_alpha);
         const int vdepth = (int)ps.vol_depth[i];
-        const float3 emitted = f3(v.emis_droplet);                          // :268 (no temperature grid)
+        const float3 emitted = f3(v.emis_droplet) + vol_temperature_emission(sc, v, rng, origin);   // :268
         float3 toSky = f3(0.0f), toLight = f3(0.0f); float4 sky = make_float4(0, 0, 0, 0), light = sky; uint32_t lgid = 0xFFFFFFFFu;
         if (cfg.EnableSkyMIS) {                                             // :273-287
             if (cfg.EnableAtmosphere) sample_sun_disk(cfg, rng, toSky, sky);
@@ -1074,8 +1094,8 @@ __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg
         // :319-369 are added by k_connect iff the query comes out clear (sky: any hit occludes; light: the sampled triangle must be the closest hit)
         if (cfg.EnableSkyMIS && sky.w > 0.0f) {
             const float ph = vol_phase(sc.phase_function, v, dir, toSky, vdepth);
-            if (ph > 0.0f || cfg.EnableAtmosphere) {                        // atmosphere: the query decides whether the transmittance walk is drawn (:328-342), even for a zero term
-                const float T = volumes_transmittance(sc, origin, toSky);
+            if (ph > 0.0f || cfg.EnableAtmosphere || sc.n_grids) {          // atmosphere / grid volumes: the query decides whether the transmittance walks are drawn (:326-342), even for a zero term
+                const float T = volumes_transmittance_shade(sc, origin, toSky);
                 const float3 c = ph > 0.0f ? ((f3(T) * (color * ph)) * (f3(sky) / sky.w)) * power_heuristic(sky.w, ph) : f3(0.0f);
                 so.sky_o[i] = make_float4(origin.x, origin.y, origin.z, 1.0f);
                 so.sky_d[i] = make_float4(toSky.x, toSky.y, toSky.z, __uint_as_float(0xFFFFFFFFu));
@@ -1085,9 +1105,9 @@ __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg
         }
         if (cfg.EnableMeshMIS && light.w > 0.0f) {
             const float ph = vol_phase(sc.phase_function, v, dir, toLight, vdepth);
-            if (ph > 0.0f) {
-                const float T = volumes_transmittance(sc, origin, toLight);
-                const float3 c = ((f3(T) * (color * ph)) * (f3(light) / light.w)) * power_heuristic(light.w, ph);
+            if (ph > 0.0f || sc.n_grids) {                                  // :361 sits outside the phase test
+                const float T = volumes_transmittance_shade(sc, origin, toLight);
+                const float3 c = ph > 0.0f ? ((f3(T) * (color * ph)) * (f3(light) / light.w)) * power_heuristic(light.w, ph) : f3(0.0f);
                 so.lit_o[i] = make_float4(origin.x, origin.y, origin.z, 1.0f);
                 so.lit_d[i] = make_float4(toLight.x, toLight.y, toLight.z, __uint_as_float(lgid));
                 so.lit_c[i] = make_float4(c.x, c.y, c.z, 0.0f);
@@ -1217,6 +1237,7 @@ static int set_attrs_for_current_device() {
     optin((const void *)k_extend<true, true>); optin((const void *)k_extend<true, false>);
     optin((const void *)k_extend<false, true>); optin((const void *)k_extend<false, false>);
     optin((const void *)k_connect<true, true>); optin((const void *)k_connect<false, true>); optin((const void *)k_connect<false, false>);
+    optin((const void *)k_connect<true, true, true>); optin((const void *)k_connect<false, true, true>); optin((const void *)k_connect<false, false, true>);
     optin((const void *)k_extend_dyn<true, true, false>); optin((const void *)k_extend_dyn<true, false, false>);
     optin((const void *)k_extend_dyn<false, true, false>); optin((const void *)k_extend_dyn<false, false, false>);
     optin((const void *)k_extend_dyn<false, true, true>); optin((const void *)k_extend_dyn<false, false, true>);
@@ -1389,17 +1410,21 @@ void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cf
                     uint32_t *ctrl, uint32_t parity, Queues q, float4 *sample_buf, uint32_t *rng_carry, WaveCounters *ctr, cudaStream_t st) {
     set_attrs_for_current_device();
     const bool smem = lc.bvh_in_smem;
+    const bool walks = cfg.EnableAtmosphere != 0u || sc.n_grids != 0u;      // k_connect<.., WALKS>
     if (lc.trav_dyn) {                                                      // shadow rays in their own dynamic-fetch kernel, then the join without tracing
         const size_t shd = trace_smem_bytes(sc, lc.dyn_stack + 1, 256, smem) + DYN_RING_BYTES_HOST + (size_t)lc.n_top4 * sizeof(Bvh4Node);
 #define B200PT_SH_DYN(S, W) k_shadow_dyn<S, W><<<lc.grid_shadow, 256, shd, st>>>(sc, so, ctrl, parity, q, lc.dyn_stack, lc.dyn_thresh, lc.n_top4, ctr)
         if (lc.wide) B200PT_SH_DYN(false, true); else if (smem) B200PT_SH_DYN(true, false); else B200PT_SH_DYN(false, false);
 #undef B200PT_SH_DYN
-        k_connect<false, false><<<lc.grid_connect, 256, 0, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
+        if (walks) k_connect<false, false, true><<<lc.grid_connect, 256, 0, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
+        else k_connect<false, false><<<lc.grid_connect, 256, 0, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
         return;
     }
     const size_t sh = trace_smem_bytes(sc, lc.max_stack, smem ? lc.extend_threads : 256, smem);
-    if (smem) k_connect<true, true><<<lc.grid_connect, lc.extend_threads, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
-    else k_connect<false, true><<<lc.grid_connect, 256, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr);
+#define B200PT_CONNECT(S, W, T) k_connect<S, true, W><<<lc.grid_connect, T, sh, st>>>(sc, cfg, src, dst, so, ctrl, parity, q, sample_buf, rng_carry, lc.max_stack, ctr)
+    if (smem) { if (walks) B200PT_CONNECT(true, true, lc.extend_threads); else B200PT_CONNECT(true, false, lc.extend_threads); }
+    else { if (walks) B200PT_CONNECT(false, true, 256); else B200PT_CONNECT(false, false, 256); }
+#undef B200PT_CONNECT
 }
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
                     const float4 *sample_buf, float4 *image, cudaStream_t st) {
