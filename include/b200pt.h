@@ -268,6 +268,11 @@ int32_t b200pt_save_png(b200pt_handle h, const char *path);
 /* ---- fine-grained hooks used by the parity tests (closest-hit semantics of RTCommon.slang:47-117) ---- */
 int32_t b200pt_trace_closest(b200pt_handle h, uint32_t n, const float *origins3, const float *directions3,
                              float tmin, float tmax, float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out2);
+/* the volume walks on given rays (parity hook; needs no scene): out_T[i] = Volume::CalculateVolumesTransmittance (SH/Volume.slang:419-446) from seeds[i],
+ * out_scatter[i] / out_volume[i] = the free-flight half of ScatteredInVolume (SH/RayGen.slang:164-209: distance or -1, index of the scattering volume
+ * or -1) from the same seed, out_rng[2*i] / [2*i+1] = the sampler state after each -- the number of random numbers a walk consumed must match too */
+int32_t b200pt_volume_walks(b200pt_handle h, uint32_t n, const float *origins3, const float *directions3, const uint32_t *seeds, float ray_depth,
+                            float *out_T, float *out_scatter, int32_t *out_volume, uint32_t *out_rng2);
 /* traversal cost of the same query: nodes_tris_out[2*i] = BVH nodes visited, [2*i+1] = triangles tested (measurement hook) */
 int32_t b200pt_trace_stats(b200pt_handle h, uint32_t n, const float *origins3, const float *directions3, float tmin, float tmax, uint32_t *nodes_tris_out);
 

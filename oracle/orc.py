@@ -263,6 +263,16 @@ def set_volumes(cfg, volumes):
     return cfg
 
 
+def volume_walks(cfg, org, dirs, seeds, ray_depth=0.0):
+    """orc_volume_walks: (T, scatter distance, scattering volume, sampler state after each walk [n, 2])"""
+    org = np.ascontiguousarray(org, np.float32); dirs = np.ascontiguousarray(dirs, np.float32); seeds = np.ascontiguousarray(seeds, np.uint32); n = len(org)
+    T = np.zeros(n, np.float32); sd = np.zeros(n, np.float32); vol = np.zeros(n, np.int32); rng = np.zeros((n, 2), np.uint32)
+    L = lib(); L.orc_volume_walks.restype = None
+    L.orc_volume_walks(C.byref(cfg), C.c_uint32(n), org.ctypes.data_as(C.c_void_p), dirs.ctypes.data_as(C.c_void_p), seeds.ctypes.data_as(C.c_void_p), C.c_float(ray_depth),
+                       T.ctypes.data_as(C.c_void_p), sd.ctypes.data_as(C.c_void_p), vol.ctypes.data_as(C.c_void_p), rng.ctypes.data_as(C.c_void_p))
+    return T, sd, vol, rng
+
+
 def default_config(**kw):
     c = OrcConfig()
     lib().orc_default_config(C.byref(c))

@@ -1873,6 +1873,29 @@ float orc_grid_transmittance(const OrcConfig *cfg, uint32_t seed, const float o[
     Rng r; r.seed = seed;
     return volumes_transmittance(cfg, &r, V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), rayDepth);
 }
+/* both volume walks on caller-supplied rays / seeds (the counterpart of b200pt_volume_walks) */
+void orc_volume_walks(const OrcConfig *cfg, uint32_t n, const float *org, const float *dir, const uint32_t *seeds, float rayDepth,
+                      float *T, float *scatter, int32_t *vol, uint32_t *rng2) {
+    for (uint32_t i = 0; i < n; i++) {
+        v3 o = V3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        Rng r; r.seed = seeds[i];
+        T[i] = volumes_transmittance(cfg, &r, o, d, rayDepth);
+        rng2[2 * i] = r.seed;
+        r.seed = seeds[i];
+        float distances[ORC_MAX_VOLUMES]; int indices[ORC_MAX_VOLUMES];             /* SH/RayGen.slang:164-209 */
+        const int nv = (int)(cfg->VolumesCount < ORC_MAX_VOLUMES ? cfg->VolumesCount : ORC_MAX_VOLUMES);
+        for (int k = 0; k < nv; k++) { VolIsect is = vol_intersect(o, d, cfg->Volumes[k].CornerMin, cfg->Volumes[k].CornerMax); distances[k] = fmaxf(0.0f, is.Near); indices[k] = k; }
+        for (int a = 0; a < nv; a++)
+            for (int b = a + 1; b < nv; b++)
+                if (distances[b] < distances[a]) { float td = distances[a]; int ti = indices[a]; distances[a] = distances[b]; indices[a] = indices[b]; distances[b] = td; indices[b] = ti; }
+        float sd = -1.0f; int sv = -1;
+        for (int k = 0; k < nv; k++) {
+            float t = vol_scatter_distance(cfg, &cfg->Volumes[indices[k]], o, d, &r, rayDepth, sd);
+            if (t >= 0.0f && (t < sd || sd < 0.0f)) { sd = t; sv = indices[k]; }
+        }
+        scatter[i] = sd; vol[i] = sv; rng2[2 * i + 1] = r.seed;
+    }
+}
 float orc_grid_sample(const OrcConfig *cfg, uint32_t volume, uint32_t seed, const float x[3]) {
     Rng r; r.seed = seed;
     const OrcVolume *v = &cfg->Volumes[volume];

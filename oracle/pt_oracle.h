@@ -123,6 +123,8 @@ void orc_prepare_density_grid(const int32_t indexMin[3], const uint32_t dim[3], 
                               float *maxDensities32, float cornerMin[3], float cornerMax[3], float *maxDensityInTheGrid);
 /* ---- KAT helpers ---- */
 float orc_grid_transmittance(const OrcConfig *cfg, uint32_t seed, const float o[3], const float d[3], float rayDepth);   /* CalculateVolumesTransmittance, one walk */
+void orc_volume_walks(const OrcConfig *cfg, uint32_t n, const float *org, const float *dir, const uint32_t *seeds, float rayDepth,
+                      float *T, float *scatter, int32_t *vol, uint32_t *rng2);                                          /* both walks on given rays / seeds */
 float orc_grid_sample(const OrcConfig *cfg, uint32_t volume, uint32_t seed, const float x[3]);                           /* SampleNanoVDBBuffer */
 void orc_blackbody(float kelvin, float out[3]);                                                                         /* SH/RTCommon.slang:139-172 */
 uint32_t orc_pcg_hash(uint32_t seed);                                  /* SH/Sampler.slang:4-9 */

@@ -497,6 +497,34 @@ def _het_cases():
             ("viking_room", 6, 0, {}, [dict(Position=(0.0, 0.0, 0.0), Scale=(1.6, 1.6, 1.6), Grid=cloud, Density=3.0, Color=(0.8, 0.85, 0.9), Anisotropy=-0.2)])]
 
 
+@pytest.mark.parametrize("case", range(3))
+def test_volume_walks_match_oracle(pt, case):
+    """The two random walks of a heterogeneous volume, alone: b200pt_volume_walks against orc_volume_walks on 40,000 random rays with given seeds --
+    CalculateVolumesTransmittance (SH/Volume.slang:419-517) and the free-flight half of ScatteredInVolume (SH/RayGen.slang:164-209, SH/Volume.slang:254-352).
+    Result AND sampler state afterwards must agree: the number of draws a walk consumes is decided, at the far side of the box, by a comparison of two
+    values that are equal in exact arithmetic, which is why volumes.cuh evaluates the volume geometry with individually rounded IEEE operations
+    (profiles/r02_het_walks.txt: 72 - 93 % of the states agreed before, > 99.99 % after)."""
+    from oracle import orc
+    name, depth, pf, kw, vols = _het_cases()[case]
+    cfg = util.oracle_config(name, Volumes=vols)
+    T = util.product_tracer(name, 32, 32, Volumes=vols)
+    rs = np.random.RandomState(50 + case)
+    n = 40000
+    gv = [v for v in vols if v.get("Grid") is not None][0]
+    lo = np.array(gv["Position"]) + np.array(gv["Grid"]["corner_min"]) * np.array(gv["Scale"]); hi = np.array(gv["Position"]) + np.array(gv["Grid"]["corner_max"]) * np.array(gv["Scale"])
+    u = rs.randn(n, 3); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    org = ((lo + hi) / 2 + u * np.linalg.norm(hi - lo) / 2 * rs.uniform(0.2, 1.6, (n, 1))).astype(np.float32)      # inside and outside the box
+    d = lo + rs.rand(n, 3) * (hi - lo) - org; d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    seeds = rs.randint(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    for ray_depth in (0.0, 3.0):
+        a = orc.volume_walks(cfg, org, d, seeds, ray_depth); b = T.volume_walks(org, d, seeds, ray_depth)
+        okT = np.abs(a[0] - b[0]) <= 1e-5; okS = (np.abs(a[1] - b[1]) <= 1e-5 * np.maximum(np.abs(a[1]), 1.0)) & (a[2] == b[2])
+        okR = a[3] == b[3]
+        print(f"walks case {case} depth {ray_depth}: T {okT.mean():.5f} scatter {okS.mean():.5f} states {okR[:, 0].mean():.5f} {okR[:, 1].mean():.5f}  mean T {a[0].mean():.4f} scattered {(a[1] >= 0).mean():.4f}")
+        assert okT.mean() > 0.9995 and okS.mean() > 0.9995 and okR.mean() > 0.999
+        assert 0.02 < a[0].mean() < 0.9 and (a[1] >= 0).mean() > 0.3                       # the rays do cross the medium
+
+
 @pytest.mark.parametrize("case", range(4))
 def test_heterogeneous_volumes_match_oracle(pt, case):
     """SURVEY 8f row 1, second half: density / temperature data through b200pt_add_density_grid_to_volume -- delta tracking against the 32^3 majorants

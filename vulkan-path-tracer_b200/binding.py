@@ -164,6 +164,7 @@ def lib():
             "b200pt_post_set_tonemap": [C.c_void_p, C.POINTER(Tonemap)], "b200pt_post_set_bloom": [C.c_void_p, C.POINTER(Bloom)],
             "b200pt_post_process": [C.c_void_p], "b200pt_get_ldr": [C.c_void_p, C.c_void_p, C.c_int32], "b200pt_get_bloom": [C.c_void_p, C.c_void_p],
             "b200pt_bloom_mip_sizes": [C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)], "b200pt_save_png": [C.c_void_p, C.c_char_p],
+            "b200pt_volume_walks": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
             "b200pt_trace_closest": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
             "b200pt_scene_stats": [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4,
             "b200pt_trace_stats": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p],
@@ -549,6 +550,13 @@ class PathTracer:
     def save_png(self, path): self._ck(self.L.b200pt_save_png(self.h, path.encode()))
 
     # ---- test hooks
+    def volume_walks(self, org, dirs, seeds, ray_depth=0.0):
+        """(T, scatter distance, scattering volume, sampler state after each walk [n, 2]) for every ray / seed"""
+        org = np.ascontiguousarray(org, np.float32); dirs = np.ascontiguousarray(dirs, np.float32); seeds = np.ascontiguousarray(seeds, np.uint32); n = len(org)
+        T = np.zeros(n, np.float32); sd = np.zeros(n, np.float32); vol = np.zeros(n, np.int32); rng = np.zeros((n, 2), np.uint32)
+        self._ck(self.L.b200pt_volume_walks(self.h, n, _p(org), _p(dirs), _p(seeds), C.c_float(ray_depth), _p(T), _p(sd), _p(vol), _p(rng)))
+        return T, sd, vol, rng
+
     def trace_closest(self, org, dirs, tmin, tmax):
         org = np.ascontiguousarray(org, np.float32); dirs = np.ascontiguousarray(dirs, np.float32); n = len(org)
         t = np.zeros(n, np.float32); prim = np.zeros(n, np.uint32); inst = np.zeros(n, np.uint32); uv = np.zeros((n, 2), np.float32)

@@ -217,6 +217,10 @@ int32_t b200pt_save_png(b200pt_handle h, const char *path) {     // Editor::Save
     });
 }
 
+int32_t b200pt_volume_walks(b200pt_handle h, uint32_t n, const float *o, const float *d, const uint32_t *seeds, float depth, float *T, float *sd, int32_t *vol, uint32_t *rng2) {
+    if (n && (!o || !d || !seeds || !T || !sd || !vol || !rng2)) return B200PT_ERR_WRONG_ARGUMENTS;
+    return guard(h, [&](Engine &e) { e.volume_walks(n, o, d, seeds, depth, T, sd, vol, rng2); });
+}
 int32_t b200pt_trace_closest(b200pt_handle h, uint32_t n, const float *o, const float *d, float tmin, float tmax, float *t, uint32_t *prim, uint32_t *inst, float *uv) {
     if (n && (!o || !d || !t || !prim || !inst || !uv)) return B200PT_ERR_WRONG_ARGUMENTS;
     return guard(h, [&](Engine &e) { e.trace_closest(n, o, d, tmin, tmax, t, prim, inst, uv); });

@@ -848,6 +848,22 @@ void Engine::get_bloom(float *dst) {
     CK(cudaStreamSynchronize(stream_));
 }
 
+void Engine::volume_walks(uint32_t n, const float *org, const float *dir, const uint32_t *seeds, float ray_depth, float *T, float *scatter, int32_t *vol, uint32_t *rng2) {
+    CK(cudaSetDevice(device_));
+    if (!n) return;
+    sync_all();
+    float *d_o = nullptr, *d_d = nullptr, *d_T = nullptr, *d_s = nullptr; uint32_t *d_seed = nullptr, *d_r = nullptr; int32_t *d_v = nullptr;
+    CK(cudaMalloc(&d_o, (size_t)n * 12)); CK(cudaMalloc(&d_d, (size_t)n * 12)); CK(cudaMalloc(&d_seed, (size_t)n * 4)); CK(cudaMalloc(&d_T, (size_t)n * 4));
+    CK(cudaMalloc(&d_s, (size_t)n * 4)); CK(cudaMalloc(&d_v, (size_t)n * 4)); CK(cudaMalloc(&d_r, (size_t)n * 8));
+    CK(cudaMemcpyAsync(d_o, org, (size_t)n * 12, cudaMemcpyHostToDevice, stream_)); CK(cudaMemcpyAsync(d_d, dir, (size_t)n * 12, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(d_seed, seeds, (size_t)n * 4, cudaMemcpyHostToDevice, stream_));
+    launch_volume_walks(ds_, n, d_o, d_d, d_seed, ray_depth, d_T, d_s, d_v, d_r, stream_);
+    CK(cudaMemcpyAsync(T, d_T, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_)); CK(cudaMemcpyAsync(scatter, d_s, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(vol, d_v, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_)); CK(cudaMemcpyAsync(rng2, d_r, (size_t)n * 8, cudaMemcpyDeviceToHost, stream_));
+    cudaError_t e = cudaStreamSynchronize(stream_);
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_seed); cudaFree(d_T); cudaFree(d_s); cudaFree(d_v); cudaFree(d_r);
+    CK(e); CK(cudaGetLastError());
+}
 void Engine::trace_closest(uint32_t n, const float *org, const float *dir, float tmin, float tmax, float *t, uint32_t *prim, uint32_t *inst, float *uv, uint32_t *stats) {
     CK(cudaSetDevice(device_));
     if (!has_scene_) throw CudaError{ B200PT_ERR_NO_SCENE, "no scene" };

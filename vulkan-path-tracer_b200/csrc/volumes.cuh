@@ -18,11 +18,24 @@ namespace b200pt {
 constexpr uint32_t VOLUME_EVENT = 0xFFFFFFFEu;      // so.hit[i].w of a path that scattered inside a volume this segment
 constexpr int MAX_VOLUMES = 100;                     // RayGen.slang:165-166 (float distances[100]; int indices[100]): the per-ray sort arrays live in local memory
 
+// The walks over the majorant blocks end on a comparison of two quantities that are EQUAL in exact arithmetic (the last block's far face reached by
+// stepping, against the box's far distance): how many random numbers a walk consumes there is decided by rounding.  So the geometry of the volume code is
+// evaluated with individually rounded IEEE operations (no fused multiply-add, no approximate division / reciprocal, whatever the build flags say),
+// which makes a collision-free walk take bit for bit the steps the oracle's takes (profiles/r02_het_walks.txt).
+__device__ __forceinline__ float ie_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float ie_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float ie_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float ie_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float3 ie_at(float3 o, float3 d, float s) { return f3(ie_add(o.x, ie_mul(d.x, s)), ie_add(o.y, ie_mul(d.y, s)), ie_add(o.z, ie_mul(d.z, s))); }   // o + d * s
+__device__ __forceinline__ float3 ie_rel(float3 p, float3 mn, float3 mx) {                        // (p - mn) / (mx - mn)
+    return f3(ie_div(ie_sub(p.x, mn.x), ie_sub(mx.x, mn.x)), ie_div(ie_sub(p.y, mn.y), ie_sub(mx.y, mn.y)), ie_div(ie_sub(p.z, mn.z), ie_sub(mx.z, mn.z)));
+}
 struct VolIsect { float Near, Far; };
 // SH/Volume.slang:188-211 (the x/y/z mix-up of the max / min chains is the reference's)
 __device__ __forceinline__ VolIsect vol_intersect(float3 o, float3 d, float3 mn, float3 mx) {
-    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    const float3 t0 = (mn - o) * inv, t1 = (mx - o) * inv;
+    const float3 inv = f3(ie_div(1.0f, d.x), ie_div(1.0f, d.y), ie_div(1.0f, d.z));
+    const float3 t0 = f3(ie_mul(ie_sub(mn.x, o.x), inv.x), ie_mul(ie_sub(mn.y, o.y), inv.y), ie_mul(ie_sub(mn.z, o.z), inv.z));
+    const float3 t1 = f3(ie_mul(ie_sub(mx.x, o.x), inv.x), ie_mul(ie_sub(mx.y, o.y), inv.y), ie_mul(ie_sub(mx.z, o.z), inv.z));
     const float3 ts = f3(fminf(t0.x, t1.x), fminf(t0.y, t1.y), fminf(t0.z, t1.z)), tb = f3(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y), fmaxf(t0.z, t1.z));
     const float tmin = fmaxf(fmaxf(ts.x, ts.y), fmaxf(ts.x, ts.z));
     const float tmax = fminf(fminf(tb.x, tb.y), fminf(tb.x, tb.z));
@@ -116,11 +129,10 @@ constexpr int GRID_DIM = 32;                                                    
 // SampleNanoVDBBuffer, SH/Volume.slang:69-117: box -> [0, 1]^3 (Y flipped) -> the grid's integer world box -> index space (float inverse map) -> floor,
 // three raw PCG draws jitter the voxel by -1 / 0 / +1, clamp to the root bbox, read, normalise
 static __device__ __noinline__ float grid_sample(const DevVolume &v, const DevGrid &g, Rng &rng, float3 x) {
-    const float3 mn = f3(v.mn_density), mx = f3(v.mx_g);
-    float3 np = f3((x.x - mn.x) / (mx.x - mn.x), (x.y - mn.y) / (mx.y - mn.y), (x.z - mn.z) / (mx.z - mn.z));
+    float3 np = ie_rel(x, f3(v.mn_density), f3(v.mx_g));
     np.y = 1.0f - np.y;
-    const float3 gp = f3(np.x * g.wext[0] + g.wmin[0], np.y * g.wext[1] + g.wmin[1], np.z * g.wext[2] + g.wmin[2]);
-    const float3 ip = f3((gp.x - g.trans[0]) * g.inv_vs[0], (gp.y - g.trans[1]) * g.inv_vs[1], (gp.z - g.trans[2]) * g.inv_vs[2]);
+    const float3 gp = f3(ie_add(ie_mul(np.x, g.wext[0]), g.wmin[0]), ie_add(ie_mul(np.y, g.wext[1]), g.wmin[1]), ie_add(ie_mul(np.z, g.wext[2]), g.wmin[2]));
+    const float3 ip = f3(ie_mul(ie_sub(gp.x, g.trans[0]), g.inv_vs[0]), ie_mul(ie_sub(gp.y, g.trans[1]), g.inv_vs[1]), ie_mul(ie_sub(gp.z, g.trans[2]), g.inv_vs[2]));
     int c[3] = { (int)floorf(ip.x), (int)floorf(ip.y), (int)floorf(ip.z) };
     c[0] = (int)((uint32_t)c[0] + (rng.next_u32() % 3u - 1u));
     c[1] = (int)((uint32_t)c[1] + (rng.next_u32() % 3u - 1u));
@@ -128,10 +140,10 @@ static __device__ __noinline__ float grid_sample(const DevVolume &v, const DevGr
 #pragma unroll
     for (int k = 0; k < 3; k++) c[k] = max(g.imin[k], min(g.imin[k] + g.dim[k] - 1, c[k]));
     const float value = __ldg(g.values + ((size_t)(c[2] - g.imin[2]) * g.dim[1] + (size_t)(c[1] - g.imin[1])) * g.dim[0] + (size_t)(c[0] - g.imin[0]));
-    return clampf(value / v.kelvin.z * v.tparams.w, 0.0f, 1.0f);
+    return clampf(ie_mul(ie_div(value, v.kelvin.z), v.tparams.w), 0.0f, 1.0f);
 }
 __device__ __forceinline__ float vol_effective_density(const DevVolume &v, float base, float rayDepth) {   // SH/Volume.slang:159-166
-    if (v.flags.x != 0u) return base * pt_pow(v.tparams.z, rayDepth);
+    if (v.flags.x != 0u) return ie_mul(base, pt_pow(v.tparams.z, rayDepth));
     return base;
 }
 struct VolCtx { float3 blockSize; float epsilon, tEnter, tExit; };
@@ -139,19 +151,19 @@ struct VolBlock { int blockIndex; float3 minCorner, maxCorner; };
 __device__ __forceinline__ VolCtx vol_ctx(const DevVolume &v, VolIsect is) {                     // CreateTraversalContext, :119-128
     VolCtx c;
     const float3 ext = f3(v.mx_g) - f3(v.mn_density);
-    c.blockSize = f3(ext.x / (float)GRID_DIM, ext.y / (float)GRID_DIM, ext.z / (float)GRID_DIM);
-    c.epsilon = 0.0001f * fmaxf(ext.x, fmaxf(ext.y, ext.z));
+    c.blockSize = f3(ie_div(ext.x, (float)GRID_DIM), ie_div(ext.y, (float)GRID_DIM), ie_div(ext.z, (float)GRID_DIM));
+    c.epsilon = ie_mul(0.0001f, fmaxf(ext.x, fmaxf(ext.y, ext.z)));
     c.tEnter = fmaxf(is.Near, 0.0f); c.tExit = is.Far;
     return c;
 }
 __device__ __forceinline__ VolBlock vol_block(const DevVolume &v, float3 p, const VolCtx &c) {  // CalculateBlockInfo, :131-147
-    const float3 mn = f3(v.mn_density), mx = f3(v.mx_g);
-    const float3 rel = f3((p.x - mn.x) / (mx.x - mn.x), (p.y - mn.y) / (mx.y - mn.y), (p.z - mn.z) / (mx.z - mn.z));
-    const int ix = max(0, min(GRID_DIM - 1, (int)(rel.x * (float)GRID_DIM))), iy = max(0, min(GRID_DIM - 1, (int)(rel.y * (float)GRID_DIM))),
-              iz = max(0, min(GRID_DIM - 1, (int)(rel.z * (float)GRID_DIM)));
+    const float3 mn = f3(v.mn_density);
+    const float3 rel = ie_rel(p, mn, f3(v.mx_g));
+    const int ix = max(0, min(GRID_DIM - 1, (int)ie_mul(rel.x, (float)GRID_DIM))), iy = max(0, min(GRID_DIM - 1, (int)ie_mul(rel.y, (float)GRID_DIM))),
+              iz = max(0, min(GRID_DIM - 1, (int)ie_mul(rel.z, (float)GRID_DIM)));
     VolBlock b;
     b.blockIndex = ix + iy * GRID_DIM + iz * GRID_DIM * GRID_DIM;
-    b.minCorner = f3(mn.x + c.blockSize.x * (float)ix, mn.y + c.blockSize.y * (float)iy, mn.z + c.blockSize.z * (float)iz);
+    b.minCorner = f3(ie_add(mn.x, ie_mul(c.blockSize.x, (float)ix)), ie_add(mn.y, ie_mul(c.blockSize.y, (float)iy)), ie_add(mn.z, ie_mul(c.blockSize.z, (float)iz)));
     b.maxCorner = b.minCorner + c.blockSize;
     return b;
 }
@@ -160,37 +172,37 @@ __device__ __forceinline__ VolBlock vol_block(const DevVolume &v, float3 p, cons
 template <bool SCATTER>
 static __device__ __noinline__ float vol_grid_walk(const DevVolume &v, const DevGrid &g, Rng &rng, float3 o, float3 d, float rayDepth, VolIsect is) {
     const VolCtx c = vol_ctx(v, is);
-    VolBlock b = vol_block(v, o + d * (c.tEnter + c.epsilon), c);
+    VolBlock b = vol_block(v, ie_at(o, d, c.tEnter + c.epsilon), c);
     float T = 1.0f, t = 0.0f;
     for (int i = 0; i < (SCATTER ? 10000 : 1000); i++) {
-        const float3 cur = o + d * (c.tEnter + t + c.epsilon);
+        const float3 cur = ie_at(o, d, c.tEnter + t + c.epsilon);
         const VolIsect bi = vol_intersect(cur, d, b.minCorner, b.maxCorner);
-        const float maxDensity = vol_effective_density(v, __ldg(g.max_densities + b.blockIndex) * v.mn_density.w, rayDepth);
-        const float sampled = -logf(rng.next()) / maxDensity;
+        const float maxDensity = vol_effective_density(v, ie_mul(__ldg(g.max_densities + b.blockIndex), v.mn_density.w), rayDepth);
+        const float sampled = ie_div(-logf(rng.next()), maxDensity);
         if (bi.Far <= 0.0f) {                                                                    // the ray misses the block (precision): creep forward
             t += c.epsilon;
             if (c.tEnter + t > c.tExit) return SCATTER ? -1.0f : T;
-            b = vol_block(v, o + d * (c.tEnter + t + c.epsilon), c);
+            b = vol_block(v, ie_at(o, d, c.tEnter + t + c.epsilon), c);
             continue;
         }
         const float toExit = bi.Far - fmaxf(bi.Near, 0.0f);
         if (sampled > toExit) {                                                                  // next block
             t += toExit + c.epsilon;
             if (c.tEnter + t > c.tExit) return SCATTER ? -1.0f : T;
-            b = vol_block(v, o + d * (c.tEnter + t + c.epsilon), c);
+            b = vol_block(v, ie_at(o, d, c.tEnter + t + c.epsilon), c);
             continue;
         }
         t += sampled;
         if (c.tEnter + t > c.tExit) return SCATTER ? -1.0f : T;
-        const float dens = vol_effective_density(v, grid_sample(v, g, rng, o + d * (c.tEnter + t)) * v.mn_density.w, rayDepth);
+        const float dens = vol_effective_density(v, ie_mul(grid_sample(v, g, rng, ie_at(o, d, c.tEnter + t)), v.mn_density.w), rayDepth);
         if (SCATTER) {
-            if (dens / maxDensity < rng.next()) continue;                                        // null collision
+            if (ie_div(dens, maxDensity) < rng.next()) continue;                                 // null collision
             return c.tEnter + t;
         } else {
-            T *= 1.0f - (dens / maxDensity);
+            T = ie_mul(T, 1.0f - ie_div(dens, maxDensity));
             const float p = T;
             if (rng.next() > p) return 0.0f;
-            T /= p;
+            T = ie_div(T, p);
         }
     }
     return SCATTER ? -1.0f : T;
@@ -234,7 +246,7 @@ __device__ __forceinline__ float vol_scatter_distance(const DevScene &sc, const 
     const float inside = is.Far - fmaxf(is.Near, 0.0f);
     if (inside <= 0.0f) return -1.0f;
     if (v.flags.w != 0xFFFFFFFFu) return vol_grid_walk<true>(v, sc.grids[v.flags.w], rng, o, d, rayDepth, is);
-    const float sampled = -logf(rng.next()) / v.mn_density.w;                                    // SH/Sampler.slang:425-428
+    const float sampled = ie_div(-logf(rng.next()), v.mn_density.w);                             // SH/Sampler.slang:425-428
     if (sampled < inside) return fmaxf(is.Near, 0.0f) + sampled;
     return -1.0f;
 }

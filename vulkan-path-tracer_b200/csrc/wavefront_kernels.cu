@@ -1125,6 +1125,21 @@ __global__ void __launch_bounds__(128) k_shade_volume(DevScene sc, DevConfig cfg
     if ((threadIdx.x & 31) == 0 && n_ev) atomicAdd(&ctr->medium_events, (unsigned long long)n_ev);
 }
 
+// parity hook (b200pt_volume_walks): the two volume walks on caller-supplied rays and seeds
+__global__ void __launch_bounds__(128) k_volume_walks(DevScene sc, uint32_t n, const float *__restrict__ org, const float *__restrict__ dir, const uint32_t *__restrict__ seeds,
+                                                      float ray_depth, float *__restrict__ T_out, float *__restrict__ scatter_out, int32_t *__restrict__ vol_out, uint32_t *__restrict__ rng_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    Rng r; r.s = seeds[i];
+    T_out[i] = sc.n_grids ? volumes_transmittance_walk(sc, r, o, d, ray_depth) : volumes_transmittance(sc, o, d);
+    rng_out[2 * i] = r.s;
+    r.s = seeds[i];
+    int vi = -1;
+    scatter_out[i] = volumes_free_flight(sc, o, d, r, ray_depth, vi);
+    vol_out[i] = vi; rng_out[2 * i + 1] = r.s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_prepare_materials : per-material constants of materials whose textures are all 1x1 (DevMaterial::pre0..pre3)
 // ------------------------------------------------------------------------------------------------
@@ -1429,6 +1444,10 @@ void launch_connect(const LaunchCfg &lc, const DevScene &sc, const DevConfig &cf
 void launch_resolve(const LaunchCfg &lc, const DevConfig &cfg, const DevDispatch *disp, uint32_t n_disp, uint32_t P,
                     const float4 *sample_buf, float4 *image, cudaStream_t st) {
     k_resolve<<<lc.grid_light, 256, 0, st>>>(cfg, disp, n_disp, P, sample_buf, image);
+}
+void launch_volume_walks(const DevScene &sc, uint32_t n, const float *org, const float *dir, const uint32_t *seeds, float ray_depth,
+                         float *T_out, float *scatter_out, int32_t *vol_out, uint32_t *rng_out, cudaStream_t st) {
+    k_volume_walks<<<(n + 127u) / 128u, 128, 0, st>>>(sc, n, org, dir, seeds, ray_depth, T_out, scatter_out, vol_out, rng_out);
 }
 void launch_trace_rays(const LaunchCfg &lc, const DevScene &sc, uint32_t n, const float *org, const float *dir, float tmin, float tmax,
                        float *t_out, uint32_t *prim_out, uint32_t *inst_out, float *uv_out, uint32_t *stats, cudaStream_t st) {
