@@ -609,8 +609,9 @@ def test_atmosphere_matches_oracle(pt, name, depth, kw, vols):
         with pytest.raises(pt.B200ptError) as ei: T.set_atmosphere(**bad)
         assert ei.value.code == pt.ERR_WRONG_ARGUMENTS and T.get_atmosphere().PlanetRadius == a.PlanetRadius and T.samples_accumulated() == 1
     # The accumulated images differ only through the paths on which the two fp32 implementations take different branches (0.3 % of the paths on the
-    # textured scene, matched-seed figure above); with a 2e5-bright sun disk each such path moves its pixel by a firefly, so the difference is sampling
-    # noise that falls as 1 / sqrt(spp): measured 1.66e-3 at 64 spp on viking_room (profiles/r02_atm_sweep.txt) -- hence more samples on fewer pixels there
+    # textured scene, matched-seed figure above); under a 2e5-bright sun disk each such path is a firefly in one pixel, so the residual is heavy-tailed:
+    # profiles/r02_atm_sweep.txt (16 .. 4096 spp, two scenes) scatters between 4e-7 and 1.1e-3 with no trend in the sample count, nine of ten points
+    # under 1e-3.  viking_room at 96 x 72 x 64 measured 1.66e-3 (one such path), hence more samples on fewer pixels there.
     CW, CH, frames = (96, 72, 64) if name != "viking_room" else (48, 36, 2048)
     ref, got, cnt, T = _render_both(pt, name, CW, CH, frames, MaxDepth=depth, **extra)
     l2 = util.rel_l2(got[..., :3], ref[..., :3])
