@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-2 call 16 (1 GPU): k_shade_hit occupancy variants (SHADE_MIN_BLOCKS 4 / 5 / 6 / 8 -> 128 / 96 / 80 / 64 registers) on Cornell and glass
+set -u; mkdir -p gpurun_out
+b() { local name=$1 lib=$2; shift 2; B200PT_LIB=$PWD/vulkan-path-tracer_b200/$lib timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline "$@" 2> gpurun_out/c16_${name}.err | tail -1 > gpurun_out/c16_${name}.json; }
+for v in "" _s4 _s6 _s8; do
+  b cornell$v libb200pt$v.so --workload cornell_1080p_d8
+  b glass$v libb200pt$v.so --workload glass_1080sq_d16
+done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/c16_*.json")):
+    try:
+        r = json.loads(open(f).read()); k = r["roofline"]["kernel_ms_per_step"]
+        print(f, "%.1f Mpaths/s  %.2f ms/step  ext %.2f shade %.2f conn %.2f" % (r["value"], r["ms_per_step"], k["extend"], k["shade"], k["connect"]))
+    except Exception as e: print(f, "unreadable", e, open(f.replace(".json", ".err")).read()[-600:])
+PY
