@@ -654,6 +654,14 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t n_shadow = 0;
     const uint32_t n_round = (n + 31u) & ~31u;                              // keep warps converged for the ballots
+#ifdef B200PT_CONNECT_PREFETCH
+    // The queue entry of this thread's NEXT path is fetched one iteration ahead and its request header pulled towards L2; the words of the CURRENT path that
+    // are only read after the shadow queries (state, contributions) are pulled towards L2 before the traversals start.
+    const uint32_t jstep = gridDim.x * blockDim.x;
+    uint32_t i_nx = 0;
+    { const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x; if (j0 < n) i_nx = hit_entry(q, span, j0); }
+#define B200PT_PF(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#endif
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
         const bool active = j < n;
         bool alive = false;
@@ -661,8 +669,17 @@ __global__ void __launch_bounds__(512) k_connect(DevScene sc, DevConfig cfg, Pat
         float3 thr = f3(0.0f), rad = f3(0.0f);
         uint32_t i = 0;
         if (active) {
+#ifdef B200PT_CONNECT_PREFETCH
+            i = i_nx;
+            const float4 e4 = so.e0[i];
+            if (j + jstep < n) { i_nx = hit_entry(q, span, j + jstep); B200PT_PF(so.e0 + i_nx); }
+            B200PT_PF(src.thr_depth + i); B200PT_PF(src.rad_slot + i); B200PT_PF(src.org_pdf + i); B200PT_PF(src.dir_rng + i); B200PT_PF(so.bxdf_pdf + i);
+            if (__float_as_uint(e4.w) & (1u << 29)) { B200PT_PF(so.sky_c + i); }
+            if (__float_as_uint(e4.w) & (1u << 30)) { B200PT_PF(so.lit_o + i); B200PT_PF(so.lit_d + i); B200PT_PF(so.lit_c + i); }
+#else
             i = hit_entry(q, span, j);
             const float4 e4 = so.e0[i];
+#endif
             uint32_t pending = (__float_as_uint(e4.w) >> 29) & 3u;         // bit 0: sky request, bit 1: light request (k_shade_hit)
             newDflags = __float_as_uint(e4.w) & 0x9FFFFFFFu;
             const uint32_t newDepth = newDflags & DEPTH_MASK;
