@@ -29,7 +29,7 @@ extern "C" {
 #define B200PT_ERR_INIT_FAILED       -3      /* VK_ERROR_INITIALIZATION_FAILED: file/scene import failed */
 #define B200PT_ERR_OUT_OF_MEMORY     -2
 #define B200PT_ERR_WRONG_ARGUMENTS   -15000  /* custom range of Error.h */
-#define B200PT_ERR_NOT_IMPLEMENTED   -15001  /* NanoVDB volume data / atmosphere API */
+#define B200PT_ERR_NOT_IMPLEMENTED   -15001  /* reading .vdb files (needs OpenVDB): b200pt_add_density_data_to_volume */
 #define B200PT_ERR_NO_SCENE          -15002
 #define B200PT_ERR_CUDA              -15003
 #define B200PT_ERR_NO_DEVICE         -15004  /* no CUDA device: the product has no CPU fallback */
