@@ -3,7 +3,7 @@
  *
  * A plain-C restatement of the Monte-Carlo estimator of Zydak/Vulkan-Path-Tracer
  * (reference paths relative to /root/reference):
- *   PathTracer/Shaders/{Defines,Sampler,RTCommon,Surface,Material,ClosestHit,Miss,RayGen}.slang
+ *   PathTracer/Shaders/{Defines,Sampler,RTCommon,Surface,Material,ClosestHit,Miss,RayGen,Volume,Atmosphere}.slang
  *   PathTracer/Shaders/PostProcess/{BloomDownSample,BloomUpSample,Tonemap}.slang
  *   PathTracer/PathTracer.cpp:122-156 (dispatch bookkeeping), :1137-1332 (env alias table)
  *   PathTracer/PostProcessor.cpp:128-246, PathTracer/FlyCamera.cpp:84-140
@@ -20,6 +20,9 @@
  *       baker (orc_bake_*_texel) reproduces them within Monte-Carlo noise (tests/test_oracle_kat.py);
  *   (b) analytic known-answer tests derived from the reference source (furnace mode, PCG sequences,
  *       Fresnel/ACES fixed points, bloom mip sizes, alias-table invariants, LUT ranges, fixture facts).
+ * The volume and atmosphere restatements (Volume.slang, Atmosphere.slang, RayGen.slang:162-471, PathTracer.cpp:1346-1528) are pinned by (b) only:
+ * the reference ships no .vdb asset and no render with known settings, and the NanoVDB / OpenVDB reads are restated from those libraries'
+ * published behaviour (OpenVDB 12.0.1 is absent from the reference tree) -- "parity unpinned" against reference-produced data for that part.
  */
 #ifndef PT_ORACLE_H
 #define PT_ORACLE_H
