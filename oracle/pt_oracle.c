@@ -1901,4 +1901,17 @@ float orc_grid_sample(const OrcConfig *cfg, uint32_t volume, uint32_t seed, cons
     const OrcVolume *v = &cfg->Volumes[volume];
     return grid_sample(v, &cfg->Grids[v->DensityDataIndex], &r, V3(x[0], x[1], x[2]));
 }
+/* atmosphere KAT hooks: one ratio-tracked transmittance walk, one Rayleigh-phase sample, one sun-disk sample */
+float orc_atm_transmittance(const OrcConfig *cfg, uint32_t seed, const float o[3], const float d[3], int channel) {
+    Rng r; r.seed = seed;
+    v3 T = atm_transmittance(cfg, &r, V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), channel);
+    return channel == 0 ? T.x : (channel == 1 ? T.y : T.z);
+}
+void orc_atm_samples(const OrcConfig *cfg, uint32_t seed, const float incident[3], float rayleigh_dir[3], float sun_dir[3], float sun_color_pdf[4]) {
+    Rng r; r.seed = seed;
+    v3 a = rng_rayleigh(&r, V3(incident[0], incident[1], incident[2]));
+    rayleigh_dir[0] = a.x; rayleigh_dir[1] = a.y; rayleigh_dir[2] = a.z;
+    v3 s; v4 cp; sample_sun_disk(cfg, &r, &s, &cp);
+    sun_dir[0] = s.x; sun_dir[1] = s.y; sun_dir[2] = s.z; sun_color_pdf[0] = cp.x; sun_color_pdf[1] = cp.y; sun_color_pdf[2] = cp.z; sun_color_pdf[3] = cp.w;
+}
 void orc_blackbody(float kelvin, float out[3]) { v3 c = blackbody(kelvin); out[0] = c.x; out[1] = c.y; out[2] = c.z; }

@@ -129,7 +129,9 @@ float orc_grid_transmittance(const OrcConfig *cfg, uint32_t seed, const float o[
 void orc_volume_walks(const OrcConfig *cfg, uint32_t n, const float *org, const float *dir, const uint32_t *seeds, float rayDepth,
                       float *T, float *scatter, int32_t *vol, uint32_t *rng2);                                          /* both walks on given rays / seeds */
 float orc_grid_sample(const OrcConfig *cfg, uint32_t volume, uint32_t seed, const float x[3]);                           /* SampleNanoVDBBuffer */
-void orc_blackbody(float kelvin, float out[3]);                                                                         /* SH/RTCommon.slang:139-172 */
+void orc_blackbody(float kelvin, float out[3]);
+float orc_atm_transmittance(const OrcConfig *cfg, uint32_t seed, const float o[3], const float d[3], int channel);      /* CalculateTransmittanceThroughAtmosphere, one walk */
+void orc_atm_samples(const OrcConfig *cfg, uint32_t seed, const float incident[3], float rayleigh_dir[3], float sun_dir[3], float sun_color_pdf[4]);   /* SampleRayleigh, SampleSunDisk */                                                                         /* SH/RTCommon.slang:139-172 */
 uint32_t orc_pcg_hash(uint32_t seed);                                  /* SH/Sampler.slang:4-9 */
 void     orc_rng_floats(uint32_t seed, uint32_t n, float *out);        /* SH/Sampler.slang:38-43 */
 float    orc_dielectric_fresnel(float cosI, float eta);                /* SH/Material.slang:434-449 */
