@@ -320,6 +320,15 @@ def test_cli_renderer_equals_the_api_and_resumes(pt, tmp_path):
     r2 = subprocess.run([exe, *common, "--spp", "6", "--resume", ck, "--out", str(tmp_path / "b6.png")], capture_output=True, text=True)
     assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr, r2.stderr)
     assert np.array_equal(pt.decode_image(str(tmp_path / "b6.png")), a)
+    # --atmosphere / --sky / --sun-color: the editor's atmosphere toggle and sky rotation through the same calls
+    ra = subprocess.run([exe, *common, "--spp", "4", "--atmosphere", "--sky", "30", "-40", "--sun-color", "1", "0.8", "0.6", "--out", str(tmp_path / "atm.png")], capture_output=True, text=True)
+    assert ra.returncode == 0, ra.stderr
+    cfg = T.get_config(); cfg.MaxSamplesAccumulated = 4; cfg.SkyRotationAzimuth = 30.0; cfg.SkyRotationAltitude = -40.0; T.set_config(cfg)
+    T.set_atmosphere(Enable=1, SunColor=(1.0, 0.8, 0.6))
+    T.path_trace(4, 5); assert T.samples_accumulated() == 4
+    T.post_process()
+    atm = pt.decode_image(str(tmp_path / "atm.png"))
+    assert np.array_equal(T.get_ldr(), atm) and not np.array_equal(atm, a)
     # errors surface as non-zero exit codes with the library's message
     r3 = subprocess.run([exe, "--scene", str(tmp_path / "missing.gltf"), "--env", hdr, "--luts", lut_dir, "--out", str(tmp_path / "c.png")], capture_output=True, text=True)
     assert r3.returncode != 0 and "failed" in r3.stderr

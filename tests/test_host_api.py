@@ -552,7 +552,7 @@ def test_cli_renderer_builds_and_fails_loudly_without_a_gpu():
     exe = os.path.join(os.path.dirname(pt.LIB_PATH), "b200pt_render")
     assert os.path.exists(exe)
     r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 2 and "usage: b200pt_render" in r.stderr
+    assert r.returncode == 2 and "usage: b200pt_render" in r.stderr and "--atmosphere" in r.stderr and "--volume" in r.stderr
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "--scene", "s.gltf", "--env", "e.hdr", "--luts", "d", "--out", "o.png"], capture_output=True, text=True)
         assert r.returncode != 0 and "no CUDA device" in r.stderr

@@ -32,6 +32,8 @@ static void usage() {
         "  --exposure E --gamma G --bloom THRESHOLD STRENGTH MIPS FALLOFF      post chain (reference defaults)\n"
         "  --volume x0 y0 z0 x1 y1 z1 density r g b   add a homogeneous AABB volume (repeatable); --volume-g G sets the anisotropy of the last one\n"
         "  --phase 0|1|2     phase function: Henyey-Greenstein, Draine, HG + Draine\n"
+        "  --sky AZ ALT      sky / sun rotation in degrees (SetSkyAzimuth / SetSkyAltitude, Editor.cpp sky panel)\n"
+        "  --atmosphere      render with the atmosphere (SetEnableAtmosphere(true): sun-disk NEE, Rayleigh / Mie / ozone scattering); --sun-color r g b\n"
         "  --checkpoint FILE save the accumulation when done         --resume FILE  continue from a checkpoint\n"
         "  --preview-every K rewrite the output PNG after every K PathTrace calls (the editor's progressive view, Editor.cpp:83-121)\n"
         "  --bake-luts N     bake missing lookup tables into DIR with N samples per texel first (Application.cpp:35-72)\n"
@@ -41,7 +43,7 @@ static void usage() {
 int main(int argc, char **argv) {
     std::string scene, env, luts, out, ckpt_out, ckpt_in;
     uint32_t W = 0, H = 0, spp = 64, depth = 200, seed = 0x1234ABCDu, chunks = 1, batch = 8, bake = 0, phase = 0, preview = 0;
-    int device = 0; bool quiet = false;
+    int device = 0; bool quiet = false, atmosphere = false, sky = false; float sky_az = 0.0f, sky_al = 0.0f, sun[3] = { 1.0f, 1.0f, 1.0f };
     b200pt_tonemap tm{ 1.0f, 2.2f }; b200pt_bloom bl{ 2.0f, 1.0f, 10, 5.0f };
     std::vector<b200pt_volume> vols;
     for (int i = 1; i < argc; i++) {
@@ -65,6 +67,9 @@ int main(int argc, char **argv) {
         }
         else if (a == "--volume-g") { need(1); if (vols.empty()) { usage(); return 2; } vols.back().Anisotropy = (float)atof(argv[++i]); }
         else if (a == "--phase") { need(1); phase = (uint32_t)atoi(argv[++i]); }
+        else if (a == "--sky") { need(2); sky = true; sky_az = (float)atof(argv[++i]); sky_al = (float)atof(argv[++i]); }
+        else if (a == "--atmosphere") atmosphere = true;
+        else if (a == "--sun-color") { need(3); for (int k = 0; k < 3; k++) sun[k] = (float)atof(argv[++i]); }
         else if (a == "--preview-every") { need(1); preview = (uint32_t)atoi(argv[++i]); }
         else if (a == "--checkpoint") { need(1); ckpt_out = argv[++i]; } else if (a == "--resume") { need(1); ckpt_in = argv[++i]; }
         else if (a == "--bake-luts") { need(1); bake = (uint32_t)atoi(argv[++i]); } else if (a == "--device") { need(1); device = atoi(argv[++i]); }
@@ -83,7 +88,13 @@ int main(int argc, char **argv) {
     CALL(b200pt_get_size(h, &W, &H));
     b200pt_config cfg; CALL(b200pt_get_config(h, &cfg));
     cfg.MaxDepth = depth; cfg.ScreenChunkCount = chunks; cfg.MaxSamplesAccumulated = spp;
+    if (sky) { cfg.SkyRotationAzimuth = sky_az; cfg.SkyRotationAltitude = sky_al; }
     CALL(b200pt_set_config(h, &cfg));
+    if (atmosphere) {
+        b200pt_atmosphere atm; CALL(b200pt_get_atmosphere(h, &atm));
+        atm.Enable = 1; for (int k = 0; k < 3; k++) atm.SunColor[k] = sun[k];
+        CALL(b200pt_set_atmosphere(h, &atm));
+    }
     for (const auto &v : vols) CALL(b200pt_add_volume(h, &v));
     if (!vols.empty() || phase) CALL(b200pt_set_phase_function(h, phase));
     if (!ckpt_in.empty()) CALL(b200pt_load_checkpoint(h, ckpt_in.c_str()));
