@@ -545,6 +545,36 @@ def test_density_grid_preparation_equals_the_oracle():
     assert L.b200pt_prepare_density_grid(C.byref(g), *args) == B.ERR_WRONG_ARGUMENTS
 
 
+def test_density_grid_preparation_property():
+    """Property form of the test above (hypothesis): any bbox shape, origin, temperature presence and explicit temperature range -- the product's host half and
+    the oracle's restatement of PathTracer.cpp:1391-1452 agree bit for bit, every majorant dominates the normalised values gathered into its cell, and
+    cells no voxel maps to stay 0."""
+    from hypothesis import given, settings, strategies as st
+    from vpt_b200 import binding as B
+    from oracle import orc
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.tuples(st.integers(1, 40), st.integers(1, 40), st.integers(1, 40)), st.tuples(st.integers(-60, 60), st.integers(-60, 60), st.integers(-60, 60)),
+           st.booleans(), st.integers(0, 2 ** 31 - 1))
+    def run(shape, imin, with_t, seed):
+        rs = np.random.RandomState(seed)
+        d = (rs.rand(*shape).astype(np.float32) * 3.0 + 0.01) * (rs.rand(*shape) > 0.3)
+        d.flat[rs.randint(d.size)] = 3.5                                              # at least one positive value
+        t = (rs.rand(*shape).astype(np.float32) * 1000.0) if with_t else None
+        tr = (50.0, 800.0) if with_t and seed % 2 else None                          # explicit range of the temperature tree's active values, or derived from the array
+        g = orc.prepare_density_grid(d, index_min=imin, temperature=t, temperature_range=tr)
+        vals, maj, cmin, cmax, mx = B.prepare_density_grid(d, index_min=imin, temperature=t, temperature_range=tr)
+        # (a bbox whose every index coordinate is 0 scales by 0 / 0: NaN corners in the reference, PathTracer.cpp:1415-1420, and in both restatements)
+        assert mx == g["max_density"] and np.array_equal(np.array(cmin + cmax, np.float32).view(np.uint32), np.array(g["corner_min"] + g["corner_max"], np.float32).view(np.uint32))
+        assert np.array_equal(vals.view(np.uint32), g["values"].view(np.uint32)) and np.array_equal(maj.view(np.uint32), g["max_densities"].view(np.uint32))
+        nz, ny, nx = shape
+        zz, yy, xx = np.mgrid[0:nz, 0:ny, 0:nx]
+        cell = (xx * 32) // nx + (((ny - 1 - yy) * 32) // ny) * 32 + ((zz * 32) // nz) * 1024        # array row yy is the loop's y = ny - 1 - yy
+        want = np.zeros(32768, np.float32); np.maximum.at(want, cell.ravel(), np.clip(d / np.float32(mx), 0.0, 1.0).astype(np.float32).ravel())
+        assert np.array_equal(maj, want)
+    run()
+
+
 def test_cli_renderer_builds_and_fails_loudly_without_a_gpu():
     """b200pt_render (csrc/cli_main.cpp), the headless stand-in for the reference's Editor: built next to the library, prints its usage,
     and -- like every product path -- refuses to run without a CUDA device instead of falling back to anything."""
